@@ -1,0 +1,184 @@
+"""NumPy float64 restatement of the parameter producer that feeds the hot path
+(tsadar/core/modules/ts_params.py and distribution_functions/base.py).  TEST INFRASTRUCTURE ONLY.
+
+The reference keeps this stage in JAX (out of scope for the kernels) but its
+exact arithmetic decides the *inputs* of the golden vector, so the oracle mirrors it.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import gammaincc, gamma
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def act_pair(param_cfg, activate):
+    """get_act_and_inv_act (ts_params.py:329-350).  NB the 'inverse' is not the logit:
+    stored = log(0.01 + x/(1-x+0.01)) so sigmoid(stored) != x."""
+    if param_cfg["active"] and activate:
+        return sigmoid, (lambda x: np.log(1e-2 + x / (1 - x + 1e-2)))
+    return (lambda x: x), (lambda x: x)
+
+
+def scalar_physical(param_cfg, activate):
+    """normalise -> store -> de-normalise for one scalar (ts_params.py:93-104, 202-205, 434-495)."""
+    act, inv = act_pair(param_cfg, activate)
+    scale = param_cfg["ub"] - param_cfg["lb"]
+    shift = param_cfg["lb"]
+    stored = inv((param_cfg["val"] - shift) / scale)
+    return act(stored) * scale + shift
+
+
+def vgrid(nvx):
+    """DistributionFunction1V grid (base.py:149-151)."""
+    vmax = 6.0
+    dv = 2 * vmax / nvx
+    return np.linspace(-vmax + dv / 2, vmax - dv / 2, nvx)
+
+
+_DLM_CACHE = {}
+
+
+def dlm_table():
+    """Regenerated stand-in for the missing blob external/numDistFuncs/DLM_x_-3_-10_10_m_-1_2_5.mat
+    (base.py:266-268): IT[20001, 31] on vx_ax = linspace(-10,10,20001), m_ax = linspace(2,5,31).
+
+    IT(v,m) = projection of exp(-(|v|/(alpha*sqrt2))^m) on one axis = Gamma(2/m) Q(2/m, (|v|/(alpha sqrt2))^m),
+    alpha = sqrt(3 Gamma(3/m) / (2 Gamma(5/m))).  Normalisation is irrelevant
+    (base.py:294 renormalises)."""
+    if "IT" not in _DLM_CACHE:
+        vx_ax = np.linspace(-10, 10, 20001)
+        m_ax = np.linspace(2, 5, 31)
+        IT = np.empty((vx_ax.size, m_ax.size))
+        for j, m in enumerate(m_ax):
+            alpha = np.sqrt(3.0 * gamma(3.0 / m) / 2.0 / gamma(5.0 / m))
+            IT[:, j] = gamma(2.0 / m) * gammaincc(2.0 / m, (np.abs(vx_ax) / (alpha * np.sqrt(2.0))) ** m)
+        _DLM_CACHE["IT"] = (vx_ax, m_ax, IT)
+    return _DLM_CACHE["IT"]
+
+
+def dlm1v(nvx, m):
+    """DLM1V.__call__ (base.py:269-272, 277-294): lerp the table in v onto vx, lerp in m, normalise."""
+    vx = vgrid(nvx)
+    vx_ax, m_ax, IT = dlm_table()
+    f_vx_m = np.stack([np.interp(vx, vx_ax, IT[:, j]) for j in range(m_ax.size)], axis=1)
+    fdlm = np.array([np.interp(m, m_ax, f_vx_m[i, :]) for i in range(vx.size)])
+    return vx, fdlm / np.sum(fdlm) / (vx[1] - vx[0])
+
+
+def dlm_m_physical(fe_cfg, activate):
+    """DLM1V.__init__ / get_unnormed_params (base.py:255-265, 274-275): scale 3, shift 2."""
+    if activate and fe_cfg["active"]:
+        inv = lambda x: np.log(1e-2 + x / (1 - x + 1e-2))
+        act = sigmoid
+    else:
+        inv = act = lambda x: x
+    return act(inv((fe_cfg["params"]["m"]["val"] - 2.0) / 3.0)) * 3.0 + 2.0
+
+
+def maxwellian1v(nvx):
+    """'mx' type (ts_params.py:135-143)."""
+    vx = vgrid(nvx)
+    f = np.exp(-(vx**2 / 2))
+    return vx, f / np.sum(f) / (vx[1] - vx[0])
+
+
+def super_gaussian_projected(vx, m):
+    """Analytic projected super-Gaussian of order m on an arbitrary grid (SURVEY.md §8d synthetic
+    sweep): f ∝ Gamma(2/m) Q(2/m, (|v|/(alpha sqrt2))^m), normalised sum(f) dv = 1."""
+    alpha = np.sqrt(3.0 * gamma(3.0 / m) / 2.0 / gamma(5.0 / m))
+    f = gamma(2.0 / m) * gammaincc(2.0 / m, (np.abs(vx) / (alpha * np.sqrt(2.0))) ** m)
+    return f / np.sum(f) / (vx[1] - vx[0])
+
+
+def second_order_butterworth(signal, f_sampling=100, f_cutoff=15, method="forward_backward"):
+    """base.py:41-96 (direct-form IIR with the reference's start-up convention)."""
+    if method == "forward_backward":
+        signal = second_order_butterworth(signal, f_sampling, f_cutoff, "forward")
+        return second_order_butterworth(signal, f_sampling, f_cutoff, "backward")
+    if method == "backward":
+        signal = signal[::-1]
+    ff = f_cutoff / f_sampling
+    ita = 1.0 / np.tan(np.pi * ff)
+    q = np.sqrt(2.0)
+    b0 = 1.0 / (1.0 + q * ita + ita**2)
+    b1, b2 = 2 * b0, b0
+    a1 = 2.0 * (ita**2 - 1.0) * b0
+    a2 = -(1.0 - q * ita + ita**2) * b0
+    x1, x2, y1, y2 = signal[1], signal[0], signal[1], signal[0]
+    out = []
+    for x in signal[2:]:
+        y = b0 * x + b1 * x1 + b2 * x2 + a1 * y1 + a2 * y2
+        x1, x2, y1, y2 = x, x1, y, y1
+        out.append(y)
+    out = np.array(out)
+    out = np.concatenate((out[0:1], out[0:1], out))
+    if method == "backward":
+        out = out[::-1]
+    return out
+
+
+def arbitrary1v_init(nvx, init_m):
+    """Arbitrary1V.init_dlm (base.py:188-196)."""
+    vx = vgrid(nvx)
+    alpha = np.sqrt(3.0 * gamma(3.0 / init_m) / 2.0 / gamma(5.0 / init_m))
+    cst = init_m / (4.0 * np.pi * alpha**3.0 * gamma(3.0 / init_m))
+    fdlm = cst * np.exp(-(np.abs(vx / alpha) ** init_m))
+    fdlm = fdlm / np.sum(fdlm) / (vx[1] - vx[0])
+    return vx, np.sqrt(-np.log10(fdlm)) / 7.0
+
+
+def arbitrary1v_call(vx, fval):
+    """Arbitrary1V.__call__ (base.py:201-204)."""
+    f = (7.0 * second_order_butterworth(fval, 100, 6, "forward_backward")) ** 2.0
+    f = np.power(10.0, -f)
+    return f / np.sum(f) / (vx[1] - vx[0])
+
+
+def thomson_params(param_cfg, activate=True, dlm_m_offset=0.0):
+    """ThomsonParams(...)() for ONE lineout (ts_params.py:583-603): nested dict of physical scalars +
+    fe/v.  ``dlm_m_offset`` shifts the DLM order m (used only to quantify the effect of the missing
+    table blob)."""
+    ecfg = param_cfg["electron"]
+    out = {"electron": {}, "general": {}}
+    for p in ["Te", "ne"]:
+        out["electron"][p] = scalar_physical(ecfg[p], activate)
+    fe_cfg = ecfg["fe"]
+    typ = fe_cfg["type"].casefold()
+    if fe_cfg["dim"] != 1:
+        raise NotImplementedError("2V parameter producer: see oracle.np_oracle_2v")
+    if typ == "dlm":
+        m = dlm_m_physical(fe_cfg, activate) + dlm_m_offset
+        vx, fe = dlm1v(fe_cfg["nvx"], m)
+        out["electron"]["m"] = m
+    elif typ == "mx":
+        vx, fe = maxwellian1v(fe_cfg["nvx"])
+    elif typ == "arbitrary":
+        vx, fval = arbitrary1v_init(fe_cfg["nvx"], fe_cfg["params"]["init_m"])
+        fe = arbitrary1v_call(vx, fval)
+    else:
+        raise NotImplementedError(typ)
+    out["electron"]["fe"], out["electron"]["v"] = fe, vx
+    for p in ["lam", "amp1", "amp2", "amp3", "ne_gradient", "Te_gradient", "ud", "Va"]:
+        out["general"][p] = scalar_physical(param_cfg["general"][p], activate)
+    ions = sorted([k for k in param_cfg if k.startswith("ion-")], key=lambda s: int(s.split("-")[1]))
+    for k in ions:
+        icfg = param_cfg[k]
+        act_f, inv_f = act_pair(icfg["fract"], activate)
+        out[k] = {
+            "A": icfg["A"]["val"],
+            "fract": act_f(inv_f(icfg["fract"]["val"])),  # ts_params.py:288,298,323 (raw val through act)
+            "Ti": scalar_physical(icfg["Ti"], activate),
+            "Z": scalar_physical(icfg["Z"], activate),
+        }
+    # renormalize_ions (ts_params.py:543-563)
+    fsum = 0.0
+    for n, k in enumerate(ions):
+        if n > 0 and param_cfg[k]["Ti"].get("same", False):
+            out[k]["Ti"] = out["ion-1"]["Ti"]
+        fsum += out[k]["fract"]
+    for k in ions:
+        out[k]["fract"] = out[k]["fract"] / fsum
+    return out
