@@ -1,0 +1,125 @@
+/* tsff.h -- C ABI of libtsff: B200-native (sm_100a) Thomson-scattering form-factor kernels.
+ *
+ * The reference (ergodicio/tsadar) is pure Python/JAX and has NO plugin / FFI interface; the only contracts on
+ * its hot path are Python signatures.  Each entry point below names the reference call it replaces; the
+ * jax.ffi / ctypes bindings a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host"; the caller (XLA / torch) owns all buffers.
+ *   - no allocation, no host synchronisation, no exceptions inside a call; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*).  Return 0 or a negative TSFF_E* code; tsff_last_error() gives the text.
+ *   - a tsff_ctx is immutable after creation (device-resident static tables): re-entrant per (ctx, stream).
+ *   - arrays are C-contiguous; B = lineouts in the call, W = wavelength points, A = scattering angles,
+ *     G = gradient points, I = ion species, V = f-table length, P = G*W*A poles per lineout.
+ *   - NaN policy: propagate (as the reference does).
+ *
+ * Parameter block  params[B][NP], NP = TSFF_P_ION0 + 4*I, float64, PHYSICAL units as produced by the reference's
+ * ThomsonParams.__call__ (ts_params.py:583-603): Te [keV], ne [1e20 cm^-3], lam [nm], Va, ud [1e6 cm/s],
+ * gradients [%], amp1..3, then per ion (A, Z, Ti [keV], fract).
+ */
+#ifndef TSFF_H_
+#define TSFF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSFF_ABI_VERSION 1
+#define TSFF_MAX_IONS 4
+
+enum {
+  TSFF_OK = 0,
+  TSFF_E_INVALID = -1, /* bad argument / unsupported shape */
+  TSFF_E_CUDA = -2,    /* a CUDA runtime call or launch failed */
+  TSFF_E_NOMEM = -3,
+  TSFF_E_NODEVICE = -4 /* no sm_100 device: there is no CPU fallback */
+};
+
+enum { TSFF_P_TE = 0, TSFF_P_NE, TSFF_P_LAM, TSFF_P_VA, TSFF_P_UD, TSFF_P_NE_GRAD, TSFF_P_TE_GRAD,
+       TSFF_P_AMP1, TSFF_P_AMP2, TSFF_P_AMP3, TSFF_P_ION0 };
+enum { TSFF_ION_A = 0, TSFF_ION_Z, TSFF_ION_TI, TSFF_ION_FRACT, TSFF_ION_STRIDE };
+
+/* electron-susceptibility mode */
+enum {
+  TSFF_MODE_TABLE = 0, /* FormFactor.__call__ (form_factor.py:163-298): f resampled on xi1 (1024), PV table on the
+                          fixed grid xi2 (1640) via ratintn, lerped to xi_e; Im chi_e from the forward difference
+                          of exp(cubic(log f)) along omega */
+  TSFF_MODE_DIRECT = 1 /* calc_chi_vals semantics (form_factor.py:369-388) on a given 1-D table: pole = xi_e,
+                          nodes = the f grid, gradient/lerp of f;  the synthetic-sweep workload of SURVEY.md 8(d) */
+};
+enum { TSFF_F32 = 0, TSFF_F64 = 1 };
+/* precision of the PV inner loop */
+enum { TSFF_PV_FP32 = 0 /* MUFU.LG2 fast path */, TSFF_PV_FP64 = 1 /* validation path, ~10x slower */ };
+
+typedef struct tsff_ctx tsff_ctx;
+
+typedef struct tsff_static_cfg {
+  int32_t abi_version;  /* TSFF_ABI_VERSION */
+  int32_t mode;         /* TSFF_MODE_* */
+  int32_t W, A, G, I, V;
+  int32_t pv_precision; /* TSFF_PV_* */
+  double lam_min, lam_max; /* FormFactor(lambda_range=...) : lamAxis = linspace(lam_min, lam_max, W)  (form_factor.py:132) */
+  double lam_shift;        /* FormFactor(lam_shift=...)    (form_factor.py:196) */
+  double v0, dv;           /* f-table grid v_i = v0 + i dv  (DistributionFunction1V, base.py:149-151) */
+  const double* sa_deg;    /* host [A]  scattering_angles["sa"] */
+  const double* weights;   /* host [A]  angular weights applied in the angle sum (generate_spectra.py:165,197) */
+  const double* jmul;      /* host [W] or NULL: static per-wavelength multiplier (IAW filter, generate_spectra.py:210-216) */
+  const double* zp_x;      /* host [zp_n]  Z' table abscissa (rdWT.txt / idWT.txt, form_factor.py:33-34) */
+  const double* zp_re;     /* host [zp_n] */
+  const double* zp_im;     /* host [zp_n] */
+  int32_t zp_n;
+  int32_t reserved;
+} tsff_static_cfg;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+/* replaces FormFactor.__init__ (form_factor.py:120-161): builds omgs, xi1, xi2, Zpi on `device`. */
+int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx** out);
+void tsff_ctx_destroy(tsff_ctx* ctx);
+const char* tsff_last_error(void); /* thread-local, host pointer */
+int tsff_abi_version(void);
+
+/* bytes the caller must provide: `saved` lives from *_fwd to the matching *_bwd, `ws` is scratch per call */
+size_t tsff_ff_saved_bytes(const tsff_ctx* ctx, int64_t B);
+size_t tsff_ff_workspace_bytes(const tsff_ctx* ctx, int64_t B);
+
+/* ---- B3: form factor ------------------------------------------------------------------------------------ */
+/* replaces FormFactor.__call__(params) -> formfactor[G,W,A] (form_factor.py:163-298) under the reference's vmap
+ * over lineouts, fused with FitModel's mean over G and weighted angle sum (generate_spectra.py:164-165,193,197):
+ *   ff_out   [B][G][W][A] float64 or NULL   (= formfactor)
+ *   modl_out [B][W]       float64 or NULL   (= jmul[j] * sum_a weights[a] * mean_g formfactor)
+ *   fe       [B][V] float32/float64 (fe_dtype), the electron distribution table per lineout
+ *   saved, ws: see *_bytes above; 256-byte aligned. */
+int tsff_ff_fwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out,
+                double* ff_out, void* saved, void* ws, void* stream);
+
+/* VJP of tsff_ff_fwd (replaces XLA's reverse-mode of the same graph, loss_function.py:107-108):
+ *   modl_bar [B][W] or NULL, ff_bar [B][G][W][A] or NULL  (cotangents; at least one non-NULL)
+ *   params_bar [B][NP] float64 (overwritten; amp1..3 and A entries are 0),  fe_bar [B][V] (fe_dtype, overwritten) */
+int tsff_ff_bwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
+                const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
+                void* stream);
+
+/* ---- B1: principal-value integral -------------------------------------------------------------------- */
+/* replaces vmap(ratintn.ratintn)(f, z[None,:] - pole[:,None], z) (ratintn.py:4-23; form_factor.py:266-268,385-386)
+ * for uniform nodes z_i = z0 + i h, i < N:
+ *   f [B][N] float64 node values, pole [B][P] float64  ->  out [B][P], dout_dpole [B][P] (NULL to skip), float64
+ *   ws: tsff_pv_workspace_bytes(B, N). */
+size_t tsff_pv_workspace_bytes(int64_t B, int64_t N, int64_t P);
+int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
+                double* out, double* dout_dpole, int pv_precision, void* ws, void* stream);
+/* VJP: out_bar [B][P] -> f_bar [B][N], pole_bar [B][P] (NULL to skip) */
+int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
+                const double* out_bar, double* f_bar, double* pole_bar, void* ws, void* stream);
+
+/* ---- microbenchmarks used for the roofline denominators --------------------------------- */
+/* runs `iters` dependent-chain FFMA (kind 0) or MUFU.LG2 (kind 1) per thread on the whole device; returns the
+ * number of operations issued (FFMA counts 1 op = 2 flop) in *ops; time it with events on `stream`. */
+int tsff_microbench(int kind, int64_t iters, double* ops, float* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSFF_H_ */

@@ -1,0 +1,167 @@
+// Host-side self-consistency checks of tsadar_b200/csrc/tsff_math.cuh and tsff_pv.cuh (the exact headers the CUDA
+// kernels compile), built with g++ by tests/test_hostsim.py.  TEST ONLY -- the product has no CPU path.
+//  1. lg_backward      vs central differences of lg_forward
+//  2. assemble/ion/kin backward vs central differences of the forward point chain
+//  3. pv_accumulate (+pv_finish) vs the literal ratintn formula (ratintn.py:4-52) and dI/dxi vs differences
+//  4. hermite_uniform derivative / weights vs differences
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include <complex>
+#include <algorithm>
+#include "../../tsadar_b200/csrc/tsff_math.cuh"
+#include "../../tsadar_b200/csrc/tsff_pv.cuh"
+using namespace tsff;
+
+static double relerr(double a, double b) { return fabs(a - b) / std::max(1e-300, std::max(fabs(a), fabs(b))); }
+
+// literal ratintn (ratintn.py:4-52) in double
+static double ratintn_literal(const std::vector<double>& f, const std::vector<double>& z, double xi) {
+  int N = (int)f.size();
+  double out = 0.0;
+  for (int i = 0; i + 2 < N; i++) {
+    double g0 = z[i] - xi, g1 = z[i + 1] - xi;
+    double fdif = f[i + 1] - f[i], gdif = g1 - g0, fav = 0.5 * (f[i + 1] + f[i]), gav = 0.5 * (g1 + g0);
+    double tmp = fav * gdif - gav * fdif;
+    double rfn = fdif / gdif + tmp * std::log(std::complex<double>((gav + 0.5 * gdif) / (gav - 0.5 * gdif), 0.0)).real() / (gdif * gdif);
+    out += rfn * (z[i + 1] - z[i]);
+  }
+  return out;
+}
+
+struct Tables { std::vector<double> zr, zi; ZTab zt; };
+
+static double point_P(const double* params, int nI, double lam_shift, double omgs, double cth, const ZTab& zt, double chiEr_in,
+                      double chiEi_in, double fphi, bool use_xie_dep) {
+  LG L; lg_zero(L); lg_forward(params, nI, 0, 1, lam_shift, L);
+  Kin q; kin_forward(L, omgs, cth, q);
+  IonOut io; ion_forward(L, nI, zt, q, io);
+  // make chiE depend on kinematics the way the kernels do: chiEr = -ikl2 * I(xie), chiEi = pi ikl2 dfe(xie), fphi(xie)
+  double I = use_xie_dep ? sin(q.xie) * 0.7 : chiEr_in;
+  double dfe = use_xie_dep ? cos(0.5 * q.xie) * 0.3 : chiEi_in;
+  double fp = use_xie_dep ? exp(-0.5 * q.xie * q.xie) * 0.4 : fphi;
+  Asm s;
+  return assemble_forward(L, q, io, -q.ikl2 * I, kPi * q.ikl2 * dfe, fp, omgs, s);
+}
+
+int main() {
+  int fails = 0;
+  // Z' like table (smooth stand-in; the real table is checked on the GPU against the oracle)
+  Tables T; T.zr.resize(1640); T.zi.resize(1640);
+  for (int i = 0; i < 1640; i++) { double x = -8.2 + 0.01 * i; T.zr[i] = -2.0 * (1 - 2 * x * x) * exp(-x * x) + 0.1 / (1 + x * x); T.zi[i] = -3.5 * x * exp(-x * x); }
+  T.zt = {T.zr.data(), T.zi.data(), 1640, -8.2, 0.01, -8.2 + 1639 * 0.01};
+  const int nI = 2, NP = 10 + 4 * nI;
+  double params[NP] = {0.8, 0.35, 526.5, 1.5, -0.7, 3.0, 2.0, 1, 1, 1, /*ion1*/ 40.0, 8.0, 0.2, 0.6, /*ion2*/ 1.0, 1.0, 0.3, 0.4};
+  const double lam_shift = 0.3;
+  // ---- 1. lg_backward
+  {
+    const int G = 3;
+    for (int g = 0; g < G; g++) {
+      // scalar functional: random linear combination of LG outputs
+      auto fun = [&](const double* p) {
+        LG L; lg_zero(L); lg_forward(p, nI, g, G, lam_shift, L);
+        double s = 1e-20 * L.ne_g + 1e-15 * L.omgL + 1e-30 * L.omgpe2 + 1e-5 * L.kL + 1e-9 * L.vTe + 1e-6 * L.Va6 + 2e-6 * L.ud6;
+        for (int i = 0; i < nI; i++) s += (i + 1) * (1e9 * L.c_kldi[i] + 1e6 * L.inv_s2vTi[i] + 1e5 * L.ioncf[i]);
+        return s;
+      };
+      LG b; lg_zero(b);
+      b.ne_g = 1e-20; b.omgL = 1e-15; b.omgpe2 = 1e-30; b.kL = 1e-5; b.vTe = 1e-9; b.Va6 = 1e-6; b.ud6 = 2e-6;
+      for (int i = 0; i < nI; i++) { b.c_kldi[i] = (i + 1) * 1e9; b.inv_s2vTi[i] = (i + 1) * 1e6; b.ioncf[i] = (i + 1) * 1e5; }
+      double pbar[NP] = {0};
+      lg_backward(params, nI, g, G, lam_shift, b, pbar);
+      for (int k = 0; k < NP; k++) {
+        if (k == P_AMP1 || k == P_AMP2 || k == P_AMP3 || (k >= P_ION0 && (k - P_ION0) % 4 == ION_A)) continue;
+        double p2[NP]; std::copy(params, params + NP, p2);
+        double h = 1e-4 * std::max(1.0, fabs(params[k]));
+        p2[k] = params[k] + h; double fp = fun(p2);
+        p2[k] = params[k] - h; double fm = fun(p2);
+        double fd = (fp - fm) / (2 * h);
+        double e = fabs(fd - pbar[k]) / std::max(1e-3, std::max(fabs(fd), fabs(pbar[k])));
+        if (e > 2e-6) { printf("FAIL lg_backward g=%d k=%d fd=%.10e ad=%.10e\n", g, k, fd, pbar[k]); fails++; }
+      }
+    }
+    printf("lg_backward checked\n");
+  }
+  // ---- 2. point chain: d P / d params through kin/ion/assemble (+ synthetic xie-dependent chi_e)
+  {
+    const double lam_nm[3] = {450.0, 526.2, 610.0};
+    for (int c = 0; c < 3; c++) {
+      const double omgs = 2e7 * kPi * kC / lam_nm[c], cth = cos(60.0 * kPi / 180);
+      LG L; lg_zero(L); lg_forward(params, nI, 0, 1, lam_shift, L);
+      Kin q; kin_forward(L, omgs, cth, q);
+      IonOut io; ion_forward(L, nI, T.zt, q, io);
+      double I = sin(q.xie) * 0.7, dI = cos(q.xie) * 0.7, dfe = cos(0.5 * q.xie) * 0.3, ddfe = -0.15 * sin(0.5 * q.xie);
+      double fp = exp(-0.5 * q.xie * q.xie) * 0.4, dfp = -q.xie * fp;
+      double chiEr = -q.ikl2 * I, chiEi = kPi * q.ikl2 * dfe;
+      Asm s; double P = assemble_forward(L, q, io, chiEr, chiEi, fp, omgs, s);
+      PointBar pb; KinBar kb = {0, 0, 0, 0, 0, 0}; LG Lb; lg_zero(Lb);
+      assemble_backward(L, nI, T.zt, q, io, chiEr, chiEi, fp, s, 1.0, pb, kb, Lb);
+      kb.ikl2 += -I * pb.chiEr + kPi * dfe * pb.chiEi;
+      kb.xie += (-q.ikl2 * pb.chiEr) * dI + (kPi * q.ikl2 * pb.chiEi) * ddfe + pb.fphi * dfp;
+      kin_backward(L, omgs, cth, q, kb, Lb);
+      double pbar[NP] = {0};
+      lg_backward(params, nI, 0, 1, lam_shift, Lb, pbar);
+      for (int k = 0; k < NP; k++) {
+        if (k == P_AMP1 || k == P_AMP2 || k == P_AMP3 || (k >= P_ION0 && (k - P_ION0) % 4 == ION_A)) continue;
+        if (k == P_NE_GRAD || k == P_TE_GRAD) { /* G=1 path */ }
+        double p2[NP]; std::copy(params, params + NP, p2);
+        double h = 1e-6 * std::max(1.0, fabs(params[k]));
+        p2[k] = params[k] + h; double f1 = point_P(p2, nI, lam_shift, omgs, cth, T.zt, 0, 0, 0, true);
+        p2[k] = params[k] - h; double f0 = point_P(p2, nI, lam_shift, omgs, cth, T.zt, 0, 0, 0, true);
+        double fd = (f1 - f0) / (2 * h);
+        double e = fabs(fd - pbar[k]) / std::max(1e-12 * fabs(P), std::max(fabs(fd), fabs(pbar[k])));
+        if (e > 2e-5) { printf("FAIL point chain lam=%g k=%d fd=%.10e ad=%.10e (P=%.4e)\n", lam_nm[c], k, fd, pbar[k], P); fails++; }
+      }
+    }
+    printf("point chain checked\n");
+  }
+  // ---- 3. PV sums
+  {
+    const int N = 512; const double z0 = -6 + 6.0 / N, h = 12.0 / N;
+    std::vector<double> f(N), z(N);
+    for (int i = 0; i < N; i++) { z[i] = z0 + i * h; f[i] = -z[i] * exp(-0.5 * z[i] * z[i]) * 0.4 + 0.01 * sin(3 * z[i]); }
+    const int M = N - 2, nodes = M + 1, npad = (nodes + 31) / 32 * 32;
+    std::vector<float> D(npad, 0.f); std::vector<double> D64(npad, 0.0);
+    for (int i = 0; i < npad; i++) { D64[i] = pv_weight(f.data(), M, h, i); D[i] = (float)D64[i]; }
+    double maxe32 = 0, maxe64 = 0, maxed = 0;
+    const double xis[] = {-7.3, -5.99, -2.345678, -0.0117, 0.0, 0.4321, 1.0 + 1e-9, 3.3333, 5.97, 6.8};
+    for (double xi : xis) {
+      double ref = ratintn_literal(f, z, xi);
+      float u0[1], nd[1]; pole_split(xi, z0, h, nodes, u0[0], nd[0]);
+      double aI[1], aJ[1];
+      pv_accumulate<1, true>(D.data(), npad / 32, (float)h, u0, nd, aI, aJ);
+      double I, dI; pv_finish(aI[0], aJ[0], f[0], f[M], z0 - xi, z0 + M * h - xi, I, dI);
+      double g0[1] = {z0 - xi}, bI[1], bJ[1];
+      pv_accumulate_f64<1, true>(D64.data(), nodes, h, g0, bI, bJ);
+      double I64, dI64; pv_finish(bI[0], bJ[0], f[0], f[M], z0 - xi, z0 + M * h - xi, I64, dI64);
+      double e = 1e-6;
+      double fd = (ratintn_literal(f, z, xi + e) - ratintn_literal(f, z, xi - e)) / (2 * e);
+      maxe32 = std::max(maxe32, fabs(I - ref)); maxe64 = std::max(maxe64, fabs(I64 - ref));
+      maxed = std::max(maxed, fabs(dI64 - fd) / std::max(1.0, fabs(fd)));
+      if (fabs(I - ref) > 3e-6 || fabs(I64 - ref) > 1e-11 || fabs(dI64 - fd) > 2e-4 * std::max(1.0, fabs(fd)) || fabs(dI - dI64) > 2e-4 * std::max(1.0, fabs(dI64))) {
+        printf("FAIL pv xi=%g ref=%.12e I32=%.12e I64=%.12e dI=%.8e dI64=%.8e fd=%.8e\n", xi, ref, I, I64, dI, dI64, fd); fails++;
+      }
+    }
+    printf("pv: max |I32-ref| = %.3e, max |I64-ref| = %.3e, max rel dI err = %.3e\n", maxe32, maxe64, maxed);
+  }
+  // ---- 4. Hermite
+  {
+    const int V = 64; const double x0 = -6 + 6.0 / V, h = 12.0 / V;
+    std::vector<double> lnf(V), sl(V);
+    for (int i = 0; i < V; i++) { double x = x0 + i * h; lnf[i] = -0.5 * x * x - 0.1 * x * x * x * x / 10; }
+    for (int i = 0; i < V; i++) sl[i] = (i == 0) ? (lnf[1] - lnf[0]) / h : (i == V - 1) ? (lnf[V - 1] - lnf[V - 2]) / h : (lnf[i + 1] - lnf[i - 1]) / (2 * h);
+    for (double x : {-5.5, -1.234, 0.0, 0.777, 4.9}) {
+      Herm hm; double H = hermite_uniform(lnf.data(), sl.data(), V, x0, h, x, -50.0, hm);
+      Herm h2; double e = 1e-6;
+      double fd = (hermite_uniform(lnf.data(), sl.data(), V, x0, h, x + e, -50.0, h2) - hermite_uniform(lnf.data(), sl.data(), V, x0, h, x - e, -50.0, h2)) / (2 * e);
+      double wf0, wf1, wm0, wm1; hermite_weights(hm.t, h, wf0, wf1, wm0, wm1);
+      double Hw = wf0 * lnf[hm.i - 1] + wf1 * lnf[hm.i] + wm0 * sl[hm.i - 1] + wm1 * sl[hm.i];
+      if (fabs(fd - hm.dHdx) > 1e-6 * std::max(1.0, fabs(fd)) || fabs(Hw - H) > 1e-12 * std::max(1.0, fabs(H))) {
+        printf("FAIL hermite x=%g H=%.10e Hw=%.10e dH=%.8e fd=%.8e\n", x, H, Hw, hm.dHdx, fd); fails++;
+      }
+    }
+    printf("hermite checked\n");
+  }
+  printf(fails ? "HOSTSIM FAILED (%d)\n" : "HOSTSIM OK\n", fails);
+  return fails ? 1 : 0;
+}

@@ -1,0 +1,209 @@
+// tsff_api.cu -- C ABI entry points (include/tsff.h): mode dispatch and the stand-alone principal-value
+// integral (boundary B1: vmap(ratintn), ratintn.py:4-23).
+#include "tsff_pv_kernels.cuh"
+
+using namespace tsff;
+
+namespace tsff {
+size_t direct_saved_bytes(const tsff_ctx*, int64_t);
+size_t direct_ws_bytes(const tsff_ctx*, int64_t);
+int direct_fwd(tsff_ctx*, int64_t, const double*, const void*, int, double*, double*, void*, void*, cudaStream_t);
+int direct_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*, const double*, const double*, double*, void*,
+               void*, cudaStream_t);
+size_t table_saved_bytes(const tsff_ctx*, int64_t);
+size_t table_ws_bytes(const tsff_ctx*, int64_t);
+int table_fwd(tsff_ctx*, int64_t, const double*, const void*, int, double*, double*, void*, void*, cudaStream_t);
+int table_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*, const double*, const double*, double*, void*,
+              void*, cudaStream_t);
+}  // namespace tsff
+
+extern "C" size_t tsff_ff_saved_bytes(const tsff_ctx* c, int64_t B) {
+  if (!c || B < 1) return 0;
+  return c->mode == TSFF_MODE_TABLE ? table_saved_bytes(c, B) : direct_saved_bytes(c, B);
+}
+extern "C" size_t tsff_ff_workspace_bytes(const tsff_ctx* c, int64_t B) {
+  if (!c || B < 1) return 0;
+  return c->mode == TSFF_MODE_TABLE ? table_ws_bytes(c, B) : direct_ws_bytes(c, B);
+}
+
+static int check_common(const tsff_ctx* c, int64_t B, const void* params, const void* fe, int fe_dtype, const void* saved,
+                        const void* ws) {
+  if (!c || !params || !fe || !saved || !ws) { set_error("null argument"); return TSFF_E_INVALID; }
+  if (B < 1) { set_error("B must be >= 1"); return TSFF_E_INVALID; }
+  if (fe_dtype != TSFF_F32 && fe_dtype != TSFF_F64) { set_error("fe_dtype must be TSFF_F32 or TSFF_F64"); return TSFF_E_INVALID; }
+  const long long blocks = (long long)B * c->G * (((long long)c->W * c->A + 255) / 256);
+  if (blocks > 0x7fffffffLL) { set_error("batch too large for one launch: split the call"); return TSFF_E_INVALID; }
+  return TSFF_OK;
+}
+
+extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out,
+                           double* ff_out, void* saved, void* ws, void* stream) {
+  int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
+  if (rc) return rc;
+  if (!modl_out && !ff_out) { set_error("no output requested"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->mode == TSFF_MODE_TABLE ? table_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st)
+                                    : direct_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st);
+}
+
+extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
+                           const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
+                           void* stream) {
+  int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
+  if (rc) return rc;
+  if (!modl_bar && !ff_bar) { set_error("no cotangent given"); return TSFF_E_INVALID; }
+  if (!params_bar || !fe_bar) { set_error("null output"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->mode == TSFF_MODE_TABLE
+             ? table_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
+             : direct_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
+}
+
+// ---- B1: stand-alone PV integral -----------------------------------------------------------------------------
+namespace {
+constexpr int kThreads = 256;
+
+struct PvLayout {
+  size_t D, D64, pend, desc, Dbar, pendbar, tI, tdI, bytes;
+  int nodes, npad;
+};
+PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
+  PvLayout L;
+  L.nodes = (int)N - 1;
+  L.npad = (L.nodes + kPvBlk - 1) / kPvBlk * kPvBlk;
+  size_t o = 0;
+  L.D = o; o += align_up((size_t)B * L.npad * 4);
+  L.D64 = o; o += align_up((size_t)B * L.npad * 8);
+  L.pend = o; o += align_up((size_t)B * 2 * 8);
+  L.desc = o; o += align_up((size_t)B * P * 16);
+  L.Dbar = o; o += align_up((size_t)B * L.npad * 8);
+  L.pendbar = o; o += align_up((size_t)B * 2 * 8);
+  L.tI = o; o += align_up((size_t)B * P * 8);
+  L.tdI = o; o += align_up((size_t)B * P * 8);
+  L.bytes = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, double h, int npad, float* D, double* D64,
+                                                      double* pend) {
+  const long long b = blockIdx.x;
+  const double* fb = f + b * N;
+  const int M = N - 2;
+  for (int i = threadIdx.x; i < npad; i += kThreads) {
+    double d = pv_weight(fb, M, h, i);
+    D[b * npad + i] = (float)d;
+    D64[b * npad + i] = d;
+  }
+  if (threadIdx.x == 0) {
+    pend[2 * b] = fb[0];
+    pend[2 * b + 1] = fb[M];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_pv_desc(const double* pole, const double* out_bar, int P, double z0, double h,
+                                                      int nodes, float4* desc, double* pendbar) {
+  __shared__ double sred[2 * (kThreads / 32)];
+  const long long b = blockIdx.x;
+  const double zM = z0 + (double)(nodes - 1) * h;
+  double e0 = 0.0, eM = 0.0;
+  for (int p = threadIdx.x; p < P; p += kThreads) {
+    const double xi = pole[b * P + p], ob = out_bar[b * P + p];
+    float u0, nd;
+    pole_split(xi, z0, h, nodes, u0, nd);
+    desc[b * P + p] = make_float4(u0, nd, (float)ob, 0.f);
+    e0 += ob * (-1.0 - log(fmax(fabs(z0 - xi), 1e-300)));
+    eM += ob * (1.0 + log(fmax(fabs(zM - xi), 1e-300)));
+  }
+  double vals[2] = {e0, eM};
+  block_accumulate<kThreads / 32>(vals, 2, sred, pendbar + 2 * b);
+}
+
+__global__ void __launch_bounds__(kThreads) k_pv_bwd_finish(const double* Dbar, const double* pendbar, int N, int npad, double h,
+                                                            double* f_bar) {
+  const long long b = blockIdx.x;
+  const int M = N - 2;
+  const double ih = 1.0 / h;
+  const double* Db = Dbar + b * npad;
+  for (int i = threadIdx.x; i < N; i += kThreads) {
+    double pb = 0.0;
+    if (i <= M) {
+      double t = 0.0;
+      if (i >= 1) t += Db[i - 1];
+      t -= Db[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
+      if (i + 1 <= M) t += Db[i + 1];
+      pb = t * ih;
+      if (i == 0) pb += pendbar[2 * b];
+      if (i == M) pb += pendbar[2 * b + 1];
+    }
+    f_bar[b * N + i] = pb;
+  }
+}
+
+__global__ void k_mul(const double* x, const double* y, long long n, double* out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = x[t] * y[t];
+}
+
+int launch_poles(const PvLayout& L, int64_t B, int64_t P, char* w, double z0, double h, const double* pole, double* out,
+                 double* dout, int prec, cudaStream_t st) {
+  PvPolesArgs p;
+  p.D = (float*)(w + L.D); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
+  p.poles = pole; p.pole_bstride = P; p.z0 = z0; p.h = h; p.nodes = L.nodes; p.npad = L.npad; p.P = (int)P;
+  p.outI = out; p.outdI = dout;
+  p.ntiles = (int)((P + kPvThreads - 1) / kPvThreads);
+  const size_t smem = (size_t)L.npad * 4;
+  if (prec == TSFF_PV_FP64) {
+    k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
+  } else {
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_pv_poles<1, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pv_poles<1, TSFF_PV_FP32><<<(unsigned)(B * p.ntiles), kPvThreads, smem, st>>>(p);
+  }
+  TSFF_LAUNCH_OK("k_pv_poles");
+  return TSFF_OK;
+}
+}  // namespace
+
+extern "C" size_t tsff_pv_workspace_bytes(int64_t B, int64_t N, int64_t P) {
+  if (B < 1 || N < 4 || P < 1) return 0;
+  return pv_layout(B, N, P).bytes;
+}
+
+extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
+                           double* out, double* dout_dpole, int pv_precision, void* ws, void* stream) {
+  if (!f || !pole || !out || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
+  if ((size_t)N * 4 > 200 * 1024) { set_error("N too large for shared-memory staging"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PvLayout L = pv_layout(B, N, P);
+  char* w = static_cast<char*>(ws);
+  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
+  TSFF_LAUNCH_OK("k_pv_prep");
+  return launch_poles(L, B, P, w, z0, h, pole, out, dout_dpole, pv_precision, st);
+}
+
+extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
+                           const double* out_bar, double* f_bar, double* pole_bar, void* ws, void* stream) {
+  if (!f || !pole || !out_bar || !f_bar || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PvLayout L = pv_layout(B, N, P);
+  char* w = static_cast<char*>(ws);
+  TSFF_CUDA_OK(cudaMemsetAsync(w + L.pendbar, 0, (size_t)B * 16, st));
+  k_pv_desc<<<(unsigned)B, kThreads, 0, st>>>(pole, out_bar, (int)P, z0, h, L.nodes, (float4*)(w + L.desc), (double*)(w + L.pendbar));
+  TSFF_LAUNCH_OK("k_pv_desc");
+  PvNodesArgs n;
+  n.desc = (float4*)(w + L.desc); n.P = (int)P; n.npad = L.npad; n.h = (float)h; n.Dbar = (double*)(w + L.Dbar);
+  n.ntiles = (L.npad + kPvThreads - 1) / kPvThreads;
+  k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+  TSFF_LAUNCH_OK("k_pv_nodes");
+  k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, h, f_bar);
+  TSFF_LAUNCH_OK("k_pv_bwd_finish");
+  if (pole_bar) {
+    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
+    TSFF_LAUNCH_OK("k_pv_prep");
+    int rc = launch_poles(L, B, P, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);
+    if (rc) return rc;
+    const long long n2 = (long long)B * P;
+    k_mul<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(out_bar, (double*)(w + L.tdI), n2, pole_bar);
+    TSFF_LAUNCH_OK("k_mul");
+  }
+  return TSFF_OK;
+}

@@ -1,0 +1,158 @@
+// tsff_ctx.cu -- context creation (static tables of FormFactor.__init__, form_factor.py:120-161), error text,
+// roofline microbenchmarks.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "tsff_common.cuh"
+
+namespace tsff {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace tsff
+
+using namespace tsff;
+
+extern "C" const char* tsff_last_error(void) { return tsff::g_err; }
+extern "C" int tsff_abi_version(void) { return TSFF_ABI_VERSION; }
+
+// scipy.interpolate.interp1d(x, y, "linear")(xq) on an ascending table (form_factor.py:39-42)
+static double table_lerp(const double* x, const double* y, int n, double xq) {
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (x[mid] <= xq) lo = mid; else hi = mid;
+  }
+  double t = (xq - x[lo]) / (x[lo + 1] - x[lo]);
+  return y[lo] + t * (y[lo + 1] - y[lo]);
+}
+
+extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx** out) {
+  if (!cfg || !out) { set_error("null argument"); return TSFF_E_INVALID; }
+  if (cfg->abi_version != TSFF_ABI_VERSION) { set_error("ABI version mismatch: %d vs %d", cfg->abi_version, TSFF_ABI_VERSION); return TSFF_E_INVALID; }
+  if (cfg->W < 2 || cfg->A < 1 || cfg->G < 1 || cfg->I < 1 || cfg->I > TSFF_MAX_IONS || cfg->V < 4) {
+    set_error("unsupported shape W=%d A=%d G=%d I=%d V=%d", cfg->W, cfg->A, cfg->G, cfg->I, cfg->V);
+    return TSFF_E_INVALID;
+  }
+  if (cfg->mode != TSFF_MODE_TABLE && cfg->mode != TSFF_MODE_DIRECT) { set_error("unknown mode %d", cfg->mode); return TSFF_E_INVALID; }
+  if (!cfg->sa_deg || !cfg->weights || !cfg->zp_x || !cfg->zp_re || !cfg->zp_im || cfg->zp_n < 2) {
+    set_error("missing static table pointer"); return TSFF_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
+    set_error("no CUDA device %d (libtsff has no CPU fallback)", device);
+    return TSFF_E_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  TSFF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { set_error("device %d is sm_%d%d; libtsff is built for sm_100a only", device, prop.major, prop.minor); return TSFF_E_NODEVICE; }
+  TSFF_CUDA_OK(cudaSetDevice(device));
+
+  tsff_ctx* c = new tsff_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->mode = cfg->mode; c->W = cfg->W; c->A = cfg->A; c->G = cfg->G; c->I = cfg->I; c->V = cfg->V;
+  c->NP = TSFF_P_ION0 + TSFF_ION_STRIDE * cfg->I;
+  c->pv_precision = cfg->pv_precision;
+  c->lam_min = cfg->lam_min; c->lam_max = cfg->lam_max; c->lam_shift = cfg->lam_shift;
+  c->v0 = cfg->v0; c->dv = cfg->dv;
+
+  const int W = c->W, A = c->A;
+  std::vector<double> h_omgs(W), h_lam(W), h_cos(A), h_w(A), h_jmul(W), h_zr(kXi2N), h_zi(kXi2N), h_xi2(kXi2N);
+  // jnp.linspace(l0, l1, W): start + i*step, endpoint exact
+  const double step = (c->lam_max - c->lam_min) / (double)(W - 1);
+  for (int j = 0; j < W; j++) {
+    double lam = (j == W - 1) ? c->lam_max : c->lam_min + (double)j * step;
+    h_omgs[j] = 2e7 * kPi * kC / lam;                 // form_factor.py:134
+    h_lam[j] = (2.0 * kPi * kC / h_omgs[j]) * 1e7;    // lams (form_factor.py:293) * 1e7 (generate_spectra.py:163,191)
+    h_jmul[j] = cfg->jmul ? cfg->jmul[j] : 1.0;
+  }
+  for (int a = 0; a < A; a++) {
+    h_cos[a] = cos(cfg->sa_deg[a] * kPi / 180.0);    // form_factor.py:210,220
+    h_w[a] = cfg->weights[a];
+  }
+  for (int i = 0; i < kXi2N; i++) {
+    h_xi2[i] = -kXiMinMax + (double)i * 0.01;         // jnp.arange(-8.2, 8.2, 0.01)  form_factor.py:138
+    h_zr[i] = table_lerp(cfg->zp_x, cfg->zp_re, cfg->zp_n, h_xi2[i]);
+    h_zi[i] = table_lerp(cfg->zp_x, cfg->zp_im, cfg->zp_n, h_xi2[i]);
+  }
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n * sizeof(double)); return o; };
+  size_t o_omgs = take(W), o_lam = take(W), o_cos = take(A), o_w = take(A), o_jmul = take(W), o_zr = take(kXi2N),
+         o_zi = take(kXi2N), o_xi2 = take(kXi2N);
+  if (cudaMalloc(&c->dev_blob, off) != cudaSuccess) { delete c; set_error("cudaMalloc(%zu) failed", off); return TSFF_E_NOMEM; }
+  char* base = static_cast<char*>(c->dev_blob);
+  auto up = [&](size_t o, const std::vector<double>& v) { return cudaMemcpy(base + o, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice); };
+  if (up(o_omgs, h_omgs) || up(o_lam, h_lam) || up(o_cos, h_cos) || up(o_w, h_w) || up(o_jmul, h_jmul) || up(o_zr, h_zr) ||
+      up(o_zi, h_zi) || up(o_xi2, h_xi2)) {
+    cudaFree(c->dev_blob); delete c; set_error("table upload failed"); return TSFF_E_CUDA;
+  }
+  c->omgs = (double*)(base + o_omgs); c->lam_nm = (double*)(base + o_lam); c->costh = (double*)(base + o_cos);
+  c->wts = (double*)(base + o_w); c->jmul = (double*)(base + o_jmul); c->zr = (double*)(base + o_zr);
+  c->zi = (double*)(base + o_zi); c->xi2 = (double*)(base + o_xi2);
+  c->zt.zr = c->zr; c->zt.zi = c->zi; c->zt.n = kXi2N; c->zt.x0 = h_xi2[0]; c->zt.h = 0.01; c->zt.xlast = h_xi2[kXi2N - 1];
+  // xi1 = linspace(-(8.2 + sqrt2/1024), +(8.2 + sqrt2/1024), 1024)   form_factor.py:137
+  const double e = kXiMinMax + sqrt(2.0) / (double)kXi1N;
+  c->xi1_0 = -e;
+  c->xi1_h = (2.0 * e) / (double)(kXi1N - 1);
+  if (c->mode == TSFF_MODE_TABLE) {
+    c->pv_nodes = kXi1N - 1; c->pv_z0 = c->xi1_0; c->pv_h = c->xi1_h;
+  } else {
+    c->pv_nodes = c->V - 1; c->pv_z0 = c->v0; c->pv_h = c->dv;
+  }
+  c->pv_npad = (c->pv_nodes + kPvBlk - 1) / kPvBlk * kPvBlk;
+  *out = c;
+  return TSFF_OK;
+}
+
+extern "C" void tsff_ctx_destroy(tsff_ctx* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->dev_blob);
+  delete ctx;
+}
+
+// ---- roofline microbenchmarks (FFMA / MUFU.LG2 issue peaks), SURVEY.md 8(d) ------------------------------
+__global__ void __launch_bounds__(256) k_micro_ffma(long long iters, float* sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+  for (long long i = 0; i < iters; i++) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678f) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_micro_lg2(long long iters, float* sink) {
+  float a0 = 1.5f + threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  for (long long i = 0; i < iters; i++) {
+    a0 = lg2_approx(a0) + 4.f; a1 = lg2_approx(a1) + 4.f; a2 = lg2_approx(a2) + 4.f; a3 = lg2_approx(a3) + 4.f;
+  }
+  float s = a0 + a1 + a2 + a3;
+  if (s == 12345.678f) sink[0] = s;
+}
+
+extern "C" int tsff_microbench(int kind, int64_t iters, double* ops, float* sink, void* stream) {
+  int dev = 0, sms = 0;
+  TSFF_CUDA_OK(cudaGetDevice(&dev));
+  TSFF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kind == 0) {
+    k_micro_ffma<<<blocks, threads, 0, st>>>(iters, sink);
+    if (ops) *ops = (double)blocks * threads * (double)iters * 8.0;
+  } else if (kind == 1) {
+    k_micro_lg2<<<blocks, threads, 0, st>>>(iters, sink);
+    if (ops) *ops = (double)blocks * threads * (double)iters * 4.0;
+  } else {
+    set_error("unknown microbench kind %d", kind);
+    return TSFF_E_INVALID;
+  }
+  TSFF_LAUNCH_OK("microbench");
+  return TSFF_OK;
+}

@@ -1,0 +1,426 @@
+// tsff_direct.cu -- TSFF_MODE_DIRECT: 1V kinematics (form_factor.py:182-253, 273-296) with the
+// calc_chi_vals electron susceptibility (form_factor.py:369-388) evaluated at every pole xi_e(omega, angle)
+// against the lineout's own f-table.  This is the synthetic-sweep workload and the per-pole
+// stage of the 2V path.
+//
+// Kernels
+//   k_direct_prep       per lineout: LG scalars, df = gradient(f), PV weights D (FP32 + FP64), endpoints
+//   k_direct_fwd        thread-owns-pole: FP64 kinematics -> FP32 PV sweep (MUFU-bound) -> FP64 assembly
+//   k_reduce_modl       mean over G, weighted angle sum, static per-wavelength multiplier
+//   k_direct_bwd_poles  FP64 reverse of the assembly per pole; emits Ibar descriptors, lerp scatter, LG cotangents
+//   k_pv_nodes          (tsff_pv_kernels.cuh) thread-owns-node adjoint PV sweep (MUFU-bound)
+//   k_direct_bwd_finish per lineout: Dbar -> df_bar -> fe_bar; LG cotangents -> params_bar
+#include "tsff_pv_kernels.cuh"
+
+using namespace tsff;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// np.gradient(f, dv) at node i (form_factor.py:372): central inside, first-order one-sided at the ends
+template <typename T>
+__device__ __forceinline__ double grad_at(const T* f, int V, double dv, int i) {
+  if (i <= 0) return ((double)f[1] - (double)f[0]) / dv;
+  if (i >= V - 1) return ((double)f[V - 1] - (double)f[V - 2]) / dv;
+  return ((double)f[i + 1] - (double)f[i - 1]) / (2.0 * dv);
+}
+
+struct DirectLayout {  // byte offsets inside `saved` and `ws` for a batch of B lineouts
+  size_t s_lg, s_I, s_dI, saved_bytes;
+  size_t w_D, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
+      ws_bytes;
+};
+
+DirectLayout direct_layout(const tsff_ctx* c, int64_t B) {
+  DirectLayout L;
+  const size_t P = (size_t)c->G * c->W * c->A;
+  size_t o = 0;
+  L.s_lg = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
+  L.s_I = o; o += align_up((size_t)B * P * 8);
+  L.s_dI = o; o += align_up((size_t)B * P * 8);
+  L.saved_bytes = o;
+  o = 0;
+  L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
+  L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
+  L.w_pend = o; o += align_up((size_t)B * 2 * 8);
+  L.w_ff = o; o += align_up((size_t)B * P * 8);
+  L.w_desc = o; o += align_up((size_t)B * P * 16);
+  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
+  L.w_zero_begin = o;
+  L.w_accfe = o; o += align_up((size_t)B * c->V * 8);
+  L.w_accdf = o; o += align_up((size_t)B * c->V * 8);
+  L.w_pendbar = o; o += align_up((size_t)B * 2 * 8);
+  L.w_lgbar = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
+  L.w_zero_end = o;
+  L.ws_bytes = o;
+  return L;
+}
+
+struct DirectArgs {
+  // static
+  int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  double lam_shift, v0, dv;
+  const double *omgs, *costh, *wts, *jmul;
+  ZTab zt;
+  // per call
+  const double* params;
+  const void* fe;
+  double* lg;        // [B][G][kLGDoubles]
+  double* sI;        // [B][P]
+  double* sdI;       // [B][P]
+  float* D;          // [B][npad]
+  double* D64;       // [B][npad] or null
+  double* pend;      // [B][2]
+  double* ff;        // [B][G][W][A]
+  // backward
+  const double* modl_bar;
+  const double* ff_bar;
+  float4* desc;
+  double *accfe, *accdf, *pendbar, *Dbar, *lgbar;
+  double* params_bar;
+  void* fe_bar;
+};
+
+__device__ __forceinline__ void load_lg(const double* src, LG& L) {
+  L.ne_g = src[0]; L.omgL = src[1]; L.omgpe2 = src[2]; L.kL = src[3]; L.vTe = src[4]; L.Va6 = src[5]; L.ud6 = src[6];
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    L.c_kldi[i] = src[7 + i]; L.inv_s2vTi[i] = src[7 + TSFF_MAX_IONS + i]; L.ioncf[i] = src[7 + 2 * TSFF_MAX_IONS + i];
+  }
+}
+__device__ __forceinline__ void store_lg(double* dst, const LG& L) {
+  dst[0] = L.ne_g; dst[1] = L.omgL; dst[2] = L.omgpe2; dst[3] = L.kL; dst[4] = L.vTe; dst[5] = L.Va6; dst[6] = L.ud6;
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    dst[7 + i] = L.c_kldi[i]; dst[7 + TSFF_MAX_IONS + i] = L.inv_s2vTi[i]; dst[7 + 2 * TSFF_MAX_IONS + i] = L.ioncf[i];
+  }
+}
+
+// ---- prep -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
+  const long long b = blockIdx.x;
+  const T* fe = static_cast<const T*>(a.fe) + b * a.V;
+  if (threadIdx.x < a.G) {
+    LG L;
+    lg_zero(L);
+    lg_forward(a.params + b * a.NP, a.nI, threadIdx.x, a.G, a.lam_shift, L);
+    store_lg(a.lg + (b * a.G + threadIdx.x) * kLGDoubles, L);
+  }
+  const int M = a.nodes - 1;
+  for (int i = threadIdx.x; i < a.npad; i += kThreads) {
+    double d = 0.0;
+    if (i <= M) {
+      double pc = grad_at(fe, a.V, a.dv, i);
+      double sR = (i < M) ? (grad_at(fe, a.V, a.dv, i + 1) - pc) / a.dv : 0.0;
+      double sL = (i > 0) ? (pc - grad_at(fe, a.V, a.dv, i - 1)) / a.dv : 0.0;
+      d = sR - sL;
+    }
+    a.D[b * a.npad + i] = (float)d;
+    if (a.D64) a.D64[b * a.npad + i] = d;
+  }
+  if (threadIdx.x == 0) {
+    a.pend[2 * b] = grad_at(fe, a.V, a.dv, 0);
+    a.pend[2 * b + 1] = grad_at(fe, a.V, a.dv, M);
+  }
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------
+// grid.x = B * G * ntiles; a tile covers kThreads*R consecutive (j,a) pairs of one (lineout, gradient point).
+template <int R, typename T, int PREC>
+__global__ void __launch_bounds__(kThreads) k_direct_fwd(const DirectArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ LG sL;
+  float* sD = reinterpret_cast<float*>(smem_raw);
+  const int tile = blockIdx.x % a.ntiles;
+  const long long bg = blockIdx.x / a.ntiles;
+  const int g = (int)(bg % a.G);
+  const long long b = bg / a.G;
+  if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
+  if (PREC == TSFF_PV_FP32) stage_bulk(sD, a.D + b * a.npad, (uint32_t)a.npad * 4u, &bar);
+  else __syncthreads();
+  const T* fe = static_cast<const T*>(a.fe) + b * a.V;
+  const int WA = a.W * a.A;
+
+  float u0[R], nd[R];
+  double g0d[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    if (idx >= WA) idx = WA - 1;
+    Kin q;
+    kin_forward(sL, a.omgs[idx / a.A], a.costh[idx % a.A], q);
+    pole_split(q.xie, a.v0, a.dv, a.nodes, u0[r], nd[r]);
+    g0d[r] = a.v0 - q.xie;
+  }
+  double accI[R], accJ[R];
+  if (PREC == TSFF_PV_FP32) pv_accumulate<R, true>(sD, a.npad / kPvBlk, (float)a.dv, u0, nd, accI, accJ);
+  else pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.dv, g0d, accI, accJ);
+
+  const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    if (idx >= WA) continue;
+    const int j = idx / a.A, ia = idx % a.A;
+    const double omgs = a.omgs[j];
+    Kin q;
+    kin_forward(sL, omgs, a.costh[ia], q);
+    IonOut io;
+    ion_forward(sL, a.nI, a.zt, q, io);
+    double I, dI;
+    pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.dv, I, dI);
+    int i_f; double t_f, sl_f;
+    const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);   // form_factor.py:376
+    const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
+    const double dfe = d0 + t_f * (d1 - d0);  // form_factor.py:377 (clamped: t_f in {0,1} picks the edge value)
+    const double chiEr = -q.ikl2 * I;          // form_factor.py:385-386
+    const double chiEi = kPi * q.ikl2 * dfe;   // form_factor.py:381
+    Asm s;
+    const double P = assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
+    const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
+    a.ff[pidx] = P;
+    a.sI[pidx] = I;
+    a.sdI[pidx] = dI;
+  }
+}
+
+// modl[b][j] = jmul[j] * sum_a w_a * mean_g ff[b][g][j][a]   (generate_spectra.py:164-165, 193, 197, 210-216)
+__global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, const double* wts, const double* jmul, int G,
+                                                          int W, int A, long long total, double* modl) {
+  long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const long long b = t / W;
+  const int j = (int)(t % W);
+  double s = 0.0;
+  for (int g = 0; g < G; g++) {
+    const double* row = ff + ((b * G + g) * (long long)W + j) * A;
+    for (int ia = 0; ia < A; ia++) s += row[ia] * wts[ia];
+  }
+  modl[t] = jmul[j] * s / (double)G;
+}
+
+// ---- backward: poles --------------------------------------------------------------------------------------
+template <int R, typename T>
+__global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs a) {
+  __shared__ LG sL;
+  __shared__ double sred[kLGDoubles * (kThreads / 32)];
+  const int tile = blockIdx.x % a.ntiles;
+  const long long bg = blockIdx.x / a.ntiles;
+  const int g = (int)(bg % a.G);
+  const long long b = bg / a.G;
+  if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
+  __syncthreads();
+  const T* fe = static_cast<const T*>(a.fe) + b * a.V;
+  const int WA = a.W * a.A;
+  const double zM = a.v0 + (double)(a.nodes - 1) * a.dv;
+  LG Lb;
+  lg_zero(Lb);
+  for (int r = 0; r < R; r++) {
+    const int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    if (idx >= WA) continue;
+    const int j = idx / a.A, ia = idx % a.A;
+    const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
+    double Pbar = 0.0;
+    if (a.modl_bar) Pbar += a.modl_bar[b * a.W + j] * a.jmul[j] * a.wts[ia] / (double)a.G;
+    if (a.ff_bar) Pbar += a.ff_bar[pidx];
+    const double omgs = a.omgs[j], cth = a.costh[ia];
+    Kin q;
+    kin_forward(sL, omgs, cth, q);
+    IonOut io;
+    ion_forward(sL, a.nI, a.zt, q, io);
+    const double I = a.sI[pidx], dI = a.sdI[pidx];
+    int i_f; double t_f, sl_f;
+    const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);
+    const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
+    const bool clamped = (q.xie <= a.v0) || (q.xie >= a.v0 + (a.V - 1) * a.dv) || !(q.xie == q.xie);
+    const double dfe = d0 + t_f * (d1 - d0);
+    const double sl_d = clamped ? 0.0 : (d1 - d0) / a.dv;
+    const double chiEr = -q.ikl2 * I, chiEi = kPi * q.ikl2 * dfe;
+    Asm s;
+    assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
+    PointBar pb;
+    KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    assemble_backward(sL, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
+    // chi_e provider reverse (form_factor.py:376-386)
+    kb.ikl2 += -I * pb.chiEr + kPi * dfe * pb.chiEi;
+    const double Ibar = -q.ikl2 * pb.chiEr;
+    const double dfe_bar = kPi * q.ikl2 * pb.chiEi;
+    kb.xie += Ibar * dI + dfe_bar * sl_d + pb.fphi * sl_f;
+    if (pb.fphi != 0.0) {
+      atomicAdd(&a.accfe[b * a.V + i_f], (1.0 - t_f) * pb.fphi);
+      atomicAdd(&a.accfe[b * a.V + i_f + 1], t_f * pb.fphi);
+    }
+    if (dfe_bar != 0.0) {
+      atomicAdd(&a.accdf[b * a.V + i_f], (1.0 - t_f) * dfe_bar);
+      atomicAdd(&a.accdf[b * a.V + i_f + 1], t_f * dfe_bar);
+    }
+    // endpoint terms of I:  dI/dp0 = -1 - ln|g0|,  dI/dpM = 1 + ln|gM|
+    const double gg0 = a.v0 - q.xie, ggM = zM - q.xie;
+    const double l0 = log(fmax(fabs(gg0), 1e-300)), lM = log(fmax(fabs(ggM), 1e-300));
+    atomicAdd(&a.pendbar[2 * b], Ibar * (-1.0 - l0));
+    atomicAdd(&a.pendbar[2 * b + 1], Ibar * (1.0 + lM));
+    kin_backward(sL, omgs, cth, q, kb, Lb);
+    float u0, nd;
+    pole_split(q.xie, a.v0, a.dv, a.nodes, u0, nd);
+    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = make_float4(u0, nd, (float)Ibar, 0.f);
+  }
+  double vals[kLGDoubles];
+  store_lg(vals, Lb);
+  block_accumulate<kThreads / 32>(vals, kLGDoubles, sred, a.lgbar + bg * kLGDoubles);
+}
+
+// ---- backward: finish ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_direct_bwd_finish(const DirectArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* spb = reinterpret_cast<double*>(smem_raw);  // pbar[V]
+  const long long b = blockIdx.x;
+  const int V = a.V, M = a.nodes - 1;
+  const double* Dbar = a.Dbar + b * a.npad;
+  const double ih = 1.0 / a.dv;
+  for (int i = threadIdx.x; i < V; i += kThreads) {
+    double pb = a.accdf[b * V + i];
+    if (i <= M) {
+      double t = 0.0;
+      if (i >= 1) t += Dbar[i - 1];
+      t -= Dbar[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
+      if (i + 1 <= M) t += Dbar[i + 1];
+      pb += t * ih;
+      if (i == 0) pb += a.pendbar[2 * b];
+      if (i == M) pb += a.pendbar[2 * b + 1];
+    }
+    spb[i] = pb;
+  }
+  __syncthreads();
+  T* fe_bar = static_cast<T*>(a.fe_bar) + b * V;
+  for (int k = threadIdx.x; k < V; k += kThreads) {
+    double fb = a.accfe[b * V + k];
+    // f_k enters p_{k-1} (+), p_{k+1} (-), and p_k at the two ends
+    if (k >= 1) fb += spb[k - 1] * ((k - 1 == 0) ? ih : 0.5 * ih);
+    if (k <= V - 2) fb -= spb[k + 1] * ((k + 1 == V - 1) ? ih : 0.5 * ih);
+    if (k == 0) fb -= spb[0] * ih;
+    if (k == V - 1) fb += spb[V - 1] * ih;
+    fe_bar[k] = (T)fb;
+  }
+  if (threadIdx.x == 0) {
+    double* pbar = a.params_bar + b * a.NP;
+    for (int k = 0; k < a.NP; k++) pbar[k] = 0.0;
+    for (int g = 0; g < a.G; g++) {
+      LG Lb;
+      load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
+      lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+    }
+  }
+}
+
+void fill_static(const tsff_ctx* c, DirectArgs& a) {
+  a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = c->V; a.NP = c->NP;
+  a.nodes = c->pv_nodes; a.npad = c->pv_npad;
+  a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;
+  a.omgs = c->omgs; a.costh = c->costh; a.wts = c->wts; a.jmul = c->jmul; a.zt = c->zt;
+}
+
+template <typename T>
+int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, double* modl_out, double* ff_out,
+                 void* saved, void* ws, cudaStream_t st) {
+  const DirectLayout L = direct_layout(c, B);
+  char* sv = static_cast<char*>(saved);
+  char* w = static_cast<char*>(ws);
+  DirectArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_static(c, a);
+  a.params = params; a.fe = fe;
+  a.lg = (double*)(sv + L.s_lg); a.sI = (double*)(sv + L.s_I); a.sdI = (double*)(sv + L.s_dI);
+  a.D = (float*)(w + L.w_D); a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
+  a.pend = (double*)(w + L.w_pend);
+  a.ff = ff_out ? ff_out : (double*)(w + L.w_ff);
+  k_direct_prep<T><<<(unsigned)B, kThreads, 0, st>>>(a);
+  TSFF_LAUNCH_OK("k_direct_prep");
+  const int WA = c->W * c->A;
+  const size_t smem = (size_t)c->pv_npad * 4;
+  // poles per thread: 2 while the grid still fills the device, else 1
+  const long long tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
+  const bool useR2 = (long long)B * c->G * tiles2 >= 2LL * c->sm_count;
+  if (c->pv_precision == TSFF_PV_FP64) {
+    a.ntiles = (WA + kThreads - 1) / kThreads;
+    k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
+  } else if (useR2) {
+    a.ntiles = (int)tiles2;
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_fwd<2, T, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_direct_fwd<2, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
+  } else {
+    a.ntiles = (WA + kThreads - 1) / kThreads;
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_fwd<1, T, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_direct_fwd<1, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
+  }
+  TSFF_LAUNCH_OK("k_direct_fwd");
+  if (modl_out) {
+    const long long total = (long long)B * c->W;
+    k_reduce_modl<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(a.ff, c->wts, c->jmul, c->G, c->W, c->A,
+                                                                                     total, modl_out);
+    TSFF_LAUNCH_OK("k_reduce_modl");
+  }
+  return TSFF_OK;
+}
+
+template <typename T>
+int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, const void* saved, const double* modl_bar,
+                 const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+  const DirectLayout L = direct_layout(c, B);
+  const char* sv = static_cast<const char*>(saved);
+  char* w = static_cast<char*>(ws);
+  DirectArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_static(c, a);
+  a.params = params; a.fe = fe;
+  a.lg = (double*)(sv + L.s_lg); a.sI = (double*)(sv + L.s_I); a.sdI = (double*)(sv + L.s_dI);
+  a.modl_bar = modl_bar; a.ff_bar = ff_bar;
+  a.desc = (float4*)(w + L.w_desc); a.accfe = (double*)(w + L.w_accfe); a.accdf = (double*)(w + L.w_accdf);
+  a.pendbar = (double*)(w + L.w_pendbar); a.Dbar = (double*)(w + L.w_Dbar); a.lgbar = (double*)(w + L.w_lgbar);
+  a.params_bar = params_bar; a.fe_bar = fe_bar;
+  TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
+  const int WA = c->W * c->A;
+  constexpr int RB = 4;
+  a.ntiles = (WA + RB * kThreads - 1) / (RB * kThreads);
+  k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
+  TSFF_LAUNCH_OK("k_direct_bwd_poles");
+  PvNodesArgs n;
+  n.desc = a.desc; n.P = c->G * WA; n.npad = c->pv_npad; n.h = (float)c->dv; n.Dbar = a.Dbar;
+  const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
+  if ((long long)B * tiles4 >= 2LL * c->sm_count) {
+    n.ntiles = (int)tiles4;
+    k_pv_nodes<4><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+  } else {
+    n.ntiles = (c->pv_npad + kPvThreads - 1) / kPvThreads;
+    k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+  }
+  TSFF_LAUNCH_OK("k_pv_nodes");
+  const size_t smem = (size_t)c->V * 8;
+  TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_bwd_finish<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_direct_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);
+  TSFF_LAUNCH_OK("k_direct_bwd_finish");
+  return TSFF_OK;
+}
+
+}  // namespace
+
+namespace tsff {
+size_t direct_saved_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B).saved_bytes; }
+size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B).ws_bytes; }
+
+int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
+               void* saved, void* ws, cudaStream_t st) {
+  if ((size_t)c->pv_npad * 4 > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
+                              : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
+}
+int direct_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
+               const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+  if ((size_t)c->V * 8 > 200 * 1024) { set_error("V=%d too large", c->V); return TSFF_E_INVALID; }
+  return fe_dtype == TSFF_F32 ? direct_bwd_t<float>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
+                              : direct_bwd_t<double>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
+}
+}  // namespace tsff

@@ -1,0 +1,385 @@
+// tsff_math.cuh -- per-lineout and per-(omega,angle) arithmetic of the Thomson-scattering form factor,
+// forward and hand-written adjoint, shared by all kernels.  FP64 throughout (the per-omega
+// assembly must stay in double; only the O(P*V) principal-value sums run in FP32, see tsff_pv.cuh).
+//
+// Reference being restated (ergodicio/tsadar): tsadar/core/physics/form_factor.py:182-296 (1V),
+// :349-388 (calc_chi_vals), ratintn.py:4-52.  Every function names the lines it follows.
+//
+// The functions are __host__ __device__ so that tests/hostsim can execute exactly this arithmetic on
+// the CPU against the oracle's autograd; the product only ever runs them inside CUDA kernels.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TSFF_HD __host__ __device__ __forceinline__
+#else
+#define TSFF_HD inline
+struct float4 { float x, y, z, w; };  // host-only stand-in (tests/hostsim)
+#endif
+
+#define TSFF_MAX_IONS 4
+
+namespace tsff {
+
+// form_factor.py:123-125, 207-209
+constexpr double kC = 2.99792458e10;
+constexpr double kMe = 510.9896 / (kC * kC);
+constexpr double kMp = kMe * 1836.1;
+constexpr double kRe = 2.8179e-13;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kCst2 = 4.0 * kPi * kC * kC * kRe;  // constants^2 = 4 pi Esq / Me, Esq = Me C^2 re
+constexpr double kOmgLNum = 2.0 * kPi * 1e7 * kC;
+constexpr double kLn2 = 0.693147180559945309417;
+constexpr double kInvSqrt2Pi = 0.398942280401432677940;
+
+// parameter block layout, one row per lineout (include/tsff.h documents the same indices)
+enum ParamIdx { P_TE = 0, P_NE, P_LAM, P_VA, P_UD, P_NE_GRAD, P_TE_GRAD, P_AMP1, P_AMP2, P_AMP3, P_ION0 };
+enum IonIdx { ION_A = 0, ION_Z, ION_TI, ION_FRACT, ION_STRIDE };
+
+// per (lineout, gradient point) scalars
+struct LG {
+  double ne_g, omgL, omgpe2, kL, vTe, Va6, ud6;
+  double c_kldi[TSFF_MAX_IONS], inv_s2vTi[TSFF_MAX_IONS], ioncf[TSFF_MAX_IONS];
+};
+
+TSFF_HD void lg_zero(LG& b) {
+  b.ne_g = b.omgL = b.omgpe2 = b.kL = b.vTe = b.Va6 = b.ud6 = 0.0;
+  for (int i = 0; i < TSFF_MAX_IONS; i++) b.c_kldi[i] = b.inv_s2vTi[i] = b.ioncf[i] = 0.0;
+}
+constexpr int kLGDoubles = 7 + 3 * TSFF_MAX_IONS;
+
+TSFF_HD double grad_factor(double grad, int g, int G) {
+  // jnp.linspace(1 - grad/200, 1 + grad/200, G)[g]  (form_factor.py:182-195); G == 1 -> lower end
+  double lo = 1.0 - grad / 200.0;
+  if (G <= 1) return lo;
+  return lo + (double)g * ((grad / 100.0) / (double)(G - 1));
+}
+TSFF_HD double grad_factor_d(int g, int G) {  // d factor / d grad
+  if (G <= 1) return -1.0 / 200.0;
+  return -1.0 / 200.0 + (double)g / (100.0 * (double)(G - 1));
+}
+
+// form_factor.py:182-243 (lineout-level part)
+TSFF_HD void lg_forward(const double* p, int nI, int g, int G, double lam_shift, LG& o) {
+  double ne_g = 1.0e20 * p[P_NE] * grad_factor(p[P_NE_GRAD], g, G);
+  double Te_g = p[P_TE] * grad_factor(p[P_TE_GRAD], g, G);
+  o.ne_g = ne_g;
+  o.omgL = kOmgLNum / (p[P_LAM] + lam_shift);
+  o.omgpe2 = kCst2 * ne_g;
+  o.kL = sqrt(o.omgL * o.omgL - o.omgpe2) / kC;
+  o.vTe = sqrt(Te_g / kMe);
+  o.Va6 = p[P_VA] * 1e6;
+  o.ud6 = p[P_UD] * 1e6;
+  double Zbar = 0.0;
+  for (int i = 0; i < nI; i++) Zbar += p[P_ION0 + i * ION_STRIDE + ION_Z] * p[P_ION0 + i * ION_STRIDE + ION_FRACT];
+  for (int i = 0; i < nI; i++) {
+    const double* q = p + P_ION0 + i * ION_STRIDE;
+    double Mi = q[ION_A] * kMp;
+    double ni = q[ION_FRACT] * ne_g / Zbar;
+    double omgpi = sqrt(kCst2) * q[ION_Z] * sqrt(ni * kMe / Mi);
+    double vTi = sqrt(q[ION_TI] / Mi);
+    o.c_kldi[i] = vTi / omgpi;
+    o.inv_s2vTi[i] = 1.0 / (1.4142135623730951 * vTi);
+    o.ioncf[i] = q[ION_FRACT] * q[ION_Z] * q[ION_Z] / (Zbar * vTi);
+  }
+}
+
+// adjoint of lg_forward: accumulates into pbar[NP]
+TSFF_HD void lg_backward(const double* p, int nI, int g, int G, double lam_shift, const LG& b, double* pbar) {
+  double fne = grad_factor(p[P_NE_GRAD], g, G), fTe = grad_factor(p[P_TE_GRAD], g, G);
+  double ne_g = 1.0e20 * p[P_NE] * fne;
+  double Te_g = p[P_TE] * fTe;
+  double lamL = p[P_LAM] + lam_shift;
+  double omgL = kOmgLNum / lamL;
+  double omgpe2 = kCst2 * ne_g;
+  double kLC = sqrt(omgL * omgL - omgpe2);  // kL * C
+  double vTe = sqrt(Te_g / kMe);
+  double ne_g_bar = b.ne_g, omgL_bar = b.omgL, omgpe2_bar = b.omgpe2, Te_g_bar = 0.0;
+  // kL = sqrt(omgL^2 - omgpe2)/C
+  omgL_bar += b.kL * omgL / (kLC * kC);
+  omgpe2_bar += -b.kL / (2.0 * kLC * kC);
+  // vTe = sqrt(Te_g/Me)
+  Te_g_bar += b.vTe / (2.0 * vTe * kMe);
+  pbar[P_VA] += b.Va6 * 1e6;
+  pbar[P_UD] += b.ud6 * 1e6;
+  // ions
+  double Zbar = 0.0;
+  for (int i = 0; i < nI; i++) Zbar += p[P_ION0 + i * ION_STRIDE + ION_Z] * p[P_ION0 + i * ION_STRIDE + ION_FRACT];
+  double Zbar_bar = 0.0;
+  for (int i = 0; i < nI; i++) {
+    const double* q = p + P_ION0 + i * ION_STRIDE;
+    double* qb = pbar + P_ION0 + i * ION_STRIDE;
+    double Mi = q[ION_A] * kMp;
+    double ni = q[ION_FRACT] * ne_g / Zbar;
+    double sq = sqrt(ni * kMe / Mi);
+    double omgpi = sqrt(kCst2) * q[ION_Z] * sq;
+    double vTi = sqrt(q[ION_TI] / Mi);
+    double vTi_bar = 0.0, omgpi_bar = 0.0;
+    // c_kldi = vTi/omgpi
+    vTi_bar += b.c_kldi[i] / omgpi;
+    omgpi_bar += -b.c_kldi[i] * vTi / (omgpi * omgpi);
+    // inv_s2vTi = 1/(sqrt2 vTi)
+    vTi_bar += -b.inv_s2vTi[i] / (1.4142135623730951 * vTi * vTi);
+    // ioncf = fract Z^2 / (Zbar vTi)
+    double ioncf = q[ION_FRACT] * q[ION_Z] * q[ION_Z] / (Zbar * vTi);
+    qb[ION_FRACT] += b.ioncf[i] * ioncf / q[ION_FRACT];
+    qb[ION_Z] += b.ioncf[i] * 2.0 * ioncf / q[ION_Z];
+    Zbar_bar += -b.ioncf[i] * ioncf / Zbar;
+    vTi_bar += -b.ioncf[i] * ioncf / vTi;
+    // vTi = sqrt(Ti/Mi)
+    qb[ION_TI] += vTi_bar / (2.0 * vTi * Mi);
+    // omgpi = cst Z sqrt(ni Me/Mi)
+    qb[ION_Z] += omgpi_bar * omgpi / q[ION_Z];
+    double ni_bar = omgpi_bar * omgpi / (2.0 * ni);
+    // ni = fract ne_g / Zbar
+    qb[ION_FRACT] += ni_bar * ne_g / Zbar;
+    ne_g_bar += ni_bar * q[ION_FRACT] / Zbar;
+    Zbar_bar += -ni_bar * ni / Zbar;
+  }
+  for (int i = 0; i < nI; i++) {
+    const double* q = p + P_ION0 + i * ION_STRIDE;
+    double* qb = pbar + P_ION0 + i * ION_STRIDE;
+    qb[ION_Z] += Zbar_bar * q[ION_FRACT];
+    qb[ION_FRACT] += Zbar_bar * q[ION_Z];
+  }
+  // omgpe2 = cst2 ne_g ; omgL = num/lamL
+  ne_g_bar += omgpe2_bar * kCst2;
+  pbar[P_LAM] += -omgL_bar * omgL / lamL;
+  // ne_g = 1e20 ne fne ; Te_g = Te fTe
+  pbar[P_NE] += ne_g_bar * 1.0e20 * fne;
+  pbar[P_NE_GRAD] += ne_g_bar * 1.0e20 * p[P_NE] * grad_factor_d(g, G);
+  pbar[P_TE] += Te_g_bar * fTe;
+  pbar[P_TE_GRAD] += Te_g_bar * p[P_TE] * grad_factor_d(g, G);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Z' table lookup: jnp.interp(xii, xi2, Zpi[0], left=xii**-2, right=xii**-2), imag with 0 fills
+// (form_factor.py:247-248).  xi2 = arange(-8.2, 8.2, 0.01) is uniform; zr/zi hold Zpi rows.
+// Returns values and d/dxii.
+// ------------------------------------------------------------------------------------------------
+struct ZTab {
+  const double* zr;
+  const double* zi;
+  int n;        // 1640
+  double x0;    // -8.2
+  double h;     // 0.01
+  double xlast; // xi2[n-1] as computed by arange
+};
+
+TSFF_HD void zprime_lerp(const ZTab& z, double x, double& zr, double& zi, double& dzr, double& dzi) {
+  if (x < z.x0 || x > z.xlast) {
+    double x2 = x * x;
+    zr = 1.0 / x2;
+    dzr = -2.0 / (x2 * x);
+    zi = 0.0;
+    dzi = 0.0;
+    return;
+  }
+  double u = (x - z.x0) / z.h;
+  int i = (int)u;
+  if (i > z.n - 2) i = z.n - 2;
+  if (i < 0) i = 0;
+  double t = u - (double)i;
+  double r0 = z.zr[i], r1 = z.zr[i + 1], i0 = z.zi[i], i1 = z.zi[i + 1];
+  zr = r0 + t * (r1 - r0);
+  zi = i0 + t * (i1 - i0);
+  dzr = (r1 - r0) / z.h;
+  dzi = (i1 - i0) / z.h;
+}
+
+// edge-clamped linear interpolation on a uniform grid (jnp.interp default; form_factor.py:270,376-377)
+// returns value; idx/t/slope for the adjoint (slope = 0 and weights collapse on the edge when clamped)
+template <typename T>
+TSFF_HD double lerp_uniform(const T* f, int n, double x0, double h, double x, int& i, double& t, double& slope) {
+  double u = (x - x0) / h;
+  if (!(u > 0.0)) {  // left clamp (also NaN)
+    i = 0; t = 0.0; slope = 0.0;
+    return (double)f[0];
+  }
+  if (u >= (double)(n - 1)) {
+    i = n - 2; t = 1.0; slope = 0.0;
+    return (double)f[n - 1];
+  }
+  i = (int)u;
+  t = u - (double)i;
+  double a = (double)f[i], b = (double)f[i + 1];
+  slope = (b - a) / h;
+  return a + t * (b - a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// point kinematics (form_factor.py:215-228, 253)
+// ------------------------------------------------------------------------------------------------
+struct Kin {
+  double ks, k2, k, omgdop, w, xie, ikl2;
+};
+
+TSFF_HD void kin_forward(const LG& L, double omgs, double cth, Kin& q) {
+  q.ks = sqrt(omgs * omgs - L.omgpe2) / kC;
+  q.k2 = q.ks * q.ks + L.kL * L.kL - 2.0 * q.ks * L.kL * cth;
+  q.k = sqrt(q.k2);
+  q.omgdop = omgs - L.omgL - q.k * L.Va6;
+  q.w = q.omgdop / q.k;
+  q.xie = (q.w - L.ud6) / L.vTe;
+  q.ikl2 = L.omgpe2 / (L.vTe * L.vTe * q.k2);
+}
+
+// ion susceptibility (form_factor.py:231-249) -> chiI, plus the ion-feature sum  sum_i ioncf_i exp(-xii^2)
+struct IonOut {
+  double chiIr, chiIi, sion;
+};
+
+TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonOut& o) {
+  o.chiIr = o.chiIi = o.sion = 0.0;
+  for (int i = 0; i < nI; i++) {
+    double xii = L.inv_s2vTi[i] * q.w;
+    double ikldi2 = 1.0 / (L.c_kldi[i] * L.c_kldi[i] * q.k2);
+    double zr, zi, dzr, dzi;
+    zprime_lerp(zt, xii, zr, zi, dzr, dzi);
+    o.chiIr += -0.5 * ikldi2 * zr;
+    o.chiIi += -0.5 * ikldi2 * zi;
+    o.sion += L.ioncf[i] * exp(-xii * xii);
+  }
+}
+
+// spectral density assembly (form_factor.py:273-296): returns PsLam
+struct Asm {
+  double er, ei, eps2, ce2, a1, Sion, Sele, dop, cP, P;
+};
+
+TSFF_HD double assemble_forward(const LG& L, const Kin& q, const IonOut& io, double chiEr, double chiEi, double fphi,
+                                double omgs, Asm& s) {
+  s.er = 1.0 + chiEr + io.chiIr;
+  s.ei = chiEi + io.chiIi;
+  s.eps2 = s.er * s.er + s.ei * s.ei;
+  s.ce2 = chiEr * chiEr + chiEi * chiEi;
+  s.a1 = (1.0 + io.chiIr) * (1.0 + io.chiIr) + io.chiIi * io.chiIi;
+  s.Sion = io.sion * s.ce2 * kInvSqrt2Pi / (q.k * s.eps2);
+  s.Sele = s.a1 * fphi / (q.k * L.vTe * s.eps2);
+  s.dop = 1.0 + 2.0 * q.omgdop / L.omgL;
+  s.cP = kRe * kRe * omgs * omgs / (2.0 * kPi * kC);  // re^2 * 2 pi C / lams^2, lams = 2 pi C / omgs
+  s.P = (s.Sion + s.Sele) * s.dop * L.ne_g * s.cP;
+  return s.P;
+}
+
+// adjoints produced by the assembly + ion + kinematics reverse sweep for one point
+struct PointBar {
+  double chiEr, chiEi, fphi;  // cotangents handed to the chi_e provider
+};
+
+// Reverse of assemble_forward and ion_forward down to (chiE, fphi, kinematic scalars).  `Pbar` is the
+// cotangent of PsLam.  Kinematic cotangents are accumulated in kb (k, k2, omgdop, w) and LG cotangents in Lb.
+struct KinBar {
+  double k, k2, omgdop, w, xie, ikl2;
+};
+
+TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q, const IonOut& io, double chiEr,
+                               double chiEi, double fphi, const Asm& s, double Pbar, PointBar& pb, KinBar& kb,
+                               LG& Lb) {
+  double Ssum = s.Sion + s.Sele;
+  double Ssum_bar = Pbar * s.dop * L.ne_g * s.cP;
+  double dop_bar = Pbar * Ssum * L.ne_g * s.cP;
+  Lb.ne_g += Pbar * Ssum * s.dop * s.cP;
+  kb.omgdop += dop_bar * 2.0 / L.omgL;
+  Lb.omgL += -dop_bar * 2.0 * q.omgdop / (L.omgL * L.omgL);
+  // Sion = sion ce2 c / (k eps2)
+  double inv_keps = 1.0 / (q.k * s.eps2);
+  double sion_bar = Ssum_bar * s.ce2 * kInvSqrt2Pi * inv_keps;
+  double ce2_bar = Ssum_bar * io.sion * kInvSqrt2Pi * inv_keps;
+  double eps2_bar = -Ssum_bar * Ssum / s.eps2;
+  kb.k += -Ssum_bar * Ssum / q.k;
+  // Sele = a1 fphi / (k vTe eps2)
+  double a1_bar = Ssum_bar * fphi * inv_keps / L.vTe;
+  pb.fphi = Ssum_bar * s.a1 * inv_keps / L.vTe;
+  Lb.vTe += -Ssum_bar * s.Sele / L.vTe;
+  double er_bar = 2.0 * s.er * eps2_bar, ei_bar = 2.0 * s.ei * eps2_bar;
+  pb.chiEr = er_bar + 2.0 * chiEr * ce2_bar;
+  pb.chiEi = ei_bar + 2.0 * chiEi * ce2_bar;
+  double chiIr_bar = er_bar + 2.0 * (1.0 + io.chiIr) * a1_bar;
+  double chiIi_bar = ei_bar + 2.0 * io.chiIi * a1_bar;
+  for (int i = 0; i < nI; i++) {
+    double xii = L.inv_s2vTi[i] * q.w;
+    double ikldi2 = 1.0 / (L.c_kldi[i] * L.c_kldi[i] * q.k2);
+    double zr, zi, dzr, dzi;
+    zprime_lerp(zt, xii, zr, zi, dzr, dzi);
+    double E = exp(-xii * xii);
+    Lb.ioncf[i] += sion_bar * E;
+    double xii_bar = sion_bar * L.ioncf[i] * E * (-2.0 * xii);
+    double ikldi2_bar = -0.5 * (zr * chiIr_bar + zi * chiIi_bar);
+    xii_bar += -0.5 * ikldi2 * (dzr * chiIr_bar + dzi * chiIi_bar);
+    Lb.c_kldi[i] += ikldi2_bar * (-2.0 * ikldi2 / L.c_kldi[i]);
+    kb.k2 += -ikldi2_bar * ikldi2 / q.k2;
+    Lb.inv_s2vTi[i] += xii_bar * q.w;
+    kb.w += xii_bar * L.inv_s2vTi[i];
+  }
+}
+
+// reverse of kin_forward: consumes kb (incl. xie, ikl2 cotangents), accumulates LG cotangents
+TSFF_HD void kin_backward(const LG& L, double omgs, double cth, const Kin& q, KinBar kb, LG& Lb) {
+  // ikl2 = omgpe2 / (vTe^2 k2)
+  Lb.omgpe2 += kb.ikl2 * q.ikl2 / L.omgpe2;
+  Lb.vTe += -2.0 * kb.ikl2 * q.ikl2 / L.vTe;
+  kb.k2 += -kb.ikl2 * q.ikl2 / q.k2;
+  // xie = (w - ud6)/vTe
+  kb.w += kb.xie / L.vTe;
+  Lb.ud6 += -kb.xie / L.vTe;
+  Lb.vTe += -kb.xie * q.xie / L.vTe;
+  // w = omgdop / k
+  kb.omgdop += kb.w / q.k;
+  kb.k += -kb.w * q.w / q.k;
+  // omgdop = omgs - omgL - k Va6
+  Lb.omgL += -kb.omgdop;
+  kb.k += -kb.omgdop * L.Va6;
+  Lb.Va6 += -kb.omgdop * q.k;
+  // k = sqrt(k2)
+  kb.k2 += kb.k / (2.0 * q.k);
+  // k2 = ks^2 + kL^2 - 2 ks kL cth
+  double ks_bar = kb.k2 * (2.0 * q.ks - 2.0 * L.kL * cth);
+  Lb.kL += kb.k2 * (2.0 * L.kL - 2.0 * q.ks * cth);
+  // ks = sqrt(omgs^2 - omgpe2)/C
+  Lb.omgpe2 += -ks_bar / (2.0 * kC * kC * q.ks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// interpax cubic Hermite on a uniform grid with pre-computed node slopes (form_factor.py:256,263;
+// SURVEY.md A-note 1).  lnf[V], slope[V]; returns H(x) (or `fill` outside [x0, x_last]) and the pieces
+// for the adjoint.
+// ------------------------------------------------------------------------------------------------
+struct Herm {
+  int i;         // right node of the cell (1..V-1); 0 when outside
+  double t;      // (x - x[i-1]) / h
+  double dHdx;   // derivative wrt x (0 outside)
+  bool inside;
+};
+
+TSFF_HD double hermite_uniform(const double* lnf, const double* slope, int V, double x0, double h, double x,
+                               double fill, Herm& o) {
+  double xlast = x0 + (double)(V - 1) * h;
+  if (x < x0 || x > xlast || !(x == x)) {
+    o.i = 0; o.t = 0.0; o.dHdx = 0.0; o.inside = false;
+    return fill;
+  }
+  // searchsorted(x, xq, 'right') clipped to [1, V-1]
+  int i = (int)floor((x - x0) / h) + 1;
+  if (i < 1) i = 1;
+  if (i > V - 1) i = V - 1;
+  double t = (x - (x0 + (double)(i - 1) * h)) / h;
+  double f0 = lnf[i - 1], f1 = lnf[i], m0 = slope[i - 1] * h, m1 = slope[i] * h;
+  double c2 = -3.0 * f0 + 3.0 * f1 - 2.0 * m0 - m1;
+  double c3 = 2.0 * f0 - 2.0 * f1 + m0 + m1;
+  o.i = i; o.t = t; o.inside = true;
+  o.dHdx = (m0 + t * (2.0 * c2 + 3.0 * c3 * t)) / h;
+  return f0 + t * (m0 + t * (c2 + c3 * t));
+}
+
+// adjoint weights of H wrt (lnf[i-1], lnf[i], slope[i-1], slope[i])
+TSFF_HD void hermite_weights(double t, double h, double& wf0, double& wf1, double& wm0, double& wm1) {
+  double t2 = t * t, t3 = t2 * t;
+  wf0 = 1.0 - 3.0 * t2 + 2.0 * t3;
+  wf1 = 3.0 * t2 - 2.0 * t3;
+  wm0 = (t - 2.0 * t2 + t3) * h;
+  wm1 = (-t2 + t3) * h;
+}
+
+}  // namespace tsff

@@ -1,0 +1,540 @@
+// tsff_table.cu -- TSFF_MODE_TABLE: the reference's 1V FormFactor.__call__ (form_factor.py:163-298).
+//
+//   f(v) --log, cubic Hermite--> ratmod on xi1 (1024) --gradient--> ratdf --ratintn--> PV table T on xi2 (1640)
+//   per (omega, angle): kinematics, chi_i from Z', fphi = exp(cubic(log f))(xi_e), Im chi_e from the forward
+//   difference of fphi along omega, Re chi_e = -lerp(T)(xi_e)/(k lambda_De)^2, S(k, omega), angle sum.
+//
+// Kernels
+//   k_table_prep        per lineout (FP64): LG scalars, log f, node slopes, ratmod, ratdf, PV weights D
+//   k_pv_poles          (tsff_pv_kernels.cuh) PV table on the fixed pole grid xi2           [MUFU-bound]
+//   k_table_fwd         per-(omega, angle) assembly in FP64; a warp owns 31 consecutive wavelengths so the forward
+//                       difference along omega is a register shuffle; angle sum in-thread        [FP64-pipe-bound]
+//   k_table_bwd         hand-written reverse of k_table_fwd (30 outputs + 2 halo lanes per warp)
+//   k_table_tbar        per lineout: Tbar -> pole descriptors + endpoint cotangents
+//   k_pv_nodes          adjoint PV sweep -> Dbar                                                [MUFU-bound]
+//   k_table_bwd_finish  per lineout: Dbar -> ratdf_bar -> ratmod_bar -> (log f, slope)_bar -> fe_bar; params_bar
+#include "tsff_pv_kernels.cuh"
+
+using namespace tsff;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct TableLayout {
+  size_t s_lg, s_lnf, s_slope, s_ratmod, s_T, saved_bytes;
+  size_t w_D, w_D64, w_pend, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pendbar, w_lgbar, w_zero_end,
+      ws_bytes;
+};
+
+TableLayout table_layout(const tsff_ctx* c, int64_t B) {
+  TableLayout L;
+  size_t o = 0;
+  L.s_lg = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
+  L.s_lnf = o; o += align_up((size_t)B * c->V * 8);
+  L.s_slope = o; o += align_up((size_t)B * c->V * 8);
+  L.s_ratmod = o; o += align_up((size_t)B * kXi1N * 8);
+  L.s_T = o; o += align_up((size_t)B * kXi2N * 8);
+  L.saved_bytes = o;
+  o = 0;
+  L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
+  L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
+  L.w_pend = o; o += align_up((size_t)B * 2 * 8);
+  L.w_desc = o; o += align_up((size_t)B * kXi2N * 16);
+  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
+  L.w_zero_begin = o;
+  L.w_Tbar = o; o += align_up((size_t)B * kXi2N * 8);
+  L.w_lnfbar = o; o += align_up((size_t)B * c->V * 8);
+  L.w_slopebar = o; o += align_up((size_t)B * c->V * 8);
+  L.w_pendbar = o; o += align_up((size_t)B * 2 * 8);
+  L.w_lgbar = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
+  L.w_zero_end = o;
+  L.ws_bytes = o;
+  return L;
+}
+
+struct TableArgs {
+  int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  double lam_shift, v0, dv, xi1_0, xi1_h, xi2_0, xi2_h;
+  const double *omgs, *costh, *wts, *jmul, *xi2;
+  ZTab zt;
+  const double* params;
+  const void* fe;
+  double *lg, *lnf, *slope, *ratmod, *T;
+  float* D;
+  double* D64;
+  double* pend;
+  double* modl;
+  double* ff;
+  // backward
+  const double* modl_bar;
+  const double* ff_bar;
+  float4* desc;
+  double *Tbar, *lnfbar, *slopebar, *pendbar, *Dbar, *lgbar;
+  double* params_bar;
+  void* fe_bar;
+};
+
+__device__ __forceinline__ void load_lg(const double* src, LG& L) {
+  L.ne_g = src[0]; L.omgL = src[1]; L.omgpe2 = src[2]; L.kL = src[3]; L.vTe = src[4]; L.Va6 = src[5]; L.ud6 = src[6];
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    L.c_kldi[i] = src[7 + i]; L.inv_s2vTi[i] = src[7 + TSFF_MAX_IONS + i]; L.ioncf[i] = src[7 + 2 * TSFF_MAX_IONS + i];
+  }
+}
+__device__ __forceinline__ void store_lg(double* dst, const LG& L) {
+  dst[0] = L.ne_g; dst[1] = L.omgL; dst[2] = L.omgpe2; dst[3] = L.kL; dst[4] = L.vTe; dst[5] = L.Va6; dst[6] = L.ud6;
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    dst[7 + i] = L.c_kldi[i]; dst[7 + TSFF_MAX_IONS + i] = L.inv_s2vTi[i]; dst[7 + 2 * TSFF_MAX_IONS + i] = L.ioncf[i];
+  }
+}
+
+// np.gradient with uniform spacing at node i of an n-array held in shared memory
+__device__ __forceinline__ double grad_sm(const double* f, int n, double ih, int i) {
+  if (i <= 0) return (f[1] - f[0]) * ih;
+  if (i >= n - 1) return (f[n - 1] - f[n - 2]) * ih;
+  return (f[i + 1] - f[i - 1]) * (0.5 * ih);
+}
+
+// ---- prep -------------------------------------------------------------------------------------------------
+// dynamic smem: lnf[V] | slope[V] | ratmod[1024] | ratdf[1024]
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_lnf = reinterpret_cast<double*>(smem_raw);
+  double* s_slope = s_lnf + a.V;
+  double* s_rat = s_slope + a.V;
+  double* s_p = s_rat + kXi1N;
+  const long long b = blockIdx.x;
+  const T* fe = static_cast<const T*>(a.fe) + b * a.V;
+  if (threadIdx.x < a.G) {
+    LG L;
+    lg_zero(L);
+    lg_forward(a.params + b * a.NP, a.nI, threadIdx.x, a.G, a.lam_shift, L);
+    store_lg(a.lg + (b * a.G + threadIdx.x) * kLGDoubles, L);
+  }
+  for (int i = threadIdx.x; i < a.V; i += kThreads) s_lnf[i] = log((double)fe[i]);   // form_factor.py:256,263
+  __syncthreads();
+  const double idv = 1.0 / a.dv;
+  for (int i = threadIdx.x; i < a.V; i += kThreads) {
+    // interpax cubic node slopes: mean of adjacent secants, one-sided at the ends (= np.gradient on a uniform grid)
+    double s = grad_sm(s_lnf, a.V, idv, i);
+    s_slope[i] = s;
+    a.lnf[b * a.V + i] = s_lnf[i];
+    a.slope[b * a.V + i] = s;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < kXi1N; n += kThreads) {
+    Herm hm;
+    double H = hermite_uniform(s_lnf, s_slope, a.V, a.v0, a.dv, a.xi1_0 + (double)n * a.xi1_h, kFillLog, hm);
+    double r = exp(H);                                                                // form_factor.py:263
+    s_rat[n] = r;
+    a.ratmod[b * kXi1N + n] = r;
+  }
+  __syncthreads();
+  const double ih = 1.0 / a.xi1_h;
+  for (int n = threadIdx.x; n < kXi1N; n += kThreads) s_p[n] = grad_sm(s_rat, kXi1N, ih, n);  // form_factor.py:264
+  __syncthreads();
+  const int M = a.nodes - 1;
+  for (int i = threadIdx.x; i < a.npad; i += kThreads) {
+    double d = pv_weight(s_p, M, a.xi1_h, i);
+    a.D[b * a.npad + i] = (float)d;
+    if (a.D64) a.D64[b * a.npad + i] = d;
+  }
+  if (threadIdx.x == 0) {
+    a.pend[2 * b] = s_p[0];
+    a.pend[2 * b + 1] = s_p[M];
+  }
+}
+
+// ---- forward assembly -----------------------------------------------------------------------------------------
+// dynamic smem: lnf[V] | slope[V] | T[1640]
+constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
+
+template <bool WRITE_FF>
+__global__ void __launch_bounds__(kThreads) k_table_fwd(const TableArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_lnf = reinterpret_cast<double*>(smem_raw);
+  double* s_slope = s_lnf + a.V;
+  double* s_T = s_slope + a.V;
+  const int tile = blockIdx.x % a.ntiles;
+  const long long b = blockIdx.x / a.ntiles;
+  for (int i = threadIdx.x; i < a.V; i += kThreads) {
+    s_lnf[i] = a.lnf[b * a.V + i];
+    s_slope[i] = a.slope[b * a.V + i];
+  }
+  for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = (tile * kWarps + wid) * kFwdJ + lane;
+  const int jc = min(j, a.W - 1);
+  const bool out = (lane < kFwdJ) && (j < a.W);
+  const double omgs = a.omgs[jc];
+  double acc = 0.0;
+  for (int g = 0; g < a.G; g++) {
+    LG L;
+    load_lg(a.lg + (b * a.G + g) * kLGDoubles, L);
+    for (int ia = 0; ia < a.A; ia++) {
+      Kin q;
+      kin_forward(L, omgs, a.costh[ia], q);
+      Herm hm;
+      const double fphi = exp(hermite_uniform(s_lnf, s_slope, a.V, a.v0, a.dv, q.xie, kFillLog, hm));  // :256
+      const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
+      const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
+      const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) / (xi_n - q.xie) : 0.0;           // :258-259
+      if (out) {
+        int ip; double tp, slp;
+        const double Tl = lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);               // :270
+        const double chiEr = -q.ikl2 * Tl;                                                                // :271
+        const double chiEi = kPi * q.ikl2 * df;                                                           // :261
+        IonOut io;
+        ion_forward(L, a.nI, a.zt, q, io);
+        Asm s;
+        const double P = assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
+        if (WRITE_FF) a.ff[((b * a.G + g) * (long long)a.W + j) * a.A + ia] = P;
+        acc += a.wts[ia] * P;
+      }
+    }
+  }
+  if (out && a.modl) a.modl[b * a.W + j] = a.jmul[j] * acc / (double)a.G;
+}
+
+// ---- backward assembly ----------------------------------------------------------------------------------------
+constexpr int kBwdJ = 30;  // outputs per warp: lanes 1..30; lane 0 = left halo, lane 31 = right halo
+
+__global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sred[kLGDoubles * kWarps];
+  double* s_lnf = reinterpret_cast<double*>(smem_raw);
+  double* s_slope = s_lnf + a.V;
+  double* s_T = s_slope + a.V;
+  const int tile = blockIdx.x % a.ntiles;
+  const long long b = blockIdx.x / a.ntiles;
+  for (int i = threadIdx.x; i < a.V; i += kThreads) {
+    s_lnf[i] = a.lnf[b * a.V + i];
+    s_slope[i] = a.slope[b * a.V + i];
+  }
+  for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = (tile * kWarps + wid) * kBwdJ - 1 + lane;
+  const bool valid = (j >= 0) && (j < a.W);
+  const int jc = min(max(j, 0), a.W - 1);
+  const bool own = valid && lane >= 1 && lane <= kBwdJ;
+  const double omgs = a.omgs[jc];
+  const double mb = (valid && a.modl_bar) ? a.modl_bar[b * a.W + jc] * a.jmul[jc] / (double)a.G : 0.0;
+  double* Tbar = a.Tbar + b * kXi2N;
+  double* lnfbar = a.lnfbar + b * a.V;
+  double* slopebar = a.slopebar + b * a.V;
+  for (int g = 0; g < a.G; g++) {
+    LG L;
+    load_lg(a.lg + (b * a.G + g) * kLGDoubles, L);
+    LG Lb;
+    lg_zero(Lb);
+    for (int ia = 0; ia < a.A; ia++) {
+      const double cth = a.costh[ia];
+      Kin q;
+      kin_forward(L, omgs, cth, q);
+      Herm hm;
+      const double fphi = exp(hermite_uniform(s_lnf, s_slope, a.V, a.v0, a.dv, q.xie, kFillLog, hm));
+      const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
+      const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
+      const bool has_df = valid && (j + 1 < a.W) && (lane < 31);
+      const double delta = has_df ? (xi_n - q.xie) : 1.0;
+      const double df = has_df ? (fphi_n - fphi) / delta : 0.0;
+      // phase 2: reverse of the assembly at this point (lanes 0..30)
+      double dfbar = 0.0;
+      PointBar pb = {0.0, 0.0, 0.0};
+      KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int ip = 0; double tp = 0.0, slp = 0.0, Tl = 0.0;
+      if (valid && lane < 31) {
+        double Pbar = mb * a.wts[ia];
+        if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
+        Tl = lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);
+        const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
+        IonOut io;
+        ion_forward(L, a.nI, a.zt, q, io);
+        Asm s;
+        assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
+        LG Ltmp;
+        lg_zero(Ltmp);
+        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, own ? Lb : Ltmp);
+        dfbar = has_df ? kPi * q.ikl2 * pb.chiEi : 0.0;
+        kb.ikl2 += -Tl * pb.chiEr + kPi * df * pb.chiEi;
+      }
+      const double dfbar_p = __shfl_up_sync(0xffffffffu, dfbar, 1);
+      const double df_p = __shfl_up_sync(0xffffffffu, df, 1);
+      const double delta_p = __shfl_up_sync(0xffffffffu, delta, 1);
+      if (own) {
+        double fphibar = pb.fphi - dfbar / delta;
+        double xiebar = kb.xie + dfbar * df / delta;
+        if (j >= 1) {
+          fphibar += dfbar_p / delta_p;
+          xiebar -= dfbar_p * df_p / delta_p;
+        }
+        const double Tlbar = -q.ikl2 * pb.chiEr;
+        xiebar += Tlbar * slp;
+        if (Tlbar != 0.0) {
+          atomicAdd(&Tbar[ip], (1.0 - tp) * Tlbar);
+          atomicAdd(&Tbar[ip + 1], tp * Tlbar);
+        }
+        if (hm.inside) {
+          const double Hbar = fphibar * fphi;
+          xiebar += Hbar * hm.dHdx;
+          double wf0, wf1, wm0, wm1;
+          hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
+          atomicAdd(&lnfbar[hm.i - 1], Hbar * wf0);
+          atomicAdd(&lnfbar[hm.i], Hbar * wf1);
+          atomicAdd(&slopebar[hm.i - 1], Hbar * wm0);
+          atomicAdd(&slopebar[hm.i], Hbar * wm1);
+        }
+        kb.xie = xiebar;
+        kin_backward(L, omgs, cth, q, kb, Lb);
+      }
+    }
+    double vals[kLGDoubles];
+    store_lg(vals, Lb);
+    block_accumulate<kWarps>(vals, kLGDoubles, sred, a.lgbar + (b * a.G + g) * kLGDoubles);
+  }
+}
+
+// ---- Tbar -> descriptors + endpoint cotangents -----------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a) {
+  __shared__ double sred[2 * kWarps];
+  const long long b = blockIdx.x;
+  const double zM = a.xi1_0 + (double)(a.nodes - 1) * a.xi1_h;
+  double e0 = 0.0, eM = 0.0;
+  for (int p = threadIdx.x; p < kXi2N; p += kThreads) {
+    const double xi = a.xi2[p];
+    const double tb = a.Tbar[b * kXi2N + p];
+    float u0, nd;
+    pole_split(xi, a.xi1_0, a.xi1_h, a.nodes, u0, nd);
+    a.desc[b * kXi2N + p] = make_float4(u0, nd, (float)tb, 0.f);
+    const double l0 = log(fmax(fabs(a.xi1_0 - xi), 1e-300)), lM = log(fmax(fabs(zM - xi), 1e-300));
+    e0 += tb * (-1.0 - l0);
+    eM += tb * (1.0 + lM);
+  }
+  double vals[2] = {e0, eM};
+  block_accumulate<kWarps>(vals, 2, sred, a.pendbar + 2 * b);
+}
+
+// ---- finish ---------------------------------------------------------------------------------------------------
+// dynamic smem: pb[1024] | hb[1024] | lnfb[V] | slb[V]
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_table_bwd_finish(const TableArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_pb = reinterpret_cast<double*>(smem_raw);
+  double* s_hb = s_pb + kXi1N;
+  double* s_lnfb = s_hb + kXi1N;
+  double* s_slb = s_lnfb + a.V;
+  const long long b = blockIdx.x;
+  const int V = a.V, M = a.nodes - 1;
+  const double* Dbar = a.Dbar + b * a.npad;
+  const double ih = 1.0 / a.xi1_h;
+  // 1. ratdf_bar from Dbar (+ endpoint terms)
+  for (int i = threadIdx.x; i < kXi1N; i += kThreads) {
+    double pb = 0.0;
+    if (i <= M) {
+      double t = 0.0;
+      if (i >= 1) t += Dbar[i - 1];
+      t -= Dbar[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
+      if (i + 1 <= M) t += Dbar[i + 1];
+      pb = t * ih;
+      if (i == 0) pb += a.pendbar[2 * b];
+      if (i == M) pb += a.pendbar[2 * b + 1];
+    }
+    s_pb[i] = pb;
+  }
+  __syncthreads();
+  // 2. ratmod_bar (adjoint of np.gradient) and Hbar_n = ratmod_bar_n * ratmod_n inside the f grid
+  const double xlast = a.v0 + (double)(V - 1) * a.dv;
+  for (int k = threadIdx.x; k < kXi1N; k += kThreads) {
+    double rb = 0.0;
+    if (k >= 1) rb += s_pb[k - 1] * ((k - 1 == 0) ? ih : 0.5 * ih);
+    if (k <= kXi1N - 2) rb -= s_pb[k + 1] * ((k + 1 == kXi1N - 1) ? ih : 0.5 * ih);
+    if (k == 0) rb -= s_pb[0] * ih;
+    if (k == kXi1N - 1) rb += s_pb[kXi1N - 1] * ih;
+    const double x = a.xi1_0 + (double)k * a.xi1_h;
+    const bool inside = !(x < a.v0 || x > xlast);
+    s_hb[k] = inside ? rb * a.ratmod[b * kXi1N + k] : 0.0;
+  }
+  __syncthreads();
+  // 3. gather the Hermite adjoint at the xi1 points onto the f nodes (deterministic, no atomics)
+  for (int k = threadIdx.x; k < V; k += kThreads) {
+    double lf = a.lnfbar[b * V + k], sl = a.slopebar[b * V + k];
+    // xi1 points whose cell [i-1, i] touches node k lie in [v_{k-1}, v_{k+1}]
+    const double xlo = a.v0 + (double)(k - 1) * a.dv, xhi = a.v0 + (double)(k + 1) * a.dv;
+    int nlo = (int)floor((xlo - a.xi1_0) / a.xi1_h) - 1, nhi = (int)ceil((xhi - a.xi1_0) / a.xi1_h) + 1;
+    nlo = max(nlo, 0); nhi = min(nhi, kXi1N - 1);
+    for (int n = nlo; n <= nhi; n++) {
+      const double hb = s_hb[n];
+      if (hb == 0.0) continue;
+      const double x = a.xi1_0 + (double)n * a.xi1_h;
+      int i = (int)floor((x - a.v0) / a.dv) + 1;
+      i = min(max(i, 1), V - 1);
+      if (k != i - 1 && k != i) continue;
+      const double t = (x - (a.v0 + (double)(i - 1) * a.dv)) / a.dv;
+      double wf0, wf1, wm0, wm1;
+      hermite_weights(t, a.dv, wf0, wf1, wm0, wm1);
+      if (k == i - 1) { lf += hb * wf0; sl += hb * wm0; }
+      else            { lf += hb * wf1; sl += hb * wm1; }
+    }
+    s_lnfb[k] = lf;
+    s_slb[k] = sl;
+  }
+  __syncthreads();
+  // 4. slope adjoint (np.gradient stencil on log f), then fe_bar = lnf_bar / fe
+  const double idv = 1.0 / a.dv;
+  const T* fe = static_cast<const T*>(a.fe) + b * V;
+  T* fe_bar = static_cast<T*>(a.fe_bar) + b * V;
+  for (int k = threadIdx.x; k < V; k += kThreads) {
+    double lb = s_lnfb[k];
+    if (k >= 1) lb += s_slb[k - 1] * ((k - 1 == 0) ? idv : 0.5 * idv);
+    if (k <= V - 2) lb -= s_slb[k + 1] * ((k + 1 == V - 1) ? idv : 0.5 * idv);
+    if (k == 0) lb -= s_slb[0] * idv;
+    if (k == V - 1) lb += s_slb[V - 1] * idv;
+    fe_bar[k] = (T)(lb / (double)fe[k]);
+  }
+  if (threadIdx.x == 0) {
+    double* pbar = a.params_bar + b * a.NP;
+    for (int k = 0; k < a.NP; k++) pbar[k] = 0.0;
+    for (int g = 0; g < a.G; g++) {
+      LG Lb;
+      load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
+      lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+    }
+  }
+}
+
+void fill_static(const tsff_ctx* c, TableArgs& a) {
+  a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = c->V; a.NP = c->NP;
+  a.nodes = c->pv_nodes; a.npad = c->pv_npad;
+  a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;
+  a.xi1_0 = c->xi1_0; a.xi1_h = c->xi1_h; a.xi2_0 = c->zt.x0; a.xi2_h = c->zt.h;
+  a.omgs = c->omgs; a.costh = c->costh; a.wts = c->wts; a.jmul = c->jmul; a.xi2 = c->xi2; a.zt = c->zt;
+}
+
+void bind_saved(const TableLayout& L, char* sv, TableArgs& a) {
+  a.lg = (double*)(sv + L.s_lg); a.lnf = (double*)(sv + L.s_lnf); a.slope = (double*)(sv + L.s_slope);
+  a.ratmod = (double*)(sv + L.s_ratmod); a.T = (double*)(sv + L.s_T);
+}
+
+template <typename T>
+int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, double* modl_out, double* ff_out, void* saved,
+                void* ws, cudaStream_t st) {
+  const TableLayout L = table_layout(c, B);
+  char* w = static_cast<char*>(ws);
+  TableArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_static(c, a);
+  bind_saved(L, static_cast<char*>(saved), a);
+  a.params = params; a.fe = fe;
+  a.D = (float*)(w + L.w_D); a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
+  a.pend = (double*)(w + L.w_pend);
+  a.modl = modl_out; a.ff = ff_out;
+  {
+    const size_t smem = (size_t)(2 * c->V + 2 * kXi1N) * 8;
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_prep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_table_prep<T><<<(unsigned)B, kThreads, smem, st>>>(a);
+    TSFF_LAUNCH_OK("k_table_prep");
+  }
+  {
+    PvPolesArgs p;
+    p.D = a.D; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
+    p.z0 = c->xi1_0; p.h = c->xi1_h; p.nodes = c->pv_nodes; p.npad = c->pv_npad; p.P = kXi2N;
+    p.outI = a.T; p.outdI = nullptr;
+    const size_t smem = (size_t)c->pv_npad * 4;
+    if (c->pv_precision == TSFF_PV_FP64) {
+      p.ntiles = (kXi2N + kPvThreads - 1) / kPvThreads;
+      k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
+    } else if ((long long)B * ((kXi2N + 2 * kPvThreads - 1) / (2 * kPvThreads)) >= 2LL * c->sm_count) {
+      p.ntiles = (kXi2N + 2 * kPvThreads - 1) / (2 * kPvThreads);
+      k_pv_poles<2, TSFF_PV_FP32><<<(unsigned)(B * p.ntiles), kPvThreads, smem, st>>>(p);
+    } else {
+      p.ntiles = (kXi2N + kPvThreads - 1) / kPvThreads;
+      k_pv_poles<1, TSFF_PV_FP32><<<(unsigned)(B * p.ntiles), kPvThreads, smem, st>>>(p);
+    }
+    TSFF_LAUNCH_OK("k_pv_poles");
+  }
+  {
+    const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
+    a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
+    if (ff_out) {
+      TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_table_fwd<true><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+    } else {
+      TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_table_fwd<false><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+    }
+    TSFF_LAUNCH_OK("k_table_fwd");
+  }
+  return TSFF_OK;
+}
+
+template <typename T>
+int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, const void* saved, const double* modl_bar,
+                const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+  const TableLayout L = table_layout(c, B);
+  char* w = static_cast<char*>(ws);
+  TableArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_static(c, a);
+  bind_saved(L, const_cast<char*>(static_cast<const char*>(saved)), a);
+  a.params = params; a.fe = fe;
+  a.modl_bar = modl_bar; a.ff_bar = ff_bar;
+  a.desc = (float4*)(w + L.w_desc); a.Dbar = (double*)(w + L.w_Dbar); a.Tbar = (double*)(w + L.w_Tbar);
+  a.lnfbar = (double*)(w + L.w_lnfbar); a.slopebar = (double*)(w + L.w_slopebar); a.pendbar = (double*)(w + L.w_pendbar);
+  a.lgbar = (double*)(w + L.w_lgbar);
+  a.params_bar = params_bar; a.fe_bar = fe_bar;
+  TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
+  {
+    const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
+    a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_table_bwd<<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+    TSFF_LAUNCH_OK("k_table_bwd");
+  }
+  k_table_tbar<<<(unsigned)B, kThreads, 0, st>>>(a);
+  TSFF_LAUNCH_OK("k_table_tbar");
+  {
+    PvNodesArgs n;
+    n.desc = a.desc; n.P = kXi2N; n.npad = c->pv_npad; n.h = (float)c->xi1_h; n.Dbar = a.Dbar;
+    const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
+    if ((long long)B * tiles4 >= 2LL * c->sm_count) {
+      n.ntiles = (int)tiles4;
+      k_pv_nodes<4><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+    } else {
+      n.ntiles = (c->pv_npad + kPvThreads - 1) / kPvThreads;
+      k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+    }
+    TSFF_LAUNCH_OK("k_pv_nodes");
+  }
+  {
+    const size_t smem = (size_t)(2 * kXi1N + 2 * c->V) * 8;
+    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_bwd_finish<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_table_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);
+    TSFF_LAUNCH_OK("k_table_bwd_finish");
+  }
+  return TSFF_OK;
+}
+
+}  // namespace
+
+namespace tsff {
+size_t table_saved_bytes(const tsff_ctx* c, int64_t B) { return table_layout(c, B).saved_bytes; }
+size_t table_ws_bytes(const tsff_ctx* c, int64_t B) { return table_layout(c, B).ws_bytes; }
+
+int table_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
+              void* saved, void* ws, cudaStream_t st) {
+  if ((size_t)(2 * c->V + 2 * kXi1N) * 8 > 200 * 1024) { set_error("V=%d too large for table mode", c->V); return TSFF_E_INVALID; }
+  return fe_dtype == TSFF_F32 ? table_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
+                              : table_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
+}
+int table_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
+              const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+  return fe_dtype == TSFF_F32 ? table_bwd_t<float>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
+                              : table_bwd_t<double>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
+}
+}  // namespace tsff
