@@ -28,3 +28,32 @@ def dummy_batch_1d():
     # tests/test_forward/test_1d.py:54-61
     return dict(i_data=np.array([1.0]), e_data=np.array([1.0]), noise_e=np.array([0.0]), noise_i=np.array([0.0]),
                 e_amps=np.array([1.0]), i_amps=np.array([1.0]))
+
+
+def row_to_params(row, fe, vx, n_ions=1):
+    """C-ABI parameter row (include/tsff.h) -> the reference's nested params dict (ts_params.py:599-603)."""
+    p = {"electron": dict(Te=row[0], ne=row[1], fe=np.asarray(fe, dtype=np.float64), v=vx),
+         "general": dict(lam=row[2], Va=row[3], ud=row[4], ne_gradient=row[5], Te_gradient=row[6], amp1=row[7],
+                         amp2=row[8], amp3=row[9])}
+    for i in range(n_ions):
+        o = 10 + 4 * i
+        p[f"ion-{i+1}"] = dict(A=row[o], Z=row[o + 1], Ti=row[o + 2], fract=row[o + 3])
+    return p
+
+
+def params_to_row(p):
+    ions = sorted([k for k in p if k.startswith("ion-")], key=lambda s: int(s.split("-")[1]))
+    g, e = p["general"], p["electron"]
+    row = [e["Te"], e["ne"], g["lam"], g["Va"], g["ud"], g["ne_gradient"], g["Te_gradient"], g["amp1"], g["amp2"], g["amp3"]]
+    for k in ions:
+        row += [p[k]["A"], p[k]["Z"], p[k]["Ti"], p[k]["fract"]]
+    return np.array([float(x) for x in row])
+
+
+def rel_err_report(got, ref, floor=1e-6):
+    """max pointwise relative error where |ref| >= floor*max|ref|, and max|diff|/max|ref|."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    m = np.abs(ref) >= floor * np.abs(ref).max()
+    pw = (np.abs(got - ref)[m] / np.abs(ref)[m]).max()
+    mx = np.abs(got - ref).max() / np.abs(ref).max()
+    return pw, mx

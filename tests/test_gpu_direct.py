@@ -1,0 +1,140 @@
+"""GPU parity, TSFF_MODE_DIRECT (synthetic-sweep workload): forward vs the NumPy oracle, VJP vs the
+torch-f64 oracle's autograd.  All calls go through the C ABI (tsff_ff_fwd / tsff_ff_bwd).
+
+Tolerances (BASELINE.json north_star): spectra <= 1e-5 relative, gradients <= 1e-4 relative.  "Relative" is measured
+as max|diff|/max|S| per lineout AND pointwise wherever |S| >= 1e-6 max|S|; for the FP32 PV path the pointwise bound is
+relaxed near sharp EPW resonances, where S ~ 1/|eps|^2 amplifies the 1e-7 FP32 error of the PV sum (the FP64 PV
+path of the same kernels meets 1e-9 everywhere and isolates that effect)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O, torch_oracle as TO
+from tests.common import row_to_params, rel_err_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(W, V, sa, weights, G=1, nI=1, pv="fp32", lam=(400.0, 700.0), lam_shift=0.0, jmul=None):
+    from tsadar_b200.engine import FormFactorEngine
+    from tsadar_b200.synthetic import vgrid
+    return FormFactorEngine(lam, W, lam_shift, sa, weights, G, nI, vgrid(V), mode="direct", jmul=jmul, pv_precision=pv)
+
+
+def _oracle_modl(params, fe, vx, grids, sa, weights, G, nI, lam_shift=0.0):
+    outs, ffs = [], []
+    for b in range(params.shape[0]):
+        ff, _ = O.form_factor_direct(row_to_params(params[b], fe[b], vx, nI), grids, sa, G, lam_shift)
+        ffs.append(ff)
+        outs.append(np.sum(np.mean(ff, 0) * weights, 1))
+    return np.array(outs), np.array(ffs)
+
+
+@pytest.mark.parametrize("pv", ["fp64", "fp32"])
+def test_direct_forward_synthetic(pv):
+    from tsadar_b200.synthetic import make_lineouts, SA_SYN
+    W, V, B = 1024, 512, 6
+    params, fe, vx, _ = make_lineouts(B, seed=42, nvx=V, dtype=np.float64)
+    eng = _engine(W, V, SA_SYN, np.array([1.0]), pv=pv)
+    modl, ff, _ = eng.forward(torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda"), want_ff=True)
+    ref, ref_ff = _oracle_modl(params, fe, vx, O.Grids([400, 700], W), SA_SYN, np.array([1.0]), 1, 1)
+    got = modl.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(ff.cpu().numpy()[:, :, :, 0], ref_ff[:, :, :, 0] , rtol=0, atol=np.abs(ref_ff).max())  # shape/layout
+    for b in range(B):
+        pw, mx = rel_err_report(got[b], ref[b])
+        if pv == "fp64":
+            assert pw < 1e-9 and mx < 1e-10, (b, pw, mx)
+        else:
+            assert mx < 1e-5, (b, pw, mx)
+
+
+def test_direct_forward_multi_angle_gradients_ions():
+    """A=10 angles (P9 weights), G=3 gradient points, two ion species, FP32 table input, flows and drift."""
+    from tsadar_b200.synthetic import make_lineouts
+    from tests.common import SA_P9
+    W, V, B, G, nI = 256, 256, 3, 3, 2
+    params1, fe, vx, _ = make_lineouts(B, seed=7, nvx=V, dtype=np.float32)
+    params = np.zeros((B, 10 + 4 * nI))
+    params[:, :14] = params1
+    params[:, 3] = [0.5, -1.0, 2.0]      # Va
+    params[:, 4] = [-0.3, 0.2, 1.0]      # ud
+    params[:, 5] = [5.0, 0.0, 10.0]      # ne_gradient
+    params[:, 6] = [2.0, 7.0, 0.0]       # Te_gradient
+    params[:, 13] = 0.7
+    params[:, 14:18] = [1.0, 1.0, 0.3, 0.3]
+    jmul = np.where(np.abs(np.linspace(500, 560, W) - 528) < 12, 1e-4, 1.0)
+    eng = _engine(W, V, SA_P9["sa"], SA_P9["weights"], G=G, nI=nI, lam=(500.0, 560.0), lam_shift=0.1, jmul=jmul)
+    modl, ff, _ = eng.forward(torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda"), want_ff=True)
+    ref, ref_ff = _oracle_modl(params, fe.astype(np.float64), vx, O.Grids([500, 560], W), SA_P9["sa"], SA_P9["weights"], G, nI, 0.1)
+    ref = ref * jmul
+    for b in range(B):
+        pw, mx = rel_err_report(modl.cpu().numpy()[b], ref[b])
+        assert mx < 1e-5 and pw < 1e-4, (b, pw, mx)
+        pw, mx = rel_err_report(ff.cpu().numpy()[b], ref_ff[b])
+        assert mx < 1e-5, (b, pw, mx)
+
+
+def _torch_grads(params, fe, vx, grids, sa, weights, G, nI, cot, lam_shift=0.0, jmul=None):
+    pbar, fbar = [], []
+    for b in range(params.shape[0]):
+        leaves, p = TO.params_from_block(params[b], nI)
+        fet = torch.tensor(np.asarray(fe[b], dtype=np.float64), requires_grad=True)
+        ff = TO.form_factor_direct(p, fet, vx, grids, sa, G, lam_shift)
+        modl = TO.modl_from_ff(ff, weights, jmul)
+        (modl * torch.tensor(cot[b])).sum().backward()
+        pbar.append(leaves.grad.numpy().copy())
+        fbar.append(fet.grad.numpy().copy())
+    return np.array(pbar), np.array(fbar)
+
+
+def test_direct_vjp_synthetic():
+    from tsadar_b200.synthetic import make_lineouts, SA_SYN
+    W, V, B = 512, 512, 4
+    params, fe, vx, _ = make_lineouts(B, seed=11, nvx=V, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    grids = O.Grids([400, 700], W)
+    ref, _ = _oracle_modl(params, fe, vx, grids, SA_SYN, np.array([1.0]), 1, 1)
+    cot = rng.normal(size=(B, W)) / np.abs(ref).max(axis=1, keepdims=True)
+    eng = _engine(W, V, SA_SYN, np.array([1.0]))
+    pt, ft = torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda")
+    modl, _, saved = eng.forward(pt, ft)
+    pb, fb = eng.backward(pt, ft, saved, modl_bar=torch.tensor(cot, device="cuda"))
+    gp, gf = _torch_grads(params, fe, vx, grids, SA_SYN, np.array([1.0]), 1, 1, cot)
+    pb, fb = pb.cpu().numpy(), fb.cpu().numpy()
+    active = [0, 1, 2, 3, 4, 5, 6, 11, 12, 13]
+    for b in range(B):
+        for k in active:
+            assert abs(pb[b, k] - gp[b, k]) <= 1e-4 * max(abs(gp[b, k]), 1e-8 * np.abs(gp[b]).max()), (b, k, pb[b, k], gp[b, k])
+        assert np.abs(fb[b] - gf[b]).max() / np.abs(gf[b]).max() < 1e-4, b
+        cos = np.dot(fb[b], gf[b]) / np.linalg.norm(fb[b]) / np.linalg.norm(gf[b])
+        assert cos > 1 - 1e-8
+
+
+def test_direct_vjp_multi_angle_ff_bar():
+    from tsadar_b200.synthetic import make_lineouts
+    from tests.common import SA_P9
+    W, V, B, G, nI = 128, 128, 2, 2, 2
+    params1, fe, vx, _ = make_lineouts(B, seed=3, nvx=V, dtype=np.float64)
+    params = np.zeros((B, 18))
+    params[:, :14] = params1
+    params[:, 3] = [0.5, -1.0]
+    params[:, 4] = [-0.3, 0.2]
+    params[:, 5] = [5.0, 1.0]
+    params[:, 6] = [2.0, 7.0]
+    params[:, 13] = 0.7
+    params[:, 14:18] = [1.0, 1.0, 0.3, 0.3]
+    grids = O.Grids([500, 560], W)
+    rng = np.random.default_rng(9)
+    ref, _ = _oracle_modl(params, fe, vx, grids, SA_P9["sa"], SA_P9["weights"], G, nI, 0.1)
+    cot = rng.normal(size=(B, W)) / np.abs(ref).max(axis=1, keepdims=True)
+    eng = _engine(W, V, SA_P9["sa"], SA_P9["weights"], G=G, nI=nI, lam=(500.0, 560.0), lam_shift=0.1)
+    pt, ft = torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda")
+    modl, _, saved = eng.forward(pt, ft)
+    pb, fb = eng.backward(pt, ft, saved, modl_bar=torch.tensor(cot, device="cuda"))
+    gp, gf = _torch_grads(params, fe, vx, grids, SA_P9["sa"], SA_P9["weights"], G, nI, cot, 0.1)
+    pb, fb = pb.cpu().numpy(), fb.cpu().numpy()
+    for b in range(B):
+        for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13, 15, 16, 17]:
+            assert abs(pb[b, k] - gp[b, k]) <= 1e-4 * max(abs(gp[b, k]), 1e-8 * np.abs(gp[b]).max()), (b, k, pb[b, k], gp[b, k])
+        assert np.abs(fb[b] - gf[b]).max() / np.abs(gf[b]).max() < 1e-4, b

@@ -1,0 +1,90 @@
+"""GPU parity, TSFF_MODE_TABLE = the reference's 1V FormFactor.__call__ (form_factor.py:163-298) + FitModel angle sum
+(generate_spectra.py:171-220), through the C ABI.  Forward vs the NumPy oracle on the golden-vector deck
+(tests/configs/1d-*.yaml, W=5120, A=10, V=128), VJP vs torch-f64 autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O, torch_oracle as TO, params_oracle as P
+from tests.common import SA_P9, DLM_M_OFFSET, load_cfg, params_to_row, row_to_params, rel_err_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(W, vx, sa, weights, G=1, nI=1, pv="fp32", lam=(400.0, 700.0), lam_shift=0.0, jmul=None):
+    from tsadar_b200.engine import FormFactorEngine
+    return FormFactorEngine(lam, W, lam_shift, sa, weights, G, nI, vx, mode="table", jmul=jmul, pv_precision=pv)
+
+
+def _jmul(lam_axis, iawfilter):
+    fb, fr = iawfilter[3] - iawfilter[2] / 2, iawfilter[3] + iawfilter[2] / 2
+    return np.where((fb < lam_axis) & (fr > lam_axis), 10.0 ** (-iawfilter[1]), 1.0)
+
+
+@pytest.mark.parametrize("pv", ["fp64", "fp32"])
+def test_table_forward_golden_deck(pv):
+    cfg = load_cfg("cfg_1d")
+    p = P.thomson_params(cfg["parameters"], activate=True, dlm_m_offset=DLM_M_OFFSET)
+    row = params_to_row(p)[None, :]
+    fe, vx = p["electron"]["fe"][None, :], p["electron"]["v"]
+    W = cfg["other"]["npts"]
+    grids = O.Grids(cfg["other"]["lamrangE"], W)
+    lamE, ref = O.fit_model_electron(p, grids, SA_P9, cfg["other"], 1, 0.0)
+    w0 = float(SA_P9["weights"][0])  # the scalar-weight quirk of un-prepared `sa`
+    eng = _engine(W, vx, SA_P9["sa"], w0, lam=cfg["other"]["lamrangE"], jmul=_jmul(grids.lam_axis, cfg["other"]["iawfilter"]), pv=pv)
+    modl, ff, _ = eng.forward(torch.tensor(row, device="cuda"), torch.tensor(fe, device="cuda"), want_ff=True)
+    got = modl.cpu().numpy()[0]
+    pw, mx = rel_err_report(got, ref)
+    ref_ff, _ = O.form_factor_1v(p, grids, SA_P9["sa"])
+    pwf, mxf = rel_err_report(ff.cpu().numpy()[0], ref_ff)
+    if pv == "fp64":
+        assert pw < 1e-9 and mx < 1e-10 and pwf < 1e-9, (pw, mx, pwf, mxf)
+    else:
+        assert pw < 1e-5 and mx < 1e-5 and pwf < 1e-5, (pw, mx, pwf, mxf)
+
+
+def test_table_forward_batch_two_ions_gradients():
+    W, V, B, G, nI = 640, 96, 3, 2, 2
+    vx = P.vgrid(V)
+    rows, fes = [], []
+    for b, (m, Te, ne) in enumerate([(2.0, 0.4, 0.15), (3.1, 1.2, 0.6), (4.5, 0.7, 0.3)]):
+        rows.append([Te, ne, 526.5 + 0.3 * b, 0.5 * b, -0.2 * b, 4.0, 3.0, 1, 1, 1, 40.0, 8.0 + b, 0.2, 0.6, 1.0, 1.0, 0.1 + 0.1 * b, 0.4])
+        fes.append(P.super_gaussian_projected(vx, m))
+    rows, fes = np.array(rows), np.array(fes)
+    grids = O.Grids([523.0, 530.0], W)
+    eng = _engine(W, vx, SA_P9["sa"], SA_P9["weights"], G=G, nI=nI, lam=(523.0, 530.0), lam_shift=0.0)
+    modl, _, _ = eng.forward(torch.tensor(rows, device="cuda"), torch.tensor(fes, device="cuda"))
+    for b in range(B):
+        ff, _ = O.form_factor_1v(row_to_params(rows[b], fes[b], vx, nI), grids, SA_P9["sa"], G, 0.0)
+        ref = np.sum(np.mean(ff, 0) * SA_P9["weights"], 1)
+        pw, mx = rel_err_report(modl.cpu().numpy()[b], ref)
+        assert mx < 1e-5 and pw < 1e-5, (b, pw, mx)
+
+
+@pytest.mark.parametrize("W,V,A", [(310, 64, 3), (96, 128, 10)])
+def test_table_vjp(W, V, A):
+    B, G, nI = 2, 2, 2
+    vx = P.vgrid(V)
+    sa = np.linspace(55.0, 65.0, A)
+    wts = np.linspace(0.5, 1.5, A) / A
+    rows = np.array([[0.6, 0.25, 526.0, 0.4, -0.3, 4.0, 3.0, 1, 1, 1, 40.0, 8.0, 0.2, 0.6, 1.0, 1.0, 0.3, 0.4],
+                     [1.1, 0.5, 524.5, -0.6, 0.2, 1.0, 6.0, 1, 1, 1, 12.0, 6.0, 0.5, 0.3, 1.0, 1.0, 0.2, 0.7]])
+    fes = np.array([P.super_gaussian_projected(vx, 2.3), P.super_gaussian_projected(vx, 3.6)])
+    lam = (430.0, 640.0)
+    grids = O.Grids(lam, W)
+    rng = np.random.default_rng(4)
+    eng = _engine(W, vx, sa, wts, G=G, nI=nI, lam=lam, lam_shift=0.05)
+    pt, ft = torch.tensor(rows, device="cuda"), torch.tensor(fes, device="cuda")
+    modl, _, saved = eng.forward(pt, ft)
+    cot = rng.normal(size=(B, W)) / np.abs(modl.cpu().numpy()).max(axis=1, keepdims=True)
+    pb, fb = eng.backward(pt, ft, saved, modl_bar=torch.tensor(cot, device="cuda"))
+    pb, fb = pb.cpu().numpy(), fb.cpu().numpy()
+    for b in range(B):
+        leaves, p = TO.params_from_block(rows[b], nI)
+        fet = torch.tensor(fes[b], requires_grad=True)
+        ff = TO.form_factor_1v(p, fet, vx, grids, sa, G, 0.05)
+        (TO.modl_from_ff(ff, wts) * torch.tensor(cot[b])).sum().backward()
+        gp, gf = leaves.grad.numpy(), fet.grad.numpy()
+        for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13, 15, 16, 17]:
+            assert abs(pb[b, k] - gp[k]) <= 1e-4 * max(abs(gp[k]), 1e-8 * np.abs(gp).max()), (b, k, pb[b, k], gp[k])
+        assert np.abs(fb[b] - gf).max() / np.abs(gf).max() < 1e-4, (b, np.abs(fb[b] - gf).max() / np.abs(gf).max())

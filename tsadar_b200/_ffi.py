@@ -1,0 +1,104 @@
+"""ctypes binding of libtsff.so (include/tsff.h).  There is NO CPU fallback: importing the product on a box
+without the built extension, or creating a context without an sm_100 GPU, raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libtsff.so")
+
+TSFF_ABI_VERSION = 1
+TSFF_MODE_TABLE, TSFF_MODE_DIRECT = 0, 1
+TSFF_F32, TSFF_F64 = 0, 1
+TSFF_PV_FP32, TSFF_PV_FP64 = 0, 1
+P_TE, P_NE, P_LAM, P_VA, P_UD, P_NE_GRAD, P_TE_GRAD, P_AMP1, P_AMP2, P_AMP3, P_ION0 = range(11)
+ION_A, ION_Z, ION_TI, ION_FRACT, ION_STRIDE = range(5)
+
+EXPORTS = [
+    "tsff_ctx_create", "tsff_ctx_destroy", "tsff_last_error", "tsff_abi_version",
+    "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd",
+    "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
+]
+
+
+class StaticCfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("mode", C.c_int32),
+        ("W", C.c_int32), ("A", C.c_int32), ("G", C.c_int32), ("I", C.c_int32), ("V", C.c_int32),
+        ("pv_precision", C.c_int32),
+        ("lam_min", C.c_double), ("lam_max", C.c_double), ("lam_shift", C.c_double),
+        ("v0", C.c_double), ("dv", C.c_double),
+        ("sa_deg", C.POINTER(C.c_double)), ("weights", C.POINTER(C.c_double)), ("jmul", C.POINTER(C.c_double)),
+        ("zp_x", C.POINTER(C.c_double)), ("zp_re", C.POINTER(C.c_double)), ("zp_im", C.POINTER(C.c_double)),
+        ("zp_n", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class IrfCfg(C.Structure):
+    _fields_ = [
+        ("W", C.c_int32), ("nbins", C.c_int32), ("norm", C.c_int32), ("kind", C.c_int32),
+        ("lam_min", C.c_double), ("lam_max", C.c_double), ("stddev", C.c_double), ("cut_sigma", C.c_double),
+    ]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("method", C.c_int32), ("nwin", C.c_int32), ("reserved", C.c_int32),
+        ("win_lo", C.c_double * 4), ("win_hi", C.c_double * 4), ("win_group", C.c_int32 * 4),
+        ("uncert", C.c_double), ("scale", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libtsff.so (built in-tree by tsadar_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m tsadar_b200.build` (nvcc, sm_100a). "
+            "tsadar_b200 has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, dp = C.c_void_p, C.c_int64, C.c_void_p
+    L.tsff_ctx_create.argtypes = [C.c_int, C.POINTER(StaticCfg), C.POINTER(vp)]
+    L.tsff_ctx_create.restype = C.c_int
+    L.tsff_ctx_destroy.argtypes = [vp]
+    L.tsff_ctx_destroy.restype = None
+    L.tsff_last_error.restype = C.c_char_p
+    L.tsff_abi_version.restype = C.c_int
+    L.tsff_ff_saved_bytes.argtypes = [vp, i64]
+    L.tsff_ff_saved_bytes.restype = C.c_size_t
+    L.tsff_ff_workspace_bytes.argtypes = [vp, i64]
+    L.tsff_ff_workspace_bytes.restype = C.c_size_t
+    L.tsff_ff_fwd.argtypes = [vp, i64, dp, vp, C.c_int, dp, dp, vp, vp, vp]
+    L.tsff_ff_fwd.restype = C.c_int
+    L.tsff_ff_bwd.argtypes = [vp, i64, dp, vp, C.c_int, vp, dp, dp, dp, vp, vp, vp]
+    L.tsff_ff_bwd.restype = C.c_int
+    L.tsff_pv_workspace_bytes.argtypes = [i64, i64, i64]
+    L.tsff_pv_workspace_bytes.restype = C.c_size_t
+    L.tsff_pv_fwd.argtypes = [i64, i64, i64, dp, C.c_double, C.c_double, dp, dp, dp, C.c_int, vp, vp]
+    L.tsff_pv_fwd.restype = C.c_int
+    L.tsff_pv_bwd.argtypes = [i64, i64, i64, dp, C.c_double, C.c_double, dp, dp, dp, dp, vp, vp]
+    L.tsff_pv_bwd.restype = C.c_int
+    L.tsff_microbench.argtypes = [C.c_int, i64, C.POINTER(C.c_double), vp, vp]
+    L.tsff_microbench.restype = C.c_int
+    if hasattr(L, "tsff_irf_fwd"):
+        L.tsff_irf_workspace_bytes.argtypes = [C.POINTER(IrfCfg), i64]
+        L.tsff_irf_workspace_bytes.restype = C.c_size_t
+        L.tsff_irf_fwd.argtypes = [C.POINTER(IrfCfg), i64, dp, dp, dp, dp, dp, vp, vp, vp]
+        L.tsff_irf_fwd.restype = C.c_int
+        L.tsff_irf_bwd.argtypes = [C.POINTER(IrfCfg), i64, dp, dp, dp, dp, vp, dp, dp, dp, vp, vp]
+        L.tsff_irf_bwd.restype = C.c_int
+        L.tsff_loss_fwd_bwd.argtypes = [C.POINTER(LossCfg), i64, dp, dp, dp, dp, dp, vp, vp]
+        L.tsff_loss_fwd_bwd.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libtsff error {rc}: {lib().tsff_last_error().decode()}")

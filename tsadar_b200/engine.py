@@ -1,0 +1,228 @@
+"""Thin torch <-> libtsff plumbing: context lifetime, workspace tensors, and the autograd Function that plays
+the role `jax.custom_vjp` plays in the JAX binding.  torch is used for device memory and
+streams only; all arithmetic happens in the CUDA kernels behind the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def _zprime_table():
+    t = np.load(os.path.join(_DATA, "zprime_table.npz"))
+    return (np.ascontiguousarray(t["x"], dtype=np.float64), np.ascontiguousarray(t["re"], dtype=np.float64),
+            np.ascontiguousarray(t["im"], dtype=np.float64))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _require_cuda(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{name} must be a CUDA tensor: tsadar_b200 has no CPU path")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+class FormFactorEngine:
+    """One immutable libtsff context (= the static state of the reference's FormFactor.__init__,
+    form_factor.py:120-161) bound to one GPU."""
+
+    def __init__(self, lambda_range, npts, lam_shift, sa_deg, weights, num_grad_points, n_ions, vx, mode="table",
+                 jmul=None, pv_precision="fp32", device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tsadar_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        vx = np.asarray(vx, dtype=np.float64)
+        dv = float(vx[1] - vx[0])
+        if not np.allclose(np.diff(vx), dv, rtol=1e-9, atol=0):
+            raise ValueError("the f-table grid must be uniform (DistributionFunction1V, base.py:149-151)")
+        sa_deg = np.ascontiguousarray(np.asarray(sa_deg, dtype=np.float64).reshape(-1))
+        weights = np.asarray(weights, dtype=np.float64)
+        if weights.ndim == 0:
+            weights = np.full(sa_deg.shape, float(weights))
+        weights = np.ascontiguousarray(weights.reshape(-1))
+        if weights.shape != sa_deg.shape:
+            raise ValueError("weights must have one entry per scattering angle")
+        self.W, self.A, self.G, self.I, self.V = int(npts), int(sa_deg.size), int(num_grad_points), int(n_ions), int(vx.size)
+        self.NP = _ffi.P_ION0 + _ffi.ION_STRIDE * self.I
+        self.mode = mode
+        zx, zr, zi = _zprime_table()
+        cfg = _ffi.StaticCfg()
+        cfg.abi_version = _ffi.TSFF_ABI_VERSION
+        cfg.mode = _ffi.TSFF_MODE_TABLE if mode == "table" else _ffi.TSFF_MODE_DIRECT
+        cfg.W, cfg.A, cfg.G, cfg.I, cfg.V = self.W, self.A, self.G, self.I, self.V
+        cfg.pv_precision = _ffi.TSFF_PV_FP64 if pv_precision == "fp64" else _ffi.TSFF_PV_FP32
+        cfg.lam_min, cfg.lam_max, cfg.lam_shift = float(lambda_range[0]), float(lambda_range[1]), float(lam_shift)
+        cfg.v0, cfg.dv = float(vx[0]), dv
+        cfg.sa_deg, cfg.weights = _dptr(sa_deg), _dptr(weights)
+        if jmul is not None:
+            jmul = np.ascontiguousarray(np.asarray(jmul, dtype=np.float64).reshape(-1))
+            assert jmul.size == self.W
+            cfg.jmul = _dptr(jmul)
+        cfg.zp_x, cfg.zp_re, cfg.zp_im, cfg.zp_n = _dptr(zx), _dptr(zr), _dptr(zi), int(zx.size)
+        self._ctx = C.c_void_p()
+        _ffi.check(_ffi.lib().tsff_ctx_create(self.device.index, C.byref(cfg), C.byref(self._ctx)))
+        # wavelength axis in nm as FitModel returns it (lams * 1e7, generate_spectra.py:163,191)
+        lam = np.linspace(cfg.lam_min, cfg.lam_max, self.W)
+        omgs = 2e7 * np.pi * 2.99792458e10 / lam
+        self.lam_cm = 2 * np.pi * 2.99792458e10 / omgs
+        self._buf = {}
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None) and self._ctx.value:
+                _ffi.lib().tsff_ctx_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- buffers ------------------------------------------------------------------------------------------
+    def _scratch(self, key, nbytes):
+        t = self._buf.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._buf[key] = t
+        return t
+
+    def saved_bytes(self, B):
+        return int(_ffi.lib().tsff_ff_saved_bytes(self._ctx, B))
+
+    def workspace_bytes(self, B):
+        return int(_ffi.lib().tsff_ff_workspace_bytes(self._ctx, B))
+
+    # ---- raw calls ----------------------------------------------------------------------------------------
+    def forward(self, params, fe, want_ff=False, want_modl=True, saved=None):
+        """params [B,NP] f64 cuda, fe [B,V] f32|f64 cuda -> (modl [B,W] | None, ff [B,G,W,A] | None, saved)."""
+        _require_cuda(params, torch.float64, "params")
+        if fe.dtype not in (torch.float32, torch.float64):
+            raise RuntimeError("fe must be float32 or float64")
+        _require_cuda(fe, fe.dtype, "fe")
+        B = params.shape[0]
+        assert params.shape == (B, self.NP) and fe.shape == (B, self.V), (params.shape, fe.shape)
+        modl = torch.empty((B, self.W), dtype=torch.float64, device=self.device) if want_modl else None
+        ff = torch.empty((B, self.G, self.W, self.A), dtype=torch.float64, device=self.device) if want_ff else None
+        if saved is None:
+            saved = torch.empty(self.saved_bytes(B), dtype=torch.uint8, device=self.device)
+        ws = self._scratch("ws", self.workspace_bytes(B))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_ff_fwd(
+            self._ctx, B, params.data_ptr(), fe.data_ptr(), _ffi.TSFF_F32 if fe.dtype == torch.float32 else _ffi.TSFF_F64,
+            modl.data_ptr() if modl is not None else None, ff.data_ptr() if ff is not None else None,
+            saved.data_ptr(), ws.data_ptr(), st))
+        return modl, ff, saved
+
+    def backward(self, params, fe, saved, modl_bar=None, ff_bar=None, params_bar=None, fe_bar=None):
+        B = params.shape[0]
+        if modl_bar is not None:
+            _require_cuda(modl_bar, torch.float64, "modl_bar")
+        if ff_bar is not None:
+            _require_cuda(ff_bar, torch.float64, "ff_bar")
+        if params_bar is None:
+            params_bar = torch.empty((B, self.NP), dtype=torch.float64, device=self.device)
+        if fe_bar is None:
+            fe_bar = torch.empty_like(fe)
+        ws = self._scratch("ws", self.workspace_bytes(B))
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_ff_bwd(
+            self._ctx, B, params.data_ptr(), fe.data_ptr(), _ffi.TSFF_F32 if fe.dtype == torch.float32 else _ffi.TSFF_F64,
+            saved.data_ptr(), modl_bar.data_ptr() if modl_bar is not None else None,
+            ff_bar.data_ptr() if ff_bar is not None else None, params_bar.data_ptr(), fe_bar.data_ptr(), ws.data_ptr(), st))
+        return params_bar, fe_bar
+
+    # number of kernel launches one forward / backward call makes (for bench.py's gpu_launches claim)
+    def launches_fwd(self, want_modl=True):
+        if self.mode == "table":
+            return 3
+        return 2 + (1 if want_modl else 0)
+
+    def launches_bwd(self):
+        return 4 if self.mode == "table" else 3  # (+1 memset node, not a kernel of ours)
+
+
+class _FFFunction(torch.autograd.Function):
+    """custom-VJP wrapper: forward saves the kernel's residual buffer, backward calls tsff_ff_bwd."""
+
+    @staticmethod
+    def forward(ctx, engine, params, fe, want_ff):
+        modl, ff, saved = engine.forward(params, fe, want_ff=want_ff, want_modl=not want_ff)
+        ctx.engine, ctx.want_ff = engine, want_ff
+        ctx.save_for_backward(params, fe, saved)
+        return ff if want_ff else modl
+
+    @staticmethod
+    def backward(ctx, out_bar):
+        params, fe, saved = ctx.saved_tensors
+        out_bar = out_bar.contiguous()
+        if ctx.want_ff:
+            pb, fb = ctx.engine.backward(params, fe, saved, ff_bar=out_bar)
+        else:
+            pb, fb = ctx.engine.backward(params, fe, saved, modl_bar=out_bar)
+        return None, pb, fb, None
+
+
+def form_factor_modl(engine, params, fe):
+    """Differentiable angle-integrated spectrum modl[B,W]."""
+    return _FFFunction.apply(engine, params, fe, False)
+
+
+def form_factor_full(engine, params, fe):
+    """Differentiable formfactor[B,G,W,A]."""
+    return _FFFunction.apply(engine, params, fe, True)
+
+
+# ---- B1: stand-alone PV integral ------------------------------------------------------------------------------
+def pv_integral(f, z0, h, pole, precision="fp32", want_grad=True):
+    """vmap(ratintn)(f, z[None]-pole[:,None], z) for uniform nodes (ratintn.py:4-23).  f [B,N], pole [B,P] f64 cuda."""
+    _require_cuda(f, torch.float64, "f")
+    _require_cuda(pole, torch.float64, "pole")
+    B, N = f.shape
+    P = pole.shape[1]
+    out = torch.empty((B, P), dtype=torch.float64, device=f.device)
+    dout = torch.empty((B, P), dtype=torch.float64, device=f.device) if want_grad else None
+    ws = torch.empty(int(_ffi.lib().tsff_pv_workspace_bytes(B, N, P)), dtype=torch.uint8, device=f.device)
+    st = torch.cuda.current_stream(f.device).cuda_stream
+    _ffi.check(_ffi.lib().tsff_pv_fwd(B, N, P, f.data_ptr(), float(z0), float(h), pole.data_ptr(), out.data_ptr(),
+                                      dout.data_ptr() if dout is not None else None,
+                                      _ffi.TSFF_PV_FP64 if precision == "fp64" else _ffi.TSFF_PV_FP32, ws.data_ptr(), st))
+    return out, dout
+
+
+def pv_integral_vjp(f, z0, h, pole, out_bar):
+    _require_cuda(out_bar, torch.float64, "out_bar")
+    B, N = f.shape
+    P = pole.shape[1]
+    f_bar = torch.empty_like(f)
+    pole_bar = torch.empty_like(pole)
+    ws = torch.empty(int(_ffi.lib().tsff_pv_workspace_bytes(B, N, P)), dtype=torch.uint8, device=f.device)
+    st = torch.cuda.current_stream(f.device).cuda_stream
+    _ffi.check(_ffi.lib().tsff_pv_bwd(B, N, P, f.data_ptr(), float(z0), float(h), pole.data_ptr(), out_bar.data_ptr(),
+                                      f_bar.data_ptr(), pole_bar.data_ptr(), ws.data_ptr(), st))
+    return f_bar, pole_bar
+
+
+def microbench(kind, iters=4096):
+    """Measured FFMA (kind 0) / MUFU.LG2 (kind 1) issue peak on the current device, ops per second."""
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    ops = C.c_double()
+    st = torch.cuda.current_stream().cuda_stream
+    L = _ffi.lib()
+    _ffi.check(L.tsff_microbench(kind, 64, C.byref(ops), sink.data_ptr(), st))  # warm
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(3):
+        e0.record()
+        _ffi.check(L.tsff_microbench(kind, iters, C.byref(ops), sink.data_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+    return best
