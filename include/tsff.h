@@ -114,6 +114,35 @@ int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, dou
 int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
                 const double* out_bar, double* f_bar, double* pole_bar, void* ws, void* stream);
 
+/* ---- B4: instrument response, pixel binning, amplitude scaling ------------------------------------------------ */
+/* replaces irf.add_electron_IRF (kind 0, irf.py:90-132) / irf.add_ion_IRF (kind 1, irf.py:50-87) under the reference's
+ * vmap over lineouts (thomson_diagnostic.py:35-36, 42-76), plus the noise add of thomson_diagnostic.py:139-140.
+ * Only PhysParams.norm == 0 (all reference decks).  The Gaussian taps are truncated at cut_sigma (<=0: 12). */
+typedef struct tsff_irf_cfg {
+  int32_t W, nbins;       /* model samples, CCD pixels (1024 in the reference, irf.py:74,124); W % nbins == 0 */
+  int32_t norm, kind;     /* PhysParams.norm (must be 0);  0 electron / 1 ion */
+  double lam_min, lam_max; /* wavelength axis of the model spectrum in nm: linspace(lam_min, lam_max, W) */
+  double stddev;          /* widIRF.spect_stddev_ele / spect_stddev_ion [nm] */
+  double cut_sigma;
+} tsff_irf_cfg;
+size_t tsff_irf_workspace_bytes(const tsff_irf_cfg* cfg, int64_t B);
+size_t tsff_irf_saved_bytes(const tsff_irf_cfg* cfg, int64_t B);
+/* modl [B][W], params [B][NP] (uses lam, amp1, amp2, amp3), amps [B] (batch["e_amps"] / ["i_amps"]),
+ * noise [B][nbins] or NULL  ->  thry [B][nbins] */
+int tsff_irf_fwd(const tsff_irf_cfg* cfg, int64_t B, const double* modl, const double* params, int32_t NP,
+                 const double* amps, const double* noise, double* thry, void* saved, void* ws, void* stream);
+/* VJP: thry_bar [B][nbins] -> modl_bar [B][W], amp_bar [B][3] (cotangents of amp1, amp2, amp3) */
+int tsff_irf_bwd(const tsff_irf_cfg* cfg, int64_t B, const double* params, int32_t NP, const double* amps,
+                 const void* saved, const double* thry_bar, double* modl_bar, double* amp_bar, void* ws, void* stream);
+
+/* ---- B5: loss -------------------------------------------------------------------------------------------------- */
+/* replaces LossFunction.calc_ei_error + loss_functionals (loss_function.py:190-267, 386-418) and the seed of the
+ * reverse pass: loss += scale * sum_{b,q} weight[q] * err(data, theory), theory_bar = d loss / d theory.
+ * The fit-window masks and nanmean denominators are static, so they arrive folded into weight[n] (device) and scale.
+ * method: 0 l2, 1 l1, 2 log-cosh, 3 poisson.  *loss_out (device scalar) is ACCUMULATED into: zero it first. */
+int tsff_loss_fwd_bwd(int64_t B, int32_t n, const double* theory, const double* data, const double* weight,
+                      double uncert, double scale, int method, double* loss_out, double* theory_bar, void* stream);
+
 /* ---- microbenchmarks used for the roofline denominators --------------------------------- */
 /* runs `iters` dependent-chain FFMA (kind 0) or MUFU.LG2 (kind 1) per thread on the whole device; returns the
  * number of operations issued (FFMA counts 1 op = 2 flop) in *ops; time it with events on `stream`. */

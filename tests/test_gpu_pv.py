@@ -17,7 +17,8 @@ def _case(N, P, B, seed):
     f = np.stack([-z * np.exp(-0.5 * z**2 / s**2) / s**3 * 0.4 + 0.01 * np.sin(3 * z) for s in rng.uniform(0.7, 1.3, B)])
     pole = rng.uniform(-7.5, 7.5, (B, P))
     pole[:, 0] = z[N // 3] + 1e-7  # a pole almost on a node
-    pole[:, 1] = z[5]              # a pole exactly on a node (reference would return inf/nan there; we return the limit)
+    if P > 1:
+        pole[:, 1] = z[5]          # a pole exactly on a node (reference would return inf/nan there; we return the limit)
     return z, z0, h, f, pole
 
 
@@ -31,11 +32,12 @@ def test_pv_forward_matches_ratintn(N, P, B):
     out64, _ = E.pv_integral(fd, z0, h, pd, precision="fp64")
     out32, dout = E.pv_integral(fd, z0, h, pd, precision="fp32")
     ok = np.ones_like(ref, dtype=bool)
-    ok[:, 1] = False  # pole exactly on a node
+    if P > 1:
+        ok[:, 1] = False  # pole exactly on a node
     scale = np.abs(ref[ok]).max()
     assert np.abs(out64.cpu().numpy() - ref)[ok].max() / scale < 1e-12
     # FP32 MUFU path: absolute error relative to the O(1) scale of the integral
-    assert np.abs(out32.cpu().numpy() - ref)[ok].max() / scale < 2e-6
+    assert np.abs(out32.cpu().numpy() - ref)[ok].max() / scale < 1e-7
     assert np.isfinite(out32.cpu().numpy()).all()
     # derivative wrt the pole vs central differences of the oracle
     e = 1e-6
@@ -45,7 +47,8 @@ def test_pv_forward_matches_ratintn(N, P, B):
     okd = ok.copy()
     okd[:, 0] = False
     d = dout.cpu().numpy()
-    assert (np.abs(d - fdv)[okd] / np.maximum(1.0, np.abs(fdv[okd]))).max() < 1e-4
+    if okd.any():
+        assert (np.abs(d - fdv)[okd] / np.maximum(1.0, np.abs(fdv[okd]))).max() < 1e-4
 
 
 def test_pv_adjoint_matches_autograd():

@@ -19,6 +19,7 @@ EXPORTS = [
     "tsff_ctx_create", "tsff_ctx_destroy", "tsff_last_error", "tsff_abi_version",
     "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd",
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
+    "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
 ]
 
 
@@ -39,14 +40,6 @@ class IrfCfg(C.Structure):
     _fields_ = [
         ("W", C.c_int32), ("nbins", C.c_int32), ("norm", C.c_int32), ("kind", C.c_int32),
         ("lam_min", C.c_double), ("lam_max", C.c_double), ("stddev", C.c_double), ("cut_sigma", C.c_double),
-    ]
-
-
-class LossCfg(C.Structure):
-    _fields_ = [
-        ("n", C.c_int32), ("method", C.c_int32), ("nwin", C.c_int32), ("reserved", C.c_int32),
-        ("win_lo", C.c_double * 4), ("win_hi", C.c_double * 4), ("win_group", C.c_int32 * 4),
-        ("uncert", C.c_double), ("scale", C.c_double),
     ]
 
 
@@ -86,15 +79,16 @@ def lib():
     L.tsff_pv_bwd.restype = C.c_int
     L.tsff_microbench.argtypes = [C.c_int, i64, C.POINTER(C.c_double), vp, vp]
     L.tsff_microbench.restype = C.c_int
-    if hasattr(L, "tsff_irf_fwd"):
-        L.tsff_irf_workspace_bytes.argtypes = [C.POINTER(IrfCfg), i64]
-        L.tsff_irf_workspace_bytes.restype = C.c_size_t
-        L.tsff_irf_fwd.argtypes = [C.POINTER(IrfCfg), i64, dp, dp, dp, dp, dp, vp, vp, vp]
-        L.tsff_irf_fwd.restype = C.c_int
-        L.tsff_irf_bwd.argtypes = [C.POINTER(IrfCfg), i64, dp, dp, dp, dp, vp, dp, dp, dp, vp, vp]
-        L.tsff_irf_bwd.restype = C.c_int
-        L.tsff_loss_fwd_bwd.argtypes = [C.POINTER(LossCfg), i64, dp, dp, dp, dp, dp, vp, vp]
-        L.tsff_loss_fwd_bwd.restype = C.c_int
+    L.tsff_irf_workspace_bytes.argtypes = [C.POINTER(IrfCfg), i64]
+    L.tsff_irf_workspace_bytes.restype = C.c_size_t
+    L.tsff_irf_saved_bytes.argtypes = [C.POINTER(IrfCfg), i64]
+    L.tsff_irf_saved_bytes.restype = C.c_size_t
+    L.tsff_irf_fwd.argtypes = [C.POINTER(IrfCfg), i64, dp, dp, C.c_int32, dp, dp, dp, vp, vp, vp]
+    L.tsff_irf_fwd.restype = C.c_int
+    L.tsff_irf_bwd.argtypes = [C.POINTER(IrfCfg), i64, dp, C.c_int32, dp, vp, dp, dp, dp, vp, vp]
+    L.tsff_irf_bwd.restype = C.c_int
+    L.tsff_loss_fwd_bwd.argtypes = [i64, C.c_int32, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, vp]
+    L.tsff_loss_fwd_bwd.restype = C.c_int
     _lib = L
     return L
 

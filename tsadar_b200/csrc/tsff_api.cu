@@ -77,7 +77,7 @@ PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
   L.pend = o; o += align_up((size_t)B * 2 * 8);
   L.desc = o; o += align_up((size_t)B * P * 16);
   L.Dbar = o; o += align_up((size_t)B * L.npad * 8);
-  L.pendbar = o; o += align_up((size_t)B * 2 * 8);
+  L.pendbar = o; o += align_up((size_t)B * L.npad * 8);
   L.tI = o; o += align_up((size_t)B * P * 8);
   L.tdI = o; o += align_up((size_t)B * P * 8);
   L.bytes = o;
@@ -90,9 +90,8 @@ __global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, do
   const double* fb = f + b * N;
   const int M = N - 2;
   for (int i = threadIdx.x; i < npad; i += kThreads) {
-    double d = pv_weight(fb, M, h, i);
-    D[b * npad + i] = (float)d;
-    D64[b * npad + i] = d;
+    D[b * npad + i] = (i >= 1 && i <= M - 1) ? (float)(fb[i] * h) : 0.f;  // far-field weights p_i * h
+    D64[b * npad + i] = pv_weight(fb, M, h, i);                            // FP64 validation path
   }
   if (threadIdx.x == 0) {
     pend[2 * b] = fb[0];
@@ -101,42 +100,21 @@ __global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, do
 }
 
 __global__ void __launch_bounds__(kThreads) k_pv_desc(const double* pole, const double* out_bar, int P, double z0, double h,
-                                                      int nodes, float4* desc, double* pendbar) {
-  __shared__ double sred[2 * (kThreads / 32)];
+                                                      int nodes, int npad, float4* desc, double* pnear) {
   const long long b = blockIdx.x;
-  const double zM = z0 + (double)(nodes - 1) * h;
-  double e0 = 0.0, eM = 0.0;
   for (int p = threadIdx.x; p < P; p += kThreads) {
     const double xi = pole[b * P + p], ob = out_bar[b * P + p];
     float u0, nd;
     pole_split(xi, z0, h, nodes, u0, nd);
-    desc[b * P + p] = make_float4(u0, nd, (float)ob, 0.f);
-    e0 += ob * (-1.0 - log(fmax(fabs(z0 - xi), 1e-300)));
-    eM += ob * (1.0 + log(fmax(fabs(zM - xi), 1e-300)));
+    desc[b * P + p] = make_float4(u0, nd, (float)(ob * h), 0.f);
+    pv_bwd_pole_exact(xi, ob, z0, h, nodes, pnear + b * npad);
   }
-  double vals[2] = {e0, eM};
-  block_accumulate<kThreads / 32>(vals, 2, sred, pendbar + 2 * b);
 }
 
-__global__ void __launch_bounds__(kThreads) k_pv_bwd_finish(const double* Dbar, const double* pendbar, int N, int npad, double h,
+__global__ void __launch_bounds__(kThreads) k_pv_bwd_finish(const double* pfar, const double* pnear, int N, int npad,
                                                             double* f_bar) {
   const long long b = blockIdx.x;
-  const int M = N - 2;
-  const double ih = 1.0 / h;
-  const double* Db = Dbar + b * npad;
-  for (int i = threadIdx.x; i < N; i += kThreads) {
-    double pb = 0.0;
-    if (i <= M) {
-      double t = 0.0;
-      if (i >= 1) t += Db[i - 1];
-      t -= Db[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
-      if (i + 1 <= M) t += Db[i + 1];
-      pb = t * ih;
-      if (i == 0) pb += pendbar[2 * b];
-      if (i == M) pb += pendbar[2 * b + 1];
-    }
-    f_bar[b * N + i] = pb;
-  }
+  for (int i = threadIdx.x; i < N; i += kThreads) f_bar[b * N + i] = (i < npad) ? pfar[b * npad + i] + pnear[b * npad + i] : 0.0;
 }
 
 __global__ void k_mul(const double* x, const double* y, long long n, double* out) {
@@ -144,10 +122,11 @@ __global__ void k_mul(const double* x, const double* y, long long n, double* out
   if (t < n) out[t] = x[t] * y[t];
 }
 
-int launch_poles(const PvLayout& L, int64_t B, int64_t P, char* w, double z0, double h, const double* pole, double* out,
+int launch_poles(const PvLayout& L, int64_t B, int64_t N, int64_t P, const double* f, char* w, double z0, double h, const double* pole, double* out,
                  double* dout, int prec, cudaStream_t st) {
   PvPolesArgs p;
   p.D = (float*)(w + L.D); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
+  p.pnodes = f; p.pnode_stride = N;
   p.poles = pole; p.pole_bstride = P; p.z0 = z0; p.h = h; p.nodes = L.nodes; p.npad = L.npad; p.P = (int)P;
   p.outI = out; p.outdI = dout;
   p.ntiles = (int)((P + kPvThreads - 1) / kPvThreads);
@@ -155,7 +134,7 @@ int launch_poles(const PvLayout& L, int64_t B, int64_t P, char* w, double z0, do
   if (prec == TSFF_PV_FP64) {
     k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
   } else {
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_pv_poles<1, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN((k_pv_poles<1, TSFF_PV_FP32>));
     k_pv_poles<1, TSFF_PV_FP32><<<(unsigned)(B * p.ntiles), kPvThreads, smem, st>>>(p);
   }
   TSFF_LAUNCH_OK("k_pv_poles");
@@ -177,7 +156,7 @@ extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   char* w = static_cast<char*>(ws);
   k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
   TSFF_LAUNCH_OK("k_pv_prep");
-  return launch_poles(L, B, P, w, z0, h, pole, out, dout_dpole, pv_precision, st);
+  return launch_poles(L, B, N, P, f, w, z0, h, pole, out, dout_dpole, pv_precision, st);
 }
 
 extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
@@ -186,20 +165,20 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);
-  TSFF_CUDA_OK(cudaMemsetAsync(w + L.pendbar, 0, (size_t)B * 16, st));
-  k_pv_desc<<<(unsigned)B, kThreads, 0, st>>>(pole, out_bar, (int)P, z0, h, L.nodes, (float4*)(w + L.desc), (double*)(w + L.pendbar));
+  TSFF_CUDA_OK(cudaMemsetAsync(w + L.pendbar, 0, (size_t)B * L.npad * 8, st));
+  k_pv_desc<<<(unsigned)B, kThreads, 0, st>>>(pole, out_bar, (int)P, z0, h, L.nodes, L.npad, (float4*)(w + L.desc), (double*)(w + L.pendbar));
   TSFF_LAUNCH_OK("k_pv_desc");
   PvNodesArgs n;
-  n.desc = (float4*)(w + L.desc); n.P = (int)P; n.npad = L.npad; n.h = (float)h; n.Dbar = (double*)(w + L.Dbar);
+  n.desc = (float4*)(w + L.desc); n.P = (int)P; n.nodes = L.nodes; n.npad = L.npad; n.h = (float)h; n.pbar = (double*)(w + L.Dbar);
   n.ntiles = (L.npad + kPvThreads - 1) / kPvThreads;
   k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
   TSFF_LAUNCH_OK("k_pv_nodes");
-  k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, h, f_bar);
+  k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, f_bar);
   TSFF_LAUNCH_OK("k_pv_bwd_finish");
   if (pole_bar) {
     k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
     TSFF_LAUNCH_OK("k_pv_prep");
-    int rc = launch_poles(L, B, P, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);
+    int rc = launch_poles(L, B, N, P, f, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);
     if (rc) return rc;
     const long long n2 = (long long)B * P;
     k_mul<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(out_bar, (double*)(w + L.tdI), n2, pole_bar);

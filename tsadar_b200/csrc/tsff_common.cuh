@@ -29,6 +29,11 @@ void set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
+// Opt a kernel in to large dynamic shared memory.  Always raise the cap to the device maximum: the attribute is a
+// per-function CAP, so setting it to "what this launch needs" would make a later, larger launch fail.
+#define TSFF_SMEM_OPTIN(kernel)                                                                          \
+  TSFF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+
 #define TSFF_LAUNCH_OK(name)                                                                 \
   do {                                                                                       \
     cudaError_t _e = cudaGetLastError();                                                     \

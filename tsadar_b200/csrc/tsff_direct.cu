@@ -110,15 +110,18 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
   }
   const int M = a.nodes - 1;
   for (int i = threadIdx.x; i < a.npad; i += kThreads) {
-    double d = 0.0;
-    if (i <= M) {
-      double pc = grad_at(fe, a.V, a.dv, i);
-      double sR = (i < M) ? (grad_at(fe, a.V, a.dv, i + 1) - pc) / a.dv : 0.0;
-      double sL = (i > 0) ? (pc - grad_at(fe, a.V, a.dv, i - 1)) / a.dv : 0.0;
-      d = sR - sL;
+    // far-field node weights p_i * h of the interior nodes (the two end nodes are summed exactly per pole)
+    a.D[b * a.npad + i] = (i >= 1 && i <= M - 1) ? (float)(grad_at(fe, a.V, a.dv, i) * a.dv) : 0.f;
+    if (a.D64) {  // log-form weights for the FP64 validation path
+      double d = 0.0;
+      if (i <= M) {
+        double pc = grad_at(fe, a.V, a.dv, i);
+        double sR = (i < M) ? (grad_at(fe, a.V, a.dv, i + 1) - pc) / a.dv : 0.0;
+        double sL = (i > 0) ? (pc - grad_at(fe, a.V, a.dv, i - 1)) / a.dv : 0.0;
+        d = sR - sL;
+      }
+      a.D64[b * a.npad + i] = d;
     }
-    a.D[b * a.npad + i] = (float)d;
-    if (a.D64) a.D64[b * a.npad + i] = d;
   }
   if (threadIdx.x == 0) {
     a.pend[2 * b] = grad_at(fe, a.V, a.dv, 0);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) k_direct_fwd(const DirectArgs a) {
     g0d[r] = a.v0 - q.xie;
   }
   double accI[R], accJ[R];
-  if (PREC == TSFF_PV_FP32) pv_accumulate<R, true>(sD, a.npad / kPvBlk, (float)a.dv, u0, nd, accI, accJ);
+  if (PREC == TSFF_PV_FP32) pv_accumulate<R, true>(sD, a.npad / kPvBlk, far_coef(a.dv), u0, nd, accI, accJ);
   else pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.dv, g0d, accI, accJ);
 
   const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
@@ -171,7 +174,15 @@ __global__ void __launch_bounds__(kThreads) k_direct_fwd(const DirectArgs a) {
     IonOut io;
     ion_forward(sL, a.nI, a.zt, q, io);
     double I, dI;
-    pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.dv, I, dI);
+    if (PREC == TSFF_PV_FP32) {
+      const int V = a.V;
+      const double dv = a.dv;
+      pv_near_exact(q.xie, a.v0, dv, a.nodes, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
+      I += accI[r];
+      dI += accJ[r];
+    } else {
+      pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.dv, I, dI);
+    }
     int i_f; double t_f, sl_f;
     const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);   // form_factor.py:376
     const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
@@ -215,7 +226,6 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
   __syncthreads();
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int WA = a.W * a.A;
-  const double zM = a.v0 + (double)(a.nodes - 1) * a.dv;
   LG Lb;
   lg_zero(Lb);
   for (int r = 0; r < R; r++) {
@@ -257,15 +267,12 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
       atomicAdd(&a.accdf[b * a.V + i_f], (1.0 - t_f) * dfe_bar);
       atomicAdd(&a.accdf[b * a.V + i_f + 1], t_f * dfe_bar);
     }
-    // endpoint terms of I:  dI/dp0 = -1 - ln|g0|,  dI/dpM = 1 + ln|gM|
-    const double gg0 = a.v0 - q.xie, ggM = zM - q.xie;
-    const double l0 = log(fmax(fabs(gg0), 1e-300)), lM = log(fmax(fabs(ggM), 1e-300));
-    atomicAdd(&a.pendbar[2 * b], Ibar * (-1.0 - l0));
-    atomicAdd(&a.pendbar[2 * b + 1], Ibar * (1.0 + lM));
+    // d I / d p_i for the nodes next to the pole and the two end nodes, exactly (FP64); the far field is k_pv_nodes'
+    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, a.accdf + b * a.V);
     kin_backward(sL, omgs, cth, q, kb, Lb);
     float u0, nd;
     pole_split(q.xie, a.v0, a.dv, a.nodes, u0, nd);
-    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = make_float4(u0, nd, (float)Ibar, 0.f);
+    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = make_float4(u0, nd, (float)(Ibar * a.dv), 0.f);
   }
   double vals[kLGDoubles];
   store_lg(vals, Lb);
@@ -279,21 +286,9 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_finish(const DirectArgs
   double* spb = reinterpret_cast<double*>(smem_raw);  // pbar[V]
   const long long b = blockIdx.x;
   const int V = a.V, M = a.nodes - 1;
-  const double* Dbar = a.Dbar + b * a.npad;
+  const double* pfar = a.Dbar + b * a.npad;  // far-field part of df_bar from k_pv_nodes
   const double ih = 1.0 / a.dv;
-  for (int i = threadIdx.x; i < V; i += kThreads) {
-    double pb = a.accdf[b * V + i];
-    if (i <= M) {
-      double t = 0.0;
-      if (i >= 1) t += Dbar[i - 1];
-      t -= Dbar[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
-      if (i + 1 <= M) t += Dbar[i + 1];
-      pb += t * ih;
-      if (i == 0) pb += a.pendbar[2 * b];
-      if (i == M) pb += a.pendbar[2 * b + 1];
-    }
-    spb[i] = pb;
-  }
+  for (int i = threadIdx.x; i < V; i += kThreads) spb[i] = a.accdf[b * V + i] + (i <= M ? pfar[i] : 0.0);
   __syncthreads();
   T* fe_bar = static_cast<T*>(a.fe_bar) + b * V;
   for (int k = threadIdx.x; k < V; k += kThreads) {
@@ -349,11 +344,11 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   } else if (useR2) {
     a.ntiles = (int)tiles2;
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_fwd<2, T, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN((k_direct_fwd<2, T, TSFF_PV_FP32>));
     k_direct_fwd<2, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
   } else {
     a.ntiles = (WA + kThreads - 1) / kThreads;
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_fwd<1, T, TSFF_PV_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN((k_direct_fwd<1, T, TSFF_PV_FP32>));
     k_direct_fwd<1, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
   }
   TSFF_LAUNCH_OK("k_direct_fwd");
@@ -388,7 +383,7 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
   PvNodesArgs n;
-  n.desc = a.desc; n.P = c->G * WA; n.npad = c->pv_npad; n.h = (float)c->dv; n.Dbar = a.Dbar;
+  n.desc = a.desc; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.h = (float)c->dv; n.pbar = a.Dbar;
   const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
   if ((long long)B * tiles4 >= 2LL * c->sm_count) {
     n.ntiles = (int)tiles4;
@@ -399,7 +394,7 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   }
   TSFF_LAUNCH_OK("k_pv_nodes");
   const size_t smem = (size_t)c->V * 8;
-  TSFF_CUDA_OK(cudaFuncSetAttribute(k_direct_bwd_finish<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TSFF_SMEM_OPTIN(k_direct_bwd_finish<T>);
   k_direct_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_finish");
   return TSFF_OK;

@@ -1,0 +1,407 @@
+// tsff_irf.cu -- instrument response + CCD binning + amplitude scaling (irf.add_electron_IRF / add_ion_IRF,
+// tsadar/core/physics/irf.py:50-132) and the masked loss (loss_function.py:190-267, 386-418), forward + adjoint.
+//
+// The reference convolves with a full-length Gaussian (jnp.convolve(model, g, "same"), irf.py:72,114).  The taps
+// are negligible beyond a few sigma, so the kernels truncate them at cut_sigma (default 12 sigma: e^-72 relative,
+// below the 1e-21 dynamic range of the golden vector).  All arithmetic FP64; HBM traffic is (W + nbins) doubles per
+// spectrum, so these stages are bandwidth/latency-bound and tiny next to the form factor.
+//
+//   k_irf_conv       tiled 'same' convolution (shared-memory halo) + per-tile max of x and of conv(x)
+//   k_irf_finish     per lineout: global maxima, rescale, bin to pixels, amplitude normalisation
+//   k_irf_bwd_pre    per lineout: reverse of k_irf_finish -> cotangent of conv(x), amplitudes, max(x) term
+//   k_irf_bwd_conv   tiled correlation with the same taps -> cotangent of the model spectrum
+//   k_loss           fused weighted loss + its gradient wrt the theory spectrum
+#include "tsff_common.cuh"
+
+using namespace tsff;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 512;  // outputs per CTA in the convolution kernels
+
+struct IrfGeom {
+  int W, nbins, r, K;      // r = W / nbins samples per pixel; K = tap half-width in samples
+  double dlam, half;       // sample spacing; tap centre offset: d = n - m - half  (half = 0.5 for even W, 0 for odd)
+  double inv2s2, gnorm;    // Gaussian 1/(2 sigma^2), 1/(sigma sqrt(2 pi))
+  int ntiles;
+};
+
+IrfGeom irf_geom(const tsff_irf_cfg* c) {
+  IrfGeom g;
+  g.W = c->W; g.nbins = c->nbins; g.r = c->W / c->nbins;
+  g.dlam = (c->lam_max - c->lam_min) / (double)(c->W - 1);
+  g.half = (c->W % 2 == 0) ? 0.5 : 0.0;
+  const double cut = c->cut_sigma > 0 ? c->cut_sigma : 12.0;
+  g.K = (int)ceil(cut * c->stddev / g.dlam) + 1;
+  if (g.K > c->W) g.K = c->W;
+  g.inv2s2 = 1.0 / (2.0 * c->stddev * c->stddev);
+  g.gnorm = 1.0 / (c->stddev * sqrt(2.0 * kPi));
+  g.ntiles = (c->W + kTile - 1) / kTile;
+  return g;
+}
+
+struct IrfStats {  // per lineout, written by k_irf_finish, read by the backward kernels
+  double mx, my, mb;
+  int im, iy, qm, pad;
+};
+
+struct IrfLayout {
+  size_t w_yc, w_pmax, w_ycbar, bytes;
+};
+IrfLayout irf_layout(const IrfGeom& g, int64_t B) {
+  IrfLayout L;
+  size_t o = 0;
+  L.w_yc = o; o += align_up((size_t)B * g.W * 8);
+  L.w_pmax = o; o += align_up((size_t)B * g.ntiles * 4 * 8);
+  L.w_ycbar = o; o += align_up((size_t)B * g.W * 8);
+  L.bytes = o;
+  return L;
+}
+
+// tap weight for output n, input m:  G((n - m - half) dlam)     (irf.py:110-114 with 'same' alignment)
+__device__ __forceinline__ double tap(const IrfGeom& g, int n, int m) {
+  const double d = ((double)(n - m) - g.half) * g.dlam;
+  return g.gnorm * exp(-d * d * g.inv2s2);
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------
+// dynamic smem: x halo [kTile + 2K] | taps [2K + 2]
+__global__ void __launch_bounds__(kThreads) k_irf_conv(const IrfGeom g, const double* __restrict__ x, double* __restrict__ yc,
+                                                      double* __restrict__ pmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_rv[2 * (kThreads / 32)];
+  __shared__ int s_ri[2 * (kThreads / 32)];
+  double* s_x = reinterpret_cast<double*>(smem_raw);
+  double* s_g = s_x + (kTile + 2 * g.K);
+  const int tile = blockIdx.x % g.ntiles;
+  const long long b = blockIdx.x / g.ntiles;
+  const int n0 = tile * kTile;
+  const double* xb = x + b * g.W;
+  for (int i = threadIdx.x; i < kTile + 2 * g.K; i += kThreads) {
+    const int m = n0 - g.K + i;
+    s_x[i] = (m >= 0 && m < g.W) ? xb[m] : 0.0;
+  }
+  // taps for offsets o = n - m in [-K, K]: s_g[o + K]
+  for (int i = threadIdx.x; i < 2 * g.K + 1; i += kThreads) {
+    const double d = ((double)(i - g.K) - g.half) * g.dlam;
+    s_g[i] = g.gnorm * exp(-d * d * g.inv2s2);
+  }
+  __syncthreads();
+  double vmax_y = -INFINITY, vmax_x = -INFINITY;
+  int imax_y = 0, imax_x = 0;
+  for (int t = threadIdx.x; t < kTile; t += kThreads) {
+    const int n = n0 + t;
+    if (n >= g.W) break;
+    double acc = 0.0;
+    // y[n] = sum_m x[m] G(n - m - half);  m = n - o, o in [-K, K];  s_x index of m: m - n0 + K = t - o + K
+    for (int o = -g.K; o <= g.K; o++) acc = fma(s_x[t - o + g.K], s_g[o + g.K], acc);
+    yc[b * g.W + n] = acc;
+    if (acc > vmax_y) { vmax_y = acc; imax_y = n; }
+    const double xv = s_x[t + g.K];
+    if (xv > vmax_x) { vmax_x = xv; imax_x = n; }
+  }
+  // block arg-max (first index wins on ties, like jnp.argmax)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double v = __shfl_down_sync(0xffffffffu, vmax_y, o); int i = __shfl_down_sync(0xffffffffu, imax_y, o);
+    if (v > vmax_y || (v == vmax_y && i < imax_y)) { vmax_y = v; imax_y = i; }
+    v = __shfl_down_sync(0xffffffffu, vmax_x, o); i = __shfl_down_sync(0xffffffffu, imax_x, o);
+    if (v > vmax_x || (v == vmax_x && i < imax_x)) { vmax_x = v; imax_x = i; }
+  }
+  if (lane == 0) { s_rv[2 * wid] = vmax_y; s_ri[2 * wid] = imax_y; s_rv[2 * wid + 1] = vmax_x; s_ri[2 * wid + 1] = imax_x; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; w++) {
+      if (s_rv[2 * w] > vmax_y || (s_rv[2 * w] == vmax_y && s_ri[2 * w] < imax_y)) { vmax_y = s_rv[2 * w]; imax_y = s_ri[2 * w]; }
+      if (s_rv[2 * w + 1] > vmax_x || (s_rv[2 * w + 1] == vmax_x && s_ri[2 * w + 1] < imax_x)) { vmax_x = s_rv[2 * w + 1]; imax_x = s_ri[2 * w + 1]; }
+    }
+    double* pm = pmax + (b * g.ntiles + tile) * 4;
+    pm[0] = vmax_y; pm[1] = (double)imax_y; pm[2] = vmax_x; pm[3] = (double)imax_x;
+  }
+}
+
+struct IrfCall {
+  int kind, norm, NP;
+  double lam_min;
+  const double *params, *amps, *noise;
+  double* thry;
+  IrfStats* stats;
+  // backward
+  const double* thry_bar;
+  double* ycbar;
+  double* amp_bar;   // [B][3]
+  double* xbar_max;  // [B] cotangent that lands on x[argmax x]
+};
+
+// dynamic smem: yb[nbins]
+__global__ void __launch_bounds__(kThreads) k_irf_finish(const IrfGeom g, const IrfCall c, const double* __restrict__ yc,
+                                                        const double* __restrict__ pmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_stat[4];
+  __shared__ int s_idx[3];
+  double* s_yb = reinterpret_cast<double*>(smem_raw);
+  const long long b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double my = -INFINITY, mx = -INFINITY; int iy = 0, im = 0;
+    for (int t = 0; t < g.ntiles; t++) {
+      const double* pm = pmax + (b * g.ntiles + t) * 4;
+      if (pm[0] > my) { my = pm[0]; iy = (int)pm[1]; }
+      if (pm[2] > mx) { mx = pm[2]; im = (int)pm[3]; }
+    }
+    s_stat[0] = mx; s_stat[1] = my; s_idx[0] = im; s_idx[1] = iy;
+  }
+  __syncthreads();
+  const double s = s_stat[0] / s_stat[1];  // irf.py:73,115  max(model)/max(conv)
+  for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
+    double a = 0.0;
+    for (int k = 0; k < g.r; k++) a += yc[b * g.W + q * g.r + k];
+    s_yb[q] = s * a / (double)g.r;             // irf.py:74,124  reshape(1024,-1).mean
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mb = -INFINITY; int qm = 0;
+    for (int q = 0; q < g.nbins; q++) if (s_yb[q] > mb) { mb = s_yb[q]; qm = q; }
+    s_stat[2] = mb; s_idx[2] = qm;
+    IrfStats st; st.mx = s_stat[0]; st.my = s_stat[1]; st.mb = mb; st.im = s_idx[0]; st.iy = s_idx[1]; st.qm = qm; st.pad = 0;
+    c.stats[b] = st;
+  }
+  __syncthreads();
+  const double mb = s_stat[2];
+  const double* p = c.params + b * c.NP;
+  const double amps = c.amps[b];
+  for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
+    // binned wavelength axis: mean of r consecutive samples of the uniform axis (irf.py:76,126)
+    const double lamq = c.lam_min + ((double)(q * g.r) + 0.5 * (double)(g.r - 1)) * g.dlam;
+    double v;
+    if (c.kind == 0) {  // electron: amps*y/max(y), then amp1 (lam < lamL) or amp2   irf.py:127-130
+      const double a = (lamq < p[P_LAM]) ? p[P_AMP1] : p[P_AMP2];
+      v = a * (amps * s_yb[q] / mb);
+    } else {            // ion: amp3*amps*y/max(y)                                   irf.py:77
+      v = p[P_AMP3] * amps * s_yb[q] / mb;
+    }
+    if (c.noise) v += c.noise[b * g.nbins + q];   // thomson_diagnostic.py:139-140
+    c.thry[b * g.nbins + q] = v;
+  }
+}
+
+// ---- backward -------------------------------------------------------------------------------------------------
+// dynamic smem: ybbar[nbins]
+__global__ void __launch_bounds__(kThreads) k_irf_bwd_pre(const IrfGeom g, const IrfCall c, const double* __restrict__ yc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sred[4 * (kThreads / 32)];
+  __shared__ double s_tot[4];
+  double* s_ybbar = reinterpret_cast<double*>(smem_raw);
+  const long long b = blockIdx.x;
+  const IrfStats st = c.stats[b];
+  const double s = st.mx / st.my;
+  const double* p = c.params + b * c.NP;
+  const double amps = c.amps[b];
+  // out_q = A_q * yb_q / mb with A_q = a_q*amps (electron) or amp3*amps (ion); yb_q = s * mean_k yc
+  double part[4] = {0.0, 0.0, 0.0, 0.0};  // mb_bar, amp1_bar|amp3_bar, amp2_bar, unused
+  for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
+    const double lamq = c.lam_min + ((double)(q * g.r) + 0.5 * (double)(g.r - 1)) * g.dlam;
+    double ysum = 0.0;
+    for (int k = 0; k < g.r; k++) ysum += yc[b * g.W + q * g.r + k];
+    const double ybq = s * ysum / (double)g.r;
+    const double ob = c.thry_bar[b * g.nbins + q];
+    double A;
+    if (c.kind == 0) {
+      const bool blue = lamq < p[P_LAM];
+      A = (blue ? p[P_AMP1] : p[P_AMP2]) * amps;
+      part[blue ? 1 : 2] += ob * amps * ybq / st.mb;
+    } else {
+      A = p[P_AMP3] * amps;
+      part[1] += ob * amps * ybq / st.mb;
+    }
+    s_ybbar[q] = ob * A / st.mb;
+    part[0] += -ob * A * ybq / (st.mb * st.mb);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < 3; k++) {
+    double v = warp_sum(part[k]);
+    if (lane == 0) sred[k * (kThreads / 32) + wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int w = 0; w < kThreads / 32; w++) v += sred[threadIdx.x * (kThreads / 32) + w];
+    s_tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_ybbar[st.qm] += s_tot[0];  // max(yb) routes its cotangent to the arg-max bin
+    double* ab = c.amp_bar + b * 3;
+    if (c.kind == 0) { ab[0] = s_tot[1]; ab[1] = s_tot[2]; ab[2] = 0.0; }
+    else             { ab[0] = 0.0; ab[1] = 0.0; ab[2] = s_tot[1]; }
+  }
+  __syncthreads();
+  // y_n = s * yc_n  ->  ycbar_n = s * ybbar_{n/r} / r ;  s_bar = sum_n ybbar_{n/r}/r * yc_n
+  double sbar = 0.0;
+  for (int n = threadIdx.x; n < g.W; n += kThreads) {
+    const double yb = s_ybbar[n / g.r] / (double)g.r;
+    const double v = yc[b * g.W + n];
+    c.ycbar[b * g.W + n] = s * yb;
+    sbar += yb * v;
+  }
+  sbar = warp_sum(sbar);
+  __syncthreads();
+  if (lane == 0) sred[wid] = sbar;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; w++) t += sred[w];
+    // s = mx/my
+    c.ycbar[b * g.W + st.iy] += -t * st.mx / (st.my * st.my);
+    c.xbar_max[b] = t / st.my;
+  }
+}
+
+// xbar_m = sum_n ycbar_n G(n - m - half)  (+ the max(x) term).  dynamic smem: ycbar halo [kTile + 2K] | taps
+__global__ void __launch_bounds__(kThreads) k_irf_bwd_conv(const IrfGeom g, const IrfCall c, double* __restrict__ xbar) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_y = reinterpret_cast<double*>(smem_raw);
+  double* s_g = s_y + (kTile + 2 * g.K);
+  const int tile = blockIdx.x % g.ntiles;
+  const long long b = blockIdx.x / g.ntiles;
+  const int m0 = tile * kTile;
+  for (int i = threadIdx.x; i < kTile + 2 * g.K; i += kThreads) {
+    const int n = m0 - g.K + i;
+    s_y[i] = (n >= 0 && n < g.W) ? c.ycbar[b * g.W + n] : 0.0;
+  }
+  for (int i = threadIdx.x; i < 2 * g.K + 1; i += kThreads) {
+    const double d = ((double)(i - g.K) - g.half) * g.dlam;
+    s_g[i] = g.gnorm * exp(-d * d * g.inv2s2);
+  }
+  __syncthreads();
+  const int im = c.stats[b].im;
+  for (int t = threadIdx.x; t < kTile; t += kThreads) {
+    const int m = m0 + t;
+    if (m >= g.W) break;
+    double acc = 0.0;
+    // n = m + o, o in [-K, K];  s_y index of n: n - m0 + K = t + o + K
+    for (int o = -g.K; o <= g.K; o++) acc = fma(s_y[t + o + g.K], s_g[o + g.K], acc);
+    if (m == im) acc += c.xbar_max[b];
+    xbar[b * g.W + m] = acc;
+  }
+}
+
+// ---- loss ---------------------------------------------------------------------------------------------------
+// loss = scale * sum_{b,q} weight[q] * err(d, t);  theory_bar = d loss / d theory      (loss_function.py:386-418)
+__global__ void __launch_bounds__(kThreads) k_loss(long long total, int n, const double* __restrict__ t, const double* __restrict__ d,
+                                                  const double* __restrict__ w, double uncert, double scale, int method,
+                                                  double* __restrict__ loss, double* __restrict__ tbar) {
+  __shared__ double sred[kThreads / 32];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const double wq = w[i % n];
+    double e = 0.0, ge = 0.0;
+    if (wq != 0.0) {
+      const double tv = t[i], dv = d[i], diff = dv - tv;
+      if (method == 0)      { e = diff * diff / uncert; ge = -2.0 * diff / uncert; }                // l2
+      else if (method == 1) { e = fabs(diff) / uncert; ge = (diff > 0 ? -1.0 : (diff < 0 ? 1.0 : 0.0)) / uncert; }  // l1
+      else if (method == 2) { e = log(cosh(diff)); ge = -tanh(diff); }                               // log-cosh
+      else                  { e = tv - dv * log(tv); ge = 1.0 - dv / tv; }                           // poisson
+    }
+    acc += wq * e;
+    if (tbar) tbar[i] = scale * wq * ge;
+  }
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sred[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < kThreads / 32; k++) s += sred[k];
+    atomicAdd(loss, scale * s);
+  }
+}
+
+int check_cfg(const tsff_irf_cfg* c) {
+  if (!c || c->W < 2 || c->nbins < 1 || c->W % c->nbins != 0 || !(c->stddev > 0.0)) {
+    set_error("bad irf cfg (W must be a multiple of nbins, stddev > 0)");
+    return TSFF_E_INVALID;
+  }
+  if (c->norm != 0) { set_error("PhysParams.norm > 0 is not implemented (every reference deck uses norm: 0)"); return TSFF_E_INVALID; }
+  if (c->kind != 0 && c->kind != 1) { set_error("irf kind must be 0 (electron) or 1 (ion)"); return TSFF_E_INVALID; }
+  return TSFF_OK;
+}
+
+}  // namespace
+
+extern "C" size_t tsff_irf_workspace_bytes(const tsff_irf_cfg* c, int64_t B) {
+  if (check_cfg(c) || B < 1) return 0;
+  return irf_layout(irf_geom(c), B).bytes + align_up((size_t)B * 8);
+}
+extern "C" size_t tsff_irf_saved_bytes(const tsff_irf_cfg* c, int64_t B) {
+  if (check_cfg(c) || B < 1) return 0;
+  return align_up((size_t)B * sizeof(IrfStats)) + align_up((size_t)B * c->W * 8);
+}
+
+extern "C" int tsff_irf_fwd(const tsff_irf_cfg* c, int64_t B, const double* modl, const double* params, int32_t NP,
+                            const double* amps, const double* noise, double* thry, void* saved, void* ws, void* stream) {
+  int rc = check_cfg(c);
+  if (rc) return rc;
+  if (!modl || !params || !amps || !thry || !saved || !ws || B < 1) { set_error("null argument"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const IrfGeom g = irf_geom(c);
+  const IrfLayout L = irf_layout(g, B);
+  char* w = static_cast<char*>(ws);
+  char* sv = static_cast<char*>(saved);
+  // conv(x) is kept in `saved` for the backward pass
+  double* yc = (double*)(sv + align_up((size_t)B * sizeof(IrfStats)));
+  double* pmax = (double*)(w + L.w_pmax);
+  const size_t smem = (size_t)(kTile + 2 * g.K + 2 * g.K + 2) * 8;
+  if (smem > 200 * 1024) { set_error("IRF too wide for shared memory (K=%d)", g.K); return TSFF_E_INVALID; }
+  TSFF_SMEM_OPTIN(k_irf_conv);
+  k_irf_conv<<<(unsigned)(B * g.ntiles), kThreads, smem, st>>>(g, modl, yc, pmax);
+  TSFF_LAUNCH_OK("k_irf_conv");
+  IrfCall call;
+  memset(&call, 0, sizeof(call));
+  call.kind = c->kind; call.norm = c->norm; call.NP = NP; call.lam_min = c->lam_min;
+  call.params = params; call.amps = amps; call.noise = noise; call.thry = thry; call.stats = (IrfStats*)sv;
+  k_irf_finish<<<(unsigned)B, kThreads, (size_t)g.nbins * 8, st>>>(g, call, yc, pmax);
+  TSFF_LAUNCH_OK("k_irf_finish");
+  return TSFF_OK;
+}
+
+extern "C" int tsff_irf_bwd(const tsff_irf_cfg* c, int64_t B, const double* params, int32_t NP, const double* amps,
+                            const void* saved, const double* thry_bar, double* modl_bar, double* amp_bar, void* ws,
+                            void* stream) {
+  int rc = check_cfg(c);
+  if (rc) return rc;
+  if (!params || !amps || !saved || !thry_bar || !modl_bar || !amp_bar || !ws || B < 1) { set_error("null argument"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const IrfGeom g = irf_geom(c);
+  const IrfLayout L = irf_layout(g, B);
+  char* w = static_cast<char*>(ws);
+  const char* sv = static_cast<const char*>(saved);
+  const double* yc = (const double*)(sv + align_up((size_t)B * sizeof(IrfStats)));
+  IrfCall call;
+  memset(&call, 0, sizeof(call));
+  call.kind = c->kind; call.norm = c->norm; call.NP = NP; call.lam_min = c->lam_min;
+  call.params = params; call.amps = amps; call.stats = (IrfStats*)sv;
+  call.thry_bar = thry_bar; call.ycbar = (double*)(w + L.w_ycbar); call.amp_bar = amp_bar;
+  call.xbar_max = (double*)(w + L.bytes);
+  k_irf_bwd_pre<<<(unsigned)B, kThreads, (size_t)g.nbins * 8, st>>>(g, call, yc);
+  TSFF_LAUNCH_OK("k_irf_bwd_pre");
+  const size_t smem = (size_t)(kTile + 2 * g.K + 2 * g.K + 2) * 8;
+  TSFF_SMEM_OPTIN(k_irf_bwd_conv);
+  k_irf_bwd_conv<<<(unsigned)(B * g.ntiles), kThreads, smem, st>>>(g, call, modl_bar);
+  TSFF_LAUNCH_OK("k_irf_bwd_conv");
+  return TSFF_OK;
+}
+
+extern "C" int tsff_loss_fwd_bwd(int64_t B, int32_t n, const double* theory, const double* data, const double* weight,
+                                 double uncert, double scale, int method, double* loss_out, double* theory_bar,
+                                 void* stream) {
+  if (!theory || !data || !weight || !loss_out || B < 1 || n < 1 || method < 0 || method > 3) { set_error("bad argument"); return TSFF_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * n;
+  long long blocks = (total + kThreads - 1) / kThreads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_loss<<<(unsigned)blocks, kThreads, 0, st>>>(total, n, theory, data, weight, uncert, scale, method, loss_out, theory_bar);
+  TSFF_LAUNCH_OK("k_loss");
+  return TSFF_OK;
+}

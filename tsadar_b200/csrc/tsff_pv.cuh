@@ -4,19 +4,24 @@
 // (fixed pole grid xi2 against nodes xi1) and :385-386 (pole = phase velocity, nodes = the f-table grid).
 //
 // Restatement used here (exact algebra, checked against the oracle's literal ratcen):  with uniform nodes
-// z_i = z_0 + i h (i = 0..M, M = N-2: the reference's slices drop the last interval), node values p_i,
-// s_i = (p_{i+1}-p_i)/h, g_i = z_i - xi,
+// z_i = z_0 + i h (i = 0..M, M = N-2: the reference's slices drop the last interval), node values p_i, g_i = z_i - xi,
+// phi(g) = g ln|g|,
 //
-//     I(xi) = sum_{i<M} [dp_i + (pav_i - gav_i s_i) ln|g_{i+1}/g_i|]
-//           = (p_M - p_0) + p_M ln|g_M| - p_0 ln|g_0| + sum_{i=0..M} D_i g_i ln|g_i|,
-//     D_0 = s_0,  D_i = s_i - s_{i-1},  D_M = -s_{M-1}                      (summation by parts)
-//     dI/dxi = -p_M/g_M + p_0/g_0 - sum_i D_i ln|g_i|                        (sum_i D_i = 0)
+//     I(xi) = sum_{i<M} [dp_i + (pav_i - gav_i s_i) ln|g_{i+1}/g_i|]                      (ratcen, ratintn.py:41-52)
+//           = sum_{i=1..M-1} p_i W(g_i) + p_0 E_0 + p_M E_M                               (summation by parts, twice)
+//     W(g)  = [phi(g+h) - 2 phi(g) + phi(g-h)] / h
+//     E_0   = [phi(g_1) - phi(g_0)]/h - 1 - ln|g_0|,   E_M = [phi(g_{M-1}) - phi(g_M)]/h + 1 + ln|g_M|
 //
-// so one pass needs ONE MUFU.LG2 per (pole,node) pair and yields both I and dI/dxi; the weights D_i do not
-// depend on the pole and are staged once in shared memory.  Precision: the pole is
-// split in FP64 into its nearest node n and the remainder delta = xi - z_n (|delta| <= h/2), and
-// g_i = (i - n) h - delta is formed by one FFMA from exact small integers, so g keeps full FP32 relative
-// accuracy next to the pole.  FP32 partial sums cover 32 nodes and are folded into FP64 accumulators.
+// I is linear in p with pole-dependent weights W, so the forward sweep (sum over nodes for each pole) and the
+// adjoint sweep (sum over poles for each node) are transposes of one Cauchy-type kernel.  Far from the pole
+//     W(g)      =  x (1 + x^2/6 + x^4/15 + ...),        x = h/g
+//     dW/dxi    = (x/g)(1 + x^2/2 + x^4/3 + ...)
+// (one MUFU.RCP and a handful of FFMA per pair; terms are O(h/g), so FP32 rounding stays ~1e-8 of the sum);
+// the 2*kNearHalf+1 nodes next to the pole and the two end nodes are evaluated exactly in FP64 once per pole.
+// A first version summed D_i g_i lg2|g_i| (one MUFU.LG2 per pair): it is 15% faster but its terms are ~100x
+// larger than the sum, which costs two digits -- measured 2e-5 instead of 1e-6 on S at sharp EPW resonances.
+// Precision of g: the pole is split in FP64 into its nearest node n and the remainder delta = xi - z_n
+// (|delta| <= h/2); g_i = (i - n) h - delta is formed by FFMAs from exact small integers.
 #pragma once
 #include "tsff_math.cuh"
 
@@ -45,10 +50,38 @@ TSFF_HD void pole_split(double xi, double z0, double h, int nnodes, float& u0, f
   ndelta = (float)(-delta);
 }
 
-// Thread-owns-pole accumulation over all node blocks.  sD: pole-independent weights D_i (zero padded to a
-// multiple of 32).  For R poles per thread:  accI[r] = sum_i D_i g_i lg2|g_i|,  accJ[r] = sum_i D_i lg2|g_i|.
-template <int R, bool WITH_J>
-TSFF_HD void pv_accumulate(const float* sD, int nblk, float h, const float (&u0)[R], const float (&ndelta)[R],
+constexpr int kNearHalf = 8;  // nodes with |i - n_p| <= kNearHalf are handled exactly in FP64
+
+TSFF_HD float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return 1.0f / x;
+#endif
+}
+
+struct FarCoef {  // series coefficients with the powers of h folded in
+  float h_hi, h_lo, c2, c4, d2, d4;
+};
+TSFF_HD FarCoef far_coef(double h) {
+  FarCoef c;
+  c.h_hi = (float)h;
+  c.h_lo = (float)(h - (double)c.h_hi);
+  c.c2 = (float)(h * h / 6.0);
+  c.c4 = (float)(h * h * h * h / 15.0);
+  c.d2 = (float)(h * h / 2.0);
+  c.d4 = (float)(h * h * h * h / 3.0);
+  return c;
+}
+
+// Thread-owns-pole far-field accumulation over all node blocks.  sPh: pole-independent node weights p_i*h for the
+// interior nodes 1..M-1 (zero at i = 0, i >= M and in the padding).  For R poles per thread:
+//     accI[r] = sum_far p_i W(g_i),     accJ[r] = sum_far p_i dW/dxi(g_i),
+// "far" = |i - n_p| > kNearHalf.  GRP = nodes per FP32 partial sum before it is folded into the FP64 accumulator.
+template <int R, bool WITH_J, int GRP = 8>
+TSFF_HD void pv_accumulate(const float* sPh, int nblk, const FarCoef cf, const float (&u0)[R], const float (&ndelta)[R],
                            double (&accI)[R], double (&accJ)[R]) {
   float u[R];
 #pragma unroll
@@ -57,37 +90,118 @@ TSFF_HD void pv_accumulate(const float* sD, int nblk, float h, const float (&u0)
     accI[r] = 0.0;
     accJ[r] = 0.0;
   }
-  const float4* sD4 = reinterpret_cast<const float4*>(sD);
+  const float4* s4 = reinterpret_cast<const float4*>(sPh);
+  const float near_lo = -(float)(kNearHalf + kPvBlk - 1), near_hi = (float)kNearHalf;
   for (int b = 0; b < nblk; b++) {
-    float gb[R], aI[R], aJ[R];
+    float gb[R];
+    bool near_blk = false;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      gb[r] = fmaf(u[r], h, ndelta[r]);
-      aI[r] = 0.f;
-      aJ[r] = 0.f;
+      gb[r] = fmaf(u[r], cf.h_hi, fmaf(u[r], cf.h_lo, ndelta[r]));
+      near_blk = near_blk || (u[r] >= near_lo && u[r] <= near_hi);  // block [u, u+31] meets [-kNearHalf, kNearHalf]
     }
+    if (!near_blk) {
 #pragma unroll
-    for (int q = 0; q < kPvBlk / 4; q++) {
-      const float4 d = sD4[b * (kPvBlk / 4) + q];
-      const float dd[4] = {d.x, d.y, d.z, d.w};
+      for (int q0 = 0; q0 < kPvBlk / 4; q0 += GRP / 4) {
+        float aI[R], aJ[R];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
+        for (int r = 0; r < R; r++) aI[r] = aJ[r] = 0.f;
+#pragma unroll
+        for (int q = q0; q < q0 + GRP / 4; q++) {
+          const float4 d = s4[b * (kPvBlk / 4) + q];
+          const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const float g = fmaf((float)(4 * q + c), cf.h_hi, gb[r]);
+              const float rg = rcp_approx(g);
+              const float s2 = rg * rg;
+              aI[r] = fmaf(dd[c], rg * fmaf(fmaf(s2, cf.c4, cf.c2), s2, 1.f), aI[r]);
+              if (WITH_J) aJ[r] = fmaf(dd[c], s2 * fmaf(fmaf(s2, cf.d4, cf.d2), s2, 1.f), aJ[r]);
+            }
+          }
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          const float g = fmaf((float)(4 * q + c), h, gb[r]);
-          const float l = lg2_approx(fmaxf(fabsf(g), kTinyG));
-          aI[r] = fmaf(dd[c], g * l, aI[r]);
-          if (WITH_J) aJ[r] = fmaf(dd[c], l, aJ[r]);
+          accI[r] += (double)aI[r];
+          if (WITH_J) accJ[r] += (double)aJ[r];
+        }
+      }
+    } else {
+      // rare path (the one or two blocks around the pole): mask the near nodes, they are summed exactly elsewhere
+      float aI[R], aJ[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) aI[r] = aJ[r] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < kPvBlk; k++) {
+        const float w = sPh[b * kPvBlk + k];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float g = fmaf((float)k, cf.h_hi, gb[r]);
+          const bool far = fabsf(u[r] + (float)k) > (float)kNearHalf + 0.5f;
+          const float rg = far ? rcp_approx(g) : 0.f;
+          const float s2 = rg * rg;
+          aI[r] = fmaf(w, rg * fmaf(fmaf(s2, cf.c4, cf.c2), s2, 1.f), aI[r]);
+          if (WITH_J) aJ[r] = fmaf(w, s2 * fmaf(fmaf(s2, cf.d4, cf.d2), s2, 1.f), aJ[r]);
+        }
+        if ((k & 7) == 7) {
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            accI[r] += (double)aI[r];
+            if (WITH_J) accJ[r] += (double)aJ[r];
+            aI[r] = aJ[r] = 0.f;
+          }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      accI[r] += (double)aI[r];
-      if (WITH_J) accJ[r] += (double)aJ[r];
-      u[r] += (float)kPvBlk;
-    }
+    for (int r = 0; r < R; r++) u[r] += (float)kPvBlk;
   }
+}
+
+TSFF_HD double pv_phi(double g) { return g * log(fmax(fabs(g), 1e-300)); }
+
+// Exact FP64 part of I and dI/dxi for one pole: the near nodes (interior ones among n-kNearHalf..n+kNearHalf) and
+// the two end nodes.  `pget(i)` returns p_i as double.
+template <typename PGet>
+TSFF_HD void pv_near_exact(double xi, double z0, double h, int nodes, PGet pget, double& I, double& dI) {
+  const int M = nodes - 1;
+  double rn = rint((xi - z0) / h);
+  if (!(rn >= 0.0)) rn = 0.0;
+  if (rn > (double)M) rn = (double)M;
+  const int n = (int)rn;
+  int lo = n - kNearHalf, hi = n + kNearHalf;
+  if (lo < 1) lo = 1;
+  if (hi > M - 1) hi = M - 1;
+  const double ih = 1.0 / h;
+  double sI = 0.0, sJ = 0.0;
+  if (lo <= hi) {
+    double gm = z0 + (double)(lo - 1) * h - xi, gc = gm + h;
+    double lm = log(fmax(fabs(gm), 1e-300)), lc = log(fmax(fabs(gc), 1e-300));
+    for (int i = lo; i <= hi; i++) {
+      const double gc_i = z0 + (double)i * h - xi;
+      const double gp = z0 + (double)(i + 1) * h - xi;
+      const double lp = log(fmax(fabs(gp), 1e-300));
+      const double p = pget(i);
+      sI += p * (gp * lp - 2.0 * gc_i * lc + gm * lm) * ih;   // W
+      sJ += -p * (lp - 2.0 * lc + lm) * ih;                   // dW/dxi = -[phi'(g+h) - 2 phi'(g) + phi'(g-h)]/h
+      gm = gc_i;
+      lm = lc;
+      lc = lp;
+    }
+    (void)gc;
+  }
+  const double g0 = z0 - xi, gM = z0 + (double)M * h - xi;
+  const double l0 = log(fmax(fabs(g0), 1e-300)), l1 = log(fmax(fabs(g0 + h), 1e-300));
+  const double lM = log(fmax(fabs(gM), 1e-300)), lM1 = log(fmax(fabs(gM - h), 1e-300));
+  const double p0 = pget(0), pM = pget(M);
+  sI += p0 * (((g0 + h) * l1 - g0 * l0) * ih - 1.0 - l0);
+  sJ += p0 * (-(l1 - l0) * ih + 1.0 / g0);
+  sI += pM * (((gM - h) * lM1 - gM * lM) * ih + 1.0 + lM);
+  sJ += pM * (-(lM1 - lM) * ih - 1.0 / gM);
+  I = sI;
+  dI = sJ;
 }
 
 // FP64 twin of pv_accumulate (validation / "exact" mode): same algebra, log2 in double.

@@ -1,7 +1,7 @@
 // tsff_pv_kernels.cuh -- the two O(poles x nodes) kernels shared by every mode.
 //
-//   k_pv_poles : thread-owns-pole forward sweep   I(xi_p), dI/dxi_p          (1 MUFU.LG2 per pair)
-//   k_pv_nodes : thread-owns-node adjoint sweep   Dbar_i = sum_p Ibar_p g ln|g|  (1 MUFU.LG2 per pair)
+//   k_pv_poles : thread-owns-pole forward sweep   I(xi_p), dI/dxi_p          (1 MUFU.RCP per pair)
+//   k_pv_nodes : thread-owns-node adjoint sweep   pbar_i = sum_p Ibar_p W(g_{p,i})  (1 MUFU.RCP per pair)
 //
 // Bound: MUFU (XU) pipe, 16 lanes/clk/SM; the FP32 FMA pipe carries 3-4 ops per pair beside it.
 // Shared memory: the pole-independent weights D (<= 16 KB for 4096 nodes) staged by one TMA bulk copy;
@@ -14,9 +14,11 @@ namespace tsff {
 constexpr int kPvThreads = 256;
 
 struct PvPolesArgs {
-  const float* D;        // [B][npad] weights (FP32)
-  const double* D64;     // [B][npad] weights (FP64 validation path) or nullptr
+  const float* D;        // [B][npad] far-field node weights p_i*h (FP32; zero at i = 0, i >= M)
+  const double* D64;     // [B][npad] log-form weights D_i (FP64 validation path) or nullptr
   const double* pend;    // [B][2]   (p_0, p_M)
+  const double* pnodes;  // node values p_i (FP64), row b at pnodes + b*pnode_stride
+  long long pnode_stride;
   const double* poles;   // pole positions, row b at poles + b*pole_bstride
   long long pole_bstride;  // 0: all lineouts share one pole list (table mode)
   double z0, h;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
   }
   double accI[R], accJ[R];
   if (PREC == TSFF_PV_FP32) {
-    pv_accumulate<R, true>(sD, a.npad / kPvBlk, (float)a.h, u0, nd, accI, accJ);
+    pv_accumulate<R, true>(sD, a.npad / kPvBlk, far_coef(a.h), u0, nd, accI, accJ);
   } else {
     pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.h, g0d, accI, accJ);
   }
@@ -58,7 +60,14 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
     int p = tile * (kPvThreads * R) + r * kPvThreads + threadIdx.x;
     if (p < a.P) {
       double I, dI;
-      pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.h, I, dI);
+      if (PREC == TSFF_PV_FP32) {
+        const double* pn = a.pnodes + b * a.pnode_stride;
+        pv_near_exact(xi[r], a.z0, a.h, a.nodes, [pn](int i) { return pn[i]; }, I, dI);
+        I += accI[r];
+        dI += accJ[r];
+      } else {
+        pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.h, I, dI);
+      }
       a.outI[b * a.P + p] = I;
       if (a.outdI) a.outdI[b * a.P + p] = dI;
     }
@@ -66,14 +75,15 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
 }
 
 struct PvNodesArgs {
-  const float4* desc;  // [B][P]  (u0 = -n_p, nd = -delta_p, Ibar_p, unused)
-  int P, npad, ntiles;
+  const float4* desc;  // [B][P]  (u0 = -n_p, nd = -delta_p, Ibar_p * h, unused)
+  int P, nodes, npad, ntiles;
   float h;
-  double* Dbar;        // [B][npad]   Dbar_i = sum_p Ibar_p g_{p,i} ln|g_{p,i}|
+  double* pbar;        // [B][npad]  far-field part of d loss / d p_i for interior nodes 1..M-1 (0 elsewhere)
 };
 
 constexpr int kNodeChunk = 512;  // poles staged per shared-memory chunk (8 KB)
 
+// pbar_i (far part) = sum_p Ibar_p W(g_{p,i}) over poles with |i - n_p| > kNearHalf
 template <int R>
 __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
   __shared__ float4 sdesc[kNodeChunk];
@@ -81,6 +91,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
   const int tile = blockIdx.x % a.ntiles;
   const int i0 = (tile * kPvThreads + threadIdx.x) * R;
   const float fi0 = (float)i0;
+  const float c2 = a.h * a.h * (1.f / 6.f), c4 = a.h * a.h * a.h * a.h * (1.f / 15.f);
   const float4* desc = a.desc + b * a.P;
   double acc[R];
 #pragma unroll
@@ -89,7 +100,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
     const int nc = min(kNodeChunk, a.P - c0);
     __syncthreads();
     for (int k = threadIdx.x; k < kNodeChunk; k += kPvThreads)
-      sdesc[k] = (k < nc) ? desc[c0 + k] : make_float4(0.f, 1.f, 0.f, 0.f);
+      sdesc[k] = (k < nc) ? desc[c0 + k] : make_float4(1e6f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int s0 = 0; s0 < kNodeChunk; s0 += 64) {
       if (s0 >= nc) break;
@@ -99,21 +110,51 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
 #pragma unroll 8
       for (int k = 0; k < 64; k++) {
         const float4 d = sdesc[s0 + k];
-        const float gbase = fmaf(fi0 + d.x, a.h, d.y);
+        const float u = fi0 + d.x;              // i0 - n_p, exact
+        const float gbase = fmaf(u, a.h, d.y);  // g at node i0
 #pragma unroll
         for (int r = 0; r < R; r++) {
           const float g = fmaf((float)r, a.h, gbase);
-          const float l = lg2_approx(fmaxf(fabsf(g), kTinyG));
-          part[r] = fmaf(d.z, g * l, part[r]);
+          const float rg = rcp_approx(g);
+          const float s2 = rg * rg;
+          const float w = rg * fmaf(fmaf(s2, c4, c2), s2, 1.f);   // W / h
+          const float wm = (fabsf(u + (float)r) > (float)kNearHalf + 0.5f) ? w : 0.f;
+          part[r] = fmaf(d.z, wm, part[r]);
         }
       }
 #pragma unroll
       for (int r = 0; r < R; r++) acc[r] += (double)part[r];
     }
   }
+  const int M = a.nodes - 1;
 #pragma unroll
   for (int r = 0; r < R; r++)
-    if (i0 + r < a.npad) a.Dbar[b * a.npad + i0 + r] = kLn2 * acc[r];
+    if (i0 + r < a.npad) a.pbar[b * a.npad + i0 + r] = (i0 + r >= 1 && i0 + r <= M - 1) ? acc[r] : 0.0;
+}
+
+// Exact (FP64) adjoint contributions of one pole: the kNearHalf nodes either side of it and the two end nodes
+// (whose weights are first differences plus the explicit endpoint terms of I).  Atomically added to pnear[0..M].
+__device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, double* pnear) {
+  if (Ibar == 0.0) return;
+  const int M = nodes - 1;
+  double rn = rint((xi - z0) / h);
+  if (!(rn >= 0.0)) rn = 0.0;
+  if (rn > (double)M) rn = (double)M;
+  const int n = (int)rn;
+  const int lo = max(1, n - kNearHalf), hi = min(M - 1, n + kNearHalf);
+  const double ih = 1.0 / h;
+  if (lo <= hi) {
+    double pm = pv_phi(z0 + (double)(lo - 1) * h - xi), pc = pv_phi(z0 + (double)lo * h - xi);
+    for (int i = lo; i <= hi; i++) {
+      const double pp = pv_phi(z0 + (double)(i + 1) * h - xi);
+      atomicAdd(&pnear[i], Ibar * (pp - 2.0 * pc + pm) * ih);
+      pm = pc;
+      pc = pp;
+    }
+  }
+  const double g0 = z0 - xi, gM = z0 + (double)M * h - xi;
+  atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log(fmax(fabs(g0), 1e-300))));
+  atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log(fmax(fabs(gM), 1e-300))));
 }
 #endif
 

@@ -24,7 +24,7 @@ constexpr int kWarps = kThreads / 32;
 
 struct TableLayout {
   size_t s_lg, s_lnf, s_slope, s_ratmod, s_T, saved_bytes;
-  size_t w_D, w_D64, w_pend, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pendbar, w_lgbar, w_zero_end,
+  size_t w_D, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
       ws_bytes;
 };
 
@@ -41,13 +41,14 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
   L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
   L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
   L.w_pend = o; o += align_up((size_t)B * 2 * 8);
+  L.w_ratdf = o; o += align_up((size_t)B * kXi1N * 8);
   L.w_desc = o; o += align_up((size_t)B * kXi2N * 16);
   L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
   L.w_zero_begin = o;
   L.w_Tbar = o; o += align_up((size_t)B * kXi2N * 8);
   L.w_lnfbar = o; o += align_up((size_t)B * c->V * 8);
   L.w_slopebar = o; o += align_up((size_t)B * c->V * 8);
-  L.w_pendbar = o; o += align_up((size_t)B * 2 * 8);
+  L.w_pnear = o; o += align_up((size_t)B * kXi1N * 8);
   L.w_lgbar = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
   L.w_zero_end = o;
   L.ws_bytes = o;
@@ -65,13 +66,14 @@ struct TableArgs {
   float* D;
   double* D64;
   double* pend;
+  double* ratdf;
   double* modl;
   double* ff;
   // backward
   const double* modl_bar;
   const double* ff_bar;
   float4* desc;
-  double *Tbar, *lnfbar, *slopebar, *pendbar, *Dbar, *lgbar;
+  double *Tbar, *lnfbar, *slopebar, *pnear, *Dbar, *lgbar;
   double* params_bar;
   void* fe_bar;
 };
@@ -139,9 +141,9 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
   __syncthreads();
   const int M = a.nodes - 1;
   for (int i = threadIdx.x; i < a.npad; i += kThreads) {
-    double d = pv_weight(s_p, M, a.xi1_h, i);
-    a.D[b * a.npad + i] = (float)d;
-    if (a.D64) a.D64[b * a.npad + i] = d;
+    a.D[b * a.npad + i] = (i >= 1 && i <= M - 1) ? (float)(s_p[i] * a.xi1_h) : 0.f;   // far-field weights p_i * h
+    if (a.D64) a.D64[b * a.npad + i] = pv_weight(s_p, M, a.xi1_h, i);                  // FP64 validation path
+    a.ratdf[b * kXi1N + i] = (i < kXi1N) ? s_p[i] : 0.0;
   }
   if (threadIdx.x == 0) {
     a.pend[2 * b] = s_p[0];
@@ -300,24 +302,17 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
   }
 }
 
-// ---- Tbar -> descriptors + endpoint cotangents -----------------------------------------------------------------
+// ---- Tbar -> descriptors for the far-field sweep + exact near / endpoint contributions ---------------------------
 __global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a) {
-  __shared__ double sred[2 * kWarps];
   const long long b = blockIdx.x;
-  const double zM = a.xi1_0 + (double)(a.nodes - 1) * a.xi1_h;
-  double e0 = 0.0, eM = 0.0;
   for (int p = threadIdx.x; p < kXi2N; p += kThreads) {
     const double xi = a.xi2[p];
     const double tb = a.Tbar[b * kXi2N + p];
     float u0, nd;
     pole_split(xi, a.xi1_0, a.xi1_h, a.nodes, u0, nd);
-    a.desc[b * kXi2N + p] = make_float4(u0, nd, (float)tb, 0.f);
-    const double l0 = log(fmax(fabs(a.xi1_0 - xi), 1e-300)), lM = log(fmax(fabs(zM - xi), 1e-300));
-    e0 += tb * (-1.0 - l0);
-    eM += tb * (1.0 + lM);
+    a.desc[b * kXi2N + p] = make_float4(u0, nd, (float)(tb * a.xi1_h), 0.f);
+    pv_bwd_pole_exact(xi, tb, a.xi1_0, a.xi1_h, a.nodes, a.pnear + b * kXi1N);
   }
-  double vals[2] = {e0, eM};
-  block_accumulate<kWarps>(vals, 2, sred, a.pendbar + 2 * b);
 }
 
 // ---- finish ---------------------------------------------------------------------------------------------------
@@ -331,22 +326,10 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd_finish(const TableArgs a
   double* s_slb = s_lnfb + a.V;
   const long long b = blockIdx.x;
   const int V = a.V, M = a.nodes - 1;
-  const double* Dbar = a.Dbar + b * a.npad;
+  const double* pfar = a.Dbar + b * a.npad;
   const double ih = 1.0 / a.xi1_h;
-  // 1. ratdf_bar from Dbar (+ endpoint terms)
-  for (int i = threadIdx.x; i < kXi1N; i += kThreads) {
-    double pb = 0.0;
-    if (i <= M) {
-      double t = 0.0;
-      if (i >= 1) t += Dbar[i - 1];
-      t -= Dbar[i] * ((i < M ? 1.0 : 0.0) + (i > 0 ? 1.0 : 0.0));
-      if (i + 1 <= M) t += Dbar[i + 1];
-      pb = t * ih;
-      if (i == 0) pb += a.pendbar[2 * b];
-      if (i == M) pb += a.pendbar[2 * b + 1];
-    }
-    s_pb[i] = pb;
-  }
+  // 1. ratdf_bar = far-field sweep + exact near/endpoint terms
+  for (int i = threadIdx.x; i < kXi1N; i += kThreads) s_pb[i] = (i <= M ? pfar[i] : 0.0) + a.pnear[b * kXi1N + i];
   __syncthreads();
   // 2. ratmod_bar (adjoint of np.gradient) and Hbar_n = ratmod_bar_n * ratmod_n inside the f grid
   const double xlast = a.v0 + (double)(V - 1) * a.dv;
@@ -432,20 +415,23 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   bind_saved(L, static_cast<char*>(saved), a);
   a.params = params; a.fe = fe;
   a.D = (float*)(w + L.w_D); a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
-  a.pend = (double*)(w + L.w_pend);
+  a.pend = (double*)(w + L.w_pend); a.ratdf = (double*)(w + L.w_ratdf);
   a.modl = modl_out; a.ff = ff_out;
   {
     const size_t smem = (size_t)(2 * c->V + 2 * kXi1N) * 8;
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_prep<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN(k_table_prep<T>);
     k_table_prep<T><<<(unsigned)B, kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_prep");
   }
   {
     PvPolesArgs p;
     p.D = a.D; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
+    p.pnodes = a.ratdf; p.pnode_stride = kXi1N;
     p.z0 = c->xi1_0; p.h = c->xi1_h; p.nodes = c->pv_nodes; p.npad = c->pv_npad; p.P = kXi2N;
     p.outI = a.T; p.outdI = nullptr;
     const size_t smem = (size_t)c->pv_npad * 4;
+    TSFF_SMEM_OPTIN((k_pv_poles<1, TSFF_PV_FP32>));
+    TSFF_SMEM_OPTIN((k_pv_poles<2, TSFF_PV_FP32>));
     if (c->pv_precision == TSFF_PV_FP64) {
       p.ntiles = (kXi2N + kPvThreads - 1) / kPvThreads;
       k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
@@ -462,10 +448,10 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
     if (ff_out) {
-      TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TSFF_SMEM_OPTIN(k_table_fwd<true>);
       k_table_fwd<true><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
     } else {
-      TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TSFF_SMEM_OPTIN(k_table_fwd<false>);
       k_table_fwd<false><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
     }
     TSFF_LAUNCH_OK("k_table_fwd");
@@ -485,14 +471,14 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   a.params = params; a.fe = fe;
   a.modl_bar = modl_bar; a.ff_bar = ff_bar;
   a.desc = (float4*)(w + L.w_desc); a.Dbar = (double*)(w + L.w_Dbar); a.Tbar = (double*)(w + L.w_Tbar);
-  a.lnfbar = (double*)(w + L.w_lnfbar); a.slopebar = (double*)(w + L.w_slopebar); a.pendbar = (double*)(w + L.w_pendbar);
+  a.lnfbar = (double*)(w + L.w_lnfbar); a.slopebar = (double*)(w + L.w_slopebar); a.pnear = (double*)(w + L.w_pnear);
   a.lgbar = (double*)(w + L.w_lgbar);
   a.params_bar = params_bar; a.fe_bar = fe_bar;
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN(k_table_bwd);
     k_table_bwd<<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_bwd");
   }
@@ -500,7 +486,7 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   TSFF_LAUNCH_OK("k_table_tbar");
   {
     PvNodesArgs n;
-    n.desc = a.desc; n.P = kXi2N; n.npad = c->pv_npad; n.h = (float)c->xi1_h; n.Dbar = a.Dbar;
+    n.desc = a.desc; n.P = kXi2N; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.h = (float)c->xi1_h; n.pbar = a.Dbar;
     const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
     if ((long long)B * tiles4 >= 2LL * c->sm_count) {
       n.ntiles = (int)tiles4;
@@ -513,7 +499,7 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   }
   {
     const size_t smem = (size_t)(2 * kXi1N + 2 * c->V) * 8;
-    TSFF_CUDA_OK(cudaFuncSetAttribute(k_table_bwd_finish<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSFF_SMEM_OPTIN(k_table_bwd_finish<T>);
     k_table_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_bwd_finish");
   }
