@@ -81,6 +81,12 @@ void tsff_ctx_destroy(tsff_ctx* ctx);
 const char* tsff_last_error(void); /* thread-local, host pointer */
 int tsff_abi_version(void);
 
+/* Optional instrumentation: when both events (cudaEvent_t, created by the caller with timing enabled) are non-NULL,
+ * tsff_ff_fwd records them on the launch stream immediately before / after its dominant kernel (the pole sweep in
+ * direct mode, the per-(omega,angle) assembly in table mode) and tsff_ff_bwd around the adjoint node sweep
+ * (ev_bwd_*).  Used by bench.py for the live per-kernel roofline number; pass NULLs to switch off. */
+int tsff_ctx_set_profile_events(tsff_ctx* ctx, void* ev_fwd_start, void* ev_fwd_stop, void* ev_bwd_start, void* ev_bwd_stop);
+
 /* bytes the caller must provide: `saved` lives from *_fwd to the matching *_bwd, `ws` is scratch per call */
 size_t tsff_ff_saved_bytes(const tsff_ctx* ctx, int64_t B);
 size_t tsff_ff_workspace_bytes(const tsff_ctx* ctx, int64_t B);

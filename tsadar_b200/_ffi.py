@@ -16,7 +16,7 @@ P_TE, P_NE, P_LAM, P_VA, P_UD, P_NE_GRAD, P_TE_GRAD, P_AMP1, P_AMP2, P_AMP3, P_I
 ION_A, ION_Z, ION_TI, ION_FRACT, ION_STRIDE = range(5)
 
 EXPORTS = [
-    "tsff_ctx_create", "tsff_ctx_destroy", "tsff_last_error", "tsff_abi_version",
+    "tsff_ctx_create", "tsff_ctx_destroy", "tsff_last_error", "tsff_abi_version", "tsff_ctx_set_profile_events",
     "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd",
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
@@ -62,6 +62,8 @@ def lib():
     L.tsff_ctx_destroy.argtypes = [vp]
     L.tsff_ctx_destroy.restype = None
     L.tsff_last_error.restype = C.c_char_p
+    L.tsff_ctx_set_profile_events.argtypes = [vp, vp, vp, vp, vp]
+    L.tsff_ctx_set_profile_events.restype = C.c_int
     L.tsff_abi_version.restype = C.c_int
     L.tsff_ff_saved_bytes.argtypes = [vp, i64]
     L.tsff_ff_saved_bytes.restype = C.c_size_t

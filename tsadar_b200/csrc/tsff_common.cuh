@@ -135,4 +135,5 @@ struct tsff_ctx {
   int pv_nodes;  // M+1 nodes used by ratintn (N-1)
   int pv_npad;   // padded to 32
   double pv_z0, pv_h;
+  cudaEvent_t ev[4];  // optional profile events (fwd start/stop, bwd start/stop)
 };

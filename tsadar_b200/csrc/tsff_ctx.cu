@@ -111,6 +111,13 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   return TSFF_OK;
 }
 
+extern "C" int tsff_ctx_set_profile_events(tsff_ctx* ctx, void* e0, void* e1, void* e2, void* e3) {
+  if (!ctx) { set_error("null ctx"); return TSFF_E_INVALID; }
+  ctx->ev[0] = static_cast<cudaEvent_t>(e0); ctx->ev[1] = static_cast<cudaEvent_t>(e1);
+  ctx->ev[2] = static_cast<cudaEvent_t>(e2); ctx->ev[3] = static_cast<cudaEvent_t>(e3);
+  return TSFF_OK;
+}
+
 extern "C" void tsff_ctx_destroy(tsff_ctx* ctx) {
   if (!ctx) return;
   cudaFree(ctx->dev_blob);

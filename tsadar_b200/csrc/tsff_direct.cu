@@ -339,6 +339,7 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   // poles per thread: 2 while the grid still fills the device, else 1
   const long long tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
   const bool useR2 = (long long)B * c->G * tiles2 >= 2LL * c->sm_count;
+  if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
   if (c->pv_precision == TSFF_PV_FP64) {
     a.ntiles = (WA + kThreads - 1) / kThreads;
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
@@ -352,6 +353,7 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
     k_direct_fwd<1, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
   }
   TSFF_LAUNCH_OK("k_direct_fwd");
+  if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
   if (modl_out) {
     const long long total = (long long)B * c->W;
     k_reduce_modl<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(a.ff, c->wts, c->jmul, c->G, c->W, c->A,
@@ -385,6 +387,7 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   PvNodesArgs n;
   n.desc = a.desc; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.h = (float)c->dv; n.pbar = a.Dbar;
   const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
+  if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
   if ((long long)B * tiles4 >= 2LL * c->sm_count) {
     n.ntiles = (int)tiles4;
     k_pv_nodes<4><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
@@ -393,6 +396,7 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
     k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
   }
   TSFF_LAUNCH_OK("k_pv_nodes");
+  if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   const size_t smem = (size_t)c->V * 8;
   TSFF_SMEM_OPTIN(k_direct_bwd_finish<T>);
   k_direct_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);

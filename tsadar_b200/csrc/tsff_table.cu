@@ -447,6 +447,7 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
+    if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (ff_out) {
       TSFF_SMEM_OPTIN(k_table_fwd<true>);
       k_table_fwd<true><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
@@ -455,6 +456,7 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
       k_table_fwd<false><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
     }
     TSFF_LAUNCH_OK("k_table_fwd");
+    if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
   }
   return TSFF_OK;
 }
@@ -478,9 +480,11 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
+    if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
     TSFF_SMEM_OPTIN(k_table_bwd);
     k_table_bwd<<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_bwd");
+    if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }
   k_table_tbar<<<(unsigned)B, kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_table_tbar");

@@ -138,6 +138,17 @@ class FormFactorEngine:
             ff_bar.data_ptr() if ff_bar is not None else None, params_bar.data_ptr(), fe_bar.data_ptr(), ws.data_ptr(), st))
         return params_bar, fe_bar
 
+    def set_profile_events(self, fwd=None, bwd=None):
+        """fwd/bwd: (start, stop) torch.cuda.Event pairs (enable_timing=True) recorded around the dominant kernels."""
+        self._prof = (fwd, bwd)  # keep the events alive
+        h = [None, None, None, None]
+        for k, pair in enumerate((fwd, bwd)):
+            if pair is not None:
+                for e in pair:
+                    e.record()  # torch creates the cudaEvent lazily on first record
+                h[2 * k], h[2 * k + 1] = pair[0].cuda_event, pair[1].cuda_event
+        _ffi.check(_ffi.lib().tsff_ctx_set_profile_events(self._ctx, h[0], h[1], h[2], h[3]))
+
     # number of kernel launches one forward / backward call makes (for bench.py's gpu_launches claim)
     def launches_fwd(self, want_modl=True):
         if self.mode == "table":
@@ -207,6 +218,25 @@ def pv_integral_vjp(f, z0, h, pole, out_bar):
     _ffi.check(_ffi.lib().tsff_pv_bwd(B, N, P, f.data_ptr(), float(z0), float(h), pole.data_ptr(), out_bar.data_ptr(),
                                       f_bar.data_ptr(), pole_bar.data_ptr(), ws.data_ptr(), st))
     return f_bar, pole_bar
+
+
+def loss_fwd_bwd(theory, data, weight, uncert=1.0, scale=1.0, method="l2", loss_out=None, want_grad=True):
+    """Fused masked loss + its gradient wrt theory (tsff_loss_fwd_bwd; loss_function.py:190-267, 386-418).
+    theory, data [B,n]; weight [n] (static window weights); returns (loss device scalar, theory_bar)."""
+    _require_cuda(theory, torch.float64, "theory")
+    _require_cuda(data, torch.float64, "data")
+    _require_cuda(weight, torch.float64, "weight")
+    B, n = theory.shape
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float64, device=theory.device)
+    else:
+        loss_out.zero_()
+    tbar = torch.empty_like(theory) if want_grad else None
+    st = torch.cuda.current_stream(theory.device).cuda_stream
+    m = {"l2": 0, "l1": 1, "log-cosh": 2, "poisson": 3}[method]
+    _ffi.check(_ffi.lib().tsff_loss_fwd_bwd(B, n, theory.data_ptr(), data.data_ptr(), weight.data_ptr(), float(uncert),
+                                            float(scale), m, loss_out.data_ptr(), tbar.data_ptr() if want_grad else None, st))
+    return loss_out, tbar
 
 
 def microbench(kind, iters=4096):
