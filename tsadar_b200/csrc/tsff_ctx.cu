@@ -128,6 +128,7 @@ extern "C" void tsff_ctx_destroy(tsff_ctx* ctx) {
 __global__ void __launch_bounds__(256) k_micro_ffma(long long iters, float* sink) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float m = 0.999f, c = 1e-3f;
+#pragma unroll 16
   for (long long i = 0; i < iters; i++) {
     a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
     a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
@@ -137,10 +138,73 @@ __global__ void __launch_bounds__(256) k_micro_ffma(long long iters, float* sink
 }
 __global__ void __launch_bounds__(256) k_micro_lg2(long long iters, float* sink) {
   float a0 = 1.5f + threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+#pragma unroll 16
   for (long long i = 0; i < iters; i++) {
     a0 = lg2_approx(a0) + 4.f; a1 = lg2_approx(a1) + 4.f; a2 = lg2_approx(a2) + 4.f; a3 = lg2_approx(a3) + 4.f;
   }
   float s = a0 + a1 + a2 + a3;
+  if (s == 12345.678f) sink[0] = s;
+}
+
+// mixed loop: one MUFU.RCP feeding NF independent FFMAs per step (machine model for the pole/node sweeps)
+template <int NF>
+__global__ void __launch_bounds__(256) k_micro_mix(long long iters, float* sink) {
+  float x0 = 1.5f + threadIdx.x * 1e-3f, x1 = x0 + 0.25f;
+  float a[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) a[k] = 0.1f * k;
+  const float c = 1.0009765625f;
+#pragma unroll 4
+  for (long long i = 0; i < iters; i++) {
+    const float r0 = rcp_approx(x0), r1 = rcp_approx(x1);
+#pragma unroll
+    for (int k = 0; k < NF; k++) a[k] = fmaf(a[k], c, (k & 1) ? r1 : r0);
+#pragma unroll
+    for (int k = 0; k < NF; k++) a[(k + 1) % 12] = fmaf(a[(k + 1) % 12], c, (k & 1) ? r0 : r1);
+    x0 += 0.001f; x1 += 0.001f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; k++) s += a[k];
+  if (s == 12345.678f) sink[0] = s;
+}
+
+// packed variant: one MUFU.RCP per NF/2 FFMA2 (= NF FMAs)
+template <int NF2>
+__global__ void __launch_bounds__(256) k_micro_mix2(long long iters, float* sink) {
+  float x0 = 1.5f + threadIdx.x * 1e-3f, x1 = x0 + 0.25f;
+  float2 a[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) a[k] = make_float2(0.1f * k, 0.2f * k);
+  const float2 c = make_float2(1.0009765625f, 1.0009765625f);
+#pragma unroll 4
+  for (long long i = 0; i < iters; i++) {
+    const float r0 = rcp_approx(x0), r1 = rcp_approx(x1);
+    const float2 rr = make_float2(r0, r1), rs = make_float2(r1, r0);
+#pragma unroll
+    for (int k = 0; k < NF2; k++) a[k] = ffma2(a[k], c, (k & 1) ? rs : rr);
+#pragma unroll
+    for (int k = 0; k < NF2; k++) a[(k + 1) % 6] = ffma2(a[(k + 1) % 6], c, (k & 1) ? rr : rs);
+    x0 += 0.001f; x1 += 0.001f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; k++) s += a[k].x + a[k].y;
+  if (s == 12345.678f) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_micro_ffma2(long long iters, float* sink) {
+  float2 a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = make_float2(threadIdx.x * 1e-3f + k, 0.5f * k);
+  const float2 m = make_float2(0.999f, 0.998f), c = make_float2(1e-3f, 2e-3f);
+#pragma unroll 16
+  for (long long i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = ffma2(a[k], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k].x + a[k].y;
   if (s == 12345.678f) sink[0] = s;
 }
 
@@ -156,6 +220,33 @@ extern "C" int tsff_microbench(int kind, int64_t iters, double* ops, float* sink
   } else if (kind == 1) {
     k_micro_lg2<<<blocks, threads, 0, st>>>(iters, sink);
     if (ops) *ops = (double)blocks * threads * (double)iters * 4.0;
+  } else if (kind == 3) {
+    k_micro_ffma2<<<blocks, threads, 0, st>>>(iters, sink);
+    if (ops) *ops = (double)blocks * threads * (double)iters * 16.0;  // FMAs
+  } else if (kind >= 200 && kind <= 206) {
+    switch (kind - 200) {  // NF2 FFMA2 per MUFU
+      case 1: k_micro_mix2<1><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 2: k_micro_mix2<2><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 3: k_micro_mix2<3><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 4: k_micro_mix2<4><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 5: k_micro_mix2<5><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 6: k_micro_mix2<6><<<blocks, threads, 0, st>>>(iters, sink); break;
+      default: set_error("unsupported mix2"); return TSFF_E_INVALID;
+    }
+    if (ops) *ops = (double)blocks * threads * (double)iters * 2.0;
+  } else if (kind >= 100 && kind <= 112) {
+    // kind = 100 + NF: per step 2 MUFU.RCP + 2*NF FFMA + 2 FADD; *ops counts MUFU ops
+    switch (kind - 100) {
+      case 0: k_micro_mix<0><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 2: k_micro_mix<2><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 4: k_micro_mix<4><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 6: k_micro_mix<6><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 8: k_micro_mix<8><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 10: k_micro_mix<10><<<blocks, threads, 0, st>>>(iters, sink); break;
+      case 12: k_micro_mix<12><<<blocks, threads, 0, st>>>(iters, sink); break;
+      default: set_error("unsupported mix"); return TSFF_E_INVALID;
+    }
+    if (ops) *ops = (double)blocks * threads * (double)iters * 2.0;
   } else {
     set_error("unknown microbench kind %d", kind);
     return TSFF_E_INVALID;

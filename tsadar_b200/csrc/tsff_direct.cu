@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
 
 // ---- forward ------------------------------------------------------------------------------------------------
 // grid.x = B * G * ntiles; a tile covers kThreads*R consecutive (j,a) pairs of one (lineout, gradient point).
-template <int R, typename T, int PREC>
-__global__ void __launch_bounds__(kThreads) k_direct_fwd(const DirectArgs a) {
+template <int R, typename T, int PREC, int MINB = 3>
+__global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const DirectArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ LG sL;
@@ -345,12 +345,12 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   } else if (useR2) {
     a.ntiles = (int)tiles2;
-    TSFF_SMEM_OPTIN((k_direct_fwd<2, T, TSFF_PV_FP32>));
-    k_direct_fwd<2, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
+    TSFF_SMEM_OPTIN((k_direct_fwd<2, T, TSFF_PV_FP32, 3>));
+    k_direct_fwd<2, T, TSFF_PV_FP32, 3><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
   } else {
     a.ntiles = (WA + kThreads - 1) / kThreads;
-    TSFF_SMEM_OPTIN((k_direct_fwd<1, T, TSFF_PV_FP32>));
-    k_direct_fwd<1, T, TSFF_PV_FP32><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
+    TSFF_SMEM_OPTIN((k_direct_fwd<1, T, TSFF_PV_FP32, 4>));
+    k_direct_fwd<1, T, TSFF_PV_FP32, 4><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
   }
   TSFF_LAUNCH_OK("k_direct_fwd");
   if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));

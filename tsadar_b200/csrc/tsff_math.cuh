@@ -15,7 +15,8 @@
 #define TSFF_HD __host__ __device__ __forceinline__
 #else
 #define TSFF_HD inline
-struct float4 { float x, y, z, w; };  // host-only stand-in (tests/hostsim)
+struct float4 { float x, y, z, w; };  // host-only stand-ins (tests/hostsim)
+struct float2 { float x, y; };
 #endif
 
 #define TSFF_MAX_IONS 4

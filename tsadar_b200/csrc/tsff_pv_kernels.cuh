@@ -83,16 +83,22 @@ struct PvNodesArgs {
 
 constexpr int kNodeChunk = 512;  // poles staged per shared-memory chunk (8 KB)
 
-// pbar_i (far part) = sum_p Ibar_p W(g_{p,i}) over poles with |i - n_p| > kNearHalf
+// pbar_i (far part) = sum_p Ibar_p W(g_{p,i}) over poles with |i - n_p| > kNearHalf.
+// Poles are staged in shared memory in chunks; for every sub-chunk of 64 poles the range of nearest-node indices is
+// recorded, so that a warp whose nodes are farther than kMidHalf from all of them runs the short, unmasked series
+// (5.25 FMA-pipe ops + 1 MUFU.RCP per pair: MUFU-bound), and only the sub-chunks next to the warp's nodes pay for the
+// long series and the near-node mask.
 template <int R>
 __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
   __shared__ float4 sdesc[kNodeChunk];
+  __shared__ float srange[kNodeChunk / 64][2];  // (max u0, min u0) = (-n_min, -n_max) per 64-pole sub-chunk
   const long long b = blockIdx.x / a.ntiles;
   const int tile = blockIdx.x % a.ntiles;
   const int i0 = (tile * kPvThreads + threadIdx.x) * R;
   const float fi0 = (float)i0;
   const float c2 = a.h * a.h * (1.f / 6.f), c4 = a.h * a.h * a.h * a.h * (1.f / 15.f);
   const float4* desc = a.desc + b * a.P;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double acc[R];
 #pragma unroll
   for (int r = 0; r < R; r++) acc[r] = 0.0;
@@ -102,24 +108,55 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
     for (int k = threadIdx.x; k < kNodeChunk; k += kPvThreads)
       sdesc[k] = (k < nc) ? desc[c0 + k] : make_float4(1e6f, 0.f, 0.f, 0.f);
     __syncthreads();
+    // one warp per sub-chunk: range of u0 over its real poles
+    for (int sc = wid; sc < kNodeChunk / 64; sc += kPvThreads / 32) {
+      float hi = -3.0e38f, lo = 3.0e38f;
+      for (int k = lane; k < 64; k += 32) {
+        const int kk = sc * 64 + k;
+        if (kk < nc) { const float v = sdesc[kk].x; hi = fmaxf(hi, v); lo = fminf(lo, v); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      }
+      if (lane == 0) { srange[sc][0] = hi; srange[sc][1] = lo; }
+    }
+    __syncthreads();
     for (int s0 = 0; s0 < kNodeChunk; s0 += 64) {
       if (s0 >= nc) break;
+      // offsets i - n_p of this thread's nodes against the sub-chunk's poles lie in [fi0 + lo, fi0 + R-1 + hi]
+      const float omin = fi0 + srange[s0 / 64][1], omax = fi0 + (float)(R - 1) + srange[s0 / 64][0];
+      const bool mid = (omin <= (float)kMidHalf) && (omax >= -(float)kMidHalf);
       float part[R];
 #pragma unroll
       for (int r = 0; r < R; r++) part[r] = 0.f;
+      if (!__any_sync(0xffffffffu, mid)) {
 #pragma unroll 8
-      for (int k = 0; k < 64; k++) {
-        const float4 d = sdesc[s0 + k];
-        const float u = fi0 + d.x;              // i0 - n_p, exact
-        const float gbase = fmaf(u, a.h, d.y);  // g at node i0
+        for (int k = 0; k < 64; k++) {
+          const float4 d = sdesc[s0 + k];
+          const float gbase = fmaf(fi0 + d.x, a.h, d.y);  // g at node i0
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float g = fmaf((float)r, a.h, gbase);
-          const float rg = rcp_approx(g);
-          const float s2 = rg * rg;
-          const float w = rg * fmaf(fmaf(s2, c4, c2), s2, 1.f);   // W / h
-          const float wm = (fabsf(u + (float)r) > (float)kNearHalf + 0.5f) ? w : 0.f;
-          part[r] = fmaf(d.z, wm, part[r]);
+          for (int r = 0; r < R; r++) {
+            const float g = fmaf((float)r, a.h, gbase);
+            const float rg = rcp_approx(g);
+            part[r] = fmaf(d.z * rg, fmaf(rg * rg, c2, 1.f), part[r]);   // Ibar h * W / h
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < 64; k++) {
+          const float4 d = sdesc[s0 + k];
+          const float u = fi0 + d.x;              // i0 - n_p, exact
+          const float gbase = fmaf(u, a.h, d.y);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float g = fmaf((float)r, a.h, gbase);
+            const bool far = fabsf(u + (float)r) > (float)kNearHalf + 0.5f;
+            const float rg = far ? rcp_approx(g) : 0.f;
+            const float s2 = rg * rg;
+            part[r] = fmaf(d.z, rg * fmaf(fmaf(s2, c4, c2), s2, 1.f), part[r]);
+          }
         }
       }
 #pragma unroll
