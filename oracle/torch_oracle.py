@@ -191,3 +191,34 @@ def modl_from_ff(ff, weights, jmul=None):
     """mean over G, weighted angle sum, static multiplier (generate_spectra.py:164-165,193,197,210-216)."""
     m = torch.sum(torch.mean(ff, 0) * T(weights), 1)
     return m if jmul is None else m * T(jmul)
+
+
+def add_electron_irf(lamAxisE, modlE, amps, lam, amp1, amp2, stddevE):
+    """np_oracle.add_electron_irf (irf.py:90-132), norm == 0."""
+    lamAxisE = T(lamAxisE)
+    origin = (lamAxisE.max() + lamAxisE.min()) / 2.0
+    inst = (1.0 / (stddevE * math.sqrt(2.0 * math.pi))) * torch.exp(-((lamAxisE - origin) ** 2.0) / (2.0 * stddevE**2.0))
+    n = modlE.numel()
+    full = torch.nn.functional.conv1d(modlE.reshape(1, 1, -1), inst.flip(0).reshape(1, 1, -1), padding=n - 1).reshape(-1)
+    y = full[(n - 1) // 2 : (n - 1) // 2 + n]          # np.convolve(..., "same")
+    y = (modlE.max() / y.max()) * y
+    y = y.reshape(1024, -1).mean(1)
+    lamb = lamAxisE.reshape(1024, -1).mean(1)
+    y = amps * y / y.max()
+    return lamb, torch.where(lamb < lam, amp1 * y, amp2 * y)
+
+
+def loss_electron(ThryE, lamb, e_data, cfg, e_norm=1.0):
+    """np_oracle.calc_ei_error electron part with nanmean (loss_function.py:234-264), l2."""
+    fr, ex = cfg["data"]["fit_rng"], cfg["other"]["extraoptions"]
+    err = (T(e_data) - ThryE) ** 2 / e_norm**2
+    tot = 0.0
+    if ex["fit_EPWb"]:
+        m = (lamb > fr["blue_min"]) & (lamb < fr["blue_max"])
+        tot = tot + err[..., m].mean()
+    if ex["fit_EPWr"]:
+        m = (lamb > fr["red_min"]) & (lamb < fr["red_max"])
+        tot = tot + err[..., m].mean()
+        if ex["fit_EPWb"]:
+            tot = tot * 0.5
+    return tot

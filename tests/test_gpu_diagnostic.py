@@ -1,0 +1,122 @@
+"""GPU parity of the full drop-in path against the reference's own golden vector and the oracle:
+ThomsonParams -> ThomsonScatteringDiagnostic (FitModel + IRF) -> LossFunction, mirroring
+tests/test_forward/test_1d.py:17-84 and the gradient path of tests/test_inverse/test_1d_random.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O, torch_oracle as TO, params_oracle as P
+from tests.common import SA_P9, DLM_M_OFFSET, load_cfg, dummy_batch_1d, GOLDEN, params_to_row
+
+pytestmark = pytest.mark.gpu
+
+
+def test_1d_forward_pass_golden():
+    """tests/test_forward/test_1d.py: ThryE vs ThryE-1d.npy (reference tolerance rtol=1e-4 pointwise)."""
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_1d")
+    gold = np.load(os.path.join(GOLDEN, "ThryE-1d.npy"))
+    ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=SA_P9)
+    ts_params = ThomsonParams(cfg["parameters"], num_params=1, batch=True, activate=True, dlm_m_offset=DLM_M_OFFSET)
+    ThryE, ThryI, lamAxisE, lamAxisI = ts_diag(ts_params, dummy_batch_1d())
+    got = ThryE.detach().cpu().numpy()
+    assert got.shape == gold.shape
+    np.testing.assert_allclose(got, gold, rtol=1e-4)          # the reference's own assertion
+    np.testing.assert_allclose(got, gold, rtol=1e-5)          # north-star tolerance, pointwise over 21 decades
+    # oracle agreement on the wavelength axis
+    p = P.thomson_params(cfg["parameters"], activate=True, dlm_m_offset=DLM_M_OFFSET)
+    _, _, lamE, _ = O.diagnostic_1d([p], cfg, SA_P9, dummy_batch_1d())
+    np.testing.assert_allclose(np.asarray(lamAxisE), lamE[0], rtol=1e-12)
+
+
+def test_irf_kernel_matches_oracle_batch():
+    """tsff_irf_fwd on random smooth spectra (electron and ion kinds), several lineouts, vs np_oracle.add_*_irf."""
+    from tsadar_b200 import irf
+    rng = np.random.default_rng(0)
+    W, B = 5120, 3
+    lam = np.linspace(400.0, 700.0, W)
+    x = np.stack([np.exp(-0.5 * ((lam - c) / s) ** 2) + 0.3 * np.exp(-0.5 * ((lam - 620) / 4.0) ** 2) + 1e-6
+                  for c, s in [(450, 3.0), (470, 8.0), (510, 1.0)]])
+    block = np.zeros((B, 14))
+    block[:, 2] = [524.0, 526.5, 527.0]
+    block[:, 7] = [1.1, 0.8, 2.0]
+    block[:, 8] = [0.9, 1.3, 0.5]
+    block[:, 9] = [1.0, 0.7, 1.5]
+    amps = np.array([1.0, 2.5, 0.3])
+    noise = rng.normal(size=(B, 1024)) * 1e-3
+    cfg = {"other": {"PhysParams": {"norm": 0, "widIRF": {"spect_stddev_ele": 1.3, "spect_stddev_ion": 0.5}}}}
+    xt, bt, at, nt = (torch.tensor(a, device="cuda") for a in (x, block, amps, noise))
+    lamb, thE = irf.add_electron_IRF(cfg, (400.0, 700.0), W, xt, at, bt, nt)
+    _, thI = irf.add_ion_IRF(cfg, (400.0, 700.0), W, xt, at, bt, None)
+    for b in range(B):
+        lo, ref = O.add_electron_irf(lam, x[b], amps[b], block[b, 2], block[b, 7], block[b, 8], 1.3)
+        np.testing.assert_allclose(thE.cpu().numpy()[b], ref + noise[b], rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(lamb, lo, rtol=1e-12)
+        _, refI = O.add_ion_irf(lam, x[b], amps[b], block[b, 9], 0.5)
+        np.testing.assert_allclose(thI.cpu().numpy()[b], refI, rtol=1e-9, atol=1e-14)
+
+
+def test_loss_and_gradients_full_chain():
+    """LossFunction.vg_loss on a 2-lineout batch: loss and d loss / d (normalised active params) vs the torch-f64
+    oracle of the same chain (ThomsonParams transforms -> form factor -> IRF -> masked L2 nanmean)."""
+    from tsadar_b200.loss_function import LossFunction
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_1d")
+    cfg["other"]["points_per_pixel"] = 1
+    cfg["other"]["npts"] = 1024
+    cfg["parameters"]["electron"]["fe"]["nvx"] = 64
+    B = 2
+    rng = np.random.default_rng(1)
+    lamb = np.linspace(400, 700, 1024)
+    e_data = 0.6 * np.exp(-0.5 * ((lamb - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamb - 590) / 15.0) ** 2) + 0.01
+    batch = dict(e_data=np.stack([e_data, 1.2 * e_data]), i_data=np.ones((B, 1024)), e_amps=np.array([1.0, 1.2]),
+                 i_amps=np.ones(B), noise_e=np.zeros((B, 1024)), noise_i=np.zeros((B, 1024)))
+    loss_fn = LossFunction(cfg, SA_P9, batch)
+    tp = ThomsonParams(cfg["parameters"], num_params=B, batch=True, activate=True)
+    with torch.no_grad():  # make the two lineouts different
+        tp.leaves[("electron", "Te")].value[1] += 0.3
+        tp.leaves[("electron", "ne")].value[1] -= 0.2
+    (loss, aux), grads = loss_fn.vg_loss(tp, batch)
+    names = [k for k, s in tp.leaves.items() if s.active]
+
+    # ---- oracle: same chain in torch float64 on the CPU
+    grids = O.Grids(cfg["other"]["lamrangE"], 1024)
+    w0 = float(SA_P9["weights"][0])
+    fb, fr_ = 528 - 12, 528 + 12
+    jmul = np.where((fb < grids.lam_axis) & (fr_ > grids.lam_axis), 1e-4, 1.0)
+    leaves = {k: tp.leaves[k].value.detach().cpu().clone().requires_grad_(tp.leaves[k].active) for k in tp.leaves}
+    m_ax, tab = tp.m_ax.cpu(), tp.f_vx_m.cpu()
+    total = 0.0
+    e_norm = float(np.amax(batch["e_data"]))
+    for b in range(B):
+        def phys(key):
+            s = tp.leaves[key]
+            v = leaves[key][b]
+            return (torch.sigmoid(v) if s.active else v) * s.scale + s.shift
+        m = phys(("electron", "m"))
+        i = int(torch.clamp(torch.searchsorted(m_ax, m.detach().reshape(1), right=True), 1, 30))
+        w = (m - m_ax[i - 1]) / (m_ax[i] - m_ax[i - 1])
+        f = tab[:, i - 1] * (1 - w) + tab[:, i] * w
+        fe = f / f.sum() / tp.dv
+        p = dict(Te=phys(("electron", "Te")), ne=phys(("electron", "ne")), lam=phys(("general", "lam")), Va=phys(("general", "Va")),
+                 ud=phys(("general", "ud")), ne_gradient=phys(("general", "ne_gradient")), Te_gradient=phys(("general", "Te_gradient")),
+                 ions=[dict(A=torch.tensor(40.0, dtype=torch.float64), Z=phys(("ion-1", "Z")), Ti=phys(("ion-1", "Ti")),
+                            fract=phys(("ion-1", "fract")) / phys(("ion-1", "fract")))])
+        ff = TO.form_factor_1v(p, fe, tp.vx, grids, SA_P9["sa"], 1, 0.0)
+        modl = TO.modl_from_ff(ff, np.full(10, w0), jmul)
+        lb, thry = TO.add_electron_irf(grids.lam_axis, modl, batch["e_amps"][b], phys(("general", "lam")), phys(("general", "amp1")),
+                                       phys(("general", "amp2")), 1.3)
+        fr, ex = cfg["data"]["fit_rng"], cfg["other"]["extraoptions"]
+        err = (torch.tensor(batch["e_data"][b]) - thry) ** 2 / e_norm**2
+        mb = (lb > fr["blue_min"]) & (lb < fr["blue_max"])
+        mr = (lb > fr["red_min"]) & (lb < fr["red_max"])
+        total = total + 0.5 * (err[mb].sum() / (B * int(mb.sum())) + err[mr].sum() / (B * int(mr.sum())))
+    total.backward()
+    assert abs(loss.item() - total.item()) <= 1e-6 * abs(total.item()), (loss.item(), total.item())
+    for k, g in zip(names, grads):
+        ref = leaves[k].grad.numpy()
+        got = g.cpu().numpy()
+        assert np.all(np.abs(got - ref) <= 1e-4 * np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max() + 1e-12)), (k, got, ref)

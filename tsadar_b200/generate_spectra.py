@@ -1,0 +1,59 @@
+"""FitModel -- mirror of tsadar.core.physics.generate_spectra.FitModel (generate_spectra.py:8-220) for the
+temporal / imaging / 1d spectypes (1V distributions).  The mean over gradient points, the weighted angle sum and the
+IAW filter are fused into the form-factor kernel (`modl` output of tsff_ff_fwd)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .form_factor import FormFactor
+
+
+class FitModel:
+    def __init__(self, config, scattering_angles, mode="table", pv_precision="fp32"):
+        self.config = config
+        self.scattering_angles = scattering_angles
+        gen = config["parameters"]["general"]
+        assert gen["Te_gradient"]["num_grad_points"] == gen["ne_gradient"]["num_grad_points"], \
+            "Number of gradient points for Te and ne must be the same"
+        G = gen["Te_gradient"]["num_grad_points"]
+        if config["parameters"]["electron"]["fe"]["dim"] != 1:
+            raise NotImplementedError("2V distributions (calc_in_2D) are not built yet")
+        oth = config["other"]
+        self.electron_form_factor = FormFactor(oth["lamrangE"], npts=oth["npts"], lam_shift=config["data"]["ele_lam_shift"],
+                                               scattering_angles=scattering_angles, num_grad_points=G, va_ang=None,
+                                               ud_ang=None, mode=mode, pv_precision=pv_precision)
+        self.ion_form_factor = FormFactor(oth["lamrangI"], npts=oth["npts"], lam_shift=0, scattering_angles=scattering_angles,
+                                          num_grad_points=G, va_ang=None, ud_ang=None, mode=mode, pv_precision=pv_precision)
+        # `weights[0]`: a scalar when `sa` comes straight from get_scattering_angles (tests, forward mode), the per-angle
+        # vector after lineouts.py:103.  Both are "one weight per angle" for the kernel.
+        w0 = np.asarray(scattering_angles["weights"])[0]
+        nA = np.asarray(scattering_angles["sa"]).size
+        self._w = np.full(nA, float(w0)) if np.ndim(w0) == 0 else np.asarray(w0, dtype=np.float64)
+        lamE = np.linspace(oth["lamrangE"][0], oth["lamrangE"][1], oth["npts"])
+        self._jmulE = None
+        if oth.get("iawoff", 0):
+            raise NotImplementedError("iawoff: untested branch in the reference (SURVEY.md A9)")
+        f = oth.get("iawfilter", [0])
+        if f[0]:
+            fb, fr = f[3] - f[2] / 2, f[3] + f[2] / 2
+            if oth["lamrangE"][0] < fr and oth["lamrangE"][1] > fb:
+                self._jmulE = np.where((fb < lamE) & (fr > lamE), 10.0 ** (-f[1]), 1.0)   # generate_spectra.py:210-216
+
+    def ion_spectrum(self, all_params):
+        if self.config["other"]["extraoptions"]["load_ion_spec"]:
+            modlI, block = self.ion_form_factor.modl(all_params, self._w)
+            lamI = np.linspace(*self.config["other"]["lamrangI"], self.config["other"]["npts"])
+            return lamI, modlI, block
+        return np.zeros(1), 0, None
+
+    def electron_spectrum(self, all_params):
+        if self.config["other"]["extraoptions"]["load_ele_spec"]:
+            modlE, block = self.electron_form_factor.modl(all_params, self._w, jmul=self._jmulE)
+            lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
+            return lamE, modlE, block
+        return [], 0, None
+
+    def __call__(self, all_params):
+        lamAxisI, modlI, _ = self.ion_spectrum(all_params)
+        lamAxisE, modlE, _ = self.electron_spectrum(all_params)
+        return modlE, modlI, lamAxisE, lamAxisI

@@ -1,0 +1,87 @@
+"""LossFunction -- mirror of tsadar.inverse.loss_function.LossFunction (loss_function.py:17-373) for the
+non-multiplexed temporal/1d path: masked loss over the fit windows (nanmean) and its gradient with respect to the
+active normalised parameters.  The loss and its seed cotangent come from the fused kernel tsff_loss_fwd_bwd; the fit
+windows and nanmean denominators are static, so they are folded into per-pixel weights once."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import loss_fwd_bwd
+from .thomson_diagnostic import ThomsonScatteringDiagnostic
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theory, data, weight, uncert, scale, method):
+        loss, tbar = loss_fwd_bwd(theory.contiguous(), data, weight, uncert, scale, method)
+        ctx.save_for_backward(tbar)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (tbar,) = ctx.saved_tensors
+        return tbar * g, None, None, None, None, None
+
+
+class LossFunction:
+    def __init__(self, cfg, scattering_angles, dummy_batch, mode="table", pv_precision="fp32"):
+        self.cfg = cfg
+        if cfg["optimizer"]["y_norm"]:
+            self.i_norm = float(np.amax(np.asarray(dummy_batch["i_data"])))
+            self.e_norm = float(np.amax(np.asarray(dummy_batch["e_data"])))
+        else:
+            self.i_norm = self.e_norm = 1.0
+        if isinstance(cfg["data"]["shotnum"], list):
+            raise NotImplementedError("multiplexed shots: 'behavior has not been checked' in the reference (loss_function.py:288)")
+        self.ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles, mode=mode, pv_precision=pv_precision)
+        self._w = {}
+
+    def _weights(self, lamE, lamI, dev):
+        """Static per-pixel weights reproducing calc_ei_error's window masks and nanmean (loss_function.py:222-264)."""
+        if not self._w:
+            fr, ex = self.cfg["data"]["fit_rng"], self.cfg["other"]["extraoptions"]
+            wE = np.zeros(len(lamE)) if len(lamE) else None
+            if wE is not None:
+                nb = ex["fit_EPWb"] and ex["fit_EPWr"]
+                if ex["fit_EPWb"]:
+                    m = (lamE > fr["blue_min"]) & (lamE < fr["blue_max"])
+                    wE += m / max(m.sum(), 1) * (0.5 if nb else 1.0)
+                if ex["fit_EPWr"]:
+                    m = (lamE > fr["red_min"]) & (lamE < fr["red_max"])
+                    wE += m / max(m.sum(), 1) * (0.5 if nb else 1.0)
+            wI = None
+            if len(lamI) and ex["fit_IAW"]:
+                m = ((lamI > fr["iaw_min"]) & (lamI < fr["iaw_cf_min"])) | ((lamI > fr["iaw_cf_max"]) & (lamI < fr["iaw_max"]))
+                wI = m / max(m.sum(), 1)
+            self._w = {"E": None if wE is None else torch.tensor(wE, dtype=torch.float64, device=dev),
+                       "I": None if wI is None else torch.tensor(wI, dtype=torch.float64, device=dev)}
+        return self._w["E"], self._w["I"]
+
+    def calc_loss(self, ts_params, batch, world_batch=None):
+        """-> total_loss (torch scalar on the GPU), ThryE, ThryI     (loss_function.py:269-342, 364-373)"""
+        ThryE, ThryI, lamE, lamI = self.ts_diag(ts_params, batch)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        wE, wI = self._weights(np.asarray(lamE), np.asarray(lamI), dev)
+        method = self.cfg["optimizer"]["loss_method"]
+        ex = self.cfg["other"]["extraoptions"]
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        if isinstance(ThryE, torch.Tensor) and (ex["fit_EPWb"] or ex["fit_EPWr"]):
+            B = ThryE.shape[0]
+            d = torch.as_tensor(batch["e_data"], dtype=torch.float64).to(dev).expand(B, ThryE.shape[1]).contiguous()
+            total = total + _LossFn.apply(ThryE, d, wE, self.e_norm**2, 1.0 / (world_batch or B), method)
+        if isinstance(ThryI, torch.Tensor) and ex["fit_IAW"] and wI is not None:
+            B = ThryI.shape[0]
+            d = torch.as_tensor(batch["i_data"], dtype=torch.float64).to(dev).expand(B, ThryI.shape[1]).contiguous()
+            total = total + self.cfg["data"]["ion_loss_scale"] * _LossFn.apply(ThryI, d, wI, self.i_norm**2, 1.0 / (world_batch or B), method)
+        return total, ThryE, ThryI
+
+    def vg_loss(self, ts_params, batch):
+        """((loss, [ThryE, params]), grads) with grads = d loss / d (active normalised leaves), like
+        filter_value_and_grad(__loss__, has_aux=True) (loss_function.py:107-108, 128-168)."""
+        leaves = ts_params.parameters()
+        for t in leaves:
+            t.grad = None
+        loss, ThryE, _ = self.calc_loss(ts_params, batch)
+        loss.backward()
+        return (loss.detach(), [ThryE.detach() if isinstance(ThryE, torch.Tensor) else ThryE, ts_params]), [t.grad for t in leaves]

@@ -1,0 +1,130 @@
+"""ThomsonParams -- torch mirror of tsadar.core.modules.ts_params.ThomsonParams (ts_params.py:498-645) for 1V
+distributions: normalised trainable leaves, sigmoid/affine de-normalisation, ion-fraction renormalisation, and the
+f(v) producers DLM1V / 'mx' / Arbitrary1V (distribution_functions/base.py).
+
+The reference keeps this stage in JAX (out of scope for the kernels, "next" row N3); it is
+mirrored here only so that the drop-in tests read like the reference's.  It is cheap elementwise host-side glue in torch
+(autograd carries the kernels' cotangents back to the normalised leaves)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy.special import gamma, gammaincc
+
+DT = torch.float64
+
+
+def _inv_act(x):
+    return np.log(1e-2 + x / (1 - x + 1e-2))  # ts_params.py:344 (not the logit: values shift on the first call)
+
+
+def vgrid(nvx):
+    vmax = 6.0
+    dv = 2 * vmax / nvx
+    return np.linspace(-vmax + dv / 2, vmax - dv / 2, nvx)
+
+
+def dlm_table(vx):
+    """Stand-in for the missing blob DLM_x_-3_-10_10_m_-1_2_5.mat (base.py:266-272): projected super-Gaussians on
+    vx_ax = linspace(-10,10,20001) x m_ax = linspace(2,5,31), lerped in v onto vx."""
+    vx_ax = np.linspace(-10, 10, 20001)
+    m_ax = np.linspace(2, 5, 31)
+    cols = []
+    for m in m_ax:
+        alpha = np.sqrt(3.0 * gamma(3.0 / m) / 2.0 / gamma(5.0 / m))
+        it = gamma(2.0 / m) * gammaincc(2.0 / m, (np.abs(vx_ax) / (alpha * np.sqrt(2.0))) ** m)
+        cols.append(np.interp(vx, vx_ax, it))
+    return m_ax, np.stack(cols, axis=1)
+
+
+class _Scalar:
+    """One (possibly batched) scalar parameter: stored normalised, trainable when active."""
+
+    def __init__(self, cfg, batch_size, activate, device, raw=False):
+        self.active = bool(cfg.get("active", False)) and activate
+        self.raw = raw
+        self.scale = 1.0 if raw else cfg["ub"] - cfg["lb"]
+        self.shift = 0.0 if raw else cfg["lb"]
+        x = np.full(batch_size, (cfg["val"] - self.shift) / self.scale, dtype=np.float64)
+        if self.active:
+            x = _inv_act(x)
+        self.value = torch.tensor(x, dtype=DT, device=device, requires_grad=self.active)
+
+    def physical(self):
+        v = torch.sigmoid(self.value) if self.active else self.value
+        return v * self.scale + self.shift
+
+
+class ThomsonParams:
+    def __init__(self, param_cfg, num_params, batch=True, activate=False, device=None, dlm_m_offset=0.0):
+        self.param_cfg = param_cfg
+        self.B = int(num_params) if batch else 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        B, dev = self.B, self.device
+        e = param_cfg["electron"]
+        self.leaves = {("electron", k): _Scalar(e[k], B, activate, dev) for k in ["Te", "ne"]}
+        for k in ["lam", "amp1", "amp2", "amp3", "ne_gradient", "Te_gradient", "ud", "Va"]:
+            self.leaves[("general", k)] = _Scalar(param_cfg["general"][k], B, activate, dev)
+        self.ions = sorted([k for k in param_cfg if k.startswith("ion-")], key=lambda s: int(s.split("-")[1]))
+        assert self.ions, "No ion species found in input deck"
+        for ion in self.ions:
+            c = param_cfg[ion]
+            self.leaves[(ion, "Ti")] = _Scalar(c["Ti"], B, activate, dev)
+            self.leaves[(ion, "Z")] = _Scalar(c["Z"], B, activate, dev)
+            self.leaves[(ion, "fract")] = _Scalar(c["fract"], B, activate, dev, raw=True)
+        fe = e["fe"]
+        if fe["dim"] != 1:
+            raise NotImplementedError("2V distributions are not built yet")
+        self.fe_type = fe["type"].casefold()
+        self.vx = vgrid(fe["nvx"])
+        self.dv = self.vx[1] - self.vx[0]
+        if self.fe_type == "dlm":
+            mcfg = dict(val=fe["params"]["m"]["val"], lb=2.0, ub=5.0, active=fe.get("active", False))  # scale 3, shift 2
+            self.leaves[("electron", "m")] = _Scalar(mcfg, B, activate, dev)
+            self.m_offset = float(dlm_m_offset)
+            m_ax, tab = dlm_table(self.vx)
+            self.m_ax = torch.tensor(m_ax, dtype=DT, device=dev)
+            self.f_vx_m = torch.tensor(tab, dtype=DT, device=dev)  # [V, 31]
+        elif self.fe_type == "mx":
+            f = np.exp(-(self.vx**2 / 2))
+            self.f_fixed = torch.tensor(f / f.sum() / self.dv, dtype=DT, device=dev)
+        elif self.fe_type == "arbitrary":
+            raise NotImplementedError("Arbitrary1V producer (Butterworth-smoothed learned f): next row N3")
+        else:
+            raise NotImplementedError(self.fe_type)
+
+    def parameters(self):
+        return [s.value for s in self.leaves.values() if s.active]
+
+    def _fe(self):
+        if self.fe_type == "mx":
+            return self.f_fixed.reshape(1, -1).expand(self.B, -1)
+        m = self.leaves[("electron", "m")].physical() + self.m_offset          # base.py:286
+        i = torch.clamp(torch.searchsorted(self.m_ax, m.detach().contiguous(), right=True), 1, self.m_ax.numel() - 1)
+        w = (m - self.m_ax[i - 1]) / (self.m_ax[i] - self.m_ax[i - 1])
+        f = self.f_vx_m[:, i - 1].T * (1 - w)[:, None] + self.f_vx_m[:, i].T * w[:, None]   # jnp.interp in m (base.py:292)
+        return f / f.sum(dim=1, keepdim=True) / self.dv                                        # base.py:294
+
+    def __call__(self):
+        out = {"electron": {"Te": self.leaves[("electron", "Te")].physical(), "ne": self.leaves[("electron", "ne")].physical(),
+                            "fe": self._fe(), "v": np.broadcast_to(self.vx, (self.B, self.vx.size))},
+               "general": {k: self.leaves[("general", k)].physical() for k in
+                           ["lam", "amp1", "amp2", "amp3", "ne_gradient", "Te_gradient", "ud", "Va"]}}
+        fsum = 0
+        for n, ion in enumerate(self.ions):
+            c = self.param_cfg[ion]
+            out[ion] = {"A": torch.full((self.B,), float(c["A"]["val"]), dtype=DT, device=self.device),
+                        "fract": self.leaves[(ion, "fract")].physical(), "Ti": self.leaves[(ion, "Ti")].physical(),
+                        "Z": self.leaves[(ion, "Z")].physical()}
+            if n > 0 and c["Ti"].get("same", False):
+                out[ion]["Ti"] = out["ion-1"]["Ti"]                           # ts_params.py:555-557
+            fsum = fsum + out[ion]["fract"]
+        for ion in self.ions:
+            out[ion]["fract"] = out[ion]["fract"] / fsum                      # ts_params.py:559-561
+        return out
+
+    def get_unnormed_params(self):
+        p = self()
+        if self.fe_type == "dlm":
+            p["electron"]["m"] = self.leaves[("electron", "m")].physical()
+        return p
