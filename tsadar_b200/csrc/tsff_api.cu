@@ -64,15 +64,17 @@ namespace {
 constexpr int kThreads = 256;
 
 struct PvLayout {
-  size_t D, D64, pend, desc, Dbar, pendbar, tI, tdI, bytes;
+  size_t D, AB, tstat, D64, pend, desc, Dbar, pendbar, tI, tdI, bytes;
   int nodes, npad;
 };
 PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
   PvLayout L;
   L.nodes = (int)N - 1;
-  L.npad = (L.nodes + kPvBlk - 1) / kPvBlk * kPvBlk;
+  L.npad = tree_npad(L.nodes);
   size_t o = 0;
   L.D = o; o += align_up((size_t)B * L.npad * 4);
+  L.AB = o; o += align_up((size_t)B * tree_ab_bytes(L.npad));
+  L.tstat = o; o += align_up((size_t)kTreeStaticDoubles * 8);
   L.D64 = o; o += align_up((size_t)B * L.npad * 8);
   L.pend = o; o += align_up((size_t)B * 2 * 8);
   L.desc = o; o += align_up((size_t)B * P * 16);
@@ -84,15 +86,13 @@ PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
   return L;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, double h, int npad, float* D, double* D64,
-                                                      double* pend) {
+__global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, double h, int npad, float* D, float4* AB,
+                                                      const double* tstat, double* D64, double* pend) {
   const long long b = blockIdx.x;
   const double* fb = f + b * N;
   const int M = N - 2;
-  for (int i = threadIdx.x; i < npad; i += kThreads) {
-    D[b * npad + i] = (i >= 1 && i <= M - 1) ? (float)(fb[i] * h) : 0.f;  // far-field weights p_i * h
-    D64[b * npad + i] = pv_weight(fb, M, h, i);                            // FP64 validation path
-  }
+  tree_prep_cta([fb](int i) { return fb[i]; }, M, npad, D + b * npad, AB + b * ((npad / kTS) * (kTK / 2)), tstat);
+  for (int i = threadIdx.x; i < npad; i += kThreads) D64[b * npad + i] = pv_weight(fb, M, h, i);  // FP64 validation path
   if (threadIdx.x == 0) {
     pend[2 * b] = fb[0];
     pend[2 * b + 1] = fb[M];
@@ -104,10 +104,9 @@ __global__ void __launch_bounds__(kThreads) k_pv_desc(const double* pole, const 
   const long long b = blockIdx.x;
   for (int p = threadIdx.x; p < P; p += kThreads) {
     const double xi = pole[b * P + p], ob = out_bar[b * P + p];
-    float u0, nd;
-    pole_split(xi, z0, h, nodes, u0, nd);
-    desc[b * P + p] = make_float4(u0, nd, (float)(ob * h), 0.f);
-    pv_bwd_pole_exact(xi, ob, z0, h, nodes, pnear + b * npad);
+    int wb0;
+    desc[b * P + p] = pv_desc(xi, ob, z0, h, nodes, npad, wb0);
+    pv_bwd_pole_exact(xi, ob, z0, h, nodes, wb0, pnear + b * npad);
   }
 }
 
@@ -125,12 +124,12 @@ __global__ void k_mul(const double* x, const double* y, long long n, double* out
 int launch_poles(const PvLayout& L, int64_t B, int64_t N, int64_t P, const double* f, char* w, double z0, double h, const double* pole, double* out,
                  double* dout, int prec, cudaStream_t st) {
   PvPolesArgs p;
-  p.D = (float*)(w + L.D); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
+  p.Wt = (float*)(w + L.D); p.AB = (float4*)(w + L.AB); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
   p.pnodes = f; p.pnode_stride = N;
   p.poles = pole; p.pole_bstride = P; p.z0 = z0; p.h = h; p.nodes = L.nodes; p.npad = L.npad; p.P = (int)P;
   p.outI = out; p.outdI = dout;
   p.ntiles = (int)((P + kPvThreads - 1) / kPvThreads);
-  const size_t smem = (size_t)L.npad * 4;
+  const size_t smem = (size_t)L.npad * 4 + tree_ab_bytes(L.npad);
   if (prec == TSFF_PV_FP64) {
     k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
   } else {
@@ -150,11 +149,13 @@ extern "C" size_t tsff_pv_workspace_bytes(int64_t B, int64_t N, int64_t P) {
 extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
                            double* out, double* dout_dpole, int pv_precision, void* ws, void* stream) {
   if (!f || !pole || !out || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
-  if ((size_t)N * 4 > 200 * 1024) { set_error("N too large for shared-memory staging"); return TSFF_E_INVALID; }
+  if (tree_npad((int)N - 1) > kTreeMaxNpad) { set_error("N too large (limit %d nodes)", kTreeMaxNpad); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);
-  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
+  k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
+  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (float4*)(w + L.AB), (double*)(w + L.tstat),
+                                            (double*)(w + L.D64), (double*)(w + L.pend));
   TSFF_LAUNCH_OK("k_pv_prep");
   return launch_poles(L, B, N, P, f, w, z0, h, pole, out, dout_dpole, pv_precision, st);
 }
@@ -168,15 +169,18 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.pendbar, 0, (size_t)B * L.npad * 8, st));
   k_pv_desc<<<(unsigned)B, kThreads, 0, st>>>(pole, out_bar, (int)P, z0, h, L.nodes, L.npad, (float4*)(w + L.desc), (double*)(w + L.pendbar));
   TSFF_LAUNCH_OK("k_pv_desc");
+  k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
   PvNodesArgs n;
-  n.desc = (float4*)(w + L.desc); n.P = (int)P; n.nodes = L.nodes; n.npad = L.npad; n.h = (float)h; n.pbar = (double*)(w + L.Dbar);
-  n.ntiles = (L.npad + kPvThreads - 1) / kPvThreads;
-  k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
+  n.desc = (float4*)(w + L.desc); n.tstat = (double*)(w + L.tstat); n.P = (int)P; n.nodes = L.nodes; n.npad = L.npad;
+  n.pbar = (double*)(w + L.Dbar); n.nsplit = 1;
+  TSFF_SMEM_OPTIN(k_pv_nodes);
+  k_pv_nodes<<<(unsigned)B, kPvThreads, pv_nodes_smem(n.npad), st>>>(n);
   TSFF_LAUNCH_OK("k_pv_nodes");
   k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, f_bar);
   TSFF_LAUNCH_OK("k_pv_bwd_finish");
   if (pole_bar) {
-    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (double*)(w + L.D64), (double*)(w + L.pend));
+    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (float4*)(w + L.AB), (double*)(w + L.tstat),
+                                              (double*)(w + L.D64), (double*)(w + L.pend));
     TSFF_LAUNCH_OK("k_pv_prep");
     int rc = launch_poles(L, B, N, P, f, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);
     if (rc) return rc;

@@ -133,7 +133,8 @@ struct tsff_ctx {
   double xi1_0, xi1_h;
   // PV geometry for the active mode
   int pv_nodes;  // M+1 nodes used by ratintn (N-1)
-  int pv_npad;   // padded to 32
+  int pv_npad;   // padded to whole 64-node blocks, at least three (tsff_tree.cuh)
   double pv_z0, pv_h;
+  double* tstat; // static expansion tables (k_tree_static) for pv_nodes
   cudaEvent_t ev[4];  // optional profile events (fwd start/stop, bwd start/stop)
 };

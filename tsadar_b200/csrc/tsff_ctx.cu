@@ -4,7 +4,7 @@
 
 #include <vector>
 
-#include "tsff_common.cuh"
+#include "tsff_pv_kernels.cuh"
 
 namespace tsff {
 static thread_local char g_err[512] = "";
@@ -106,7 +106,18 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   } else {
     c->pv_nodes = c->V - 1; c->pv_z0 = c->v0; c->pv_h = c->dv;
   }
-  c->pv_npad = (c->pv_nodes + kPvBlk - 1) / kPvBlk * kPvBlk;
+  c->pv_npad = tree_npad(c->pv_nodes);
+  if (c->pv_npad > kTreeMaxNpad) {
+    cudaFree(c->dev_blob); delete c; set_error("f-table too long (%d nodes; limit %d)", cfg->V, kTreeMaxNpad); return TSFF_E_INVALID;
+  }
+  if (cudaMalloc(&c->tstat, kTreeStaticDoubles * sizeof(double)) != cudaSuccess) {
+    cudaFree(c->dev_blob); delete c; set_error("cudaMalloc failed"); return TSFF_E_NOMEM;
+  }
+  k_tree_static<<<1, 256>>>(c->pv_nodes - 1, c->tstat);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(c->tstat); cudaFree(c->dev_blob); delete c; set_error("k_tree_static failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TSFF_E_CUDA;
+  }
   *out = c;
   return TSFF_OK;
 }
@@ -120,6 +131,7 @@ extern "C" int tsff_ctx_set_profile_events(tsff_ctx* ctx, void* e0, void* e1, vo
 
 extern "C" void tsff_ctx_destroy(tsff_ctx* ctx) {
   if (!ctx) return;
+  cudaFree(ctx->tstat);
   cudaFree(ctx->dev_blob);
   delete ctx;
 }

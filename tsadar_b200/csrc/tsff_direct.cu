@@ -28,7 +28,7 @@ __device__ __forceinline__ double grad_at(const T* f, int V, double dv, int i) {
 
 struct DirectLayout {  // byte offsets inside `saved` and `ws` for a batch of B lineouts
   size_t s_lg, s_I, s_dI, saved_bytes;
-  size_t w_D, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
+  size_t w_D, w_AB, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
       ws_bytes;
 };
 
@@ -42,12 +42,13 @@ DirectLayout direct_layout(const tsff_ctx* c, int64_t B) {
   L.saved_bytes = o;
   o = 0;
   L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
+  L.w_AB = o; o += align_up((size_t)B * tree_ab_bytes(c->pv_npad));
   L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
   L.w_pend = o; o += align_up((size_t)B * 2 * 8);
   L.w_ff = o; o += align_up((size_t)B * P * 8);
   L.w_desc = o; o += align_up((size_t)B * P * 16);
-  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
   L.w_zero_begin = o;
+  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
   L.w_accfe = o; o += align_up((size_t)B * c->V * 8);
   L.w_accdf = o; o += align_up((size_t)B * c->V * 8);
   L.w_pendbar = o; o += align_up((size_t)B * 2 * 8);
@@ -69,7 +70,9 @@ struct DirectArgs {
   double* lg;        // [B][G][kLGDoubles]
   double* sI;        // [B][P]
   double* sdI;       // [B][P]
-  float* D;          // [B][npad]
+  float* D;          // [B][npad]  FP32 node weights p_i (interior nodes)
+  float4* AB;        // [B][NB*kTK/2] block expansion coefficients (tsff_tree.cuh)
+  const double* tstat;
   double* D64;       // [B][npad] or null
   double* pend;      // [B][2]
   double* ff;        // [B][G][W][A]
@@ -109,10 +112,14 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
     store_lg(a.lg + (b * a.G + threadIdx.x) * kLGDoubles, L);
   }
   const int M = a.nodes - 1;
-  for (int i = threadIdx.x; i < a.npad; i += kThreads) {
-    // far-field node weights p_i * h of the interior nodes (the two end nodes are summed exactly per pole)
-    a.D[b * a.npad + i] = (i >= 1 && i <= M - 1) ? (float)(grad_at(fe, a.V, a.dv, i) * a.dv) : 0.f;
-    if (a.D64) {  // log-form weights for the FP64 validation path
+  {
+    const int V = a.V;
+    const double dv = a.dv;
+    tree_prep_cta([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * a.npad,
+                  a.AB + b * ((a.npad / kTS) * (kTK / 2)), a.tstat);
+  }
+  if (a.D64) {  // log-form weights for the FP64 validation path
+    for (int i = threadIdx.x; i < a.npad; i += kThreads) {
       double d = 0.0;
       if (i <= M) {
         double pc = grad_at(fe, a.V, a.dv, i);
@@ -136,36 +143,46 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const DirectArgs 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ LG sL;
-  float* sD = reinterpret_cast<float*>(smem_raw);
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float4* sAB = reinterpret_cast<float4*>(smem_raw + (size_t)a.npad * 4);
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
   const long long b = bg / a.G;
+  const int NB = a.npad / kTS, M = a.nodes - 1;
   if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
-  if (PREC == TSFF_PV_FP32) stage_bulk(sD, a.D + b * a.npad, (uint32_t)a.npad * 4u, &bar);
+  if (PREC == TSFF_PV_FP32)
+    stage_bulk2(sW, a.D + b * a.npad, (uint32_t)a.npad * 4u, sAB, a.AB + b * (NB * (kTK / 2)), (uint32_t)tree_ab_bytes(a.npad), &bar);
   else __syncthreads();
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int WA = a.W * a.A;
 
-  float u0[R], nd[R];
+  TreePole tp[R];
   double g0d[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    int idx = (tile * kThreads + threadIdx.x) * R + r;
     if (idx >= WA) idx = WA - 1;
     Kin q;
     kin_forward(sL, a.omgs[idx / a.A], a.costh[idx % a.A], q);
-    pole_split(q.xie, a.v0, a.dv, a.nodes, u0[r], nd[r]);
+    tp[r] = tree_pole(q.xie, a.v0, a.dv, M, NB);
     g0d[r] = a.v0 - q.xie;
   }
-  double accI[R], accJ[R];
-  if (PREC == TSFF_PV_FP32) pv_accumulate<R, true>(sD, a.npad / kPvBlk, far_coef(a.dv), u0, nd, accI, accJ);
-  else pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.dv, g0d, accI, accJ);
+  double accI[R], accJ[R], nrI[R], nrJ[R];
+  if (PREC == TSFF_PV_FP32) {
+#pragma unroll
+    for (int r = 0; r < R; r++) accI[r] = accJ[r] = nrI[r] = nrJ[r] = 0.0;
+    tree_far<R>(sAB, NB, tp, accI, accJ);
+#pragma unroll
+    for (int r = 0; r < R; r++) tree_near(sW, tp[r], nrI[r], nrJ[r]);
+  } else {
+    pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.dv, g0d, accI, accJ);
+  }
 
   const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    const int idx = (tile * kThreads + threadIdx.x) * R + r;
     if (idx >= WA) continue;
     const int j = idx / a.A, ia = idx % a.A;
     const double omgs = a.omgs[j];
@@ -177,9 +194,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const DirectArgs 
     if (PREC == TSFF_PV_FP32) {
       const int V = a.V;
       const double dv = a.dv;
-      pv_near_exact(q.xie, a.v0, dv, a.nodes, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
-      I += accI[r];
-      dI += accJ[r];
+      tree_near_exact(q.xie, a.v0, dv, M, tp[r].wb0, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
+      I += accI[r] + nrI[r];
+      dI += accJ[r] / (kTs * dv) + nrJ[r] / dv;
     } else {
       pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.dv, I, dI);
     }
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
   LG Lb;
   lg_zero(Lb);
   for (int r = 0; r < R; r++) {
-    const int idx = tile * (kThreads * R) + r * kThreads + threadIdx.x;
+    const int idx = (tile * kThreads + threadIdx.x) * R + r;
     if (idx >= WA) continue;
     const int j = idx / a.A, ia = idx % a.A;
     const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
@@ -267,12 +284,12 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
       atomicAdd(&a.accdf[b * a.V + i_f], (1.0 - t_f) * dfe_bar);
       atomicAdd(&a.accdf[b * a.V + i_f + 1], t_f * dfe_bar);
     }
-    // d I / d p_i for the nodes next to the pole and the two end nodes, exactly (FP64); the far field is k_pv_nodes'
-    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, a.accdf + b * a.V);
+    // d I / d p_i for the nodes next to the pole (and an end node inside its window), exactly (FP64); the rest is
+    // k_pv_nodes' (far blocks + near-window series)
+    int wb0;
+    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = pv_desc(q.xie, Ibar, a.v0, a.dv, a.nodes, a.npad, wb0);
+    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, wb0, a.accdf + b * a.V);
     kin_backward(sL, omgs, cth, q, kb, Lb);
-    float u0, nd;
-    pole_split(q.xie, a.v0, a.dv, a.nodes, u0, nd);
-    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = make_float4(u0, nd, (float)(Ibar * a.dv), 0.f);
   }
   double vals[kLGDoubles];
   store_lg(vals, Lb);
@@ -316,6 +333,7 @@ void fill_static(const tsff_ctx* c, DirectArgs& a) {
   a.nodes = c->pv_nodes; a.npad = c->pv_npad;
   a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;
   a.omgs = c->omgs; a.costh = c->costh; a.wts = c->wts; a.jmul = c->jmul; a.zt = c->zt;
+  a.tstat = c->tstat;
 }
 
 template <typename T>
@@ -329,13 +347,14 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   fill_static(c, a);
   a.params = params; a.fe = fe;
   a.lg = (double*)(sv + L.s_lg); a.sI = (double*)(sv + L.s_I); a.sdI = (double*)(sv + L.s_dI);
-  a.D = (float*)(w + L.w_D); a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
+  a.D = (float*)(w + L.w_D); a.AB = (float4*)(w + L.w_AB);
+  a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend);
   a.ff = ff_out ? ff_out : (double*)(w + L.w_ff);
   k_direct_prep<T><<<(unsigned)B, kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_prep");
   const int WA = c->W * c->A;
-  const size_t smem = (size_t)c->pv_npad * 4;
+  const size_t smem = (size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad);
   // poles per thread: 2 while the grid still fills the device, else 1
   const long long tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
   const bool useR2 = (long long)B * c->G * tiles2 >= 2LL * c->sm_count;
@@ -385,16 +404,11 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
   PvNodesArgs n;
-  n.desc = a.desc; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.h = (float)c->dv; n.pbar = a.Dbar;
-  const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
+  n.desc = a.desc; n.tstat = c->tstat; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.pbar = a.Dbar;
+  n.nsplit = pv_nodes_split(B, n.P, c->sm_count);
   if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
-  if ((long long)B * tiles4 >= 2LL * c->sm_count) {
-    n.ntiles = (int)tiles4;
-    k_pv_nodes<4><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
-  } else {
-    n.ntiles = (c->pv_npad + kPvThreads - 1) / kPvThreads;
-    k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
-  }
+  TSFF_SMEM_OPTIN(k_pv_nodes);
+  k_pv_nodes<<<(unsigned)(B * n.nsplit), kPvThreads, pv_nodes_smem(n.npad), st>>>(n);
   TSFF_LAUNCH_OK("k_pv_nodes");
   if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   const size_t smem = (size_t)c->V * 8;
@@ -412,7 +426,7 @@ size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B
 
 int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
                void* saved, void* ws, cudaStream_t st) {
-  if ((size_t)c->pv_npad * 4 > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  if ((size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
                               : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
 }

@@ -1,22 +1,82 @@
-// tsff_pv_kernels.cuh -- the two O(poles x nodes) kernels shared by every mode.
+// tsff_pv_kernels.cuh -- the principal-value sweeps shared by every mode (block-multipole form, tsff_tree.cuh).
 //
-//   k_pv_poles : thread-owns-pole forward sweep   I(xi_p), dI/dxi_p          (1 MUFU.RCP per pair)
-//   k_pv_nodes : thread-owns-node adjoint sweep   pbar_i = sum_p Ibar_p W(g_{p,i})  (1 MUFU.RCP per pair)
+//   tree_prep_cta : per lineout: FP32 node weights + the K Laurent coefficients of every 64-node block
+//   k_pv_poles    : thread-owns-pole forward sweep   I(xi_p), dI/dxi_p
+//   k_pv_nodes    : adjoint sweep  pbar_i = sum_p Ibar_p dI_p/dp_i  (far: block-owner gathers local coefficients over
+//                   the poles, near: node-owner loops over the poles whose window covers its block)
 //
-// Bound: MUFU (XU) pipe, 16 lanes/clk/SM; the FP32 FMA pipe carries 3-4 ops per pair beside it.
-// Shared memory: the pole-independent weights D (<= 16 KB for 4096 nodes) staged by one TMA bulk copy;
-// pole descriptors for the adjoint sweep staged in 8 KB chunks.
+// Bound: instruction issue (FP32 FMA pipe + XU side by side); no HBM traffic to speak of.
+// Shared memory: node weights (<= 16 KB at 4096 nodes) + block coefficients (6 KB) staged by TMA bulk copies.
 #pragma once
 #include "tsff_common.cuh"
+#include "tsff_tree.cuh"
 
 namespace tsff {
 
 constexpr int kPvThreads = 256;
 
+// bytes of the per-lineout coefficient array  [NB][kTK] x (A_m, (m+1) A_m)
+TSFF_HD size_t tree_ab_bytes(int npad) { return (size_t)(npad / kTS) * kTK * 8; }
+
+#if defined(__CUDACC__)
+// Two bulk copies completed on one mbarrier.  Called by all threads; one use per kernel (parity 0).
+__device__ __forceinline__ void stage_bulk2(void* d0, const void* s0, uint32_t n0, void* d1, const void* s1, uint32_t n1,
+                                            uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, n0 + n1);
+    bulk_g2s(d0, s0, n0, bar);
+    bulk_g2s(d1, s1, n1, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// Static tables of the expansion (depend only on the node count): q_m(e) for the kTS in-block offsets, the two end-node
+// rows (node 0, node M), and the cm matrix.  Built once per context / call by k_tree_static.
+constexpr int kTreeStaticDoubles = (kTS + 2) * kTK + kTK * (kTK / 2);
+static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) {
+  for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) {
+    const double c = 0.5 * (double)(kTS - 1);
+    double v;
+    if (i < (kTS + 2) * kTK) {
+      const int k = i / kTK, m = i % kTK;
+      if (k < kTS) v = tree_q(m, (double)k - c);
+      else if (k == kTS) v = tree_q_end(m, 0.0 - c, false);
+      else v = tree_q_end(m, (double)(M % kTS) - c, true);
+    } else {
+      const int k = i - (kTS + 2) * kTK;
+      v = tree_cm(k / (kTK / 2), k % (kTK / 2));
+    }
+    out[i] = v;
+  }
+}
+
+// Per-lineout preparation, executed by one CTA.  pget(i) -> p_i (FP64) for 0 <= i <= M.
+//   Wt [npad]  FP32 weights of the interior nodes 1..M-1 (0 elsewhere)
+//   AB [NB*kTK/2] float4 = (A_m, (m+1) A_m, A_{m+1}, (m+2) A_{m+1})
+// tstat: the k_tree_static table (global).
+template <typename PGet>
+__device__ __forceinline__ void tree_prep_cta(PGet pget, int M, int npad, float* Wt, float4* AB, const double* tstat) {
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)pget(i) : 0.f;
+  const double* cm = tstat + (kTS + 2) * kTK;
+  const int NB = npad / kTS;
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) {
+    double A[kTK];
+    tree_block_coeffs(pget, M, b, cm, tstat + kTS * kTK, A);
+#pragma unroll
+    for (int q = 0; q < kTK / 2; q++)
+      AB[b * (kTK / 2) + q] = make_float4((float)A[2 * q], (float)((double)(2 * q + 1) * A[2 * q]), (float)A[2 * q + 1],
+                                          (float)((double)(2 * q + 2) * A[2 * q + 1]));
+  }
+}
+#endif
+
 struct PvPolesArgs {
-  const float* D;        // [B][npad] far-field node weights p_i*h (FP32; zero at i = 0, i >= M)
-  const double* D64;     // [B][npad] log-form weights D_i (FP64 validation path) or nullptr
-  const double* pend;    // [B][2]   (p_0, p_M)
+  const float* Wt;       // [B][npad] FP32 node weights
+  const float4* AB;      // [B][NB*kTK/2] block coefficients
+  const double* D64;     // [B][npad64] log-form weights D_i (FP64 validation path) or nullptr
+  const double* pend;    // [B][2]   (p_0, p_M)   (FP64 validation path)
   const double* pnodes;  // node values p_i (FP64), row b at pnodes + b*pnode_stride
   long long pnode_stride;
   const double* poles;   // pole positions, row b at poles + b*pole_bstride
@@ -32,40 +92,48 @@ template <int R, int PREC>
 __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  float* sD = reinterpret_cast<float*>(smem_raw);
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float4* sAB = reinterpret_cast<float4*>(smem_raw + (size_t)a.npad * 4);
   const long long b = blockIdx.x / a.ntiles;
   const int tile = blockIdx.x % a.ntiles;
-  if (PREC == TSFF_PV_FP32) stage_bulk(sD, a.D + b * a.npad, (uint32_t)a.npad * 4u, &bar);
+  const int NB = a.npad / kTS, M = a.nodes - 1;
+  if (PREC == TSFF_PV_FP32)
+    stage_bulk2(sW, a.Wt + b * a.npad, (uint32_t)a.npad * 4u, sAB, a.AB + b * (NB * (kTK / 2)), (uint32_t)tree_ab_bytes(a.npad),
+                &bar);
 
   const double* poles = a.poles + b * a.pole_bstride;
   double xi[R];
-  float u0[R], nd[R];
+  TreePole tp[R];
   double g0d[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    int p = tile * (kPvThreads * R) + r * kPvThreads + threadIdx.x;
+    int p = (tile * kPvThreads + threadIdx.x) * R + r;
     xi[r] = poles[p < a.P ? p : a.P - 1];
-    pole_split(xi[r], a.z0, a.h, a.nodes, u0[r], nd[r]);
+    tp[r] = tree_pole(xi[r], a.z0, a.h, M, NB);
     g0d[r] = a.z0 - xi[r];
   }
-  double accI[R], accJ[R];
+  double accI[R], accJ[R], nrI[R], nrJ[R];
   if (PREC == TSFF_PV_FP32) {
-    pv_accumulate<R, true>(sD, a.npad / kPvBlk, far_coef(a.h), u0, nd, accI, accJ);
+#pragma unroll
+    for (int r = 0; r < R; r++) accI[r] = accJ[r] = nrI[r] = nrJ[r] = 0.0;
+    tree_far<R>(sAB, NB, tp, accI, accJ);
+#pragma unroll
+    for (int r = 0; r < R; r++) tree_near(sW, tp[r], nrI[r], nrJ[r]);
   } else {
     pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.h, g0d, accI, accJ);
   }
-  const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    int p = tile * (kPvThreads * R) + r * kPvThreads + threadIdx.x;
+    int p = (tile * kPvThreads + threadIdx.x) * R + r;
     if (p < a.P) {
       double I, dI;
       if (PREC == TSFF_PV_FP32) {
         const double* pn = a.pnodes + b * a.pnode_stride;
-        pv_near_exact(xi[r], a.z0, a.h, a.nodes, [pn](int i) { return pn[i]; }, I, dI);
-        I += accI[r];
-        dI += accJ[r];
+        tree_near_exact(xi[r], a.z0, a.h, M, tp[r].wb0, [pn](int i) { return pn[i]; }, I, dI);
+        I += accI[r] + nrI[r];
+        dI += accJ[r] / (kTs * a.h) + nrJ[r] / a.h;
       } else {
+        const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
         pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.h, I, dI);
       }
       a.outI[b * a.P + p] = I;
@@ -73,105 +141,201 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
     }
   }
 }
+#endif
 
+// ---- adjoint ----------------------------------------------------------------------------------------------------
 struct PvNodesArgs {
-  const float4* desc;  // [B][P]  (u0 = -n_p, nd = -delta_p, Ibar_p * h, unused)
-  int P, nodes, npad, ntiles;
-  float h;
-  double* pbar;        // [B][npad]  far-field part of d loss / d p_i for interior nodes 1..M-1 (0 elsewhere)
+  const float4* desc;   // [B][P]  (un = -n_p, ndh = -delta_p/h, Ibar_p, wb0 as int bits)
+  const double* tstat;  // k_tree_static table
+  int P, nodes, npad, nsplit;
+  double* pbar;         // [B][npad]  d loss / d p_i without the exact near part (nsplit > 1: atomically accumulated, zero it)
 };
 
-constexpr int kNodeChunk = 512;  // poles staged per shared-memory chunk (8 KB)
+constexpr int kNodeChunk = 1024;   // poles staged per shared-memory chunk (2 x 16 KB)
+constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per block
 
-// pbar_i (far part) = sum_p Ibar_p W(g_{p,i}) over poles with |i - n_p| > kNearHalf.
-// Poles are staged in shared memory in chunks; for every sub-chunk of 64 poles the range of nearest-node indices is
-// recorded, so that a warp whose nodes are farther than kMidHalf from all of them runs the short, unmasked series
-// (5.25 FMA-pipe ops + 1 MUFU.RCP per pair: MUFU-bound), and only the sub-chunks next to the warp's nodes pay for the
-// long series and the near-node mask.
-template <int R>
-__global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
-  __shared__ float4 sdesc[kNodeChunk];
-  __shared__ float srange[kNodeChunk / 64][2];  // (max u0, min u0) = (-n_min, -n_max) per 64-pole sub-chunk
-  const long long b = blockIdx.x / a.ntiles;
-  const int tile = blockIdx.x % a.ntiles;
-  const int i0 = (tile * kPvThreads + threadIdx.x) * R;
-  const float fi0 = (float)i0;
-  const float c2 = a.h * a.h * (1.f / 6.f), c4 = a.h * a.h * a.h * a.h * (1.f / 15.f);
-  const float4* desc = a.desc + b * a.P;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double acc[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
-  for (int c0 = 0; c0 < a.P; c0 += kNodeChunk) {
-    const int nc = min(kNodeChunk, a.P - c0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < kNodeChunk; k += kPvThreads)
-      sdesc[k] = (k < nc) ? desc[c0 + k] : make_float4(1e6f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // one warp per sub-chunk: range of u0 over its real poles
-    for (int sc = wid; sc < kNodeChunk / 64; sc += kPvThreads / 32) {
-      float hi = -3.0e38f, lo = 3.0e38f;
-      for (int k = lane; k < 64; k += 32) {
-        const int kk = sc * 64 + k;
-        if (kk < nc) { const float v = sdesc[kk].x; hi = fmaxf(hi, v); lo = fminf(lo, v); }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      }
-      if (lane == 0) { srange[sc][0] = hi; srange[sc][1] = lo; }
-    }
-    __syncthreads();
-    for (int s0 = 0; s0 < kNodeChunk; s0 += 64) {
-      if (s0 >= nc) break;
-      // offsets i - n_p of this thread's nodes against the sub-chunk's poles lie in [fi0 + lo, fi0 + R-1 + hi]
-      const float omin = fi0 + srange[s0 / 64][1], omax = fi0 + (float)(R - 1) + srange[s0 / 64][0];
-      const bool mid = (omin <= (float)kMidHalf) && (omax >= -(float)kMidHalf);
-      float part[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) part[r] = 0.f;
-      if (!__any_sync(0xffffffffu, mid)) {
-#pragma unroll 8
-        for (int k = 0; k < 64; k++) {
-          const float4 d = sdesc[s0 + k];
-          const float gbase = fmaf(fi0 + d.x, a.h, d.y);  // g at node i0
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float g = fmaf((float)r, a.h, gbase);
-            const float rg = rcp_approx(g);
-            part[r] = fmaf(d.z * rg, fmaf(rg * rg, c2, 1.f), part[r]);   // Ibar h * W / h
-          }
-        }
-      } else {
-#pragma unroll 4
-        for (int k = 0; k < 64; k++) {
-          const float4 d = sdesc[s0 + k];
-          const float u = fi0 + d.x;              // i0 - n_p, exact
-          const float gbase = fmaf(u, a.h, d.y);
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const float g = fmaf((float)r, a.h, gbase);
-            const bool far = fabsf(u + (float)r) > (float)kNearHalf + 0.5f;
-            const float rg = far ? rcp_approx(g) : 0.f;
-            const float s2 = rg * rg;
-            part[r] = fmaf(d.z, rg * fmaf(fmaf(s2, c4, c2), s2, 1.f), part[r]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; r++) acc[r] += (double)part[r];
-    }
-  }
-  const int M = a.nodes - 1;
-#pragma unroll
-  for (int r = 0; r < R; r++)
-    if (i0 + r < a.npad) a.pbar[b * a.npad + i0 + r] = (i0 + r >= 1 && i0 + r <= M - 1) ? acc[r] : 0.0;
+inline size_t pv_nodes_smem(int npad) {
+  const int NB = npad / kTS;
+  return (size_t)kNodeChunk * 16 * 2 + (size_t)npad * 8 + (size_t)NB * kTK * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
 }
 
-// Exact (FP64) adjoint contributions of one pole: the kNearHalf nodes either side of it and the two end nodes
-// (whose weights are first differences plus the explicit endpoint terms of I).  Atomically added to pnear[0..M].
-__device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, double* pnear) {
+// pole splits per lineout: 1 when the batch alone fills the device, else enough CTAs for two per SM (each split
+// re-does the O(nodes) spreading, so never more than one split per kNodeChunk poles)
+inline int pv_nodes_split(int64_t B, int P, int sm_count) {
+  if (B >= 2LL * sm_count) return 1;
+  long long want = (2LL * sm_count + B - 1) / B;
+  long long most = (P + kNodeChunk - 1) / kNodeChunk;
+  if (want > most) want = most;
+  return want < 1 ? 1 : (int)want;
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// One CTA per (lineout, pole split).  Per chunk of kNodeChunk poles:
+//   1. stage the descriptors in shared memory
+//   2. far:  thread (block fb, pole subset fq) accumulates L_{fb,m} += Ibar_p t^(m+1) over its far poles (two poles per
+//      packed instruction); FP32 within the chunk, FP64 across chunks
+//   3. counting-sort the descriptors by window start wb0, so that every node block sees its near poles as one
+//      contiguous range
+//   4. near: a warp owns one 64-node block at a time (two nodes per lane, packed) and loops over the poles with
+//      wb0 in [nb-2, nb]; short series, |i - n_p| <= kNearHalf masked (the exact FP64 terms are added by the caller)
+// then L is spread to the nodes with the static weights q_m(e) and everything is written (or atomically added) to pbar.
+static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int NB = a.npad / kTS, M = a.nodes - 1;
+  float4* sraw = reinterpret_cast<float4*>(smem_raw);
+  float4* ssort = sraw + kNodeChunk;
+  double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad]
+  double* sL = spbar + a.npad;                                         // [NB][kTK]
+  int* shist = reinterpret_cast<int*>(sL + NB * kTK);                  // [NB + 1]
+  int* scur = shist + NB + 1;                                          // [NB + 1]
+  const long long b = blockIdx.x / a.nsplit;
+  const int split = blockIdx.x % a.nsplit;
+  const int per = (a.P + a.nsplit - 1) / a.nsplit;
+  const int p_begin = split * per, p_end = min(a.P, p_begin + per);
+  const float4* desc = a.desc + b * a.P;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < a.npad; i += kPvThreads) spbar[i] = 0.0;
+  for (int i = threadIdx.x; i < NB * kTK; i += kPvThreads) sL[i] = 0.0;
+  // far-phase thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
+  int NBP = 1;
+  while (NBP < NB) NBP <<= 1;
+  const int Q = kPvThreads / NBP;
+  const int fb = threadIdx.x % NBP, fq = threadIdx.x / NBP;
+  const float cb = (float)(2 * fb) + (float)(0.5 * (kTS - 1) / kTs);
+  double L64[kTK];
+#pragma unroll
+  for (int m = 0; m < kTK; m++) L64[m] = 0.0;
+  const float2 one = make_float2(1.f, 1.f), c2 = make_float2(1.f / 6.f, 1.f / 6.f), c4 = make_float2(1.f / 15.f, 1.f / 15.f);
+  const float lim = (float)kNearHalf + 0.5f;
+
+  for (int c0 = p_begin; c0 < p_end; c0 += kNodeChunk) {
+    const int nc = min(kNodeChunk, p_end - c0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) sraw[k] = desc[c0 + k];
+    for (int k = threadIdx.x; k <= NB; k += kPvThreads) shist[k] = 0;
+    __syncthreads();
+    // ---- far
+    if (fb < NB) {
+      float2 Lp[kTK];
+#pragma unroll
+      for (int m = 0; m < kTK; m++) Lp[m] = make_float2(0.f, 0.f);
+      for (int k = fq; k < nc; k += 2 * Q) {
+        const float4 d0 = sraw[k];
+        const bool has1 = (k + Q) < nc;
+        const float4 d1 = has1 ? sraw[k + Q] : make_float4(0.f, 0.f, 0.f, __int_as_float(fb));
+        const float g0 = fmaf(d0.y, kInvTs, fmaf(d0.x, kInvTs, cb));
+        const float g1 = fmaf(d1.y, kInvTs, fmaf(d1.x, kInvTs, cb));
+        const bool far0 = (unsigned)(fb - __float_as_int(d0.w)) > 2u;
+        const bool far1 = has1 && ((unsigned)(fb - __float_as_int(d1.w)) > 2u);
+        const float2 t = make_float2(far0 ? rcp_approx(g0) : 0.f, far1 ? rcp_approx(g1) : 0.f);
+        float2 pw = fmul2(make_float2(d0.z, d1.z), t);
+#pragma unroll
+        for (int m = 0; m < kTK; m++) {
+          Lp[m] = fadd2(Lp[m], pw);
+          pw = fmul2(pw, t);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < kTK; m++) L64[m] += (double)Lp[m].x + (double)Lp[m].y;
+    }
+    // ---- counting sort by wb0
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[__float_as_int(sraw[k].w) + 1], 1);
+    __syncthreads();
+    if (wid == 0) {  // inclusive scan -> shist[k] = first sorted slot of key k, shist[NB] = nc
+      int carry = 0;
+      for (int k0 = 0; k0 <= NB; k0 += 32) {
+        const int k = k0 + lane;
+        int v = (k <= NB) ? shist[k] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += n;
+        }
+        v += carry;
+        if (k <= NB) { shist[k] = v; scur[k] = v; }
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) {
+      const float4 d = sraw[k];
+      ssort[atomicAdd(&scur[__float_as_int(d.w)], 1)] = d;
+    }
+    __syncthreads();
+    // ---- near
+    for (int nb = wid; nb < NB; nb += kPvThreads / 32) {
+      // poles whose window [wb0, wb0+2] contains block nb: wb0 in [nb-2, nb]
+      const int klo = shist[max(nb - 2, 0)], khi = shist[nb + 1];
+      const float fi0 = (float)(kTS * nb + 2 * lane);
+      float2 acc = make_float2(0.f, 0.f);
+      double acc64x = 0.0, acc64y = 0.0;
+      int cnt = 0;
+      for (int k = klo; k < khi; k++) {
+        const float4 d = ssort[k];
+        const float u0 = fi0 + d.x, u1 = u0 + 1.f;   // i - n_p, exact
+        float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
+        // the masked zone |i - n_p| <= kNearHalf touches this block only if n_p is within kNearHalf of it (warp-uniform)
+        const float nrel = -d.x - (float)(kTS * nb);
+        if (nrel >= -lim && nrel <= (float)(kTS - 1) + lim) {
+          x0 = fabsf(u0) > lim ? x0 : 0.f;
+          x1 = fabsf(u1) > lim ? x1 : 0.f;
+        }
+        const float2 x = make_float2(x0, x1);
+        const float2 s2 = fmul2(x, x);
+        acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
+        if (++cnt == 64) {
+          acc64x += (double)acc.x;
+          acc64y += (double)acc.y;
+          acc = make_float2(0.f, 0.f);
+          cnt = 0;
+        }
+      }
+      spbar[kTS * nb + 2 * lane] += acc64x + (double)acc.x;
+      spbar[kTS * nb + 2 * lane + 1] += acc64y + (double)acc.y;
+    }
+  }
+  if (fb < NB) {
+#pragma unroll
+    for (int m = 0; m < kTK; m++) atomicAdd(&sL[fb * kTK + m], L64[m]);
+  }
+  __syncthreads();
+  // ---- spread the local coefficients to the nodes and write out
+  double* out = a.pbar + b * a.npad;
+  const double* q = a.tstat;
+  for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+    double v = 0.0;
+    const int nb = i / kTS, k = i % kTS;
+    if (i >= 1 && i <= M - 1) {
+      v = spbar[i];
+#pragma unroll
+      for (int m = 0; m < kTK; m++) v += sL[nb * kTK + m] * q[k * kTK + m];
+    } else if (i == 0) {
+#pragma unroll
+      for (int m = 0; m < kTK; m++) v += sL[m] * q[kTS * kTK + m];
+    } else if (i == M) {
+#pragma unroll
+      for (int m = 0; m < kTK; m++) v += sL[nb * kTK + m] * q[(kTS + 1) * kTK + m];
+    }
+    if (a.nsplit == 1) out[i] = v;
+    else if (v != 0.0) atomicAdd(&out[i], v);
+  }
+}
+
+// Exact (FP64) adjoint contributions of one pole: the kNearHalf nodes either side of it, and an end node when its
+// block lies in the pole's near window.  Atomically added to pnear[0..M].
+__device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, int wb0,
+                                                  double* pnear) {
   if (Ibar == 0.0) return;
   const int M = nodes - 1;
   double rn = rint((xi - z0) / h);
@@ -189,9 +353,21 @@ __device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double
       pc = pp;
     }
   }
-  const double g0 = z0 - xi, gM = z0 + (double)M * h - xi;
-  atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log(fmax(fabs(g0), 1e-300))));
-  atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log(fmax(fabs(gM), 1e-300))));
+  if (wb0 == 0) {
+    const double g0 = z0 - xi;
+    atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log(fmax(fabs(g0), 1e-300))));
+  }
+  if ((unsigned)(M / kTS - wb0) <= 2u) {
+    const double gM = z0 + (double)M * h - xi;
+    atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log(fmax(fabs(gM), 1e-300))));
+  }
+}
+
+// descriptor of one pole for k_pv_nodes
+__device__ __forceinline__ float4 pv_desc(double xi, double Ibar, double z0, double h, int nodes, int npad, int& wb0) {
+  const TreePole t = tree_pole(xi, z0, h, nodes - 1, npad / kTS);
+  wb0 = t.wb0;
+  return make_float4(t.un, t.ndh, (float)Ibar, __int_as_float(t.wb0));
 }
 #endif
 

@@ -24,7 +24,7 @@ constexpr int kWarps = kThreads / 32;
 
 struct TableLayout {
   size_t s_lg, s_lnf, s_slope, s_ratmod, s_T, saved_bytes;
-  size_t w_D, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
+  size_t w_D, w_AB, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
       ws_bytes;
 };
 
@@ -39,12 +39,13 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
   L.saved_bytes = o;
   o = 0;
   L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
+  L.w_AB = o; o += align_up((size_t)B * tree_ab_bytes(c->pv_npad));
   L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
   L.w_pend = o; o += align_up((size_t)B * 2 * 8);
   L.w_ratdf = o; o += align_up((size_t)B * kXi1N * 8);
   L.w_desc = o; o += align_up((size_t)B * kXi2N * 16);
-  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
   L.w_zero_begin = o;
+  L.w_Dbar = o; o += align_up((size_t)B * c->pv_npad * 8);
   L.w_Tbar = o; o += align_up((size_t)B * kXi2N * 8);
   L.w_lnfbar = o; o += align_up((size_t)B * c->V * 8);
   L.w_slopebar = o; o += align_up((size_t)B * c->V * 8);
@@ -64,6 +65,8 @@ struct TableArgs {
   const void* fe;
   double *lg, *lnf, *slope, *ratmod, *T;
   float* D;
+  float4* AB;
+  const double* tstat;
   double* D64;
   double* pend;
   double* ratdf;
@@ -140,10 +143,10 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
   for (int n = threadIdx.x; n < kXi1N; n += kThreads) s_p[n] = grad_sm(s_rat, kXi1N, ih, n);  // form_factor.py:264
   __syncthreads();
   const int M = a.nodes - 1;
-  for (int i = threadIdx.x; i < a.npad; i += kThreads) {
-    a.D[b * a.npad + i] = (i >= 1 && i <= M - 1) ? (float)(s_p[i] * a.xi1_h) : 0.f;   // far-field weights p_i * h
+  tree_prep_cta([s_p](int i) { return s_p[i]; }, M, a.npad, a.D + b * a.npad, a.AB + b * ((a.npad / kTS) * (kTK / 2)), a.tstat);
+  for (int i = threadIdx.x; i < kXi1N; i += kThreads) {
     if (a.D64) a.D64[b * a.npad + i] = pv_weight(s_p, M, a.xi1_h, i);                  // FP64 validation path
-    a.ratdf[b * kXi1N + i] = (i < kXi1N) ? s_p[i] : 0.0;
+    a.ratdf[b * kXi1N + i] = s_p[i];
   }
   if (threadIdx.x == 0) {
     a.pend[2 * b] = s_p[0];
@@ -308,10 +311,9 @@ __global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a) {
   for (int p = threadIdx.x; p < kXi2N; p += kThreads) {
     const double xi = a.xi2[p];
     const double tb = a.Tbar[b * kXi2N + p];
-    float u0, nd;
-    pole_split(xi, a.xi1_0, a.xi1_h, a.nodes, u0, nd);
-    a.desc[b * kXi2N + p] = make_float4(u0, nd, (float)(tb * a.xi1_h), 0.f);
-    pv_bwd_pole_exact(xi, tb, a.xi1_0, a.xi1_h, a.nodes, a.pnear + b * kXi1N);
+    int wb0;
+    a.desc[b * kXi2N + p] = pv_desc(xi, tb, a.xi1_0, a.xi1_h, a.nodes, a.npad, wb0);
+    pv_bwd_pole_exact(xi, tb, a.xi1_0, a.xi1_h, a.nodes, wb0, a.pnear + b * kXi1N);
   }
 }
 
@@ -397,6 +399,7 @@ void fill_static(const tsff_ctx* c, TableArgs& a) {
   a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;
   a.xi1_0 = c->xi1_0; a.xi1_h = c->xi1_h; a.xi2_0 = c->zt.x0; a.xi2_h = c->zt.h;
   a.omgs = c->omgs; a.costh = c->costh; a.wts = c->wts; a.jmul = c->jmul; a.xi2 = c->xi2; a.zt = c->zt;
+  a.tstat = c->tstat;
 }
 
 void bind_saved(const TableLayout& L, char* sv, TableArgs& a) {
@@ -414,7 +417,8 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   fill_static(c, a);
   bind_saved(L, static_cast<char*>(saved), a);
   a.params = params; a.fe = fe;
-  a.D = (float*)(w + L.w_D); a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
+  a.D = (float*)(w + L.w_D); a.AB = (float4*)(w + L.w_AB);
+  a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend); a.ratdf = (double*)(w + L.w_ratdf);
   a.modl = modl_out; a.ff = ff_out;
   {
@@ -425,11 +429,11 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   }
   {
     PvPolesArgs p;
-    p.D = a.D; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
+    p.Wt = a.D; p.AB = a.AB; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
     p.pnodes = a.ratdf; p.pnode_stride = kXi1N;
     p.z0 = c->xi1_0; p.h = c->xi1_h; p.nodes = c->pv_nodes; p.npad = c->pv_npad; p.P = kXi2N;
     p.outI = a.T; p.outdI = nullptr;
-    const size_t smem = (size_t)c->pv_npad * 4;
+    const size_t smem = (size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad);
     TSFF_SMEM_OPTIN((k_pv_poles<1, TSFF_PV_FP32>));
     TSFF_SMEM_OPTIN((k_pv_poles<2, TSFF_PV_FP32>));
     if (c->pv_precision == TSFF_PV_FP64) {
@@ -490,15 +494,10 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   TSFF_LAUNCH_OK("k_table_tbar");
   {
     PvNodesArgs n;
-    n.desc = a.desc; n.P = kXi2N; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.h = (float)c->xi1_h; n.pbar = a.Dbar;
-    const long long tiles4 = (c->pv_npad + 4 * kPvThreads - 1) / (4 * kPvThreads);
-    if ((long long)B * tiles4 >= 2LL * c->sm_count) {
-      n.ntiles = (int)tiles4;
-      k_pv_nodes<4><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
-    } else {
-      n.ntiles = (c->pv_npad + kPvThreads - 1) / kPvThreads;
-      k_pv_nodes<1><<<(unsigned)(B * n.ntiles), kPvThreads, 0, st>>>(n);
-    }
+    n.desc = a.desc; n.tstat = c->tstat; n.P = kXi2N; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.pbar = a.Dbar;
+    n.nsplit = pv_nodes_split(B, n.P, c->sm_count);
+    TSFF_SMEM_OPTIN(k_pv_nodes);
+    k_pv_nodes<<<(unsigned)(B * n.nsplit), kPvThreads, pv_nodes_smem(n.npad), st>>>(n);
     TSFF_LAUNCH_OK("k_pv_nodes");
   }
   {
