@@ -136,5 +136,10 @@ def test_direct_vjp_multi_angle_ff_bar():
     pb, fb = pb.cpu().numpy(), fb.cpu().numpy()
     for b in range(B):
         for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13, 15, 16, 17]:
-            assert abs(pb[b, k] - gp[b, k]) <= 1e-4 * max(abs(gp[b, k]), 1e-8 * np.abs(gp[b]).max()), (b, k, pb[b, k], gp[b, k])
+            scale = max(abs(gp[b, k]), 1e-8 * np.abs(gp[b]).max())
+            if k in (5, 6):
+                # d/d(ne_gradient), d/d(Te_gradient) = sum_g (dL/dne_g)(+-ne/200): with G = 2 the two gradient points cancel
+                # to first order (here 130:1), so the 1e-4 is taken relative to the size of the terms that cancel
+                scale = max(scale, abs(gp[b, 1 if k == 5 else 0]) * params[b, 1 if k == 5 else 0] / 200.0)
+            assert abs(pb[b, k] - gp[b, k]) <= 1e-4 * scale, (b, k, pb[b, k], gp[b, k])
         assert np.abs(fb[b] - gf[b]).max() / np.abs(gf[b]).max() < 1e-4, b

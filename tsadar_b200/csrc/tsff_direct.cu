@@ -280,15 +280,12 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
       atomicAdd(&a.accfe[b * a.V + i_f], (1.0 - t_f) * pb.fphi);
       atomicAdd(&a.accfe[b * a.V + i_f + 1], t_f * pb.fphi);
     }
-    if (dfe_bar != 0.0) {
-      atomicAdd(&a.accdf[b * a.V + i_f], (1.0 - t_f) * dfe_bar);
-      atomicAdd(&a.accdf[b * a.V + i_f + 1], t_f * dfe_bar);
-    }
     // d I / d p_i for the nodes next to the pole (and an end node inside its window), exactly (FP64); the rest is
     // k_pv_nodes' (far blocks + near-window series)
     int wb0;
     a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = pv_desc(q.xie, Ibar, a.v0, a.dv, a.nodes, a.npad, wb0);
-    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, wb0, a.accdf + b * a.V);
+    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, wb0, a.accdf + b * a.V, i_f, (1.0 - t_f) * dfe_bar, i_f + 1,
+                      t_f * dfe_bar);
     kin_backward(sL, omgs, cth, q, kb, Lb);
   }
   double vals[kLGDoubles];

@@ -217,7 +217,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
 #pragma unroll
   for (int m = 0; m < kTK; m++) L64[m] = 0.0;
   const float2 one = make_float2(1.f, 1.f), c2 = make_float2(1.f / 6.f, 1.f / 6.f), c4 = make_float2(1.f / 15.f, 1.f / 15.f);
-  const float lim = (float)kNearHalf + 0.5f;
+  const float lim = (float)kNearHalf + 0.5f, mid = (float)kMidHalf + 0.5f;
 
   for (int c0 = p_begin; c0 < p_end; c0 += kNodeChunk) {
     const int nc = min(kNodeChunk, p_end - c0);
@@ -284,16 +284,23 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       for (int k = klo; k < khi; k++) {
         const float4 d = ssort[k];
         const float u0 = fi0 + d.x, u1 = u0 + 1.f;   // i - n_p, exact
-        float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
-        // the masked zone |i - n_p| <= kNearHalf touches this block only if n_p is within kNearHalf of it (warp-uniform)
+        const float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
+        // this block comes within kMidHalf nodes of the pole only if n_p is within kMidHalf of it (warp-uniform test)
         const float nrel = -d.x - (float)(kTS * nb);
-        if (nrel >= -lim && nrel <= (float)(kTS - 1) + lim) {
-          x0 = fabsf(u0) > lim ? x0 : 0.f;
-          x1 = fabsf(u1) > lim ? x1 : 0.f;
+        if (nrel >= -mid && nrel <= (float)(kTS - 1) + mid) {
+          const float2 x = make_float2(fabsf(u0) > lim ? x0 : 0.f, fabsf(u1) > lim ? x1 : 0.f);
+          const float2 s2 = fmul2(x, x);
+          float2 pI = ffma2(make_float2(1.f / 66.f, 1.f / 66.f), s2, make_float2(1.f / 45.f, 1.f / 45.f));
+          pI = ffma2(pI, s2, make_float2(1.f / 28.f, 1.f / 28.f));
+          pI = ffma2(pI, s2, c4);
+          pI = ffma2(pI, s2, c2);
+          pI = ffma2(pI, s2, one);
+          acc = ffma2(fmul2(make_float2(d.z, d.z), x), pI, acc);
+        } else {
+          const float2 x = make_float2(x0, x1);
+          const float2 s2 = fmul2(x, x);
+          acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
         }
-        const float2 x = make_float2(x0, x1);
-        const float2 s2 = fmul2(x, x);
-        acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
         if (++cnt == 64) {
           acc64x += (double)acc.x;
           acc64y += (double)acc.y;
@@ -333,10 +340,11 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
 }
 
 // Exact (FP64) adjoint contributions of one pole: the kNearHalf nodes either side of it, and an end node when its
-// block lies in the pole's near window.  Atomically added to pnear[0..M].
+// block lies in the pole's near window.  Atomically added to pnear[0..M].  Two extra contributions (ei0, ev0),
+// (ei1, ev1) to the same array (the lerp adjoint of the direct mode, which lands on nodes next to the pole) ride on the
+// same atomics when they fall on a node of the exact zone; pass ev = 0 to skip.
 __device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, int wb0,
-                                                  double* pnear) {
-  if (Ibar == 0.0) return;
+                                                  double* pnear, int ei0 = 0, double ev0 = 0.0, int ei1 = 0, double ev1 = 0.0) {
   const int M = nodes - 1;
   double rn = rint((xi - z0) / h);
   if (!(rn >= 0.0)) rn = 0.0;
@@ -344,15 +352,21 @@ __device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double
   const int n = (int)rn;
   const int lo = max(1, n - kNearHalf), hi = min(M - 1, n + kNearHalf);
   const double ih = 1.0 / h;
-  if (lo <= hi) {
+  if (lo <= hi && Ibar != 0.0) {
     double pm = pv_phi(z0 + (double)(lo - 1) * h - xi), pc = pv_phi(z0 + (double)lo * h - xi);
     for (int i = lo; i <= hi; i++) {
       const double pp = pv_phi(z0 + (double)(i + 1) * h - xi);
-      atomicAdd(&pnear[i], Ibar * (pp - 2.0 * pc + pm) * ih);
+      double v = Ibar * (pp - 2.0 * pc + pm) * ih;
+      if (i == ei0) { v += ev0; ev0 = 0.0; }
+      if (i == ei1) { v += ev1; ev1 = 0.0; }
+      atomicAdd(&pnear[i], v);
       pm = pc;
       pc = pp;
     }
   }
+  if (ev0 != 0.0) atomicAdd(&pnear[ei0], ev0);
+  if (ev1 != 0.0) atomicAdd(&pnear[ei1], ev1);
+  if (Ibar == 0.0) return;
   if (wb0 == 0) {
     const double g0 = z0 - xi;
     atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log(fmax(fabs(g0), 1e-300))));

@@ -9,8 +9,8 @@
 //
 // the nodes are cut into blocks of kTS = 64.  For a pole whose nearest node n lies in block bn, the three blocks
 // wb0..wb0+2 (wb0 = clamp(bn-1, 0, NB-3)) are its NEAR WINDOW: their nodes are summed one by one (FP32 series
-// x(1 + x^2/6 + x^4/15) for |i-n| > kNearHalf, exact FP64 logs for the 2*kNearHalf+1 nodes around the pole and for an
-// end node inside the window).  Every other block is FAR and enters through a Laurent expansion about its centre c_b:
+// x(1 + x^2/6 + x^4/15) for |i-n| > kMidHalf = 8, six terms for kNearHalf = 3 < |i-n| <= 8, exact FP64 logs for the
+// 2*kNearHalf+1 nodes around the pole and for an end node inside the window).  Every other block is FAR and enters through a Laurent expansion about its centre c_b:
 //
 //     sum_{i in b} p_i W(g_i)  (+ end-node term)  =  sum_{m<K} A_{b,m} t^(m+1),       t = s h / (z_{c_b} - xi),  s = 32,
 //     A_{b,m} = (1/s) sum_j C(m,2j) / ((2j+1)(j+1)) s^(-2j) mu_{m-2j},               mu_k = sum_{i in b} p_i (-(i-c_b)/s)^k
@@ -190,15 +190,16 @@ TSFF_HD void tree_far(const float4* sAB, int NB, const TreePole (&tp)[R], double
 TSFF_HD void tree_near(const float* sW, const TreePole tp, double& accI, double& accJ) {
   const float4* w4 = reinterpret_cast<const float4*>(sW + kTS * tp.wb0);
   const float ub = (float)(kTS * tp.wb0) + tp.un;  // i0 - n, exact
-  const float2 one = f2(1.f, 1.f), c2 = f2(1.f / 6.f, 1.f / 6.f), c4 = f2(1.f / 15.f, 1.f / 15.f), d2 = f2(0.5f, 0.5f),
-               d4 = f2(1.f / 3.f, 1.f / 3.f);
-  const float lim = (float)kNearHalf + 0.5f;
+  const float2 one = f2(1.f, 1.f);
+  const float lim = (float)kNearHalf + 0.5f, mid = (float)kMidHalf + 0.5f;
   for (int q0 = 0; q0 < kTWin / 4; q0 += 8) {
-    // does this group of 32 nodes [ub + 4 q0, ub + 4 q0 + 31] touch the masked zone [-kNearHalf, kNearHalf]?
+    // does this group of 32 nodes [ub + 4 q0, ub + 4 q0 + 31] come within kMidHalf nodes of the pole?
     const float ulo = ub + (float)(4 * q0);
-    const bool touch = (ulo <= lim) && (ulo + 31.f >= -lim);
+    const bool touch = (ulo <= mid) && (ulo + 31.f >= -mid);
     float2 aI = f2(0.f, 0.f), aJ = f2(0.f, 0.f);
     if (!TSFF_WARP_ANY(touch)) {
+      // |i - n| > kMidHalf: W = x (1 + x^2/6 + x^4/15),  h dW/dxi = x^2 (1 + x^2/2 + x^4/3)
+      const float2 c2 = f2(1.f / 6.f, 1.f / 6.f), c4 = f2(1.f / 15.f, 1.f / 15.f), d2 = f2(0.5f, 0.5f), d4 = f2(1.f / 3.f, 1.f / 3.f);
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const float4 w = w4[q0 + q];
@@ -213,6 +214,7 @@ TSFF_HD void tree_near(const float* sW, const TreePole tp, double& accI, double&
         }
       }
     } else {
+      // next to the pole: six terms (x <= 1/3.5: the seventh is 3e-9), nodes with |i - n| <= kNearHalf left to FP64
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const float4 w = w4[q0 + q];
@@ -224,8 +226,19 @@ TSFF_HD void tree_near(const float* sW, const TreePole tp, double& accI, double&
           const float2 x = f2(x0, x1);
           const float2 s2 = fmul2(x, x);
           const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
-          aI = ffma2(fmul2(wv, x), ffma2(ffma2(s2, c4, c2), s2, one), aI);
-          aJ = ffma2(fmul2(wv, s2), ffma2(ffma2(s2, d4, d2), s2, one), aJ);
+          float2 pI = f2(1.f / 66.f, 1.f / 66.f), pJ = f2(1.f / 6.f, 1.f / 6.f);
+          pI = ffma2(pI, s2, f2(1.f / 45.f, 1.f / 45.f));
+          pJ = ffma2(pJ, s2, f2(0.2f, 0.2f));
+          pI = ffma2(pI, s2, f2(1.f / 28.f, 1.f / 28.f));
+          pJ = ffma2(pJ, s2, f2(0.25f, 0.25f));
+          pI = ffma2(pI, s2, f2(1.f / 15.f, 1.f / 15.f));
+          pJ = ffma2(pJ, s2, f2(1.f / 3.f, 1.f / 3.f));
+          pI = ffma2(pI, s2, f2(1.f / 6.f, 1.f / 6.f));
+          pJ = ffma2(pJ, s2, f2(0.5f, 0.5f));
+          pI = ffma2(pI, s2, one);
+          pJ = ffma2(pJ, s2, one);
+          aI = ffma2(fmul2(wv, x), pI, aI);
+          aJ = ffma2(fmul2(wv, s2), pJ, aJ);
         }
       }
     }
