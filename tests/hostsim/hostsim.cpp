@@ -161,43 +161,49 @@ int main() {
     printf("hermite checked\n");
   }
   // ---- 5. block-multipole PV evaluation (tsff_tree.cuh) vs the literal ratintn, several grid sizes
-  for (int N : {4096, 1024, 130, 37}) {
+  for (int N : {4096, 1024, 512, 130, 37}) {
     const double z0 = -6 + 6.0 / N, h = 12.0 / N;
     std::vector<double> f(N), z(N);
     for (int i = 0; i < N; i++) { z[i] = z0 + i * h; f[i] = -z[i] * exp(-0.5 * z[i] * z[i]) * 0.4 + 0.01 * sin(3 * z[i]); }
-    const int M = N - 2, npad = tree_npad(M + 1), NB = npad / kTS;
-    std::vector<double> cm(kTK * (kTK / 2));
-    for (int m = 0; m < kTK; m++) for (int j = 0; j < kTK / 2; j++) cm[m * (kTK / 2) + j] = tree_cm(m, j);
-    std::vector<float> W(npad, 0.f);
+    const int M = N - 2, npad = tree_npad(M + 1);
+    const TreeBlob tb = tree_blob(npad);
+    std::vector<double> ts(kTreeStaticDoubles);
+    for (int i = 0; i < kTreeStaticDoubles; i++) ts[i] = tree_static_entry(i, M);
+    std::vector<double> blob8(tb.bytes / 8 + 2, 0.0);   // 8-byte aligned storage
+    unsigned char* blob = reinterpret_cast<unsigned char*>(blob8.data());
+    float* W = reinterpret_cast<float*>(blob + tb.oW);
     for (int i = 1; i <= M - 1; i++) W[i] = (float)f[i];
-    std::vector<float4> AB(NB * kTK / 2);
     auto pget = [&](int i) { return f[i]; };
-    std::vector<double> qend(2 * kTK);
-    for (int m = 0; m < kTK; m++) { qend[m] = tree_q_end(m, -0.5 * (kTS - 1), false); qend[kTK + m] = tree_q_end(m, (double)(M % kTS) - 0.5 * (kTS - 1), true); }
-    for (int b = 0; b < NB; b++) {
-      double A[kTK]; tree_block_coeffs(pget, M, b, cm.data(), qend.data(), A);
-      for (int q = 0; q < kTK / 2; q++) AB[b * (kTK / 2) + q] = {(float)A[2 * q], (float)((2 * q + 1) * A[2 * q]), (float)A[2 * q + 1], (float)((2 * q + 2) * A[2 * q + 1])};
+    for (int lvl = 0; lvl < 2; lvl++) {
+      const int S = lvl ? kTS2 : kTS, nb = lvl ? tb.NB2 : tb.NB;
+      const double s = lvl ? kTs2 : kTs;
+      for (int b = 0; b < nb; b++) {
+        double mu[kTK], A[kTK];
+        tree_block_moments(pget, M, b, S, s, 0, 1, mu);
+        tree_coeffs_from_moments(pget, M, b, S, s, mu, ts.data() + (lvl ? kTsCM2 : kTsCM1), ts.data() + (lvl ? kTsQE2 : kTsQE1), A);
+        tree_pack(A, reinterpret_cast<float4*>(blob + (lvl ? tb.oAB2 : tb.oAB1)) + b * (kTK / 2),
+                  reinterpret_cast<double*>(blob + (lvl ? tb.oLD2 : tb.oLD1)) + 2 * b);
+      }
     }
     double maxe = 0, maxd = 0, scale = 0;
     std::vector<double> xis = {-7.3, -5.99, -5.2, -2.345678, -0.0117, 0.0, 0.4321, 1.0 + 1e-9, 3.3333, 5.2, 5.97, 6.8};
-    for (int k = 0; k < 40; k++) xis.push_back(-7.0 + 14.0 * (k + 0.37) / 40.0);
+    for (int k = 0; k < 60; k++) xis.push_back(-7.0 + 14.0 * (k + 0.37) / 60.0);
     for (double xi : xis) scale = std::max(scale, fabs(ratintn_literal(f, z, xi)));
     for (double xi : xis) {
       const double ref = ratintn_literal(f, z, xi);
-      TreePole tp[1] = {tree_pole(xi, z0, h, M, NB)};
-      double fI[1] = {0}, fJ[1] = {0}, nI_ = 0, nJ = 0, eI, eJ;
-      tree_far<1>(AB.data(), NB, tp, fI, fJ);
-      tree_near(W.data(), tp[0], nI_, nJ);
+      TreePole tp[1] = {tree_pole(xi, z0, h, M, npad)};
+      double fI[1] = {0}, fJ1[1] = {0}, fJ2[1] = {0}, eI, eJ;
+      tree_far<1>(blob, tb, tp, fI, fJ1, fJ2);
+      const TreeAcc na = tree_near(W, tp[0]);
       tree_near_exact(xi, z0, h, M, tp[0].wb0, pget, eI, eJ);
-      const double I = eI + nI_ + fI[0], dI = eJ + nJ / h + fJ[0] / (kTs * h);
+      const double I = eI + na.I + fI[0], dI = eJ + na.J / h + fJ1[0] / (kTs * h) + fJ2[0] / (kTs2 * h);
       const double e = 1e-6;
       const double fd = (ratintn_literal(f, z, xi + e) - ratintn_literal(f, z, xi - e)) / (2 * e);
       maxe = std::max(maxe, fabs(I - ref) / scale); maxd = std::max(maxd, fabs(dI - fd) / std::max(1.0, fabs(fd)));
-      if (fabs(I - ref) > 1e-7 * scale || fabs(dI - fd) > 2e-4 * std::max(1.0, fabs(fd))) {
+      if (fabs(I - ref) > 1.5e-7 * scale || fabs(dI - fd) > 2e-4 * std::max(1.0, fabs(fd))) {
         printf("FAIL tree N=%d xi=%g ref=%.12e I=%.12e dI=%.8e fd=%.8e\n", N, xi, ref, I, dI, fd); fails++;
       }
     }
-    // adjoint weights: dI/dp_i from the spreading formulas vs the forward coefficients (linearity in p)
     printf("tree N=%d: max |I-ref|/scale = %.3e, max rel dI err = %.3e\n", N, maxe, maxd);
   }
   printf(fails ? "HOSTSIM FAILED (%d)\n" : "HOSTSIM OK\n", fails);

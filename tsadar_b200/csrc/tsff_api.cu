@@ -64,7 +64,7 @@ namespace {
 constexpr int kThreads = 256;
 
 struct PvLayout {
-  size_t D, AB, tstat, D64, pend, desc, Dbar, pendbar, tI, tdI, bytes;
+  size_t D, tstat, D64, pend, desc, Dbar, pendbar, tI, tdI, bytes;
   int nodes, npad;
 };
 PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
@@ -72,8 +72,7 @@ PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
   L.nodes = (int)N - 1;
   L.npad = tree_npad(L.nodes);
   size_t o = 0;
-  L.D = o; o += align_up((size_t)B * L.npad * 4);
-  L.AB = o; o += align_up((size_t)B * tree_ab_bytes(L.npad));
+  L.D = o; o += align_up((size_t)B * tree_blob(L.npad).bytes);
   L.tstat = o; o += align_up((size_t)kTreeStaticDoubles * 8);
   L.D64 = o; o += align_up((size_t)B * L.npad * 8);
   L.pend = o; o += align_up((size_t)B * 2 * 8);
@@ -86,12 +85,12 @@ PvLayout pv_layout(int64_t B, int64_t N, int64_t P) {
   return L;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, double h, int npad, float* D, float4* AB,
+__global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, double h, int npad, unsigned char* blob,
                                                       const double* tstat, double* D64, double* pend) {
   const long long b = blockIdx.x;
   const double* fb = f + b * N;
   const int M = N - 2;
-  tree_prep_cta([fb](int i) { return fb[i]; }, M, npad, D + b * npad, AB + b * ((npad / kTS) * (kTK / 2)), tstat);
+  tree_prep_cta([fb](int i) { return fb[i]; }, M, npad, blob + b * tree_blob(npad).bytes, tstat);
   for (int i = threadIdx.x; i < npad; i += kThreads) D64[b * npad + i] = pv_weight(fb, M, h, i);  // FP64 validation path
   if (threadIdx.x == 0) {
     pend[2 * b] = fb[0];
@@ -124,12 +123,12 @@ __global__ void k_mul(const double* x, const double* y, long long n, double* out
 int launch_poles(const PvLayout& L, int64_t B, int64_t N, int64_t P, const double* f, char* w, double z0, double h, const double* pole, double* out,
                  double* dout, int prec, cudaStream_t st) {
   PvPolesArgs p;
-  p.Wt = (float*)(w + L.D); p.AB = (float4*)(w + L.AB); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
+  p.blob = (unsigned char*)(w + L.D); p.D64 = (double*)(w + L.D64); p.pend = (double*)(w + L.pend);
   p.pnodes = f; p.pnode_stride = N;
   p.poles = pole; p.pole_bstride = P; p.z0 = z0; p.h = h; p.nodes = L.nodes; p.npad = L.npad; p.P = (int)P;
   p.outI = out; p.outdI = dout;
   p.ntiles = (int)((P + kPvThreads - 1) / kPvThreads);
-  const size_t smem = (size_t)L.npad * 4 + tree_ab_bytes(L.npad);
+  const size_t smem = (size_t)tree_blob(L.npad).bytes;
   if (prec == TSFF_PV_FP64) {
     k_pv_poles<1, TSFF_PV_FP64><<<(unsigned)(B * p.ntiles), kPvThreads, 0, st>>>(p);
   } else {
@@ -154,7 +153,7 @@ extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);
   k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
-  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (float4*)(w + L.AB), (double*)(w + L.tstat),
+  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
                                             (double*)(w + L.D64), (double*)(w + L.pend));
   TSFF_LAUNCH_OK("k_pv_prep");
   return launch_poles(L, B, N, P, f, w, z0, h, pole, out, dout_dpole, pv_precision, st);
@@ -179,7 +178,7 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, f_bar);
   TSFF_LAUNCH_OK("k_pv_bwd_finish");
   if (pole_bar) {
-    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (float*)(w + L.D), (float4*)(w + L.AB), (double*)(w + L.tstat),
+    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
                                               (double*)(w + L.D64), (double*)(w + L.pend));
     TSFF_LAUNCH_OK("k_pv_prep");
     int rc = launch_poles(L, B, N, P, f, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);

@@ -10,6 +10,8 @@
 //   k_direct_bwd_poles  FP64 reverse of the assembly per pole; emits Ibar descriptors, lerp scatter, LG cotangents
 //   k_pv_nodes          (tsff_pv_kernels.cuh) thread-owns-node adjoint PV sweep (MUFU-bound)
 //   k_direct_bwd_finish per lineout: Dbar -> df_bar -> fe_bar; LG cotangents -> params_bar
+#include <stdlib.h>
+
 #include "tsff_pv_kernels.cuh"
 
 using namespace tsff;
@@ -28,7 +30,7 @@ __device__ __forceinline__ double grad_at(const T* f, int V, double dv, int i) {
 
 struct DirectLayout {  // byte offsets inside `saved` and `ws` for a batch of B lineouts
   size_t s_lg, s_I, s_dI, saved_bytes;
-  size_t w_D, w_AB, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
+  size_t w_D, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
       ws_bytes;
 };
 
@@ -41,8 +43,7 @@ DirectLayout direct_layout(const tsff_ctx* c, int64_t B) {
   L.s_dI = o; o += align_up((size_t)B * P * 8);
   L.saved_bytes = o;
   o = 0;
-  L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
-  L.w_AB = o; o += align_up((size_t)B * tree_ab_bytes(c->pv_npad));
+  L.w_D = o; o += align_up((size_t)B * tree_blob(c->pv_npad).bytes);
   L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
   L.w_pend = o; o += align_up((size_t)B * 2 * 8);
   L.w_ff = o; o += align_up((size_t)B * P * 8);
@@ -70,8 +71,7 @@ struct DirectArgs {
   double* lg;        // [B][G][kLGDoubles]
   double* sI;        // [B][P]
   double* sdI;       // [B][P]
-  float* D;          // [B][npad]  FP32 node weights p_i (interior nodes)
-  float4* AB;        // [B][NB*kTK/2] block expansion coefficients (tsff_tree.cuh)
+  unsigned char* D;  // [B][blob bytes]  per-lineout tree blob: FP32 node weights + block expansion coefficients
   const double* tstat;
   double* D64;       // [B][npad] or null
   double* pend;      // [B][2]
@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
   {
     const int V = a.V;
     const double dv = a.dv;
-    tree_prep_cta([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * a.npad,
-                  a.AB + b * ((a.npad / kTS) * (kTK / 2)), a.tstat);
+    tree_prep_cta([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat);
   }
   if (a.D64) {  // log-form weights for the FP64 validation path
     for (int i = threadIdx.x; i < a.npad; i += kThreads) {
@@ -136,23 +135,58 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
   }
 }
 
+// FP64 tail of one pole: exact near nodes, ion susceptibility, lerp of f and f', assembly; stores P, I, dI/dxi.
+// Not inlined: shared by the R poles of a thread (the kernel would otherwise carry R copies of the FP64 log code).
+template <typename T, int PREC>
+__device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, const T* fe, long long b, int g, int idx, int wb0,
+                                          double farI, double farJ, double g0d) {
+  const int j = idx / a.A, ia = idx % a.A;
+  const int M = a.nodes - 1;
+  const double omgs = a.omgs[j];
+  Kin q;
+  kin_forward(sL, omgs, a.costh[ia], q);
+  IonOut io;
+  ion_forward(sL, a.nI, a.zt, q, io);
+  double I, dI;
+  if (PREC == TSFF_PV_FP32) {
+    const int V = a.V;
+    const double dv = a.dv;
+    tree_near_exact(q.xie, a.v0, dv, M, wb0, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
+    I += farI;
+    dI += farJ;
+  } else {
+    const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
+    pv_finish(farI, farJ, p0, pM, g0d, g0d + (double)(a.nodes - 1) * a.dv, I, dI);
+  }
+  int i_f; double t_f, sl_f;
+  const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);   // form_factor.py:376
+  const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
+  const double dfe = d0 + t_f * (d1 - d0);  // form_factor.py:377 (clamped: t_f in {0,1} picks the edge value)
+  const double chiEr = -q.ikl2 * I;          // form_factor.py:385-386
+  const double chiEi = kPi * q.ikl2 * dfe;   // form_factor.py:381
+  Asm s;
+  const double P = assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
+  const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
+  a.ff[pidx] = P;
+  a.sI[pidx] = I;
+  a.sdI[pidx] = dI;
+}
+
 // ---- forward ------------------------------------------------------------------------------------------------
 // grid.x = B * G * ntiles; a tile covers kThreads*R consecutive (j,a) pairs of one (lineout, gradient point).
 template <int R, typename T, int PREC, int MINB = 3>
-__global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const DirectArgs a) {
+__global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_constant__ DirectArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ LG sL;
-  float* sW = reinterpret_cast<float*>(smem_raw);
-  float4* sAB = reinterpret_cast<float4*>(smem_raw + (size_t)a.npad * 4);
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
   const long long b = bg / a.G;
-  const int NB = a.npad / kTS, M = a.nodes - 1;
+  const int M = a.nodes - 1;
+  const TreeBlob tb = tree_blob(a.npad);
   if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
-  if (PREC == TSFF_PV_FP32)
-    stage_bulk2(sW, a.D + b * a.npad, (uint32_t)a.npad * 4u, sAB, a.AB + b * (NB * (kTK / 2)), (uint32_t)tree_ab_bytes(a.npad), &bar);
+  if (PREC == TSFF_PV_FP32) stage_blob(smem_raw, a.D + b * tb.bytes, (uint32_t)tb.bytes, &bar);
   else __syncthreads();
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int WA = a.W * a.A;
@@ -165,53 +199,34 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const DirectArgs 
     if (idx >= WA) idx = WA - 1;
     Kin q;
     kin_forward(sL, a.omgs[idx / a.A], a.costh[idx % a.A], q);
-    tp[r] = tree_pole(q.xie, a.v0, a.dv, M, NB);
+    tp[r] = tree_pole(q.xie, a.v0, a.dv, M, a.npad);
     g0d[r] = a.v0 - q.xie;
   }
-  double accI[R], accJ[R], nrI[R], nrJ[R];
+  double accI[R], accJ[R], accJ2[R], nrI[R], nrJ[R];
   if (PREC == TSFF_PV_FP32) {
 #pragma unroll
-    for (int r = 0; r < R; r++) accI[r] = accJ[r] = nrI[r] = nrJ[r] = 0.0;
-    tree_far<R>(sAB, NB, tp, accI, accJ);
+    for (int r = 0; r < R; r++) accI[r] = accJ[r] = accJ2[r] = nrI[r] = nrJ[r] = 0.0;
+    tree_far<R>(smem_raw, tb, tp, accI, accJ, accJ2);
 #pragma unroll
-    for (int r = 0; r < R; r++) tree_near(sW, tp[r], nrI[r], nrJ[r]);
+    for (int r = 0; r < R; r++) {
+      const TreeAcc na = tree_near(reinterpret_cast<const float*>(smem_raw + tb.oW), tp[r]);
+      nrI[r] = na.I;
+      nrJ[r] = na.J;
+    }
   } else {
     pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.dv, g0d, accI, accJ);
   }
 
-  const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int idx = (tile * kThreads + threadIdx.x) * R + r;
     if (idx >= WA) continue;
-    const int j = idx / a.A, ia = idx % a.A;
-    const double omgs = a.omgs[j];
-    Kin q;
-    kin_forward(sL, omgs, a.costh[ia], q);
-    IonOut io;
-    ion_forward(sL, a.nI, a.zt, q, io);
-    double I, dI;
+    double farI = accI[r], farJ = accJ[r];
     if (PREC == TSFF_PV_FP32) {
-      const int V = a.V;
-      const double dv = a.dv;
-      tree_near_exact(q.xie, a.v0, dv, M, tp[r].wb0, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
-      I += accI[r] + nrI[r];
-      dI += accJ[r] / (kTs * dv) + nrJ[r] / dv;
-    } else {
-      pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.dv, I, dI);
+      farI += nrI[r];
+      farJ = accJ[r] / (kTs * a.dv) + accJ2[r] / (kTs2 * a.dv) + nrJ[r] / a.dv;
     }
-    int i_f; double t_f, sl_f;
-    const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);   // form_factor.py:376
-    const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
-    const double dfe = d0 + t_f * (d1 - d0);  // form_factor.py:377 (clamped: t_f in {0,1} picks the edge value)
-    const double chiEr = -q.ikl2 * I;          // form_factor.py:385-386
-    const double chiEi = kPi * q.ikl2 * dfe;   // form_factor.py:381
-    Asm s;
-    const double P = assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
-    const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
-    a.ff[pidx] = P;
-    a.sI[pidx] = I;
-    a.sdI[pidx] = dI;
+    direct_point<T, PREC>(a, sL, fe, b, g, idx, tp[r].wb0, farI, farJ, g0d[r]);
   }
 }
 
@@ -344,22 +359,25 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   fill_static(c, a);
   a.params = params; a.fe = fe;
   a.lg = (double*)(sv + L.s_lg); a.sI = (double*)(sv + L.s_I); a.sdI = (double*)(sv + L.s_dI);
-  a.D = (float*)(w + L.w_D); a.AB = (float4*)(w + L.w_AB);
+  a.D = (unsigned char*)(w + L.w_D);
   a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend);
   a.ff = ff_out ? ff_out : (double*)(w + L.w_ff);
   k_direct_prep<T><<<(unsigned)B, kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_prep");
   const int WA = c->W * c->A;
-  const size_t smem = (size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad);
-  // poles per thread: 2 while the grid still fills the device, else 1
-  const long long tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
-  const bool useR2 = (long long)B * c->G * tiles2 >= 2LL * c->sm_count;
+  const size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
+  // poles per thread: 4 (four independent Horner chains per thread) while the grid still fills the device, else 2 / 1
+  const long long tiles4 = (WA + 4 * kThreads - 1) / (4 * kThreads), tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
   if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
   if (c->pv_precision == TSFF_PV_FP64) {
     a.ntiles = (WA + kThreads - 1) / kThreads;
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
-  } else if (useR2) {
+  } else if ((long long)B * c->G * tiles4 >= 2LL * c->sm_count && !getenv("TSFF_FWD_R2")) {
+    a.ntiles = (int)tiles4;
+    TSFF_SMEM_OPTIN((k_direct_fwd<4, T, TSFF_PV_FP32, 2>));
+    k_direct_fwd<4, T, TSFF_PV_FP32, 2><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
+  } else if ((long long)B * c->G * tiles2 >= 2LL * c->sm_count) {
     a.ntiles = (int)tiles2;
     TSFF_SMEM_OPTIN((k_direct_fwd<2, T, TSFF_PV_FP32, 3>));
     k_direct_fwd<2, T, TSFF_PV_FP32, 3><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);
@@ -423,7 +441,7 @@ size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B
 
 int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
                void* saved, void* ws, cudaStream_t st) {
-  if ((size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
                               : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
 }

@@ -82,7 +82,7 @@ inline float2 ffma2(float2 a, float2 b, float2 c) { return make_f2(fmaf(a.x, b.x
 inline float2 fmul2(float2 a, float2 b) { return make_f2(a.x * b.x, a.y * b.y); }
 #endif
 
-TSFF_HD double pv_phi(double g) { return g * log(fmax(fabs(g), 1e-300)); }
+TSFF_HD double pv_phi(double g) { return g * log_abs(g); }
 
 // FP64 validation path ("exact" mode): log form  I = sum_i D_i g_i ln|g_i| + endpoint terms, D = second difference
 // of p / h (pv_weight), log2 in double.
@@ -106,7 +106,7 @@ TSFF_HD void pv_accumulate_f64(const double* D, int nnodes, double h, const doub
 // Endpoint terms and final values (FP64, once per pole).  g0 = z_0 - xi, gM = z_M - xi.
 TSFF_HD void pv_finish(double accI, double accJ, double p0, double pM, double g0, double gM, double& I,
                        double& dIdxi) {
-  double l0 = log(fmax(fabs(g0), 1e-300)), lM = log(fmax(fabs(gM), 1e-300));
+  double l0 = log_abs(g0), lM = log_abs(gM);
   I = (pM - p0) + pM * lM - p0 * l0 + kLn2 * accI;
   dIdxi = -pM / gM + p0 / g0 - kLn2 * accJ;
 }

@@ -1,12 +1,13 @@
 // tsff_pv_kernels.cuh -- the principal-value sweeps shared by every mode (block-multipole form, tsff_tree.cuh).
 //
-//   tree_prep_cta : per lineout: FP32 node weights + the K Laurent coefficients of every 64-node block
+//   tree_prep_cta : per lineout: FP32 node weights + the Laurent coefficients of every 64- and 256-node block
 //   k_pv_poles    : thread-owns-pole forward sweep   I(xi_p), dI/dxi_p
 //   k_pv_nodes    : adjoint sweep  pbar_i = sum_p Ibar_p dI_p/dp_i  (far: block-owner gathers local coefficients over
 //                   the poles, near: node-owner loops over the poles whose window covers its block)
 //
 // Bound: instruction issue (FP32 FMA pipe + XU side by side); no HBM traffic to speak of.
-// Shared memory: node weights (<= 16 KB at 4096 nodes) + block coefficients (6 KB) staged by TMA bulk copies.
+// Shared memory: the per-lineout blob (node weights 16 KB + block coefficients 10 KB at 4096 nodes) staged by TMA
+// bulk copies.
 #pragma once
 #include "tsff_common.cuh"
 #include "tsff_tree.cuh"
@@ -15,67 +16,65 @@ namespace tsff {
 
 constexpr int kPvThreads = 256;
 
-// bytes of the per-lineout coefficient array  [NB][kTK] x (A_m, (m+1) A_m)
-TSFF_HD size_t tree_ab_bytes(int npad) { return (size_t)(npad / kTS) * kTK * 8; }
-
 #if defined(__CUDACC__)
-// Two bulk copies completed on one mbarrier.  Called by all threads; one use per kernel (parity 0).
-__device__ __forceinline__ void stage_bulk2(void* d0, const void* s0, uint32_t n0, void* d1, const void* s1, uint32_t n1,
-                                            uint64_t* bar) {
+// One bulk copy completed on an mbarrier, in pieces of at most 32 KB.  Called by all threads; one use per kernel.
+__device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, n0 + n1);
-    bulk_g2s(d0, s0, n0, bar);
-    bulk_g2s(d1, s1, n1, bar);
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u)
+      bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, min(32768u, bytes - o), bar);
   }
   mbar_wait(bar, 0);
 }
 
-// Static tables of the expansion (depend only on the node count): q_m(e) for the kTS in-block offsets, the two end-node
-// rows (node 0, node M), and the cm matrix.  Built once per context / call by k_tree_static.
-constexpr int kTreeStaticDoubles = (kTS + 2) * kTK + kTK * (kTK / 2);
+// Static tables of the expansion (tree_static_entry): built once per context / call.
 static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) {
-  for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) {
-    const double c = 0.5 * (double)(kTS - 1);
-    double v;
-    if (i < (kTS + 2) * kTK) {
-      const int k = i / kTK, m = i % kTK;
-      if (k < kTS) v = tree_q(m, (double)k - c);
-      else if (k == kTS) v = tree_q_end(m, 0.0 - c, false);
-      else v = tree_q_end(m, (double)(M % kTS) - c, true);
-    } else {
-      const int k = i - (kTS + 2) * kTK;
-      v = tree_cm(k / (kTK / 2), k % (kTK / 2));
-    }
-    out[i] = v;
-  }
+  for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) out[i] = tree_static_entry(i, M);
 }
 
-// Per-lineout preparation, executed by one CTA.  pget(i) -> p_i (FP64) for 0 <= i <= M.
-//   Wt [npad]  FP32 weights of the interior nodes 1..M-1 (0 elsewhere)
-//   AB [NB*kTK/2] float4 = (A_m, (m+1) A_m, A_{m+1}, (m+2) A_{m+1})
-// tstat: the k_tree_static table (global).
+// Per-lineout preparation, executed by one CTA (any block size that is a multiple of 32).  pget(i) -> p_i (FP64).
+// Writes the lineout's blob (tree_blob layout) to global memory: weights, packed coefficients of both levels, leading
+// coefficients.  A warp owns one block at a time: the lanes split its nodes, the moments are summed by shuffles, lane 0
+// turns them into coefficients.
 template <typename PGet>
-__device__ __forceinline__ void tree_prep_cta(PGet pget, int M, int npad, float* Wt, float4* AB, const double* tstat) {
+__device__ __forceinline__ void tree_prep_cta(PGet pget, int M, int npad, unsigned char* blob, const double* tstat) {
+  const TreeBlob tb = tree_blob(npad);
+  float* Wt = reinterpret_cast<float*>(blob + tb.oW);
   for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)pget(i) : 0.f;
-  const double* cm = tstat + (kTS + 2) * kTK;
-  const int NB = npad / kTS;
-  for (int b = threadIdx.x; b < NB; b += blockDim.x) {
-    double A[kTK];
-    tree_block_coeffs(pget, M, b, cm, tstat + kTS * kTK, A);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int item = wid; item < tb.NB + tb.NB2; item += nw) {
+    const bool lvl2 = item >= tb.NB;
+    const int b = lvl2 ? item - tb.NB : item;
+    const int S = lvl2 ? kTS2 : kTS;
+    const double s = lvl2 ? kTs2 : kTs;
+    double mu[kTK];
+    tree_block_moments(pget, M, b, S, s, lane, 32, mu);
 #pragma unroll
-    for (int q = 0; q < kTK / 2; q++)
-      AB[b * (kTK / 2) + q] = make_float4((float)A[2 * q], (float)((double)(2 * q + 1) * A[2 * q]), (float)A[2 * q + 1],
-                                          (float)((double)(2 * q + 2) * A[2 * q + 1]));
+    for (int k = 0; k < kTK; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mu[k] += __shfl_xor_sync(0xffffffffu, mu[k], o);
+    }
+    if (lane == 0) {
+      double A[kTK], ld[2];
+      float4 ab[kTK / 2];
+      tree_coeffs_from_moments(pget, M, b, S, s, mu, tstat + (lvl2 ? kTsCM2 : kTsCM1), tstat + (lvl2 ? kTsQE2 : kTsQE1), A);
+      tree_pack(A, ab, ld);
+      float4* dst = reinterpret_cast<float4*>(blob + (lvl2 ? tb.oAB2 : tb.oAB1)) + b * (kTK / 2);
+#pragma unroll
+      for (int q = 0; q < kTK / 2; q++) dst[q] = ab[q];
+      double* dl = reinterpret_cast<double*>(blob + (lvl2 ? tb.oLD2 : tb.oLD1)) + 2 * b;
+      dl[0] = ld[0];
+      dl[1] = ld[1];
+    }
   }
 }
 #endif
 
 struct PvPolesArgs {
-  const float* Wt;       // [B][npad] FP32 node weights
-  const float4* AB;      // [B][NB*kTK/2] block coefficients
-  const double* D64;     // [B][npad64] log-form weights D_i (FP64 validation path) or nullptr
+  const unsigned char* blob;  // [B][blob_bytes]  per-lineout tree blob (tree_prep_cta)
+  const double* D64;     // [B][npad] log-form weights D_i (FP64 validation path) or nullptr
   const double* pend;    // [B][2]   (p_0, p_M)   (FP64 validation path)
   const double* pnodes;  // node values p_i (FP64), row b at pnodes + b*pnode_stride
   long long pnode_stride;
@@ -92,14 +91,11 @@ template <int R, int PREC>
 __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  float* sW = reinterpret_cast<float*>(smem_raw);
-  float4* sAB = reinterpret_cast<float4*>(smem_raw + (size_t)a.npad * 4);
   const long long b = blockIdx.x / a.ntiles;
   const int tile = blockIdx.x % a.ntiles;
-  const int NB = a.npad / kTS, M = a.nodes - 1;
-  if (PREC == TSFF_PV_FP32)
-    stage_bulk2(sW, a.Wt + b * a.npad, (uint32_t)a.npad * 4u, sAB, a.AB + b * (NB * (kTK / 2)), (uint32_t)tree_ab_bytes(a.npad),
-                &bar);
+  const int M = a.nodes - 1;
+  const TreeBlob tb = tree_blob(a.npad);
+  if (PREC == TSFF_PV_FP32) stage_blob(smem_raw, a.blob + b * tb.bytes, (uint32_t)tb.bytes, &bar);
 
   const double* poles = a.poles + b * a.pole_bstride;
   double xi[R];
@@ -109,16 +105,20 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
   for (int r = 0; r < R; r++) {
     int p = (tile * kPvThreads + threadIdx.x) * R + r;
     xi[r] = poles[p < a.P ? p : a.P - 1];
-    tp[r] = tree_pole(xi[r], a.z0, a.h, M, NB);
+    tp[r] = tree_pole(xi[r], a.z0, a.h, M, a.npad);
     g0d[r] = a.z0 - xi[r];
   }
-  double accI[R], accJ[R], nrI[R], nrJ[R];
+  double accI[R], accJ[R], accJ2[R], nrI[R], nrJ[R];
   if (PREC == TSFF_PV_FP32) {
 #pragma unroll
-    for (int r = 0; r < R; r++) accI[r] = accJ[r] = nrI[r] = nrJ[r] = 0.0;
-    tree_far<R>(sAB, NB, tp, accI, accJ);
+    for (int r = 0; r < R; r++) accI[r] = accJ[r] = accJ2[r] = nrI[r] = nrJ[r] = 0.0;
+    tree_far<R>(smem_raw, tb, tp, accI, accJ, accJ2);
 #pragma unroll
-    for (int r = 0; r < R; r++) tree_near(sW, tp[r], nrI[r], nrJ[r]);
+    for (int r = 0; r < R; r++) {
+      const TreeAcc na = tree_near(reinterpret_cast<const float*>(smem_raw + tb.oW), tp[r]);
+      nrI[r] = na.I;
+      nrJ[r] = na.J;
+    }
   } else {
     pv_accumulate_f64<R, true>(a.D64 + b * a.npad, a.nodes, a.h, g0d, accI, accJ);
   }
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
         const double* pn = a.pnodes + b * a.pnode_stride;
         tree_near_exact(xi[r], a.z0, a.h, M, tp[r].wb0, [pn](int i) { return pn[i]; }, I, dI);
         I += accI[r] + nrI[r];
-        dI += accJ[r] / (kTs * a.h) + nrJ[r] / a.h;
+        dI += accJ[r] / (kTs * a.h) + accJ2[r] / (kTs2 * a.h) + nrJ[r] / a.h;
       } else {
         const double p0 = a.pend[2 * b], pM = a.pend[2 * b + 1];
         pv_finish(accI[r], accJ[r], p0, pM, g0d[r], g0d[r] + (double)(a.nodes - 1) * a.h, I, dI);
@@ -156,7 +156,7 @@ constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per block
 
 inline size_t pv_nodes_smem(int npad) {
   const int NB = npad / kTS;
-  return (size_t)kNodeChunk * 16 * 2 + (size_t)npad * 8 + (size_t)NB * kTK * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
+  return (size_t)kNodeChunk * 16 * 2 + (size_t)npad * 8 + (size_t)NB * kTKA * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
 }
 
 // pole splits per lineout: 1 when the batch alone fills the device, else enough CTAs for two per SM (each split
@@ -195,8 +195,8 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   float4* sraw = reinterpret_cast<float4*>(smem_raw);
   float4* ssort = sraw + kNodeChunk;
   double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad]
-  double* sL = spbar + a.npad;                                         // [NB][kTK]
-  int* shist = reinterpret_cast<int*>(sL + NB * kTK);                  // [NB + 1]
+  double* sL = spbar + a.npad;                                         // [NB][kTKA]
+  int* shist = reinterpret_cast<int*>(sL + NB * kTKA);                  // [NB + 1]
   int* scur = shist + NB + 1;                                          // [NB + 1]
   const long long b = blockIdx.x / a.nsplit;
   const int split = blockIdx.x % a.nsplit;
@@ -206,16 +206,16 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   for (int i = threadIdx.x; i < a.npad; i += kPvThreads) spbar[i] = 0.0;
-  for (int i = threadIdx.x; i < NB * kTK; i += kPvThreads) sL[i] = 0.0;
+  for (int i = threadIdx.x; i < NB * kTKA; i += kPvThreads) sL[i] = 0.0;
   // far-phase thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
   int NBP = 1;
   while (NBP < NB) NBP <<= 1;
   const int Q = kPvThreads / NBP;
   const int fb = threadIdx.x % NBP, fq = threadIdx.x / NBP;
   const float cb = (float)(2 * fb) + (float)(0.5 * (kTS - 1) / kTs);
-  double L64[kTK];
+  double L64[kTKA];
 #pragma unroll
-  for (int m = 0; m < kTK; m++) L64[m] = 0.0;
+  for (int m = 0; m < kTKA; m++) L64[m] = 0.0;
   const float2 one = make_float2(1.f, 1.f), c2 = make_float2(1.f / 6.f, 1.f / 6.f), c4 = make_float2(1.f / 15.f, 1.f / 15.f);
   const float lim = (float)kNearHalf + 0.5f, mid = (float)kMidHalf + 0.5f;
 
@@ -227,9 +227,9 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
     __syncthreads();
     // ---- far
     if (fb < NB) {
-      float2 Lp[kTK];
+      float2 Lp[kTKA];
 #pragma unroll
-      for (int m = 0; m < kTK; m++) Lp[m] = make_float2(0.f, 0.f);
+      for (int m = 0; m < kTKA; m++) Lp[m] = make_float2(0.f, 0.f);
       for (int k = fq; k < nc; k += 2 * Q) {
         const float4 d0 = sraw[k];
         const bool has1 = (k + Q) < nc;
@@ -241,13 +241,13 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
         const float2 t = make_float2(far0 ? rcp_approx(g0) : 0.f, far1 ? rcp_approx(g1) : 0.f);
         float2 pw = fmul2(make_float2(d0.z, d1.z), t);
 #pragma unroll
-        for (int m = 0; m < kTK; m++) {
+        for (int m = 0; m < kTKA; m++) {
           Lp[m] = fadd2(Lp[m], pw);
           pw = fmul2(pw, t);
         }
       }
 #pragma unroll
-      for (int m = 0; m < kTK; m++) L64[m] += (double)Lp[m].x + (double)Lp[m].y;
+      for (int m = 0; m < kTKA; m++) L64[m] += (double)Lp[m].x + (double)Lp[m].y;
     }
     // ---- counting sort by wb0
     for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[__float_as_int(sraw[k].w) + 1], 1);
@@ -314,25 +314,25 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   }
   if (fb < NB) {
 #pragma unroll
-    for (int m = 0; m < kTK; m++) atomicAdd(&sL[fb * kTK + m], L64[m]);
+    for (int m = 0; m < kTKA; m++) atomicAdd(&sL[fb * kTKA + m], L64[m]);
   }
   __syncthreads();
   // ---- spread the local coefficients to the nodes and write out
   double* out = a.pbar + b * a.npad;
-  const double* q = a.tstat;
+  const double* q = a.tstat + kTsQA;
   for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
     double v = 0.0;
     const int nb = i / kTS, k = i % kTS;
     if (i >= 1 && i <= M - 1) {
       v = spbar[i];
 #pragma unroll
-      for (int m = 0; m < kTK; m++) v += sL[nb * kTK + m] * q[k * kTK + m];
+      for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[k * kTKA + m];
     } else if (i == 0) {
 #pragma unroll
-      for (int m = 0; m < kTK; m++) v += sL[m] * q[kTS * kTK + m];
+      for (int m = 0; m < kTKA; m++) v += sL[m] * q[kTS * kTKA + m];
     } else if (i == M) {
 #pragma unroll
-      for (int m = 0; m < kTK; m++) v += sL[nb * kTK + m] * q[(kTS + 1) * kTK + m];
+      for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m];
     }
     if (a.nsplit == 1) out[i] = v;
     else if (v != 0.0) atomicAdd(&out[i], v);
@@ -369,17 +369,17 @@ __device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double
   if (Ibar == 0.0) return;
   if (wb0 == 0) {
     const double g0 = z0 - xi;
-    atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log(fmax(fabs(g0), 1e-300))));
+    atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log_abs(g0)));
   }
   if ((unsigned)(M / kTS - wb0) <= 2u) {
     const double gM = z0 + (double)M * h - xi;
-    atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log(fmax(fabs(gM), 1e-300))));
+    atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log_abs(gM)));
   }
 }
 
 // descriptor of one pole for k_pv_nodes
 __device__ __forceinline__ float4 pv_desc(double xi, double Ibar, double z0, double h, int nodes, int npad, int& wb0) {
-  const TreePole t = tree_pole(xi, z0, h, nodes - 1, npad / kTS);
+  const TreePole t = tree_pole(xi, z0, h, nodes - 1, npad);
   wb0 = t.wb0;
   return make_float4(t.un, t.ndh, (float)Ibar, __int_as_float(t.wb0));
 }

@@ -24,7 +24,7 @@ constexpr int kWarps = kThreads / 32;
 
 struct TableLayout {
   size_t s_lg, s_lnf, s_slope, s_ratmod, s_T, saved_bytes;
-  size_t w_D, w_AB, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
+  size_t w_D, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
       ws_bytes;
 };
 
@@ -38,8 +38,7 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
   L.s_T = o; o += align_up((size_t)B * kXi2N * 8);
   L.saved_bytes = o;
   o = 0;
-  L.w_D = o; o += align_up((size_t)B * c->pv_npad * 4);
-  L.w_AB = o; o += align_up((size_t)B * tree_ab_bytes(c->pv_npad));
+  L.w_D = o; o += align_up((size_t)B * tree_blob(c->pv_npad).bytes);
   L.w_D64 = o; o += align_up(c->pv_precision == TSFF_PV_FP64 ? (size_t)B * c->pv_npad * 8 : 0);
   L.w_pend = o; o += align_up((size_t)B * 2 * 8);
   L.w_ratdf = o; o += align_up((size_t)B * kXi1N * 8);
@@ -64,8 +63,7 @@ struct TableArgs {
   const double* params;
   const void* fe;
   double *lg, *lnf, *slope, *ratmod, *T;
-  float* D;
-  float4* AB;
+  unsigned char* D;  // per-lineout tree blobs
   const double* tstat;
   double* D64;
   double* pend;
@@ -143,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
   for (int n = threadIdx.x; n < kXi1N; n += kThreads) s_p[n] = grad_sm(s_rat, kXi1N, ih, n);  // form_factor.py:264
   __syncthreads();
   const int M = a.nodes - 1;
-  tree_prep_cta([s_p](int i) { return s_p[i]; }, M, a.npad, a.D + b * a.npad, a.AB + b * ((a.npad / kTS) * (kTK / 2)), a.tstat);
+  tree_prep_cta([s_p](int i) { return s_p[i]; }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat);
   for (int i = threadIdx.x; i < kXi1N; i += kThreads) {
     if (a.D64) a.D64[b * a.npad + i] = pv_weight(s_p, M, a.xi1_h, i);                  // FP64 validation path
     a.ratdf[b * kXi1N + i] = s_p[i];
@@ -417,7 +415,7 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   fill_static(c, a);
   bind_saved(L, static_cast<char*>(saved), a);
   a.params = params; a.fe = fe;
-  a.D = (float*)(w + L.w_D); a.AB = (float4*)(w + L.w_AB);
+  a.D = (unsigned char*)(w + L.w_D);
   a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend); a.ratdf = (double*)(w + L.w_ratdf);
   a.modl = modl_out; a.ff = ff_out;
@@ -429,11 +427,11 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   }
   {
     PvPolesArgs p;
-    p.Wt = a.D; p.AB = a.AB; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
+    p.blob = a.D; p.D64 = a.D64; p.pend = a.pend; p.poles = c->xi2; p.pole_bstride = 0;
     p.pnodes = a.ratdf; p.pnode_stride = kXi1N;
     p.z0 = c->xi1_0; p.h = c->xi1_h; p.nodes = c->pv_nodes; p.npad = c->pv_npad; p.P = kXi2N;
     p.outI = a.T; p.outdI = nullptr;
-    const size_t smem = (size_t)c->pv_npad * 4 + tree_ab_bytes(c->pv_npad);
+    const size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
     TSFF_SMEM_OPTIN((k_pv_poles<1, TSFF_PV_FP32>));
     TSFF_SMEM_OPTIN((k_pv_poles<2, TSFF_PV_FP32>));
     if (c->pv_precision == TSFF_PV_FP64) {

@@ -7,31 +7,65 @@
 //     W(g)   = sum_{j>=0} x^(2j+1) / ((2j+1)(j+1))                          (second difference of g ln|g|, |x| < 1)
 //     E_0(g) = sum_{k>=1} (-1)^(k+1) x^k / (k(k+1)),    E_M(g) = sum_{k>=1} x^k / (k(k+1)),
 //
-// the nodes are cut into blocks of kTS = 64.  For a pole whose nearest node n lies in block bn, the three blocks
-// wb0..wb0+2 (wb0 = clamp(bn-1, 0, NB-3)) are its NEAR WINDOW: their nodes are summed one by one (FP32 series
-// x(1 + x^2/6 + x^4/15) for |i-n| > kMidHalf = 8, six terms for kNearHalf = 3 < |i-n| <= 8, exact FP64 logs for the
-// 2*kNearHalf+1 nodes around the pole and for an end node inside the window).  Every other block is FAR and enters through a Laurent expansion about its centre c_b:
+// the nodes are cut into blocks of 64 (level 1) and 256 (level 2).  For a pole whose nearest node n lies in level-1
+// block bn and level-2 block Bn:
+//   NEAR WINDOW  level-1 blocks wb0..wb0+2 (wb0 = clamp(bn-1, 0, NB-3)): nodes summed one by one -- FP32 series
+//                x(1 + x^2/6 + x^4/15) for |i-n| > kMidHalf = 8, six terms for kNearHalf = 3 < |i-n| <= 8, exact FP64
+//                logs for the 2*kNearHalf+1 nodes around the pole and for an end node inside the window;
+//   FAR, level 1 the other level-1 blocks whose parent lies in the level-2 window w2..w2+2 (w2 = clamp(Bn-1, ...));
+//   FAR, level 2 every level-2 block outside that window.
+// A far block of S nodes enters through its Laurent expansion about the block centre c:
 //
-//     sum_{i in b} p_i W(g_i)  (+ end-node term)  =  sum_{m<K} A_{b,m} t^(m+1),       t = s h / (z_{c_b} - xi),  s = 32,
-//     A_{b,m} = (1/s) sum_j C(m,2j) / ((2j+1)(j+1)) s^(-2j) mu_{m-2j},               mu_k = sum_{i in b} p_i (-(i-c_b)/s)^k
+//     sum_{i in blk} p_i W(g_i) (+ end-node term) = sum_{m<K} A_m t^(m+1),   t = s h / (z_c - xi),  s = S/2,
+//     A_m = (1/s) sum_j C(m,2j) / ((2j+1)(j+1)) s^(-2j) mu_{m-2j},           mu_k = sum_{i in blk} p_i (-(i-c)/s)^k
 //
-// |t| <= 31.5/96: K = 12 terms truncate at 2e-8 of the sum (tools/tree_proto.py).  Cost per pole: NB far blocks x
-// (1 MUFU.RCP + K packed FMAs) + 192 near nodes, instead of (nodes) x (1 MUFU + ~9 FMA): 9x fewer issue slots at
-// 4096 nodes.  The adjoint is the transpose: per block the local coefficients L_{b,m} = sum_p Ibar_p t^(m+1) are
+// |t| <= 0.332 at both levels; K = 14 truncates at ~3e-9 of the sum.  The two leading terms A_0 t + A_1 t^2 carry the
+// magnitude (for an EPW-resonance pole essentially all of I sits in them) and are evaluated in FP64 from the FP32
+// reciprocal plus one Newton step; the tail t^3 (A_2 + A_3 t + ...) and the derivative series run as one packed-FP32
+// Horner recurrence (fma.rn.f32x2: lanes = (tail of I, dI/dxi)).  Cost per pole at 4096 nodes: ~32 block evaluations
+// x (1 MUFU.RCP + 13 packed FMAs + 6 FP64 ops) + 192 near nodes, instead of 4094 x (1 MUFU + ~9 FMA).
+// The adjoint is the transpose (tsff_pv_kernels.cuh): per block the local coefficients L_m = sum_p Ibar_p t^(m+1) are
 // gathered over the far poles, then spread to the nodes with the same static weights q_m(e) that build A from p.
 #pragma once
 #include "tsff_pv.cuh"
 
 namespace tsff {
 
-constexpr int kTS = 64;              // nodes per block
-constexpr int kTK = 12;              // expansion order
-constexpr double kTs = 32.0;         // scale of the block-local coordinate (half a block)
+constexpr int kTS = 64;              // nodes per level-1 block
+constexpr int kTS2 = 256;            // nodes per level-2 block
+constexpr int kTK = 14;              // expansion order of the forward sweep
+constexpr int kTKA = 12;             // expansion order of the adjoint sweep (gradients need 1e-4, not 1e-5)
+constexpr double kTs = 32.0;         // scale of the level-1 block-local coordinate (half a block)
+constexpr double kTs2 = 128.0;
 constexpr int kTWin = 3 * kTS;       // near-window nodes per pole
+constexpr float kInvTs = (float)(1.0 / kTs);
 
-TSFF_HD int tree_npad(int nodes) {   // nodes = M + 1; at least one full window
-  int n = (nodes + kTS - 1) / kTS * kTS;
-  return n < kTWin ? kTWin : n;
+TSFF_HD int tree_npad(int nodes) {   // nodes = M + 1, padded to whole level-2 blocks (zero weights)
+  return (nodes + kTS2 - 1) / kTS2 * kTS2;
+}
+
+// Per-lineout blob staged into shared memory by one bulk copy (all sizes multiples of 16 bytes):
+//   W   [npad]        float     node weights p_i (interior nodes 1..M-1, zero elsewhere)
+//   AB1 [NB ][kTK/2]  float4    level-1 packed Horner coefficients, step m: (A_{m+2} or 0, (m+1) A_m)
+//   AB2 [NB2][kTK/2]  float4    level-2 ...
+//   LD1 [NB ]         double2   level-1 leading coefficients (A_0, A_1)
+//   LD2 [NB2]         double2
+struct TreeBlob {
+  int npad, NB, NB2;
+  int oW, oAB1, oAB2, oLD1, oLD2, bytes;  // byte offsets
+};
+TSFF_HD TreeBlob tree_blob(int npad) {
+  TreeBlob t;
+  t.npad = npad;
+  t.NB = npad / kTS;
+  t.NB2 = npad / kTS2;
+  t.oW = 0;
+  t.oAB1 = npad * 4;
+  t.oAB2 = t.oAB1 + t.NB * (kTK / 2) * 16;
+  t.oLD1 = t.oAB2 + t.NB2 * (kTK / 2) * 16;
+  t.oLD2 = t.oLD1 + t.NB * 16;
+  t.bytes = t.oLD2 + t.NB2 * 16;
+  return t;
 }
 
 TSFF_HD float2 f2(float x, float y) {
@@ -48,203 +82,320 @@ TSFF_HD double tree_binom(int n, int k) {
   return r;
 }
 // coefficient of mu_{m-2j} in s * A_m
-TSFF_HD double tree_cm(int m, int j) {
+TSFF_HD double tree_cm(int m, int j, double s) {
   double s2j = 1.0;
-  for (int i = 0; i < 2 * j; i++) s2j /= kTs;
+  for (int i = 0; i < 2 * j; i++) s2j /= s;
   return tree_binom(m, 2 * j) / ((double)(2 * j + 1) * (double)(j + 1)) * s2j;
 }
-
-// q_m(e): d A_{b,m} / d p_i for an interior node at offset e = i - c_b  (also the spreading weight of the adjoint)
-TSFF_HD double tree_q(int m, double e) {
-  const double eh = -e / kTs;
+// q_m(e): d A_m / d p_i for an interior node at offset e = i - c  (also the spreading weight of the adjoint)
+TSFF_HD double tree_q(int m, double e, double s) {
+  const double eh = -e / s;
   double acc = 0.0;
   for (int j = 0; 2 * j <= m; j++) {
     double pw = 1.0;
     for (int i = 0; i < m - 2 * j; i++) pw *= eh;
-    acc += tree_cm(m, j) * pw;
+    acc += tree_cm(m, j, s) * pw;
   }
-  return acc / kTs;
+  return acc / s;
 }
 // the same for an end node: `last` = false -> node 0 (kernel E_0), true -> node M (kernel E_M)
-TSFF_HD double tree_q_end(int m, double e, bool last) {
-  const double eh = -e / kTs;
+TSFF_HD double tree_q_end(int m, double e, bool last, double s) {
+  const double eh = -e / s;
   double acc = 0.0;
   for (int r = 0; r <= m; r++) {
     double pw = 1.0;
     for (int i = 0; i < r; i++) pw *= eh;
     double sc = 1.0;
-    for (int i = 0; i < m + 1 - r; i++) sc /= kTs;
+    for (int i = 0; i < m + 1 - r; i++) sc /= s;
     const double sg = last ? 1.0 : (((m - r) & 1) ? -1.0 : 1.0);
     acc += sg * tree_binom(m, r) / ((double)(m + 1 - r) * (double)(m + 2 - r)) * pw * sc;
   }
   return acc;
 }
 
-// Expansion coefficients of block b (FP64).  pget(i) = p_i for 0 <= i <= M.  cmtab: kTK x (kTK/2) table of tree_cm.
-// qend: [2][kTK] rows tree_q_end(m, -c, false), tree_q_end(m, M % kTS - c, true) (the static table's last two rows).
+// Static tables (depend only on the node count M+1): built once per context / call.
+//   QA  [(kTS+2)][kTKA]   adjoint spreading weights q_m(e) of the kTS in-block offsets (level 1), then the rows of
+//                         node 0 and node M
+//   CM1 [kTK][kTK/2], QE1 [2][kTK]    level-1 forward tables (cm matrix, end-node rows)
+//   CM2 [kTK][kTK/2], QE2 [2][kTK]    level-2 forward tables
+constexpr int kTsQA = 0;
+constexpr int kTsCM1 = (kTS + 2) * kTKA;
+constexpr int kTsQE1 = kTsCM1 + kTK * (kTK / 2);
+constexpr int kTsCM2 = kTsQE1 + 2 * kTK;
+constexpr int kTsQE2 = kTsCM2 + kTK * (kTK / 2);
+constexpr int kTreeStaticDoubles = kTsQE2 + 2 * kTK;
+TSFF_HD double tree_static_entry(int i, int M) {
+  const double c1 = 0.5 * (double)(kTS - 1), c2 = 0.5 * (double)(kTS2 - 1);
+  if (i < kTsCM1) {
+    const int k = i / kTKA, m = i % kTKA;
+    if (k < kTS) return tree_q(m, (double)k - c1, kTs);
+    if (k == kTS) return tree_q_end(m, 0.0 - c1, false, kTs);
+    return tree_q_end(m, (double)(M % kTS) - c1, true, kTs);
+  }
+  if (i < kTsQE1) return tree_cm((i - kTsCM1) / (kTK / 2), (i - kTsCM1) % (kTK / 2), kTs);
+  if (i < kTsCM2) {
+    const int k = i - kTsQE1;
+    return k < kTK ? tree_q_end(k, 0.0 - c1, false, kTs) : tree_q_end(k - kTK, (double)(M % kTS) - c1, true, kTs);
+  }
+  if (i < kTsQE2) return tree_cm((i - kTsCM2) / (kTK / 2), (i - kTsCM2) % (kTK / 2), kTs2);
+  const int k = i - kTsQE2;
+  return k < kTK ? tree_q_end(k, 0.0 - c2, false, kTs2) : tree_q_end(k - kTK, (double)(M % kTS2) - c2, true, kTs2);
+}
+
+// Raw moments of block b of S nodes over the node subset {first, first+stride, ...} (a warp splits a block over its
+// lanes and adds the partial moments).  pget(i) = p_i for 0 <= i <= M; interior nodes only.
 template <typename PGet>
-TSFF_HD void tree_block_coeffs(PGet pget, int M, int b, const double* cmtab, const double* qend, double* A /*[kTK]*/) {
-  double mu[kTK];
+TSFF_HD void tree_block_moments(PGet pget, int M, int b, int S, double s, int first, int stride, double* mu /*[kTK]*/) {
   for (int k = 0; k < kTK; k++) mu[k] = 0.0;
-  const double c = (double)(kTS * b) + 0.5 * (double)(kTS - 1);
-  for (int k = 0; k < kTS; k++) {
-    const int i = kTS * b + k;
+  const double c = (double)(S * b) + 0.5 * (double)(S - 1);
+  for (int k = first; k < S; k += stride) {
+    const int i = S * b + k;
     if (i < 1 || i > M - 1) continue;
-    const double eh = -((double)i - c) / kTs;
+    const double eh = -((double)i - c) / s;
     double pw = pget(i);
     for (int q = 0; q < kTK; q++) {
       mu[q] += pw;
       pw *= eh;
     }
   }
+}
+// Expansion coefficients from the (complete) moments, end-node terms included.
+template <typename PGet>
+TSFF_HD void tree_coeffs_from_moments(PGet pget, int M, int b, int S, double s, const double* mu, const double* cmtab,
+                                      const double* qend, double* A /*[kTK]*/) {
   for (int m = 0; m < kTK; m++) {
     double a = 0.0;
     for (int j = 0; 2 * j <= m; j++) a += cmtab[m * (kTK / 2) + j] * mu[m - 2 * j];
-    A[m] = a / kTs;
+    A[m] = a / s;
   }
   if (b == 0)
     for (int m = 0; m < kTK; m++) A[m] += pget(0) * qend[m];
-  if (M >= kTS * b && M < kTS * (b + 1))
+  if (M >= S * b && M < S * (b + 1))
     for (int m = 0; m < kTK; m++) A[m] += pget(M) * qend[kTK + m];
+}
+// Pack the coefficients of one block: ab[kTK/2] float4 = steps (2q, 2q+1), each (A_{m+2} or 0, (m+1) A_m); ld = (A_0, A_1)
+TSFF_HD void tree_pack(const double* A, float4* ab, double* ld) {
+  for (int q = 0; q < kTK / 2; q++) {
+    const int m0 = 2 * q, m1 = 2 * q + 1;
+    float4 v;
+    v.x = m0 + 2 < kTK ? (float)A[m0 + 2] : 0.f;
+    v.y = (float)((double)(m0 + 1) * A[m0]);
+    v.z = m1 + 2 < kTK ? (float)A[m1 + 2] : 0.f;
+    v.w = (float)((double)(m1 + 1) * A[m1]);
+    ab[q] = v;
+  }
+  ld[0] = A[0];
+  ld[1] = A[1];
 }
 
 // A pole in block-local form.  n = nearest node (clamped to [0, M]), delta = xi - z_n:
-//   un = -n (exact),  ndh = -delta/h (|.| <= 1/2 unless the pole lies outside the grid),  wb0 = first window block
+//   un = -n (exact),  ndh = -delta/h (|.| <= 1/2 unless the pole lies outside the grid),
+//   wb0 = first level-1 window block,  w2 = first level-2 window block,  gw = (un + ndh) in double (= (z_0 - xi)/h)
 struct TreePole {
   float un, ndh;
-  int wb0;
+  int wb0, w2;
+  double gw;
 };
-TSFF_HD TreePole tree_pole(double xi, double z0, double h, int M, int NB) {
+TSFF_HD TreePole tree_pole(double xi, double z0, double h, int M, int npad) {
   double r = rint((xi - z0) / h);
   if (!(r >= 0.0)) r = 0.0;  // also NaN
   if (r > (double)M) r = (double)M;
+  const double dh = -(xi - (z0 + r * h)) / h;
   TreePole t;
   t.un = (float)(-r);
-  t.ndh = (float)(-(xi - (z0 + r * h)) / h);
-  int bn = (int)r / kTS;
-  int w = bn - 1;
-  if (w < 0) w = 0;
+  t.ndh = (float)dh;
+  t.gw = -r + dh;
+  const int NB = npad / kTS, NB2 = npad / kTS2;
+  int w = (int)r / kTS - 1;
   if (w > NB - 3) w = NB - 3;
+  if (w < 0) w = 0;
   t.wb0 = w;
+  int w2 = (int)r / kTS2 - 1;
+  if (w2 > NB2 - 3) w2 = NB2 - 3;
+  if (w2 < 0) w2 = 0;
+  t.w2 = w2;
   return t;
 }
 
-constexpr float kInvTs = (float)(1.0 / kTs);
-
-// Far field for R poles of one thread.  sAB: [NB][kTK] pairs (A_m, (m+1) A_m), 16-byte aligned rows.
-// accI += sum_far A t^(m+1);  accJ += t^2 sum_far (m+1) A t^m   (dI/dxi = accJ / (s h), applied by the caller).
-// Four blocks are summed in FP32 before they enter the FP64 accumulator: left and right of the pole the block sums are
-// O(1) with opposite signs, and a running FP32 sum over all of them costs 2e-7 (tools/tree_proto.py).
+// One far block for R poles: packed FP32 Horner (tail of I, dI/dxi) + FP64 leading terms.
+//   cbs = c_b / s (exact in FP32 and FP64), invs = 1/s, ab = the block's kTK/2 float4, ld = (A_0, A_1)
+//   use[r]: the block is far for pole r.  aI/aJ: FP32 partial sums, acc64: FP64 sum of the leading terms.
 template <int R>
-TSFF_HD void tree_far(const float4* sAB, int NB, const TreePole (&tp)[R], double (&accI)[R], double (&accJ)[R]) {
+TSFF_HD void tree_far_block(const float4* ab, const double* ld, float cbs, float invs, const TreePole (&tp)[R],
+                            const bool (&use)[R], float (&aI)[R], float (&aJ)[R], double (&acc64)[R]) {
   constexpr int H = kTK / 2;
-  for (int b0 = 0; b0 < NB; b0 += 4) {
-    float aI[R], aJ[R];
+  float2 tt[R], acc[R];
+  float t[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) aI[r] = aJ[r] = 0.f;
+  for (int r = 0; r < R; r++) {
+    const float u = fmaf(tp[r].un, invs, cbs);    // (c_b - n)/s, exact
+    const float g = fmaf(tp[r].ndh, invs, u);     // (z_cb - xi)/(s h)
+    t[r] = use[r] ? rcp_approx(g) : 0.f;
+    tt[r] = f2(t[r], t[r]);
+  }
+  float4 c = ab[H - 1];
+#pragma unroll
+  for (int r = 0; r < R; r++) acc[r] = ffma2(f2(c.z, c.w), tt[r], f2(c.x, c.y));
+#pragma unroll
+  for (int q = H - 2; q >= 0; q--) {
+    c = ab[q];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      acc[r] = ffma2(acc[r], tt[r], f2(c.z, c.w));
+      acc[r] = ffma2(acc[r], tt[r], f2(c.x, c.y));
+    }
+  }
+  const double A0 = ld[0], A1 = ld[1];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const float t2 = t[r] * t[r];
+    aI[r] = fmaf(t2 * t[r], acc[r].x, aI[r]);
+    aJ[r] = fmaf(t2, acc[r].y, aJ[r]);
+    // leading terms in FP64: one Newton step on the FP32 reciprocal (t = 0 stays 0 for a masked block)
+    const double g64 = fma(tp[r].gw, (double)invs, (double)cbs);
+    double t64 = (double)t[r];
+    t64 = fma(t64, fma(-g64, t64, 1.0), t64);
+    acc64[r] = fma(t64, fma(A1, t64, A0), acc64[r]);
+  }
+}
+
+// Far field for R poles of one thread.  blob: the staged per-lineout blob (shared memory), tb its layout.
+// accI += sum_far A t^(m+1);  accJ1 / accJ2: t^2 sum (m+1) A t^m per level (dI/dxi = accJ1/(s1 h) + accJ2/(s2 h)).
+// Must be called by all 32 lanes (warp min/max of the level-2 windows).
+template <int R>
+TSFF_HD void tree_far(const unsigned char* blob, const TreeBlob tb, const TreePole (&tp)[R], double (&accI)[R], double (&accJ1)[R],
+                      double (&accJ2)[R]) {
+  constexpr int H = kTK / 2;
+  const float4* ab1 = reinterpret_cast<const float4*>(blob + tb.oAB1);
+  const float4* ab2 = reinterpret_cast<const float4*>(blob + tb.oAB2);
+  const double* ld1 = reinterpret_cast<const double*>(blob + tb.oLD1);
+  const double* ld2 = reinterpret_cast<const double*>(blob + tb.oLD2);
+  float aI[R], aJ[R];
+  double a64[R];
+  bool use[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) { aI[r] = aJ[r] = 0.f; a64[r] = 0.0; }
+  // ---- level 2: every block outside the level-2 window
+  for (int B = 0; B < tb.NB2; B++) {
+#pragma unroll
+    for (int r = 0; r < R; r++) use[r] = (unsigned)(B - tp[r].w2) > 2u;
+    tree_far_block<R>(ab2 + B * H, ld2 + 2 * B, (float)(2 * B) + (float)(0.5 * (kTS2 - 1) / kTs2), (float)(1.0 / kTs2), tp, use, aI, aJ, a64);
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    accI[r] += a64[r] + (double)aI[r];
+    accJ2[r] += (double)aJ[r];
+    aI[r] = aJ[r] = 0.f;
+    a64[r] = 0.0;
+  }
+  // ---- level 1: children of the level-2 windows of this warp's poles, minus each pole's near window
+  int wlo = tp[0].w2, whi = tp[0].w2;
+#pragma unroll
+  for (int r = 1; r < R; r++) { wlo = tp[r].w2 < wlo ? tp[r].w2 : wlo; whi = tp[r].w2 > whi ? tp[r].w2 : whi; }
+#if defined(__CUDA_ARCH__)
+  wlo = __reduce_min_sync(0xffffffffu, wlo);
+  whi = __reduce_max_sync(0xffffffffu, whi);
+#endif
+  int bend = 4 * (whi + 3);
+  if (bend > tb.NB) bend = tb.NB;
+  for (int b0 = 4 * wlo; b0 < bend; b0 += 4) {
 #pragma unroll
     for (int bb = 0; bb < 4; bb++) {
       const int b = b0 + bb;
-      if (b < NB) {
-        const float cb = (float)(2 * b) + (float)(0.5 * (kTS - 1) / kTs);  // c_b / s, exact
-        float2 tt[R], acc[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float u = fmaf(tp[r].un, kInvTs, cb);                       // (c_b - n)/s, exact
-          const float g = fmaf(tp[r].ndh, kInvTs, u);                       // (z_cb - xi)/(s h)
-          const bool far = (unsigned)(b - tp[r].wb0) > 2u;
-          const float t = far ? rcp_approx(g) : 0.f;
-          tt[r] = f2(t, t);
-        }
-        float4 c = sAB[b * H + H - 1];
-#pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = ffma2(f2(c.z, c.w), tt[r], f2(c.x, c.y));
-#pragma unroll
-        for (int q = H - 2; q >= 0; q--) {
-          c = sAB[b * H + q];
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            acc[r] = ffma2(acc[r], tt[r], f2(c.z, c.w));
-            acc[r] = ffma2(acc[r], tt[r], f2(c.x, c.y));
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          aI[r] = fmaf(tt[r].x, acc[r].x, aI[r]);
-          aJ[r] = fmaf(tt[r].x * tt[r].x, acc[r].y, aJ[r]);
-        }
-      }
+      for (int r = 0; r < R; r++) use[r] = ((unsigned)((b >> 2) - tp[r].w2) <= 2u) && ((unsigned)(b - tp[r].wb0) > 2u);
+      tree_far_block<R>(ab1 + b * H, ld1 + 2 * b, (float)(2 * b) + (float)(0.5 * (kTS - 1) / kTs), (float)(1.0 / kTs), tp, use, aI, aJ, a64);
     }
+  }
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      accI[r] += (double)aI[r];
-      accJ[r] += (double)aJ[r];
-    }
+  for (int r = 0; r < R; r++) {
+    accI[r] += a64[r] + (double)aI[r];
+    accJ1[r] += (double)aJ[r];
   }
 }
 
 // Near window of ONE pole: the 192 nodes of blocks wb0..wb0+2 except those with |i - n| <= kNearHalf.
 // sW: node weights p_i (FP32; zero at i = 0, i >= M and in the padding), 16-byte aligned.
-// accI += sum p_i W(g_i);  accJ += sum p_i h dW/dxi(g_i)   (dI/dxi = accJ / h, applied by the caller).
-// Two nodes share one packed instruction; groups of 32 nodes enter the FP64 accumulators.
-TSFF_HD void tree_near(const float* sW, const TreePole tp, double& accI, double& accJ) {
+// returns I = sum p_i W(g_i),  J = sum p_i h dW/dxi(g_i)   (dI/dxi = J / h, applied by the caller).
+// The window is walked in 12 groups of 16 nodes, ROTATED so that every lane starts at the group that holds its own
+// pole: the pole's group and its two neighbours take the six-term series with the exact-zone mask, the other nine the
+// three-term series -- the same instruction stream for all lanes whatever their pole positions (no vote, no
+// divergence).  Two nodes share one packed instruction; every 16-node group enters the FP64 accumulator of I.
+struct TreeAcc {
+  double I, J;
+};
+TSFF_HD_NOINLINE TreeAcc tree_near(const float* sW, const TreePole tp) {
+  double accI = 0.0;
   const float4* w4 = reinterpret_cast<const float4*>(sW + kTS * tp.wb0);
-  const float ub = (float)(kTS * tp.wb0) + tp.un;  // i0 - n, exact
+  const float ub = (float)(kTS * tp.wb0) + tp.un;  // i0 - n, exact (<= 0)
+  const int qn = ((int)(-ub)) >> 4;                // group of the pole's nearest node, 0..11
   const float2 one = f2(1.f, 1.f);
-  const float lim = (float)kNearHalf + 0.5f, mid = (float)kMidHalf + 0.5f;
-  for (int q0 = 0; q0 < kTWin / 4; q0 += 8) {
-    // does this group of 32 nodes [ub + 4 q0, ub + 4 q0 + 31] come within kMidHalf nodes of the pole?
-    const float ulo = ub + (float)(4 * q0);
-    const bool touch = (ulo <= mid) && (ulo + 31.f >= -mid);
-    float2 aI = f2(0.f, 0.f), aJ = f2(0.f, 0.f);
-    if (!TSFF_WARP_ANY(touch)) {
-      // |i - n| > kMidHalf: W = x (1 + x^2/6 + x^4/15),  h dW/dxi = x^2 (1 + x^2/2 + x^4/3)
-      const float2 c2 = f2(1.f / 6.f, 1.f / 6.f), c4 = f2(1.f / 15.f, 1.f / 15.f), d2 = f2(0.5f, 0.5f), d4 = f2(1.f / 3.f, 1.f / 3.f);
+  const float lim = (float)kNearHalf + 0.5f;
+  float2 aJ = f2(0.f, 0.f);
+  // ---- the pole's group and its neighbours: six terms (x <= 1/3.5: the seventh is 3e-9); |i - n| <= kNearHalf -> FP64
+#pragma unroll 1
+  for (int j = -1; j <= 1; j++) {
+    int q = qn + j;
+    q = q < 0 ? q + 12 : (q >= 12 ? q - 12 : q);
+    const float ulo = ub + (float)(16 * q);
+    float2 aI = f2(0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const float4 w = w4[q0 + q];
+    for (int c = 0; c < 4; c++) {
+      const float4 w = w4[4 * q + c];
 #pragma unroll
-        for (int hlf = 0; hlf < 2; hlf++) {
-          const float u0 = ulo + (float)(4 * q + 2 * hlf);
-          const float2 x = f2(rcp_approx(u0 + tp.ndh), rcp_approx((u0 + 1.f) + tp.ndh));
-          const float2 s2 = fmul2(x, x);
-          const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
-          aI = ffma2(fmul2(wv, x), ffma2(ffma2(s2, c4, c2), s2, one), aI);
-          aJ = ffma2(fmul2(wv, s2), ffma2(ffma2(s2, d4, d2), s2, one), aJ);
-        }
-      }
-    } else {
-      // next to the pole: six terms (x <= 1/3.5: the seventh is 3e-9), nodes with |i - n| <= kNearHalf left to FP64
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const float4 w = w4[q0 + q];
-#pragma unroll
-        for (int hlf = 0; hlf < 2; hlf++) {
-          const float u0 = ulo + (float)(4 * q + 2 * hlf), u1 = u0 + 1.f;
-          const float x0 = fabsf(u0) > lim ? rcp_approx(u0 + tp.ndh) : 0.f;
-          const float x1 = fabsf(u1) > lim ? rcp_approx(u1 + tp.ndh) : 0.f;
-          const float2 x = f2(x0, x1);
-          const float2 s2 = fmul2(x, x);
-          const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
-          float2 pI = f2(1.f / 66.f, 1.f / 66.f), pJ = f2(1.f / 6.f, 1.f / 6.f);
-          pI = ffma2(pI, s2, f2(1.f / 45.f, 1.f / 45.f));
-          pJ = ffma2(pJ, s2, f2(0.2f, 0.2f));
-          pI = ffma2(pI, s2, f2(1.f / 28.f, 1.f / 28.f));
-          pJ = ffma2(pJ, s2, f2(0.25f, 0.25f));
-          pI = ffma2(pI, s2, f2(1.f / 15.f, 1.f / 15.f));
-          pJ = ffma2(pJ, s2, f2(1.f / 3.f, 1.f / 3.f));
-          pI = ffma2(pI, s2, f2(1.f / 6.f, 1.f / 6.f));
-          pJ = ffma2(pJ, s2, f2(0.5f, 0.5f));
-          pI = ffma2(pI, s2, one);
-          pJ = ffma2(pJ, s2, one);
-          aI = ffma2(fmul2(wv, x), pI, aI);
-          aJ = ffma2(fmul2(wv, s2), pJ, aJ);
-        }
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const float u0 = ulo + (float)(4 * c + 2 * hlf), u1 = u0 + 1.f;
+        const float x0 = fabsf(u0) > lim ? rcp_approx(u0 + tp.ndh) : 0.f;
+        const float x1 = fabsf(u1) > lim ? rcp_approx(u1 + tp.ndh) : 0.f;
+        const float2 x = f2(x0, x1);
+        const float2 s2 = fmul2(x, x);
+        const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
+        float2 pI = f2(1.f / 66.f, 1.f / 66.f), pJ = f2(1.f / 6.f, 1.f / 6.f);
+        pI = ffma2(pI, s2, f2(1.f / 45.f, 1.f / 45.f));
+        pJ = ffma2(pJ, s2, f2(0.2f, 0.2f));
+        pI = ffma2(pI, s2, f2(1.f / 28.f, 1.f / 28.f));
+        pJ = ffma2(pJ, s2, f2(0.25f, 0.25f));
+        pI = ffma2(pI, s2, f2(1.f / 15.f, 1.f / 15.f));
+        pJ = ffma2(pJ, s2, f2(1.f / 3.f, 1.f / 3.f));
+        pI = ffma2(pI, s2, f2(1.f / 6.f, 1.f / 6.f));
+        pJ = ffma2(pJ, s2, f2(0.5f, 0.5f));
+        pI = ffma2(pI, s2, one);
+        pJ = ffma2(pJ, s2, one);
+        aI = ffma2(fmul2(wv, x), pI, aI);
+        aJ = ffma2(fmul2(wv, s2), pJ, aJ);
       }
     }
-    accI += (double)(aI.x + aI.y);
-    accJ += (double)(aJ.x + aJ.y);
+    accI += (double)aI.x + (double)aI.y;
   }
+  double accJ = (double)aJ.x + (double)aJ.y;
+  aJ = f2(0.f, 0.f);
+  // ---- the other nine groups (|i - n| >= 17): W = x (1 + x^2/6 + x^4/15),  h dW/dxi = x^2 (1 + x^2/2 + x^4/3)
+  const float2 c2 = f2(1.f / 6.f, 1.f / 6.f), c4 = f2(1.f / 15.f, 1.f / 15.f), d2 = f2(0.5f, 0.5f), d4 = f2(1.f / 3.f, 1.f / 3.f);
+#pragma unroll 1
+  for (int j = 2; j <= 10; j++) {
+    int q = qn + j;
+    q = q >= 12 ? q - 12 : q;
+    const float ulo = ub + (float)(16 * q);
+    float2 aI = f2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const float4 w = w4[4 * q + c];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const float u0 = ulo + (float)(4 * c + 2 * hlf);
+        const float2 x = f2(rcp_approx(u0 + tp.ndh), rcp_approx((u0 + 1.f) + tp.ndh));
+        const float2 s2 = fmul2(x, x);
+        const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
+        aI = ffma2(fmul2(wv, x), ffma2(ffma2(s2, c4, c2), s2, one), aI);
+        aJ = ffma2(fmul2(wv, s2), ffma2(ffma2(s2, d4, d2), s2, one), aJ);
+      }
+    }
+    accI += (double)aI.x + (double)aI.y;
+  }
+  TreeAcc r;
+  r.I = accI;
+  r.J = accJ + ((double)aJ.x + (double)aJ.y);
+  return r;
 }
 
 // Exact FP64 part of I and dI/dxi for one pole: the interior nodes with |i - n| <= kNearHalf, and an end node when its
@@ -262,11 +413,11 @@ TSFF_HD void tree_near_exact(double xi, double z0, double h, int M, int wb0, PGe
   double sI = 0.0, sJ = 0.0;
   if (lo <= hi) {
     double gm = z0 + (double)(lo - 1) * h - xi;
-    double lm = log(fmax(fabs(gm), 1e-300)), lc = log(fmax(fabs(gm + h), 1e-300));
+    double lm = log_abs(gm), lc = log_abs(gm + h);
     for (int i = lo; i <= hi; i++) {
       const double gc = z0 + (double)i * h - xi;
       const double gp = z0 + (double)(i + 1) * h - xi;
-      const double lp = log(fmax(fabs(gp), 1e-300));
+      const double lp = log_abs(gp);
       const double p = pget(i);
       sI += p * (gp * lp - 2.0 * gc * lc + gm * lm) * ih;   // W
       sJ += -p * (lp - 2.0 * lc + lm) * ih;                 // dW/dxi
@@ -277,14 +428,14 @@ TSFF_HD void tree_near_exact(double xi, double z0, double h, int M, int wb0, PGe
   }
   if (wb0 == 0) {
     const double g0 = z0 - xi;
-    const double l0 = log(fmax(fabs(g0), 1e-300)), l1 = log(fmax(fabs(g0 + h), 1e-300));
+    const double l0 = log_abs(g0), l1 = log_abs(g0 + h);
     const double p0 = pget(0);
     sI += p0 * (((g0 + h) * l1 - g0 * l0) * ih - 1.0 - l0);
     sJ += p0 * (-(l1 - l0) * ih + 1.0 / g0);
   }
   if ((unsigned)(M / kTS - wb0) <= 2u) {
     const double gM = z0 + (double)M * h - xi;
-    const double lM = log(fmax(fabs(gM), 1e-300)), lM1 = log(fmax(fabs(gM - h), 1e-300));
+    const double lM = log_abs(gM), lM1 = log_abs(gM - h);
     const double pM = pget(M);
     sI += pM * (((gM - h) * lM1 - gM * lM) * ih + 1.0 + lM);
     sJ += pM * (-(lM1 - lM) * ih - 1.0 / gM);
