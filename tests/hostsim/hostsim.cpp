@@ -185,6 +185,21 @@ int main() {
                   reinterpret_cast<double*>(blob + (lvl ? tb.oLD2 : tb.oLD1)) + 2 * b);
       }
     }
+    {  // the prep kernel's route to the level-2 moments (static tables E1, T12) vs the direct sums
+      double worst = 0;
+      for (int B2 = 0; B2 < tb.NB2; B2++) {
+        double direct[kTK]; tree_block_moments(pget, M, B2, kTS2, kTs2, 0, 1, direct);
+        double viaT[kTK] = {0};
+        for (int c = 0; c < 4; c++) {
+          double mu1[kTK] = {0};
+          for (int o = 0; o < kTS; o++) { const int i = kTS * (4 * B2 + c) + o; if (i >= 1 && i <= M - 1) for (int k = 0; k < kTK; k++) mu1[k] += f[i] * ts[kTsE1 + o * kTK + k]; }
+          for (int k = 0; k < kTK; k++) for (int j = 0; j <= k; j++) viaT[k] += ts[kTsT12 + (c * kTK + k) * kTK + j] * mu1[j];
+        }
+        double nrm = 0; for (int k = 0; k < kTK; k++) nrm = std::max(nrm, fabs(direct[k]));
+        for (int k = 0; k < kTK; k++) worst = std::max(worst, fabs(viaT[k] - direct[k]) / std::max(nrm, 1e-300));
+      }
+      if (worst > 1e-12) { printf("FAIL moment translation N=%d err=%.3e\n", N, worst); fails++; }
+    }
     double maxe = 0, maxd = 0, scale = 0;
     std::vector<double> xis = {-7.3, -5.99, -5.2, -2.345678, -0.0117, 0.0, 0.4321, 1.0 + 1e-9, 3.3333, 5.2, 5.97, 6.8};
     for (int k = 0; k < 60; k++) xis.push_back(-7.0 + 14.0 * (k + 0.37) / 60.0);
@@ -195,7 +210,7 @@ int main() {
       double fI[1] = {0}, fJ1[1] = {0}, fJ2[1] = {0}, eI, eJ;
       tree_far<1>(blob, tb, tp, fI, fJ1, fJ2);
       const TreeAcc na = tree_near(W, tp[0]);
-      tree_near_exact(xi, z0, h, M, tp[0].wb0, pget, eI, eJ);
+      tree_near_exact(xi, z0, h, M, (int)(-tp[0].un), tp[0].wb0, pget, eI, eJ);
       const double I = eI + na.I + fI[0], dI = eJ + na.J / h + fJ1[0] / (kTs * h) + fJ2[0] / (kTs2 * h);
       const double e = 1e-6;
       const double fd = (ratintn_literal(f, z, xi + e) - ratintn_literal(f, z, xi - e)) / (2 * e);

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kThreads) k_pv_prep(const double* f, int N, do
   const long long b = blockIdx.x;
   const double* fb = f + b * N;
   const int M = N - 2;
-  tree_prep_cta([fb](int i) { return fb[i]; }, M, npad, blob + b * tree_blob(npad).bytes, tstat);
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  tree_prep_cta(fb, M, npad, blob + b * tree_blob(npad).bytes, tstat, reinterpret_cast<double*>(prep_smem));
   for (int i = threadIdx.x; i < npad; i += kThreads) D64[b * npad + i] = pv_weight(fb, M, h, i);  // FP64 validation path
   if (threadIdx.x == 0) {
     pend[2 * b] = fb[0];
@@ -103,9 +104,9 @@ __global__ void __launch_bounds__(kThreads) k_pv_desc(const double* pole, const 
   const long long b = blockIdx.x;
   for (int p = threadIdx.x; p < P; p += kThreads) {
     const double xi = pole[b * P + p], ob = out_bar[b * P + p];
-    int wb0;
-    desc[b * P + p] = pv_desc(xi, ob, z0, h, nodes, npad, wb0);
-    pv_bwd_pole_exact(xi, ob, z0, h, nodes, wb0, pnear + b * npad);
+    int np, wb0;
+    desc[b * P + p] = pv_desc(xi, ob, z0, h, nodes, npad, np, wb0);
+    pv_bwd_pole_exact(xi, ob, z0, h, nodes, np, wb0, pnear + b * npad);
   }
 }
 
@@ -153,7 +154,7 @@ extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);
   k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
-  k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
+  k_pv_prep<<<(unsigned)B, kThreads, tree_prep_scratch_bytes(L.npad), st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
                                             (double*)(w + L.D64), (double*)(w + L.pend));
   TSFF_LAUNCH_OK("k_pv_prep");
   return launch_poles(L, B, N, P, f, w, z0, h, pole, out, dout_dpole, pv_precision, st);
@@ -178,7 +179,7 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   k_pv_bwd_finish<<<(unsigned)B, kThreads, 0, st>>>((double*)(w + L.Dbar), (double*)(w + L.pendbar), (int)N, L.npad, f_bar);
   TSFF_LAUNCH_OK("k_pv_bwd_finish");
   if (pole_bar) {
-    k_pv_prep<<<(unsigned)B, kThreads, 0, st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
+    k_pv_prep<<<(unsigned)B, kThreads, tree_prep_scratch_bytes(L.npad), st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
                                               (double*)(w + L.D64), (double*)(w + L.pend));
     TSFF_LAUNCH_OK("k_pv_prep");
     int rc = launch_poles(L, B, N, P, f, w, z0, h, pole, (double*)(w + L.tI), (double*)(w + L.tdI), TSFF_PV_FP32, st);

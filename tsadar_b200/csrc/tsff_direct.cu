@@ -21,11 +21,14 @@ namespace {
 constexpr int kThreads = 256;
 
 // np.gradient(f, dv) at node i (form_factor.py:372): central inside, first-order one-sided at the ends
+// (division by the uniform spacing as a multiplication by its reciprocal: every consumer of df goes through this one
+// function, so the node values seen by the tree weights, the exact zone and the adjoint agree bit for bit)
 template <typename T>
 __device__ __forceinline__ double grad_at(const T* f, int V, double dv, int i) {
-  if (i <= 0) return ((double)f[1] - (double)f[0]) / dv;
-  if (i >= V - 1) return ((double)f[V - 1] - (double)f[V - 2]) / dv;
-  return ((double)f[i + 1] - (double)f[i - 1]) / (2.0 * dv);
+  const double idv = fast_rcp(dv);
+  if (i <= 0) return ((double)f[1] - (double)f[0]) * idv;
+  if (i >= V - 1) return ((double)f[V - 1] - (double)f[V - 2]) * idv;
+  return ((double)f[i + 1] - (double)f[i - 1]) * (0.5 * idv);
 }
 
 struct DirectLayout {  // byte offsets inside `saved` and `ws` for a batch of B lineouts
@@ -113,9 +116,12 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
   }
   const int M = a.nodes - 1;
   {
-    const int V = a.V;
-    const double dv = a.dv;
-    tree_prep_cta([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat);
+    // node values p_i = gradient(f)_i in shared memory, then the tree blob
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    double* sp = reinterpret_cast<double*>(prep_smem);
+    for (int i = threadIdx.x; i < a.npad; i += kThreads) sp[i] = (i <= M) ? grad_at(fe, a.V, a.dv, i) : 0.0;
+    __syncthreads();
+    tree_prep_cta(sp, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat, sp + a.npad);
   }
   if (a.D64) {  // log-form weights for the FP64 validation path
     for (int i = threadIdx.x; i < a.npad; i += kThreads) {
@@ -138,8 +144,8 @@ __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
 // FP64 tail of one pole: exact near nodes, ion susceptibility, lerp of f and f', assembly; stores P, I, dI/dxi.
 // Not inlined: shared by the R poles of a thread (the kernel would otherwise carry R copies of the FP64 log code).
 template <typename T, int PREC>
-__device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, const T* fe, long long b, int g, int idx, int wb0,
-                                          double farI, double farJ, double g0d) {
+__device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, const T* fe, long long b, int g, int idx, int n,
+                                          int wb0, double farI, double farJ, double g0d) {
   const int j = idx / a.A, ia = idx % a.A;
   const int M = a.nodes - 1;
   const double omgs = a.omgs[j];
@@ -151,7 +157,7 @@ __device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, con
   if (PREC == TSFF_PV_FP32) {
     const int V = a.V;
     const double dv = a.dv;
-    tree_near_exact(q.xie, a.v0, dv, M, wb0, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
+    tree_near_exact(q.xie, a.v0, dv, M, n, wb0, [fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, I, dI);
     I += farI;
     dI += farJ;
   } else {
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_cons
       farI += nrI[r];
       farJ = accJ[r] / (kTs * a.dv) + accJ2[r] / (kTs2 * a.dv) + nrJ[r] / a.dv;
     }
-    direct_point<T, PREC>(a, sL, fe, b, g, idx, tp[r].wb0, farI, farJ, g0d[r]);
+    direct_point<T, PREC>(a, sL, fe, b, g, idx, (int)(-tp[r].un), tp[r].wb0, farI, farJ, g0d[r]);
   }
 }
 
@@ -297,9 +303,9 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs 
     }
     // d I / d p_i for the nodes next to the pole (and an end node inside its window), exactly (FP64); the rest is
     // k_pv_nodes' (far blocks + near-window series)
-    int wb0;
-    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = pv_desc(q.xie, Ibar, a.v0, a.dv, a.nodes, a.npad, wb0);
-    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, wb0, a.accdf + b * a.V, i_f, (1.0 - t_f) * dfe_bar, i_f + 1,
+    int np, wb0;
+    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = pv_desc(q.xie, Ibar, a.v0, a.dv, a.nodes, a.npad, np, wb0);
+    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, np, wb0, a.accdf + b * a.V, i_f, (1.0 - t_f) * dfe_bar, i_f + 1,
                       t_f * dfe_bar);
     kin_backward(sL, omgs, cth, q, kb, Lb);
   }
@@ -363,7 +369,11 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend);
   a.ff = ff_out ? ff_out : (double*)(w + L.w_ff);
-  k_direct_prep<T><<<(unsigned)B, kThreads, 0, st>>>(a);
+  {
+    const size_t psm = (size_t)c->pv_npad * 8 + tree_prep_scratch_bytes(c->pv_npad);
+    TSFF_SMEM_OPTIN(k_direct_prep<T>);
+    k_direct_prep<T><<<(unsigned)B, kThreads, psm, st>>>(a);
+  }
   TSFF_LAUNCH_OK("k_direct_prep");
   const int WA = c->W * c->A;
   const size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
@@ -441,7 +451,7 @@ size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B
 
 int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
                void* saved, void* ws, cudaStream_t st) {
-  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024 || (size_t)c->pv_npad * 8 + tree_prep_scratch_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
                               : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
 }

@@ -157,6 +157,64 @@ TSFF_HD void lg_backward(const double* p, int nI, int g, int G, double lam_shift
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP64 reciprocal, square root and exp(y <= 0) at ~1-2 ulp from the MUFU seeds (rcp/rsqrt.approx.ftz.f64) and Newton
+// steps: 5-20 instructions instead of the 30-60 of the IEEE-exact library paths.  The per-pole FP64 stage runs ~15
+// divisions, 2 square roots and 1 exponential per pole; the reference is float64 and parity is asked to 1e-5.
+// Arguments are positive normal numbers (the kernels' NaN policy is "propagate": NaN in -> NaN out still holds).
+// ------------------------------------------------------------------------------------------------
+TSFF_HD double fast_rcp(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / d;
+#endif
+}
+TSFF_HD double fast_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double h = 0.5 * r, s = x * r;             // Goldschmidt: s -> sqrt(x), h -> 1/(2 sqrt(x))
+  double e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  return fma(fma(-s, s, x), h, s);
+#else
+  return sqrt(x);
+#endif
+}
+TSFF_HD double fast_exp_neg(double y) {       // exp(y), y <= 0
+#if defined(__CUDA_ARCH__)
+  if (!(y > -700.0)) return y == y ? 0.0 : y;
+  const double n = rint(y * 1.4426950408889634);
+  double f = fma(-n, 0.693147180369123816490, y);   // ln2 split hi/lo
+  f = fma(-n, 1.90821492927058770002e-10, f);
+  double p = 1.0 / 479001600.0;
+  p = fma(p, f, 1.0 / 39916800.0);
+  p = fma(p, f, 1.0 / 3628800.0);
+  p = fma(p, f, 1.0 / 362880.0);
+  p = fma(p, f, 1.0 / 40320.0);
+  p = fma(p, f, 1.0 / 5040.0);
+  p = fma(p, f, 1.0 / 720.0);
+  p = fma(p, f, 1.0 / 120.0);
+  p = fma(p, f, 1.0 / 24.0);
+  p = fma(p, f, 1.0 / 6.0);
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));   // p * 2^n, n >= -1010
+#else
+  return exp(y);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // ln(x) for a positive, normal double to ~2e-15 relative-to-1 accuracy in ~30 instructions (the CUDA library log costs
 // ~100 SASS instructions inline, and the exact near-pole terms of the PV sums need 11 logs per pole).
 // x = 2^e m, m in [sqrt(1/2), sqrt(2)):  ln x = e ln2 + 2 atanh(s),  s = (m-1)/(m+1),  |s| <= 0.1716.
@@ -217,13 +275,14 @@ struct ZTab {
 TSFF_HD void zprime_lerp(const ZTab& z, double x, double& zr, double& zi, double& dzr, double& dzi) {
   if (x < z.x0 || x > z.xlast) {
     double x2 = x * x;
-    zr = 1.0 / x2;
-    dzr = -2.0 / (x2 * x);
+    zr = fast_rcp(x2);
+    dzr = -2.0 * zr * fast_rcp(x);
     zi = 0.0;
     dzi = 0.0;
     return;
   }
-  double u = (x - z.x0) / z.h;
+  const double ih = fast_rcp(z.h);
+  double u = (x - z.x0) * ih;
   int i = (int)u;
   if (i > z.n - 2) i = z.n - 2;
   if (i < 0) i = 0;
@@ -231,15 +290,16 @@ TSFF_HD void zprime_lerp(const ZTab& z, double x, double& zr, double& zi, double
   double r0 = z.zr[i], r1 = z.zr[i + 1], i0 = z.zi[i], i1 = z.zi[i + 1];
   zr = r0 + t * (r1 - r0);
   zi = i0 + t * (i1 - i0);
-  dzr = (r1 - r0) / z.h;
-  dzi = (i1 - i0) / z.h;
+  dzr = (r1 - r0) * ih;
+  dzi = (i1 - i0) * ih;
 }
 
 // edge-clamped linear interpolation on a uniform grid (jnp.interp default; form_factor.py:270,376-377)
 // returns value; idx/t/slope for the adjoint (slope = 0 and weights collapse on the edge when clamped)
 template <typename T>
 TSFF_HD double lerp_uniform(const T* f, int n, double x0, double h, double x, int& i, double& t, double& slope) {
-  double u = (x - x0) / h;
+  const double ih = fast_rcp(h);
+  double u = (x - x0) * ih;
   if (!(u > 0.0)) {  // left clamp (also NaN)
     i = 0; t = 0.0; slope = 0.0;
     return (double)f[0];
@@ -251,7 +311,7 @@ TSFF_HD double lerp_uniform(const T* f, int n, double x0, double h, double x, in
   i = (int)u;
   t = u - (double)i;
   double a = (double)f[i], b = (double)f[i + 1];
-  slope = (b - a) / h;
+  slope = (b - a) * ih;
   return a + t * (b - a);
 }
 
@@ -263,13 +323,14 @@ struct Kin {
 };
 
 TSFF_HD void kin_forward(const LG& L, double omgs, double cth, Kin& q) {
-  q.ks = sqrt(omgs * omgs - L.omgpe2) / kC;
+  q.ks = fast_sqrt(omgs * omgs - L.omgpe2) * (1.0 / kC);
   q.k2 = q.ks * q.ks + L.kL * L.kL - 2.0 * q.ks * L.kL * cth;
-  q.k = sqrt(q.k2);
+  q.k = fast_sqrt(q.k2);
   q.omgdop = omgs - L.omgL - q.k * L.Va6;
-  q.w = q.omgdop / q.k;
-  q.xie = (q.w - L.ud6) / L.vTe;
-  q.ikl2 = L.omgpe2 / (L.vTe * L.vTe * q.k2);
+  q.w = q.omgdop * fast_rcp(q.k);
+  const double ivTe = fast_rcp(L.vTe);
+  q.xie = (q.w - L.ud6) * ivTe;
+  q.ikl2 = L.omgpe2 * ivTe * ivTe * fast_rcp(q.k2);
 }
 
 // ion susceptibility (form_factor.py:231-249) -> chiI, plus the ion-feature sum  sum_i ioncf_i exp(-xii^2)
@@ -281,12 +342,12 @@ TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonO
   o.chiIr = o.chiIi = o.sion = 0.0;
   for (int i = 0; i < nI; i++) {
     double xii = L.inv_s2vTi[i] * q.w;
-    double ikldi2 = 1.0 / (L.c_kldi[i] * L.c_kldi[i] * q.k2);
+    double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;
     zprime_lerp(zt, xii, zr, zi, dzr, dzi);
     o.chiIr += -0.5 * ikldi2 * zr;
     o.chiIi += -0.5 * ikldi2 * zi;
-    o.sion += L.ioncf[i] * exp(-xii * xii);
+    o.sion += L.ioncf[i] * fast_exp_neg(-xii * xii);
   }
 }
 
@@ -302,9 +363,10 @@ TSFF_HD double assemble_forward(const LG& L, const Kin& q, const IonOut& io, dou
   s.eps2 = s.er * s.er + s.ei * s.ei;
   s.ce2 = chiEr * chiEr + chiEi * chiEi;
   s.a1 = (1.0 + io.chiIr) * (1.0 + io.chiIr) + io.chiIi * io.chiIi;
-  s.Sion = io.sion * s.ce2 * kInvSqrt2Pi / (q.k * s.eps2);
-  s.Sele = s.a1 * fphi / (q.k * L.vTe * s.eps2);
-  s.dop = 1.0 + 2.0 * q.omgdop / L.omgL;
+  const double ike = fast_rcp(q.k * s.eps2);
+  s.Sion = io.sion * s.ce2 * kInvSqrt2Pi * ike;
+  s.Sele = s.a1 * fphi * ike * fast_rcp(L.vTe);
+  s.dop = 1.0 + 2.0 * q.omgdop * fast_rcp(L.omgL);
   s.cP = kRe * kRe * omgs * omgs / (2.0 * kPi * kC);  // re^2 * 2 pi C / lams^2, lams = 2 pi C / omgs
   s.P = (s.Sion + s.Sele) * s.dop * L.ne_g * s.cP;
   return s.P;
@@ -328,18 +390,19 @@ TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q
   double Ssum_bar = Pbar * s.dop * L.ne_g * s.cP;
   double dop_bar = Pbar * Ssum * L.ne_g * s.cP;
   Lb.ne_g += Pbar * Ssum * s.dop * s.cP;
-  kb.omgdop += dop_bar * 2.0 / L.omgL;
-  Lb.omgL += -dop_bar * 2.0 * q.omgdop / (L.omgL * L.omgL);
+  const double iomgL = fast_rcp(L.omgL), ivTe = fast_rcp(L.vTe), ik = fast_rcp(q.k), ik2 = fast_rcp(q.k2);
+  kb.omgdop += dop_bar * 2.0 * iomgL;
+  Lb.omgL += -dop_bar * 2.0 * q.omgdop * iomgL * iomgL;
   // Sion = sion ce2 c / (k eps2)
-  double inv_keps = 1.0 / (q.k * s.eps2);
+  double inv_keps = fast_rcp(q.k * s.eps2);
   double sion_bar = Ssum_bar * s.ce2 * kInvSqrt2Pi * inv_keps;
   double ce2_bar = Ssum_bar * io.sion * kInvSqrt2Pi * inv_keps;
-  double eps2_bar = -Ssum_bar * Ssum / s.eps2;
-  kb.k += -Ssum_bar * Ssum / q.k;
+  double eps2_bar = -Ssum_bar * Ssum * (inv_keps * q.k);
+  kb.k += -Ssum_bar * Ssum * ik;
   // Sele = a1 fphi / (k vTe eps2)
-  double a1_bar = Ssum_bar * fphi * inv_keps / L.vTe;
-  pb.fphi = Ssum_bar * s.a1 * inv_keps / L.vTe;
-  Lb.vTe += -Ssum_bar * s.Sele / L.vTe;
+  double a1_bar = Ssum_bar * fphi * inv_keps * ivTe;
+  pb.fphi = Ssum_bar * s.a1 * inv_keps * ivTe;
+  Lb.vTe += -Ssum_bar * s.Sele * ivTe;
   double er_bar = 2.0 * s.er * eps2_bar, ei_bar = 2.0 * s.ei * eps2_bar;
   pb.chiEr = er_bar + 2.0 * chiEr * ce2_bar;
   pb.chiEi = ei_bar + 2.0 * chiEi * ce2_bar;
@@ -347,16 +410,16 @@ TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q
   double chiIi_bar = ei_bar + 2.0 * io.chiIi * a1_bar;
   for (int i = 0; i < nI; i++) {
     double xii = L.inv_s2vTi[i] * q.w;
-    double ikldi2 = 1.0 / (L.c_kldi[i] * L.c_kldi[i] * q.k2);
+    double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;
     zprime_lerp(zt, xii, zr, zi, dzr, dzi);
-    double E = exp(-xii * xii);
+    double E = fast_exp_neg(-xii * xii);
     Lb.ioncf[i] += sion_bar * E;
     double xii_bar = sion_bar * L.ioncf[i] * E * (-2.0 * xii);
     double ikldi2_bar = -0.5 * (zr * chiIr_bar + zi * chiIi_bar);
     xii_bar += -0.5 * ikldi2 * (dzr * chiIr_bar + dzi * chiIi_bar);
-    Lb.c_kldi[i] += ikldi2_bar * (-2.0 * ikldi2 / L.c_kldi[i]);
-    kb.k2 += -ikldi2_bar * ikldi2 / q.k2;
+    Lb.c_kldi[i] += ikldi2_bar * (-2.0 * ikldi2 * fast_rcp(L.c_kldi[i]));
+    kb.k2 += -ikldi2_bar * ikldi2 * ik2;
     Lb.inv_s2vTi[i] += xii_bar * q.w;
     kb.w += xii_bar * L.inv_s2vTi[i];
   }
@@ -364,28 +427,29 @@ TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q
 
 // reverse of kin_forward: consumes kb (incl. xie, ikl2 cotangents), accumulates LG cotangents
 TSFF_HD void kin_backward(const LG& L, double omgs, double cth, const Kin& q, KinBar kb, LG& Lb) {
+  const double ivTe = fast_rcp(L.vTe), ik = fast_rcp(q.k), ik2 = ik * ik;
   // ikl2 = omgpe2 / (vTe^2 k2)
-  Lb.omgpe2 += kb.ikl2 * q.ikl2 / L.omgpe2;
-  Lb.vTe += -2.0 * kb.ikl2 * q.ikl2 / L.vTe;
-  kb.k2 += -kb.ikl2 * q.ikl2 / q.k2;
+  Lb.omgpe2 += kb.ikl2 * q.ikl2 * fast_rcp(L.omgpe2);
+  Lb.vTe += -2.0 * kb.ikl2 * q.ikl2 * ivTe;
+  kb.k2 += -kb.ikl2 * q.ikl2 * ik2;
   // xie = (w - ud6)/vTe
-  kb.w += kb.xie / L.vTe;
-  Lb.ud6 += -kb.xie / L.vTe;
-  Lb.vTe += -kb.xie * q.xie / L.vTe;
+  kb.w += kb.xie * ivTe;
+  Lb.ud6 += -kb.xie * ivTe;
+  Lb.vTe += -kb.xie * q.xie * ivTe;
   // w = omgdop / k
-  kb.omgdop += kb.w / q.k;
-  kb.k += -kb.w * q.w / q.k;
+  kb.omgdop += kb.w * ik;
+  kb.k += -kb.w * q.w * ik;
   // omgdop = omgs - omgL - k Va6
   Lb.omgL += -kb.omgdop;
   kb.k += -kb.omgdop * L.Va6;
   Lb.Va6 += -kb.omgdop * q.k;
   // k = sqrt(k2)
-  kb.k2 += kb.k / (2.0 * q.k);
+  kb.k2 += kb.k * (0.5 * ik);
   // k2 = ks^2 + kL^2 - 2 ks kL cth
   double ks_bar = kb.k2 * (2.0 * q.ks - 2.0 * L.kL * cth);
   Lb.kL += kb.k2 * (2.0 * L.kL - 2.0 * q.ks * cth);
   // ks = sqrt(omgs^2 - omgpe2)/C
-  Lb.omgpe2 += -ks_bar / (2.0 * kC * kC * q.ks);
+  Lb.omgpe2 += -ks_bar * fast_rcp(2.0 * kC * kC * q.ks);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@ namespace tsff {
 
 constexpr int kPvThreads = 256;
 
+TSFF_HD size_t tree_prep_scratch_bytes(int npad) { return (size_t)(npad / kTS + npad / kTS2) * kTK * 2 * 8; }
+
 #if defined(__CUDACC__)
 // One bulk copy completed on an mbarrier, in pieces of at most 32 KB.  Called by all threads; one use per kernel.
 __device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -34,41 +36,82 @@ static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) 
   for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) out[i] = tree_static_entry(i, M);
 }
 
-// Per-lineout preparation, executed by one CTA (any block size that is a multiple of 32).  pget(i) -> p_i (FP64).
+// Per-lineout preparation, executed by one CTA.  p[0..M]: node values (FP64; shared or global memory).
 // Writes the lineout's blob (tree_blob layout) to global memory: weights, packed coefficients of both levels, leading
-// coefficients.  A warp owns one block at a time: the lanes split its nodes, the moments are summed by shuffles, lane 0
-// turns them into coefficients.
-template <typename PGet>
-__device__ __forceinline__ void tree_prep_cta(PGet pget, int M, int npad, unsigned char* blob, const double* tstat) {
+// coefficients.  All phases are spread over the whole CTA:
+//   1. level-1 moments  mu1[b][k] = sum_i p_i x_i^k           thread (b, k), static power table E1
+//   2. level-2 moments from the four children by translation  thread (B, k), static matrices T12
+//   3. coefficients A_m from the moments (+ end-node rows)    thread (block, m)
+//   4. packing into the Horner layout                          thread (block, q)
+// scratch: shared, (NB + NB2) * kTK * 2 doubles.  Ends with the CTA synchronised.
+__device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, unsigned char* blob, const double* tstat,
+                                              double* scratch) {
   const TreeBlob tb = tree_blob(npad);
+  const int NB = tb.NB, NB2 = tb.NB2, NT = NB + NB2;
+  double* mu = scratch;              // [NT][kTK]  (level 1 first)
+  double* A = scratch + NT * kTK;    // [NT][kTK]
   float* Wt = reinterpret_cast<float*>(blob + tb.oW);
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)pget(i) : 0.f;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int item = wid; item < tb.NB + tb.NB2; item += nw) {
-    const bool lvl2 = item >= tb.NB;
-    const int b = lvl2 ? item - tb.NB : item;
-    const int S = lvl2 ? kTS2 : kTS;
-    const double s = lvl2 ? kTs2 : kTs;
-    double mu[kTK];
-    tree_block_moments(pget, M, b, S, s, lane, 32, mu);
-#pragma unroll
-    for (int k = 0; k < kTK; k++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mu[k] += __shfl_xor_sync(0xffffffffu, mu[k], o);
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)p[i] : 0.f;
+  const double* E1 = tstat + kTsE1;
+  for (int it = threadIdx.x; it < NB * kTK; it += blockDim.x) {
+    const int b = it / kTK, k = it % kTK;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int o = 0; o < kTS; o++) {
+      const int i = kTS * b + o;
+      const double pv = (i >= 1 && i <= M - 1) ? p[i] : 0.0;
+      acc = fma(pv, E1[o * kTK + k], acc);
     }
-    if (lane == 0) {
-      double A[kTK], ld[2];
-      float4 ab[kTK / 2];
-      tree_coeffs_from_moments(pget, M, b, S, s, mu, tstat + (lvl2 ? kTsCM2 : kTsCM1), tstat + (lvl2 ? kTsQE2 : kTsQE1), A);
-      tree_pack(A, ab, ld);
-      float4* dst = reinterpret_cast<float4*>(blob + (lvl2 ? tb.oAB2 : tb.oAB1)) + b * (kTK / 2);
-#pragma unroll
-      for (int q = 0; q < kTK / 2; q++) dst[q] = ab[q];
+    mu[it] = acc;
+  }
+  __syncthreads();
+  const double* T12 = tstat + kTsT12;
+  for (int it = threadIdx.x; it < NB2 * kTK; it += blockDim.x) {
+    const int B = it / kTK, k = it % kTK;
+    double acc = 0.0;
+    for (int c = 0; c < 4; c++) {
+      const double* m1 = mu + (4 * B + c) * kTK;
+      const double* t = T12 + (c * kTK + k) * kTK;
+      for (int j = 0; j <= k; j++) acc = fma(t[j], m1[j], acc);
+    }
+    mu[NB * kTK + it] = acc;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < NT * kTK; it += blockDim.x) {
+    const int blk = it / kTK, m = it % kTK;
+    const bool lvl2 = blk >= NB;
+    const int b = lvl2 ? blk - NB : blk, S = lvl2 ? kTS2 : kTS;
+    const double s = lvl2 ? kTs2 : kTs;
+    const double* cm = tstat + (lvl2 ? kTsCM2 : kTsCM1);
+    const double* qe = tstat + (lvl2 ? kTsQE2 : kTsQE1);
+    const double* mb = mu + blk * kTK;
+    double a = 0.0;
+    for (int j = 0; 2 * j <= m; j++) a = fma(cm[m * (kTK / 2) + j], mb[m - 2 * j], a);
+    a /= s;
+    if (b == 0) a = fma(p[0], qe[m], a);
+    if (M >= S * b && M < S * (b + 1)) a = fma(p[M], qe[kTK + m], a);
+    A[it] = a;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < NT * (kTK / 2); it += blockDim.x) {
+    const int blk = it / (kTK / 2), q = it % (kTK / 2);
+    const bool lvl2 = blk >= NB;
+    const int b = lvl2 ? blk - NB : blk;
+    const double* Ab = A + blk * kTK;
+    const int m0 = 2 * q, m1 = 2 * q + 1;
+    float4 v;
+    v.x = m0 + 2 < kTK ? (float)Ab[m0 + 2] : 0.f;
+    v.y = (float)((double)(m0 + 1) * Ab[m0]);
+    v.z = m1 + 2 < kTK ? (float)Ab[m1 + 2] : 0.f;
+    v.w = (float)((double)(m1 + 1) * Ab[m1]);
+    reinterpret_cast<float4*>(blob + (lvl2 ? tb.oAB2 : tb.oAB1))[b * (kTK / 2) + q] = v;
+    if (q == 0) {
       double* dl = reinterpret_cast<double*>(blob + (lvl2 ? tb.oLD2 : tb.oLD1)) + 2 * b;
-      dl[0] = ld[0];
-      dl[1] = ld[1];
+      dl[0] = Ab[0];
+      dl[1] = Ab[1];
     }
   }
+  __syncthreads();
 }
 #endif
 
@@ -129,7 +172,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
       double I, dI;
       if (PREC == TSFF_PV_FP32) {
         const double* pn = a.pnodes + b * a.pnode_stride;
-        tree_near_exact(xi[r], a.z0, a.h, M, tp[r].wb0, [pn](int i) { return pn[i]; }, I, dI);
+        tree_near_exact(xi[r], a.z0, a.h, M, (int)(-tp[r].un), tp[r].wb0, [pn](int i) { return pn[i]; }, I, dI);
         I += accI[r] + nrI[r];
         dI += accJ[r] / (kTs * a.h) + accJ2[r] / (kTs2 * a.h) + nrJ[r] / a.h;
       } else {
@@ -339,19 +382,16 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   }
 }
 
-// Exact (FP64) adjoint contributions of one pole: the kNearHalf nodes either side of it, and an end node when its
+// Exact (FP64) adjoint contributions of one pole (nearest node n as split by tree_pole / pv_desc): the kNearHalf nodes
+// either side of it, and an end node when its
 // block lies in the pole's near window.  Atomically added to pnear[0..M].  Two extra contributions (ei0, ev0),
 // (ei1, ev1) to the same array (the lerp adjoint of the direct mode, which lands on nodes next to the pole) ride on the
 // same atomics when they fall on a node of the exact zone; pass ev = 0 to skip.
-__device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, int wb0,
+__device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double z0, double h, int nodes, int n, int wb0,
                                                   double* pnear, int ei0 = 0, double ev0 = 0.0, int ei1 = 0, double ev1 = 0.0) {
   const int M = nodes - 1;
-  double rn = rint((xi - z0) / h);
-  if (!(rn >= 0.0)) rn = 0.0;
-  if (rn > (double)M) rn = (double)M;
-  const int n = (int)rn;
   const int lo = max(1, n - kNearHalf), hi = min(M - 1, n + kNearHalf);
-  const double ih = 1.0 / h;
+  const double ih = fast_rcp(h);
   if (lo <= hi && Ibar != 0.0) {
     double pm = pv_phi(z0 + (double)(lo - 1) * h - xi), pc = pv_phi(z0 + (double)lo * h - xi);
     for (int i = lo; i <= hi; i++) {
@@ -378,8 +418,9 @@ __device__ __forceinline__ void pv_bwd_pole_exact(double xi, double Ibar, double
 }
 
 // descriptor of one pole for k_pv_nodes
-__device__ __forceinline__ float4 pv_desc(double xi, double Ibar, double z0, double h, int nodes, int npad, int& wb0) {
+__device__ __forceinline__ float4 pv_desc(double xi, double Ibar, double z0, double h, int nodes, int npad, int& n, int& wb0) {
   const TreePole t = tree_pole(xi, z0, h, nodes - 1, npad);
+  n = (int)(-t.un);
   wb0 = t.wb0;
   return make_float4(t.un, t.ndh, (float)Ibar, __int_as_float(t.wb0));
 }

@@ -102,7 +102,7 @@ __device__ __forceinline__ double grad_sm(const double* f, int n, double ih, int
 }
 
 // ---- prep -------------------------------------------------------------------------------------------------
-// dynamic smem: lnf[V] | slope[V] | ratmod[1024] | ratdf[1024]
+// dynamic smem: lnf[V] | slope[V] | ratmod[1024] | ratdf[1024] | tree_prep scratch
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
   for (int n = threadIdx.x; n < kXi1N; n += kThreads) s_p[n] = grad_sm(s_rat, kXi1N, ih, n);  // form_factor.py:264
   __syncthreads();
   const int M = a.nodes - 1;
-  tree_prep_cta([s_p](int i) { return s_p[i]; }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat);
+  tree_prep_cta(s_p, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat, s_p + kXi1N);
   for (int i = threadIdx.x; i < kXi1N; i += kThreads) {
     if (a.D64) a.D64[b * a.npad + i] = pv_weight(s_p, M, a.xi1_h, i);                  // FP64 validation path
     a.ratdf[b * kXi1N + i] = s_p[i];
@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a) {
   for (int p = threadIdx.x; p < kXi2N; p += kThreads) {
     const double xi = a.xi2[p];
     const double tb = a.Tbar[b * kXi2N + p];
-    int wb0;
-    a.desc[b * kXi2N + p] = pv_desc(xi, tb, a.xi1_0, a.xi1_h, a.nodes, a.npad, wb0);
-    pv_bwd_pole_exact(xi, tb, a.xi1_0, a.xi1_h, a.nodes, wb0, a.pnear + b * kXi1N);
+    int np, wb0;
+    a.desc[b * kXi2N + p] = pv_desc(xi, tb, a.xi1_0, a.xi1_h, a.nodes, a.npad, np, wb0);
+    pv_bwd_pole_exact(xi, tb, a.xi1_0, a.xi1_h, a.nodes, np, wb0, a.pnear + b * kXi1N);
   }
 }
 
@@ -420,7 +420,7 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   a.pend = (double*)(w + L.w_pend); a.ratdf = (double*)(w + L.w_ratdf);
   a.modl = modl_out; a.ff = ff_out;
   {
-    const size_t smem = (size_t)(2 * c->V + 2 * kXi1N) * 8;
+    const size_t smem = (size_t)(2 * c->V + 2 * kXi1N) * 8 + tree_prep_scratch_bytes(c->pv_npad);
     TSFF_SMEM_OPTIN(k_table_prep<T>);
     k_table_prep<T><<<(unsigned)B, kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_prep");

@@ -123,7 +123,11 @@ constexpr int kTsCM1 = (kTS + 2) * kTKA;
 constexpr int kTsQE1 = kTsCM1 + kTK * (kTK / 2);
 constexpr int kTsCM2 = kTsQE1 + 2 * kTK;
 constexpr int kTsQE2 = kTsCM2 + kTK * (kTK / 2);
-constexpr int kTreeStaticDoubles = kTsQE2 + 2 * kTK;
+//   E1  [kTS][kTK]        powers x^k of the level-1 in-block coordinate x = -(i - c)/s of the kTS offsets
+//   T12 [4][kTK][kTK]     moment translation child -> parent: mu2_k += sum_j T12[c][k][j] mu1_j(child c)
+constexpr int kTsE1 = kTsQE2 + 2 * kTK;
+constexpr int kTsT12 = kTsE1 + kTS * kTK;
+constexpr int kTreeStaticDoubles = kTsT12 + 4 * kTK * kTK;
 TSFF_HD double tree_static_entry(int i, int M) {
   const double c1 = 0.5 * (double)(kTS - 1), c2 = 0.5 * (double)(kTS2 - 1);
   if (i < kTsCM1) {
@@ -138,8 +142,27 @@ TSFF_HD double tree_static_entry(int i, int M) {
     return k < kTK ? tree_q_end(k, 0.0 - c1, false, kTs) : tree_q_end(k - kTK, (double)(M % kTS) - c1, true, kTs);
   }
   if (i < kTsQE2) return tree_cm((i - kTsCM2) / (kTK / 2), (i - kTsCM2) % (kTK / 2), kTs2);
-  const int k = i - kTsQE2;
-  return k < kTK ? tree_q_end(k, 0.0 - c2, false, kTs2) : tree_q_end(k - kTK, (double)(M % kTS2) - c2, true, kTs2);
+  if (i < kTsE1) {
+    const int k = i - kTsQE2;
+    return k < kTK ? tree_q_end(k, 0.0 - c2, false, kTs2) : tree_q_end(k - kTK, (double)(M % kTS2) - c2, true, kTs2);
+  }
+  if (i < kTsT12) {
+    const int o = (i - kTsE1) / kTK, k = (i - kTsE1) % kTK;
+    const double x = -((double)o - c1) / kTs;
+    double pw = 1.0;
+    for (int q = 0; q < k; q++) pw *= x;
+    return pw;
+  }
+  {
+    // x2 = (x1 - D)/4 with D = (c_child - c_parent)/s1 = 2 c - 3 for child c = 0..3:  x2^k = 4^-k sum_j C(k,j) (-D)^(k-j) x1^j
+    const int c = (i - kTsT12) / (kTK * kTK), k = ((i - kTsT12) / kTK) % kTK, j = (i - kTsT12) % kTK;
+    if (j > k) return 0.0;
+    const double D = 2.0 * (double)c - 3.0;
+    double v = tree_binom(k, j);
+    for (int q = 0; q < k - j; q++) v *= -D;
+    for (int q = 0; q < k; q++) v *= 0.25;
+    return v;
+  }
 }
 
 // Raw moments of block b of S nodes over the node subset {first, first+stride, ...} (a warp splits a block over its
@@ -197,10 +220,11 @@ struct TreePole {
   double gw;
 };
 TSFF_HD TreePole tree_pole(double xi, double z0, double h, int M, int npad) {
-  double r = rint((xi - z0) / h);
+  const double ih = fast_rcp(h);
+  double r = rint((xi - z0) * ih);
   if (!(r >= 0.0)) r = 0.0;  // also NaN
   if (r > (double)M) r = (double)M;
-  const double dh = -(xi - (z0 + r * h)) / h;
+  const double dh = -(xi - (z0 + r * h)) * ih;
   TreePole t;
   t.un = (float)(-r);
   t.ndh = (float)dh;
@@ -400,16 +424,13 @@ TSFF_HD_NOINLINE TreeAcc tree_near(const float* sW, const TreePole tp) {
 
 // Exact FP64 part of I and dI/dxi for one pole: the interior nodes with |i - n| <= kNearHalf, and an end node when its
 // block lies inside the pole's near window (otherwise the end node is part of that block's far expansion).
+// n = the pole's nearest node as split by tree_pole (n = -un): the FP32 near window masks exactly these nodes.
 template <typename PGet>
-TSFF_HD void tree_near_exact(double xi, double z0, double h, int M, int wb0, PGet pget, double& I, double& dI) {
-  double rn = rint((xi - z0) / h);
-  if (!(rn >= 0.0)) rn = 0.0;
-  if (rn > (double)M) rn = (double)M;
-  const int n = (int)rn;
+TSFF_HD void tree_near_exact(double xi, double z0, double h, int M, int n, int wb0, PGet pget, double& I, double& dI) {
   int lo = n - kNearHalf, hi = n + kNearHalf;
   if (lo < 1) lo = 1;
   if (hi > M - 1) hi = M - 1;
-  const double ih = 1.0 / h;
+  const double ih = fast_rcp(h);
   double sI = 0.0, sJ = 0.0;
   if (lo <= hi) {
     double gm = z0 + (double)(lo - 1) * h - xi;
@@ -431,14 +452,14 @@ TSFF_HD void tree_near_exact(double xi, double z0, double h, int M, int wb0, PGe
     const double l0 = log_abs(g0), l1 = log_abs(g0 + h);
     const double p0 = pget(0);
     sI += p0 * (((g0 + h) * l1 - g0 * l0) * ih - 1.0 - l0);
-    sJ += p0 * (-(l1 - l0) * ih + 1.0 / g0);
+    sJ += p0 * (-(l1 - l0) * ih + fast_rcp(g0));
   }
   if ((unsigned)(M / kTS - wb0) <= 2u) {
     const double gM = z0 + (double)M * h - xi;
     const double lM = log_abs(gM), lM1 = log_abs(gM - h);
     const double pM = pget(M);
     sI += pM * (((gM - h) * lM1 - gM * lM) * ih + 1.0 + lM);
-    sJ += pM * (-(lM1 - lM) * ih - 1.0 / gM);
+    sJ += pM * (-(lM1 - lM) * ih - fast_rcp(gM));
   }
   I = sI;
   dI = sJ;
