@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-lineouts", type=int, default=8)
     ap.add_argument("--warmup-ref", type=int, default=1)
-    ap.add_argument("--cpu-baseline-lineouts", type=int, default=32)
+    ap.add_argument("--cpu-baseline-lineouts", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -221,24 +221,51 @@ def main():
     eng.set_profile_events(None, None)
     tf, tb = tf / nprof, tb / nprof
 
-    # ---- leg 2: end to end through the public call with HOST buffers (H2D of inputs, D2H of loss + params_bar)
+    # ---- leg 2: end to end through the public call with HOST buffers: every step copies params + fe from pinned host
+    # memory and reads loss + params_bar back.  The batch is cut into chunks that alternate between two streams (each
+    # with its own engine = its own scratch), so the H2D copy of one chunk overlaps the kernels of the other.
+    NCH = 4 if B % 4 == 0 and B >= 64 else 1
+    Bc = B // NCH
     pbar_pin = torch.empty_like(params_pin).pin_memory()
-    loss_pin = torch.zeros(1, dtype=torch.float64).pin_memory()
-    p_in, f_in = torch.empty_like(params_d), torch.empty_like(fe_d)
+    loss_pin = torch.zeros(NCH, dtype=torch.float64).pin_memory()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    engs = [eng, FormFactorEngine(LAM_RANGE, W_SYN, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")]
+    ch = []
+    for c in range(NCH):
+        ch.append(dict(p=torch.empty((Bc, NP), dtype=torch.float64, device=dev), f=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev),
+                       saved=torch.empty(eng.saved_bytes(Bc), dtype=torch.uint8, device=dev), pbar=torch.empty((Bc, NP), dtype=torch.float64, device=dev),
+                       fbar=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev), loss=torch.zeros(1, dtype=torch.float64, device=dev),
+                       tgt=target[c * Bc:(c + 1) * Bc].contiguous()))
 
     def step_e2e():
-        p_in.copy_(params_pin, non_blocking=True)
-        f_in.copy_(fe_pin, non_blocking=True)
-        step(p_in, f_in)
-        pbar_pin.copy_(pbar, non_blocking=True)
-        loss_pin.copy_(loss, non_blocking=True)
+        for c in range(NCH):
+            st, e, k = streams[c % 2], engs[c % 2], ch[c]
+            with torch.cuda.stream(st):
+                k["p"].copy_(params_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
+                k["f"].copy_(fe_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
+                modl, _, _ = e.forward(k["p"], k["f"], saved=k["saved"])
+                _, tbar = loss_fwd_bwd(modl, k["tgt"], wq, unc, scale, "l2", loss_out=k["loss"], want_grad=True)
+                e.backward(k["p"], k["f"], k["saved"], modl_bar=tbar, params_bar=k["pbar"], fe_bar=k["fbar"])
+                pbar_pin[c * Bc:(c + 1) * Bc].copy_(k["pbar"], non_blocking=True)
+                loss_pin[c:c + 1].copy_(k["loss"], non_blocking=True)
 
-    step_e2e()
+    def e2e_region(nsteps):
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+        for _ in range(nsteps):
+            step_e2e()
+        for st in streams:
+            cur.wait_stream(st)
+        if world > 1:
+            tot = loss_pin.sum().to(dev)   # the scalar loss all-reduce of the sharded fit
+            dist.all_reduce(tot)
+
+    e2e_region(2)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(K):
-        step_e2e()
+    e2e_region(K)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -261,6 +288,17 @@ def main():
         nominal_tf = 148 * 128 * 2 * 1.965e9 / 1e12
         step_tf = value / world * PAIRS_PER_LINEOUT * FLOP_PER_PAIR_STEP / 1e12
         clocks = _parse_clocks(clk_path, local)
+        # per-launch DRAM traffic and executed pipe utilisation of the dominant kernel come from the committed ncu capture
+        # of this same command (profiles/ncu_latest.json, written by tools/ncu_summary.py json); scaled to this batch
+        traffic, executed = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_latest.json")))
+            traffic = prof["dram_bytes_per_launch"] * B / prof["lineouts_per_launch"]
+            executed = {k: prof[k] for k in ("kernel", "issue_slots_busy_pct", "fma_pipe_pct", "xu_pipe_pct", "fp64_pipe_pct")}
+            executed["thread_instructions_per_pole"] = prof["warp_instructions"] * 32 / (prof["lineouts_per_launch"] * W_SYN)
+            executed["source"] = prof["source"]
+        except Exception:
+            pass
         line = {
             "metric": "lineouts/sec (form-factor fwd+VJP)", "value": value, "unit": "lineouts/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
@@ -269,12 +307,15 @@ def main():
                        "lineouts_per_gpu": B, "pairs_per_lineout": PAIRS_PER_LINEOUT, "parallelism": f"lineouts x{world}",
                        "cache": f"working set {int((fe_d.numel()*4*2 + saved.numel() + B*W_SYN*8*3)/2**20)} MiB per step > 126 MiB L2"},
             "e2e": {"value": e2e_val, "unit": "lineouts/s", "h2d_bytes_per_step": int(params_pin.numel() * 8 + fe_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(pbar_pin.numel() * 8 + 8), "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": int(pbar_pin.numel() * 8 + 8 * NCH), "ms_per_step": ms_e2e / K,
+                    "pipeline": f"{NCH} chunks alternating on 2 streams (H2D of a chunk overlaps the kernels of the previous one)"},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "kernel": "k_direct_fwd (pole sweep: I and dI/dxi)", "achieved": fwd_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": fwd_tf / peak_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": fwd_tf / peak_tf, "traffic": traffic, "executed": executed,
+                "note": "achieved = ALGORITHMIC flops (12 per (omega,v) pair for I and dI/dxi, SURVEY 8d) / kernel time; the block-multipole "
+                        "sweep executes ~15x fewer instructions than that pairwise count, so frac may exceed 1: 'executed' (ncu) is the pipe view",
                 "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry); nominal %.1f" % nominal_tf,
                 "frac_of_nominal": fwd_tf / nominal_tf, "ms_per_launch": tf,
                 "mufu": {"achieved_gops": pairs / (tf * 1e-3) / 1e9, "peak_gops": mufu_peak / 1e9,

@@ -69,5 +69,34 @@ def raw(path):
         print()
 
 
+def tojson(path, kernel_regex, lineouts):
+    """python tools/ncu_summary.py json <raw.csv> <kernel regex> <lineouts per launch>  -> JSON for bench.py's roofline"""
+    import json, re
+    rows = list(csv.reader(open(path, errors="replace")))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        if re.search(kernel_regex, r[idx["Kernel Name"]]):
+            def val(m):
+                v = float(r[idx[m]].replace(",", ""))
+                u = units[idx[m]]
+                return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+            out = {"kernel": r[idx["Kernel Name"]].split("(")[0][-60:], "lineouts_per_launch": int(lineouts),
+                   "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                   "issue_slots_busy_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "fma_pipe_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "xu_pipe_pct": val("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                   "fp64_pipe_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "warp_instructions": val("smsp__inst_executed.sum"),
+                   "duration_us_under_ncu": val("gpu__time_duration.sum") * (1e-3 if units[idx["gpu__time_duration.sum"]] == "ns" else (1e3 if units[idx["gpu__time_duration.sum"]] == "ms" else 1.0)),
+                   "source": path}
+            print(json.dumps(out, indent=1))
+            return
+    raise SystemExit("kernel not found")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "json":
+        tojson(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])

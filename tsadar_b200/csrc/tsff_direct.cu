@@ -377,13 +377,13 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   TSFF_LAUNCH_OK("k_direct_prep");
   const int WA = c->W * c->A;
   const size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
-  // poles per thread: 4 (four independent Horner chains per thread) while the grid still fills the device, else 2 / 1
+  // poles per thread: 2 while the grid still fills the device, else 1 (4 poles/thread at 128 registers measured 7% slower)
   const long long tiles4 = (WA + 4 * kThreads - 1) / (4 * kThreads), tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
   if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
   if (c->pv_precision == TSFF_PV_FP64) {
     a.ntiles = (WA + kThreads - 1) / kThreads;
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
-  } else if ((long long)B * c->G * tiles4 >= 2LL * c->sm_count && !getenv("TSFF_FWD_R2")) {
+  } else if ((long long)B * c->G * tiles4 >= 2LL * c->sm_count && getenv("TSFF_FWD_R4")) {  // tuning switch: measured slower
     a.ntiles = (int)tiles4;
     TSFF_SMEM_OPTIN((k_direct_fwd<4, T, TSFF_PV_FP32, 2>));
     k_direct_fwd<4, T, TSFF_PV_FP32, 2><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);

@@ -16,7 +16,7 @@ namespace tsff {
 
 constexpr int kPvThreads = 256;
 
-TSFF_HD size_t tree_prep_scratch_bytes(int npad) { return (size_t)(npad / kTS + npad / kTS2) * kTK * 2 * 8; }
+TSFF_HD size_t tree_prep_scratch_bytes(int npad) { return ((size_t)(npad / kTS + npad / kTS2) * kTK * 2 + (size_t)kTS * kTK) * 8; }
 
 #if defined(__CUDACC__)
 // One bulk copy completed on an mbarrier, in pieces of at most 32 KB.  Called by all threads; one use per kernel.
@@ -43,26 +43,37 @@ static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) 
 //   2. level-2 moments from the four children by translation  thread (B, k), static matrices T12
 //   3. coefficients A_m from the moments (+ end-node rows)    thread (block, m)
 //   4. packing into the Horner layout                          thread (block, q)
-// scratch: shared, (NB + NB2) * kTK * 2 doubles.  Ends with the CTA synchronised.
+// scratch: shared, tree_prep_scratch_bytes(npad).  Ends with the CTA synchronised.
 __device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, unsigned char* blob, const double* tstat,
                                               double* scratch) {
   const TreeBlob tb = tree_blob(npad);
   const int NB = tb.NB, NB2 = tb.NB2, NT = NB + NB2;
   double* mu = scratch;              // [NT][kTK]  (level 1 first)
   double* A = scratch + NT * kTK;    // [NT][kTK]
+  double* E1 = A + NT * kTK;         // [kTS][kTK] staged copy of the static power table
   float* Wt = reinterpret_cast<float*>(blob + tb.oW);
+  for (int i = threadIdx.x; i < kTS * kTK; i += blockDim.x) E1[i] = tstat[kTsE1 + i];
   for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)p[i] : 0.f;
-  const double* E1 = tstat + kTsE1;
+  __syncthreads();
   for (int it = threadIdx.x; it < NB * kTK; it += blockDim.x) {
     const int b = it / kTK, k = it % kTK;
-    double acc = 0.0;
-#pragma unroll 8
-    for (int o = 0; o < kTS; o++) {
-      const int i = kTS * b + o;
-      const double pv = (i >= 1 && i <= M - 1) ? p[i] : 0.0;
-      acc = fma(pv, E1[o * kTK + k], acc);
+    const double* pb = p + kTS * b;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (b > 0 && kTS * (b + 1) <= M) {   // all 64 nodes interior
+#pragma unroll 4
+      for (int o = 0; o < kTS; o += 4) {
+        a0 = fma(pb[o], E1[o * kTK + k], a0);
+        a1 = fma(pb[o + 1], E1[(o + 1) * kTK + k], a1);
+        a2 = fma(pb[o + 2], E1[(o + 2) * kTK + k], a2);
+        a3 = fma(pb[o + 3], E1[(o + 3) * kTK + k], a3);
+      }
+    } else {
+      for (int o = 0; o < kTS; o++) {
+        const int i = kTS * b + o;
+        if (i >= 1 && i <= M - 1) a0 = fma(pb[o], E1[o * kTK + k], a0);
+      }
     }
-    mu[it] = acc;
+    mu[it] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   const double* T12 = tstat + kTsT12;
@@ -87,7 +98,7 @@ __device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, 
     const double* mb = mu + blk * kTK;
     double a = 0.0;
     for (int j = 0; 2 * j <= m; j++) a = fma(cm[m * (kTK / 2) + j], mb[m - 2 * j], a);
-    a /= s;
+    a *= 1.0 / s;   // s is a power of two
     if (b == 0) a = fma(p[0], qe[m], a);
     if (M >= S * b && M < S * (b + 1)) a = fma(p[M], qe[kTK + m], a);
     A[it] = a;
