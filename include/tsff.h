@@ -141,6 +141,31 @@ int tsff_irf_fwd(const tsff_irf_cfg* cfg, int64_t B, const double* modl, const d
 int tsff_irf_bwd(const tsff_irf_cfg* cfg, int64_t B, const double* params, int32_t NP, const double* amps,
                  const void* saved, const double* thry_bar, double* modl_bar, double* amp_bar, void* ws, void* stream);
 
+/* ---- B4 (ARTS): angular instrument response + reduction to resolution units ------------------------------------ */
+/* replaces irf.add_ATS_IRF (irf.py:5-47, norm == 0) followed by ThomsonScatteringDiagnostic.reduce_ATS_to_resunit and
+ * the noise add (thomson_diagnostic.py:78-107, 139) for spectype "angular_full":
+ *   modl [NA][W] (= weights @ formfactor^T, generate_spectra.py:194-195)  ->  thry [row_end-row_start][ceil(W/lam_step)]
+ * taps_ang [NA], taps_lam [W]: DEVICE arrays with the reference's full-length Gaussian tap vectors (irf.py:26-33);
+ * only indices [t0, t1] are visited (the caller truncates where the taps are negligible). */
+typedef struct tsff_ats_cfg {
+  int32_t NA, W;             /* angle rows (1024), wavelength samples (npts) */
+  int32_t lam_step, ang_step; /* round(W / e_data.shape[1]), round(NA / CCDsize[0])   (thomson_diagnostic.py:93-94) */
+  int32_t row_start, row_end; /* data.lineouts.start / end, in angle units          (thomson_diagnostic.py:101) */
+  int32_t norm, reserved;    /* PhysParams.norm (must be 0) */
+  int32_t ang_t0, ang_t1, lam_t0, lam_t1; /* tap supports, inclusive */
+  double lam_min, lam_max;   /* wavelength axis linspace(lam_min, lam_max, W) in nm */
+  const double* taps_ang;    /* device [NA] */
+  const double* taps_lam;    /* device [W] */
+} tsff_ats_cfg;
+size_t tsff_ats_saved_bytes(const tsff_ats_cfg* cfg);
+size_t tsff_ats_workspace_bytes(const tsff_ats_cfg* cfg);
+/* params: one row [NP] (uses lam, amp1, amp2), e_amps [rows], noise [rows][units] or NULL */
+int tsff_ats_fwd(const tsff_ats_cfg* cfg, const double* modl, const double* params, const double* e_amps,
+                 const double* noise, double* thry, void* saved, void* ws, void* stream);
+/* VJP: thry_bar -> modl_bar [NA][W], amp_bar [2] (cotangents of amp1, amp2) */
+int tsff_ats_bwd(const tsff_ats_cfg* cfg, const double* params, const double* e_amps, const void* saved,
+                 const double* thry_bar, double* modl_bar, double* amp_bar, void* ws, void* stream);
+
 /* ---- B5: loss -------------------------------------------------------------------------------------------------- */
 /* replaces LossFunction.calc_ei_error + loss_functionals (loss_function.py:190-267, 386-418) and the seed of the
  * reverse pass: loss += scale * sum_{b,q} weight[q] * err(data, theory), theory_bar = d loss / d theory.

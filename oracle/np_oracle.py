@@ -383,6 +383,57 @@ def diagnostic_1d(params_list, cfg, sa, batch, mode="table"):
 
 
 # --------------------------------------------------------------------------------------
+# a8/a9 (ARTS): irf.add_ATS_IRF (irf.py:5-47) and reduce_ATS_to_resunit (thomson_diagnostic.py:78-107)
+# --------------------------------------------------------------------------------------
+def ats_taps(axis, fwhm):
+    """Gaussian instrument function sampled on `axis`, centred at mid-axis (irf.py:22-33)."""
+    stddev = fwhm / 2.3548
+    origin = (np.amax(axis) + np.amin(axis)) / 2.0
+    return np.squeeze((1.0 / (stddev * np.sqrt(2.0 * np.pi))) * np.exp(-((axis - origin) ** 2.0) / (2.0 * stddev**2.0)))
+
+
+def add_ats_irf(lamAxisE, angAxis, modlE, spect_fwhm, ang_fwhm, norm=0):
+    """add_ATS_IRF (irf.py:5-47): modlE [NA, W] -> ThryE [NA, W]."""
+    inst_lam = ats_taps(lamAxisE, spect_fwhm)
+    inst_ang = ats_taps(angAxis, ang_fwhm)
+    ThryE = np.array([np.convolve(modlE[:, i], inst_ang, "same") for i in range(modlE.shape[1])])  # :34 -> [W, NA]
+    ThryE = np.array([np.convolve(ThryE[:, i], inst_lam, "same") for i in range(ThryE.shape[1])])  # :36 -> [NA, W]
+    ThryE = np.amax(modlE, axis=1, keepdims=True) / np.amax(ThryE, axis=1, keepdims=True) * ThryE   # :39
+    if norm > 0:
+        raise NotImplementedError("PhysParams.norm > 0: not used by any reference deck")
+    return lamAxisE, ThryE
+
+
+def reduce_ats_to_resunit(ThryE, lamAxisE, lam, amp1, amp2, e_amps, n_lam_data, ccd0, row_start, row_end):
+    """reduce_ATS_to_resunit (thomson_diagnostic.py:78-107)."""
+    lam_step = round(ThryE.shape[1] / n_lam_data)   # :93
+    ang_step = round(ThryE.shape[0] / ccd0)          # :94
+    ThryE = np.array([np.average(ThryE[:, i:i + lam_step], axis=1) for i in range(0, ThryE.shape[1], lam_step)])
+    ThryE = np.array([np.average(ThryE[:, i:i + ang_step], axis=1) for i in range(0, ThryE.shape[1], ang_step)])
+    lamAxisE = np.array([np.average(lamAxisE[i:i + lam_step], axis=0) for i in range(0, lamAxisE.shape[0], lam_step)])
+    ThryE = ThryE[row_start:row_end, :]
+    ThryE = e_amps * ThryE / np.amax(ThryE, axis=1, keepdims=True)
+    ThryE = np.where(lamAxisE < lam, amp1 * ThryE, amp2 * ThryE)
+    return ThryE, lamAxisE
+
+
+def diagnostic_arts(params, cfg, sa, batch, mode="table"):
+    """ThomsonScatteringDiagnostic.__call__ for spectype "angular_full" (thomson_diagnostic.py:109-142): one parameter
+    set, one image.  sa = {"sa": deg[241], "weights": [1024, 241], "angAxis": [1024]}."""
+    oth = cfg["other"]
+    G = cfg["parameters"]["general"]["Te_gradient"]["num_grad_points"]
+    gE = Grids(oth["lamrangE"], oth["npts"])
+    lamE, modlE = fit_model_electron(params, gE, sa, oth, G, cfg["data"]["ele_lam_shift"], mode, angular_full=True)
+    wid = oth["PhysParams"]["widIRF"]
+    lamE, ThryE = add_ats_irf(lamE, sa["angAxis"], modlE, wid["spect_FWHM_ele"], wid["ang_FWHM_ele"], oth["PhysParams"]["norm"])
+    gen = params["general"]
+    ThryE, lamE = reduce_ats_to_resunit(ThryE, lamE, float(gen["lam"]), float(gen["amp1"]), float(gen["amp2"]),
+                                        np.asarray(batch["e_amps"]), np.asarray(batch["e_data"]).shape[1], oth["CCDsize"][0],
+                                        cfg["data"]["lineouts"]["start"], cfg["data"]["lineouts"]["end"])
+    return ThryE + np.asarray(batch["noise_e"]), lamE, modlE
+
+
+# --------------------------------------------------------------------------------------
 # a10: loss (loss_function.py:190-267, 269-342, 364-373, 386-418)
 # --------------------------------------------------------------------------------------
 def loss_functionals(d, t, uncert, method="l2"):

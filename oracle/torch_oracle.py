@@ -222,3 +222,27 @@ def loss_electron(ThryE, lamb, e_data, cfg, e_norm=1.0):
         if ex["fit_EPWb"]:
             tot = tot * 0.5
     return tot
+
+
+def _conv_same(x, v):
+    """np.convolve(x, v, "same") for equal lengths, along the last axis of x [rows, n]."""
+    n = x.shape[-1]
+    full = torch.nn.functional.conv1d(x.reshape(-1, 1, n), v.flip(0).reshape(1, 1, -1), padding=n - 1)
+    return full[:, 0, (n - 1) // 2:(n - 1) // 2 + n].reshape(x.shape)
+
+
+def ats_chain(modlE, lamAxisE, angAxis, spect_fwhm, ang_fwhm, lam, amp1, amp2, e_amps, n_lam_data, ccd0, row_start, row_end):
+    """np_oracle.add_ats_irf + reduce_ats_to_resunit (irf.py:5-47, thomson_diagnostic.py:78-107) with autograd."""
+    from . import np_oracle as O
+    inst_lam, inst_ang = T(O.ats_taps(np.asarray(lamAxisE), spect_fwhm)), T(O.ats_taps(np.asarray(angAxis), ang_fwhm))
+    y = _conv_same(modlE.t().contiguous(), inst_ang).t()      # along the angle axis
+    y = _conv_same(y.contiguous(), inst_lam)                  # along wavelength
+    y = modlE.max(dim=1, keepdim=True).values / y.max(dim=1, keepdim=True).values * y
+    NA, W = y.shape
+    lam_step, ang_step = round(W / n_lam_data), round(NA / ccd0)
+    y = torch.stack([y[:, i:i + lam_step].mean(dim=1) for i in range(0, W, lam_step)])            # [nl, NA]
+    y = torch.stack([y[:, i:i + ang_step].mean(dim=1) for i in range(0, NA, ang_step)])           # [na, nl]
+    lamb = T(np.array([np.average(np.asarray(lamAxisE)[i:i + lam_step]) for i in range(0, W, lam_step)]))
+    y = y[row_start:row_end]
+    y = T(e_amps).reshape(-1, 1) * y / y.max(dim=1, keepdim=True).values
+    return torch.where(lamb < lam, amp1 * y, amp2 * y), lamb

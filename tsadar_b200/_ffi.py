@@ -20,6 +20,7 @@ EXPORTS = [
     "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd",
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
+    "tsff_ats_saved_bytes", "tsff_ats_workspace_bytes", "tsff_ats_fwd", "tsff_ats_bwd",
 ]
 
 
@@ -40,6 +41,16 @@ class IrfCfg(C.Structure):
     _fields_ = [
         ("W", C.c_int32), ("nbins", C.c_int32), ("norm", C.c_int32), ("kind", C.c_int32),
         ("lam_min", C.c_double), ("lam_max", C.c_double), ("stddev", C.c_double), ("cut_sigma", C.c_double),
+    ]
+
+
+class AtsCfg(C.Structure):
+    _fields_ = [
+        ("NA", C.c_int32), ("W", C.c_int32), ("lam_step", C.c_int32), ("ang_step", C.c_int32),
+        ("row_start", C.c_int32), ("row_end", C.c_int32), ("norm", C.c_int32), ("reserved", C.c_int32),
+        ("ang_t0", C.c_int32), ("ang_t1", C.c_int32), ("lam_t0", C.c_int32), ("lam_t1", C.c_int32),
+        ("lam_min", C.c_double), ("lam_max", C.c_double),
+        ("taps_ang", C.c_void_p), ("taps_lam", C.c_void_p),
     ]
 
 
@@ -89,6 +100,14 @@ def lib():
     L.tsff_irf_fwd.restype = C.c_int
     L.tsff_irf_bwd.argtypes = [C.POINTER(IrfCfg), i64, dp, C.c_int32, dp, vp, dp, dp, dp, vp, vp]
     L.tsff_irf_bwd.restype = C.c_int
+    L.tsff_ats_saved_bytes.argtypes = [C.POINTER(AtsCfg)]
+    L.tsff_ats_saved_bytes.restype = C.c_size_t
+    L.tsff_ats_workspace_bytes.argtypes = [C.POINTER(AtsCfg)]
+    L.tsff_ats_workspace_bytes.restype = C.c_size_t
+    L.tsff_ats_fwd.argtypes = [C.POINTER(AtsCfg), dp, dp, dp, dp, dp, vp, vp, vp]
+    L.tsff_ats_fwd.restype = C.c_int
+    L.tsff_ats_bwd.argtypes = [C.POINTER(AtsCfg), dp, dp, vp, dp, dp, dp, vp, vp]
+    L.tsff_ats_bwd.restype = C.c_int
     L.tsff_loss_fwd_bwd.argtypes = [i64, C.c_int32, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, vp]
     L.tsff_loss_fwd_bwd.restype = C.c_int
     _lib = L

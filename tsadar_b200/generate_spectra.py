@@ -1,11 +1,14 @@
-"""FitModel -- mirror of tsadar.core.physics.generate_spectra.FitModel (generate_spectra.py:8-220) for the
-temporal / imaging / 1d spectypes (1V distributions).  The mean over gradient points, the weighted angle sum and the
-IAW filter are fused into the form-factor kernel (`modl` output of tsff_ff_fwd)."""
+"""FitModel -- mirror of tsadar.core.physics.generate_spectra.FitModel (generate_spectra.py:8-220) for 1V distributions.
+Temporal / imaging / 1d spectypes: the mean over gradient points, the weighted angle sum and the IAW filter are fused
+into the form-factor kernel (`modl` output of tsff_ff_fwd).  "angular_full" (ARTS): the kernel returns the full
+formfactor [G, W, A]; the angular weight matrix product (generate_spectra.py:194-195) is a plain FP64 GEMM (cuBLAS via
+torch.matmul) followed by the IAW filter."""
 from __future__ import annotations
 
 import numpy as np
+import torch
 
-from .form_factor import FormFactor
+from .form_factor import FormFactor, pack_params
 
 
 class FitModel:
@@ -26,9 +29,15 @@ class FitModel:
                                           num_grad_points=G, va_ang=None, ud_ang=None, mode=mode, pv_precision=pv_precision)
         # `weights[0]`: a scalar when `sa` comes straight from get_scattering_angles (tests, forward mode), the per-angle
         # vector after lineouts.py:103.  Both are "one weight per angle" for the kernel.
-        w0 = np.asarray(scattering_angles["weights"])[0]
+        self.angular_full = config["other"]["extraoptions"]["spectype"] == "angular_full"
         nA = np.asarray(scattering_angles["sa"]).size
-        self._w = np.full(nA, float(w0)) if np.ndim(w0) == 0 else np.asarray(w0, dtype=np.float64)
+        if self.angular_full:
+            self._wmat = np.asarray(scattering_angles["weights"], dtype=np.float64)   # [1024, A]
+            assert self._wmat.ndim == 2 and self._wmat.shape[1] == nA
+            self._w = np.ones(nA)
+        else:
+            w0 = np.asarray(scattering_angles["weights"])[0]
+            self._w = np.full(nA, float(w0)) if np.ndim(w0) == 0 else np.asarray(w0, dtype=np.float64)
         lamE = np.linspace(oth["lamrangE"][0], oth["lamrangE"][1], oth["npts"])
         self._jmulE = None
         if oth.get("iawoff", 0):
@@ -47,6 +56,22 @@ class FitModel:
         return np.zeros(1), 0, None
 
     def electron_spectrum(self, all_params):
+        if self.config["other"]["extraoptions"]["load_ele_spec"] and self.angular_full:
+            ff, _ = self.electron_form_factor(all_params)                       # [G, W, A] (one parameter set per image)
+            if ff.dim() == 4:
+                assert ff.shape[0] == 1, "angular_full takes a single parameter set (thomson_diagnostic.py:37-38)"
+                ff = ff[0]
+            dev = ff.device
+            ThryE = ff.mean(dim=0)                                               # generate_spectra.py:193
+            wm = getattr(self, "_wmat_dev", None)
+            if wm is None or wm.device != dev:
+                wm = self._wmat_dev = torch.tensor(self._wmat, dtype=torch.float64, device=dev)
+            modlE = torch.matmul(wm, ThryE.t())                                  # :194-195  [1024, W]
+            if self._jmulE is not None:
+                modlE = modlE * torch.tensor(self._jmulE, dtype=torch.float64, device=dev)   # :210-216
+            block, _, _, _, _ = pack_params(all_params, dev)
+            lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
+            return lamE, modlE, block
         if self.config["other"]["extraoptions"]["load_ele_spec"]:
             modlE, block = self.electron_form_factor.modl(all_params, self._w, jmul=self._jmulE)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])

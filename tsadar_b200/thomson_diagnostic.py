@@ -1,10 +1,15 @@
-"""ThomsonScatteringDiagnostic -- mirror of tsadar.core.thomson_diagnostic (thomson_diagnostic.py:10-142) for the
-temporal / imaging / 1d spectypes: FitModel + instrument response + noise, batched over lineouts."""
+"""ThomsonScatteringDiagnostic -- mirror of tsadar.core.thomson_diagnostic (thomson_diagnostic.py:10-142): FitModel +
+instrument response + noise.  Temporal / imaging / 1d spectypes are batched over lineouts; "angular_full" (ARTS, 1V
+distributions) is one parameter set for one image: weight-matrix product, 2-D instrument response, reduction to
+resolution units (tsadar_b200/ats.py)."""
 from __future__ import annotations
 
 import torch
 
+import numpy as np
+
 from . import irf
+from .ats import AtsStage
 from .generate_spectra import FitModel
 
 
@@ -18,9 +23,11 @@ class ThomsonScatteringDiagnostic:
         self.cfg = cfg
         self.scattering_angles = scattering_angles
         st = cfg["other"]["extraoptions"]["spectype"]
-        if not ("temporal" in st or "imaging" in st or "1d" in st):
-            raise NotImplementedError(f"spectype {st}: only the vmapped 1V spectypes are built (DESIGN.md: scope)")
+        self.angular = "angular" in st
+        if not ("temporal" in st or "imaging" in st or "1d" in st or st == "angular_full"):
+            raise NotImplementedError(f"spectype {st}: not built (DESIGN.md: scope)")
         self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision)
+        self._ats = None
 
     def __call__(self, ts_params, batch):
         """-> ThryE [B,1024], ThryI [B,1024], lamAxisE, lamAxisI   (thomson_diagnostic.py:109-142)"""
@@ -28,6 +35,8 @@ class ThomsonScatteringDiagnostic:
         oth = self.cfg["other"]
         ex = oth["extraoptions"]
         dev = torch.device("cuda", torch.cuda.current_device())
+        if self.angular:
+            return self._call_angular(physical_params, batch, dev)
         ThryE = ThryI = 0
         lamAxisE, lamAxisI = [], []
         if ex["load_ion_spec"]:
@@ -49,3 +58,23 @@ class ThomsonScatteringDiagnostic:
         if t.numel() == 1 and float(t.reshape(-1)[0]) == 0.0:
             return None
         return t.expand(B, nbins).contiguous() if t.dim() < 2 or t.shape != (B, nbins) else t.contiguous()
+
+    def _call_angular(self, physical_params, batch, dev):
+        """spectype "angular_full" (thomson_diagnostic.py:131-142 with :58-61, 136-137): electron spectrum only."""
+        oth = self.cfg["other"]
+        if oth["extraoptions"]["load_ion_spec"]:
+            raise NotImplementedError("angular_full with an ion spectrum: no reference deck does this")
+        lamE, modlE, block = self.model.electron_spectrum(physical_params)
+        n_lam_data = np.asarray(batch["e_data"]).shape[1]
+        if self._ats is None:
+            self._ats = AtsStage(self.cfg, self.scattering_angles, oth["lamrangE"], oth["npts"], n_lam_data, device=dev.index)
+        st = self._ats
+        ea = np.asarray(batch["e_amps"], dtype=np.float64).reshape(-1)
+        ea = np.full(st.nrows, ea[0]) if ea.size == 1 else ea[:st.nrows]
+        e_amps = torch.as_tensor(ea.copy(), dtype=torch.float64, device=dev)
+        noise = np.asarray(batch["noise_e"], dtype=np.float64)
+        noise_t = None
+        if not (noise.size == 1 and float(noise.reshape(-1)[0]) == 0.0):
+            noise_t = torch.as_tensor(np.broadcast_to(noise, (st.nrows, st.nl)).copy(), dtype=torch.float64, device=dev)
+        ThryE = st(modlE, block, e_amps, noise_t)
+        return ThryE, 0, st.lam_units, []
