@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TSFF_ABI_VERSION 1
+#define TSFF_ABI_VERSION 2
 #define TSFF_MAX_IONS 4
 
 enum {
@@ -47,8 +47,11 @@ enum {
   TSFF_MODE_TABLE = 0, /* FormFactor.__call__ (form_factor.py:163-298): f resampled on xi1 (1024), PV table on the
                           fixed grid xi2 (1640) via ratintn, lerped to xi_e; Im chi_e from the forward difference
                           of exp(cubic(log f)) along omega */
-  TSFF_MODE_DIRECT = 1 /* calc_chi_vals semantics (form_factor.py:369-388) on a given 1-D table: pole = xi_e,
+  TSFF_MODE_DIRECT = 1, /* calc_chi_vals semantics (form_factor.py:369-388) on a given 1-D table: pole = xi_e,
                           nodes = the f grid, gradient/lerp of f;  the synthetic-sweep workload of SURVEY.md 8(d) */
+  TSFF_MODE_2V = 2     /* FormFactor.calc_in_2D (form_factor.py:449-587): fe is a 2-D table [V][V] (float64) on vx x vx,
+                          rotated / projected per pole (rotate :300-324, calc_chi_vals :349-388).  Forward only so far:
+                          tsff_ff_fwd with ff_out; tsff_ff_bwd returns TSFF_E_INVALID */
 };
 enum { TSFF_F32 = 0, TSFF_F64 = 1 };
 /* precision of the PV inner loop */
@@ -72,6 +75,7 @@ typedef struct tsff_static_cfg {
   const double* zp_im;     /* host [zp_n] */
   int32_t zp_n;
   int32_t reserved;
+  double ud_angle_deg, va_angle_deg; /* FormFactor(ud_ang=..., va_ang=...): directions of drift and flow, 2V mode (form_factor.py:501-504) */
 } tsff_static_cfg;
 
 /* ---- context ------------------------------------------------------------------------------------------ */

@@ -268,6 +268,137 @@ def form_factor_direct(params, grids, sa_deg, num_grad_points=1, lam_shift=0.0, 
 
 
 # --------------------------------------------------------------------------------------
+# a5/a6: FormFactor.calc_in_2D (form_factor.py:449-587), rotate (:300-324), calc_chi_vals (:349-388)
+# PARITY UNPINNED: the reference golden for this path (ThryE-arts2v.npy) is a missing blob and interpax's bicubic
+# interp2d(..., extrap=True) is restated from its published algorithm (tensor-product cubic Hermite, node derivatives
+# fx, fy, fxy from the same 3-point rule as the 1-D "cubic" method, edge cell evaluated outside the grid).
+# --------------------------------------------------------------------------------------
+def _hermite_node_weights(xq, x):
+    """1-D cubic (interpax "cubic") as explicit weights on 4 nodes: returns idx [n,4], w [n,4] such that
+    interp1d_cubic(xq, x, f, extrap=True) == sum_k w[:,k] f[idx[:,k]] (uniform or non-uniform grid)."""
+    xq = np.asarray(xq, dtype=np.float64)
+    n = len(x)
+    i = np.clip(np.searchsorted(x, xq, side="right"), 1, n - 1)
+    dx = x[i] - x[i - 1]
+    t = (xq - x[i - 1]) / dx
+    h00, h01 = 2 * t**3 - 3 * t**2 + 1, -2 * t**3 + 3 * t**2
+    h10, h11 = (t**3 - 2 * t**2 + t) * dx, (t**3 - t**2) * dx
+    idx = np.stack([i - 2, i - 1, i, i + 1], axis=1)
+    w = np.zeros((len(xq), 4))
+    w[:, 1] += h00
+    w[:, 2] += h01
+    # slope at node k = i-1 (weights h10) and k = i (weights h11): mean of adjacent secants, one-sided at the ends
+    for col, k, h in ((1, i - 1, h10), (2, i, h11)):
+        left, right = k == 0, k == n - 1
+        interior = ~(left | right)
+        kk = np.clip(k, 1, n - 2)
+        sl = 1.0 / (x[kk] - x[kk - 1])
+        sr = 1.0 / (x[kk + 1] - x[kk])
+        # m_k = 0.5 * ((f_k - f_{k-1}) sl + (f_{k+1} - f_k) sr)
+        w[:, col - 1] += np.where(interior, -0.5 * sl * h, 0.0)
+        w[:, col] += np.where(interior, 0.5 * (sl - sr) * h, 0.0)
+        w[:, col + 1] += np.where(interior, 0.5 * sr * h, 0.0)
+        # left end: m_0 = (f_1 - f_0)/(x_1 - x_0)   (k = i-1 = 0 -> columns 1, 2)
+        s0 = 1.0 / (x[1] - x[0])
+        w[:, col] += np.where(left, -s0 * h, 0.0)
+        w[:, col + 1] += np.where(left, s0 * h, 0.0)
+        # right end: m_{n-1} = (f_{n-1} - f_{n-2})/(...)   (k = i = n-1 -> columns 1, 2)
+        s1 = 1.0 / (x[n - 1] - x[n - 2])
+        w[:, col - 1] += np.where(right, -s1 * h, 0.0)
+        w[:, col] += np.where(right, s1 * h, 0.0)
+    return np.clip(idx, 0, n - 1), w
+
+
+def interp2d_cubic(xq, yq, x, y, f):
+    """interpax.interp2d(xq, yq, x, y, f, method="cubic", extrap=True) (call site form_factor.py:324): f[i, j] = f(x_i, y_j)."""
+    ix, wx = _hermite_node_weights(xq, x)
+    iy, wy = _hermite_node_weights(yq, y)
+    out = np.zeros(len(xq))
+    for a in range(4):
+        for b in range(4):
+            out += wx[:, a] * wy[:, b] * f[ix[:, a], iy[:, b]]
+    return out
+
+
+def rotate(vx, df, angle_deg):
+    """FormFactor.rotate (form_factor.py:300-324)."""
+    rad = np.deg2rad(-angle_deg)
+    c, s = np.cos(rad), np.sin(rad)
+    R = np.array([[c, -s], [s, c]])
+    _vx, _vy = np.meshgrid(vx, vx)
+    coords = np.stack((_vx.flatten(), _vy.flatten()))
+    rc = np.einsum("ij, ik->kj", R, coords)
+    return interp2d_cubic(rc[:, 0], rc[:, 1], vx, vx, df).reshape((vx.size, vx.size), order="F")
+
+
+def calc_chi_vals_2d(vx, DF, beta, xie_mag, klde_mag):
+    """calc_chi_vals (form_factor.py:349-388) for one pole."""
+    dvx = vx[1] - vx[0]
+    fe_2D_k = rotate(vx, DF, beta * 180 / np.pi)       # :370
+    fe_1D_k = np.sum(fe_2D_k, axis=0) * dvx             # :371
+    df = np.gradient(fe_1D_k, dvx)                      # :372
+    fe_vphi = np.interp(xie_mag, vx, fe_1D_k)           # :376
+    dfe = np.interp(xie_mag, vx, df)                    # :377
+    chiEI = np.pi / (klde_mag**2) * dfe                 # :381
+    chiERrat = -1.0 / (klde_mag**2) * ratintn(df[None, :], (vx - xie_mag)[None, :], vx)[0]   # :385-386
+    return fe_vphi, chiEI, chiERrat, fe_1D_k
+
+
+def form_factor_2d(params, grids, sa_deg, num_grad_points=1, lam_shift=0.0, ud_ang=0.0, va_ang=0.0, return_parts=False):
+    """FormFactor.calc_in_2D (form_factor.py:449-587).  params["electron"]["fe"] is the 2-D table DF[V, V] on vx x vx."""
+    G = num_grad_points
+    gen, ele = params["general"], params["electron"]
+    ne = 1.0e20 * float(ele["ne"]) * np.linspace(1 - float(gen["ne_gradient"]) / 200, 1 + float(gen["ne_gradient"]) / 200, G)
+    Te = float(ele["Te"]) * np.linspace(1 - float(gen["Te_gradient"]) / 200, 1 + float(gen["Te_gradient"]) / 200, G)
+    lam = float(gen["lam"]) + lam_shift
+    A, Z, Ti, fract = _ion_lists(params)
+    Va = float(gen["Va"]) * 1e6
+    ud = float(gen["ud"]) * 1e6
+    DF = np.squeeze(np.asarray(ele["fe"], dtype=np.float64))
+    vx = np.asarray(ele["v"], dtype=np.float64).reshape(-1)
+    Mi = A * MP
+    Esq = ME * C**2 * RE
+    constants = np.sqrt(4 * np.pi * Esq / ME)
+    sarad = (np.asarray(sa_deg, dtype=np.float64) * np.pi / 180).reshape(1, 1, -1)
+    Va = (Va * np.cos(va_ang * np.pi / 180), Va * np.sin(va_ang * np.pi / 180))      # :501
+    ud = (ud * np.cos(ud_ang * np.pi / 180), ud * np.sin(ud_ang * np.pi / 180))      # :504
+    omgL = grids.omgL_num / lam
+    omgpe = constants * np.sqrt(ne[:, None, None])
+    omgs = grids.omgs
+    omg = omgs - omgL
+    kLx = np.sqrt(omgL**2 - omgpe**2) / C                                              # :512 (y component 0)
+    ks_mag = np.sqrt(omgs**2 - omgpe**2) / C
+    kx, ky = np.cos(sarad) * ks_mag - kLx, np.sin(sarad) * ks_mag + 0.0 * kLx          # :513-515
+    k_mag = np.sqrt(kx * kx + ky * ky)
+    omgdop = omg - (kx * Va[0] + ky * Va[1])                                           # :519
+    vTe = np.sqrt(Te[:, None, None] / ME)
+    klde_mag = (vTe / omgpe) * k_mag
+    Z4, Mi4, fr4 = Z.reshape(1, 1, 1, -1), Mi.reshape(1, 1, 1, -1), fract.reshape(1, 1, 1, -1)
+    Zbar = np.sum(Z4 * fr4)
+    ni = fr4 * ne[:, None, None, None] / Zbar
+    omgpi = constants * Z4 * np.sqrt(ni * ME / Mi4)
+    vTi = np.sqrt(Ti / Mi4)
+    kldi = (vTi / omgpi) * k_mag[..., None]
+    xii = 1.0 / (np.sqrt(2.0) * vTi) * ((omgdop / k_mag)[..., None])
+    kin = dict(ne=ne, Te=Te, omgL=omgL, omgpe=omgpe, omgs=omgs, k=k_mag, omgdop=omgdop, vTe=vTe, klde=klde_mag,
+               Z=Z4, fract=fr4, Zbar=Zbar, vTi=vTi, kldi=kldi, xii=xii)
+    chiI = _chi_ion(kin, grids)
+    xiex = ((omgdop / k_mag**2) * kx - ud[0]) / vTe                                    # :552
+    xiey = ((omgdop / k_mag**2) * ky - ud[1]) / vTe
+    xie_mag = np.sqrt(xiex**2 + xiey**2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        beta = np.arctan(xiey / xiex) + np.pi * (-np.heaviside(xiex, 1) + 1)           # :558
+    fe_vphi, chiEI, chiER = np.empty(beta.shape), np.empty(beta.shape), np.empty(beta.shape)
+    for idx in np.ndindex(beta.shape):
+        fe_vphi[idx], chiEI[idx], chiER[idx], _ = calc_chi_vals_2d(vx, DF, beta[idx], xie_mag[idx], klde_mag[idx])
+    chiE = chiER + 1j * chiEI
+    out, lams = _assemble(kin, chiE, chiI, fe_vphi, grids)
+    if return_parts:
+        return out, lams, dict(kin=kin, chiE=chiE, chiI=chiI, fe_vphi=fe_vphi, beta=beta, xie_mag=xie_mag)
+    return out, lams
+
+
+# --------------------------------------------------------------------------------------
 # a7: FitModel (generate_spectra.py:139-220), temporal / 1d spectype
 # --------------------------------------------------------------------------------------
 def fit_model_electron(params, grids, sa, cfg_other, num_grad_points=1, lam_shift=0.0, mode="table",

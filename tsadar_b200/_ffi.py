@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libtsff.so")
 
-TSFF_ABI_VERSION = 1
-TSFF_MODE_TABLE, TSFF_MODE_DIRECT = 0, 1
+TSFF_ABI_VERSION = 2
+TSFF_MODE_TABLE, TSFF_MODE_DIRECT, TSFF_MODE_2V = 0, 1, 2
 TSFF_F32, TSFF_F64 = 0, 1
 TSFF_PV_FP32, TSFF_PV_FP64 = 0, 1
 P_TE, P_NE, P_LAM, P_VA, P_UD, P_NE_GRAD, P_TE_GRAD, P_AMP1, P_AMP2, P_AMP3, P_ION0 = range(11)
@@ -34,6 +34,7 @@ class StaticCfg(C.Structure):
         ("sa_deg", C.POINTER(C.c_double)), ("weights", C.POINTER(C.c_double)), ("jmul", C.POINTER(C.c_double)),
         ("zp_x", C.POINTER(C.c_double)), ("zp_re", C.POINTER(C.c_double)), ("zp_im", C.POINTER(C.c_double)),
         ("zp_n", C.c_int32), ("reserved", C.c_int32),
+        ("ud_angle_deg", C.c_double), ("va_angle_deg", C.c_double),
     ]
 
 

@@ -123,6 +123,8 @@ struct tsff_ctx {
   double* omgs;   // [W]   2e7 pi C / linspace(lam_min, lam_max, W)       form_factor.py:132-135
   double* lam_nm; // [W]   wavelength axis in nm (= lams*1e7)
   double* costh;  // [A]   cos(sa)
+  double* sinth;  // [A]   sin(sa)   (2V mode: ks as a vector, form_factor.py:514)
+  double ud_angle_deg, va_angle_deg;
   double* wts;    // [A]
   double* jmul;   // [W]
   double* zr;     // [1640] Zpi[0]                                        form_factor.py:139

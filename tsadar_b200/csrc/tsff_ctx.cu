@@ -39,7 +39,7 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
     set_error("unsupported shape W=%d A=%d G=%d I=%d V=%d", cfg->W, cfg->A, cfg->G, cfg->I, cfg->V);
     return TSFF_E_INVALID;
   }
-  if (cfg->mode != TSFF_MODE_TABLE && cfg->mode != TSFF_MODE_DIRECT) { set_error("unknown mode %d", cfg->mode); return TSFF_E_INVALID; }
+  if (cfg->mode != TSFF_MODE_TABLE && cfg->mode != TSFF_MODE_DIRECT && cfg->mode != TSFF_MODE_2V) { set_error("unknown mode %d", cfg->mode); return TSFF_E_INVALID; }
   if (!cfg->sa_deg || !cfg->weights || !cfg->zp_x || !cfg->zp_re || !cfg->zp_im || cfg->zp_n < 2) {
     set_error("missing static table pointer"); return TSFF_E_INVALID;
   }
@@ -62,9 +62,10 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   c->pv_precision = cfg->pv_precision;
   c->lam_min = cfg->lam_min; c->lam_max = cfg->lam_max; c->lam_shift = cfg->lam_shift;
   c->v0 = cfg->v0; c->dv = cfg->dv;
+  c->ud_angle_deg = cfg->ud_angle_deg; c->va_angle_deg = cfg->va_angle_deg;
 
   const int W = c->W, A = c->A;
-  std::vector<double> h_omgs(W), h_lam(W), h_cos(A), h_w(A), h_jmul(W), h_zr(kXi2N), h_zi(kXi2N), h_xi2(kXi2N);
+  std::vector<double> h_omgs(W), h_lam(W), h_cos(A), h_sin(A), h_w(A), h_jmul(W), h_zr(kXi2N), h_zi(kXi2N), h_xi2(kXi2N);
   // jnp.linspace(l0, l1, W): start + i*step, endpoint exact
   const double step = (c->lam_max - c->lam_min) / (double)(W - 1);
   for (int j = 0; j < W; j++) {
@@ -75,6 +76,7 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   }
   for (int a = 0; a < A; a++) {
     h_cos[a] = cos(cfg->sa_deg[a] * kPi / 180.0);    // form_factor.py:210,220
+    h_sin[a] = sin(cfg->sa_deg[a] * kPi / 180.0);    // form_factor.py:514
     h_w[a] = cfg->weights[a];
   }
   for (int i = 0; i < kXi2N; i++) {
@@ -84,16 +86,17 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   }
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n * sizeof(double)); return o; };
-  size_t o_omgs = take(W), o_lam = take(W), o_cos = take(A), o_w = take(A), o_jmul = take(W), o_zr = take(kXi2N),
+  size_t o_omgs = take(W), o_lam = take(W), o_cos = take(A), o_sin = take(A), o_w = take(A), o_jmul = take(W), o_zr = take(kXi2N),
          o_zi = take(kXi2N), o_xi2 = take(kXi2N);
   if (cudaMalloc(&c->dev_blob, off) != cudaSuccess) { delete c; set_error("cudaMalloc(%zu) failed", off); return TSFF_E_NOMEM; }
   char* base = static_cast<char*>(c->dev_blob);
   auto up = [&](size_t o, const std::vector<double>& v) { return cudaMemcpy(base + o, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice); };
-  if (up(o_omgs, h_omgs) || up(o_lam, h_lam) || up(o_cos, h_cos) || up(o_w, h_w) || up(o_jmul, h_jmul) || up(o_zr, h_zr) ||
+  if (up(o_omgs, h_omgs) || up(o_lam, h_lam) || up(o_cos, h_cos) || up(o_sin, h_sin) || up(o_w, h_w) || up(o_jmul, h_jmul) || up(o_zr, h_zr) ||
       up(o_zi, h_zi) || up(o_xi2, h_xi2)) {
     cudaFree(c->dev_blob); delete c; set_error("table upload failed"); return TSFF_E_CUDA;
   }
   c->omgs = (double*)(base + o_omgs); c->lam_nm = (double*)(base + o_lam); c->costh = (double*)(base + o_cos);
+  c->sinth = (double*)(base + o_sin);
   c->wts = (double*)(base + o_w); c->jmul = (double*)(base + o_jmul); c->zr = (double*)(base + o_zr);
   c->zi = (double*)(base + o_zi); c->xi2 = (double*)(base + o_xi2);
   c->zt.zr = c->zr; c->zt.zi = c->zi; c->zt.n = kXi2N; c->zt.x0 = h_xi2[0]; c->zt.h = 0.01; c->zt.xlast = h_xi2[kXi2N - 1];

@@ -36,7 +36,7 @@ class FormFactorEngine:
     form_factor.py:120-161) bound to one GPU."""
 
     def __init__(self, lambda_range, npts, lam_shift, sa_deg, weights, num_grad_points, n_ions, vx, mode="table",
-                 jmul=None, pv_precision="fp32", device=None):
+                 jmul=None, pv_precision="fp32", device=None, ud_ang=0.0, va_ang=0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("tsadar_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -57,7 +57,8 @@ class FormFactorEngine:
         zx, zr, zi = _zprime_table()
         cfg = _ffi.StaticCfg()
         cfg.abi_version = _ffi.TSFF_ABI_VERSION
-        cfg.mode = _ffi.TSFF_MODE_TABLE if mode == "table" else _ffi.TSFF_MODE_DIRECT
+        cfg.mode = {"table": _ffi.TSFF_MODE_TABLE, "direct": _ffi.TSFF_MODE_DIRECT, "2v": _ffi.TSFF_MODE_2V}[mode]
+        cfg.ud_angle_deg, cfg.va_angle_deg = float(ud_ang or 0.0), float(va_ang or 0.0)
         cfg.W, cfg.A, cfg.G, cfg.I, cfg.V = self.W, self.A, self.G, self.I, self.V
         cfg.pv_precision = _ffi.TSFF_PV_FP64 if pv_precision == "fp64" else _ffi.TSFF_PV_FP32
         cfg.lam_min, cfg.lam_max, cfg.lam_shift = float(lambda_range[0]), float(lambda_range[1]), float(lam_shift)
@@ -107,7 +108,11 @@ class FormFactorEngine:
             raise RuntimeError("fe must be float32 or float64")
         _require_cuda(fe, fe.dtype, "fe")
         B = params.shape[0]
-        assert params.shape == (B, self.NP) and fe.shape == (B, self.V), (params.shape, fe.shape)
+        if self.mode == "2v":
+            assert params.shape == (B, self.NP) and fe.shape == (B, self.V, self.V) and fe.dtype == torch.float64, (params.shape, fe.shape)
+            want_ff, want_modl = True, False
+        else:
+            assert params.shape == (B, self.NP) and fe.shape == (B, self.V), (params.shape, fe.shape)
         modl = torch.empty((B, self.W), dtype=torch.float64, device=self.device) if want_modl else None
         ff = torch.empty((B, self.G, self.W, self.A), dtype=torch.float64, device=self.device) if want_ff else None
         if saved is None:

@@ -85,4 +85,28 @@ class FormFactor:
         return form_factor_modl(eng, block, fe), block
 
     def calc_in_2D(self, params):
-        raise NotImplementedError("2V (ARTS-2V) path: SURVEY.md 8 row a5/a6 is not built yet (DESIGN.md: scope)")
+        """-> formfactor [G,W,A], lams [1,W,1]   (form_factor.py:449-587).  params["electron"]["fe"] is the 2-D table
+        DF[V,V] on vx x vx.  FORWARD ONLY: the adjoint of the rotate/project stage is not built yet, so the result
+        carries no autograd graph (forward mode, tsadar/forward/calc_series.py, needs none)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ele = params["electron"]
+        fe = ele["fe"] if isinstance(ele["fe"], torch.Tensor) else torch.as_tensor(np.asarray(ele["fe"]), dtype=torch.float64)
+        fe = fe.detach().to(device=dev, dtype=torch.float64)
+        fe = fe.reshape((-1,) + tuple(fe.shape[-2:]))
+        assert fe.shape[0] == 1 and fe.shape[1] == fe.shape[2], "calc_in_2D takes one 2-D table [V, V]"
+        p1 = {k: (dict(v) if isinstance(v, dict) else v) for k, v in params.items()}
+        p1["electron"] = dict(ele)
+        p1["electron"]["fe"] = torch.zeros(fe.shape[1], dtype=torch.float64)     # placeholder row for pack_params
+        v = ele["v"]
+        v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        p1["electron"]["v"] = np.asarray(v, dtype=np.float64).reshape(-1)[: fe.shape[1]] if np.ndim(v) == 1 else np.asarray(v[0], dtype=np.float64)
+        block, _, vx, _, nI = pack_params(p1, dev)
+        key = ("2v", vx.size, float(vx[0]), float(vx[1] - vx[0]), nI)
+        if key not in self._engines:
+            sa = np.asarray(self.scattering_angles["sa"], dtype=np.float64).reshape(-1)
+            self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, np.ones_like(sa),
+                                                  self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle)
+        eng = self._engines[key]
+        with torch.no_grad():
+            _, ff, _ = eng.forward(block.detach()[:1].contiguous(), fe.contiguous(), want_ff=True)
+        return ff[0], torch.as_tensor(self._lams, device=dev)
