@@ -50,8 +50,8 @@ enum {
   TSFF_MODE_DIRECT = 1, /* calc_chi_vals semantics (form_factor.py:369-388) on a given 1-D table: pole = xi_e,
                           nodes = the f grid, gradient/lerp of f;  the synthetic-sweep workload of SURVEY.md 8(d) */
   TSFF_MODE_2V = 2     /* FormFactor.calc_in_2D (form_factor.py:449-587): fe is a 2-D table [V][V] (float64) on vx x vx,
-                          rotated / projected per pole (rotate :300-324, calc_chi_vals :349-388).  Forward only so far:
-                          tsff_ff_fwd with ff_out; tsff_ff_bwd returns TSFF_E_INVALID */
+                          rotated / projected per pole (rotate :300-324, calc_chi_vals :349-388).  tsff_ff_fwd produces
+                          ff_out only (no fused modl); tsff_ff_bwd takes ff_bar and returns params_bar, fe_bar [B][V][V] */
 };
 enum { TSFF_F32 = 0, TSFF_F64 = 1 };
 /* precision of the PV inner loop */

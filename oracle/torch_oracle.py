@@ -246,3 +246,96 @@ def ats_chain(modlE, lamAxisE, angAxis, spect_fwhm, ang_fwhm, lam, amp1, amp2, e
     y = y[row_start:row_end]
     y = T(e_amps).reshape(-1, 1) * y / y.max(dim=1, keepdim=True).values
     return torch.where(lamb < lam, amp1 * y, amp2 * y), lamb
+
+
+# ---- 2V path (np_oracle.form_factor_2d) with autograd: bicubic rotate/project per pole ---------------------------------
+def _t_hermite_weights(xq, x):
+    """torch twin of np_oracle._hermite_node_weights on a UNIFORM grid x: idx [n,4] (clamped), w [n,4] differentiable in xq."""
+    x = T(x)
+    n = x.numel()
+    h = x[1] - x[0]
+    i = torch.clamp(torch.searchsorted(x, xq.detach().contiguous(), right=True), 1, n - 1)
+    t = (xq - x[i - 1]) / h
+    h00, h01 = 2 * t**3 - 3 * t**2 + 1, -2 * t**3 + 3 * t**2
+    h10, h11 = t**3 - 2 * t**2 + t, t**3 - t**2          # in units of h (slopes are multiplied by h)
+    z = torch.zeros_like(t)
+    left, right = (i == 1), (i == n - 1)
+    w0 = torch.where(left, z, -0.5 * h10)
+    w1 = torch.where(left, h00 - h10 - 0.5 * h11, torch.where(right, h00 - h11, h00 - 0.5 * h11))
+    w2 = torch.where(left, h01 + h10, torch.where(right, h01 + 0.5 * h10 + h11, h01 + 0.5 * h10))
+    w3 = torch.where(right, z, 0.5 * h11)
+    idx = torch.stack([i - 2, i - 1, i, i + 1], dim=1).clamp(0, n - 1)
+    return idx, torch.stack([w0, w1, w2, w3], dim=1)
+
+
+def t_interp2d_cubic(xq, yq, x, y, f):
+    ix, wx = _t_hermite_weights(xq, x)
+    iy, wy = _t_hermite_weights(yq, y)
+    out = 0.0
+    for a in range(4):
+        for b in range(4):
+            out = out + wx[:, a] * wy[:, b] * f[ix[:, a], iy[:, b]]
+    return out
+
+
+def form_factor_2d(p, fe2d, vx, grids, sa_deg, G=1, lam_shift=0.0, ud_ang=0.0, va_ang=0.0):
+    """torch twin of np_oracle.form_factor_2d (form_factor.py:449-587).  p as in `kinematics`; fe2d [V,V] tensor."""
+    ne = 1.0e20 * p["ne"] * _linspace_factor(p["ne_gradient"], G)
+    Te = p["Te"] * _linspace_factor(p["Te_gradient"], G)
+    lam = p["lam"] + lam_shift
+    A = torch.stack([T(i["A"]) for i in p["ions"]])
+    Z = torch.stack([T(i["Z"]) for i in p["ions"]])
+    Ti = torch.stack([T(i["Ti"]) for i in p["ions"]])
+    fract = torch.stack([T(i["fract"]) for i in p["ions"]])
+    Va, ud = p["Va"] * 1e6, p["ud"] * 1e6
+    Vax, Vay = Va * math.cos(va_ang * math.pi / 180), Va * math.sin(va_ang * math.pi / 180)
+    udx, udy = ud * math.cos(ud_ang * math.pi / 180), ud * math.sin(ud_ang * math.pi / 180)
+    Mi = A * MP
+    constants = math.sqrt(4 * math.pi * (ME * C**2 * RE) / ME)
+    sarad = (T(np.asarray(sa_deg, dtype=np.float64)) * math.pi / 180).reshape(1, 1, -1)
+    omgL = grids.omgL_num / lam
+    omgpe = constants * torch.sqrt(ne[:, None, None])
+    omgs = T(grids.omgs)
+    omg = omgs - omgL
+    kLx = torch.sqrt(omgL**2 - omgpe**2) / C
+    ks_mag = torch.sqrt(omgs**2 - omgpe**2) / C
+    kx, ky = torch.cos(sarad) * ks_mag - kLx, torch.sin(sarad) * ks_mag + 0.0 * kLx
+    k = torch.sqrt(kx * kx + ky * ky)
+    omgdop = omg - (kx * Vax + ky * Vay)
+    vTe = torch.sqrt(Te[:, None, None] / ME)
+    klde = (vTe / omgpe) * k
+    Z4, Mi4, fr4 = Z.reshape(1, 1, 1, -1), Mi.reshape(1, 1, 1, -1), fract.reshape(1, 1, 1, -1)
+    Zbar = torch.sum(Z4 * fr4)
+    ni = fr4 * ne[:, None, None, None] / Zbar
+    omgpi = constants * Z4 * torch.sqrt(ni * ME / Mi4)
+    vTi = torch.sqrt(Ti / Mi4)
+    kldi = (vTi / omgpi) * k[..., None]
+    xii = 1.0 / (math.sqrt(2.0) * vTi) * ((omgdop / k)[..., None])
+    kin = dict(ne=ne, omgL=omgL, omgs=omgs, k=k, omgdop=omgdop, vTe=vTe, klde=klde, Z=Z4, fract=fr4, Zbar=Zbar, vTi=vTi,
+               kldi=kldi, xii=xii)
+    chiIr, chiIi = chi_ion(kin, grids)
+    xiex = ((omgdop / k**2) * kx - udx) / vTe
+    xiey = ((omgdop / k**2) * ky - udy) / vTe
+    xmag = torch.sqrt(xiex**2 + xiey**2)
+    beta = torch.atan(xiey / xiex) + math.pi * (xiex < 0).to(DT)
+    vxt = T(vx)
+    dv = float(vx[1] - vx[0])
+    V = len(vx)
+    shp = beta.shape
+    fphi_l, chiEi_l, chiEr_l = [], [], []
+    va, vb = torch.meshgrid(vxt, vxt, indexing="ij")          # F[a][b]: x = vx[a], y = vx[b]
+    for bq, xm, kl in zip(beta.reshape(-1), xmag.reshape(-1), (klde * torch.ones_like(beta)).reshape(-1)):
+        cb, sb = torch.cos(bq), torch.sin(bq)
+        xq = (cb * va - sb * vb).reshape(-1)
+        yq = (sb * va + cb * vb).reshape(-1)
+        F = t_interp2d_cubic(xq, yq, vx, vx, fe2d).reshape(V, V)
+        f1 = F.sum(dim=0) * dv
+        df = t_gradient(f1, dv)
+        fphi_l.append(t_interp(xm.reshape(1), vx, f1)[0])
+        dfe = t_interp(xm.reshape(1), vx, df)[0]
+        chiEi_l.append(math.pi / kl**2 * dfe)
+        chiEr_l.append(-1.0 / kl**2 * t_ratintn(df, vxt - xm, vx))
+    fphi = torch.stack(fphi_l).reshape(shp)
+    chiEi = torch.stack(chiEi_l).reshape(shp)
+    chiEr = torch.stack(chiEr_l).reshape(shp)
+    return assemble(kin, chiEr, chiEi, chiIr, chiIi, fphi, grids)

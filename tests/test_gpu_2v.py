@@ -67,3 +67,36 @@ def test_isotropic_2v_equals_1v_direct():
     _, ff1, _ = eng.forward(torch.tensor(row, device="cuda"), torch.tensor(f1[None], device="cuda"), want_ff=True)
     a, b = got2.cpu().numpy()[0, :, 0], ff1.cpu().numpy()[0, 0, :, 0]
     assert np.abs(a - b).max() / np.abs(b).max() < 2e-3      # bicubic rotation of a V = 64 Maxwellian: ~1e-4 in f1
+
+
+def test_calc_in_2D_vjp_matches_autograd():
+    """Adjoint of the 2V path (fe_bar [V,V] through the bicubic rotate/project scatter, params_bar through |xi|, beta and the
+    kinematics) vs torch autograd of the oracle, with drift, flow and two gradient points."""
+    from oracle import torch_oracle as TO
+    from tsadar_b200.engine import FormFactorEngine
+    V, W, G = 16, 6, 2
+    vx = _grid(V)
+    dv = vx[1] - vx[0]
+    X, Y = np.meshgrid(vx, vx, indexing="ij")
+    DF = np.exp(-0.5 * ((X - 0.3) ** 2 / 1.2 + (Y + 0.2) ** 2 / 0.8) ** 1.2) * (1 + 0.2 * np.tanh(X))
+    DF = DF / DF.sum() / dv**2
+    sa = np.array([60.0, 100.0])
+    row = np.array([0.8, 0.3, 526.5, -0.8, 0.4, 3.0, 1.0, 1, 1, 1, 40.0, 8.0, 0.2, 1.0])
+    grids = O.Grids([400.0, 700.0], W)
+    leaves, pt = TO.params_from_block(row, 1)
+    fo = torch.tensor(DF, requires_grad=True)
+    ffo = TO.form_factor_2d(pt, fo, vx, grids, sa, G, 0.0, 30.0, 110.0)
+    rng = np.random.default_rng(2)
+    cot = rng.normal(size=tuple(ffo.shape)) / np.abs(ffo.detach().numpy()).max()
+    (ffo * torch.tensor(cot)).sum().backward()
+    eng = FormFactorEngine((400.0, 700.0), W, 0.0, sa, np.ones(2), G, 1, vx, mode="2v", ud_ang=30.0, va_ang=110.0)
+    ptg = torch.tensor(row[None], device="cuda")
+    feg = torch.tensor(DF[None], device="cuda")
+    _, ff, saved = eng.forward(ptg, feg, want_ff=True)
+    assert np.abs(ff.cpu().numpy()[0] - ffo.detach().numpy()).max() / np.abs(ffo.detach().numpy()).max() < 1e-10
+    pb, fb = eng.backward(ptg, feg, saved, ff_bar=torch.tensor(cot[None], device="cuda"))
+    gp, gf = leaves.grad.numpy(), fo.grad.numpy()
+    pb, fb = pb.cpu().numpy()[0], fb.cpu().numpy()[0]
+    assert np.abs(fb - gf).max() / np.abs(gf).max() < 1e-9, np.abs(fb - gf).max() / np.abs(gf).max()
+    for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13]:
+        assert abs(pb[k] - gp[k]) <= 1e-4 * max(abs(gp[k]), 1e-8 * np.abs(gp).max()), (k, pb[k], gp[k])

@@ -14,7 +14,8 @@
 // All FP64 (a 1e-7 error in f1' is amplified ~250x at an EPW resonance).  The f table sits in shared memory (padded
 // rows, 129 KB at V = 128); a CTA of 1024 threads works on 1024/V poles at a time, thread b of a group owning column b
 // of its pole's rotated table (no reductions in the hot loop).  Bound: FP64 pipe + shared-memory gathers.
-// The adjoint (scatter of f1bar through the 16 taps into fbar, d/dbeta through the patch derivatives) is the next row.
+// The adjoint (k_ff2v_bwd) scatters f1bar through the same 16 taps into a CTA-private fbar in shared memory, gathers
+// d f1 / d beta from the patch derivatives, and reverses the 2-vector kinematics.
 #include "tsff_common.cuh"
 
 using namespace tsff;
@@ -30,6 +31,11 @@ struct Args2V {
   const double* params;   // [B][NP]
   const double* fe;       // [B][V][V]
   double* ff;             // [B][G][W][A]
+  double* f1save;         // [B][P][V] projected tables per pole (forward -> backward), or null
+  // backward
+  const double* ff_bar;   // [B][G][W][A]
+  double* fe_bar;         // [B][V][V]   (atomically accumulated: zero it)
+  double* lgbar;          // [B][G][kLGDoubles] (atomically accumulated: zero it)
 };
 
 // 1-D cubic-Hermite node weights on a uniform grid (interpax "cubic"): query coordinate q -> first node index i0 (clamped
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long
         acc += s;
       }
       sf1[grp * V + tb] = acc * a.dv;
+      if (a.f1save) a.f1save[(b_lineout * a.P + p) * V + tb] = acc * a.dv;
     }
     __syncthreads();
     if (valid && tb < V) {   // np.gradient(f1, dv) (:372)
@@ -176,10 +183,317 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long
     __syncthreads();
   }
 }
+
+// ---- adjoint ------------------------------------------------------------------------------------------------------
+// hermite4 plus the derivative weights d w / d t (for d f / d beta through the query coordinates)
+__device__ __forceinline__ void hermite4d(double q, double v0, double idv, int V, int& i0, double (&w)[4], double (&dw)[4]) {
+  const double u = (q - v0) * idv;
+  int i = (int)floor(u) + 1;
+  i = i < 1 ? 1 : (i > V - 1 ? V - 1 : i);
+  const double t = u - (double)(i - 1);
+  const double t2 = t * t;
+  const double h00 = (2.0 * t - 3.0) * t2 + 1.0, h01 = 1.0 - h00;
+  const double h10 = ((t - 2.0) * t + 1.0) * t, h11 = (t - 1.0) * t2;
+  const double g00 = 6.0 * (t2 - t), g01 = -g00;
+  const double g10 = (3.0 * t - 4.0) * t + 1.0, g11 = (3.0 * t - 2.0) * t;
+  if (i == 1) {
+    i0 = 0;
+    w[0] = h00 - h10 - 0.5 * h11; w[1] = h01 + h10; w[2] = 0.5 * h11; w[3] = 0.0;
+    dw[0] = g00 - g10 - 0.5 * g11; dw[1] = g01 + g10; dw[2] = 0.5 * g11; dw[3] = 0.0;
+    return;
+  }
+  if (i == V - 1) {
+    i0 = i - 2;
+    w[0] = -0.5 * h10; w[1] = h00 - h11; w[2] = h01 + 0.5 * h10 + h11; w[3] = 0.0;
+    dw[0] = -0.5 * g10; dw[1] = g00 - g11; dw[2] = g01 + 0.5 * g10 + g11; dw[3] = 0.0;
+    if (i0 + 3 > V - 1) {
+      i0 -= 1;
+      w[3] = w[2]; w[2] = w[1]; w[1] = w[0]; w[0] = 0.0;
+      dw[3] = dw[2]; dw[2] = dw[1]; dw[1] = dw[0]; dw[0] = 0.0;
+    }
+    return;
+  }
+  i0 = i - 2;
+  w[0] = -0.5 * h10; w[1] = h00 - 0.5 * h11; w[2] = h01 + 0.5 * h10; w[3] = 0.5 * h11;
+  dw[0] = -0.5 * g10; dw[1] = g00 - 0.5 * g11; dw[2] = g01 + 0.5 * g10; dw[3] = 0.5 * g11;
+}
+
+__device__ __forceinline__ void atomic_add_shared(double* addr, double v) { atomicAdd(addr, v); }
+
+// One CTA works on kThreads2V / GS poles at a time (as the forward).  Per pole:
+//   f1 (saved by the forward) -> df; per-node PV weights Wt_i and dWt_i/dxi -> I, dI/dxi; thread 0 reverses the
+//   assembly -> Ibar, dfe_bar, fphi_bar, kinematic cotangents; df_bar -> f1_bar; then the rotate/project adjoint: every
+//   (a, b) point scatters f1_bar[b] dv wx wy into the CTA's private fbar (shared memory, FP64 CAS adds; a warp owns a
+//   column b and its lanes take points four nodes apart so that their 4x4 stencils barely collide) and gathers
+//   d f1[b] / d beta from f; finally the kinematics reverse (|xi|, beta -> parameters).
+// dynamic smem: f [V][V+1] | fbar [V][V+1] | 3 x [NG][V] | red [NG][16] | scal [NG][16]
+__global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long long b_lineout) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int V = a.V, VP = V + 1;
+  const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS, NWG = GS / 32;
+  float* sf = reinterpret_cast<float*>(smem_raw);                 // f as FP32 (only d/dbeta reads it; 1e-4 is asked)
+  double* sfb = reinterpret_cast<double*>(smem_raw + (((size_t)V * VP * 4 + 15) / 16) * 16);
+  double* sA = sfb + (size_t)V * VP;           // [NG][V]: f1, later df_bar
+  double* sB = sA + (size_t)NG * V;            // [NG][V]: df, later f1_bar
+  double* sW = sB + (size_t)NG * V;            // [NG][V]: Wt
+  double* sred = sW + (size_t)NG * V;          // [NG][16]
+  double* ssc = sred + (size_t)NG * 16;        // [NG][16]
+  __shared__ LG sL[8];
+  __shared__ double sLb[8][kLGDoubles];
+  const double* fe = a.fe + b_lineout * (long long)V * V;
+  for (int i = threadIdx.x; i < V * V; i += kThreads2V) sf[(i / V) * VP + (i % V)] = (float)fe[i];
+  for (int i = threadIdx.x; i < V * VP; i += kThreads2V) sfb[i] = 0.0;
+  for (int i = threadIdx.x; i < 8 * kLGDoubles; i += kThreads2V) (&sLb[0][0])[i] = 0.0;
+  if (threadIdx.x < a.G) {
+    LG L;
+    lg_zero(L);
+    lg_forward(a.params + b_lineout * a.NP, a.nI, threadIdx.x, a.G, a.lam_shift, L);
+    sL[threadIdx.x] = L;
+  }
+  __syncthreads();
+  const int grp = threadIdx.x / GS, tb = threadIdx.x % GS, wg = tb >> 5, lane = tb & 31;
+  const bool active_grp = grp < NG;
+  const double idv = fast_rcp(a.dv), h = a.dv;
+  const int WA = a.W * a.A, M = V - 2;
+
+  for (long long p0 = (long long)blockIdx.x * NG; p0 < a.P; p0 += (long long)gridDim.x * NG) {
+    const long long p = p0 + grp;
+    const bool valid = active_grp && p < a.P;
+    Kin q;
+    double cb = 1.0, sb = 0.0, xmag = 0.0, omgs = 0.0, kx = 0.0, ky = 0.0, xx = 1.0, xy = 0.0;
+    int g = 0, j = 0, ia = 0;
+    if (valid) {
+      g = (int)(p / WA);
+      const int r = (int)(p % WA);
+      j = r / a.A; ia = r % a.A;
+      const LG& L = sL[g];
+      omgs = a.omgs[j];
+      const double ks = fast_sqrt(omgs * omgs - L.omgpe2) * (1.0 / kC);
+      kx = a.costh[ia] * ks - L.kL; ky = a.sinth[ia] * ks;
+      q.ks = ks;
+      q.k2 = kx * kx + ky * ky;
+      q.k = fast_sqrt(q.k2);
+      q.omgdop = omgs - L.omgL - (kx * L.Va6 * a.cos_va + ky * L.Va6 * a.sin_va);
+      q.w = q.omgdop * fast_rcp(q.k);
+      const double ivTe = fast_rcp(L.vTe), ok2 = q.omgdop * fast_rcp(q.k2);
+      xx = (ok2 * kx - L.ud6 * a.cos_ud) * ivTe; xy = (ok2 * ky - L.ud6 * a.sin_ud) * ivTe;
+      xmag = sqrt(xx * xx + xy * xy);
+      q.xie = xmag;
+      q.ikl2 = L.omgpe2 * ivTe * ivTe * fast_rcp(q.k2);
+      const double beta = atan(xy / xx) + (xx < 0.0 ? kPi : 0.0);
+      sincos(beta, &sb, &cb);
+    }
+    // ---- f1 (saved), df, PV node weights
+    if (valid && tb < V) sA[grp * V + tb] = a.f1save[(b_lineout * a.P + p) * V + tb];
+    __syncthreads();
+    if (valid && tb < V) {
+      const double* f1 = sA + grp * V;
+      sB[grp * V + tb] = tb == 0 ? (f1[1] - f1[0]) * idv : (tb == V - 1 ? (f1[V - 1] - f1[V - 2]) * idv : (f1[tb + 1] - f1[tb - 1]) * (0.5 * idv));
+    }
+    __syncthreads();
+    double tI = 0.0, tJ = 0.0;
+    if (valid && tb < V) {
+      double wt = 0.0, dwt = 0.0;
+      if (tb <= M) {
+        const double gi = a.v0 + (double)tb * h - xmag;
+        const double lc = log_abs(gi);
+        if (tb == 0) {
+          const double lp = log_abs(gi + h);
+          wt = ((gi + h) * lp - gi * lc) * idv - 1.0 - lc;
+          dwt = -(lp - lc) * idv + fast_rcp(gi);
+        } else if (tb == M) {
+          const double lm = log_abs(gi - h);
+          wt = ((gi - h) * lm - gi * lc) * idv + 1.0 + lc;
+          dwt = -(lm - lc) * idv - fast_rcp(gi);
+        } else {
+          const double lp = log_abs(gi + h), lm = log_abs(gi - h);
+          wt = ((gi + h) * lp - 2.0 * gi * lc + (gi - h) * lm) * idv;
+          dwt = -(lp - 2.0 * lc + lm) * idv;
+        }
+      }
+      sW[grp * V + tb] = wt;
+      tI = sB[grp * V + tb] * wt;
+      tJ = sB[grp * V + tb] * dwt;
+    }
+    tI = warp_sum(tI);
+    tJ = warp_sum(tJ);
+    if (active_grp && lane == 0) { sred[grp * 16 + wg] = tI; sred[grp * 16 + 8 + wg] = tJ; }
+    __syncthreads();
+    // ---- thread 0 of the group: reverse of the assembly
+    LG Lb;
+    lg_zero(Lb);
+    KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (valid && tb == 0) {
+      double I = 0.0, J = 0.0;
+      for (int w = 0; w < NWG; w++) { I += sred[grp * 16 + w]; J += sred[grp * 16 + 8 + w]; }
+      const LG& L = sL[g];
+      int i_f; double t_f, sl_f;
+      const double fphi = lerp_uniform(sA + grp * V, V, a.v0, a.dv, xmag, i_f, t_f, sl_f);
+      const double d0 = sB[grp * V + i_f], d1 = sB[grp * V + i_f + 1];
+      const bool clamped = (xmag <= a.v0) || (xmag >= a.v0 + (V - 1) * a.dv) || !(xmag == xmag);
+      const double dfe = d0 + t_f * (d1 - d0);
+      const double sl_d = clamped ? 0.0 : (d1 - d0) * idv;
+      IonOut io;
+      ion_forward(L, a.nI, a.zt, q, io);
+      Asm s;
+      const double chiEr = -q.ikl2 * I, chiEi = kPi * q.ikl2 * dfe;
+      assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
+      PointBar pb;
+      const double Pbar = a.ff_bar[((b_lineout * a.G + g) * (long long)a.W + j) * a.A + ia];
+      assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
+      kb.ikl2 += -I * pb.chiEr + kPi * dfe * pb.chiEi;
+      const double Ibar = -q.ikl2 * pb.chiEr, dfe_bar = kPi * q.ikl2 * pb.chiEi;
+      double* sc = ssc + grp * 16;
+      sc[0] = Ibar; sc[1] = dfe_bar; sc[2] = pb.fphi; sc[3] = (double)i_f; sc[4] = t_f;
+      sc[5] = Ibar * J + dfe_bar * sl_d + pb.fphi * sl_f;   // cotangent of |xi|
+    }
+    __syncthreads();
+    // ---- df_bar (into sA), then f1_bar (into sB)
+    double Ibar = 0.0, dfe_bar = 0.0, fphi_bar = 0.0, t_f = 0.0;
+    int i_f = 0;
+    if (valid) {
+      const double* sc = ssc + grp * 16;
+      Ibar = sc[0]; dfe_bar = sc[1]; fphi_bar = sc[2]; i_f = (int)sc[3]; t_f = sc[4];
+    }
+    if (valid && tb < V) {
+      double v = Ibar * sW[grp * V + tb];
+      if (tb == i_f) v += (1.0 - t_f) * dfe_bar;
+      if (tb == i_f + 1) v += t_f * dfe_bar;
+      sA[grp * V + tb] = v;
+    }
+    __syncthreads();
+    if (valid && tb < V) {
+      const double* dfb = sA + grp * V;
+      const int k = tb;
+      double fb = 0.0;
+      if (k >= 1) fb += dfb[k - 1] * ((k - 1 == 0) ? idv : 0.5 * idv);
+      if (k <= V - 2) fb -= dfb[k + 1] * ((k + 1 == V - 1) ? idv : 0.5 * idv);
+      if (k == 0) fb -= dfb[0] * idv;
+      if (k == V - 1) fb += dfb[V - 1] * idv;
+      if (k == i_f) fb += (1.0 - t_f) * fphi_bar;
+      if (k == i_f + 1) fb += t_f * fphi_bar;
+      sB[grp * V + k] = fb;
+    }
+    __syncthreads();
+    // ---- rotate/project adjoint: warp wg of the group owns columns b = wg, wg + NWG, ...; lanes take a = 4 lane + c
+    double bbar = 0.0;
+    if (valid) {
+      for (int b = wg; b < V; b += NWG) {
+        const double wcol = sB[grp * V + b] * a.dv;
+        if (wcol == 0.0) continue;
+        const double vb = a.v0 + (double)b * a.dv;
+        for (int c = 0; c < 4; c++) {
+          const int aa = 4 * lane + c;
+          if (aa >= V) break;
+          const double va = a.v0 + (double)aa * a.dv;
+          const double xq = cb * va - sb * vb, yq = sb * va + cb * vb;
+          int ix, iy;
+          double wx[4], wy[4], dwx[4], dwy[4];
+          hermite4d(xq, a.v0, idv, V, ix, wx, dwx);
+          hermite4d(yq, a.v0, idv, V, iy, wy, dwy);
+          const float* fb = sf + ix * VP + iy;
+          double* ob = sfb + ix * VP + iy;
+          double sx = 0.0, sy = 0.0;
+#pragma unroll
+          for (int m = 0; m < 4; m++) {
+            double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+              const double fv = (double)fb[m * VP + n];
+              r0 = fma(wy[n], fv, r0);
+              r1 = fma(dwy[n], fv, r1);
+              const double wv = wcol * wx[m] * wy[n];
+              if (wv != 0.0) atomic_add_shared(ob + m * VP + n, wv);
+            }
+            sx = fma(dwx[m], r0, sx);
+            sy = fma(wx[m], r1, sy);
+          }
+          // d xq / d beta = -yq, d yq / d beta = xq;  d/dxq = idv d/dt
+          bbar += wcol * (-yq * sx + xq * sy) * idv;
+        }
+      }
+    }
+    bbar = warp_sum(bbar);
+    if (active_grp && lane == 0) sred[grp * 16 + wg] = bbar;
+    __syncthreads();
+    // ---- kinematics reverse for (|xi|, beta) and the rest of kb
+    if (valid && tb == 0) {
+      double beta_bar = 0.0;
+      for (int w = 0; w < NWG; w++) beta_bar += sred[grp * 16 + w];
+      const LG& L = sL[g];
+      const double xmag_bar = ssc[grp * 16 + 5];
+      const double ixm = fast_rcp(xmag);
+      // xmag = sqrt(xx^2 + xy^2); beta = atan(xy/xx) (+ const)
+      const double xx_bar = xmag_bar * xx * ixm - beta_bar * xy * ixm * ixm;
+      const double xy_bar = xmag_bar * xy * ixm + beta_bar * xx * ixm * ixm;
+      // xx = (ok2 kx - udx) / vTe,  ok2 = omgdop / k2
+      const double ivTe = fast_rcp(L.vTe), ik2 = fast_rcp(q.k2), ok2 = q.omgdop * ik2;
+      Lb.vTe += -(xx_bar * xx + xy_bar * xy) * ivTe;
+      Lb.ud6 += -(xx_bar * a.cos_ud + xy_bar * a.sin_ud) * ivTe;
+      const double ok2_bar = (xx_bar * kx + xy_bar * ky) * ivTe;
+      double kx_bar = xx_bar * ok2 * ivTe, ky_bar = xy_bar * ok2 * ivTe;
+      kb.omgdop += ok2_bar * ik2;
+      kb.k2 += -ok2_bar * ok2 * ik2;
+      // ikl2 = omgpe2 / (vTe^2 k2)
+      Lb.omgpe2 += kb.ikl2 * q.ikl2 * fast_rcp(L.omgpe2);
+      Lb.vTe += -2.0 * kb.ikl2 * q.ikl2 * ivTe;
+      kb.k2 += -kb.ikl2 * q.ikl2 * ik2;
+      // w = omgdop / k
+      const double ik = fast_rcp(q.k);
+      kb.omgdop += kb.w * ik;
+      kb.k += -kb.w * q.w * ik;
+      // omgdop = omgs - omgL - (kx Vax + ky Vay)
+      Lb.omgL += -kb.omgdop;
+      kx_bar += -kb.omgdop * L.Va6 * a.cos_va;
+      ky_bar += -kb.omgdop * L.Va6 * a.sin_va;
+      Lb.Va6 += -kb.omgdop * (kx * a.cos_va + ky * a.sin_va);
+      // k = sqrt(k2); k2 = kx^2 + ky^2
+      kb.k2 += kb.k * (0.5 * ik);
+      kx_bar += kb.k2 * 2.0 * kx;
+      ky_bar += kb.k2 * 2.0 * ky;
+      // kx = cos(sa) ks - kL, ky = sin(sa) ks;  ks = sqrt(omgs^2 - omgpe2)/C
+      const double ks_bar = kx_bar * a.costh[ia] + ky_bar * a.sinth[ia];
+      Lb.kL += -kx_bar;
+      Lb.omgpe2 += -ks_bar * fast_rcp(2.0 * kC * kC * q.ks);
+      double vals[kLGDoubles];
+      vals[0] = Lb.ne_g; vals[1] = Lb.omgL; vals[2] = Lb.omgpe2; vals[3] = Lb.kL; vals[4] = Lb.vTe; vals[5] = Lb.Va6; vals[6] = Lb.ud6;
+      for (int i = 0; i < TSFF_MAX_IONS; i++) { vals[7 + i] = Lb.c_kldi[i]; vals[7 + TSFF_MAX_IONS + i] = Lb.inv_s2vTi[i]; vals[7 + 2 * TSFF_MAX_IONS + i] = Lb.ioncf[i]; }
+      for (int i = 0; i < kLGDoubles; i++) if (vals[i] != 0.0) atomicAdd(&sLb[g][i], vals[i]);
+    }
+    __syncthreads();
+  }
+  // ---- flush the CTA's private accumulators
+  double* feb = a.fe_bar + b_lineout * (long long)V * V;
+  for (int i = threadIdx.x; i < V * V; i += kThreads2V) {
+    const double v = sfb[(i / V) * VP + (i % V)];
+    if (v != 0.0) atomicAdd(&feb[i], v);
+  }
+  for (int i = threadIdx.x; i < a.G * kLGDoubles; i += kThreads2V) {
+    const double v = sLb[i / kLGDoubles][i % kLGDoubles];
+    if (v != 0.0) atomicAdd(&a.lgbar[(b_lineout * a.G) * kLGDoubles + i], v);
+  }
+}
+
+__global__ void k_ff2v_params_bar(const Args2V a, double* params_bar, int64_t B) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double* pbar = params_bar + b * a.NP;
+  for (int k = 0; k < a.NP; k++) pbar[k] = 0.0;
+  for (int g = 0; g < a.G; g++) {
+    const double* src = a.lgbar + (b * a.G + g) * kLGDoubles;
+    LG Lb;
+    Lb.ne_g = src[0]; Lb.omgL = src[1]; Lb.omgpe2 = src[2]; Lb.kL = src[3]; Lb.vTe = src[4]; Lb.Va6 = src[5]; Lb.ud6 = src[6];
+    for (int i = 0; i < TSFF_MAX_IONS; i++) { Lb.c_kldi[i] = src[7 + i]; Lb.inv_s2vTi[i] = src[7 + TSFF_MAX_IONS + i]; Lb.ioncf[i] = src[7 + 2 * TSFF_MAX_IONS + i]; }
+    lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+  }
+}
 }  // namespace
 
 namespace tsff {
-int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, double* ff_out, cudaStream_t st) {
+size_t ff2v_saved_bytes(const tsff_ctx* c, int64_t B) { return align_up((size_t)B * c->G * c->W * c->A * c->V * 8); }
+size_t ff2v_ws_bytes(const tsff_ctx* c, int64_t B) { return align_up((size_t)B * c->G * kLGDoubles * 8); }
+
+int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, double* ff_out, void* saved, cudaStream_t st) {
   const int V = c->V;
   if (V > 128 || V < 8) { set_error("2V path: V must be in [8, 128] (got %d)", V); return TSFF_E_INVALID; }
   if (c->G > 8) { set_error("2V path: at most 8 gradient points"); return TSFF_E_INVALID; }
@@ -190,7 +504,7 @@ int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, dou
   a.cos_va = cos(c->va_angle_deg * kPi / 180.0); a.sin_va = sin(c->va_angle_deg * kPi / 180.0);
   a.cos_ud = cos(c->ud_angle_deg * kPi / 180.0); a.sin_ud = sin(c->ud_angle_deg * kPi / 180.0);
   a.omgs = c->omgs; a.costh = c->costh; a.sinth = c->sinth; a.zt = c->zt;
-  a.params = params; a.fe = fe; a.ff = ff_out;
+  a.params = params; a.fe = fe; a.ff = ff_out; a.f1save = static_cast<double*>(saved);
   const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
   const size_t smem = ((size_t)V * (V + 1) + (size_t)NG * V * 2 + (size_t)NG * 16) * 8;
   TSFF_SMEM_OPTIN(k_ff2v_fwd<32>);
@@ -200,6 +514,35 @@ int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, dou
     k_ff2v_fwd<32><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
     TSFF_LAUNCH_OK("k_ff2v_fwd");
   }
+  return TSFF_OK;
+}
+
+int ff2v_bwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, const void* saved, const double* ff_bar,
+             double* params_bar, double* fe_bar, void* ws, cudaStream_t st) {
+  const int V = c->V;
+  if (V > 128 || V < 8) { set_error("2V path: V must be in [8, 128] (got %d)", V); return TSFF_E_INVALID; }
+  Args2V a;
+  memset(&a, 0, sizeof(a));
+  a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = V; a.NP = c->NP; a.P = c->G * c->W * c->A;
+  a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;
+  a.cos_va = cos(c->va_angle_deg * kPi / 180.0); a.sin_va = sin(c->va_angle_deg * kPi / 180.0);
+  a.cos_ud = cos(c->ud_angle_deg * kPi / 180.0); a.sin_ud = sin(c->ud_angle_deg * kPi / 180.0);
+  a.omgs = c->omgs; a.costh = c->costh; a.sinth = c->sinth; a.zt = c->zt;
+  a.params = params; a.fe = fe; a.f1save = const_cast<double*>(static_cast<const double*>(saved));
+  a.ff_bar = ff_bar; a.fe_bar = fe_bar; a.lgbar = static_cast<double*>(ws);
+  TSFF_CUDA_OK(cudaMemsetAsync(fe_bar, 0, (size_t)B * V * V * 8, st));
+  TSFF_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)B * c->G * kLGDoubles * 8, st));
+  const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
+  const size_t smem = (((size_t)V * (V + 1) * 4 + 15) / 16) * 16 + ((size_t)V * (V + 1) + (size_t)NG * V * 3 + (size_t)NG * 32) * 8;
+  TSFF_SMEM_OPTIN(k_ff2v_bwd);
+  const long long nbatch = ((long long)a.P + NG - 1) / NG;
+  const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
+  for (int64_t b = 0; b < B; b++) {
+    k_ff2v_bwd<<<grid, kThreads2V, smem, st>>>(a, (long long)b);
+    TSFF_LAUNCH_OK("k_ff2v_bwd");
+  }
+  k_ff2v_params_bar<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(a, params_bar, B);
+  TSFF_LAUNCH_OK("k_ff2v_params_bar");
   return TSFF_OK;
 }
 }  // namespace tsff

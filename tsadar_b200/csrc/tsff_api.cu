@@ -15,17 +15,20 @@ size_t table_ws_bytes(const tsff_ctx*, int64_t);
 int table_fwd(tsff_ctx*, int64_t, const double*, const void*, int, double*, double*, void*, void*, cudaStream_t);
 int table_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*, const double*, const double*, double*, void*,
               void*, cudaStream_t);
-int ff2v_fwd(tsff_ctx*, int64_t, const double*, const double*, double*, cudaStream_t);
+int ff2v_fwd(tsff_ctx*, int64_t, const double*, const double*, double*, void*, cudaStream_t);
+int ff2v_bwd(tsff_ctx*, int64_t, const double*, const double*, const void*, const double*, double*, double*, void*, cudaStream_t);
+size_t ff2v_saved_bytes(const tsff_ctx*, int64_t);
+size_t ff2v_ws_bytes(const tsff_ctx*, int64_t);
 }  // namespace tsff
 
 extern "C" size_t tsff_ff_saved_bytes(const tsff_ctx* c, int64_t B) {
   if (!c || B < 1) return 0;
-  if (c->mode == TSFF_MODE_2V) return 256;   // nothing saved: the 2V adjoint is not built yet
+  if (c->mode == TSFF_MODE_2V) return ff2v_saved_bytes(c, B);
   return c->mode == TSFF_MODE_TABLE ? table_saved_bytes(c, B) : direct_saved_bytes(c, B);
 }
 extern "C" size_t tsff_ff_workspace_bytes(const tsff_ctx* c, int64_t B) {
   if (!c || B < 1) return 0;
-  if (c->mode == TSFF_MODE_2V) return 256;
+  if (c->mode == TSFF_MODE_2V) return ff2v_ws_bytes(c, B);
   return c->mode == TSFF_MODE_TABLE ? table_ws_bytes(c, B) : direct_ws_bytes(c, B);
 }
 
@@ -47,7 +50,7 @@ extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const v
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->mode == TSFF_MODE_2V) {
     if (fe_dtype != TSFF_F64 || !ff_out || modl_out) { set_error("2V mode: fe must be float64 [B][V][V]; only ff_out is produced"); return TSFF_E_INVALID; }
-    return ff2v_fwd(c, B, params, static_cast<const double*>(fe), ff_out, st);
+    return ff2v_fwd(c, B, params, static_cast<const double*>(fe), ff_out, saved, st);
   }
   return c->mode == TSFF_MODE_TABLE ? table_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st)
                                     : direct_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st);
@@ -60,8 +63,11 @@ extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const v
   if (rc) return rc;
   if (!modl_bar && !ff_bar) { set_error("no cotangent given"); return TSFF_E_INVALID; }
   if (!params_bar || !fe_bar) { set_error("null output"); return TSFF_E_INVALID; }
-  if (c->mode == TSFF_MODE_2V) { set_error("the adjoint of the 2V path is not built yet (DESIGN.md)"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->mode == TSFF_MODE_2V) {
+    if (fe_dtype != TSFF_F64 || !ff_bar || modl_bar) { set_error("2V mode: fe float64, cotangent of the formfactor only"); return TSFF_E_INVALID; }
+    return ff2v_bwd(c, B, params, static_cast<const double*>(fe), saved, ff_bar, params_bar, static_cast<double*>(fe_bar), ws, st);
+  }
   return c->mode == TSFF_MODE_TABLE
              ? table_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
              : direct_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);

@@ -86,12 +86,12 @@ class FormFactor:
 
     def calc_in_2D(self, params):
         """-> formfactor [G,W,A], lams [1,W,1]   (form_factor.py:449-587).  params["electron"]["fe"] is the 2-D table
-        DF[V,V] on vx x vx.  FORWARD ONLY: the adjoint of the rotate/project stage is not built yet, so the result
-        carries no autograd graph (forward mode, tsadar/forward/calc_series.py, needs none)."""
+        DF[V,V] on vx x vx (one parameter set, as in the reference's angular spectypes).  Differentiable: the custom
+        Function calls tsff_ff_bwd (rotate/project adjoint, d/dbeta, kinematics reverse)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         ele = params["electron"]
         fe = ele["fe"] if isinstance(ele["fe"], torch.Tensor) else torch.as_tensor(np.asarray(ele["fe"]), dtype=torch.float64)
-        fe = fe.detach().to(device=dev, dtype=torch.float64)
+        fe = fe.to(device=dev, dtype=torch.float64)
         fe = fe.reshape((-1,) + tuple(fe.shape[-2:]))
         assert fe.shape[0] == 1 and fe.shape[1] == fe.shape[2], "calc_in_2D takes one 2-D table [V, V]"
         p1 = {k: (dict(v) if isinstance(v, dict) else v) for k, v in params.items()}
@@ -107,6 +107,5 @@ class FormFactor:
             self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, np.ones_like(sa),
                                                   self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle)
         eng = self._engines[key]
-        with torch.no_grad():
-            _, ff, _ = eng.forward(block.detach()[:1].contiguous(), fe.contiguous(), want_ff=True)
+        ff = form_factor_full(eng, block[:1].contiguous(), fe.contiguous())
         return ff[0], torch.as_tensor(self._lams, device=dev)
