@@ -23,7 +23,8 @@ def _grid(V):
 
 
 @pytest.mark.parametrize("V,W,sa,ud,Va,ud_ang,va_ang,G", [(32, 24, [40.0, 75.0, 120.0], 0.0, 0.0, 0.0, 0.0, 1),
-                                                           (48, 16, [60.0, 100.0], 0.4, -0.8, 30.0, 110.0, 2)])
+                                                           (48, 16, [60.0, 100.0], 0.4, -0.8, 30.0, 110.0, 2),
+                                                           (128, 5, [60.0, 130.0], 0.2, 0.3, 200.0, 45.0, 1)])   # arts-2d table size
 def test_calc_in_2D_matches_oracle(V, W, sa, ud, Va, ud_ang, va_ang, G):
     from tsadar_b200.form_factor import FormFactor
     vx = _grid(V)
@@ -100,3 +101,40 @@ def test_calc_in_2D_vjp_matches_autograd():
     assert np.abs(fb - gf).max() / np.abs(gf).max() < 1e-9, np.abs(fb - gf).max() / np.abs(gf).max()
     for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13]:
         assert abs(pb[k] - gp[k]) <= 1e-4 * max(abs(gp[k]), 1e-8 * np.abs(gp).max()), (k, pb[k], gp[k])
+
+
+def test_calc_in_2D_vjp_full_size_table_fd():
+    """V = 128 (the arts-2d table, 225 KB of shared memory in the adjoint kernel): the VJP against central differences of the
+    kernel's own forward for Te, ne and one table entry."""
+    from tsadar_b200.engine import FormFactorEngine
+    V, W = 128, 3
+    vx = _grid(V)
+    dv = vx[1] - vx[0]
+    X, Y = np.meshgrid(vx, vx, indexing="ij")
+    DF = np.exp(-0.5 * (X**2 + 1.3 * Y**2)) * (1 + 0.1 * X)
+    DF = np.clip(DF, 1e-30, None)
+    DF = DF / DF.sum() / dv**2
+    sa = np.array([60.0, 120.0])
+    row = np.array([[0.8, 0.3, 526.5, 0.3, 0.2, 0.0, 0.0, 1, 1, 1, 40.0, 8.0, 0.2, 1.0]])
+    eng = FormFactorEngine((450.0, 600.0), W, 0.0, sa, np.ones(2), 1, 1, vx, mode="2v", ud_ang=20.0, va_ang=70.0)
+    pt, ft = torch.tensor(row, device="cuda"), torch.tensor(DF[None], device="cuda")
+    _, ff, saved = eng.forward(pt, ft, want_ff=True)
+    rng = np.random.default_rng(0)
+    cot = torch.tensor(rng.normal(size=tuple(ff.shape)) / float(ff.abs().max()), device="cuda")
+    pb, fb = eng.backward(pt, ft, saved, ff_bar=cot)
+    assert torch.isfinite(pb).all() and torch.isfinite(fb).all()
+
+    def L(rw, tab):
+        _, f2, _ = eng.forward(torch.tensor(rw, device="cuda"), torch.tensor(tab[None], device="cuda"), want_ff=True)
+        return float((f2 * cot).sum())
+    for k, h in ((0, 1e-6), (1, 1e-6)):
+        rp, rm = row.copy(), row.copy()
+        rp[0, k] += h; rm[0, k] -= h
+        fd = (L(rp, DF) - L(rm, DF)) / (2 * h)
+        assert abs(pb[0, k].item() - fd) <= 2e-4 * abs(fd), (k, pb[0, k].item(), fd)
+    i, j = 70, 61
+    h = 1e-4 * DF[i, j]
+    Dp, Dm = DF.copy(), DF.copy()
+    Dp[i, j] += h; Dm[i, j] -= h
+    fd = (L(row, Dp) - L(row, Dm)) / (2 * h)
+    assert abs(fb[0, i, j].item() - fd) <= 1e-4 * abs(fd), (fb[0, i, j].item(), fd)

@@ -534,7 +534,7 @@ int ff2v_bwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, con
   TSFF_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)B * c->G * kLGDoubles * 8, st));
   const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
   const size_t smem = (((size_t)V * (V + 1) * 4 + 15) / 16) * 16 + ((size_t)V * (V + 1) + (size_t)NG * V * 3 + (size_t)NG * 32) * 8;
-  TSFF_SMEM_OPTIN(k_ff2v_bwd);
+  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));  // 225 KB at V = 128
   const long long nbatch = ((long long)a.P + NG - 1) / NG;
   const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
   for (int64_t b = 0; b < B; b++) {

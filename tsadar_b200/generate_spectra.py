@@ -19,12 +19,13 @@ class FitModel:
         assert gen["Te_gradient"]["num_grad_points"] == gen["ne_gradient"]["num_grad_points"], \
             "Number of gradient points for Te and ne must be the same"
         G = gen["Te_gradient"]["num_grad_points"]
-        if config["parameters"]["electron"]["fe"]["dim"] != 1:
-            raise NotImplementedError("2V distributions (calc_in_2D) are not built yet")
+        self.dim = int(config["parameters"]["electron"]["fe"]["dim"])
         oth = config["other"]
         self.electron_form_factor = FormFactor(oth["lamrangE"], npts=oth["npts"], lam_shift=config["data"]["ele_lam_shift"],
-                                               scattering_angles=scattering_angles, num_grad_points=G, va_ang=None,
-                                               ud_ang=None, mode=mode, pv_precision=pv_precision)
+                                               scattering_angles=scattering_angles, num_grad_points=G,
+                                               va_ang=config["parameters"]["general"].get("Va", {}).get("angle", 0.0) if self.dim == 2 else None,
+                                               ud_ang=config["parameters"]["general"].get("ud", {}).get("angle", 0.0) if self.dim == 2 else None,
+                                               mode=mode, pv_precision=pv_precision)
         self.ion_form_factor = FormFactor(oth["lamrangI"], npts=oth["npts"], lam_shift=0, scattering_angles=scattering_angles,
                                           num_grad_points=G, va_ang=None, ud_ang=None, mode=mode, pv_precision=pv_precision)
         # `weights[0]`: a scalar when `sa` comes straight from get_scattering_angles (tests, forward mode), the per-angle
@@ -57,7 +58,8 @@ class FitModel:
 
     def electron_spectrum(self, all_params):
         if self.config["other"]["extraoptions"]["load_ele_spec"] and self.angular_full:
-            ff, _ = self.electron_form_factor(all_params)                       # [G, W, A] (one parameter set per image)
+            # generate_spectra.py:185-188: 1V table or 2V table (calc_in_2D); [G, W, A], one parameter set per image
+            ff, _ = self.electron_form_factor(all_params) if self.dim == 1 else self.electron_form_factor.calc_in_2D(all_params)
             if ff.dim() == 4:
                 assert ff.shape[0] == 1, "angular_full takes a single parameter set (thomson_diagnostic.py:37-38)"
                 ff = ff[0]
@@ -72,6 +74,8 @@ class FitModel:
             block, _, _, _, _ = pack_params(all_params, dev)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
             return lamE, modlE, block
+        if self.config["other"]["extraoptions"]["load_ele_spec"] and self.dim == 2:
+            raise NotImplementedError("2V distributions with a temporal/imaging spectype: no reference deck (calc_in_2D is wired for angular_full)")
         if self.config["other"]["extraoptions"]["load_ele_spec"]:
             modlE, block = self.electron_form_factor.modl(all_params, self._w, jmul=self._jmulE)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
