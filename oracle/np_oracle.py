@@ -402,11 +402,14 @@ def form_factor_2d(params, grids, sa_deg, num_grad_points=1, lam_shift=0.0, ud_a
 # a7: FitModel (generate_spectra.py:139-220), temporal / 1d spectype
 # --------------------------------------------------------------------------------------
 def fit_model_electron(params, grids, sa, cfg_other, num_grad_points=1, lam_shift=0.0, mode="table",
-                       angular_full=False):
+                       angular_full=False, ud_ang=0.0, va_ang=0.0):
     """electron_spectrum (generate_spectra.py:171-220).  ``sa`` = {"sa": deg[A], "weights": ...}.
-    cfg_other needs: iawoff, iawfilter, lamrangE."""
-    ff = form_factor_1v if mode == "table" else form_factor_direct
-    ThryE, lamAxisE = ff(params, grids, sa["sa"], num_grad_points, lam_shift)
+    cfg_other needs: iawoff, iawfilter, lamrangE.  A 2-D params["electron"]["fe"] takes calc_in_2D (:185-188)."""
+    if np.ndim(params["electron"]["fe"]) == 2:
+        ThryE, lamAxisE = form_factor_2d(params, grids, sa["sa"], num_grad_points, lam_shift, ud_ang, va_ang)
+    else:
+        ff = form_factor_1v if mode == "table" else form_factor_direct
+        ThryE, lamAxisE = ff(params, grids, sa["sa"], num_grad_points, lam_shift)
     lamAxisE = np.squeeze(lamAxisE) * 1e7  # :191
     ThryE = np.mean(ThryE, axis=0)  # :193  [W,A]
     if angular_full:
@@ -554,7 +557,9 @@ def diagnostic_arts(params, cfg, sa, batch, mode="table"):
     oth = cfg["other"]
     G = cfg["parameters"]["general"]["Te_gradient"]["num_grad_points"]
     gE = Grids(oth["lamrangE"], oth["npts"])
-    lamE, modlE = fit_model_electron(params, gE, sa, oth, G, cfg["data"]["ele_lam_shift"], mode, angular_full=True)
+    gen_cfg = cfg["parameters"]["general"]
+    lamE, modlE = fit_model_electron(params, gE, sa, oth, G, cfg["data"]["ele_lam_shift"], mode, angular_full=True,
+                                     ud_ang=gen_cfg["ud"].get("angle", 0.0), va_ang=gen_cfg["Va"].get("angle", 0.0))
     wid = oth["PhysParams"]["widIRF"]
     lamE, ThryE = add_ats_irf(lamE, sa["angAxis"], modlE, wid["spect_FWHM_ele"], wid["ang_FWHM_ele"], oth["PhysParams"]["norm"])
     gen = params["general"]

@@ -137,6 +137,97 @@ def arbitrary1v_call(vx, fval):
     return f / np.sum(f) / (vx[1] - vx[0])
 
 
+# ---- 2V producers (base.py:335-426, spherical_harmonics.py:59-318) ---------------------------------------------------
+def smooth1d(array, window_size):
+    """base.py:17-38."""
+    window = np.hanning(window_size)
+    window = window / window.sum()
+    return np.convolve(array, window, mode="same")
+
+
+def arbitrary2v_init(nvx, init_m, learn_log):
+    """Arbitrary2V.init_dlm (base.py:374-405)."""
+    vx = vgrid(nvx)
+    vth_x = np.sqrt(2.0)
+    alpha = np.sqrt(3.0 * gamma(3.0 / init_m) / 2.0 / gamma(5.0 / init_m))
+    cst = init_m / (4.0 * np.pi * alpha**3.0 * gamma(3.0 / init_m))
+    fdlm = cst / vth_x**3.0 * np.exp(-((np.sqrt(vx[:, None] ** 2.0 + vx[None, :] ** 2.0) / alpha / vth_x) ** init_m))
+    fdlm = fdlm / np.sum(fdlm) / (vx[1] - vx[0]) ** 2.0
+    if learn_log:
+        fdlm = -np.log10(fdlm)
+    return vx, np.sqrt(fdlm)
+
+
+def arbitrary2v_call(vx, fval, learn_log):
+    """Arbitrary2V.__call__ (base.py:410-426)."""
+    f = fval**2.0
+    if learn_log:
+        f = np.power(10.0, -f)
+    return f / np.sum(f) / (vx[1] - vx[0]) ** 2.0
+
+
+def flm_mora_yahi(vr, log_10_LT, m_f0, f00):
+    """FLM_MY.__call__ (spherical_harmonics.py:94-117)."""
+    v0 = 1.0
+    lambda_e = 1.0
+    ve = gamma(5.0 / m_f0) / 3 / gamma(3.0 / m_f0) * v0
+    uu = vr / v0
+    lambda_v = lambda_e * (vr / ve) ** 4.0
+    coeff = (m_f0 / 2 * uu**m_f0 - 5 * m_f0 / 12 * gamma(8 / m_f0) / gamma(6 / m_f0) * uu ** (m_f0 - 2) - 1.5) * lambda_v
+    return coeff / 10**log_10_LT * f00
+
+
+def flm_arbitrary_vr(flm_sign, flm_mag):
+    """ArbitraryVr.__call__ (spherical_harmonics.py:142-147)."""
+    nvr = flm_sign.size
+    sign = np.tanh(smooth1d(flm_sign, nvr // 4))
+    mag = -sigmoid(smooth1d(flm_mag, nvr // 4)) * 10
+    return 10**mag * sign
+
+
+def spherical_harmonics_fe(dist_cfg, normed_m=None, flm_leaves=None):
+    """SphericalHarmonics.__init__ + __call__ (spherical_harmonics.py:199-247, 267-318) -> vx, f[V, V].
+    `normed_m` / `flm_leaves[(l, m)]` override the initial trainable values ({"log_10_LT": x} for mora-yahi,
+    {"flm_sign": a, "flm_mag": b} for arbitrary).  jax.scipy.special.sph_harm(m, n, theta=azimuth, phi=polar) is restated
+    with scipy.special.sph_harm_y(n, m, polar, azimuth); JAX builds P_l^m from sqrt(1 - cos^2(polar)) >= 0, i.e. the polar
+    angle folded into [0, pi], whatever the sign of arctan2(vy, vx)."""
+    from scipy.special import sph_harm_y
+    p = dist_cfg["params"]
+    vx = vgrid(dist_cfg["nvx"])
+    vmax = 6.0 * 1.05 * np.sqrt(2.0)
+    dvr = vmax / p["nvr"]
+    vr = np.linspace(dvr / 2, vmax - dvr / 2, p["nvr"])
+    VX, VY = np.meshgrid(vx, vx)
+    th = np.arctan2(VY, VX)
+    phi = np.arccos(VY / np.abs(VY))
+    vr_vxvy = np.sqrt(VX**2 + VY**2)
+    if normed_m is None:
+        normed_m = np.log(1e-2 + ((p["init_m"] - 2.0) / 3.0) / (1 - (p["init_m"] - 2.0) / 3.0 + 1e-2))
+    m_f0 = sigmoid(normed_m) * 3.0 + 2.0
+    v0 = 1.0 / np.sqrt(gamma(5.0 / m_f0) / 3.0 / gamma(3.0 / m_f0))
+    cst = m_f0 / (4 * np.pi * gamma(3.0 / m_f0))
+    f00 = cst / v0**3.0 * np.exp(-((vr / v0) ** m_f0))
+    f00 = f00 / (np.sum(f00 * 4 * np.pi * vr**2.0) * (vr[1] - vr[0]))
+    f = np.interp(vr_vxvy, vr, f00, right=1e-16)
+    typ = p["flm_type"].casefold()
+    for l in range(1, p["Nl"] + 1):
+        for m in range(l + 1):
+            lv = (flm_leaves or {}).get((l, m), {})
+            if typ == "mora-yahi":
+                LT = {(1, 0): p["LTx"], (1, 1): p["LTy"]}[(l, m)]
+                flm = flm_mora_yahi(vr, lv.get("log_10_LT", np.log10(LT)), m_f0, f00)
+            elif typ == "arbitrary":
+                flm = flm_arbitrary_vr(lv.get("flm_sign", np.zeros(p["nvr"])), lv.get("flm_mag", np.zeros(p["nvr"])))
+            else:
+                raise NotImplementedError(typ)
+            flm_xy = np.interp(vr_vxvy, vr, flm, right=1e-32)
+            ylm = sph_harm_y(l, m, np.arccos(np.cos(th.reshape(-1))), phi.reshape(-1)).reshape(vr_vxvy.shape)
+            f = f + flm_xy * np.real(ylm)
+    f = np.maximum(f, 1e-32)
+    f = f / (np.sum(f) * (vx[1] - vx[0]) * (vx[1] - vx[0]))
+    return vx, f
+
+
 def thomson_params(param_cfg, activate=True, dlm_m_offset=0.0):
     """ThomsonParams(...)() for ONE lineout (ts_params.py:583-603): nested dict of physical scalars +
     fe/v.  ``dlm_m_offset`` shifts the DLM order m (used only to quantify the effect of the missing
@@ -147,9 +238,15 @@ def thomson_params(param_cfg, activate=True, dlm_m_offset=0.0):
         out["electron"][p] = scalar_physical(ecfg[p], activate)
     fe_cfg = ecfg["fe"]
     typ = fe_cfg["type"].casefold()
-    if fe_cfg["dim"] != 1:
-        raise NotImplementedError("2V parameter producer: see oracle.np_oracle_2v")
-    if typ == "dlm":
+    if fe_cfg["dim"] == 2:
+        if "sph" in typ:
+            vx, fe = spherical_harmonics_fe(fe_cfg)
+        elif typ == "arbitrary":
+            vx, fval = arbitrary2v_init(fe_cfg["nvx"], fe_cfg["params"]["init_m"], fe_cfg["params"]["learn_log"])
+            fe = arbitrary2v_call(vx, fval, fe_cfg["params"]["learn_log"])
+        else:
+            raise NotImplementedError(typ)
+    elif typ == "dlm":
         m = dlm_m_physical(fe_cfg, activate) + dlm_m_offset
         vx, fe = dlm1v(fe_cfg["nvx"], m)
         out["electron"]["m"] = m

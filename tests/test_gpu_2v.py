@@ -138,3 +138,43 @@ def test_calc_in_2D_vjp_full_size_table_fd():
     Dp[i, j] += h; Dm[i, j] -= h
     fd = (L(row, Dp) - L(row, Dm)) / (2 * h)
     assert abs(fb[0, i, j].item() - fd) <= 1e-4 * abs(fd), (fb[0, i, j].item(), fd)
+
+
+def test_arts2v_diagnostic_with_spherical_harmonics_matches_oracle():
+    """test_arts2d_forward_pass (tests/test_forward/test_angular_2v.py:18-94) at a reduced size: SphericalHarmonics
+    (Mora-Yahi l=1) producer -> calc_in_2D over the 241 ARTS angles -> [1024, 241] weight matrix -> ATS IRF ->
+    resolution units, against the NumPy oracle of the same chain.  PARITY UNPINNED (ThryE-arts2v.npy is a missing blob)."""
+    import os
+    from oracle import params_oracle as P
+    from tests.common import load_cfg
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_arts2v")
+    npts = 32
+    cfg["other"]["lamrangE"] = [cfg["data"]["fit_rng"]["forward_epw_start"], cfg["data"]["fit_rng"]["forward_epw_end"]]
+    cfg["other"]["lamrangI"] = [cfg["data"]["fit_rng"]["forward_iaw_start"], cfg["data"]["fit_rng"]["forward_iaw_end"]]
+    cfg["other"]["npts"] = npts
+    cfg["other"]["extraoptions"]["spectype"] = "angular_full"
+    cfg["parameters"]["electron"]["fe"]["nvx"] = 24
+    cfg["parameters"]["electron"]["fe"]["params"]["nvr"] = 16
+    cfg["parameters"]["electron"]["fe"]["params"]["LTx"] = 60.0      # visible anisotropy at this resolution
+    cfg["parameters"]["electron"]["fe"]["params"]["LTy"] = 90.0
+    tab = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tsadar_b200", "data", "arts_angles.npz"))
+    sa = dict(sa=np.arange(19, 139.5, 0.5), weights=tab["weightMatrix"], angAxis=tab["angsFRED"])
+    n_lam = npts // 2
+    batch = dict(i_data=np.ones((1024, n_lam)), e_data=np.ones((1024, n_lam)), noise_e=np.array([0.0]), noise_i=np.array([0.0]),
+                 e_amps=np.array([1.0]), i_amps=np.array([1.0]))
+    p = P.thomson_params(cfg["parameters"], activate=False)
+    assert np.ndim(p["electron"]["fe"]) == 2
+    ref, lamb, _ = O.diagnostic_arts(p, cfg, sa, batch)
+    ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=sa)
+    ts_params = ThomsonParams(cfg["parameters"], num_params=1, batch=False)        # the reference's call (:81)
+    ThryE, _, lamE, _ = ts_diag(ts_params, batch)
+    got = ThryE.detach().cpu().numpy()
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(lamE, lamb, rtol=1e-13)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-8
+    # and the chain is differentiable down to the producer's leaves (m of f00, log10 LTx, log10 LTy)
+    (ThryE * ThryE).sum().backward()
+    g = [t.grad for t in ts_params.parameters()]
+    assert len(g) == 3 and all(x is not None and torch.isfinite(x).all() for x in g) and all(float(x.abs()) > 0 for x in g)

@@ -1,6 +1,6 @@
-"""ThomsonParams -- torch mirror of tsadar.core.modules.ts_params.ThomsonParams (ts_params.py:498-645) for 1V
-distributions: normalised trainable leaves, sigmoid/affine de-normalisation, ion-fraction renormalisation, and the
-f(v) producers DLM1V / 'mx' / Arbitrary1V (distribution_functions/base.py).
+"""ThomsonParams -- torch mirror of tsadar.core.modules.ts_params.ThomsonParams (ts_params.py:498-645) :
+normalised trainable leaves, sigmoid/affine de-normalisation, ion-fraction renormalisation, and the f(v) producers
+DLM1V / 'mx' (here) and Arbitrary1V / Arbitrary2V / SphericalHarmonics (tsadar_b200/distribution_functions.py).
 
 The reference keeps this stage in JAX (out of scope for the kernels, "next" row N3); it is
 mirrored here only so that the drop-in tests read like the reference's.  It is cheap elementwise host-side glue in torch
@@ -10,6 +10,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 from scipy.special import gamma, gammaincc
+
+from .distribution_functions import Arbitrary1V, Arbitrary2V, SphericalHarmonics
 
 DT = torch.float64
 
@@ -73,12 +75,25 @@ class ThomsonParams:
             self.leaves[(ion, "Z")] = _Scalar(c["Z"], B, activate, dev)
             self.leaves[(ion, "fract")] = _Scalar(c["fract"], B, activate, dev, raw=True)
         fe = e["fe"]
-        if fe["dim"] != 1:
-            raise NotImplementedError("2V distributions are not built yet")
         self.fe_type = fe["type"].casefold()
+        self.fe_dim = int(fe["dim"])
         self.vx = vgrid(fe["nvx"])
         self.dv = self.vx[1] - self.vx[0]
-        if self.fe_type == "dlm":
+        self.dist = None
+        fe_trainable = bool(fe.get("active", False))      # get_filter_spec: fe leaves follow cfg["fe"]["active"] alone
+        if self.fe_dim == 2:
+            # ElectronParams.init_dists (ts_params.py:155-166): one table per image, no batch mode
+            if batch:
+                raise NotImplementedError("Batch mode not implemented for 2D distributions as a precautionary measure against memory issues")
+            if "sph" in self.fe_type:
+                self.dist = SphericalHarmonics(fe, dev, fe_trainable)
+            elif self.fe_type == "arbitrary":
+                self.dist = Arbitrary2V(fe, dev, fe_trainable)
+            else:
+                raise NotImplementedError(f"Unknown 2D distribution type: {fe['type']}")
+        elif self.fe_dim != 1:
+            raise NotImplementedError(f"Not implemented distribution dimension: {fe['dim']}")
+        elif self.fe_type == "dlm":
             mcfg = dict(val=fe["params"]["m"]["val"], lb=2.0, ub=5.0, active=fe.get("active", False))  # scale 3, shift 2
             self.leaves[("electron", "m")] = _Scalar(mcfg, B, activate, dev)
             self.m_offset = float(dlm_m_offset)
@@ -89,14 +104,20 @@ class ThomsonParams:
             f = np.exp(-(self.vx**2 / 2))
             self.f_fixed = torch.tensor(f / f.sum() / self.dv, dtype=DT, device=dev)
         elif self.fe_type == "arbitrary":
-            raise NotImplementedError("Arbitrary1V producer (Butterworth-smoothed learned f): next row N3")
+            self.dist = Arbitrary1V(fe, B, dev, fe_trainable)
         else:
-            raise NotImplementedError(self.fe_type)
+            raise NotImplementedError(f"Unknown 1D distribution type: {fe['type']}")
 
     def parameters(self):
-        return [s.value for s in self.leaves.values() if s.active]
+        """The trainable leaves (what eqx.partition(ts_params, get_filter_spec(...)) selects, ts_params.py:648-685)."""
+        out = [s.value for s in self.leaves.values() if s.active]
+        if self.dist is not None:
+            out += [t for t in self.dist.leaves().values() if t.requires_grad]
+        return out
 
     def _fe(self):
+        if self.dist is not None:
+            return self.dist()
         if self.fe_type == "mx":
             return self.f_fixed.reshape(1, -1).expand(self.B, -1)
         m = self.leaves[("electron", "m")].physical() + self.m_offset          # base.py:286
@@ -107,7 +128,7 @@ class ThomsonParams:
 
     def __call__(self):
         out = {"electron": {"Te": self.leaves[("electron", "Te")].physical(), "ne": self.leaves[("electron", "ne")].physical(),
-                            "fe": self._fe(), "v": np.broadcast_to(self.vx, (self.B, self.vx.size))},
+                            "fe": self._fe(), "v": self.vx if self.fe_dim == 2 else np.broadcast_to(self.vx, (self.B, self.vx.size))},
                "general": {k: self.leaves[("general", k)].physical() for k in
                            ["lam", "amp1", "amp2", "amp3", "ne_gradient", "Te_gradient", "ud", "Va"]}}
         fsum = 0
@@ -125,6 +146,12 @@ class ThomsonParams:
 
     def get_unnormed_params(self):
         p = self()
-        if self.fe_type == "dlm":
+        if self.fe_dim == 1 and self.fe_type == "dlm":
             p["electron"]["m"] = self.leaves[("electron", "m")].physical()
+        elif self.fe_dim == 1 and self.fe_type == "arbitrary":
+            p["electron"]["f"] = p["electron"]["fe"]
+        elif isinstance(self.dist, SphericalHarmonics):
+            p["electron"].update(self.dist.get_unnormed_params())
+        elif isinstance(self.dist, Arbitrary2V):
+            p["electron"]["f"] = p["electron"]["fe"]
         return p
