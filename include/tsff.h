@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TSFF_ABI_VERSION 2
+#define TSFF_ABI_VERSION 3
 #define TSFF_MAX_IONS 4
 
 enum {
@@ -76,6 +76,12 @@ typedef struct tsff_static_cfg {
   int32_t zp_n;
   int32_t reserved;
   double ud_angle_deg, va_angle_deg; /* FormFactor(ud_ang=..., va_ang=...): directions of drift and flow, 2V mode (form_factor.py:501-504) */
+  /* Wavelength shard (ARTS multi-GPU, the W-axis sharding of form_factor.py:431-447): this context covers the W points
+   * [w_offset, w_offset + W) of lamAxis = linspace(lam_min, lam_max, W_total), computed exactly as the full axis would be.
+   * W_total == 0 means the whole axis (W_total = W, w_offset = 0).  jmul is the LOCAL slice [W].  In table mode the
+   * forward difference along omega (form_factor.py:258-261) of the last local point is 0, as at the end of the full
+   * axis: a shard that is not the last one includes one halo point and drops its output. */
+  int32_t W_total, w_offset;
 } tsff_static_cfg;
 
 /* ---- context ------------------------------------------------------------------------------------------ */

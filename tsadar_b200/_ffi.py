@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libtsff.so")
 
-TSFF_ABI_VERSION = 2
+TSFF_ABI_VERSION = 3
 TSFF_MODE_TABLE, TSFF_MODE_DIRECT, TSFF_MODE_2V = 0, 1, 2
 TSFF_F32, TSFF_F64 = 0, 1
 TSFF_PV_FP32, TSFF_PV_FP64 = 0, 1
@@ -35,6 +35,7 @@ class StaticCfg(C.Structure):
         ("zp_x", C.POINTER(C.c_double)), ("zp_re", C.POINTER(C.c_double)), ("zp_im", C.POINTER(C.c_double)),
         ("zp_n", C.c_int32), ("reserved", C.c_int32),
         ("ud_angle_deg", C.c_double), ("va_angle_deg", C.c_double),
+        ("W_total", C.c_int32), ("w_offset", C.c_int32),
     ]
 
 

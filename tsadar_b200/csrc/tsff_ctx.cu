@@ -67,9 +67,12 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   const int W = c->W, A = c->A;
   std::vector<double> h_omgs(W), h_lam(W), h_cos(A), h_sin(A), h_w(A), h_jmul(W), h_zr(kXi2N), h_zi(kXi2N), h_xi2(kXi2N);
   // jnp.linspace(l0, l1, W): start + i*step, endpoint exact
-  const double step = (c->lam_max - c->lam_min) / (double)(W - 1);
+  const int Wt = cfg->W_total > 0 ? cfg->W_total : W, w0 = cfg->W_total > 0 ? cfg->w_offset : 0;
+  if (w0 < 0 || w0 + W > Wt) { delete c; set_error("wavelength shard [%d, %d) outside the axis of %d points", w0, w0 + W, Wt); return TSFF_E_INVALID; }
+  const double step = (c->lam_max - c->lam_min) / (double)(Wt - 1);
   for (int j = 0; j < W; j++) {
-    double lam = (j == W - 1) ? c->lam_max : c->lam_min + (double)j * step;
+    const int jg = w0 + j;
+    double lam = (jg == Wt - 1) ? c->lam_max : c->lam_min + (double)jg * step;
     h_omgs[j] = 2e7 * kPi * kC / lam;                 // form_factor.py:134
     h_lam[j] = (2.0 * kPi * kC / h_omgs[j]) * 1e7;    // lams (form_factor.py:293) * 1e7 (generate_spectra.py:163,191)
     h_jmul[j] = cfg->jmul ? cfg->jmul[j] : 1.0;

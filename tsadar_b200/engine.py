@@ -36,7 +36,9 @@ class FormFactorEngine:
     form_factor.py:120-161) bound to one GPU."""
 
     def __init__(self, lambda_range, npts, lam_shift, sa_deg, weights, num_grad_points, n_ions, vx, mode="table",
-                 jmul=None, pv_precision="fp32", device=None, ud_ang=0.0, va_ang=0.0):
+                 jmul=None, pv_precision="fp32", device=None, ud_ang=0.0, va_ang=0.0, w_slice=None):
+        """w_slice = (j0, j1): this engine covers the wavelength points [j0, j1) of linspace(lambda_range, npts) (the
+        W-axis shard of one rank, tsadar_b200/parallel.py); jmul is then the local slice."""
         if not torch.cuda.is_available():
             raise RuntimeError("tsadar_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -51,7 +53,10 @@ class FormFactorEngine:
         weights = np.ascontiguousarray(weights.reshape(-1))
         if weights.shape != sa_deg.shape:
             raise ValueError("weights must have one entry per scattering angle")
-        self.W, self.A, self.G, self.I, self.V = int(npts), int(sa_deg.size), int(num_grad_points), int(n_ions), int(vx.size)
+        j0, j1 = (0, int(npts)) if w_slice is None else (int(w_slice[0]), int(w_slice[1]))
+        if not (0 <= j0 < j1 <= int(npts)):
+            raise ValueError(f"w_slice {w_slice} outside [0, {npts})")
+        self.W, self.A, self.G, self.I, self.V = j1 - j0, int(sa_deg.size), int(num_grad_points), int(n_ions), int(vx.size)
         self.NP = _ffi.P_ION0 + _ffi.ION_STRIDE * self.I
         self.mode = mode
         zx, zr, zi = _zprime_table()
@@ -60,6 +65,7 @@ class FormFactorEngine:
         cfg.mode = {"table": _ffi.TSFF_MODE_TABLE, "direct": _ffi.TSFF_MODE_DIRECT, "2v": _ffi.TSFF_MODE_2V}[mode]
         cfg.ud_angle_deg, cfg.va_angle_deg = float(ud_ang or 0.0), float(va_ang or 0.0)
         cfg.W, cfg.A, cfg.G, cfg.I, cfg.V = self.W, self.A, self.G, self.I, self.V
+        cfg.W_total, cfg.w_offset = int(npts), j0
         cfg.pv_precision = _ffi.TSFF_PV_FP64 if pv_precision == "fp64" else _ffi.TSFF_PV_FP32
         cfg.lam_min, cfg.lam_max, cfg.lam_shift = float(lambda_range[0]), float(lambda_range[1]), float(lam_shift)
         cfg.v0, cfg.dv = float(vx[0]), dv
@@ -72,7 +78,7 @@ class FormFactorEngine:
         self._ctx = C.c_void_p()
         _ffi.check(_ffi.lib().tsff_ctx_create(self.device.index, C.byref(cfg), C.byref(self._ctx)))
         # wavelength axis in nm as FitModel returns it (lams * 1e7, generate_spectra.py:163,191)
-        lam = np.linspace(cfg.lam_min, cfg.lam_max, self.W)
+        lam = np.linspace(cfg.lam_min, cfg.lam_max, int(npts))[j0:j1]
         omgs = 2e7 * np.pi * 2.99792458e10 / lam
         self.lam_cm = 2 * np.pi * 2.99792458e10 / omgs
         self._buf = {}

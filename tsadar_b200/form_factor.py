@@ -45,7 +45,7 @@ def pack_params(params, device):
 
 class FormFactor:
     def __init__(self, lambda_range, npts, lam_shift, scattering_angles, num_grad_points, ud_ang, va_ang, mode="table",
-                 pv_precision="fp32"):
+                 pv_precision="fp32", w_shard=None):
         # form_factor.py:120-161 -- the static grids live in the libtsff context, created lazily once the f-grid is seen
         self.lambda_range = [float(lambda_range[0]), float(lambda_range[1])]
         self.npts = int(npts)
@@ -55,9 +55,21 @@ class FormFactor:
         self.ud_angle, self.va_angle = ud_ang, va_ang
         self.mode, self.pv_precision = mode, pv_precision
         self._engines = {}
+        # w_shard (parallel.WShard): this instance evaluates only its rank's wavelengths [j0, j1e) of the axis; operands pass
+        # through copy_to_shards so that their cotangents are summed over the ranks in the backward pass
+        self.w_shard = w_shard
+        self._w_slice = None if w_shard is None else (w_shard.j0, w_shard.j1e)
         lam = np.linspace(self.lambda_range[0], self.lambda_range[1], self.npts)
+        if self._w_slice is not None:
+            lam = lam[self._w_slice[0]:self._w_slice[1]]
         omgs = 2e7 * np.pi * C_CM / lam
         self._lams = (2 * np.pi * C_CM / omgs)[None, :, None]
+
+    def _enter(self, t):
+        if self.w_shard is None:
+            return t
+        from .parallel import copy_to_shards
+        return copy_to_shards(t, self.w_shard.group)
 
     def engine(self, vx, n_ions, weights=None, jmul=None):
         key = (vx.size, float(vx[0]), float(vx[1] - vx[0]), n_ions, None if weights is None else tuple(np.ravel(weights)),
@@ -66,7 +78,8 @@ class FormFactor:
             sa = np.asarray(self.scattering_angles["sa"], dtype=np.float64).reshape(-1)
             w = np.ones_like(sa) if weights is None else weights
             self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, w, self.num_grad_points,
-                                                  n_ions, vx, mode=self.mode, jmul=jmul, pv_precision=self.pv_precision)
+                                                  n_ions, vx, mode=self.mode, jmul=jmul, pv_precision=self.pv_precision,
+                                                  w_slice=self._w_slice)
         return self._engines[key]
 
     def __call__(self, params):
@@ -74,7 +87,7 @@ class FormFactor:
         dev = torch.device("cuda", torch.cuda.current_device())
         block, fe, vx, batched, nI = pack_params(params, dev)
         eng = self.engine(vx, nI)
-        ff = form_factor_full(eng, block, fe)
+        ff = form_factor_full(eng, self._enter(block), self._enter(fe))
         return (ff if batched else ff[0]), torch.as_tensor(self._lams, device=dev)
 
     def modl(self, params, weights, jmul=None):
@@ -105,7 +118,8 @@ class FormFactor:
         if key not in self._engines:
             sa = np.asarray(self.scattering_angles["sa"], dtype=np.float64).reshape(-1)
             self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, np.ones_like(sa),
-                                                  self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle)
+                                                  self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle,
+                                                  w_slice=self._w_slice)
         eng = self._engines[key]
-        ff = form_factor_full(eng, block[:1].contiguous(), fe.contiguous())
+        ff = form_factor_full(eng, self._enter(block[:1].contiguous()), self._enter(fe.contiguous()))
         return ff[0], torch.as_tensor(self._lams, device=dev)

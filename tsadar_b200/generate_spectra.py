@@ -12,7 +12,9 @@ from .form_factor import FormFactor, pack_params
 
 
 class FitModel:
-    def __init__(self, config, scattering_angles, mode="table", pv_precision="fp32"):
+    def __init__(self, config, scattering_angles, mode="table", pv_precision="fp32", shard_group=False):
+        """shard_group: False = single GPU; None or a process group = "angular_full" spectra are evaluated W-sharded over
+        that group's ranks (tsadar_b200/parallel.py), every rank returning the full modlE."""
         self.config = config
         self.scattering_angles = scattering_angles
         gen = config["parameters"]["general"]
@@ -21,11 +23,16 @@ class FitModel:
         G = gen["Te_gradient"]["num_grad_points"]
         self.dim = int(config["parameters"]["electron"]["fe"]["dim"])
         oth = config["other"]
+        self.w_shard = None
+        if shard_group is not False and config["other"]["extraoptions"]["spectype"] == "angular_full":
+            from .parallel import WShard, _active
+            if _active(shard_group):
+                self.w_shard = WShard(oth["npts"], group=shard_group, halo=(self.dim == 1 and mode == "table"))
         self.electron_form_factor = FormFactor(oth["lamrangE"], npts=oth["npts"], lam_shift=config["data"]["ele_lam_shift"],
                                                scattering_angles=scattering_angles, num_grad_points=G,
                                                va_ang=config["parameters"]["general"].get("Va", {}).get("angle", 0.0) if self.dim == 2 else None,
                                                ud_ang=config["parameters"]["general"].get("ud", {}).get("angle", 0.0) if self.dim == 2 else None,
-                                               mode=mode, pv_precision=pv_precision)
+                                               mode=mode, pv_precision=pv_precision, w_shard=self.w_shard)
         self.ion_form_factor = FormFactor(oth["lamrangI"], npts=oth["npts"], lam_shift=0, scattering_angles=scattering_angles,
                                           num_grad_points=G, va_ang=None, ud_ang=None, mode=mode, pv_precision=pv_precision)
         # `weights[0]`: a scalar when `sa` comes straight from get_scattering_angles (tests, forward mode), the per-angle
@@ -68,9 +75,16 @@ class FitModel:
             wm = getattr(self, "_wmat_dev", None)
             if wm is None or wm.device != dev:
                 wm = self._wmat_dev = torch.tensor(self._wmat, dtype=torch.float64, device=dev)
+            jm = self._jmulE
+            if self.w_shard is not None:                                         # this rank's wavelengths, halo dropped
+                ThryE = ThryE[: self.w_shard.keep]
+                jm = None if jm is None else jm[self.w_shard.j0:self.w_shard.j1]
             modlE = torch.matmul(wm, ThryE.t())                                  # :194-195  [1024, W]
-            if self._jmulE is not None:
-                modlE = modlE * torch.tensor(self._jmulE, dtype=torch.float64, device=dev)   # :210-216
+            if jm is not None:
+                modlE = modlE * torch.tensor(jm, dtype=torch.float64, device=dev)   # :210-216
+            if self.w_shard is not None:
+                from .parallel import gather_columns
+                modlE = gather_columns(modlE.contiguous(), self.w_shard.npts, self.w_shard.group)
             block, _, _, _, _ = pack_params(all_params, dev)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
             return lamE, modlE, block

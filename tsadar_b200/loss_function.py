@@ -25,7 +25,7 @@ class _LossFn(torch.autograd.Function):
 
 
 class LossFunction:
-    def __init__(self, cfg, scattering_angles, dummy_batch, mode="table", pv_precision="fp32"):
+    def __init__(self, cfg, scattering_angles, dummy_batch, mode="table", pv_precision="fp32", shard_group=False):
         self.cfg = cfg
         if cfg["optimizer"]["y_norm"]:
             self.i_norm = float(np.amax(np.asarray(dummy_batch["i_data"])))
@@ -34,7 +34,7 @@ class LossFunction:
             self.i_norm = self.e_norm = 1.0
         if isinstance(cfg["data"]["shotnum"], list):
             raise NotImplementedError("multiplexed shots: 'behavior has not been checked' in the reference (loss_function.py:288)")
-        self.ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles, mode=mode, pv_precision=pv_precision)
+        self.ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group)
         self._w = {}
 
     def _weights(self, lamE, lamI, dev):

@@ -1,7 +1,16 @@
 """Multi-GPU sharding of the hot path.  Lineouts are independent (every parameter is per-lineout,
 ts_params.py:93-99), so ranks own contiguous blocks of lineouts with all static tables replicated and NO data-path
 collective; the only exchange is the all-reduce of the scalar loss (the reference's loss is a nanmean over the whole
-batch, loss_function.py:371, so per-rank partial sums carry the global 1/B_total already)."""
+batch, loss_function.py:371, so per-rank partial sums carry the global 1/B_total already).
+
+ARTS ("angular_full": ONE parameter set for one image) shards the wavelength axis instead, mirroring
+the reference's own device split of the pole grid (form_factor.py:431-447): every rank evaluates the form factor on W/N
+wavelengths x all angles and applies the angular weight matrix locally; the [1024, W/N] slabs are all-gathered in front
+of the instrument stage, which is replicated.  The pair of graph operators below keeps autograd exact:
+    copy_to_shards   forward identity,   backward all-reduce(sum)   -- on the operands entering the sharded region
+    gather_columns   forward all-gather, backward "take my slab"    -- on its output
+so the partial cotangents of the shared parameters / f table are summed across ranks exactly once, while everything
+computed redundantly downstream (amp1/amp2/lam in the instrument stage, the loss) is left alone."""
 from __future__ import annotations
 
 import torch
@@ -34,3 +43,69 @@ def gather_rows(x: torch.Tensor, n_total: int) -> torch.Tensor:
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return torch.cat([o[: e - s] for o, (s, e) in zip(out, sizes)], dim=0)
+
+
+# ---- ARTS: wavelength-axis sharding ------------------------------------------------------------------------------
+def _active(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+class _CopyToShards(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+class _GatherColumns(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sizes, rank, group):
+        ctx.sizes, ctx.rank = sizes, rank
+        pad = max(sizes)
+        buf = x.new_zeros(tuple(x.shape[:-1]) + (pad,))
+        buf[..., : x.shape[-1]] = x
+        out = [torch.empty_like(buf) for _ in sizes]
+        dist.all_gather(out, buf.contiguous(), group=group)
+        return torch.cat([o[..., :n] for o, n in zip(out, sizes)], dim=-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        o = sum(ctx.sizes[: ctx.rank])
+        return g[..., o:o + ctx.sizes[ctx.rank]].contiguous(), None, None, None
+
+
+def copy_to_shards(x: torch.Tensor, group=None) -> torch.Tensor:
+    return _CopyToShards.apply(x, group) if _active(group) and x.requires_grad else x
+
+
+def gather_columns(x_local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather the last axis: rank r holds columns shard_range(n_total, r, world)."""
+    if not _active(group):
+        return x_local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [e - s for s, e in (shard_range(n_total, r, world) for r in range(world))]
+    assert x_local.shape[-1] == sizes[rank], (x_local.shape, sizes, rank)
+    return _GatherColumns.apply(x_local, sizes, rank, group)
+
+
+class WShard:
+    """This rank's slice of a wavelength axis of `npts` points.  [j0, j1) are the points it owns; in table mode the
+    forward difference along omega (form_factor.py:258-261) needs the next point, so the evaluated slice [j0, j1e) carries
+    one halo point whose output is dropped (`keep` = j1 - j0 outputs are kept)."""
+
+    def __init__(self, npts, rank=None, world=None, group=None, halo=True):
+        self.group = group
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.npts = int(npts)
+        self.j0, self.j1 = shard_range(self.npts, self.rank, self.world)
+        if self.j1 <= self.j0:
+            raise ValueError(f"rank {self.rank} of {self.world} owns no wavelength of {npts}: use fewer ranks")
+        self.j1e = min(self.j1 + (1 if halo else 0), self.npts)
+        self.keep = self.j1 - self.j0

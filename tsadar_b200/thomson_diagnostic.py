@@ -19,14 +19,14 @@ def _dev_vec(x, B, dev):
 
 
 class ThomsonScatteringDiagnostic:
-    def __init__(self, cfg, scattering_angles, mode="table", pv_precision="fp32"):
+    def __init__(self, cfg, scattering_angles, mode="table", pv_precision="fp32", shard_group=False):
         self.cfg = cfg
         self.scattering_angles = scattering_angles
         st = cfg["other"]["extraoptions"]["spectype"]
         self.angular = "angular" in st
         if not ("temporal" in st or "imaging" in st or "1d" in st or st == "angular_full"):
             raise NotImplementedError(f"spectype {st}: not built (DESIGN.md: scope)")
-        self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision)
+        self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group)
         self._ats = None
 
     def __call__(self, ts_params, batch):
