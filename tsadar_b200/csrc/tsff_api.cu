@@ -44,6 +44,7 @@ static int check_common(const tsff_ctx* c, int64_t B, const void* params, const 
 
 extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out,
                            double* ff_out, void* saved, void* ws, void* stream) {
+  if (c && B == 0) return TSFF_OK;   // an empty batch (vmap over zero lineouts) is a no-op, as in the reference
   int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
   if (rc) return rc;
   if (!modl_out && !ff_out) { set_error("no output requested"); return TSFF_E_INVALID; }
@@ -59,6 +60,7 @@ extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const v
 extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
                            const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
                            void* stream) {
+  if (c && B == 0) return TSFF_OK;
   int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
   if (rc) return rc;
   if (!modl_bar && !ff_bar) { set_error("no cotangent given"); return TSFF_E_INVALID; }
@@ -162,6 +164,7 @@ extern "C" size_t tsff_pv_workspace_bytes(int64_t B, int64_t N, int64_t P) {
 
 extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
                            double* out, double* dout_dpole, int pv_precision, void* ws, void* stream) {
+  if (B == 0 || P == 0) return TSFF_OK;
   if (!f || !pole || !out || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
   if (tree_npad((int)N - 1) > kTreeMaxNpad) { set_error("N too large (limit %d nodes)", kTreeMaxNpad); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -176,6 +179,7 @@ extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, dou
 
 extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, double h, const double* pole,
                            const double* out_bar, double* f_bar, double* pole_bar, void* ws, void* stream) {
+  if (B == 0) return TSFF_OK;
   if (!f || !pole || !out_bar || !f_bar || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PvLayout L = pv_layout(B, N, P);

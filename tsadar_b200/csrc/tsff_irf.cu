@@ -343,6 +343,7 @@ extern "C" int tsff_irf_fwd(const tsff_irf_cfg* c, int64_t B, const double* modl
                             const double* amps, const double* noise, double* thry, void* saved, void* ws, void* stream) {
   int rc = check_cfg(c);
   if (rc) return rc;
+  if (B == 0) return TSFF_OK;
   if (!modl || !params || !amps || !thry || !saved || !ws || B < 1) { set_error("null argument"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const IrfGeom g = irf_geom(c);
@@ -371,6 +372,7 @@ extern "C" int tsff_irf_bwd(const tsff_irf_cfg* c, int64_t B, const double* para
                             void* stream) {
   int rc = check_cfg(c);
   if (rc) return rc;
+  if (B == 0) return TSFF_OK;
   if (!params || !amps || !saved || !thry_bar || !modl_bar || !amp_bar || !ws || B < 1) { set_error("null argument"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const IrfGeom g = irf_geom(c);
@@ -396,6 +398,7 @@ extern "C" int tsff_irf_bwd(const tsff_irf_cfg* c, int64_t B, const double* para
 extern "C" int tsff_loss_fwd_bwd(int64_t B, int32_t n, const double* theory, const double* data, const double* weight,
                                  double uncert, double scale, int method, double* loss_out, double* theory_bar,
                                  void* stream) {
+  if (B == 0 && loss_out) return TSFF_OK;   // nothing to accumulate
   if (!theory || !data || !weight || !loss_out || B < 1 || n < 1 || method < 0 || method > 3) { set_error("bad argument"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = (long long)B * n;
