@@ -78,7 +78,8 @@ struct DirectArgs {
   const double* tstat;
   double* D64;       // [B][npad] or null
   double* pend;      // [B][2]
-  double* ff;        // [B][G][W][A]
+  double* ff;        // [B][G][W][A]  (null: not wanted and the angle sum is fused, see modl1)
+  double* modl1;     // [B][W] or null: A == 1 and G == 1 -> the pole kernel writes modl itself (no k_reduce_modl pass)
   // backward
   const double* modl_bar;
   const double* ff_bar;
@@ -173,7 +174,8 @@ __device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, con
   Asm s;
   const double P = assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
   const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
-  a.ff[pidx] = P;
+  if (a.ff) a.ff[pidx] = P;
+  if (a.modl1) a.modl1[pidx] = a.jmul[j] * (0.0 + P * a.wts[0]) / 1.0;   // k_reduce_modl's arithmetic for A = G = 1
   a.sI[pidx] = I;
   a.sdI[pidx] = dI;
 }
@@ -346,6 +348,19 @@ __global__ void __launch_bounds__(kThreads) k_direct_bwd_finish(const DirectArgs
   }
 }
 
+// params_bar alone (the table cotangent is finished inside k_pv_nodes when one CTA owns the whole lineout)
+__global__ void __launch_bounds__(64) k_direct_params_bar(const DirectArgs a, long long B) {
+  const long long b = (long long)blockIdx.x * 64 + threadIdx.x;
+  if (b >= B) return;
+  double* pbar = a.params_bar + b * a.NP;
+  for (int k = 0; k < a.NP; k++) pbar[k] = 0.0;
+  for (int g = 0; g < a.G; g++) {
+    LG Lb;
+    load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
+    lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+  }
+}
+
 void fill_static(const tsff_ctx* c, DirectArgs& a) {
   a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = c->V; a.NP = c->NP;
   a.nodes = c->pv_nodes; a.npad = c->pv_npad;
@@ -368,7 +383,9 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   a.D = (unsigned char*)(w + L.w_D);
   a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend);
-  a.ff = ff_out ? ff_out : (double*)(w + L.w_ff);
+  const bool fuse_modl = modl_out && c->A == 1 && c->G == 1;
+  a.ff = ff_out ? ff_out : (fuse_modl ? nullptr : (double*)(w + L.w_ff));
+  a.modl1 = fuse_modl ? modl_out : nullptr;
   {
     const size_t psm = (size_t)c->pv_npad * 8 + tree_prep_scratch_bytes(c->pv_npad);
     TSFF_SMEM_OPTIN(k_direct_prep<T>);
@@ -398,7 +415,7 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   }
   TSFF_LAUNCH_OK("k_direct_fwd");
   if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
-  if (modl_out) {
+  if (modl_out && !fuse_modl) {
     const long long total = (long long)B * c->W;
     k_reduce_modl<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(a.ff, c->wts, c->jmul, c->G, c->W, c->A,
                                                                                      total, modl_out);
@@ -422,20 +439,31 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   a.desc = (float4*)(w + L.w_desc); a.accfe = (double*)(w + L.w_accfe); a.accdf = (double*)(w + L.w_accdf);
   a.pendbar = (double*)(w + L.w_pendbar); a.Dbar = (double*)(w + L.w_Dbar); a.lgbar = (double*)(w + L.w_lgbar);
   a.params_bar = params_bar; a.fe_bar = fe_bar;
-  TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   const int WA = c->W * c->A;
+  PvNodesArgs n;
+  n.desc = a.desc; n.tstat = c->tstat; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.pbar = a.Dbar;
+  n.nsplit = pv_nodes_split(B, n.P, c->sm_count);
+  // one CTA per lineout in the node sweep: it finishes fe_bar itself and Dbar (first in the zeroed range) is never touched
+  const bool fused = n.nsplit == 1;
+  const size_t z0 = fused ? L.w_accfe : L.w_zero_begin;
+  TSFF_CUDA_OK(cudaMemsetAsync(w + z0, 0, L.w_zero_end - z0, st));
   constexpr int RB = 4;
   a.ntiles = (WA + RB * kThreads - 1) / (RB * kThreads);
   k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
-  PvNodesArgs n;
-  n.desc = a.desc; n.tstat = c->tstat; n.P = c->G * WA; n.nodes = c->pv_nodes; n.npad = c->pv_npad; n.pbar = a.Dbar;
-  n.nsplit = pv_nodes_split(B, n.P, c->sm_count);
+  if (fused) {
+    n.accdf = a.accdf; n.accfe = a.accfe; n.fe_bar = fe_bar; n.fe_f32 = sizeof(T) == 4; n.ih = 1.0 / c->dv;
+  }
   if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
   TSFF_SMEM_OPTIN(k_pv_nodes);
   k_pv_nodes<<<(unsigned)(B * n.nsplit), kPvThreads, pv_nodes_smem(n.npad), st>>>(n);
   TSFF_LAUNCH_OK("k_pv_nodes");
   if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
+  if (fused) {
+    k_direct_params_bar<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(a, (long long)B);
+    TSFF_LAUNCH_OK("k_direct_params_bar");
+    return TSFF_OK;
+  }
   const size_t smem = (size_t)c->V * 8;
   TSFF_SMEM_OPTIN(k_direct_bwd_finish<T>);
   k_direct_bwd_finish<T><<<(unsigned)B, kThreads, smem, st>>>(a);

@@ -203,6 +203,15 @@ struct PvNodesArgs {
   const double* tstat;  // k_tree_static table
   int P, nodes, npad, nsplit;
   double* pbar;         // [B][npad]  d loss / d p_i without the exact near part (nsplit > 1: atomically accumulated, zero it)
+  // Optional fused epilogue (direct mode, nsplit == 1, fe_bar != null): p = gradient(f) on V = nodes + 1 table entries,
+  // so the lineout's table cotangent is finished here instead of in a second pass over pbar:
+  //   fe_bar[k] = accfe[k] + sum_i d p_i / d f_k (pbar_i + accdf_i)         (np.gradient adjoint, form_factor.py:372)
+  // accdf / accfe [B][V]: the exact near-zone and lerp contributions scattered by the pole kernel.  pbar is not written.
+  const double* accdf = nullptr;
+  const double* accfe = nullptr;
+  void* fe_bar = nullptr;
+  int fe_f32 = 0;
+  double ih = 0.0;      // 1 / dv
 };
 
 constexpr int kNodeChunk = 1024;   // poles staged per shared-memory chunk (2 x 16 KB)
@@ -210,7 +219,7 @@ constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per block
 
 inline size_t pv_nodes_smem(int npad) {
   const int NB = npad / kTS;
-  return (size_t)kNodeChunk * 16 * 2 + (size_t)npad * 8 + (size_t)NB * kTKA * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
+  return (size_t)kNodeChunk * 16 * 2 + (size_t)(npad + 2) * 8 + (size_t)NB * kTKA * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
 }
 
 // pole splits per lineout: 1 when the batch alone fills the device, else enough CTAs for two per SM (each split
@@ -248,8 +257,8 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   const int NB = a.npad / kTS, M = a.nodes - 1;
   float4* sraw = reinterpret_cast<float4*>(smem_raw);
   float4* ssort = sraw + kNodeChunk;
-  double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad]
-  double* sL = spbar + a.npad;                                         // [NB][kTKA]
+  double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad + 2]  (the fused epilogue needs nodes + 1 <= npad + 1)
+  double* sL = spbar + a.npad + 2;                                     // [NB][kTKA]
   int* shist = reinterpret_cast<int*>(sL + NB * kTKA);                  // [NB + 1]
   int* scur = shist + NB + 1;                                          // [NB + 1]
   const long long b = blockIdx.x / a.nsplit;
@@ -259,8 +268,15 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   const float4* desc = a.desc + b * a.P;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-  for (int i = threadIdx.x; i < a.npad; i += kPvThreads) spbar[i] = 0.0;
+  for (int i = threadIdx.x; i < a.npad + 2; i += kPvThreads) spbar[i] = 0.0;
   for (int i = threadIdx.x; i < NB * kTKA; i += kPvThreads) sL[i] = 0.0;
+  if (a.fe_bar) {   // fused epilogue: pull this lineout's accumulator rows towards L2 now, they are read at the very end
+    const int Vv = a.nodes + 1;
+    for (int i = threadIdx.x * 16; i < Vv; i += kPvThreads * 16) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.accdf + b * Vv + i));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.accfe + b * Vv + i));
+    }
+  }
   // far-phase thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
   int NBP = 1;
   while (NBP < NB) NBP <<= 1;
@@ -374,7 +390,10 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   // ---- spread the local coefficients to the nodes and write out
   double* out = a.pbar + b * a.npad;
   const double* q = a.tstat + kTsQA;
-  for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+  const bool fused = a.fe_bar != nullptr;
+  const int V = a.nodes + 1;
+  for (int i = threadIdx.x; i < a.npad + 2; i += kPvThreads) {
+    if (i >= a.npad) continue;
     double v = 0.0;
     const int nb = i / kTS, k = i % kTS;
     if (i >= 1 && i <= M - 1) {
@@ -388,8 +407,42 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
 #pragma unroll
       for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m];
     }
-    if (a.nsplit == 1) out[i] = v;
+    if (fused) spbar[i] = v;   // each thread rewrites only the slot it has just read
+    else if (a.nsplit == 1) out[i] = v;
     else if (v != 0.0) atomicAdd(&out[i], v);
+  }
+  if (!fused) return;
+  // + the pole kernel's exact near-zone / lerp contributions (eight independent loads in flight per thread; the rows
+  // were prefetched into L2 when the CTA started)
+  const double* adf = a.accdf + b * V;
+  const double* afe = a.accfe + b * V;
+  constexpr int U = 8;
+  for (int i0 = threadIdx.x; i0 < V; i0 += U * kPvThreads) {
+    double t[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { const int i = i0 + u * kPvThreads; t[u] = i < V ? __ldg(adf + i) : 0.0; }
+#pragma unroll
+    for (int u = 0; u < U; u++) { const int i = i0 + u * kPvThreads; if (i < V) spbar[i] += t[u]; }
+  }
+  __syncthreads();
+  // f_k enters p_{k-1} (+), p_{k+1} (-), and p_k at the two ends (central differences inside, one-sided at the ends)
+  const double ih = a.ih;
+  for (int k0 = threadIdx.x; k0 < V; k0 += U * kPvThreads) {
+    double t[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { const int k = k0 + u * kPvThreads; t[u] = k < V ? __ldg(afe + k) : 0.0; }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = k0 + u * kPvThreads;
+      if (k >= V) break;
+      double fb = t[u];
+      if (k >= 1) fb += spbar[k - 1] * ((k - 1 == 0) ? ih : 0.5 * ih);
+      if (k <= V - 2) fb -= spbar[k + 1] * ((k + 1 == V - 1) ? ih : 0.5 * ih);
+      if (k == 0) fb -= spbar[0] * ih;
+      if (k == V - 1) fb += spbar[V - 1] * ih;
+      if (a.fe_f32) static_cast<float*>(a.fe_bar)[b * V + k] = (float)fb;
+      else static_cast<double*>(a.fe_bar)[b * V + k] = fb;
+    }
   }
 }
 
