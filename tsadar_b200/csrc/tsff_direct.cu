@@ -4,7 +4,8 @@
 // stage of the 2V path.
 //
 // Kernels
-//   k_direct_prep       per lineout: LG scalars, df = gradient(f), PV weights D (FP32 + FP64), endpoints
+//   k_direct_lg         per (lineout, gradient point): LG scalars
+//   k_direct_prep       per lineout: df = gradient(f), tree blob (FP32 node weights + block coefficients), endpoints
 //   k_direct_fwd        thread-owns-pole: FP64 kinematics -> FP32 PV sweep (MUFU-bound) -> FP64 assembly
 //   k_reduce_modl       mean over G, weighted angle sum, static per-wavelength multiplier
 //   k_direct_bwd_poles  FP64 reverse of the assembly per pole; emits Ibar descriptors, lerp scatter, LG cotangents
@@ -105,24 +106,30 @@ __device__ __forceinline__ void store_lg(double* dst, const LG& L) {
 }
 
 // ---- prep -------------------------------------------------------------------------------------------------
+// LG scalars of every (lineout, gradient point): one thread each (FP64 divisions and square roots; kept out of the
+// per-lineout CTA of k_direct_prep, where a single thread's serial chain would hold back the whole CTA)
+__global__ void __launch_bounds__(128) k_direct_lg(const DirectArgs a, long long BG) {
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (t >= BG) return;
+  const long long b = t / a.G;
+  LG L;
+  lg_zero(L);
+  lg_forward(a.params + b * a.NP, a.nI, (int)(t % a.G), a.G, a.lam_shift, L);
+  store_lg(a.lg + t * kLGDoubles, L);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
   const long long b = blockIdx.x;
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
-  if (threadIdx.x < a.G) {
-    LG L;
-    lg_zero(L);
-    lg_forward(a.params + b * a.NP, a.nI, threadIdx.x, a.G, a.lam_shift, L);
-    store_lg(a.lg + (b * a.G + threadIdx.x) * kLGDoubles, L);
-  }
   const int M = a.nodes - 1;
   {
-    // node values p_i = gradient(f)_i in shared memory, then the tree blob
+    // node values p_i = gradient(f)_i straight from the table (16 consecutive nodes per thread), then the tree blob
     extern __shared__ __align__(16) unsigned char prep_smem[];
-    double* sp = reinterpret_cast<double*>(prep_smem);
-    for (int i = threadIdx.x; i < a.npad; i += kThreads) sp[i] = (i <= M) ? grad_at(fe, a.V, a.dv, i) : 0.0;
-    __syncthreads();
-    tree_prep_cta(sp, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat, sp + a.npad);
+    const int V = a.V;
+    const double dv = a.dv;
+    tree_prep_cta_f([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat,
+                    reinterpret_cast<double*>(prep_smem));
   }
   if (a.D64) {  // log-form weights for the FP64 validation path
     for (int i = threadIdx.x; i < a.npad; i += kThreads) {
@@ -387,7 +394,10 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   a.ff = ff_out ? ff_out : (fuse_modl ? nullptr : (double*)(w + L.w_ff));
   a.modl1 = fuse_modl ? modl_out : nullptr;
   {
-    const size_t psm = (size_t)c->pv_npad * 8 + tree_prep_scratch_bytes(c->pv_npad);
+    const long long BG = (long long)B * c->G;
+    k_direct_lg<<<(unsigned)((BG + 127) / 128), 128, 0, st>>>(a, BG);
+    TSFF_LAUNCH_OK("k_direct_lg");
+    const size_t psm = tree_prep_scratch_bytes(c->pv_npad);
     TSFF_SMEM_OPTIN(k_direct_prep<T>);
     k_direct_prep<T><<<(unsigned)B, kThreads, psm, st>>>(a);
   }
@@ -479,7 +489,7 @@ size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B
 
 int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
                void* saved, void* ws, cudaStream_t st) {
-  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024 || (size_t)c->pv_npad * 8 + tree_prep_scratch_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024 || tree_prep_scratch_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
                               : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
 }

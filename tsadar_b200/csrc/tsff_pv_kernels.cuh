@@ -16,7 +16,8 @@ namespace tsff {
 
 constexpr int kPvThreads = 256;
 
-TSFF_HD size_t tree_prep_scratch_bytes(int npad) { return ((size_t)(npad / kTS + npad / kTS2) * kTK * 2 + (size_t)kTS * kTK) * 8; }
+constexpr int kPrepStatic = (kTsE1 - kTsCM1) + 4 * kTK * kTK;   // staged static tables: CM1 QE1 CM2 QE2 | T12
+TSFF_HD size_t tree_prep_scratch_bytes(int npad) { return ((size_t)(npad / kTS + npad / kTS2) * kTK * 2 + kPrepStatic) * 8; }   // moments + coefficients + tables
 
 #if defined(__CUDACC__)
 // One bulk copy completed on an mbarrier, in pieces of at most 32 KB.  Called by all threads; one use per kernel.
@@ -36,54 +37,77 @@ static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) 
   for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) out[i] = tree_static_entry(i, M);
 }
 
-// Per-lineout preparation, executed by one CTA.  p[0..M]: node values (FP64; shared or global memory).
+// Per-lineout preparation, executed by one CTA.  pget(i), 0 <= i <= M: node values p_i (FP64).
 // Writes the lineout's blob (tree_blob layout) to global memory: weights, packed coefficients of both levels, leading
 // coefficients.  All phases are spread over the whole CTA:
-//   1. level-1 moments  mu1[b][k] = sum_i p_i x_i^k           thread (b, k), static power table E1
+//   1. level-1 moments  mu1[b][k] = sum_i p_i x_i^k           thread (b, quarter): 16 consecutive nodes held in registers,
+//                                                             powers by recurrence, the four quarters added by shuffles
+//                                                             (also writes the FP32 node weights)
 //   2. level-2 moments from the four children by translation  thread (B, k), static matrices T12
 //   3. coefficients A_m from the moments (+ end-node rows)    thread (block, m)
 //   4. packing into the Horner layout                          thread (block, q)
-// scratch: shared, tree_prep_scratch_bytes(npad).  Ends with the CTA synchronised.
-__device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, unsigned char* blob, const double* tstat,
-                                              double* scratch) {
+// scratch: shared, tree_prep_scratch_bytes(npad).  Ends with the CTA synchronised.  blockDim.x must be a multiple of 32.
+template <typename PGet>
+__device__ __forceinline__ void tree_prep_cta_f(PGet pget, int M, int npad, unsigned char* blob, const double* tstat,
+                                                double* scratch) {
   const TreeBlob tb = tree_blob(npad);
   const int NB = tb.NB, NB2 = tb.NB2, NT = NB + NB2;
   double* mu = scratch;              // [NT][kTK]  (level 1 first)
   double* A = scratch + NT * kTK;    // [NT][kTK]
-  double* E1 = A + NT * kTK;         // [kTS][kTK] staged copy of the static power table
+  double* sCM = A + NT * kTK;        // static tables CM1 QE1 CM2 QE2 (offsets relative to kTsCM1), then T12
+  double* sT12 = sCM + (kTsE1 - kTsCM1);
   float* Wt = reinterpret_cast<float*>(blob + tb.oW);
-  for (int i = threadIdx.x; i < kTS * kTK; i += blockDim.x) E1[i] = tstat[kTsE1 + i];
-  for (int i = threadIdx.x; i < npad; i += blockDim.x) Wt[i] = (i >= 1 && i <= M - 1) ? (float)p[i] : 0.f;
-  __syncthreads();
-  for (int it = threadIdx.x; it < NB * kTK; it += blockDim.x) {
-    const int b = it / kTK, k = it % kTK;
-    const double* pb = p + kTS * b;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (b > 0 && kTS * (b + 1) <= M) {   // all 64 nodes interior
-#pragma unroll 4
-      for (int o = 0; o < kTS; o += 4) {
-        a0 = fma(pb[o], E1[o * kTK + k], a0);
-        a1 = fma(pb[o + 1], E1[(o + 1) * kTK + k], a1);
-        a2 = fma(pb[o + 2], E1[(o + 2) * kTK + k], a2);
-        a3 = fma(pb[o + 3], E1[(o + 3) * kTK + k], a3);
+  // the static tables are fetched while phase 1 runs (their first use is behind its barrier)
+  for (int i = threadIdx.x; i < kPrepStatic; i += blockDim.x)
+    sCM[i] = i < kTsE1 - kTsCM1 ? tstat[kTsCM1 + i] : tstat[kTsT12 + (i - (kTsE1 - kTsCM1))];
+  constexpr int kQ = 16;             // nodes per thread
+  for (int base = 0; base < NB * (kTS / kQ); base += blockDim.x) {   // warp-uniform trip count (shuffles inside)
+    const int item = base + threadIdx.x;
+    const bool valid = item < NB * (kTS / kQ);
+    const int b = item / (kTS / kQ), qd = item % (kTS / kQ);
+    double m[kTK];
+#pragma unroll
+    for (int k = 0; k < kTK; k++) m[k] = 0.0;
+    if (valid) {
+      float wv[kQ];
+#pragma unroll
+      for (int o = 0; o < kQ; o++) {
+        const int i = kTS * b + kQ * qd + o;
+        const double pv = (i >= 1 && i <= M - 1) ? pget(i) : 0.0;
+        wv[o] = (float)pv;
+        const double x = -((double)(kQ * qd + o) - 0.5 * (double)(kTS - 1)) * (1.0 / kTs);   // exact
+        double pw = pv;
+#pragma unroll
+        for (int k = 0; k < kTK; k++) {
+          m[k] += pw;
+          pw *= x;
+        }
       }
-    } else {
-      for (int o = 0; o < kTS; o++) {
-        const int i = kTS * b + o;
-        if (i >= 1 && i <= M - 1) a0 = fma(pb[o], E1[o * kTK + k], a0);
-      }
+      float4* w4 = reinterpret_cast<float4*>(Wt + kTS * b + kQ * qd);
+#pragma unroll
+      for (int o = 0; o < kQ; o += 4) w4[o / 4] = make_float4(wv[o], wv[o + 1], wv[o + 2], wv[o + 3]);
     }
-    mu[it] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int k = 0; k < kTK; k++) {
+      m[k] += __shfl_xor_sync(0xffffffffu, m[k], 1);
+      m[k] += __shfl_xor_sync(0xffffffffu, m[k], 2);
+    }
+    if (valid && qd == 0) {
+#pragma unroll
+      for (int k = 0; k < kTK; k++) mu[b * kTK + k] = m[k];
+    }
   }
   __syncthreads();
-  const double* T12 = tstat + kTsT12;
+  const double* T12 = sT12;
   for (int it = threadIdx.x; it < NB2 * kTK; it += blockDim.x) {
     const int B = it / kTK, k = it % kTK;
     double acc = 0.0;
+#pragma unroll
     for (int c = 0; c < 4; c++) {
       const double* m1 = mu + (4 * B + c) * kTK;
       const double* t = T12 + (c * kTK + k) * kTK;
-      for (int j = 0; j <= k; j++) acc = fma(t[j], m1[j], acc);
+#pragma unroll
+      for (int j = 0; j < kTK; j++) acc = fma(t[j], m1[j], acc);   // T12[c][k][j] = 0 for j > k
     }
     mu[NB * kTK + it] = acc;
   }
@@ -93,14 +117,15 @@ __device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, 
     const bool lvl2 = blk >= NB;
     const int b = lvl2 ? blk - NB : blk, S = lvl2 ? kTS2 : kTS;
     const double s = lvl2 ? kTs2 : kTs;
-    const double* cm = tstat + (lvl2 ? kTsCM2 : kTsCM1);
-    const double* qe = tstat + (lvl2 ? kTsQE2 : kTsQE1);
+    const double* cm = sCM + ((lvl2 ? kTsCM2 : kTsCM1) - kTsCM1);
+    const double* qe = sCM + ((lvl2 ? kTsQE2 : kTsQE1) - kTsCM1);
     const double* mb = mu + blk * kTK;
     double a = 0.0;
-    for (int j = 0; 2 * j <= m; j++) a = fma(cm[m * (kTK / 2) + j], mb[m - 2 * j], a);
+#pragma unroll
+    for (int j = 0; j < kTK / 2; j++) a = fma(cm[m * (kTK / 2) + j], 2 * j <= m ? mb[m - 2 * j] : 0.0, a);   // cm = 0 there too
     a *= 1.0 / s;   // s is a power of two
-    if (b == 0) a = fma(p[0], qe[m], a);
-    if (M >= S * b && M < S * (b + 1)) a = fma(p[M], qe[kTK + m], a);
+    if (b == 0) a = fma(pget(0), qe[m], a);
+    if (M >= S * b && M < S * (b + 1)) a = fma(pget(M), qe[kTK + m], a);
     A[it] = a;
   }
   __syncthreads();
@@ -123,6 +148,11 @@ __device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, 
     }
   }
   __syncthreads();
+}
+// p[0..M] given as an array (shared or global memory)
+__device__ __forceinline__ void tree_prep_cta(const double* p, int M, int npad, unsigned char* blob, const double* tstat,
+                                              double* scratch) {
+  tree_prep_cta_f([p](int i) { return p[i]; }, M, npad, blob, tstat, scratch);
 }
 #endif
 

@@ -164,7 +164,9 @@ class FormFactorEngine:
     def launches_fwd(self, want_modl=True):
         if self.mode == "table":
             return 3
-        return 2 + (1 if want_modl and not (self.A == 1 and self.G == 1) else 0)   # A = G = 1: the angle sum is fused
+        if self.mode == "2v":
+            return 1
+        return 3 + (1 if want_modl and not (self.A == 1 and self.G == 1) else 0)   # A = G = 1: the angle sum is fused
 
     def launches_bwd(self):
         return 4 if self.mode == "table" else 3  # (+1 memset node, not a kernel of ours)
