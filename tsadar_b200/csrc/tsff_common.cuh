@@ -91,6 +91,26 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Segmented warp reduction over contiguous runs of lanes with equal `key` (scatter-adds whose target index changes slowly
+// along the warp: one atomic per run instead of one per lane).  run_head: lane index of the first lane of this lane's run;
+// run_sum: suffix sums within runs -- the head lane ends up with the run's total.  All 32 lanes must call both.
+__device__ __forceinline__ int run_head(int key) {
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+  return 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+}
+__device__ __forceinline__ double run_sum(double v, int head) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double vo = __shfl_down_sync(0xffffffffu, v, o);
+    const int ho = __shfl_down_sync(0xffffffffu, head, o);
+    if (lane + o < 32 && ho == head) v += vo;
+  }
+  return v;
+}
+
 // Sum `n` per-thread values across the CTA and atomically add the totals to dst[0..n).  sred: >= n*nwarps doubles.
 template <int NW>
 __device__ __forceinline__ void block_accumulate(const double* vals, int n, double* sred, double* dst) {

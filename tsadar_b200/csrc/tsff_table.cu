@@ -270,6 +270,11 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
       const double dfbar_p = __shfl_up_sync(0xffffffffu, dfbar, 1);
       const double df_p = __shfl_up_sync(0xffffffffu, df, 1);
       const double delta_p = __shfl_up_sync(0xffffffffu, delta, 1);
+      // scatter-adds of this point: T table (cells ip, ip + 1) and the log-f Hermite data (nodes hm.i - 1, hm.i).  The cell
+      // indices change slowly along the warp (consecutive wavelengths), so runs of equal index are summed with shuffles
+      // and only the first lane of a run issues the atomics (~20x fewer, and no same-address pile-up in L2).
+      double tb0 = 0.0, tb1 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+      int kT = -1, kH = -1;
       if (own) {
         double fphibar = pb.fphi - dfbar / delta;
         double xiebar = kb.xie + dfbar * df / delta;
@@ -279,22 +284,36 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
         }
         const double Tlbar = -q.ikl2 * pb.chiEr;
         xiebar += Tlbar * slp;
-        if (Tlbar != 0.0) {
-          atomicAdd(&Tbar[ip], (1.0 - tp) * Tlbar);
-          atomicAdd(&Tbar[ip + 1], tp * Tlbar);
-        }
+        kT = ip;
+        tb0 = (1.0 - tp) * Tlbar;
+        tb1 = tp * Tlbar;
         if (hm.inside) {
           const double Hbar = fphibar * fphi;
           xiebar += Hbar * hm.dHdx;
           double wf0, wf1, wm0, wm1;
           hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
-          atomicAdd(&lnfbar[hm.i - 1], Hbar * wf0);
-          atomicAdd(&lnfbar[hm.i], Hbar * wf1);
-          atomicAdd(&slopebar[hm.i - 1], Hbar * wm0);
-          atomicAdd(&slopebar[hm.i], Hbar * wm1);
+          kH = hm.i;
+          c0 = Hbar * wf0; c1 = Hbar * wf1; c2 = Hbar * wm0; c3 = Hbar * wm1;
         }
         kb.xie = xiebar;
         kin_backward(L, omgs, cth, q, kb, Lb);
+      }
+      {
+        const int hT = run_head(kT);
+        tb0 = run_sum(tb0, hT);
+        tb1 = run_sum(tb1, hT);
+        if (lane == hT && kT >= 0) {
+          if (tb0 != 0.0) atomicAdd(&Tbar[kT], tb0);
+          if (tb1 != 0.0) atomicAdd(&Tbar[kT + 1], tb1);
+        }
+        const int hH = run_head(kH);
+        c0 = run_sum(c0, hH); c1 = run_sum(c1, hH); c2 = run_sum(c2, hH); c3 = run_sum(c3, hH);
+        if (lane == hH && kH >= 0) {
+          atomicAdd(&lnfbar[kH - 1], c0);
+          atomicAdd(&lnfbar[kH], c1);
+          atomicAdd(&slopebar[kH - 1], c2);
+          atomicAdd(&slopebar[kH], c3);
+        }
       }
     }
     double vals[kLGDoubles];
