@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, cons
 
 // ---- backward: poles --------------------------------------------------------------------------------------
 template <int R, typename T>
-__global__ void __launch_bounds__(kThreads) k_direct_bwd_poles(const DirectArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_direct_bwd_poles(const DirectArgs a) {
   __shared__ LG sL;
   __shared__ double sred[kLGDoubles * (kThreads / 32)];
   const int tile = blockIdx.x % a.ntiles;

@@ -340,7 +340,9 @@ struct IonOut {
 
 TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonOut& o) {
   o.chiIr = o.chiIi = o.sion = 0.0;
-  for (int i = 0; i < nI; i++) {
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {   // fixed trip count + predicate: the per-ion arrays stay in registers
+    if (i >= nI) break;
     double xii = L.inv_s2vTi[i] * q.w;
     double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;
@@ -408,7 +410,9 @@ TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q
   pb.chiEi = ei_bar + 2.0 * chiEi * ce2_bar;
   double chiIr_bar = er_bar + 2.0 * (1.0 + io.chiIr) * a1_bar;
   double chiIi_bar = ei_bar + 2.0 * io.chiIi * a1_bar;
-  for (int i = 0; i < nI; i++) {
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    if (i >= nI) break;
     double xii = L.inv_s2vTi[i] * q.w;
     double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;

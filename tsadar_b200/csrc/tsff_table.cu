@@ -57,6 +57,7 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
 
 struct TableArgs {
   int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  int asplit;   // angle chunks per wavelength tile (ARTS: one lineout, 241 angles -- the grid would not fill the device otherwise)
   double lam_shift, v0, dv, xi1_0, xi1_h, xi2_0, xi2_h;
   const double *omgs, *costh, *wts, *jmul, *xi2;
   ZTab zt;
@@ -157,19 +158,21 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
 constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
 
 template <bool WRITE_FF>
-__global__ void __launch_bounds__(kThreads) k_table_fwd(const TableArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ LG sL;   // CTA-uniform scalars of the (lineout, gradient point)
   double* s_lnf = reinterpret_cast<double*>(smem_raw);
   double* s_slope = s_lnf + a.V;
   double* s_T = s_slope + a.V;
-  const int tile = blockIdx.x % a.ntiles;
-  const long long b = blockIdx.x / a.ntiles;
+  const int chunk = blockIdx.x % a.asplit;
+  const int tile = (blockIdx.x / a.asplit) % a.ntiles;
+  const long long b = blockIdx.x / ((long long)a.asplit * a.ntiles);
+  const int aper = (a.A + a.asplit - 1) / a.asplit, ia0 = chunk * aper, ia1 = min(a.A, ia0 + aper);
   for (int i = threadIdx.x; i < a.V; i += kThreads) {
     s_lnf[i] = a.lnf[b * a.V + i];
     s_slope[i] = a.slope[b * a.V + i];
   }
   for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = (tile * kWarps + wid) * kFwdJ + lane;
   const int jc = min(j, a.W - 1);
@@ -177,9 +180,11 @@ __global__ void __launch_bounds__(kThreads) k_table_fwd(const TableArgs a) {
   const double omgs = a.omgs[jc];
   double acc = 0.0;
   for (int g = 0; g < a.G; g++) {
-    LG L;
-    load_lg(a.lg + (b * a.G + g) * kLGDoubles, L);
-    for (int ia = 0; ia < a.A; ia++) {
+    __syncthreads();
+    if (threadIdx.x == 0) load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+    __syncthreads();
+    const LG& L = sL;
+    for (int ia = ia0; ia < ia1; ia++) {
       Kin q;
       kin_forward(L, omgs, a.costh[ia], q);
       Herm hm;
@@ -207,20 +212,22 @@ __global__ void __launch_bounds__(kThreads) k_table_fwd(const TableArgs a) {
 // ---- backward assembly ----------------------------------------------------------------------------------------
 constexpr int kBwdJ = 30;  // outputs per warp: lanes 1..30; lane 0 = left halo, lane 31 = right halo
 
-__global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_table_bwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sred[kLGDoubles * kWarps];
+  __shared__ LG sL;   // the (lineout, gradient point) scalars are CTA-uniform: shared, not 19 doubles of registers per thread
   double* s_lnf = reinterpret_cast<double*>(smem_raw);
   double* s_slope = s_lnf + a.V;
   double* s_T = s_slope + a.V;
-  const int tile = blockIdx.x % a.ntiles;
-  const long long b = blockIdx.x / a.ntiles;
+  const int chunk = blockIdx.x % a.asplit;
+  const int tile = (blockIdx.x / a.asplit) % a.ntiles;
+  const long long b = blockIdx.x / ((long long)a.asplit * a.ntiles);
+  const int aper = (a.A + a.asplit - 1) / a.asplit, ia0 = chunk * aper, ia1 = min(a.A, ia0 + aper);
   for (int i = threadIdx.x; i < a.V; i += kThreads) {
     s_lnf[i] = a.lnf[b * a.V + i];
     s_slope[i] = a.slope[b * a.V + i];
   }
   for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = (tile * kWarps + wid) * kBwdJ - 1 + lane;
   const bool valid = (j >= 0) && (j < a.W);
@@ -232,11 +239,13 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
   double* lnfbar = a.lnfbar + b * a.V;
   double* slopebar = a.slopebar + b * a.V;
   for (int g = 0; g < a.G; g++) {
-    LG L;
-    load_lg(a.lg + (b * a.G + g) * kLGDoubles, L);
-    LG Lb;
+    __syncthreads();   // first pass: the staged tables; later passes: everyone is done with the previous sL
+    if (threadIdx.x == 0) load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+    __syncthreads();
+    const LG& L = sL;
+    LG Lb;             // lanes 1..kBwdJ: cotangents of the points they own; halo lanes: discarded below
     lg_zero(Lb);
-    for (int ia = 0; ia < a.A; ia++) {
+    for (int ia = ia0; ia < ia1; ia++) {
       const double cth = a.costh[ia];
       Kin q;
       kin_forward(L, omgs, cth, q);
@@ -261,9 +270,7 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
         ion_forward(L, a.nI, a.zt, q, io);
         Asm s;
         assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
-        LG Ltmp;
-        lg_zero(Ltmp);
-        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, own ? Lb : Ltmp);
+        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
         dfbar = has_df ? kPi * q.ikl2 * pb.chiEi : 0.0;
         kb.ikl2 += -Tl * pb.chiEr + kPi * df * pb.chiEi;
       }
@@ -316,6 +323,7 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd(const TableArgs a) {
         }
       }
     }
+    if (lane < 1 || lane > kBwdJ) lg_zero(Lb);   // a halo lane only ran the assembly for its neighbour's forward difference
     double vals[kLGDoubles];
     store_lg(vals, Lb);
     block_accumulate<kWarps>(vals, kLGDoubles, sred, a.lgbar + (b * a.G + g) * kLGDoubles);
@@ -410,6 +418,14 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd_finish(const TableArgs a
   }
 }
 
+// angle chunks per wavelength tile: 1 when the (lineout, tile) grid alone gives two CTAs per SM, else enough to get there
+int table_angle_split(long long ctas, int A, int sm_count) {
+  if (ctas >= 2LL * sm_count) return 1;
+  long long want = (2LL * sm_count + ctas - 1) / ctas;
+  if (want > A) want = A;
+  return want < 1 ? 1 : (int)want;
+}
+
 void fill_static(const tsff_ctx* c, TableArgs& a) {
   a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = c->V; a.NP = c->NP;
   a.nodes = c->pv_nodes; a.npad = c->pv_npad;
@@ -468,13 +484,15 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
+    // the fused angle sum (modl) needs all angles in one CTA; the plain formfactor output can split them
+    a.asplit = modl_out ? 1 : table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (ff_out) {
       TSFF_SMEM_OPTIN(k_table_fwd<true>);
-      k_table_fwd<true><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+      k_table_fwd<true><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
     } else {
       TSFF_SMEM_OPTIN(k_table_fwd<false>);
-      k_table_fwd<false><<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+      k_table_fwd<false><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
     }
     TSFF_LAUNCH_OK("k_table_fwd");
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
@@ -501,9 +519,10 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
+    a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
     TSFF_SMEM_OPTIN(k_table_bwd);
-    k_table_bwd<<<(unsigned)(B * a.ntiles), kThreads, smem, st>>>(a);
+    k_table_bwd<<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
     TSFF_LAUNCH_OK("k_table_bwd");
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }
