@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""ms per fit step of the reference's 1d deck (2 lineouts per batch, EPW window, adam): eager launches vs one CUDA graph."""
+import os, sys, time, copy
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+from tests.common import SA_P9, load_cfg
+from tsadar_b200.loss_function import LossFunction
+from tsadar_b200.ts_params import ThomsonParams
+from tsadar_b200.fit import adam_fit
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+N = 200
+cfg = load_cfg("cfg_1d")
+lamb = np.linspace(400, 700, 1024)
+e_data = 0.6 * np.exp(-0.5 * ((lamb - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamb - 590) / 15.0) ** 2) + 0.01
+batch = dict(e_data=np.tile(e_data, (B, 1)), i_data=np.ones((B, 1024)), e_amps=np.ones(B), i_amps=np.ones(B),
+             noise_e=np.zeros((B, 1024)), noise_i=np.zeros((B, 1024)))
+batch_t = {k: torch.as_tensor(v, dtype=torch.float64, device="cuda") for k, v in batch.items()}
+loss_fn = LossFunction(cfg, SA_P9, batch)
+for graphed in (False, True):
+    tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+    closure = lambda p: loss_fn.calc_loss(p, batch_t)[0]
+    adam_fit(closure, tp, 0.01, 5, cuda_graph=graphed)      # warm
+    tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    hist = adam_fit(closure, tp, 0.01, N, cuda_graph=graphed)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"B={B} {'CUDA graph' if graphed else 'eager     '}: {dt / N * 1e3:7.3f} ms/step ({N} adam steps, loss {hist[0]:.4e} -> {hist[-1]:.4e})")

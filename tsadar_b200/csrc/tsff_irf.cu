@@ -18,7 +18,36 @@ using namespace tsff;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTile = 512;  // outputs per CTA in the convolution kernels
+constexpr int kConvR = 8;                        // consecutive outputs per thread in the convolution kernels
+constexpr int kConvThreads = 128;
+constexpr int kTile = kConvThreads * kConvR;     // outputs per CTA in the convolution kernels
+
+// Register-tiled sliding dot product: acc[r] += sum_i s[i0 + r + DIR * i] * sg[i], i = 0 .. ntp - 1 (ntp a multiple of 8;
+// taps beyond the real ones are zero), every output summed in tap order.  The eight-sample window lives in registers and
+// rotates by one per tap (fully unrolled: no moves): one shared-memory load of a sample and one broadcast load of a tap
+// feed eight DFMAs, instead of two loads per DFMA.
+template <int DIR>
+__device__ __forceinline__ void conv_tile8(const double* __restrict__ s, const double* __restrict__ sg, int ntp, int i0,
+                                           double (&acc)[kConvR]) {
+  double v[kConvR];
+#pragma unroll
+  for (int r = 0; r < kConvR; r++) v[r] = s[i0 + r];
+  for (int ib = 0; ib < ntp; ib += kConvR) {
+#pragma unroll
+    for (int u = 0; u < kConvR; u++) {
+      const double gv = sg[ib + u];
+      if (DIR > 0) {
+#pragma unroll
+        for (int r = 0; r < kConvR; r++) acc[r] = fma(v[(r + u) & (kConvR - 1)], gv, acc[r]);
+        v[u] = s[i0 + ib + u + kConvR];                                   // enters as r = 7 of the next tap
+      } else {
+#pragma unroll
+        for (int r = 0; r < kConvR; r++) acc[r] = fma(v[(r - u) & (kConvR - 1)], gv, acc[r]);
+        v[(kConvR - 1 - u) & (kConvR - 1)] = s[i0 - ib - u - 1];          // enters as r = 0 of the next tap
+      }
+    }
+  }
+}
 
 struct IrfGeom {
   int W, nbins, r, K;      // r = W / nbins samples per pixel; K = tap half-width in samples
@@ -66,40 +95,48 @@ __device__ __forceinline__ double tap(const IrfGeom& g, int n, int m) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------------------
-// dynamic smem: x halo [kTile + 2K] | taps [2K + 2]
-__global__ void __launch_bounds__(kThreads) k_irf_conv(const IrfGeom g, const double* __restrict__ x, double* __restrict__ yc,
-                                                      double* __restrict__ pmax) {
+// dynamic smem: 8 zeros | x halo [kTile + 2K] | 8 zeros | taps [ntp] (zero-padded to a multiple of 8)
+__global__ void __launch_bounds__(kConvThreads) k_irf_conv(const IrfGeom g, const double* __restrict__ x, double* __restrict__ yc,
+                                                          double* __restrict__ pmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double s_rv[2 * (kThreads / 32)];
-  __shared__ int s_ri[2 * (kThreads / 32)];
-  double* s_x = reinterpret_cast<double*>(smem_raw);
-  double* s_g = s_x + (kTile + 2 * g.K);
+  __shared__ double s_rv[2 * (kConvThreads / 32)];
+  __shared__ int s_ri[2 * (kConvThreads / 32)];
+  const int ntp = (2 * g.K + 1 + kConvR - 1) / kConvR * kConvR;
+  double* s_x = reinterpret_cast<double*>(smem_raw) + 8;
+  double* s_g = s_x + (kTile + 2 * g.K) + 8;
   const int tile = blockIdx.x % g.ntiles;
   const long long b = blockIdx.x / g.ntiles;
   const int n0 = tile * kTile;
   const double* xb = x + b * g.W;
-  for (int i = threadIdx.x; i < kTile + 2 * g.K; i += kThreads) {
+  for (int i = threadIdx.x - 8; i < kTile + 2 * g.K + 8; i += kConvThreads) {
     const int m = n0 - g.K + i;
-    s_x[i] = (m >= 0 && m < g.W) ? xb[m] : 0.0;
+    s_x[i] = (i >= 0 && i < kTile + 2 * g.K && m >= 0 && m < g.W) ? xb[m] : 0.0;
   }
   // taps for offsets o = n - m in [-K, K]: s_g[o + K]
-  for (int i = threadIdx.x; i < 2 * g.K + 1; i += kThreads) {
+  for (int i = threadIdx.x; i < ntp; i += kConvThreads) {
     const double d = ((double)(i - g.K) - g.half) * g.dlam;
-    s_g[i] = g.gnorm * exp(-d * d * g.inv2s2);
+    s_g[i] = i <= 2 * g.K ? g.gnorm * exp(-d * d * g.inv2s2) : 0.0;
   }
   __syncthreads();
   double vmax_y = -INFINITY, vmax_x = -INFINITY;
   int imax_y = 0, imax_x = 0;
-  for (int t = threadIdx.x; t < kTile; t += kThreads) {
-    const int n = n0 + t;
-    if (n >= g.W) break;
-    double acc = 0.0;
-    // y[n] = sum_m x[m] G(n - m - half);  m = n - o, o in [-K, K];  s_x index of m: m - n0 + K = t - o + K
-    for (int o = -g.K; o <= g.K; o++) acc = fma(s_x[t - o + g.K], s_g[o + g.K], acc);
-    yc[b * g.W + n] = acc;
-    if (acc > vmax_y) { vmax_y = acc; imax_y = n; }
-    const double xv = s_x[t + g.K];
-    if (xv > vmax_x) { vmax_x = xv; imax_x = n; }
+  {
+    // y[n] = sum_m x[m] G(n - m - half);  m = n - o, o in [-K, K];  s_x index of m: t - o + K = t + 2K - i, i = o + K
+    const int t0 = threadIdx.x * kConvR;
+    double acc[kConvR];
+#pragma unroll
+    for (int r = 0; r < kConvR; r++) acc[r] = 0.0;
+    conv_tile8<-1>(s_x, s_g, ntp, t0 + 2 * g.K, acc);
+#pragma unroll
+    for (int r = 0; r < kConvR; r++) {
+      const int n = n0 + t0 + r;
+      if (n < g.W) {
+        yc[b * g.W + n] = acc[r];
+        if (acc[r] > vmax_y) { vmax_y = acc[r]; imax_y = n; }
+        const double xv = s_x[t0 + r + g.K];
+        if (xv > vmax_x) { vmax_x = xv; imax_x = n; }
+      }
+    }
   }
   // block arg-max (first index wins on ties, like jnp.argmax)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -113,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) k_irf_conv(const IrfGeom g, const do
   if (lane == 0) { s_rv[2 * wid] = vmax_y; s_ri[2 * wid] = imax_y; s_rv[2 * wid + 1] = vmax_x; s_ri[2 * wid + 1] = imax_x; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kThreads / 32; w++) {
+    for (int w = 1; w < kConvThreads / 32; w++) {
       if (s_rv[2 * w] > vmax_y || (s_rv[2 * w] == vmax_y && s_ri[2 * w] < imax_y)) { vmax_y = s_rv[2 * w]; imax_y = s_ri[2 * w]; }
       if (s_rv[2 * w + 1] > vmax_x || (s_rv[2 * w + 1] == vmax_x && s_ri[2 * w + 1] < imax_x)) { vmax_x = s_rv[2 * w + 1]; imax_x = s_ri[2 * w + 1]; }
     }
@@ -259,31 +296,34 @@ __global__ void __launch_bounds__(kThreads) k_irf_bwd_pre(const IrfGeom g, const
 }
 
 // xbar_m = sum_n ycbar_n G(n - m - half)  (+ the max(x) term).  dynamic smem: ycbar halo [kTile + 2K] | taps
-__global__ void __launch_bounds__(kThreads) k_irf_bwd_conv(const IrfGeom g, const IrfCall c, double* __restrict__ xbar) {
+__global__ void __launch_bounds__(kConvThreads) k_irf_bwd_conv(const IrfGeom g, const IrfCall c, double* __restrict__ xbar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_y = reinterpret_cast<double*>(smem_raw);
-  double* s_g = s_y + (kTile + 2 * g.K);
+  const int ntp = (2 * g.K + 1 + kConvR - 1) / kConvR * kConvR;
+  double* s_y = reinterpret_cast<double*>(smem_raw) + 8;
+  double* s_g = s_y + (kTile + 2 * g.K) + 8;
   const int tile = blockIdx.x % g.ntiles;
   const long long b = blockIdx.x / g.ntiles;
   const int m0 = tile * kTile;
-  for (int i = threadIdx.x; i < kTile + 2 * g.K; i += kThreads) {
+  for (int i = threadIdx.x - 8; i < kTile + 2 * g.K + 8; i += kConvThreads) {
     const int n = m0 - g.K + i;
-    s_y[i] = (n >= 0 && n < g.W) ? c.ycbar[b * g.W + n] : 0.0;
+    s_y[i] = (i >= 0 && i < kTile + 2 * g.K && n >= 0 && n < g.W) ? c.ycbar[b * g.W + n] : 0.0;
   }
-  for (int i = threadIdx.x; i < 2 * g.K + 1; i += kThreads) {
+  for (int i = threadIdx.x; i < ntp; i += kConvThreads) {
     const double d = ((double)(i - g.K) - g.half) * g.dlam;
-    s_g[i] = g.gnorm * exp(-d * d * g.inv2s2);
+    s_g[i] = i <= 2 * g.K ? g.gnorm * exp(-d * d * g.inv2s2) : 0.0;
   }
   __syncthreads();
   const int im = c.stats[b].im;
-  for (int t = threadIdx.x; t < kTile; t += kThreads) {
-    const int m = m0 + t;
-    if (m >= g.W) break;
-    double acc = 0.0;
-    // n = m + o, o in [-K, K];  s_y index of n: n - m0 + K = t + o + K
-    for (int o = -g.K; o <= g.K; o++) acc = fma(s_y[t + o + g.K], s_g[o + g.K], acc);
-    if (m == im) acc += c.xbar_max[b];
-    xbar[b * g.W + m] = acc;
+  // n = m + o, o in [-K, K];  s_y index of n: t + o + K = t + i
+  const int t0 = threadIdx.x * kConvR;
+  double acc[kConvR];
+#pragma unroll
+  for (int r = 0; r < kConvR; r++) acc[r] = 0.0;
+  conv_tile8<1>(s_y, s_g, ntp, t0, acc);
+#pragma unroll
+  for (int r = 0; r < kConvR; r++) {
+    const int m = m0 + t0 + r;
+    if (m < g.W) xbar[b * g.W + m] = acc[r] + (m == im ? c.xbar_max[b] : 0.0);
   }
 }
 
@@ -353,10 +393,10 @@ extern "C" int tsff_irf_fwd(const tsff_irf_cfg* c, int64_t B, const double* modl
   // conv(x) is kept in `saved` for the backward pass
   double* yc = (double*)(sv + align_up((size_t)B * sizeof(IrfStats)));
   double* pmax = (double*)(w + L.w_pmax);
-  const size_t smem = (size_t)(kTile + 2 * g.K + 2 * g.K + 2) * 8;
+  const size_t smem = (size_t)(kTile + 2 * g.K + 16 + 2 * g.K + 1 + kConvR) * 8;
   if (smem > 200 * 1024) { set_error("IRF too wide for shared memory (K=%d)", g.K); return TSFF_E_INVALID; }
   TSFF_SMEM_OPTIN(k_irf_conv);
-  k_irf_conv<<<(unsigned)(B * g.ntiles), kThreads, smem, st>>>(g, modl, yc, pmax);
+  k_irf_conv<<<(unsigned)(B * g.ntiles), kConvThreads, smem, st>>>(g, modl, yc, pmax);
   TSFF_LAUNCH_OK("k_irf_conv");
   IrfCall call;
   memset(&call, 0, sizeof(call));
@@ -388,9 +428,9 @@ extern "C" int tsff_irf_bwd(const tsff_irf_cfg* c, int64_t B, const double* para
   call.xbar_max = (double*)(w + L.bytes);
   k_irf_bwd_pre<<<(unsigned)B, kThreads, (size_t)g.nbins * 8, st>>>(g, call, yc);
   TSFF_LAUNCH_OK("k_irf_bwd_pre");
-  const size_t smem = (size_t)(kTile + 2 * g.K + 2 * g.K + 2) * 8;
+  const size_t smem = (size_t)(kTile + 2 * g.K + 16 + 2 * g.K + 1 + kConvR) * 8;
   TSFF_SMEM_OPTIN(k_irf_bwd_conv);
-  k_irf_bwd_conv<<<(unsigned)(B * g.ntiles), kThreads, smem, st>>>(g, call, modl_bar);
+  k_irf_bwd_conv<<<(unsigned)(B * g.ntiles), kConvThreads, smem, st>>>(g, call, modl_bar);
   TSFF_LAUNCH_OK("k_irf_bwd_conv");
   return TSFF_OK;
 }
