@@ -72,3 +72,51 @@ def test_1d_inverse_adam_reduces_loss():
     hist = adam_fit(loss_fn, fit, 0.004, 100)
     assert np.all(np.isfinite(hist))
     assert hist[-1] < 0.5 * hist[0], (hist[0], hist[-1])
+
+
+def test_hessian_of_the_fit_loss_and_sigmas():
+    """Second-order path (loss_function.py:110,170-188; postprocess.get_sigmas): the finite-difference-of-adjoint Hessian is
+    symmetric, block-diagonal over lineouts, matches second differences of the loss itself, and is positive definite at
+    the optimum of a noiseless synthetic fit (so every sigma is real and positive)."""
+    from tsadar_b200.loss_function import LossFunction, get_sigmas
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    from tsadar_b200.fit import ravel_leaves, unravel_into
+    cfg = load_cfg("cfg_1d")
+    cfg["other"]["points_per_pixel"] = 1
+    cfg["other"]["npts"] = 1024
+    B = 2
+    tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+    with torch.no_grad():
+        tp.leaves[("electron", "Te")].value[1] += 0.2
+    diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=SA_P9)
+    dummy = dict(i_data=np.ones((B, 1024)), e_data=np.ones((B, 1024)), noise_e=np.zeros((B, 1024)), noise_i=np.zeros((B, 1024)),
+                 e_amps=np.ones(B), i_amps=np.ones(B))
+    with torch.no_grad():
+        data, _, _, _ = diag(tp, dummy)
+    batch = dict(dummy, e_data=data.detach().cpu().numpy())           # noiseless data generated at the current parameters
+    lf = LossFunction(cfg, SA_P9, batch)
+    H, rows = lf.h_loss_wrt_params(tp, batch)
+    n = H.shape[0]
+    assert n == len(tp.parameters()) * B
+    assert np.allclose(H, H.T)
+    # different lineouts do not talk to each other
+    for a, (la, ea) in enumerate(rows):
+        for b, (lb, eb) in enumerate(rows):
+            if ea != eb:
+                assert abs(H[a, b]) <= 1e-6 * np.sqrt(abs(H[a, a] * H[b, b])), (a, b, H[a, b])
+    # one diagonal entry against the second difference of the loss itself
+    leaves = tp.parameters()
+    x0 = ravel_leaves(leaves)
+    k, h = 0, 2e-3
+    vals = []
+    for dx in (-h, 0.0, h):
+        x = x0.copy(); x[k] += dx
+        unravel_into(leaves, x)
+        vals.append(float(lf.loss_for_hess(tp, batch).detach()))
+    unravel_into(leaves, x0)
+    d2 = (vals[0] - 2 * vals[1] + vals[2]) / h**2
+    assert abs(d2 - H[k, k]) <= 2e-3 * abs(H[k, k]), (d2, H[k, k])
+    assert np.linalg.eigvalsh(H).min() > 0
+    sig = get_sigmas(H, rows, B)
+    assert sig.shape == (B, len(leaves)) and np.all(sig > 0) and np.all(np.isfinite(sig))

@@ -85,3 +85,57 @@ class LossFunction:
         loss, ThryE, _ = self.calc_loss(ts_params, batch)
         loss.backward()
         return (loss.detach(), [ThryE.detach() if isinstance(ThryE, torch.Tensor) else ThryE, ts_params]), [t.grad for t in leaves]
+
+    # ---- second-order path (loss_function.py:110, 170-188; postprocess.py:134, 167-179, 188-251) -- SURVEY.md 8f row N2
+    def loss_for_hess(self, ts_params, batch):
+        """_loss_for_hess_fn_ (loss_function.py:173-188): errors weighted by 1/(|data| + 1e-10), SUMMED over the fit windows.
+        As written the reference reduces the NaN-masked error with jnp.sum, which yields NaN; the masked sum is what
+        get_sigmas needs and is what this computes."""
+        ThryE, ThryI, lamE, lamI = self.ts_diag(ts_params, batch)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        wE, wI = self._weights(np.asarray(lamE), np.asarray(lamI), dev)
+        ex = self.cfg["other"]["extraoptions"]
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        if isinstance(ThryE, torch.Tensor) and (ex["fit_EPWb"] or ex["fit_EPWr"]):
+            d = torch.as_tensor(batch["e_data"], dtype=torch.float64).to(dev).expand_as(ThryE)
+            total = total + (((wE > 0).to(torch.float64) * (0.5 if ex["fit_EPWb"] and ex["fit_EPWr"] else 1.0)) * (d - ThryE) ** 2 / (d.abs() + 1e-10)).sum()
+        if isinstance(ThryI, torch.Tensor) and ex["fit_IAW"] and wI is not None:
+            d = torch.as_tensor(batch["i_data"], dtype=torch.float64).to(dev).expand_as(ThryI)
+            total = total + ((wI > 0).to(torch.float64) * (d - ThryI) ** 2 / (d.abs() + 1e-10)).sum()
+        return total
+
+    def h_loss_wrt_params(self, ts_params, batch, rel_step=1e-4, loss=None):
+        """Hessian of `loss_for_hess` with respect to the flattened active leaves: central differences of the gradient
+        that the adjoint kernels return exactly (the custom-VJP path has no forward-over-reverse; 2 n gradient calls,
+        n = number of active scalars).  -> (H [n, n] float64 numpy, symmetrised; list of (leaf index, element) per row)."""
+        from .fit import ravel_leaves, unravel_into, value_and_grad
+        leaves = ts_params.parameters()
+        x0 = ravel_leaves(leaves)
+        closure = (lambda tp: self.loss_for_hess(tp, batch)) if loss is None else loss
+        n = x0.size
+        H = np.zeros((n, n))
+        for k in range(n):
+            h = rel_step * max(1.0, abs(x0[k]))
+            xp, xm = x0.copy(), x0.copy()
+            xp[k] += h
+            xm[k] -= h
+            unravel_into(leaves, xp)
+            _, gp = value_and_grad(closure, ts_params)
+            unravel_into(leaves, xm)
+            _, gm = value_and_grad(closure, ts_params)
+            H[k] = (gp - gm) / (2 * h)
+        unravel_into(leaves, x0)
+        rows = [(li, e) for li, t in enumerate(leaves) for e in range(t.numel())]
+        return 0.5 * (H + H.T), rows
+
+
+def get_sigmas(H, rows, batch_size):
+    """postprocess.get_sigmas (postprocess.py:188-251) on the dense Hessian of h_loss_wrt_params: per lineout, the block of
+    its own parameters is inverted and sigma = sign(d) sqrt|d| of the diagonal (cross-lineout terms are zero and dropped)."""
+    n_leaf = 1 + max(li for li, _ in rows)
+    sig = np.zeros((batch_size, n_leaf))
+    for i in range(batch_size):
+        idx = [k for k, (li, e) in enumerate(rows) if e == i]
+        d = np.diag(np.linalg.inv(H[np.ix_(idx, idx)]))
+        sig[i, [rows[k][0] for k in idx]] = np.sign(d) * np.sqrt(np.abs(d))
+    return sig
