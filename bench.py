@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--lineouts", type=int, default=4096, help="lineouts per GPU per step")
+    ap.add_argument("--lineouts", type=int, default=16384, help="lineouts per GPU per step (measured: 4096 -> 1.74M, 8192 -> 1.79M, 16384 -> 1.82M lineouts/s: fewer partial waves)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-lineouts", type=int, default=8)
     ap.add_argument("--warmup-ref", type=int, default=1)
