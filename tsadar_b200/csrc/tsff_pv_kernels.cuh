@@ -378,38 +378,36 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       // poles whose window [wb0, wb0+2] contains block nb: wb0 in [nb-2, nb]
       const int klo = shist[max(nb - 2, 0)], khi = shist[nb + 1];
       const float fi0 = (float)(kTS * nb + 2 * lane);
-      float2 acc = make_float2(0.f, 0.f);
       double acc64x = 0.0, acc64y = 0.0;
-      int cnt = 0;
-      for (int k = klo; k < khi; k++) {
-        const float4 d = ssort[k];
-        const float u0 = fi0 + d.x, u1 = u0 + 1.f;   // i - n_p, exact
-        const float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
-        // this block comes within kMidHalf nodes of the pole only if n_p is within kMidHalf of it (warp-uniform test)
-        const float nrel = -d.x - (float)(kTS * nb);
-        if (nrel >= -mid && nrel <= (float)(kTS - 1) + mid) {
-          const float2 x = make_float2(fabsf(u0) > lim ? x0 : 0.f, fabsf(u1) > lim ? x1 : 0.f);
-          const float2 s2 = fmul2(x, x);
-          float2 pI = ffma2(make_float2(1.f / 66.f, 1.f / 66.f), s2, make_float2(1.f / 45.f, 1.f / 45.f));
-          pI = ffma2(pI, s2, make_float2(1.f / 28.f, 1.f / 28.f));
-          pI = ffma2(pI, s2, c4);
-          pI = ffma2(pI, s2, c2);
-          pI = ffma2(pI, s2, one);
-          acc = ffma2(fmul2(make_float2(d.z, d.z), x), pI, acc);
-        } else {
-          const float2 x = make_float2(x0, x1);
-          const float2 s2 = fmul2(x, x);
-          acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
+      for (int kc = klo; kc < khi; kc += 64) {     // FP32 partial sums over at most 64 poles, then into the FP64 accumulators
+        const int ke = min(kc + 64, khi);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int k = kc; k < ke; k++) {
+          const float4 d = ssort[k];
+          const float u0 = fi0 + d.x, u1 = u0 + 1.f;   // i - n_p, exact
+          const float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
+          // this block comes within kMidHalf nodes of the pole only if n_p is within kMidHalf of it (warp-uniform test)
+          const float nrel = -d.x - (float)(kTS * nb);
+          if (nrel >= -mid && nrel <= (float)(kTS - 1) + mid) {
+            const float2 x = make_float2(fabsf(u0) > lim ? x0 : 0.f, fabsf(u1) > lim ? x1 : 0.f);
+            const float2 s2 = fmul2(x, x);
+            float2 pI = ffma2(make_float2(1.f / 66.f, 1.f / 66.f), s2, make_float2(1.f / 45.f, 1.f / 45.f));
+            pI = ffma2(pI, s2, make_float2(1.f / 28.f, 1.f / 28.f));
+            pI = ffma2(pI, s2, c4);
+            pI = ffma2(pI, s2, c2);
+            pI = ffma2(pI, s2, one);
+            acc = ffma2(fmul2(make_float2(d.z, d.z), x), pI, acc);
+          } else {
+            const float2 x = make_float2(x0, x1);
+            const float2 s2 = fmul2(x, x);
+            acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
+          }
         }
-        if (++cnt == 64) {
-          acc64x += (double)acc.x;
-          acc64y += (double)acc.y;
-          acc = make_float2(0.f, 0.f);
-          cnt = 0;
-        }
+        acc64x += (double)acc.x;
+        acc64y += (double)acc.y;
       }
-      spbar[kTS * nb + 2 * lane] += acc64x + (double)acc.x;
-      spbar[kTS * nb + 2 * lane + 1] += acc64y + (double)acc.y;
+      spbar[kTS * nb + 2 * lane] += acc64x;
+      spbar[kTS * nb + 2 * lane + 1] += acc64y;
     }
   }
   if (fb < NB) {
