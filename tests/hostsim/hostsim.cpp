@@ -174,6 +174,12 @@ int main() {
     float* W = reinterpret_cast<float*>(blob + tb.oW);
     for (int i = 1; i <= M - 1; i++) W[i] = (float)f[i];
     auto pget = [&](int i) { return f[i]; };
+    for (int b = 0; b < tb.NB0; b++) {   // level 0: interior nodes only, no end-node rows
+      double mu[kTK], A[kTK];
+      tree_block_moments(pget, M, b, kTS0, kTs0, 0, 1, mu);
+      tree_coeffs_from_moments(pget, M, b, kTS0, kTs0, mu, ts.data() + kTsCM0, (const double*)nullptr, A);
+      tree_pack(A, reinterpret_cast<float4*>(blob + tb.oAB0) + b * (kTK / 2), reinterpret_cast<double*>(blob + tb.oLD0) + 2 * b);
+    }
     for (int lvl = 0; lvl < 2; lvl++) {
       const int S = lvl ? kTS2 : kTS, nb = lvl ? tb.NB2 : tb.NB;
       const double s = lvl ? kTs2 : kTs;
@@ -209,7 +215,7 @@ int main() {
       TreePole tp[1] = {tree_pole(xi, z0, h, M, npad)};
       double fI[1] = {0}, fJ1[1] = {0}, fJ2[1] = {0}, eI, eJ;
       tree_far<1>(blob, tb, tp, fI, fJ1, fJ2);
-      const TreeAcc na = tree_near(W, tp[0]);
+      const TreeAcc na = tree_near(blob, tb, tp[0]);
       tree_near_exact(xi, z0, h, M, (int)(-tp[0].un), tp[0].wb0, pget, eI, eJ);
       const double I = eI + na.I + fI[0], dI = eJ + na.J / h + fJ1[0] / (kTs * h) + fJ2[0] / (kTs2 * h);
       const double e = 1e-6;

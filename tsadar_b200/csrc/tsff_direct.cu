@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) k_direct_lg(const DirectArgs a, long long
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_direct_prep(const DirectArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) k_direct_prep(const DirectArgs a) {
   const long long b = blockIdx.x;
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int M = a.nodes - 1;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_cons
     tree_far<R>(smem_raw, tb, tp, accI, accJ, accJ2);
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      const TreeAcc na = tree_near(reinterpret_cast<const float*>(smem_raw + tb.oW), tp[r]);
+      const TreeAcc na = tree_near(smem_raw, tb, tp[r]);
       nrI[r] = na.I;
       nrJ[r] = na.J;
     }

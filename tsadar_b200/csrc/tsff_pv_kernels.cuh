@@ -61,6 +61,8 @@ __device__ __forceinline__ void tree_prep_cta_f(PGet pget, int M, int npad, unsi
   for (int i = threadIdx.x; i < kPrepStatic; i += blockDim.x)
     sCM[i] = i < kTsE1 - kTsCM1 ? tstat[kTsCM1 + i] : tstat[kTsT12 + (i - (kTsE1 - kTsCM1))];
   constexpr int kQ = 16;             // nodes per thread
+  static_assert(kQ == kTS0, "one thread per level-0 block");
+  __syncthreads();                   // sT12 is used inside phase 1
   for (int base = 0; base < NB * (kTS / kQ); base += blockDim.x) {   // warp-uniform trip count (shuffles inside)
     const int item = base + threadIdx.x;
     const bool valid = item < NB * (kTS / kQ);
@@ -69,23 +71,60 @@ __device__ __forceinline__ void tree_prep_cta_f(PGet pget, int M, int npad, unsi
 #pragma unroll
     for (int k = 0; k < kTK; k++) m[k] = 0.0;
     if (valid) {
+      // the thread's 16 nodes ARE one level-0 block: moments about its own centre (scale 8) by power recurrence
+      const int b0 = (kTS / kTS0) * b + qd;
+      double m0[kTK];
+#pragma unroll
+      for (int k = 0; k < kTK; k++) m0[k] = 0.0;
       float wv[kQ];
 #pragma unroll
       for (int o = 0; o < kQ; o++) {
-        const int i = kTS * b + kQ * qd + o;
+        const int i = kTS0 * b0 + o;
         const double pv = (i >= 1 && i <= M - 1) ? pget(i) : 0.0;
         wv[o] = (float)pv;
-        const double x = -((double)(kQ * qd + o) - 0.5 * (double)(kTS - 1)) * (1.0 / kTs);   // exact
+        const double x = -((double)o - 0.5 * (double)(kTS0 - 1)) * (1.0 / kTs0);   // exact
         double pw = pv;
 #pragma unroll
         for (int k = 0; k < kTK; k++) {
-          m[k] += pw;
+          m0[k] += pw;
           pw *= x;
         }
       }
-      float4* w4 = reinterpret_cast<float4*>(Wt + kTS * b + kQ * qd);
+      float4* w4 = reinterpret_cast<float4*>(Wt + kTS0 * b0);
 #pragma unroll
       for (int o = 0; o < kQ; o += 4) w4[o / 4] = make_float4(wv[o], wv[o + 1], wv[o + 2], wv[o + 3]);
+      // this block's share of the level-1 moments: translation child qd -> parent (the same matrices as level 1 -> 2)
+      {
+        const double* t = sT12 + qd * kTK * kTK;
+#pragma unroll
+        for (int k = 0; k < kTK; k++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j <= k; j++) acc = fma(t[k * kTK + j], m0[j], acc);
+          m[k] = acc;
+        }
+      }
+      // level-0 coefficients (interior nodes only, no end-node rows), packed, straight to the blob
+      const double* cm0 = tstat + kTsCM0;
+      double A0[kTK];
+#pragma unroll
+      for (int mm = 0; mm < kTK; mm++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < kTK / 2; j++)
+          if (2 * j <= mm) acc = fma(__ldg(cm0 + mm * (kTK / 2) + j), m0[mm - 2 * j], acc);
+        A0[mm] = acc * (1.0 / kTs0);
+      }
+      float4* ab = reinterpret_cast<float4*>(blob + tb.oAB0) + b0 * (kTK / 2);
+#pragma unroll
+      for (int q = 0; q < kTK / 2; q++) {
+        const int e0 = 2 * q, e1 = 2 * q + 1;
+        ab[q] = make_float4(e0 + 2 < kTK ? (float)A0[e0 + 2] : 0.f, (float)((double)(e0 + 1) * A0[e0]),
+                            e1 + 2 < kTK ? (float)A0[e1 + 2] : 0.f, (float)((double)(e1 + 1) * A0[e1]));
+      }
+      double* dl = reinterpret_cast<double*>(blob + tb.oLD0) + 2 * b0;
+      dl[0] = A0[0];
+      dl[1] = A0[1];
     }
 #pragma unroll
     for (int k = 0; k < kTK; k++) {
@@ -199,7 +238,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
     tree_far<R>(smem_raw, tb, tp, accI, accJ, accJ2);
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      const TreeAcc na = tree_near(reinterpret_cast<const float*>(smem_raw + tb.oW), tp[r]);
+      const TreeAcc na = tree_near(smem_raw, tb, tp[r]);
       nrI[r] = na.I;
       nrJ[r] = na.J;
     }

@@ -9,9 +9,11 @@
 //
 // the nodes are cut into blocks of 64 (level 1) and 256 (level 2).  For a pole whose nearest node n lies in level-1
 // block bn and level-2 block Bn:
-//   NEAR WINDOW  level-1 blocks wb0..wb0+2 (wb0 = clamp(bn-1, 0, NB-3)): nodes summed one by one -- FP32 series
-//                x(1 + x^2/6 + x^4/15) for |i-n| > kMidHalf = 8, six terms for kNearHalf = 3 < |i-n| <= 8, exact FP64
-//                logs for the 2*kNearHalf+1 nodes around the pole and for an end node inside the window;
+//   NEAR WINDOW  level-1 blocks wb0..wb0+2 (wb0 = clamp(bn-1, 0, NB-3)) = twelve level-0 groups of 16 nodes.  The pole's
+//                group and its two neighbours are summed node by node (FP32 six-term series, exact FP64 logs for the
+//                2*kNearHalf+1 nodes around the pole and for an end node inside the window); the other nine groups lie
+//                at least 17 nodes from the pole and enter through their own level-0 expansions (interior nodes only:
+//                the end-node terms of the window stay with the exact part);
 //   FAR, level 1 the other level-1 blocks whose parent lies in the level-2 window w2..w2+2 (w2 = clamp(Bn-1, ...));
 //   FAR, level 2 every level-2 block outside that window.
 // A far block of S nodes enters through its Laurent expansion about the block centre c:
@@ -31,6 +33,8 @@
 
 namespace tsff {
 
+constexpr int kTS0 = 16;             // nodes per level-0 block (the 16-node groups of the near window)
+constexpr double kTs0 = 8.0;
 constexpr int kTS = 64;              // nodes per level-1 block
 constexpr int kTS2 = 256;            // nodes per level-2 block
 constexpr int kTK = 14;              // expansion order of the forward sweep
@@ -50,9 +54,11 @@ TSFF_HD int tree_npad(int nodes) {   // nodes = M + 1, padded to whole level-2 b
 //   AB2 [NB2][kTK/2]  float4    level-2 ...
 //   LD1 [NB ]         double2   level-1 leading coefficients (A_0, A_1)
 //   LD2 [NB2]         double2
+//   AB0 [NB0][kTK/2]  float4    level-0 (16-node groups, interior nodes only, no end-node rows)
+//   LD0 [NB0]         double2
 struct TreeBlob {
-  int npad, NB, NB2;
-  int oW, oAB1, oAB2, oLD1, oLD2, bytes;  // byte offsets
+  int npad, NB, NB2, NB0;
+  int oW, oAB1, oAB2, oLD1, oLD2, oAB0, oLD0, bytes;  // byte offsets
 };
 TSFF_HD TreeBlob tree_blob(int npad) {
   TreeBlob t;
@@ -64,7 +70,10 @@ TSFF_HD TreeBlob tree_blob(int npad) {
   t.oAB2 = t.oAB1 + t.NB * (kTK / 2) * 16;
   t.oLD1 = t.oAB2 + t.NB2 * (kTK / 2) * 16;
   t.oLD2 = t.oLD1 + t.NB * 16;
-  t.bytes = t.oLD2 + t.NB2 * 16;
+  t.NB0 = npad / kTS0;
+  t.oAB0 = t.oLD2 + t.NB2 * 16;
+  t.oLD0 = t.oAB0 + t.NB0 * (kTK / 2) * 16;
+  t.bytes = t.oLD0 + t.NB0 * 16;
   return t;
 }
 
@@ -127,7 +136,9 @@ constexpr int kTsQE2 = kTsCM2 + kTK * (kTK / 2);
 //   T12 [4][kTK][kTK]     moment translation child -> parent: mu2_k += sum_j T12[c][k][j] mu1_j(child c)
 constexpr int kTsE1 = kTsQE2 + 2 * kTK;
 constexpr int kTsT12 = kTsE1 + kTS * kTK;
-constexpr int kTreeStaticDoubles = kTsT12 + 4 * kTK * kTK;
+//   CM0 [kTK][kTK/2]      level-0 cm matrix
+constexpr int kTsCM0 = kTsT12 + 4 * kTK * kTK;
+constexpr int kTreeStaticDoubles = kTsCM0 + kTK * (kTK / 2);
 TSFF_HD double tree_static_entry(int i, int M) {
   const double c1 = 0.5 * (double)(kTS - 1), c2 = 0.5 * (double)(kTS2 - 1);
   if (i < kTsCM1) {
@@ -153,6 +164,7 @@ TSFF_HD double tree_static_entry(int i, int M) {
     for (int q = 0; q < k; q++) pw *= x;
     return pw;
   }
+  if (i >= kTsCM0) return tree_cm((i - kTsCM0) / (kTK / 2), (i - kTsCM0) % (kTK / 2), kTs0);
   {
     // x2 = (x1 - D)/4 with D = (c_child - c_parent)/s1 = 2 c - 3 for child c = 0..3:  x2^k = 4^-k sum_j C(k,j) (-D)^(k-j) x1^j
     const int c = (i - kTsT12) / (kTK * kTK), k = ((i - kTsT12) / kTK) % kTK, j = (i - kTsT12) % kTK;
@@ -191,6 +203,7 @@ TSFF_HD void tree_coeffs_from_moments(PGet pget, int M, int b, int S, double s, 
     for (int j = 0; 2 * j <= m; j++) a += cmtab[m * (kTK / 2) + j] * mu[m - 2 * j];
     A[m] = a / s;
   }
+  if (!qend) return;   // level 0: interior nodes only
   if (b == 0)
     for (int m = 0; m < kTK; m++) A[m] += pget(0) * qend[m];
   if (M >= S * b && M < S * (b + 1))
@@ -339,16 +352,18 @@ TSFF_HD void tree_far(const unsigned char* blob, const TreeBlob tb, const TreePo
 }
 
 // Near window of ONE pole: the 192 nodes of blocks wb0..wb0+2 except those with |i - n| <= kNearHalf.
-// sW: node weights p_i (FP32; zero at i = 0, i >= M and in the padding), 16-byte aligned.
+// blob: the staged per-lineout blob; its node weights p_i are FP32, zero at i = 0, i >= M and in the padding.
 // returns I = sum p_i W(g_i),  J = sum p_i h dW/dxi(g_i)   (dI/dxi = J / h, applied by the caller).
 // The window is walked in 12 groups of 16 nodes, ROTATED so that every lane starts at the group that holds its own
-// pole: the pole's group and its two neighbours take the six-term series with the exact-zone mask, the other nine the
-// three-term series -- the same instruction stream for all lanes whatever their pole positions (no vote, no
-// divergence).  Two nodes share one packed instruction; every 16-node group enters the FP64 accumulator of I.
+// pole: the pole's group and its two neighbours are summed node by node (six-term series with the exact-zone mask, two
+// nodes per packed instruction), the other nine through their level-0 expansions (tree_far_block, one reciprocal and 13
+// packed FMAs per group instead of 16 reciprocals and ~120 FP32 instructions) -- the same instruction stream for all
+// lanes whatever their pole positions (no vote, no divergence).
 struct TreeAcc {
   double I, J;
 };
-TSFF_HD_NOINLINE TreeAcc tree_near(const float* sW, const TreePole tp) {
+TSFF_HD_NOINLINE TreeAcc tree_near(const unsigned char* blob, const TreeBlob tb, const TreePole tp) {
+  const float* sW = reinterpret_cast<const float*>(blob + tb.oW);
   double accI = 0.0;
   const float4* w4 = reinterpret_cast<const float4*>(sW + kTS * tp.wb0);
   const float ub = (float)(kTS * tp.wb0) + tp.un;  // i0 - n, exact (<= 0)
@@ -391,34 +406,25 @@ TSFF_HD_NOINLINE TreeAcc tree_near(const float* sW, const TreePole tp) {
     }
     accI += (double)aI.x + (double)aI.y;
   }
-  double accJ = (double)aJ.x + (double)aJ.y;
-  aJ = f2(0.f, 0.f);
-  // ---- the other nine groups (|i - n| >= 17): W = x (1 + x^2/6 + x^4/15),  h dW/dxi = x^2 (1 + x^2/2 + x^4/3)
-  const float2 c2 = f2(1.f / 6.f, 1.f / 6.f), c4 = f2(1.f / 15.f, 1.f / 15.f), d2 = f2(0.5f, 0.5f), d4 = f2(1.f / 3.f, 1.f / 3.f);
+  const double accJ = (double)aJ.x + (double)aJ.y;
+  // ---- the other nine groups (|i - n| >= 17, |t| = 8 h / |z_c - xi| <= 0.34): level-0 expansions
+  const float4* ab0 = reinterpret_cast<const float4*>(blob + tb.oAB0);
+  const double* ld0 = reinterpret_cast<const double*>(blob + tb.oLD0);
+  const TreePole tp1[1] = {tp};
+  const bool use1[1] = {true};
+  float fI[1] = {0.f}, fJ[1] = {0.f};
+  double f64[1] = {0.0};
 #pragma unroll 1
   for (int j = 2; j <= 10; j++) {
     int q = qn + j;
     q = q >= 12 ? q - 12 : q;
-    const float ulo = ub + (float)(16 * q);
-    float2 aI = f2(0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const float4 w = w4[4 * q + c];
-#pragma unroll
-      for (int hlf = 0; hlf < 2; hlf++) {
-        const float u0 = ulo + (float)(4 * c + 2 * hlf);
-        const float2 x = f2(rcp_approx(u0 + tp.ndh), rcp_approx((u0 + 1.f) + tp.ndh));
-        const float2 s2 = fmul2(x, x);
-        const float2 wv = hlf ? f2(w.z, w.w) : f2(w.x, w.y);
-        aI = ffma2(fmul2(wv, x), ffma2(ffma2(s2, c4, c2), s2, one), aI);
-        aJ = ffma2(fmul2(wv, s2), ffma2(ffma2(s2, d4, d2), s2, one), aJ);
-      }
-    }
-    accI += (double)aI.x + (double)aI.y;
+    const int b0 = (kTS / kTS0) * tp.wb0 + q;
+    tree_far_block<1>(ab0 + b0 * (kTK / 2), ld0 + 2 * b0, (float)(2 * b0) + (float)(0.5 * (kTS0 - 1) / kTs0), (float)(1.0 / kTs0), tp1,
+                      use1, fI, fJ, f64);
   }
   TreeAcc r;
-  r.I = accI;
-  r.J = accJ + ((double)aJ.x + (double)aJ.y);
+  r.I = accI + f64[0] + (double)fI[0];
+  r.J = accJ + (double)fJ[0] * (1.0 / kTs0);   // the block sums carry 1 / (s0 h), the node sums 1 / h
   return r;
 }
 
