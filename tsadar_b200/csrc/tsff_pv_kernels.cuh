@@ -284,11 +284,11 @@ struct PvNodesArgs {
 };
 
 constexpr int kNodeChunk = 1024;   // poles staged per shared-memory chunk (2 x 16 KB)
-constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per block
+constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per level-1 block
 
 inline size_t pv_nodes_smem(int npad) {
-  const int NB = npad / kTS;
-  return (size_t)kNodeChunk * 16 * 2 + (size_t)(npad + 2) * 8 + (size_t)NB * kTKA * 8 + (size_t)(NB + 1) * 4 * 2 + 64;
+  const int NB = npad / kTS, NB0 = npad / kTS0;
+  return (size_t)kNodeChunk * 16 + (size_t)(npad + 2) * 8 + (size_t)NB * kTKA * 8 + (size_t)NB0 * kTKA * 4 + (size_t)(NB0 + 2) * 4 * 2 + 64;
 }
 
 // pole splits per lineout: 1 when the batch alone fills the device, else enough CTAs for two per SM (each split
@@ -312,24 +312,29 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// Adjoint partition (the transpose of the forward sweep's, level 2 left out).  For a pole with nearest node n, level-0
+// group gn = n / 16 and level-1 window wb0..wb0+2 (twelve level-0 groups):
+//   FAR 1    level-1 blocks outside the window: local coefficients L1_{b,m} += Ibar t^(m+1), t = 32 h / (z_c - xi)
+//   FAR 0    level-0 groups of the window at least two groups from gn: L0_{b,m} += Ibar t^(m+1), t = 8 h / (z_c - xi)
+//   NEAR     the nodes of groups gn-1 .. gn+1, one by one (six-term series); |i - n| <= kNearHalf masked -- those nodes, and
+//            an end node inside the window, get their exact FP64 terms from the caller (pv_bwd_pole_exact)
 // One CTA per (lineout, pole split).  Per chunk of kNodeChunk poles:
 //   1. stage the descriptors in shared memory
-//   2. far:  thread (block fb, pole subset fq) accumulates L_{fb,m} += Ibar_p t^(m+1) over its far poles (two poles per
-//      packed instruction); FP32 within the chunk, FP64 across chunks
-//   3. counting-sort the descriptors by window start wb0, so that every node block sees its near poles as one
-//      contiguous range
-//   4. near: a warp owns one 64-node block at a time (two nodes per lane, packed) and loops over the poles with
-//      wb0 in [nb-2, nb]; short series, |i - n_p| <= kNearHalf masked (the exact FP64 terms are added by the caller)
-// then L is spread to the nodes with the static weights q_m(e) and everything is written (or atomically added) to pbar.
+//   2. FAR 1: thread (block fb, pole subset fq) over all poles of the chunk, two poles per packed instruction
+//   3. counting-sort the descriptors by gn: every set of poles used below is one contiguous range of the sorted list
+//   4. FAR 0: thread <-> level-0 group, over the poles whose window holds the group's level-1 parent
+//   5. NEAR: thread <-> node, over the poles with gn within one group of the node's group
+// FP32 inside a chunk (at most 64 poles per partial sum in the near loop), FP64 across.  Then L1 and L0 are spread to
+// the nodes with the static weights q_m(e) and everything is written (or atomically added) to pbar.
 static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int NB = a.npad / kTS, M = a.nodes - 1;
-  float4* sraw = reinterpret_cast<float4*>(smem_raw);
-  float4* ssort = sraw + kNodeChunk;
+  const int NB = a.npad / kTS, NB0 = a.npad / kTS0, M = a.nodes - 1;
+  float4* ssort = reinterpret_cast<float4*>(smem_raw);                 // [kNodeChunk] descriptors sorted by gn
   double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad + 2]  (the fused epilogue needs nodes + 1 <= npad + 1)
   double* sL = spbar + a.npad + 2;                                     // [NB][kTKA]
-  int* shist = reinterpret_cast<int*>(sL + NB * kTKA);                  // [NB + 1]
-  int* scur = shist + NB + 1;                                          // [NB + 1]
+  float* sL0 = reinterpret_cast<float*>(sL + NB * kTKA);               // [NB0][kTKA]  (FP32: three CTAs per SM fit with it)
+  int* shist = reinterpret_cast<int*>(sL0 + NB0 * kTKA);               // [NB0 + 2]  first sorted slot of key gn
+  int* scur = shist + NB0 + 2;                                         // [NB0 + 2]
   const long long b = blockIdx.x / a.nsplit;
   const int split = blockIdx.x % a.nsplit;
   const int per = (a.P + a.nsplit - 1) / a.nsplit;
@@ -339,6 +344,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
 
   for (int i = threadIdx.x; i < a.npad + 2; i += kPvThreads) spbar[i] = 0.0;
   for (int i = threadIdx.x; i < NB * kTKA; i += kPvThreads) sL[i] = 0.0;
+  for (int i = threadIdx.x; i < NB0 * kTKA; i += kPvThreads) sL0[i] = 0.f;
   if (a.fe_bar) {   // fused epilogue: pull this lineout's accumulator rows towards L2 now, they are read at the very end
     const int Vv = a.nodes + 1;
     for (int i = threadIdx.x * 16; i < Vv; i += kPvThreads * 16) {
@@ -346,7 +352,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.accfe + b * Vv + i));
     }
   }
-  // far-phase thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
+  // far-1 thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
   int NBP = 1;
   while (NBP < NB) NBP <<= 1;
   const int Q = kPvThreads / NBP;
@@ -355,24 +361,49 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   double L64[kTKA];
 #pragma unroll
   for (int m = 0; m < kTKA; m++) L64[m] = 0.0;
-  const float2 one = make_float2(1.f, 1.f), c2 = make_float2(1.f / 6.f, 1.f / 6.f), c4 = make_float2(1.f / 15.f, 1.f / 15.f);
-  const float lim = (float)kNearHalf + 0.5f, mid = (float)kMidHalf + 0.5f;
+  const float lim = (float)kNearHalf + 0.5f;
+  // first / last level-0 key of the poles whose window starts at level-1 block w
+  auto glo = [NB](int w) { return w <= 0 ? 0 : (kTS / kTS0) * (w + 1); };
+  auto ghi = [NB, NB0](int w) { return w >= NB - 3 ? NB0 - 1 : (kTS / kTS0) * (w + 1) + (kTS / kTS0) - 1; };
 
   for (int c0 = p_begin; c0 < p_end; c0 += kNodeChunk) {
     const int nc = min(kNodeChunk, p_end - c0);
     __syncthreads();
-    for (int k = threadIdx.x; k < nc; k += kPvThreads) sraw[k] = desc[c0 + k];
-    for (int k = threadIdx.x; k <= NB; k += kPvThreads) shist[k] = 0;
+    for (int k = threadIdx.x; k < NB0 + 2; k += kPvThreads) shist[k] = 0;
     __syncthreads();
-    // ---- far
+    // ---- counting sort by gn = n / 16 (n = -un), straight from global memory (the second read hits L1 / L2)
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[(((int)(-desc[c0 + k].x)) >> 4) + 1], 1);
+    __syncthreads();
+    if (wid == 0) {  // inclusive scan -> shist[k] = first sorted slot of key k, shist[NB0] = nc
+      int carry = 0;
+      for (int k0 = 0; k0 <= NB0; k0 += 32) {
+        const int k = k0 + lane;
+        int v = (k <= NB0) ? shist[k] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += n;
+        }
+        v += carry;
+        if (k <= NB0) { shist[k] = v; scur[k] = v; }
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) {
+      const float4 d = desc[c0 + k];
+      ssort[atomicAdd(&scur[((int)(-d.x)) >> 4], 1)] = d;
+    }
+    __syncthreads();
+    // ---- far 1 (the order of the poles does not matter)
     if (fb < NB) {
       float2 Lp[kTKA];
 #pragma unroll
       for (int m = 0; m < kTKA; m++) Lp[m] = make_float2(0.f, 0.f);
       for (int k = fq; k < nc; k += 2 * Q) {
-        const float4 d0 = sraw[k];
+        const float4 d0 = ssort[k];
         const bool has1 = (k + Q) < nc;
-        const float4 d1 = has1 ? sraw[k + Q] : make_float4(0.f, 0.f, 0.f, __int_as_float(fb));
+        const float4 d1 = has1 ? ssort[k + Q] : make_float4(0.f, 0.f, 0.f, __int_as_float(fb));
         const float g0 = fmaf(d0.y, kInvTs, fmaf(d0.x, kInvTs, cb));
         const float g1 = fmaf(d1.y, kInvTs, fmaf(d1.x, kInvTs, cb));
         const bool far0 = (unsigned)(fb - __float_as_int(d0.w)) > 2u;
@@ -388,65 +419,68 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
 #pragma unroll
       for (int m = 0; m < kTKA; m++) L64[m] += (double)Lp[m].x + (double)Lp[m].y;
     }
-    // ---- counting sort by wb0
-    for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[__float_as_int(sraw[k].w) + 1], 1);
-    __syncthreads();
-    if (wid == 0) {  // inclusive scan -> shist[k] = first sorted slot of key k, shist[NB] = nc
-      int carry = 0;
-      for (int k0 = 0; k0 <= NB; k0 += 32) {
-        const int k = k0 + lane;
-        int v = (k <= NB) ? shist[k] : 0;
+    // ---- far 0: a warp takes one level-1 block at a time (strided over the warps: every warp samples the whole grid, so
+    // bunched poles do not leave warps idle); lane = (child group c = lane / 8, pole subset lane % 8) over the poles whose
+    // window [wb0, wb0 + 2] holds the block; the eight subsets are added by shuffles
+    for (int b1 = wid; b1 < NB; b1 += kPvThreads / 32) {
+      const int b0 = (kTS / kTS0) * b1 + (lane >> 3), sub = lane & 7;
+      const int klo = shist[glo(max(b1 - 2, 0))], khi = shist[ghi(min(b1, NB - 3)) + 1];
+      const float cb0 = (float)(2 * b0) + (float)(0.5 * (kTS0 - 1) / kTs0);
+      const float invs0 = (float)(1.0 / kTs0);
+      float2 Lp[kTKA];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int n = __shfl_up_sync(0xffffffffu, v, o);
-          if (lane >= o) v += n;
+      for (int m = 0; m < kTKA; m++) Lp[m] = make_float2(0.f, 0.f);
+      for (int k = klo + sub; k < khi; k += 16) {
+        const float4 d0 = ssort[k];
+        const bool has1 = (k + 8) < khi;
+        const float4 d1 = has1 ? ssort[k + 8] : d0;
+        const int g0n = ((int)(-d0.x)) >> 4, g1n = ((int)(-d1.x)) >> 4;
+        const bool far0 = abs(b0 - g0n) >= 2;
+        const bool far1 = has1 && abs(b0 - g1n) >= 2;
+        const float g0 = fmaf(d0.y, invs0, fmaf(d0.x, invs0, cb0));
+        const float g1 = fmaf(d1.y, invs0, fmaf(d1.x, invs0, cb0));
+        const float2 t = make_float2(far0 ? rcp_approx(g0) : 0.f, far1 ? rcp_approx(g1) : 0.f);
+        float2 pw = fmul2(make_float2(d0.z, d1.z), t);
+#pragma unroll
+        for (int m = 0; m < kTKA; m++) {
+          Lp[m] = fadd2(Lp[m], pw);
+          pw = fmul2(pw, t);
         }
-        v += carry;
-        if (k <= NB) { shist[k] = v; scur[k] = v; }
-        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+#pragma unroll
+      for (int m = 0; m < kTKA; m++) {
+        float v = Lp[m].x + Lp[m].y;             // FP32 like the sums themselves; FP64 across chunks
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == 0) sL0[b0 * kTKA + m] += v;   // one writer per group
       }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nc; k += kPvThreads) {
-      const float4 d = sraw[k];
-      ssort[atomicAdd(&scur[__float_as_int(d.w)], 1)] = d;
-    }
-    __syncthreads();
-    // ---- near
-    for (int nb = wid; nb < NB; nb += kPvThreads / 32) {
-      // poles whose window [wb0, wb0+2] contains block nb: wb0 in [nb-2, nb]
-      const int klo = shist[max(nb - 2, 0)], khi = shist[nb + 1];
-      const float fi0 = (float)(kTS * nb + 2 * lane);
-      double acc64x = 0.0, acc64y = 0.0;
-      for (int kc = klo; kc < khi; kc += 64) {     // FP32 partial sums over at most 64 poles, then into the FP64 accumulators
+    // ---- near: thread <-> node i (its slot of spbar is private), poles with gn in [gi - 1, gi + 1]
+    for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+      if (i < 1 || i > M - 1) continue;
+      const int gi = i >> 4;
+      const int klo = shist[max(gi - 1, 0)], khi = shist[min(gi + 1, NB0 - 1) + 1];
+      const float fi = (float)i;
+      double acc64 = 0.0;
+      for (int kc = klo; kc < khi; kc += 64) {
         const int ke = min(kc + 64, khi);
-        float2 acc = make_float2(0.f, 0.f);
+        float acc = 0.f;
         for (int k = kc; k < ke; k++) {
           const float4 d = ssort[k];
-          const float u0 = fi0 + d.x, u1 = u0 + 1.f;   // i - n_p, exact
-          const float x0 = rcp_approx(u0 + d.y), x1 = rcp_approx(u1 + d.y);
-          // this block comes within kMidHalf nodes of the pole only if n_p is within kMidHalf of it (warp-uniform test)
-          const float nrel = -d.x - (float)(kTS * nb);
-          if (nrel >= -mid && nrel <= (float)(kTS - 1) + mid) {
-            const float2 x = make_float2(fabsf(u0) > lim ? x0 : 0.f, fabsf(u1) > lim ? x1 : 0.f);
-            const float2 s2 = fmul2(x, x);
-            float2 pI = ffma2(make_float2(1.f / 66.f, 1.f / 66.f), s2, make_float2(1.f / 45.f, 1.f / 45.f));
-            pI = ffma2(pI, s2, make_float2(1.f / 28.f, 1.f / 28.f));
-            pI = ffma2(pI, s2, c4);
-            pI = ffma2(pI, s2, c2);
-            pI = ffma2(pI, s2, one);
-            acc = ffma2(fmul2(make_float2(d.z, d.z), x), pI, acc);
-          } else {
-            const float2 x = make_float2(x0, x1);
-            const float2 s2 = fmul2(x, x);
-            acc = ffma2(fmul2(make_float2(d.z, d.z), x), ffma2(ffma2(s2, c4, c2), s2, one), acc);
-          }
+          const float u = fi + d.x;   // i - n_p, exact
+          const float x = fabsf(u) > lim ? rcp_approx(u + d.y) : 0.f;
+          const float s2 = x * x;
+          float pI = fmaf(1.f / 66.f, s2, 1.f / 45.f);
+          pI = fmaf(pI, s2, 1.f / 28.f);
+          pI = fmaf(pI, s2, 1.f / 15.f);
+          pI = fmaf(pI, s2, 1.f / 6.f);
+          pI = fmaf(pI, s2, 1.f);
+          acc = fmaf(d.z * x, pI, acc);
         }
-        acc64x += (double)acc.x;
-        acc64y += (double)acc.y;
+        acc64 += (double)acc;
       }
-      spbar[kTS * nb + 2 * lane] += acc64x;
-      spbar[kTS * nb + 2 * lane + 1] += acc64y;
+      spbar[i] += acc64;
     }
   }
   if (fb < NB) {
@@ -454,29 +488,40 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
     for (int m = 0; m < kTKA; m++) atomicAdd(&sL[fb * kTKA + m], L64[m]);
   }
   __syncthreads();
-  // ---- spread the local coefficients to the nodes and write out
+  // ---- spread the local coefficients of both levels to the nodes and write out
   double* out = a.pbar + b * a.npad;
   const double* q = a.tstat + kTsQA;
   const bool fused = a.fe_bar != nullptr;
   const int V = a.nodes + 1;
-  for (int i = threadIdx.x; i < a.npad + 2; i += kPvThreads) {
-    if (i >= a.npad) continue;
-    double v = 0.0;
-    const int nb = i / kTS, k = i % kTS;
-    if (i >= 1 && i <= M - 1) {
-      v = spbar[i];
+  {
+    // node i = threadIdx.x + k kPvThreads: its in-block offsets i % 64 and i % 16 do not depend on k, so the two rows of
+    // spreading weights are loaded once per thread
+    double wq1[kTKA], wq0[kTKA];
 #pragma unroll
-      for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[k * kTKA + m];
-    } else if (i == 0) {
-#pragma unroll
-      for (int m = 0; m < kTKA; m++) v += sL[m] * q[kTS * kTKA + m];
-    } else if (i == M) {
-#pragma unroll
-      for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m];
+    for (int m = 0; m < kTKA; m++) {
+      wq1[m] = q[(threadIdx.x % kTS) * kTKA + m];
+      wq0[m] = a.tstat[kTsQA0 + (threadIdx.x % kTS0) * kTKA + m];
     }
-    if (fused) spbar[i] = v;   // each thread rewrites only the slot it has just read
-    else if (a.nsplit == 1) out[i] = v;
-    else if (v != 0.0) atomicAdd(&out[i], v);
+    for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+      double v = 0.0;
+      const int nb = i / kTS;
+      if (i >= 1 && i <= M - 1) {
+        v = spbar[i];
+        const double* l1 = sL + nb * kTKA;
+        const float* l0 = sL0 + (i / kTS0) * kTKA;
+#pragma unroll
+        for (int m = 0; m < kTKA; m++) v += l1[m] * wq1[m] + (double)l0[m] * wq0[m];
+      } else if (i == 0) {
+#pragma unroll
+        for (int m = 0; m < kTKA; m++) v += sL[m] * q[kTS * kTKA + m];
+      } else if (i == M) {
+#pragma unroll
+        for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m];
+      }
+      if (fused) spbar[i] = v;   // each thread rewrites only the slot it has just read
+      else if (a.nsplit == 1) out[i] = v;
+      else if (v != 0.0) atomicAdd(&out[i], v);
+    }
   }
   if (!fused) return;
   // + the pole kernel's exact near-zone / lerp contributions (eight independent loads in flight per thread; the rows

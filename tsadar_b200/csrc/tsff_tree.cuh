@@ -138,7 +138,9 @@ constexpr int kTsE1 = kTsQE2 + 2 * kTK;
 constexpr int kTsT12 = kTsE1 + kTS * kTK;
 //   CM0 [kTK][kTK/2]      level-0 cm matrix
 constexpr int kTsCM0 = kTsT12 + 4 * kTK * kTK;
-constexpr int kTreeStaticDoubles = kTsCM0 + kTK * (kTK / 2);
+//   QA0 [kTS0][kTKA]      adjoint spreading weights of the level-0 in-block offsets (interior nodes only)
+constexpr int kTsQA0 = kTsCM0 + kTK * (kTK / 2);
+constexpr int kTreeStaticDoubles = kTsQA0 + kTS0 * kTKA;
 TSFF_HD double tree_static_entry(int i, int M) {
   const double c1 = 0.5 * (double)(kTS - 1), c2 = 0.5 * (double)(kTS2 - 1);
   if (i < kTsCM1) {
@@ -164,6 +166,7 @@ TSFF_HD double tree_static_entry(int i, int M) {
     for (int q = 0; q < k; q++) pw *= x;
     return pw;
   }
+  if (i >= kTsQA0) return tree_q((i - kTsQA0) % kTKA, (double)((i - kTsQA0) / kTKA) - 0.5 * (double)(kTS0 - 1), kTs0);
   if (i >= kTsCM0) return tree_cm((i - kTsCM0) / (kTK / 2), (i - kTsCM0) % (kTK / 2), kTs0);
   {
     // x2 = (x1 - D)/4 with D = (c_child - c_parent)/s1 = 2 c - 3 for child c = 0..3:  x2^k = 4^-k sum_j C(k,j) (-D)^(k-j) x1^j
