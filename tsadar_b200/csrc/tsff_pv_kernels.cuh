@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kPvThreads) k_pv_poles(const PvPolesArgs a) {
 
 // ---- adjoint ----------------------------------------------------------------------------------------------------
 struct PvNodesArgs {
-  const float4* desc;   // [B][P]  (un = -n_p, ndh = -delta_p/h, Ibar_p, wb0 as int bits)
+  const float4* desc;   // [B][P]  (un = -n_p, ndh = -delta_p/h, Ibar_p, packed keys gn | wb0 << 10 | w2 << 18: pv_desc)
   const double* tstat;  // k_tree_static table
   int P, nodes, npad, nsplit;
   double* pbar;         // [B][npad]  d loss / d p_i without the exact near part (nsplit > 1: atomically accumulated, zero it)
@@ -284,11 +284,11 @@ struct PvNodesArgs {
 };
 
 constexpr int kNodeChunk = 1024;   // poles staged per shared-memory chunk (2 x 16 KB)
-constexpr int kTreeMaxNpad = 256 * kTS;  // one far-phase thread per level-1 block
+constexpr int kTreeMaxNpad = 256 * kTS;  // 1024 level-0 groups (10-bit key), 256 level-1 and 64 level-2 blocks
 
 inline size_t pv_nodes_smem(int npad) {
   const int NB = npad / kTS, NB0 = npad / kTS0;
-  return (size_t)kNodeChunk * 16 + (size_t)(npad + 2) * 8 + (size_t)NB * kTKA * 8 + (size_t)NB0 * kTKA * 4 + (size_t)(NB0 + 2) * 4 * 2 + 64;
+  return (size_t)kNodeChunk * 16 + (size_t)(npad + 2) * 8 + (size_t)(NB + npad / kTS2) * kTKA * 8 + (size_t)NB0 * kTKA * 4 + (size_t)(NB0 + 2) * 4 * 2 + 64;
 }
 
 // pole splits per lineout: 1 when the batch alone fills the device, else enough CTAs for two per SM (each split
@@ -312,27 +312,30 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
-// Adjoint partition (the transpose of the forward sweep's, level 2 left out).  For a pole with nearest node n, level-0
-// group gn = n / 16 and level-1 window wb0..wb0+2 (twelve level-0 groups):
-//   FAR 1    level-1 blocks outside the window: local coefficients L1_{b,m} += Ibar t^(m+1), t = 32 h / (z_c - xi)
+// Adjoint partition = the transpose of the forward sweep's.  For a pole with nearest node n, level-0 group gn = n / 16,
+// level-1 window wb0..wb0+2 (twelve level-0 groups) and level-2 window w2..w2+2:
+//   FAR 2    level-2 blocks outside the level-2 window: L2_{B,m} += Ibar t^(m+1), t = 128 h / (z_c - xi)
+//   FAR 1    level-1 blocks inside the level-2 window but outside the level-1 window: L1_{b,m}, t = 32 h / (z_c - xi)
 //   FAR 0    level-0 groups of the window at least two groups from gn: L0_{b,m} += Ibar t^(m+1), t = 8 h / (z_c - xi)
 //   NEAR     the nodes of groups gn-1 .. gn+1, one by one (six-term series); |i - n| <= kNearHalf masked -- those nodes, and
 //            an end node inside the window, get their exact FP64 terms from the caller (pv_bwd_pole_exact)
 // One CTA per (lineout, pole split).  Per chunk of kNodeChunk poles:
 //   1. stage the descriptors in shared memory
-//   2. FAR 1: thread (block fb, pole subset fq) over all poles of the chunk, two poles per packed instruction
-//   3. counting-sort the descriptors by gn: every set of poles used below is one contiguous range of the sorted list
-//   4. FAR 0: thread <-> level-0 group, over the poles whose window holds the group's level-1 parent
+//   2. counting-sort the descriptors by gn: every set of poles used below is one contiguous range of the sorted list
+//   3. FAR 2: thread (block, pole subset) over all poles of the chunk, two poles per packed instruction
+//   4. FAR 1 / FAR 0: a warp takes one parent block at a time, lanes = 4 children x 8 pole subsets, over the poles whose
+//      window holds the parent; the subsets are added by shuffles
 //   5. NEAR: thread <-> node, over the poles with gn within one group of the node's group
 // FP32 inside a chunk (at most 64 poles per partial sum in the near loop), FP64 across.  Then L1 and L0 are spread to
 // the nodes with the static weights q_m(e) and everything is written (or atomically added) to pbar.
-static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArgs a) {
+static __global__ void __launch_bounds__(kPvThreads, 3) k_pv_nodes(const PvNodesArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int NB = a.npad / kTS, NB0 = a.npad / kTS0, M = a.nodes - 1;
+  const int NB = a.npad / kTS, NB0 = a.npad / kTS0, NB2 = a.npad / kTS2, M = a.nodes - 1;
   float4* ssort = reinterpret_cast<float4*>(smem_raw);                 // [kNodeChunk] descriptors sorted by gn
   double* spbar = reinterpret_cast<double*>(ssort + kNodeChunk);       // [npad + 2]  (the fused epilogue needs nodes + 1 <= npad + 1)
   double* sL = spbar + a.npad + 2;                                     // [NB][kTKA]
-  float* sL0 = reinterpret_cast<float*>(sL + NB * kTKA);               // [NB0][kTKA]  (FP32: three CTAs per SM fit with it)
+  double* sL2 = sL + NB * kTKA;                                        // [NB2][kTKA]
+  float* sL0 = reinterpret_cast<float*>(sL2 + NB2 * kTKA);             // [NB0][kTKA]  (FP32: three CTAs per SM fit with it)
   int* shist = reinterpret_cast<int*>(sL0 + NB0 * kTKA);               // [NB0 + 2]  first sorted slot of key gn
   int* scur = shist + NB0 + 2;                                         // [NB0 + 2]
   const long long b = blockIdx.x / a.nsplit;
@@ -343,7 +346,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   for (int i = threadIdx.x; i < a.npad + 2; i += kPvThreads) spbar[i] = 0.0;
-  for (int i = threadIdx.x; i < NB * kTKA; i += kPvThreads) sL[i] = 0.0;
+  for (int i = threadIdx.x; i < (NB + NB2) * kTKA; i += kPvThreads) sL[i] = 0.0;
   for (int i = threadIdx.x; i < NB0 * kTKA; i += kPvThreads) sL0[i] = 0.f;
   if (a.fe_bar) {   // fused epilogue: pull this lineout's accumulator rows towards L2 now, they are read at the very end
     const int Vv = a.nodes + 1;
@@ -352,12 +355,13 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.accfe + b * Vv + i));
     }
   }
-  // far-1 thread layout: NBP (power of two >= NB, <= 256) blocks x Q pole subsets
+  // far-2 thread layout: NBP (power of two >= NB2, <= 64) blocks x Q pole subsets
   int NBP = 1;
-  while (NBP < NB) NBP <<= 1;
+  while (NBP < NB2) NBP <<= 1;
   const int Q = kPvThreads / NBP;
   const int fb = threadIdx.x % NBP, fq = threadIdx.x / NBP;
-  const float cb = (float)(2 * fb) + (float)(0.5 * (kTS - 1) / kTs);
+  const float cb = (float)(2 * fb) + (float)(0.5 * (kTS2 - 1) / kTs2);
+  const float invs2 = (float)(1.0 / kTs2);
   double L64[kTKA];
 #pragma unroll
   for (int m = 0; m < kTKA; m++) L64[m] = 0.0;
@@ -365,6 +369,9 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   // first / last level-0 key of the poles whose window starts at level-1 block w
   auto glo = [NB](int w) { return w <= 0 ? 0 : (kTS / kTS0) * (w + 1); };
   auto ghi = [NB, NB0](int w) { return w >= NB - 3 ? NB0 - 1 : (kTS / kTS0) * (w + 1) + (kTS / kTS0) - 1; };
+  // the same for the level-2 window start w2
+  auto g2lo = [](int w) { return w <= 0 ? 0 : (kTS2 / kTS0) * (w + 1); };
+  auto g2hi = [NB2, NB0](int w) { return w >= NB2 - 3 ? NB0 - 1 : (kTS2 / kTS0) * (w + 1) + (kTS2 / kTS0) - 1; };
 
   for (int c0 = p_begin; c0 < p_end; c0 += kNodeChunk) {
     const int nc = min(kNodeChunk, p_end - c0);
@@ -372,7 +379,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
     for (int k = threadIdx.x; k < NB0 + 2; k += kPvThreads) shist[k] = 0;
     __syncthreads();
     // ---- counting sort by gn = n / 16 (n = -un), straight from global memory (the second read hits L1 / L2)
-    for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[(((int)(-desc[c0 + k].x)) >> 4) + 1], 1);
+    for (int k = threadIdx.x; k < nc; k += kPvThreads) atomicAdd(&shist[(__float_as_int(desc[c0 + k].w) & 1023) + 1], 1);
     __syncthreads();
     if (wid == 0) {  // inclusive scan -> shist[k] = first sorted slot of key k, shist[NB0] = nc
       int carry = 0;
@@ -392,22 +399,23 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
     __syncthreads();
     for (int k = threadIdx.x; k < nc; k += kPvThreads) {
       const float4 d = desc[c0 + k];
-      ssort[atomicAdd(&scur[((int)(-d.x)) >> 4], 1)] = d;
+      ssort[atomicAdd(&scur[__float_as_int(d.w) & 1023], 1)] = d;
     }
     __syncthreads();
-    // ---- far 1 (the order of the poles does not matter)
-    if (fb < NB) {
+    // ---- far 2 (the order of the poles does not matter): level-2 window start w2 = clamp(n / 256 - 1, 0, NB2 - 3)
+    if (fb < NB2) {
       float2 Lp[kTKA];
 #pragma unroll
       for (int m = 0; m < kTKA; m++) Lp[m] = make_float2(0.f, 0.f);
       for (int k = fq; k < nc; k += 2 * Q) {
         const float4 d0 = ssort[k];
         const bool has1 = (k + Q) < nc;
-        const float4 d1 = has1 ? ssort[k + Q] : make_float4(0.f, 0.f, 0.f, __int_as_float(fb));
-        const float g0 = fmaf(d0.y, kInvTs, fmaf(d0.x, kInvTs, cb));
-        const float g1 = fmaf(d1.y, kInvTs, fmaf(d1.x, kInvTs, cb));
-        const bool far0 = (unsigned)(fb - __float_as_int(d0.w)) > 2u;
-        const bool far1 = has1 && ((unsigned)(fb - __float_as_int(d1.w)) > 2u);
+        const float4 d1 = has1 ? ssort[k + Q] : d0;
+        const int w20 = __float_as_int(d0.w) >> 18, w21 = __float_as_int(d1.w) >> 18;
+        const float g0 = fmaf(d0.y, invs2, fmaf(d0.x, invs2, cb));
+        const float g1 = fmaf(d1.y, invs2, fmaf(d1.x, invs2, cb));
+        const bool far0 = (unsigned)(fb - w20) > 2u;
+        const bool far1 = has1 && ((unsigned)(fb - w21) > 2u);
         const float2 t = make_float2(far0 ? rcp_approx(g0) : 0.f, far1 ? rcp_approx(g1) : 0.f);
         float2 pw = fmul2(make_float2(d0.z, d1.z), t);
 #pragma unroll
@@ -418,6 +426,40 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       }
 #pragma unroll
       for (int m = 0; m < kTKA; m++) L64[m] += (double)Lp[m].x + (double)Lp[m].y;
+    }
+    // ---- far 1: a warp takes one level-2 block at a time; lane = (child level-1 block lane / 8, pole subset lane % 8) over
+    // the poles whose level-2 window holds it; a child inside the pole's level-1 window is masked
+    for (int B2 = wid; B2 < NB2; B2 += kPvThreads / 32) {
+      const int b1 = (kTS2 / kTS) * B2 + (lane >> 3), sub = lane & 7;
+      const int klo = shist[g2lo(max(B2 - 2, 0))], khi = shist[g2hi(min(B2, NB2 - 3)) + 1];
+      const float cb1 = (float)(2 * b1) + (float)(0.5 * (kTS - 1) / kTs);
+      float2 Lp[kTKA];
+#pragma unroll
+      for (int m = 0; m < kTKA; m++) Lp[m] = make_float2(0.f, 0.f);
+      for (int k = klo + sub; k < khi; k += 16) {
+        const float4 d0 = ssort[k];
+        const bool has1 = (k + 8) < khi;
+        const float4 d1 = has1 ? ssort[k + 8] : d0;
+        const bool far0 = (unsigned)(b1 - ((__float_as_int(d0.w) >> 10) & 255)) > 2u;
+        const bool far1 = has1 && ((unsigned)(b1 - ((__float_as_int(d1.w) >> 10) & 255)) > 2u);
+        const float g0 = fmaf(d0.y, kInvTs, fmaf(d0.x, kInvTs, cb1));
+        const float g1 = fmaf(d1.y, kInvTs, fmaf(d1.x, kInvTs, cb1));
+        const float2 t = make_float2(far0 ? rcp_approx(g0) : 0.f, far1 ? rcp_approx(g1) : 0.f);
+        float2 pw = fmul2(make_float2(d0.z, d1.z), t);
+#pragma unroll
+        for (int m = 0; m < kTKA; m++) {
+          Lp[m] = fadd2(Lp[m], pw);
+          pw = fmul2(pw, t);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < kTKA; m++) {
+        float v = Lp[m].x + Lp[m].y;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == 0) sL[b1 * kTKA + m] += (double)v;   // one writer per block
+      }
     }
     // ---- far 0: a warp takes one level-1 block at a time (strided over the warps: every warp samples the whole grid, so
     // bunched poles do not leave warps idle); lane = (child group c = lane / 8, pole subset lane % 8) over the poles whose
@@ -434,7 +476,7 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
         const float4 d0 = ssort[k];
         const bool has1 = (k + 8) < khi;
         const float4 d1 = has1 ? ssort[k + 8] : d0;
-        const int g0n = ((int)(-d0.x)) >> 4, g1n = ((int)(-d1.x)) >> 4;
+        const int g0n = __float_as_int(d0.w) & 1023, g1n = __float_as_int(d1.w) & 1023;
         const bool far0 = abs(b0 - g0n) >= 2;
         const bool far1 = has1 && abs(b0 - g1n) >= 2;
         const float g0 = fmaf(d0.y, invs0, fmaf(d0.x, invs0, cb0));
@@ -483,9 +525,9 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
       spbar[i] += acc64;
     }
   }
-  if (fb < NB) {
+  if (fb < NB2) {
 #pragma unroll
-    for (int m = 0; m < kTKA; m++) atomicAdd(&sL[fb * kTKA + m], L64[m]);
+    for (int m = 0; m < kTKA; m++) atomicAdd(&sL2[fb * kTKA + m], L64[m]);
   }
   __syncthreads();
   // ---- spread the local coefficients of both levels to the nodes and write out
@@ -494,29 +536,48 @@ static __global__ void __launch_bounds__(kPvThreads) k_pv_nodes(const PvNodesArg
   const bool fused = a.fe_bar != nullptr;
   const int V = a.nodes + 1;
   {
-    // node i = threadIdx.x + k kPvThreads: its in-block offsets i % 64 and i % 16 do not depend on k, so the two rows of
-    // spreading weights are loaded once per thread
-    double wq1[kTKA], wq0[kTKA];
+    // node i = threadIdx.x + k kPvThreads: its in-block offsets i % 16, i % 64, i % 256 do not depend on k, so a thread needs
+    // one row of spreading weights per level; one pass per level keeps only twelve of them in registers at a time (the
+    // slots of spbar a thread touches are its own)
+    static_assert(kPvThreads % kTS2 == 0, "the level-2 offset of a thread's nodes must not depend on k");
+    const double* q2 = a.tstat + kTsQA2;
+    double wq[kTKA];
 #pragma unroll
-    for (int m = 0; m < kTKA; m++) {
-      wq1[m] = q[(threadIdx.x % kTS) * kTKA + m];
-      wq0[m] = a.tstat[kTsQA0 + (threadIdx.x % kTS0) * kTKA + m];
+    for (int m = 0; m < kTKA; m++) wq[m] = a.tstat[kTsQA0 + (threadIdx.x % kTS0) * kTKA + m];
+    for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+      if (i < 1 || i > M - 1) continue;
+      const float* l0 = sL0 + (i / kTS0) * kTKA;
+      double v = spbar[i];
+#pragma unroll
+      for (int m = 0; m < kTKA; m++) v += (double)l0[m] * wq[m];
+      spbar[i] = v;
     }
+#pragma unroll
+    for (int m = 0; m < kTKA; m++) wq[m] = q[(threadIdx.x % kTS) * kTKA + m];
+    for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
+      if (i < 1 || i > M - 1) continue;
+      const double* l1 = sL + (i / kTS) * kTKA;
+      double v = spbar[i];
+#pragma unroll
+      for (int m = 0; m < kTKA; m++) v += l1[m] * wq[m];
+      spbar[i] = v;
+    }
+#pragma unroll
+    for (int m = 0; m < kTKA; m++) wq[m] = q2[(threadIdx.x % kTS2) * kTKA + m];
     for (int i = threadIdx.x; i < a.npad; i += kPvThreads) {
       double v = 0.0;
       const int nb = i / kTS;
       if (i >= 1 && i <= M - 1) {
+        const double* l2 = sL2 + (i / kTS2) * kTKA;
         v = spbar[i];
-        const double* l1 = sL + nb * kTKA;
-        const float* l0 = sL0 + (i / kTS0) * kTKA;
 #pragma unroll
-        for (int m = 0; m < kTKA; m++) v += l1[m] * wq1[m] + (double)l0[m] * wq0[m];
+        for (int m = 0; m < kTKA; m++) v += l2[m] * wq[m];
       } else if (i == 0) {
 #pragma unroll
-        for (int m = 0; m < kTKA; m++) v += sL[m] * q[kTS * kTKA + m];
+        for (int m = 0; m < kTKA; m++) v += sL[m] * q[kTS * kTKA + m] + sL2[m] * q2[kTS2 * kTKA + m];
       } else if (i == M) {
 #pragma unroll
-        for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m];
+        for (int m = 0; m < kTKA; m++) v += sL[nb * kTKA + m] * q[(kTS + 1) * kTKA + m] + sL2[(i / kTS2) * kTKA + m] * q2[(kTS2 + 1) * kTKA + m];
       }
       if (fused) spbar[i] = v;   // each thread rewrites only the slot it has just read
       else if (a.nsplit == 1) out[i] = v;
@@ -598,7 +659,8 @@ __device__ __forceinline__ float4 pv_desc(double xi, double Ibar, double z0, dou
   const TreePole t = tree_pole(xi, z0, h, nodes - 1, npad);
   n = (int)(-t.un);
   wb0 = t.wb0;
-  return make_float4(t.un, t.ndh, (float)Ibar, __int_as_float(t.wb0));
+  // window keys packed for the node sweep: level-0 group gn (10 bits) | level-1 window start (8 bits) | level-2 window start
+  return make_float4(t.un, t.ndh, (float)Ibar, __int_as_float((n >> 4) | (t.wb0 << 10) | (t.w2 << 18)));
 }
 #endif
 

@@ -140,7 +140,9 @@ constexpr int kTsT12 = kTsE1 + kTS * kTK;
 constexpr int kTsCM0 = kTsT12 + 4 * kTK * kTK;
 //   QA0 [kTS0][kTKA]      adjoint spreading weights of the level-0 in-block offsets (interior nodes only)
 constexpr int kTsQA0 = kTsCM0 + kTK * (kTK / 2);
-constexpr int kTreeStaticDoubles = kTsQA0 + kTS0 * kTKA;
+//   QA2 [(kTS2+2)][kTKA]  adjoint spreading weights of the level-2 in-block offsets, then the rows of node 0 and node M
+constexpr int kTsQA2 = kTsQA0 + kTS0 * kTKA;
+constexpr int kTreeStaticDoubles = kTsQA2 + (kTS2 + 2) * kTKA;
 TSFF_HD double tree_static_entry(int i, int M) {
   const double c1 = 0.5 * (double)(kTS - 1), c2 = 0.5 * (double)(kTS2 - 1);
   if (i < kTsCM1) {
@@ -165,6 +167,12 @@ TSFF_HD double tree_static_entry(int i, int M) {
     double pw = 1.0;
     for (int q = 0; q < k; q++) pw *= x;
     return pw;
+  }
+  if (i >= kTsQA2) {
+    const int k = (i - kTsQA2) / kTKA, m = (i - kTsQA2) % kTKA;
+    if (k < kTS2) return tree_q(m, (double)k - c2, kTs2);
+    if (k == kTS2) return tree_q_end(m, 0.0 - c2, false, kTs2);
+    return tree_q_end(m, (double)(M % kTS2) - c2, true, kTs2);
   }
   if (i >= kTsQA0) return tree_q((i - kTsQA0) % kTKA, (double)((i - kTsQA0) / kTKA) - 0.5 * (double)(kTS0 - 1), kTs0);
   if (i >= kTsCM0) return tree_cm((i - kTsCM0) / (kTK / 2), (i - kTsCM0) % (kTK / 2), kTs0);
