@@ -8,7 +8,7 @@ from tsadar_b200.loss_function import LossFunction
 from tsadar_b200.ts_params import ThomsonParams
 from tsadar_b200.fit import adam_fit
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-N = 200
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 cfg = load_cfg("cfg_1d")
 lamb = np.linspace(400, 700, 1024)
 e_data = 0.6 * np.exp(-0.5 * ((lamb - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamb - 590) / 15.0) ** 2) + 0.01
@@ -20,8 +20,10 @@ for graphed in (False, True):
     tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
     closure = lambda p: loss_fn.calc_loss(p, batch_t)[0]
     adam_fit(closure, tp, 0.01, 5, cuda_graph=graphed)      # warm
-    tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    hist = adam_fit(closure, tp, 0.01, N, cuda_graph=graphed)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    dt = 1e30
+    for _ in range(3):      # best of three: the first graphed run of a process also pays lazy module loading
+        tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        hist = adam_fit(closure, tp, 0.01, N, cuda_graph=graphed)
+        torch.cuda.synchronize(); dt = min(dt, time.perf_counter() - t0)
     print(f"B={B} {'CUDA graph' if graphed else 'eager     '}: {dt / N * 1e3:7.3f} ms/step ({N} adam steps, loss {hist[0]:.4e} -> {hist[-1]:.4e})")
