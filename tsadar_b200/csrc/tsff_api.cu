@@ -170,7 +170,7 @@ extern "C" int tsff_pv_fwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);
-  k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
+  k_tree_static<<<kTreeStaticGrid, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
   k_pv_prep<<<(unsigned)B, kThreads, tree_prep_scratch_bytes(L.npad), st>>>(f, (int)N, h, L.npad, (unsigned char*)(w + L.D), (double*)(w + L.tstat),
                                             (double*)(w + L.D64), (double*)(w + L.pend));
   TSFF_LAUNCH_OK("k_pv_prep");
@@ -187,7 +187,7 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.pendbar, 0, (size_t)B * L.npad * 8, st));
   k_pv_desc<<<(unsigned)B, kThreads, 0, st>>>(pole, out_bar, (int)P, z0, h, L.nodes, L.npad, (float4*)(w + L.desc), (double*)(w + L.pendbar));
   TSFF_LAUNCH_OK("k_pv_desc");
-  k_tree_static<<<1, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
+  k_tree_static<<<kTreeStaticGrid, 256, 0, st>>>((int)N - 2, (double*)(w + L.tstat));
   PvNodesArgs n;
   n.desc = (float4*)(w + L.desc); n.tstat = (double*)(w + L.tstat); n.P = (int)P; n.nodes = L.nodes; n.npad = L.npad;
   n.pbar = (double*)(w + L.Dbar); n.nsplit = 1;

@@ -119,7 +119,7 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   if (cudaMalloc(&c->tstat, kTreeStaticDoubles * sizeof(double)) != cudaSuccess) {
     cudaFree(c->dev_blob); delete c; set_error("cudaMalloc failed"); return TSFF_E_NOMEM;
   }
-  k_tree_static<<<1, 256>>>(c->pv_nodes - 1, c->tstat);
+  k_tree_static<<<kTreeStaticGrid, 256>>>(c->pv_nodes - 1, c->tstat);
   if (cudaDeviceSynchronize() != cudaSuccess) {
     cudaFree(c->tstat); cudaFree(c->dev_blob); delete c; set_error("k_tree_static failed: %s", cudaGetErrorString(cudaGetLastError()));
     return TSFF_E_CUDA;

@@ -34,7 +34,27 @@ __device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t 
 
 // Static tables of the expansion (tree_static_entry): built once per context / call.
 static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) {
-  for (int i = threadIdx.x; i < kTreeStaticDoubles; i += blockDim.x) out[i] = tree_static_entry(i, M);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTreeStaticDoubles; i += gridDim.x * blockDim.x) out[i] = tree_static_entry(i, M);
+}
+constexpr int kTreeStaticGrid = (kTreeStaticDoubles + 255) / 256;   // one entry per thread (the entries are small serial loops)
+
+template <int C>
+__device__ __forceinline__ void tree_translate_fixed(const double (&m0)[kTK], double (&m)[kTK]) {
+#pragma unroll
+  for (int k = 0; k < kTK; k++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j <= k; j++) acc = fma(tree_T(C, k, j), m0[j], acc);   // folded: C, k, j are compile-time here
+    m[k] = acc;
+  }
+}
+__device__ __forceinline__ void tree_translate_child(int c, const double (&m0)[kTK], double (&m)[kTK]) {
+  switch (c) {
+    case 0: tree_translate_fixed<0>(m0, m); break;
+    case 1: tree_translate_fixed<1>(m0, m); break;
+    case 2: tree_translate_fixed<2>(m0, m); break;
+    default: tree_translate_fixed<3>(m0, m); break;
+  }
 }
 
 // Per-lineout preparation, executed by one CTA.  pget(i), 0 <= i <= M: node values p_i (FP64).
@@ -93,26 +113,21 @@ __device__ __forceinline__ void tree_prep_cta_f(PGet pget, int M, int npad, unsi
       float4* w4 = reinterpret_cast<float4*>(Wt + kTS0 * b0);
 #pragma unroll
       for (int o = 0; o < kQ; o += 4) w4[o / 4] = make_float4(wv[o], wv[o + 1], wv[o + 2], wv[o + 3]);
-      // this block's share of the level-1 moments: translation child qd -> parent (the same matrices as level 1 -> 2)
-      {
-        const double* t = sT12 + qd * kTK * kTK;
-#pragma unroll
-        for (int k = 0; k < kTK; k++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j <= k; j++) acc = fma(t[k * kTK + j], m0[j], acc);
-          m[k] = acc;
-        }
-      }
+      // this block's share of the level-1 moments: translation child qd -> parent; the 105 matrix entries of each child
+      // are compile-time constants (immediate operands: no shared-memory traffic in this hot loop)
+      tree_translate_child(qd, m0, m);
       // level-0 coefficients (interior nodes only, no end-node rows), packed, straight to the blob
-      const double* cm0 = tstat + kTsCM0;
       double A0[kTK];
 #pragma unroll
       for (int mm = 0; mm < kTK; mm++) {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < kTK / 2; j++)
-          if (2 * j <= mm) acc = fma(__ldg(cm0 + mm * (kTK / 2) + j), m0[mm - 2 * j], acc);
+          if (2 * j <= mm) {
+            constexpr double s0 = kTs0;
+            const double cmv = tree_cm(mm, j, s0);   // folded at compile time (mm, j are unrolled)
+            acc = fma(cmv, m0[mm - 2 * j], acc);
+          }
         A0[mm] = acc * (1.0 / kTs0);
       }
       float4* ab = reinterpret_cast<float4*>(blob + tb.oAB0) + b0 * (kTK / 2);

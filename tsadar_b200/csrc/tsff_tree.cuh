@@ -84,17 +84,27 @@ TSFF_HD float2 f2(float x, float y) {
   return r;
 }
 
-TSFF_HD double tree_binom(int n, int k) {
+TSFF_HD constexpr double tree_binom(int n, int k) {
   if (k < 0 || k > n) return 0.0;
   double r = 1.0;
   for (int i = 1; i <= k; i++) r = r * (double)(n - k + i) / (double)i;
   return r;
 }
 // coefficient of mu_{m-2j} in s * A_m
-TSFF_HD double tree_cm(int m, int j, double s) {
+TSFF_HD constexpr double tree_cm(int m, int j, double s) {
   double s2j = 1.0;
   for (int i = 0; i < 2 * j; i++) s2j /= s;
   return tree_binom(m, 2 * j) / ((double)(2 * j + 1) * (double)(j + 1)) * s2j;
+}
+// moment translation child c (of four) -> parent: x_parent = (x_child - D) / 4 with D = 2 c - 3, so
+//   mu_parent_k += sum_{j <= k} T(c, k, j) mu_child_j,   T = C(k, j) (-D)^(k-j) / 4^k     (exact in double)
+TSFF_HD constexpr double tree_T(int c, int k, int j) {
+  if (j > k) return 0.0;
+  const double D = 2.0 * (double)c - 3.0;
+  double v = tree_binom(k, j);
+  for (int q = 0; q < k - j; q++) v *= -D;
+  for (int q = 0; q < k; q++) v *= 0.25;
+  return v;
 }
 // q_m(e): d A_m / d p_i for an interior node at offset e = i - c  (also the spreading weight of the adjoint)
 TSFF_HD double tree_q(int m, double e, double s) {
@@ -179,12 +189,7 @@ TSFF_HD double tree_static_entry(int i, int M) {
   {
     // x2 = (x1 - D)/4 with D = (c_child - c_parent)/s1 = 2 c - 3 for child c = 0..3:  x2^k = 4^-k sum_j C(k,j) (-D)^(k-j) x1^j
     const int c = (i - kTsT12) / (kTK * kTK), k = ((i - kTsT12) / kTK) % kTK, j = (i - kTsT12) % kTK;
-    if (j > k) return 0.0;
-    const double D = 2.0 * (double)c - 3.0;
-    double v = tree_binom(k, j);
-    for (int q = 0; q < k - j; q++) v *= -D;
-    for (int q = 0; q < k; q++) v *= 0.25;
-    return v;
+    return tree_T(c, k, j);
   }
 }
 
