@@ -146,10 +146,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (the default of some images): keep stdout to the one
-        # JSON line the contract asks for
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its debug output -- including the version banner at NCCL_DEBUG=VERSION / WARN -- to STDOUT by default:
+        # send it to stderr so that stdout carries only the one JSON line the contract asks for
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K, Wm = args.lineouts, args.steps, max(args.warmup, 3)
