@@ -151,3 +151,41 @@ def test_full_size_vjp_is_linear_in_the_cotangent():
     assert float(((p12 - (p1 + 2 * p2)).abs() / ps).max()) < 1e-4
     fs = (f1.abs() + 2 * f2.abs()).amax(dim=1, keepdim=True)
     assert float(((f12 - (f1 + 2 * f2)).abs() / fs).max()) < 1e-4
+
+
+@pytest.mark.parametrize("V", [8192, 9216])   # (beyond ~11000 nodes the oracle would need ratcen's Taylor branch, ratintn.py:47-51)
+def test_large_tables(V):
+    """Maximum sizes: f tables of 8192 and 9216 nodes (the per-lineout tree blob is staged in shared memory: 14.5 B per
+    node, 200 KB limit) against the oracle, forward and table cotangent; beyond the limit the library must refuse cleanly."""
+    from oracle import torch_oracle as TO
+    W = 48
+    params, fe, vx, _ = make_lineouts(2, seed=9, nvx=V, dtype=np.float64)
+    eng = FormFactorEngine(LAM_RANGE, W, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")
+    pt, ft = torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda")
+    modl, _, saved = eng.forward(pt, ft)
+    got = modl.cpu().numpy()
+    grids = O.Grids(list(LAM_RANGE), W)
+    for b in range(2):
+        ref, _ = O.form_factor_direct(row_to_params(params[b], fe[b], vx, 1), grids, SA_SYN, 1, 0.0)
+        ref = ref[0, :, 0]
+        assert np.abs(got[b] - ref).max() / np.abs(ref).max() < 1e-5
+    rng = np.random.default_rng(3)
+    cot = rng.normal(size=(2, W)) / np.abs(got).max(axis=1, keepdims=True)
+    pb, fb = eng.backward(pt, ft, saved, modl_bar=torch.tensor(cot, device="cuda"))
+    leaves, p = TO.params_from_block(params[0], 1)
+    fet = torch.tensor(fe[0], requires_grad=True)
+    ffo = TO.form_factor_direct(p, fet, vx, grids, SA_SYN, 1, 0.0)
+    (TO.modl_from_ff(ffo, np.array([1.0])) * torch.tensor(cot[0])).sum().backward()
+    gf = fet.grad.numpy()
+    assert np.abs(fb[0].cpu().numpy() - gf).max() / np.abs(gf).max() < 1e-4
+    assert abs(pb[0, 0].item() - leaves.grad.numpy()[0]) <= 1e-4 * abs(leaves.grad.numpy()[0])
+
+
+@pytest.mark.parametrize("V", [16384, 32768])
+def test_table_too_large_is_refused(V):
+    """16384 nodes pass the context check but their tree blob (14.5 B per node) exceeds the shared-memory staging limit;
+    32768 nodes are refused when the context is created.  Either way: an error code and a message, no crash."""
+    params, fe, vx, _ = make_lineouts(1, seed=9, nvx=V, dtype=np.float64)
+    with pytest.raises(RuntimeError, match="too l"):
+        eng = FormFactorEngine(LAM_RANGE, 16, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")
+        eng.forward(torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda"))
