@@ -3,7 +3,7 @@
   1d       table mode, W=5120, A=10, V=320->1024-node xi1 table, B lineouts, EPW+IAW windows, forward + VJP
   arts-1d  table mode, W=2048, A=241, one image: formfactor + weights GEMM + ATS stage, forward + VJP
   arts-2d  2V mode,   W=1024, A=241, V=128 (246 784 poles x 16 384 bicubic points), forward and VJP"""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from tsadar_b200.engine import FormFactorEngine

@@ -1,9 +1,9 @@
 """Quick device timing of the synthetic sweep (scratch tool used while developing; bench.py is the contract)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from tsadar_b200.engine import FormFactorEngine, microbench
-from tsadar_b200.synthetic import make_lineouts, SA_SYN, LAM_RANGE, W_SYN, V_SYN
+from tsadar_b200.synthetic import make_lineouts, SA_SYN, LAM_RANGE, W_SYN
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 params, fe, vx, _ = make_lineouts(B)

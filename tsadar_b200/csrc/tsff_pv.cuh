@@ -35,7 +35,6 @@ TSFF_HD float lg2_approx(float x) {
 }
 
 constexpr int kNearHalf = 3;   // nodes with |i - n_p| <= kNearHalf are handled exactly in FP64
-constexpr int kMidHalf = 8;    // up to this distance the W series runs to x^11 (6 terms), beyond it to x^5 (3 terms)
 
 #if defined(__CUDA_ARCH__)
 #define TSFF_WARP_ANY(p) __any_sync(0xffffffffu, (p))
