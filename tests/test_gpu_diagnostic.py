@@ -120,3 +120,80 @@ def test_loss_and_gradients_full_chain():
         ref = leaves[k].grad.numpy()
         got = g.cpu().numpy()
         assert np.all(np.abs(got - ref) <= 1e-4 * np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max() + 1e-12)), (k, got, ref)
+
+
+def test_ion_and_electron_loss_two_species():
+    """The IAW branch end to end (rows a7-a10): two ion species, ion + electron spectra loaded, fit_IAW on, against the NumPy
+    oracle (ThryI, ThryE, total loss = ion_loss_scale * i_error + e_error) and the loss gradient against central differences
+    of the same CUDA loss (the ion window is 1.5 nm wide: every feature is sharp, a good test of the adjoint)."""
+    import copy
+    from tsadar_b200.loss_function import LossFunction
+    from tsadar_b200.ts_params import ThomsonParams
+    from tsadar_b200.fit import ravel_leaves, unravel_into, value_and_grad
+    cfg = load_cfg("cfg_1d")
+    cfg["other"]["points_per_pixel"] = 1
+    cfg["other"]["npts"] = 1024
+    cfg["parameters"]["electron"]["fe"]["nvx"] = 64
+    ex = cfg["other"]["extraoptions"]
+    ex["load_ion_spec"] = True
+    ex["fit_IAW"] = True
+    cfg["data"]["ion_loss_scale"] = 0.7
+    par = cfg["parameters"]
+    par["ion-1"]["fract"]["val"] = 0.6
+    par["ion-2"] = copy.deepcopy(par["ion-1"])
+    par["ion-2"]["A"]["val"], par["ion-2"]["Z"]["val"], par["ion-2"]["fract"]["val"] = 1.0, 1.0, 0.4
+    par["ion-2"]["Ti"]["val"] = 0.35
+    par["ion-1"]["Ti"]["active"] = True
+    par["general"]["amp3"]["active"] = True
+    B = 2
+    rng = np.random.default_rng(7)
+    lamI = np.linspace(cfg["other"]["lamrangI"][0], cfg["other"]["lamrangI"][1], 1024)
+    lamE = np.linspace(400, 700, 1024)
+    e_data = 0.6 * np.exp(-0.5 * ((lamE - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamE - 590) / 15.0) ** 2) + 0.01
+    i_data = np.exp(-0.5 * ((lamI - 526.2) / 0.08) ** 2) + 0.8 * np.exp(-0.5 * ((lamI - 526.8) / 0.08) ** 2) + 0.02
+    batch = dict(e_data=np.stack([e_data, 1.1 * e_data]), i_data=np.stack([i_data, 0.9 * i_data]), e_amps=np.array([1.0, 1.1]),
+                 i_amps=np.array([1.0, 0.9]), noise_e=rng.normal(size=(B, 1024)) * 1e-3, noise_i=rng.normal(size=(B, 1024)) * 1e-3)
+    loss_fn = LossFunction(cfg, SA_P9, batch)
+    tp = ThomsonParams(par, num_params=B, batch=True, activate=True)
+    with torch.no_grad():
+        tp.leaves[("electron", "Te")].value[1] += 0.25
+        tp.leaves[("ion-1", "Ti")].value[1] -= 0.3
+    loss, ThryE, ThryI = loss_fn.calc_loss(tp, batch)
+    # ---- oracle values
+    phys = tp()
+    plist = []
+    for b in range(B):
+        phys = {k: {kk: (vv.detach() if isinstance(vv, torch.Tensor) else vv) for kk, vv in v.items()} for k, v in phys.items()}
+        p = {"electron": dict(Te=float(phys["electron"]["Te"][b]), ne=float(phys["electron"]["ne"][b]),
+                              fe=phys["electron"]["fe"][b].detach().cpu().numpy(), v=tp.vx),
+             "general": {k: float(v[b]) for k, v in phys["general"].items()}}
+        for ion in tp.ions:
+            p[ion] = {k: float(v[b]) for k, v in phys[ion].items()}
+        plist.append(p)
+    i_norm, e_norm = float(np.amax(batch["i_data"])), float(np.amax(batch["e_data"]))
+    ref_loss, refE, refI = O.loss_1d(plist, cfg, SA_P9, batch, i_norm=i_norm, e_norm=e_norm)
+    gI, gE = ThryI.detach().cpu().numpy(), ThryE.detach().cpu().numpy()
+    assert np.abs(gI - refI).max() / np.abs(refI).max() < 1e-5
+    assert np.abs(gE - refE).max() / np.abs(refE).max() < 1e-5
+    assert abs(float(loss) - ref_loss) <= 1e-6 * abs(ref_loss), (float(loss), ref_loss)
+    # ---- gradient: FP32-sweep path vs the FP64 validation path of the same kernels, and the latter vs central differences
+    # of its own loss (differences of the FP32 path would drown in its 1e-7 rounding noise for the small d/dm)
+    closure32 = lambda t: loss_fn.calc_loss(t, batch)[0]
+    _, g32 = value_and_grad(closure32, tp)
+    loss_fn64 = LossFunction(cfg, SA_P9, batch, pv_precision="fp64")
+    closure = lambda t: loss_fn64.calc_loss(t, batch)[0]
+    _, g = value_and_grad(closure, tp)
+    leaves = tp.parameters()
+    x0 = ravel_leaves(leaves)
+    assert g.size == x0.size and np.all(np.isfinite(g))
+    assert np.all(np.abs(g32 - g) <= 1e-4 * np.maximum(np.abs(g), 1e-4 * np.abs(g).max()))
+    for k in range(0, x0.size, 3):
+        h = 1e-5
+        vals = []
+        for dx in (-h, h):
+            x = x0.copy(); x[k] += dx
+            unravel_into(leaves, x)
+            vals.append(float(closure(tp).detach()))
+        unravel_into(leaves, x0)
+        fd = (vals[1] - vals[0]) / (2 * h)
+        assert abs(g[k] - fd) <= 2e-4 * max(abs(fd), 1e-3 * np.abs(g).max()), (k, g[k], fd)
