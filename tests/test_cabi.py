@@ -47,3 +47,17 @@ def test_hostsim_math_selfcheck(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "HOSTSIM OK" in out.stdout, out.stdout
+
+
+def test_jax_binding_is_import_guarded():
+    """The jax.ffi binding (tsadar_b200/jax_binding) is shipped for the reference side; where JAX is absent it must fail
+    with an ImportError that says why, and nothing else in the package may import it."""
+    import importlib, importlib.util
+    if importlib.util.find_spec("jax") is not None:
+        pytest.skip("JAX present: the binding is exercised on the reference side")
+    with pytest.raises(ImportError, match="needs jax"):
+        importlib.import_module("tsadar_b200.jax_binding.tsff_jax")
+    import tsadar_b200  # noqa: F401  (the package itself imports without JAX)
+    src = open(os.path.join(ROOT, "tsadar_b200", "jax_binding", "tsff_xla_ffi.cc")).read()
+    for sym in ("TsffFfFwd", "TsffFfBwd", "TsffFfFullFwd", "TsffFfFullBwd", "TsffPvFwd", "TsffLossFwdBwd"):
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({sym}," in src

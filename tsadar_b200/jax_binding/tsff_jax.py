@@ -1,0 +1,94 @@
+"""jax.ffi + jax.custom_vjp wrappers over libtsff: the module a TSADAR maintainer drops into
+`tsadar/core/physics/` so that `FormFactor`, `ThomsonScatteringDiagnostic`, `LossFunction`, the yaml decks and the
+optax / SciPy optimisers stay untouched.
+
+JAX is not installable in the image this repository is developed in, so this module is NOT imported by the package or by
+any test that runs here; importing it without JAX raises a clear ImportError.  It is a thin translation of the C ABI
+(include/tsff.h): contexts are created through ctypes (tsadar_b200/_ffi.py, same struct as the torch harness), the
+handlers of tsff_xla_ffi.cc are registered as FFI targets, and each forward/backward pair is tied by jax.custom_vjp."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+try:
+    import jax
+    import jax.numpy as jnp
+    import numpy as np
+except ImportError as e:  # pragma: no cover - JAX is absent where this repository's tests run
+    raise ImportError("tsadar_b200.jax_binding.tsff_jax needs jax/jaxlib (and libtsff_xla.so built from "
+                      "tsff_xla_ffi.cc against jax.ffi.include_dir())") from e
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_XLA_LIB = ctypes.CDLL(os.environ.get("TSFF_XLA_LIB", os.path.join(_HERE, "..", "_lib", "libtsff_xla.so")))
+for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffPvFwd", "TsffLossFwdBwd"):
+    jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_XLA_LIB, _name)), platform="CUDA")
+
+
+def make_form_factor(ctx: int, B: int, W: int, V: int, NP: int, saved_bytes: int, ws_bytes: int):
+    """-> f(params [B, NP] f64, fe [B, V]) = modl [B, W] f64, differentiable in both arguments.
+    `ctx` = the integer value of a tsff_ctx* made with tsff_ctx_create (ctypes); saved_bytes / ws_bytes from
+    tsff_ff_saved_bytes / tsff_ff_workspace_bytes for this batch size.  The lineout axis is the kernel's own batch axis, so
+    the reference's vmap over lineouts (thomson_diagnostic.py:35) is dropped."""
+    cid = np.int64(ctx)
+
+    @jax.custom_vjp
+    def ff(params, fe):
+        return _fwd(params, fe)[0]
+
+    def _fwd(params, fe):
+        modl, saved, _ = jax.ffi.ffi_call(
+            "TsffFfFwd",
+            (jax.ShapeDtypeStruct((B, W), jnp.float64), jax.ShapeDtypeStruct((saved_bytes,), jnp.uint8),
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, ctx=cid)
+        return modl, (params, fe, saved)
+
+    def _bwd(res, modl_bar):
+        params, fe, saved = res
+        pbar, fbar, _ = jax.ffi.ffi_call(
+            "TsffFfBwd",
+            (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct((B, V), fe.dtype),
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, saved, modl_bar, ctx=cid)
+        return pbar, fbar
+
+    ff.defvjp(_fwd, _bwd)
+    return ff
+
+
+def make_form_factor_full(ctx: int, B: int, G: int, W: int, A: int, fe_shape, NP: int, saved_bytes: int, ws_bytes: int):
+    """The same returning the full formfactor [B, G, W, A] (ARTS; TSFF_MODE_2V takes fe [B, V, V] float64)."""
+    cid = np.int64(ctx)
+
+    @jax.custom_vjp
+    def ff(params, fe):
+        return _fwd(params, fe)[0]
+
+    def _fwd(params, fe):
+        out, saved, _ = jax.ffi.ffi_call(
+            "TsffFfFullFwd",
+            (jax.ShapeDtypeStruct((B, G, W, A), jnp.float64), jax.ShapeDtypeStruct((saved_bytes,), jnp.uint8),
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, ctx=cid)
+        return out, (params, fe, saved)
+
+    def _bwd(res, ff_bar):
+        params, fe, saved = res
+        pbar, fbar, _ = jax.ffi.ffi_call(
+            "TsffFfFullBwd",
+            (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct(tuple(fe_shape), fe.dtype),
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, saved, ff_bar, ctx=cid)
+        return pbar, fbar
+
+    ff.defvjp(_fwd, _bwd)
+    return ff
+
+
+def pack_params(params):
+    """ThomsonParams.__call__ dict (ts_params.py:599-603) -> block [B, NP] in the column order of include/tsff.h."""
+    ions = sorted([k for k in params if k.startswith("ion-")], key=lambda s: int(s.split("-")[1]))
+    e, g = params["electron"], params["general"]
+    cols = [e["Te"], e["ne"], g["lam"], g["Va"], g["ud"], g["ne_gradient"], g["Te_gradient"], g["amp1"], g["amp2"], g["amp3"]]
+    for k in ions:
+        cols += [params[k]["A"], params[k]["Z"], params[k]["Ti"], params[k]["fract"]]
+    cols = [jnp.atleast_1d(jnp.asarray(c, dtype=jnp.float64)).reshape(-1) for c in cols]
+    B = max(c.shape[0] for c in cols)
+    return jnp.stack([jnp.broadcast_to(c, (B,)) for c in cols], axis=1)
