@@ -36,6 +36,30 @@ FLOP_PER_PAIR_FWD = 12                   # the forward pole sweep computes I and
 FLOP_PER_PAIR_BWD = 7
 
 
+# stdout must carry exactly ONE JSON line (the driver parses it).  Libraries write there too (NCCL prints its version
+# banner on stdout when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole run
+# and the JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def _clock_sampler(path, stop):
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -115,7 +139,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "lineouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -130,6 +154,7 @@ def main():
     ap.add_argument("--cpu-baseline-lineouts", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)
         return run_reference(args)
@@ -146,9 +171,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its debug output -- including the version banner at NCCL_DEBUG=VERSION / WARN -- to STDOUT by default:
-        # send it to stderr so that stdout carries only the one JSON line the contract asks for
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K, Wm = args.lineouts, args.steps, max(args.warmup, 3)
@@ -343,7 +365,7 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": nb / dt, "unit": "lineouts/s", "cores": cores, "kind": "port",
                                     "sample": f"{nb} lineouts of the same workload, torch-f64 forward + autograd VJP (oracle/torch_oracle.py)"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
