@@ -113,7 +113,9 @@ int tsff_ff_fwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, 
 
 /* VJP of tsff_ff_fwd (replaces XLA's reverse-mode of the same graph, loss_function.py:107-108):
  *   modl_bar [B][W] or NULL, ff_bar [B][G][W][A] or NULL  (cotangents; at least one non-NULL)
- *   params_bar [B][NP] float64 (overwritten; amp1..3 and A entries are 0),  fe_bar [B][V] (fe_dtype, overwritten) */
+ *   params_bar [B][NP] float64 (overwritten; amp1..3 and A entries are 0),  fe_bar [B][V] (fe_dtype, overwritten)
+ *   TSFF_MODE_2V only: params_bar may be NULL when no kinematic parameter is trainable (the reference's arts-2d deck fits
+ *   the table alone); the d/dbeta gather and the kinematics reverse are then skipped. */
 int tsff_ff_bwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
                 const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
                 void* stream);

@@ -178,3 +178,29 @@ def test_arts2v_diagnostic_with_spherical_harmonics_matches_oracle():
     (ThryE * ThryE).sum().backward()
     g = [t.grad for t in ts_params.parameters()]
     assert len(g) == 3 and all(x is not None and torch.isfinite(x).all() for x in g) and all(float(x.abs()) > 0 for x in g)
+
+
+def test_calc_in_2D_vjp_table_only():
+    """Only the table trainable (the reference's arts-2d deck: Te, ne inactive): tsff_ff_bwd with params_bar = NULL skips
+    the d/dbeta gather and the kinematics reverse; fe_bar must be bit-identical to the full adjoint's."""
+    from tsadar_b200.engine import FormFactorEngine, form_factor_full
+    V, W = 48, 12
+    vx = _grid(V)
+    X, Y = np.meshgrid(vx, vx, indexing="ij")
+    DF = np.exp(-0.5 * ((X - 0.2) ** 2 / 1.1 + Y**2 / 0.9) ** 1.1)
+    DF = DF / DF.sum() / (vx[1] - vx[0]) ** 2
+    sa = np.array([50.0, 95.0, 130.0])
+    row = np.array([[0.8, 0.3, 526.5, 0.3, 0.2, 0.0, 0.0, 1, 1, 1, 40.0, 8.0, 0.2, 1.0]])
+    eng = FormFactorEngine((450.0, 600.0), W, 0.0, sa, np.ones(3), 1, 1, vx, mode="2v", ud_ang=20.0, va_ang=70.0)
+    pt, ft = torch.tensor(row, device="cuda"), torch.tensor(DF[None], device="cuda")
+    _, ff, saved = eng.forward(pt, ft, want_ff=True)
+    cot = torch.tensor(np.random.default_rng(1).normal(size=tuple(ff.shape)) / float(ff.abs().max()), device="cuda")
+    pb, fb = eng.backward(pt, ft, saved, ff_bar=cot)
+    fb = fb.clone()
+    pb2, fb2 = eng.backward(pt, ft, saved, ff_bar=cot, want_params=False)
+    assert pb2 is None and pb is not None
+    assert float((fb2 - fb).abs().max()) <= 1e-13 * float(fb.abs().max())      # same taps, atomics in another order
+    # through autograd: a params tensor that does not require grad selects the short path
+    ftg = ft.clone().requires_grad_(True)
+    (form_factor_full(eng, pt, ftg) * cot).sum().backward()
+    assert float((ftg.grad - fb).abs().max()) <= 1e-13 * float(fb.abs().max())

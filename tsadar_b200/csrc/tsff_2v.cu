@@ -227,6 +227,9 @@ __device__ __forceinline__ void atomic_add_shared(double* addr, double v) { atom
 //   column b and its lanes take points four nodes apart so that their 4x4 stencils barely collide) and gathers
 //   d f1[b] / d beta from f; finally the kinematics reverse (|xi|, beta -> parameters).
 // dynamic smem: f [V][V+1] | fbar [V][V+1] | 3 x [NG][V] | red [NG][16] | scal [NG][16]
+// WANT_PARAMS = false: no kinematic parameter is trainable (only the table is, as in the reference's arts-2d deck):
+// d f1 / d beta, the 2-vector kinematics reverse and the lineout-scalar cotangents are skipped.
+template <bool WANT_PARAMS>
 __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long long b_lineout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int V = a.V, VP = V + 1;
@@ -389,8 +392,13 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
           const double xq = cb * va - sb * vb, yq = sb * va + cb * vb;
           int ix, iy;
           double wx[4], wy[4], dwx[4], dwy[4];
-          hermite4d(xq, a.v0, idv, V, ix, wx, dwx);
-          hermite4d(yq, a.v0, idv, V, iy, wy, dwy);
+          if (WANT_PARAMS) {
+            hermite4d(xq, a.v0, idv, V, ix, wx, dwx);
+            hermite4d(yq, a.v0, idv, V, iy, wy, dwy);
+          } else {
+            hermite4(xq, a.v0, idv, V, ix, wx);
+            hermite4(yq, a.v0, idv, V, iy, wy);
+          }
           const float* fb = sf + ix * VP + iy;
           double* ob = sfb + ix * VP + iy;
           double sx = 0.0, sy = 0.0;
@@ -399,17 +407,21 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
             double r0 = 0.0, r1 = 0.0;
 #pragma unroll
             for (int n = 0; n < 4; n++) {
-              const double fv = (double)fb[m * VP + n];
-              r0 = fma(wy[n], fv, r0);
-              r1 = fma(dwy[n], fv, r1);
+              if (WANT_PARAMS) {
+                const double fv = (double)fb[m * VP + n];
+                r0 = fma(wy[n], fv, r0);
+                r1 = fma(dwy[n], fv, r1);
+              }
               const double wv = wcol * wx[m] * wy[n];
               if (wv != 0.0) atomic_add_shared(ob + m * VP + n, wv);
             }
-            sx = fma(dwx[m], r0, sx);
-            sy = fma(wx[m], r1, sy);
+            if (WANT_PARAMS) {
+              sx = fma(dwx[m], r0, sx);
+              sy = fma(wx[m], r1, sy);
+            }
           }
           // d xq / d beta = -yq, d yq / d beta = xq;  d/dxq = idv d/dt
-          bbar += wcol * (-yq * sx + xq * sy) * idv;
+          if (WANT_PARAMS) bbar += wcol * (-yq * sx + xq * sy) * idv;
         }
       }
     }
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
     if (active_grp && lane == 0) sred[grp * 16 + wg] = bbar;
     __syncthreads();
     // ---- kinematics reverse for (|xi|, beta) and the rest of kb
-    if (valid && tb == 0) {
+    if (WANT_PARAMS && valid && tb == 0) {
       double beta_bar = 0.0;
       for (int w = 0; w < NWG; w++) beta_bar += sred[grp * 16 + w];
       const LG& L = sL[g];
@@ -534,15 +546,19 @@ int ff2v_bwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, con
   TSFF_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)B * c->G * kLGDoubles * 8, st));
   const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
   const size_t smem = (((size_t)V * (V + 1) * 4 + 15) / 16) * 16 + ((size_t)V * (V + 1) + (size_t)NG * V * 3 + (size_t)NG * 32) * 8;
-  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));  // 225 KB at V = 128
+  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));
+  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));  // 225 KB at V = 128
   const long long nbatch = ((long long)a.P + NG - 1) / NG;
   const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
   for (int64_t b = 0; b < B; b++) {
-    k_ff2v_bwd<<<grid, kThreads2V, smem, st>>>(a, (long long)b);
+    if (params_bar) k_ff2v_bwd<true><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
+    else k_ff2v_bwd<false><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
     TSFF_LAUNCH_OK("k_ff2v_bwd");
   }
-  k_ff2v_params_bar<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(a, params_bar, B);
-  TSFF_LAUNCH_OK("k_ff2v_params_bar");
+  if (params_bar) {
+    k_ff2v_params_bar<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(a, params_bar, B);
+    TSFF_LAUNCH_OK("k_ff2v_params_bar");
+  }
   return TSFF_OK;
 }
 }  // namespace tsff

@@ -64,7 +64,7 @@ extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const v
   int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
   if (rc) return rc;
   if (!modl_bar && !ff_bar) { set_error("no cotangent given"); return TSFF_E_INVALID; }
-  if (!params_bar || !fe_bar) { set_error("null output"); return TSFF_E_INVALID; }
+  if (!fe_bar || (!params_bar && c->mode != TSFF_MODE_2V)) { set_error("null output"); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->mode == TSFF_MODE_2V) {
     if (fe_dtype != TSFF_F64 || !ff_bar || modl_bar) { set_error("2V mode: fe float64, cotangent of the formfactor only"); return TSFF_E_INVALID; }

@@ -131,13 +131,15 @@ class FormFactorEngine:
             saved.data_ptr(), ws.data_ptr(), st))
         return modl, ff, saved
 
-    def backward(self, params, fe, saved, modl_bar=None, ff_bar=None, params_bar=None, fe_bar=None):
+    def backward(self, params, fe, saved, modl_bar=None, ff_bar=None, params_bar=None, fe_bar=None, want_params=True):
+        """want_params=False (2V mode only): skip params_bar (returned as None) when no kinematic parameter is trainable."""
         B = params.shape[0]
         if modl_bar is not None:
             _require_cuda(modl_bar, torch.float64, "modl_bar")
         if ff_bar is not None:
             _require_cuda(ff_bar, torch.float64, "ff_bar")
-        if params_bar is None:
+        skip_params = (not want_params) and self.mode == "2v"
+        if params_bar is None and not skip_params:
             params_bar = torch.empty((B, self.NP), dtype=torch.float64, device=self.device)
         if fe_bar is None:
             fe_bar = torch.empty_like(fe)
@@ -146,7 +148,8 @@ class FormFactorEngine:
         _ffi.check(_ffi.lib().tsff_ff_bwd(
             self._ctx, B, params.data_ptr(), fe.data_ptr(), _ffi.TSFF_F32 if fe.dtype == torch.float32 else _ffi.TSFF_F64,
             saved.data_ptr(), modl_bar.data_ptr() if modl_bar is not None else None,
-            ff_bar.data_ptr() if ff_bar is not None else None, params_bar.data_ptr(), fe_bar.data_ptr(), ws.data_ptr(), st))
+            ff_bar.data_ptr() if ff_bar is not None else None, None if skip_params else params_bar.data_ptr(), fe_bar.data_ptr(),
+            ws.data_ptr(), st))
         return params_bar, fe_bar
 
     def set_profile_events(self, fwd=None, bwd=None):
@@ -187,7 +190,7 @@ class _FFFunction(torch.autograd.Function):
         params, fe, saved = ctx.saved_tensors
         out_bar = out_bar.contiguous()
         if ctx.want_ff:
-            pb, fb = ctx.engine.backward(params, fe, saved, ff_bar=out_bar)
+            pb, fb = ctx.engine.backward(params, fe, saved, ff_bar=out_bar, want_params=ctx.needs_input_grad[1])
         else:
             pb, fb = ctx.engine.backward(params, fe, saved, modl_bar=out_bar)
         return None, pb, fb, None
