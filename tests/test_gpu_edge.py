@@ -189,3 +189,38 @@ def test_table_too_large_is_refused(V):
     with pytest.raises(RuntimeError, match="too l"):
         eng = FormFactorEngine(LAM_RANGE, 16, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")
         eng.forward(torch.tensor(params, device="cuda"), torch.tensor(fe, device="cuda"))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_shapes_match_oracle(seed):
+    """Seeded fuzz over the shape space: wavelengths, table length, angles, gradient points, ion species and mode drawn at
+    random (odd sizes on purpose), every plasma parameter drawn from the range of the reference's random-fit test; spectrum
+    vs the NumPy oracle at the north-star tolerance."""
+    rng = np.random.default_rng(1000 + seed)
+    W, V = int(rng.integers(17, 260)), int(rng.integers(40, 700))
+    A, G, nI = int(rng.integers(1, 6)), int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    mode = ["direct", "table"][seed % 2]
+    lam = (float(rng.uniform(380, 480)), float(rng.uniform(600, 720)))
+    sa = np.sort(rng.uniform(35.0, 140.0, A))
+    wts = rng.uniform(0.05, 1.0, A)
+    B = 2
+    params, fe, vx, _ = make_lineouts(B, seed=seed, nvx=V, dtype=np.float64)
+    rows = np.zeros((B, 10 + 4 * nI))
+    rows[:, :10] = params[:, :10]
+    rows[:, 3] = rng.uniform(-3, 3, B)            # Va
+    rows[:, 4] = rng.uniform(-1, 1, B)            # ud
+    rows[:, 5] = rng.uniform(0, 8, B) * (G > 1)   # ne gradient [%]
+    rows[:, 6] = rng.uniform(0, 8, B) * (G > 1)
+    fr = rng.uniform(0.2, 1.0, nI)
+    for i in range(nI):
+        rows[:, 10 + 4 * i: 14 + 4 * i] = [float(rng.choice([1.0, 12.0, 40.0])), float(rng.uniform(1, 10)), float(rng.uniform(0.05, 0.6)), fr[i] / fr.sum()]
+    eng = FormFactorEngine(lam, W, 0.0, sa, wts, G, nI, vx, mode=mode)
+    modl, _, _ = eng.forward(torch.tensor(rows, device="cuda"), torch.tensor(fe, device="cuda"))
+    got = modl.cpu().numpy()
+    grids = O.Grids(list(lam), W)
+    fn = O.form_factor_direct if mode == "direct" else O.form_factor_1v
+    for b in range(B):
+        ff, _ = fn(row_to_params(rows[b], fe[b], vx, nI), grids, sa, G, 0.0)
+        ref = (ff.mean(axis=0) * wts).sum(axis=1)
+        err = np.abs(got[b] - ref).max() / np.abs(ref).max()
+        assert err < 1e-5, (seed, mode, W, V, A, G, nI, b, err)
