@@ -61,21 +61,51 @@ AtsLayout ats_layout(const AtsGeom& g) {
 
 // 'same' convolution with equal-length taps (jnp.convolve(x, v, "same")): y[n] = sum_t v[t] x[n + c - t], c = (N-1)/2.
 // ADJ: the transpose  xbar[m] = sum_t v[t] ybar[m - c + t].   Axis 0: the conv index is the row (stride W), axis 1: column.
+// Register-tiled: a thread computes kR = 8 consecutive outputs along the convolution axis; their eight-sample window lives
+// in registers and rotates by one per tap (fully unrolled: no moves), so one load of a sample and one (broadcast) load of a
+// tap feed eight DFMAs.  Every output is still summed in tap order t0 .. t1, out-of-range samples contribute 0.
+// Axis 0: adjacent threads take adjacent columns (coalesced row loads); axis 1: adjacent threads take adjacent 8-column
+// blocks of one row (the lines stay in L1 across the next taps).
+constexpr int kR = 8;
 template <bool AXIS0, bool ADJ>
 __global__ void __launch_bounds__(kThreads) k_ats_conv(const double* __restrict__ x, double* __restrict__ y, int NA, int W,
                                                       const double* __restrict__ taps, int t0, int t1) {
+  const int N = AXIS0 ? NA : W;                      // length of the convolution axis
+  const int nblk = (N + kR - 1) / kR;                // output blocks along it
+  const int other = AXIS0 ? W : NA;                  // the other axis
   const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (idx >= (long long)NA * W) return;
-  const int i = (int)(idx / W), j = (int)(idx % W);
-  const int N = AXIS0 ? NA : W, n = AXIS0 ? i : j;
+  if (idx >= (long long)nblk * other) return;
+  // axis 0: idx = blk * W + j (threads of a warp: consecutive j);  axis 1: idx = i * nblk + blk
+  const int blk = AXIS0 ? (int)(idx / other) : (int)(idx % nblk);
+  const int o = AXIS0 ? (int)(idx % other) : (int)(idx / nblk);
+  const int n0 = blk * kR;
   const int c = (N - 1) / 2;
-  double acc = 0.0;
-  for (int t = t0; t <= t1; t++) {
-    const int m = ADJ ? n - c + t : n + c - t;
-    if (m < 0 || m >= N) continue;
-    acc = fma(taps[t], AXIS0 ? x[(long long)m * W + j] : x[(long long)i * W + m], acc);
+  const long long stride = AXIS0 ? W : 1, base = AXIS0 ? o : (long long)o * W;
+  auto ld = [&](int m) { return (m >= 0 && m < N) ? x[base + (long long)m * stride] : 0.0; };
+  // fwd: sample index of output n, tap t: n + c - t (decreasing in t);  adj: n - c + t (increasing)
+  const int i0 = ADJ ? n0 - c + t0 : n0 + c - t0;
+  double acc[kR], v[kR];
+#pragma unroll
+  for (int r = 0; r < kR; r++) { acc[r] = 0.0; v[r] = ld(i0 + r); }
+  const int nt = t1 - t0 + 1;
+  for (int ib = 0; ib < nt; ib += kR) {
+#pragma unroll
+    for (int u = 0; u < kR; u++) {
+      const double gv = (ib + u < nt) ? taps[t0 + ib + u] : 0.0;
+      if (ADJ) {
+#pragma unroll
+        for (int r = 0; r < kR; r++) acc[r] = fma(gv, v[(r + u) & (kR - 1)], acc[r]);
+        v[u] = ld(i0 + ib + u + kR);                                   // enters as r = 7 of the next tap
+      } else {
+#pragma unroll
+        for (int r = 0; r < kR; r++) acc[r] = fma(gv, v[(r - u) & (kR - 1)], acc[r]);
+        v[(kR - 1 - u) & (kR - 1)] = ld(i0 - ib - u - 1);              // enters as r = 0 of the next tap
+      }
+    }
   }
-  y[idx] = acc;
+#pragma unroll
+  for (int r = 0; r < kR; r++)
+    if (n0 + r < N) y[base + (long long)(n0 + r) * stride] = acc[r];
 }
 
 // per row: max / first argmax of two arrays (jnp.amax semantics)
@@ -281,8 +311,10 @@ extern "C" int tsff_ats_fwd(const tsff_ats_cfg* cfg, const double* modl, const d
   RowStat* rs = (RowStat*)(sv + L.s_stats);
   UnitStat* us = (UnitStat*)(sv + L.s_stats + (size_t)g.NA * sizeof(RowStat));
   const unsigned nb = (unsigned)(((long long)g.NA * g.W + kThreads - 1) / kThreads);
-  k_ats_conv<true, false><<<nb, kThreads, 0, st>>>(modl, Y1, g.NA, g.W, cfg->taps_ang, g.ta0, g.ta1);
-  k_ats_conv<false, false><<<nb, kThreads, 0, st>>>(Y1, Y2, g.NA, g.W, cfg->taps_lam, g.tl0, g.tl1);
+  const unsigned nb0 = (unsigned)(((long long)((g.NA + kR - 1) / kR) * g.W + kThreads - 1) / kThreads);   // axis-0 conv: 8 rows per thread
+  const unsigned nb1 = (unsigned)(((long long)((g.W + kR - 1) / kR) * g.NA + kThreads - 1) / kThreads);   // axis-1 conv: 8 columns per thread
+  k_ats_conv<true, false><<<nb0, kThreads, 0, st>>>(modl, Y1, g.NA, g.W, cfg->taps_ang, g.ta0, g.ta1);
+  k_ats_conv<false, false><<<nb1, kThreads, 0, st>>>(Y1, Y2, g.NA, g.W, cfg->taps_lam, g.tl0, g.tl1);
   k_ats_rowstat<<<(unsigned)g.NA, kThreads, 0, st>>>(modl, Y2, g.W, rs);
   k_ats_reduce<<<(unsigned)(((long long)g.nrows * g.nl + kThreads - 1) / kThreads), kThreads, 0, st>>>(g, Y2, rs, R);
   AtsCall c;
@@ -319,8 +351,10 @@ extern "C" int tsff_ats_bwd(const tsff_ats_cfg* cfg, const double* params, const
   k_ats_reduce_bwd<<<nb, kThreads, 0, st>>>(g, Rbar, rs, Zbar);
   double* xmaxbar = (double*)(w + L.w_xmax);
   k_ats_rescale_bwd<<<(unsigned)g.NA, kThreads, 0, st>>>(Y2, Zbar, g.W, rs, xmaxbar);
-  k_ats_conv<false, true><<<nb, kThreads, 0, st>>>(Zbar, Y1bar, g.NA, g.W, cfg->taps_lam, g.tl0, g.tl1);
-  k_ats_conv<true, true><<<nb, kThreads, 0, st>>>(Y1bar, modl_bar, g.NA, g.W, cfg->taps_ang, g.ta0, g.ta1);
+  const unsigned nb0 = (unsigned)(((long long)((g.NA + kR - 1) / kR) * g.W + kThreads - 1) / kThreads);
+  const unsigned nb1 = (unsigned)(((long long)((g.W + kR - 1) / kR) * g.NA + kThreads - 1) / kThreads);
+  k_ats_conv<false, true><<<nb1, kThreads, 0, st>>>(Zbar, Y1bar, g.NA, g.W, cfg->taps_lam, g.tl0, g.tl1);
+  k_ats_conv<true, true><<<nb0, kThreads, 0, st>>>(Y1bar, modl_bar, g.NA, g.W, cfg->taps_ang, g.ta0, g.ta1);
   k_ats_add_xmax<<<(unsigned)((g.NA + kThreads - 1) / kThreads), kThreads, 0, st>>>(modl_bar, g.W, rs, xmaxbar, g.NA);
   TSFF_LAUNCH_OK("tsff_ats_bwd");
   return TSFF_OK;
