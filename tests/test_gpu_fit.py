@@ -37,27 +37,30 @@ def _setup():
     from tsadar_b200.ts_params import ThomsonParams
     cfg = load_cfg("cfg_1d")
     rng = np.random.default_rng(42)
+    from tsadar_b200.fit import batch_to_device
     ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=SA_P9)
     cfg["parameters"] = _perturb_params_(rng, cfg["parameters"])
     gt = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=1, batch=True, activate=True)
+    dummy = batch_to_device(dummy_batch_1d())          # device-resident, so that the step can also be graph-captured
     with torch.no_grad():
-        ThryE_gt, _, _, _ = ts_diag(gt, dummy_batch_1d())
+        ThryE_gt, _, _, _ = ts_diag(gt, dummy)
     ThryE_gt = ThryE_gt.detach()
     cfg["parameters"] = _perturb_params_(rng, cfg["parameters"])
     fit = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=1, batch=True, activate=True)
 
     def loss_fn(tp):
-        ThryE, _, _, _ = ts_diag(tp, dummy_batch_1d())
+        ThryE, _, _, _ = ts_diag(tp, dummy)
         return torch.mean(torch.square(ThryE - ThryE_gt))
 
     return gt, fit, loss_fn
 
 
-def test_1d_inverse_lbfgsb_recovers_parameters():
+@pytest.mark.parametrize("graphed", [False, True])
+def test_1d_inverse_lbfgsb_recovers_parameters(graphed):
     from tsadar_b200.fit import scipy_fit
     gt, fit, loss_fn = _setup()
     l0 = float(loss_fn(fit).detach())
-    res = scipy_fit(loss_fn, fit, method="L-BFGS-B")
+    res = scipy_fit(loss_fn, fit, method="L-BFGS-B", cuda_graph=graphed)
     assert res["fun"] < 1e-4 * l0, (res["fun"], l0)
     g, l = _flat(gt.get_unnormed_params()), _flat(fit.get_unnormed_params())
     assert ("electron", "m") in g and ("electron", "Te") in g

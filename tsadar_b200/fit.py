@@ -15,6 +15,13 @@ import numpy as np
 import torch
 
 
+def batch_to_device(batch, device=None):
+    """The data batch (`e_data`, `i_data`, `e_amps`, `i_amps`, `noise_e`, `noise_i`; loops.py:135-142) as float64 CUDA
+    tensors.  Needed for the graphed drivers: a CUDA graph cannot capture copies from pageable host arrays."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v), dtype=torch.float64)).to(dev) for k, v in batch.items()}
+
+
 def ravel_leaves(leaves):
     """Flat float64 host vector of the active leaves (jax.flatten_util.ravel_pytree in the reference)."""
     return np.concatenate([t.detach().reshape(-1).cpu().numpy() for t in leaves]) if leaves else np.zeros(0)
@@ -40,11 +47,70 @@ def value_and_grad(loss_closure, ts_params):
     return float(loss.detach()), g
 
 
-def scipy_fit(loss_closure, ts_params, method="L-BFGS-B", options=None, bounds=None):
+class GraphedValueAndGrad:
+    """loss and gradient as ONE captured CUDA graph: a call copies the flat parameter vector into the leaves (one H2D),
+    replays the graph (transforms -> form factor -> IRF -> loss -> hand-written adjoints) and reads loss + flat gradient
+    back (one D2H).  For the SciPy drivers, whose every function evaluation is otherwise a few dozen small launches.
+    The closure must work on device-resident data only (batch_to_device): host arrays cannot be copied inside a capture."""
+
+    def __init__(self, loss_closure, ts_params):
+        self.leaves = ts_params.parameters()
+        dev = self.leaves[0].device
+        n = sum(t.numel() for t in self.leaves)
+        self.x_dev = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.out_dev = torch.zeros(n + 1, dtype=torch.float64, device=dev)          # [loss, flat gradient]
+        self.x_pin = torch.zeros(n, dtype=torch.float64).pin_memory()
+        self.out_pin = torch.zeros(n + 1, dtype=torch.float64).pin_memory()
+
+        def body():
+            o = 0
+            with torch.no_grad():
+                for t in self.leaves:
+                    t.copy_(self.x_dev[o:o + t.numel()].reshape(t.shape))
+                    o += t.numel()
+            loss = loss_closure(ts_params)
+            g = torch.autograd.grad(loss, self.leaves, allow_unused=True)
+            with torch.no_grad():
+                self.out_dev[0] = loss.detach()
+                o = 1
+                for t, gt in zip(self.leaves, g):
+                    self.out_dev[o:o + t.numel()] = 0.0 if gt is None else gt.reshape(-1)
+                    o += t.numel()
+
+        self.x_dev.copy_(torch.as_tensor(ravel_leaves(self.leaves)))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def __call__(self, x):
+        self.x_pin.copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)))
+        self.x_dev.copy_(self.x_pin, non_blocking=True)
+        self.graph.replay()
+        self.out_pin.copy_(self.out_dev, non_blocking=True)
+        torch.cuda.current_stream(self.x_dev.device).synchronize()
+        out = self.out_pin.numpy()
+        return float(out[0]), out[1:].copy()
+
+
+def scipy_fit(loss_closure, ts_params, method="L-BFGS-B", options=None, bounds=None, cuda_graph=False):
     """scipy.optimize.minimize(jac=True) over the active leaves of `ts_params` (updated in place).  Returns the
-    OptimizeResult.  NaN losses propagate to SciPy unchanged, as in the reference."""
+    OptimizeResult.  NaN losses propagate to SciPy unchanged, as in the reference.  cuda_graph=True evaluates loss and
+    gradient through GraphedValueAndGrad."""
     from scipy.optimize import minimize
     leaves = ts_params.parameters()
+    if cuda_graph:
+        x0 = ravel_leaves(leaves)
+        fun = GraphedValueAndGrad(loss_closure, ts_params)
+        res = minimize(fun, x0, method=method, jac=True, bounds=bounds, options=options or {})
+        unravel_into(leaves, res["x"])
+        return res
 
     def fun(x):
         unravel_into(leaves, x)

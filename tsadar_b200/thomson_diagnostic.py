@@ -54,9 +54,11 @@ class ThomsonScatteringDiagnostic:
     @staticmethod
     def _noise(n, B, dev, nbins=1024):
         t = n if isinstance(n, torch.Tensor) else torch.as_tensor(n, dtype=torch.float64)
-        t = t.to(device=dev, dtype=torch.float64)
-        if t.numel() == 1 and float(t.reshape(-1)[0]) == 0.0:
+        # "no noise" (the scalar 0 of the reference's dummy batches) is recognised on the host only: reading a device scalar
+        # would synchronise, which a CUDA-graph capture of the fit step does not allow (a device-resident zero is simply added)
+        if not t.is_cuda and t.numel() == 1 and float(t.reshape(-1)[0]) == 0.0:
             return None
+        t = t.to(device=dev, dtype=torch.float64)
         return t.expand(B, nbins).contiguous() if t.dim() < 2 or t.shape != (B, nbins) else t.contiguous()
 
     def _call_angular(self, physical_params, batch, dev):
