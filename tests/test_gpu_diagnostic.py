@@ -197,3 +197,26 @@ def test_ion_and_electron_loss_two_species():
         unravel_into(leaves, x0)
         fd = (vals[1] - vals[0]) / (2 * h)
         assert abs(g[k] - fd) <= 2e-4 * max(abs(fd), 1e-3 * np.abs(g).max()), (k, g[k], fd)
+
+
+def test_unbatched_angular_spectype_equals_the_batched_path():
+    """spectype "angular" (not "angular_full"): the reference runs the same FitModel + electron IRF without the vmap over
+    lineouts (thomson_diagnostic.py:37-38, 67-73); one parameter set, spectra without a batch axis."""
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_1d")
+    ref_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=SA_P9)
+    tp = ThomsonParams(cfg["parameters"], num_params=1, batch=True, activate=True)
+    ref, _, lam_ref, _ = ref_diag(tp, dummy_batch_1d())
+    import copy
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["other"]["extraoptions"]["spectype"] = "angular"
+    diag = ThomsonScatteringDiagnostic(cfg2, scattering_angles=SA_P9)
+    tp1 = ThomsonParams(cfg2["parameters"], num_params=1, batch=False, activate=True)
+    got, _, lam, _ = diag(tp1, dummy_batch_1d())
+    assert got.shape == (1024,)
+    assert torch.equal(got, ref[0])
+    np.testing.assert_array_equal(np.asarray(lam), np.asarray(lam_ref))
+    with pytest.raises(NotImplementedError):
+        cfg2["other"]["extraoptions"]["spectype"] = "streaked"
+        ThomsonScatteringDiagnostic(cfg2, scattering_angles=SA_P9)

@@ -23,9 +23,12 @@ class ThomsonScatteringDiagnostic:
         self.cfg = cfg
         self.scattering_angles = scattering_angles
         st = cfg["other"]["extraoptions"]["spectype"]
-        self.angular = "angular" in st
-        if not ("temporal" in st or "imaging" in st or "1d" in st or st == "angular_full"):
-            raise NotImplementedError(f"spectype {st}: not built (DESIGN.md: scope)")
+        self.angular = st == "angular_full"
+        # any other "angular*" spectype: the reference runs the same model and IRF as the temporal ones, just without the vmap
+        # over lineouts (thomson_diagnostic.py:37-38, 67-73): one parameter set in, un-batched spectra out
+        self.unbatched = "angular" in st and not self.angular
+        if not ("temporal" in st or "imaging" in st or "1d" in st or "angular" in st):
+            raise NotImplementedError(f"Unknown spectype: {st}")
         self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group)
         self._ats = None
 
@@ -49,6 +52,9 @@ class ThomsonScatteringDiagnostic:
             B = modlE.shape[0]
             noise = self._noise(batch["noise_e"], B, dev)
             lamAxisE, ThryE = irf.add_electron_IRF(self.cfg, oth["lamrangE"], oth["npts"], modlE, _dev_vec(batch["e_amps"], B, dev), block, noise)
+        if self.unbatched:
+            ThryE = ThryE[0] if isinstance(ThryE, torch.Tensor) else ThryE
+            ThryI = ThryI[0] if isinstance(ThryI, torch.Tensor) else ThryI
         return ThryE, ThryI, lamAxisE, lamAxisI
 
     @staticmethod
