@@ -220,3 +220,29 @@ def test_unbatched_angular_spectype_equals_the_batched_path():
     with pytest.raises(NotImplementedError):
         cfg2["other"]["extraoptions"]["spectype"] = "streaked"
         ThomsonScatteringDiagnostic(cfg2, scattering_angles=SA_P9)
+
+
+def test_post_loss_per_lineout_matches_oracle():
+    """LossFunction.post_loss (loss_function.py:375-384): uncertainty = the theory itself, nanmean over the wavelength axis,
+    one loss per lineout -- against np_oracle.calc_ei_error with the same arguments."""
+    from tsadar_b200.loss_function import LossFunction
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_1d")
+    cfg["other"]["points_per_pixel"] = 1
+    cfg["other"]["npts"] = 1024
+    cfg["parameters"]["electron"]["fe"]["nvx"] = 64
+    B = 3
+    lamb = np.linspace(400, 700, 1024)
+    e_data = 0.6 * np.exp(-0.5 * ((lamb - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamb - 590) / 15.0) ** 2) + 0.01
+    batch = dict(e_data=np.stack([e_data, 1.2 * e_data, 0.7 * e_data]), i_data=np.ones((B, 1024)), e_amps=np.array([1.0, 1.2, 0.7]),
+                 i_amps=np.ones(B), noise_e=np.zeros((B, 1024)), noise_i=np.zeros((B, 1024)))
+    lf = LossFunction(cfg, SA_P9, batch)
+    tp = ThomsonParams(cfg["parameters"], num_params=B, batch=True, activate=True)
+    total, sqdev, ThryE, ThryI, phys = lf.post_loss(tp, batch)
+    assert total.shape == (B,) and sqdev["ele"].shape == (B, 1024)
+    thE = ThryE.cpu().numpy()
+    _, _, lamE, _ = lf.ts_diag(tp, batch)
+    nanmean1 = lambda a: np.nanmean(a, axis=1)
+    _, e_ref = O.calc_ei_error(cfg, batch, 0.0, np.zeros(1), thE, np.asarray(lamE), [0.0, thE], reduce_func=nanmean1)
+    np.testing.assert_allclose(total.cpu().numpy(), e_ref, rtol=1e-12)
+    assert float(lf.loss(tp, batch)) > 0

@@ -86,6 +86,62 @@ class LossFunction:
         loss.backward()
         return (loss.detach(), [ThryE.detach() if isinstance(ThryE, torch.Tensor) else ThryE, ts_params]), [t.grad for t in leaves]
 
+    def loss(self, ts_params, batch):
+        """Value only (LossFunction.loss, loss_function.py:344-362)."""
+        with torch.no_grad():
+            return self.calc_loss(ts_params, batch)[0]
+
+    def post_loss(self, ts_params, batch):
+        """Output wrapper for postprocessing (loss_function.py:375-384): calc_loss with denom = [] (per-pixel uncertainty =
+        the theory itself, :325-326) and reduce_func = nanmean over the wavelength axis, i.e. ONE loss per lineout.
+        -> (total_loss [B], sqdev {"ele": [B, n], "ion": [B, n]}, ThryE, ThryI, physical params).  No gradient: plain
+        elementwise torch on the kernels' spectra (run once after a fit, postprocess.py:139-183)."""
+        with torch.no_grad():
+            ThryE, ThryI, lamE, lamI = self.ts_diag(ts_params, batch)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            fr, ex = self.cfg["data"]["fit_rng"], self.cfg["other"]["extraoptions"]
+            method = self.cfg["optimizer"]["loss_method"]
+
+            def err(d, t):
+                if method == "l1":
+                    return torch.abs(d - t) / t
+                if method == "l2":
+                    return torch.square(d - t) / t
+                if method == "log-cosh":
+                    return torch.log(torch.cosh(d - t))        # no uncertainty in this functional (loss_function.py:414-415)
+                if method == "poisson":
+                    return t - d * torch.log(t)
+                raise NotImplementedError(method)
+
+            def masked_mean(e, m):
+                m = torch.as_tensor(m, device=dev)
+                return (e * m).sum(dim=1) / m.sum().clamp(min=1), e * m
+
+            B = (ThryE if isinstance(ThryE, torch.Tensor) else ThryI).shape[0]
+            e_error = torch.zeros(B, dtype=torch.float64, device=dev)
+            i_error = torch.zeros(B, dtype=torch.float64, device=dev)
+            sqdev = {"ele": 0, "ion": 0}
+            if isinstance(ThryI, torch.Tensor) and ex["fit_IAW"]:
+                lam = np.asarray(lamI)
+                d = torch.as_tensor(batch["i_data"], dtype=torch.float64).to(dev).expand_as(ThryI)
+                m = ((lam > fr["iaw_min"]) & (lam < fr["iaw_cf_min"])) | ((lam > fr["iaw_cf_max"]) & (lam < fr["iaw_max"]))
+                v, sq = masked_mean(err(d, ThryI), m)
+                i_error, sqdev["ion"] = i_error + v, sq
+            if isinstance(ThryE, torch.Tensor):
+                lam = np.asarray(lamE)
+                d = torch.as_tensor(batch["e_data"], dtype=torch.float64).to(dev).expand_as(ThryE)
+                e = err(d, ThryE)
+                if ex["fit_EPWb"]:
+                    v, sq = masked_mean(e, (lam > fr["blue_min"]) & (lam < fr["blue_max"]))
+                    e_error, sqdev["ele"] = e_error + v, sqdev["ele"] + sq
+                if ex["fit_EPWr"]:
+                    v, sq = masked_mean(e, (lam > fr["red_min"]) & (lam < fr["red_max"]))
+                    e_error, sqdev["ele"] = e_error + v, sqdev["ele"] + sq
+                    if ex["fit_EPWb"]:
+                        e_error = e_error * 0.5
+            total = self.cfg["data"]["ion_loss_scale"] * i_error + e_error
+            return total, sqdev, ThryE, ThryI, (ts_params() if callable(ts_params) else ts_params)
+
     # ---- second-order path (loss_function.py:110, 170-188; postprocess.py:134, 167-179, 188-251) -- SURVEY.md 8f row N2
     def loss_for_hess(self, ts_params, batch):
         """_loss_for_hess_fn_ (loss_function.py:173-188): errors weighted by 1/(|data| + 1e-10), SUMMED over the fit windows.
