@@ -129,3 +129,22 @@ def test_thomson_params_oracle_2v_dispatch():
     cfg = _cfg_2v()
     p = P.thomson_params(copy.deepcopy(cfg), activate=False)
     assert p["electron"]["fe"].shape == (48, 48) and p["electron"]["v"].shape == (48,)
+
+
+def test_get_unnormed_and_fitted_params():
+    """ts_params.py:565-581, 605-645: the reported parameters exclude the f table; fitted = the active ones (+ m when the
+    distribution is active, + flm with the assembled table for spherical harmonics)."""
+    cfg = load_cfg("cfg_1d")["parameters"]
+    tp = ThomsonParams(cfg, num_params=2, batch=True, activate=True, device="cpu")
+    un = tp.get_unnormed_params()
+    assert set(un["electron"]) == {"Te", "ne", "m"} and "fe" not in un["electron"]
+    fitted, n = tp.get_fitted_params(cfg)
+    active = [(k, k2) for k in cfg for k2 in cfg[k] if k2 != "fe" and cfg[k][k2].get("active")]
+    assert n == len(active) + 1                                   # + m
+    assert set(fitted["electron"]) == {"Te", "ne", "m"} and set(fitted["general"]) == {"amp1", "amp2", "lam"}
+    assert fitted["ion-1"] == {}
+    cfg2 = _cfg_2v("mora-yahi")
+    tp2 = ThomsonParams(cfg2, num_params=1, batch=False, device="cpu")
+    fitted2, n2 = tp2.get_fitted_params(cfg2)
+    assert n2 == 0 and set(fitted2["electron"]) == {"flm"}
+    assert fitted2["electron"]["flm"]["fvxvy"].shape == (48, 48) and set(fitted2["electron"]["flm"]) >= {0, 1, "fvxvy", "v"}

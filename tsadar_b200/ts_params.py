@@ -145,13 +145,40 @@ class ThomsonParams:
         return out
 
     def get_unnormed_params(self):
+        """Physical values of the parameters WITHOUT the f table and its grid (ts_params.py:168-200, 565-581): Te, ne and
+        what the distribution itself reports -- m (DLM), f (arbitrary tables), flm (spherical harmonics); a Maxwellian
+        reports nothing."""
         p = self()
+        fe = p["electron"].pop("fe")
+        p["electron"].pop("v")
         if self.fe_dim == 1 and self.fe_type == "dlm":
             p["electron"]["m"] = self.leaves[("electron", "m")].physical()
-        elif self.fe_dim == 1 and self.fe_type == "arbitrary":
-            p["electron"]["f"] = p["electron"]["fe"]
+        elif self.fe_type == "arbitrary":
+            p["electron"]["f"] = fe
         elif isinstance(self.dist, SphericalHarmonics):
             p["electron"].update(self.dist.get_unnormed_params())
-        elif isinstance(self.dist, Arbitrary2V):
-            p["electron"]["f"] = p["electron"]["fe"]
         return p
+
+    def get_fitted_params(self, param_cfg):
+        """(fitted_params, num_params): the active entries of get_unnormed_params (ts_params.py:605-645); m counts when the
+        distribution is active, f / flm are always reported (flm with the assembled table and its grid)."""
+        param_dict = self.get_unnormed_params()
+        num_params = 0
+        fitted = {}
+        for k in param_dict:
+            fitted[k] = {}
+            for k2 in param_dict[k]:
+                if k2 == "m":
+                    if param_cfg[k]["fe"]["active"]:
+                        fitted[k][k2] = param_dict[k][k2]
+                        num_params += 1
+                elif k2 in ("f", "fe", "flm"):
+                    fitted[k][k2] = param_dict[k][k2]
+                    if k2 == "flm":
+                        out = self()
+                        fitted[k][k2]["fvxvy"] = out["electron"]["fe"]
+                        fitted[k][k2]["v"] = out["electron"]["v"]
+                elif param_cfg[k][k2]["active"]:
+                    fitted[k][k2] = param_dict[k][k2]
+                    num_params += 1
+        return fitted, num_params
