@@ -246,3 +246,27 @@ def test_post_loss_per_lineout_matches_oracle():
     _, e_ref = O.calc_ei_error(cfg, batch, 0.0, np.zeros(1), thE, np.asarray(lamE), [0.0, thE], reduce_func=nanmean1)
     np.testing.assert_allclose(total.cpu().numpy(), e_ref, rtol=1e-12)
     assert float(lf.loss(tp, batch)) > 0
+
+
+def test_detailed_spectrum_breakdown():
+    """FitModel.detailed_spectrum (generate_spectra.py:222-330): same angle-integrated spectrum as electron_spectrum, plus the
+    raw formfactor it was integrated from (scaled by 1e-9 inside the IAW filter window, as the reference does)."""
+    from tsadar_b200.generate_spectra import FitModel
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_1d")
+    fm = FitModel(cfg, SA_P9)
+    tp = ThomsonParams(cfg["parameters"], num_params=2, batch=True, activate=True)
+    with torch.no_grad():
+        phys = tp()
+        lamE, modlE, _ = fm.electron_spectrum(phys)
+        modlE_d, modlI_d, ThryE, ThryI, lamE_d, lamI_d = fm.detailed_spectrum(phys)
+    np.testing.assert_array_equal(lamE, lamE_d)
+    assert ThryE.shape == (2, 1, cfg["other"]["npts"], 10) and modlI_d == 0 and ThryI == 0
+    assert float((modlE_d - modlE).abs().max()) <= 1e-12 * float(modlE.abs().max())
+    f = cfg["other"]["iawfilter"]
+    inside = (lamE > f[3] - f[2] / 2) & (lamE < f[3] + f[2] / 2)
+    w0 = float(SA_P9["weights"][0])
+    recon = (ThryE.mean(dim=1) * w0).sum(dim=-1).cpu().numpy()
+    m = modlE.cpu().numpy()
+    np.testing.assert_allclose(recon[:, ~inside], m[:, ~inside], rtol=1e-12)
+    np.testing.assert_allclose(recon[:, inside] * 1e9 * 10.0 ** (-f[1]), m[:, inside], rtol=1e-12)

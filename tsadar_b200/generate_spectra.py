@@ -96,6 +96,43 @@ class FitModel:
             return lamE, modlE, block
         return [], 0, None
 
+    # ---- breakdown used by the reference's postprocessing plots (generate_spectra.py:222-330): the angle-integrated spectra
+    # together with the raw formfactor [.., G, W, A] they were integrated from
+    def ion_spectrum_detailed(self, all_params):
+        if not self.config["other"]["extraoptions"]["load_ion_spec"]:
+            return np.zeros(1), 0, 0
+        ff = self.ion_form_factor
+        ThryI, _ = ff(all_params) if self.dim == 1 else ff.calc_in_2D(all_params)
+        lamI = np.linspace(*self.config["other"]["lamrangI"], self.config["other"]["npts"])
+        w = torch.tensor(self._w, dtype=torch.float64, device=ThryI.device)
+        modlI = (ThryI.mean(dim=-3) * w).sum(dim=-1)                                # :259-260
+        return lamI, modlI, ThryI
+
+    def electron_spectrum_detailed(self, all_params):
+        if not self.config["other"]["extraoptions"]["load_ele_spec"]:
+            return [], 0, 0
+        ff = self.electron_form_factor
+        ThryE, _ = ff(all_params) if self.dim == 1 else ff.calc_in_2D(all_params)
+        dev = ThryE.device
+        lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
+        mean = ThryE.mean(dim=-3)                                                   # over gradient points  :296
+        if self.angular_full:
+            wm = torch.tensor(self._wmat, dtype=torch.float64, device=dev)
+            modlE = torch.matmul(wm, mean.transpose(-1, -2))                        # :297-298
+        else:
+            modlE = (mean * torch.tensor(self._w, dtype=torch.float64, device=dev)).sum(dim=-1)   # :300
+        if self._jmulE is not None:                                                 # :311-318
+            jm = torch.tensor(self._jmulE, dtype=torch.float64, device=dev)
+            modlE = modlE * jm
+            inside = torch.tensor(self._jmulE != 1.0, device=dev)
+            ThryE = torch.where(inside[:, None], ThryE * 1e-9, ThryE)               # the reference scales the raw one by 1e-9
+        return lamE, modlE, ThryE
+
+    def detailed_spectrum(self, all_params):
+        lamAxisI, modlI, ThryI = self.ion_spectrum_detailed(all_params)
+        lamAxisE, modlE, ThryE = self.electron_spectrum_detailed(all_params)
+        return modlE, modlI, ThryE, ThryI, lamAxisE, lamAxisI
+
     def __call__(self, all_params):
         lamAxisI, modlI, _ = self.ion_spectrum(all_params)
         lamAxisE, modlE, _ = self.electron_spectrum(all_params)
