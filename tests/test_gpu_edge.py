@@ -224,3 +224,36 @@ def test_random_shapes_match_oracle(seed):
         ref = (ff.mean(axis=0) * wts).sum(axis=1)
         err = np.abs(got[b] - ref).max() / np.abs(ref).max()
         assert err < 1e-5, (seed, mode, W, V, A, G, nI, b, err)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_shapes_vjp_matches_autograd(seed):
+    """The same fuzz for the hand-written adjoint (direct mode): params_bar and fe_bar vs torch autograd of the oracle."""
+    from tests.test_gpu_direct import _torch_grads
+    rng = np.random.default_rng(2000 + seed)
+    W, V = int(rng.integers(17, 200)), int(rng.integers(40, 900))
+    A, G, nI = int(rng.integers(1, 4)), int(rng.integers(1, 3)), int(rng.integers(1, 3))
+    lam = (float(rng.uniform(380, 480)), float(rng.uniform(600, 720)))
+    sa = np.sort(rng.uniform(35.0, 140.0, A))
+    wts = rng.uniform(0.05, 1.0, A)
+    B = 2
+    params, fe, vx, _ = make_lineouts(B, seed=seed, nvx=V, dtype=np.float64)
+    rows = np.zeros((B, 10 + 4 * nI))
+    rows[:, :10] = params[:, :10]
+    rows[:, 3], rows[:, 4] = rng.uniform(-3, 3, B), rng.uniform(-1, 1, B)
+    rows[:, 5], rows[:, 6] = rng.uniform(0, 8, B) * (G > 1), rng.uniform(0, 8, B) * (G > 1)
+    fr = rng.uniform(0.2, 1.0, nI)
+    for i in range(nI):
+        rows[:, 10 + 4 * i: 14 + 4 * i] = [float(rng.choice([1.0, 12.0, 40.0])), float(rng.uniform(1, 10)), float(rng.uniform(0.05, 0.6)), fr[i] / fr.sum()]
+    eng = FormFactorEngine(lam, W, 0.0, sa, wts, G, nI, vx, mode="direct")
+    pt, ft = torch.tensor(rows, device="cuda"), torch.tensor(fe, device="cuda")
+    modl, _, saved = eng.forward(pt, ft)
+    cot = rng.normal(size=(B, W)) / np.abs(modl.cpu().numpy()).max(axis=1, keepdims=True)
+    pb, fb = eng.backward(pt, ft, saved, modl_bar=torch.tensor(cot, device="cuda"))
+    gp, gf = _torch_grads(rows, fe, vx, O.Grids(list(lam), W), sa, wts, G, nI, cot)
+    pb, fb = pb.cpu().numpy(), fb.cpu().numpy()
+    cols = [0, 1, 2, 3, 4] + ([5, 6] if G > 1 else []) + [c for i in range(nI) for c in (11 + 4 * i, 12 + 4 * i, 13 + 4 * i)]
+    for b in range(B):
+        assert np.abs(fb[b] - gf[b]).max() / np.abs(gf[b]).max() < 1e-4, (seed, b)
+        for k in cols:
+            assert abs(pb[b, k] - gp[b, k]) <= 1e-4 * max(abs(gp[b, k]), 1e-6 * np.abs(gp[b]).max()), (seed, b, k, pb[b, k], gp[b, k])
