@@ -26,4 +26,6 @@ print(f"fwd {ms:.1f} ms")
 cot2 = torch.randn(1, 1, W, 241, dtype=torch.float64, device=dev)
 _, ff2, saved2 = eng2.forward(pr, fe2, want_ff=True)
 ms = timeit(lambda: eng2.backward(pr, fe2, saved2, ff_bar=cot2))
-print(f"stride {os.environ.get('TSFF_2V_STRIDE')} bwd {ms:.1f} ms")
+print(f"bwd {ms:.1f} ms")
+ms = timeit(lambda: eng2.backward(pr, fe2, saved2, ff_bar=cot2, want_params=False))
+print(f"bwd table-only {ms:.1f} ms")

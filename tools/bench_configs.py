@@ -76,4 +76,6 @@ cot2 = torch.randn(1, 1, 1024, 241, dtype=torch.float64, device=dev)
 _, ff2, saved2 = eng2.forward(pr, fe2, want_ff=True)
 ms = timeit(lambda: eng2.backward(pr, fe2, saved2, ff_bar=cot2), n=2, warm=1)
 out.append(f"arts-2d  calc_in_2D VJP (rotate/project scatter + d/dbeta): {ms:8.1f} ms")
+ms = timeit(lambda: eng2.backward(pr, fe2, saved2, ff_bar=cot2, want_params=False), n=2, warm=1)
+out.append(f"arts-2d  calc_in_2D VJP, table cotangent only (the reference's arts-2d deck: only f is trainable): {ms:8.1f} ms")
 print("\n".join(out))

@@ -378,16 +378,21 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
       sB[grp * V + k] = fb;
     }
     __syncthreads();
-    // ---- rotate/project adjoint: warp wg of the group owns columns b = wg, wg + NWG, ...; lanes take a = 4 lane + c
+    // ---- rotate/project adjoint: warp wg of the group owns lines o = wg, wg + NWG, ... of the mesh (columns b, or rows a),
+    //      lanes take the points 4 lane + c along the line
     double bbar = 0.0;
     if (valid) {
-      for (int b = wg; b < V; b += NWG) {
-        const double wcol = sB[grp * V + b] * a.dv;
-        if (wcol == 0.0) continue;
-        const double vb = a.v0 + (double)b * a.dv;
+      // lanes step 4 nodes along a (address step 4 (cb VP + sb), i.e. 4 (cb + sb) banks since VP = 1 mod 16) or along b
+      // (4 (cb - sb)): take the direction with the larger bank step, the other one piles the lanes onto a few banks
+      const bool along_b = fabs(cb - sb) > fabs(cb + sb);
+      for (int o = wg; o < V; o += NWG) {
         for (int c = 0; c < 4; c++) {
-          const int aa = 4 * lane + c;
-          if (aa >= V) break;
+          const int in = 4 * lane + c;
+          if (in >= V) break;
+          const int aa = along_b ? o : in, b = along_b ? in : o;
+          const double wcol = sB[grp * V + b] * a.dv;
+          if (wcol == 0.0) continue;
+          const double vb = a.v0 + (double)b * a.dv;
           const double va = a.v0 + (double)aa * a.dv;
           const double xq = cb * va - sb * vb, yq = sb * va + cb * vb;
           int ix, iy;
