@@ -15,6 +15,8 @@ def timeit(fn, n=2, warm=1):
 p = np.zeros((1, 14)); p[:, 0], p[:, 1], p[:, 2] = 0.6, 0.25, 526.5; p[:, 7:10] = 1.0; p[:, 10:14] = [40.0, 8.0, 0.2, 1.0]
 pr = torch.tensor(p, device=dev)
 sa = np.arange(19, 139.5, 0.5)
+if len(sys.argv) > 2 and sys.argv[2] == 'mirror':
+    sa = -sa            # beta around 225 deg instead of 135 deg: the other diagonal of the table
 V = 128; vx = vgrid(V)
 X, Y = np.meshgrid(vx, vx, indexing="ij")
 DF = np.exp(-0.5 * (X**2 + Y**2)) / (2 * np.pi)

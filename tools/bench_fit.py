@@ -31,10 +31,12 @@ for graphed in (False, True):
 # ---- the reference's default optimiser: L-BFGS-B through SciPy, eager vs graphed function evaluations
 from tsadar_b200.fit import scipy_fit
 for graphed in (False, True):
-    tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
     closure = lambda p: loss_fn.calc_loss(p, batch_t)[0]
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = scipy_fit(closure, tp, method="L-BFGS-B", options={"maxiter": 60}, cuda_graph=graphed)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    dt = 1e30
+    for _ in range(3):      # best of three: the first graphed fit of a process also pays the pinned-memory allocator start-up
+        tp = ThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        res = scipy_fit(closure, tp, method="L-BFGS-B", options={"maxiter": 60}, cuda_graph=graphed)
+        torch.cuda.synchronize(); dt = min(dt, time.perf_counter() - t0)
     print(f"B={B} L-BFGS-B {'CUDA graph' if graphed else 'eager     '}: {dt * 1e3:8.1f} ms for {res['nfev']} evaluations "
           f"({dt / res['nfev'] * 1e3:.3f} ms each, capture included), loss {res['fun']:.4e}")

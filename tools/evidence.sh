@@ -1,6 +1,6 @@
 set -x
-mkdir -p gpurun_out/r01i
-O=gpurun_out/r01i
+mkdir -p gpurun_out/r01j
+O=gpurun_out/r01j
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
 python bench.py > $O/bench.json 2> $O/bench.err; tail -c 600 $O/bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; cat $O/bench_ref.json | cut -c1-300
