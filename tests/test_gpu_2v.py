@@ -24,7 +24,11 @@ def _grid(V):
 
 @pytest.mark.parametrize("V,W,sa,ud,Va,ud_ang,va_ang,G", [(32, 24, [40.0, 75.0, 120.0], 0.0, 0.0, 0.0, 0.0, 1),
                                                            (48, 16, [60.0, 100.0], 0.4, -0.8, 30.0, 110.0, 2),
-                                                           (128, 5, [60.0, 130.0], 0.2, 0.3, 200.0, 45.0, 1)])   # arts-2d table size
+                                                           (128, 5, [60.0, 130.0], 0.2, 0.3, 200.0, 45.0, 1),    # arts-2d table size
+                                                           # mirrored detector: beta near 225 deg, where the forward kernel
+                                                           # staggers the threads' walk over a (bank conflicts) -- both signs
+                                                           (64, 12, [-35.0, -90.0, -150.0], 0.0, 0.0, 0.0, 0.0, 1),
+                                                           (64, 12, [-20.0, 170.0, 210.0, 300.0], 0.3, 0.5, 75.0, 290.0, 1)])
 def test_calc_in_2D_matches_oracle(V, W, sa, ud, Va, ud_ang, va_ang, G):
     from tsadar_b200.form_factor import FormFactor
     vx = _grid(V)
