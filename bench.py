@@ -174,6 +174,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K, Wm = args.lineouts, args.steps, max(args.warmup, 3)
+    # several ranks on one node: keep each rank's pinned staging buffers on its GPU's own NUMA node (the e2e leg moves
+    # ~270 MB per step per GPU from host memory).  Not at N=1, where the cpu_baseline leg wants every host core.
+    numa_cpus = None
+    if world > 1:
+        from tsadar_b200.parallel import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)
 
     # ---- inputs (pinned host copies for the e2e leg, resident device copies for the kernel leg)
     params_h, fe_h, vx, _ = make_lineouts(B, seed=42 + rank)
@@ -334,7 +340,8 @@ def main():
                        "cache": f"working set {int((fe_d.numel()*4*2 + saved.numel() + B*W_SYN*8*3)/2**20)} MiB per step > 126 MiB L2"},
             "e2e": {"value": e2e_val, "unit": "lineouts/s", "h2d_bytes_per_step": int(params_pin.numel() * 8 + fe_pin.numel() * 4),
                     "d2h_bytes_per_step": int(pbar_pin.numel() * 8 + 8 * NCH), "ms_per_step": ms_e2e / K,
-                    "pipeline": f"{NCH} chunks alternating on 2 streams (H2D of a chunk overlaps the kernels of the previous one)"},
+                    "pipeline": f"{NCH} chunks alternating on 2 streams (H2D of a chunk overlaps the kernels of the previous one)",
+                    "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {

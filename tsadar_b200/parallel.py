@@ -109,3 +109,30 @@ class WShard:
             raise ValueError(f"rank {self.rank} of {self.world} owns no wavelength of {npts}: use fewer ranks")
         self.j1e = min(self.j1 + (1 if halo else 0), self.npts)
         self.keep = self.j1 - self.j0
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict the calling process to the CPUs NVML reports as local to this GPU (nvmlDeviceSetCpuAffinity), so that the
+    pinned staging buffers it allocates afterwards are first-touched on the GPU's own NUMA node and the H2D copies of the
+    ranks of a node do not cross the socket interconnect.  One process per GPU, call it before allocating pinned memory.
+    Returns the number of CPUs in the new affinity mask, or None when NVML or the topology information is unavailable
+    (the process is then left as it was)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(props.uuid))
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
