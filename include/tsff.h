@@ -120,6 +120,15 @@ int tsff_ff_bwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, 
                 const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
                 void* stream);
 
+/* ---- B2: electron susceptibility pieces of the 2V path ---------------------------------------------------------- */
+/* replaces FormFactor.calc_all_chi_vals(vx, DF, beta, xie_mag, klde_mag) -> (fe_vphi, chiEI, chiERrat)
+ * (form_factor.py:390-447; per pole calc_chi_vals :349-388 with rotate :300-324) for a TSFF_MODE_2V context:
+ *   fe [V][V] float64 (the table DF on vx x vx),  beta / xie_mag / klde_mag [P] float64 (any [G,W,A] shape, flattened)
+ *   chi_out [3][P] float64: fe_vphi | chiEI | chiERrat.  Forward only: the reference differentiates this stage through
+ *   calc_in_2D, whose adjoint is tsff_ff_bwd. */
+int tsff_chi2v_fwd(tsff_ctx* ctx, const double* fe, const double* beta, const double* xie_mag, const double* klde_mag,
+                   int64_t P, double* chi_out, void* stream);
+
 /* ---- B1: principal-value integral -------------------------------------------------------------------- */
 /* replaces vmap(ratintn.ratintn)(f, z[None,:] - pole[:,None], z) (ratintn.py:4-23; form_factor.py:266-268,385-386)
  * for uniform nodes z_i = z0 + i h, i < N:

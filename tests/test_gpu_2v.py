@@ -208,3 +208,44 @@ def test_calc_in_2D_vjp_table_only():
     ftg = ft.clone().requires_grad_(True)
     (form_factor_full(eng, pt, ftg) * cot).sum().backward()
     assert float((ftg.grad - fb).abs().max()) <= 1e-13 * float(fb.abs().max())
+
+
+@pytest.mark.gpu
+def test_calc_all_chi_vals_matches_oracle_per_pole():
+    """Boundary B2: FormFactor.calc_all_chi_vals(vx, DF, beta, xie_mag, klde_mag) -> (fe_vphi, chiEI, chiERrat),
+    form_factor.py:390-447, against the oracle's per-pole calc_chi_vals (:349-388), all quadrants of beta, poles inside
+    and outside the grid."""
+    from tsadar_b200.form_factor import FormFactor
+    V = 64
+    vx = _grid(V)
+    X, Y = np.meshgrid(vx, vx, indexing="ij")
+    DF = np.exp(-0.5 * ((X - 0.3) ** 2 / 1.2 + (Y + 0.2) ** 2 / 0.8) ** 1.2) * (1 + 0.2 * np.tanh(X))
+    DF = DF / DF.sum() / (vx[1] - vx[0]) ** 2
+    rng = np.random.default_rng(4)
+    G, W, A = 1, 7, 5
+    beta = rng.uniform(-np.pi, 2 * np.pi, (G, W, A))
+    beta[0, 0, :] = [0.0, np.pi / 4, 3 * np.pi / 4, 5 * np.pi / 4, np.pi / 2]      # the axis / diagonal cases of the bank logic
+    xie = rng.uniform(0.0, 5.0, (G, W, A))
+    xie[0, 1, 0] = 7.5                                                             # beyond the table: clamped lerps
+    klde = rng.uniform(0.2, 3.0, (G, W, A, 1))                                     # trailing unit axis as in the reference (:565)
+    ff = FormFactor([400.0, 700.0], 16, 0.0, {"sa": np.array([60.0])}, 1, 0.0, 0.0)
+    fphi, chiEI, chiER = ff.calc_all_chi_vals(vx, DF, beta, xie, klde)
+    assert fphi.shape == chiEI.shape == chiER.shape == (G, W, A)
+    ref = np.array([O.calc_chi_vals_2d(vx, DF, b, x, k)[:3] for b, x, k in zip(beta.ravel(), xie.ravel(), klde.ravel())])
+    for got, want, name in ((fphi, ref[:, 0], "fe_vphi"), (chiEI, ref[:, 1], "chiEI"), (chiER, ref[:, 2], "chiERrat")):
+        got = got.cpu().numpy().ravel()
+        assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want)), (name, np.max(np.abs(got - want)), np.max(np.abs(want)))
+
+
+@pytest.mark.gpu
+def test_chi2v_needs_2v_context():
+    import torch
+    from tsadar_b200 import _ffi
+    from tsadar_b200.engine import FormFactorEngine
+    vx = _grid(64)
+    eng = FormFactorEngine((400.0, 700.0), 16, 0.0, np.array([60.0]), np.ones(1), 1, 1, vx, mode="direct")
+    z = torch.zeros(4, dtype=torch.float64, device="cuda")
+    rc = _ffi.lib().tsff_chi2v_fwd(eng._ctx, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, z.data_ptr(), None)
+    assert rc != 0
+    with pytest.raises(RuntimeError, match="2V"):
+        _ffi.check(rc)

@@ -32,6 +32,9 @@ struct Args2V {
   const double* fe;       // [B][V][V]
   double* ff;             // [B][G][W][A]
   double* f1save;         // [B][P][V] projected tables per pole (forward -> backward), or null
+  // calc_all_chi_vals entry (form_factor.py:390-447): poles given by the caller instead of the kinematics
+  const double *beta_in, *xie_in, *klde_in;   // [P] each, or null
+  double* chi_out;                            // [3][P]: fe_vphi, chiEI, chiERrat
   // backward
   const double* ff_bar;   // [B][G][W][A]
   double* fe_bar;         // [B][V][V]   (atomically accumulated: zero it)
@@ -103,7 +106,12 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long
     Kin q;
     double cb = 1.0, sb = 0.0, xmag = 0.0, omgs = 0.0;
     int g = 0, j = 0, ia = 0;
-    if (valid) {
+    if (valid && a.beta_in) {                    // calc_all_chi_vals: (beta, |xi|, k lambda_De) straight from the caller
+      sincos(a.beta_in[p], &sb, &cb);
+      xmag = a.xie_in[p];
+      const double kl = a.klde_in[p];
+      q.ikl2 = 1.0 / (kl * kl);
+    } else if (valid) {
       g = (int)(p / WA);
       const int r = (int)(p % WA);
       j = r / a.A; ia = r % a.A;
@@ -182,11 +190,17 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long
       const double fphi = lerp_uniform(sf1 + grp * V, V, a.v0, a.dv, xmag, i_f, t_f, sl_f);   // :376
       const double d0 = sdf[grp * V + i_f], d1 = sdf[grp * V + i_f + 1];
       const double dfe = d0 + t_f * (d1 - d0);                                                // :377
-      IonOut io;
-      ion_forward(L, a.nI, a.zt, q, io);
-      Asm s;
-      const double Pl = assemble_forward(L, q, io, -q.ikl2 * I, kPi * q.ikl2 * dfe, fphi, omgs, s);
-      a.ff[((b_lineout * a.G + g) * (long long)a.W + j) * a.A + ia] = Pl;
+      if (a.chi_out) {
+        a.chi_out[p] = fphi;                                 // fe_vphi   :376
+        a.chi_out[a.P + p] = kPi * q.ikl2 * dfe;             // chiEI     :381
+        a.chi_out[2 * (long long)a.P + p] = -q.ikl2 * I;     // chiERrat  :385-386
+      } else {
+        IonOut io;
+        ion_forward(L, a.nI, a.zt, q, io);
+        Asm s;
+        const double Pl = assemble_forward(L, q, io, -q.ikl2 * I, kPi * q.ikl2 * dfe, fphi, omgs, s);
+        a.ff[((b_lineout * a.G + g) * (long long)a.W + j) * a.A + ia] = Pl;
+      }
     }
     __syncthreads();
   }
@@ -539,6 +553,27 @@ int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, dou
     k_ff2v_fwd<32><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
     TSFF_LAUNCH_OK("k_ff2v_fwd");
   }
+  return TSFF_OK;
+}
+
+// FormFactor.calc_all_chi_vals (form_factor.py:390-447): chi_out = [fe_vphi | chiEI | chiERrat], each [P]
+int chi2v_fwd(tsff_ctx* c, const double* fe, const double* beta, const double* xie_mag, const double* klde_mag, int64_t P,
+              double* chi_out, cudaStream_t st) {
+  const int V = c->V;
+  if (V > 128 || V < 8) { set_error("2V path: V must be in [8, 128] (got %d)", V); return TSFF_E_INVALID; }
+  if (P > 0x7fffffffLL) { set_error("2V path: too many poles"); return TSFF_E_INVALID; }
+  Args2V a;
+  memset(&a, 0, sizeof(a));
+  a.W = 1; a.A = 1; a.G = 0; a.nI = c->I; a.V = V; a.NP = c->NP; a.P = (int)P;
+  a.v0 = c->v0; a.dv = c->dv; a.zt = c->zt;
+  a.fe = fe; a.beta_in = beta; a.xie_in = xie_mag; a.klde_in = klde_mag; a.chi_out = chi_out;
+  const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
+  const size_t smem = ((size_t)V * (V + 1) + (size_t)NG * V * 2 + (size_t)NG * 16) * 8;
+  TSFF_SMEM_OPTIN(k_ff2v_fwd<32>);
+  const long long nbatch = ((long long)a.P + NG - 1) / NG;
+  const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
+  k_ff2v_fwd<32><<<grid, kThreads2V, smem, st>>>(a, 0LL);
+  TSFF_LAUNCH_OK("k_ff2v_fwd (chi)");
   return TSFF_OK;
 }
 

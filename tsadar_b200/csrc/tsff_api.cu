@@ -17,6 +17,7 @@ int table_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*, 
               void*, cudaStream_t);
 int ff2v_fwd(tsff_ctx*, int64_t, const double*, const double*, double*, void*, cudaStream_t);
 int ff2v_bwd(tsff_ctx*, int64_t, const double*, const double*, const void*, const double*, double*, double*, void*, cudaStream_t);
+int chi2v_fwd(tsff_ctx*, const double*, const double*, const double*, const double*, int64_t, double*, cudaStream_t);
 size_t ff2v_saved_bytes(const tsff_ctx*, int64_t);
 size_t ff2v_ws_bytes(const tsff_ctx*, int64_t);
 }  // namespace tsff
@@ -55,6 +56,15 @@ extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const v
   }
   return c->mode == TSFF_MODE_TABLE ? table_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st)
                                     : direct_fwd(c, B, params, fe, fe_dtype, modl_out, ff_out, saved, ws, st);
+}
+
+extern "C" int tsff_chi2v_fwd(tsff_ctx* c, const double* fe, const double* beta, const double* xie_mag, const double* klde_mag,
+                              int64_t P, double* chi_out, void* stream) {
+  if (!c) { set_error("null context"); return TSFF_E_INVALID; }
+  if (c->mode != TSFF_MODE_2V) { set_error("tsff_chi2v_fwd needs a TSFF_MODE_2V context"); return TSFF_E_INVALID; }
+  if (P == 0) return TSFF_OK;
+  if (P < 0 || !fe || !beta || !xie_mag || !klde_mag || !chi_out) { set_error("null argument"); return TSFF_E_INVALID; }
+  return chi2v_fwd(c, fe, beta, xie_mag, klde_mag, P, chi_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,

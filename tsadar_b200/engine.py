@@ -131,6 +131,22 @@ class FormFactorEngine:
             saved.data_ptr(), ws.data_ptr(), st))
         return modl, ff, saved
 
+    def chi_vals_2v(self, fe, beta, xie_mag, klde_mag):
+        """2V mode: FormFactor.calc_all_chi_vals -- fe [V,V], beta / xie_mag / klde_mag of any common shape (float64 cuda)
+        -> (fe_vphi, chiEI, chiERrat) of that shape."""
+        assert self.mode == "2v", "chi_vals_2v needs a 2V engine"
+        for name, t in (("fe", fe), ("beta", beta), ("xie_mag", xie_mag), ("klde_mag", klde_mag)):
+            _require_cuda(t, torch.float64, name)
+        assert fe.shape == (self.V, self.V), fe.shape
+        shape = beta.shape
+        P = beta.numel()
+        assert xie_mag.numel() == P and klde_mag.numel() == P
+        out = torch.empty((3, P), dtype=torch.float64, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_chi2v_fwd(self._ctx, fe.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                             xie_mag.contiguous().data_ptr(), klde_mag.contiguous().data_ptr(), P, out.data_ptr(), st))
+        return out[0].reshape(shape), out[1].reshape(shape), out[2].reshape(shape)
+
     def backward(self, params, fe, saved, modl_bar=None, ff_bar=None, params_bar=None, fe_bar=None, want_params=True):
         """want_params=False (2V mode only): skip params_bar (returned as None) when no kinematic parameter is trainable."""
         B = params.shape[0]

@@ -97,6 +97,32 @@ class FormFactor:
         eng = self.engine(vx, nI, weights=weights, jmul=jmul)
         return form_factor_modl(eng, block, fe), block
 
+    def _engine_2v(self, vx, nI):
+        key = ("2v", vx.size, float(vx[0]), float(vx[1] - vx[0]), nI)
+        if key not in self._engines:
+            sa = np.asarray(self.scattering_angles["sa"], dtype=np.float64).reshape(-1)
+            self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, np.ones_like(sa),
+                                                  self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle,
+                                                  w_slice=self._w_slice)
+        return self._engines[key]
+
+    def calc_all_chi_vals(self, x, DF, beta, xie_mag, klde_mag):
+        """-> fe_vphi, chiEI, chiERrat, each shaped like beta   (form_factor.py:390-447; per pole :349-388).
+        x: the velocity grid vx[V]; DF: the table [V,V]; beta, xie_mag [G,W,A]; klde_mag [G,W,A] or [G,W,A,1].
+        Forward only (the reference differentiates this stage through calc_in_2D)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def T(t):
+            t = t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t), dtype=torch.float64)
+            return t.detach().to(device=dev, dtype=torch.float64).contiguous()
+
+        vx = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        vx = np.asarray(vx, dtype=np.float64).reshape(-1)
+        beta = T(beta)
+        klde = T(klde_mag).reshape(beta.shape)             # the reference carries a trailing unit axis (:565)
+        eng = self._engine_2v(vx, 1)
+        return eng.chi_vals_2v(T(DF), beta, T(xie_mag).reshape(beta.shape), klde)
+
     def calc_in_2D(self, params):
         """-> formfactor [G,W,A], lams [1,W,1]   (form_factor.py:449-587).  params["electron"]["fe"] is the 2-D table
         DF[V,V] on vx x vx (one parameter set, as in the reference's angular spectypes).  Differentiable: the custom
@@ -114,12 +140,6 @@ class FormFactor:
         v = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
         p1["electron"]["v"] = np.asarray(v, dtype=np.float64).reshape(-1)[: fe.shape[1]] if np.ndim(v) == 1 else np.asarray(v[0], dtype=np.float64)
         block, _, vx, _, nI = pack_params(p1, dev)
-        key = ("2v", vx.size, float(vx[0]), float(vx[1] - vx[0]), nI)
-        if key not in self._engines:
-            sa = np.asarray(self.scattering_angles["sa"], dtype=np.float64).reshape(-1)
-            self._engines[key] = FormFactorEngine(self.lambda_range, self.npts, self.lam_shift, sa, np.ones_like(sa),
-                                                  self.num_grad_points, nI, vx, mode="2v", ud_ang=self.ud_angle, va_ang=self.va_angle,
-                                                  w_slice=self._w_slice)
-        eng = self._engines[key]
+        eng = self._engine_2v(vx, nI)
         ff = form_factor_full(eng, self._enter(block[:1].contiguous()), self._enter(fe.contiguous()))
         return ff[0], torch.as_tensor(self._lams, device=dev)
