@@ -122,3 +122,15 @@ def test_wavelength_sharding_operators(world, npts):
         assert ok, f"rank {rank} mismatch"
         covered += list(range(s, e))
     assert covered == list(range(npts))
+
+
+def test_numa_binding_is_a_no_op_without_gpu_topology():
+    """bind_to_gpu_numa_node must never break a rank: without a CUDA device / NVML it leaves the affinity alone."""
+    import os
+    import torch
+    from tsadar_b200.parallel import bind_to_gpu_numa_node
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side behaviour")
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
