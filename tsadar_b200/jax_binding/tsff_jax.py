@@ -21,7 +21,7 @@ except ImportError as e:  # pragma: no cover - JAX is absent where this reposito
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _XLA_LIB = ctypes.CDLL(os.environ.get("TSFF_XLA_LIB", os.path.join(_HERE, "..", "_lib", "libtsff_xla.so")))
-for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffPvFwd", "TsffLossFwdBwd"):
+for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffPvFwd", "TsffChi2vFwd", "TsffLossFwdBwd"):
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_XLA_LIB, _name)), platform="CUDA")
 
 
@@ -92,3 +92,12 @@ def pack_params(params):
     cols = [jnp.atleast_1d(jnp.asarray(c, dtype=jnp.float64)).reshape(-1) for c in cols]
     B = max(c.shape[0] for c in cols)
     return jnp.stack([jnp.broadcast_to(c, (B,)) for c in cols], axis=1)
+
+
+def calc_all_chi_vals(ctx: int, DF, beta, xie_mag, klde_mag):
+    """FormFactor.calc_all_chi_vals (form_factor.py:390-447) on a TSFF_MODE_2V context -> (fe_vphi, chiEI, chiERrat), each
+    shaped like beta.  Forward only: inside calc_in_2D the whole stage is one custom call with its own VJP."""
+    P = int(np.prod(beta.shape))
+    chi = jax.ffi.ffi_call("TsffChi2vFwd", jax.ShapeDtypeStruct((3, P), jnp.float64), vmap_method="sequential")(
+        DF, beta.reshape(-1), xie_mag.reshape(-1), klde_mag.reshape(-1), ctx=np.int64(ctx))
+    return chi[0].reshape(beta.shape), chi[1].reshape(beta.shape), chi[2].reshape(beta.shape)

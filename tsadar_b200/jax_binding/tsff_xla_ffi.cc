@@ -66,6 +66,14 @@ ffi::Error PvFwd(cudaStream_t stream, double z0, double h, ffi::Buffer<ffi::F64>
                             TSFF_PV_FP32, ws->typed_data(), stream));
 }
 
+// FormFactor.calc_all_chi_vals (form_factor.py:390-447): DF [V, V]; beta, xie_mag, klde_mag flattened [P] -> chi [3, P]
+ffi::Error Chi2vFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> fe, ffi::Buffer<ffi::F64> beta,
+                    ffi::Buffer<ffi::F64> xie_mag, ffi::Buffer<ffi::F64> klde_mag, ffi::ResultBuffer<ffi::F64> chi) {
+  const int64_t P = static_cast<int64_t>(beta.element_count());
+  return status(tsff_chi2v_fwd(reinterpret_cast<tsff_ctx*>(ctx), fe.typed_data(), beta.typed_data(), xie_mag.typed_data(),
+                               klde_mag.typed_data(), P, chi->typed_data(), stream));
+}
+
 // masked loss + seed cotangent (loss_function.py:190-267, 386-418)
 ffi::Error LossFwdBwd(cudaStream_t stream, double uncert, double scale, int64_t method, ffi::Buffer<ffi::F64> theory,
                       ffi::Buffer<ffi::F64> data, ffi::Buffer<ffi::F64> weight, ffi::ResultBuffer<ffi::F64> loss,
@@ -97,6 +105,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffPvFwd, PvFwd,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<double>("z0").Attr<double>("h")
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffChi2vFwd, Chi2vFwd,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("ctx")
+                                  .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffLossFwdBwd, LossFwdBwd,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<double>("uncert").Attr<double>("scale")
                                   .Attr<int64_t>("method").Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
