@@ -49,6 +49,7 @@ extern "C" int tsff_ff_fwd(tsff_ctx* c, int64_t B, const double* params, const v
   int rc = check_common(c, B, params, fe, fe_dtype, saved, ws);
   if (rc) return rc;
   if (!modl_out && !ff_out) { set_error("no output requested"); return TSFF_E_INVALID; }
+  TSFF_ON_DEVICE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->mode == TSFF_MODE_2V) {
     if (fe_dtype != TSFF_F64 || !ff_out || modl_out) { set_error("2V mode: fe must be float64 [B][V][V]; only ff_out is produced"); return TSFF_E_INVALID; }
@@ -64,6 +65,7 @@ extern "C" int tsff_chi2v_fwd(tsff_ctx* c, const double* fe, const double* beta,
   if (c->mode != TSFF_MODE_2V) { set_error("tsff_chi2v_fwd needs a TSFF_MODE_2V context"); return TSFF_E_INVALID; }
   if (P == 0) return TSFF_OK;
   if (P < 0 || !fe || !beta || !xie_mag || !klde_mag || !chi_out) { set_error("null argument"); return TSFF_E_INVALID; }
+  TSFF_ON_DEVICE(c);
   return chi2v_fwd(c, fe, beta, xie_mag, klde_mag, P, chi_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -75,6 +77,7 @@ extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const v
   if (rc) return rc;
   if (!modl_bar && !ff_bar) { set_error("no cotangent given"); return TSFF_E_INVALID; }
   if (!fe_bar || (!params_bar && c->mode != TSFF_MODE_2V)) { set_error("null output"); return TSFF_E_INVALID; }
+  TSFF_ON_DEVICE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->mode == TSFF_MODE_2V) {
     if (fe_dtype != TSFF_F64 || !ff_bar || modl_bar) { set_error("2V mode: fe float64, cotangent of the formfactor only"); return TSFF_E_INVALID; }
@@ -191,6 +194,7 @@ extern "C" int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, dou
                            const double* out_bar, double* f_bar, double* pole_bar, void* ws, void* stream) {
   if (B == 0) return TSFF_OK;
   if (!f || !pole || !out_bar || !f_bar || !ws || B < 1 || N < 4 || P < 1) { set_error("bad argument"); return TSFF_E_INVALID; }
+  if (tree_npad((int)N - 1) > kTreeMaxNpad) { set_error("N too large (limit %d nodes)", kTreeMaxNpad); return TSFF_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PvLayout L = pv_layout(B, N, P);
   char* w = static_cast<char*>(ws);

@@ -29,6 +29,27 @@ void set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
+// RAII: make `device` current for the duration of a C-ABI call and restore the caller's device afterwards (a process may
+// hold contexts on several GPUs; the library must neither depend on nor change the caller's current device).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+    if (cur != device) {
+      ok = cudaSetDevice(device) == cudaSuccess;
+      if (ok) prev = cur;
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define TSFF_ON_DEVICE(ctx)                                                                  \
+  tsff::DeviceGuard _dev_guard((ctx)->device);                                               \
+  if (!_dev_guard.ok) { tsff::set_error("cannot make device %d current", (ctx)->device); return TSFF_E_CUDA; }
+
 // Opt a kernel in to large dynamic shared memory.  Always raise the cap to the device maximum: the attribute is a
 // per-function CAP, so setting it to "what this launch needs" would make a later, larger launch fail.
 #define TSFF_SMEM_OPTIN(kernel)                                                                          \
@@ -159,4 +180,5 @@ struct tsff_ctx {
   double pv_z0, pv_h;
   double* tstat; // static expansion tables (k_tree_static) for pv_nodes
   cudaEvent_t ev[4];  // optional profile events (fwd start/stop, bwd start/stop)
+  int tune_fwd_r4;    // TSFF_FWD_R4 tuning switch, read once at creation (four poles per thread in k_direct_fwd: measured slower)
 };

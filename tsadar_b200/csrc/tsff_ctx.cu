@@ -4,6 +4,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "tsff_pv_kernels.cuh"
 
 namespace tsff {
@@ -51,11 +53,13 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   cudaDeviceProp prop;
   TSFF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) { set_error("device %d is sm_%d%d; libtsff is built for sm_100a only", device, prop.major, prop.minor); return TSFF_E_NODEVICE; }
-  TSFF_CUDA_OK(cudaSetDevice(device));
+  DeviceGuard guard(device);   // the caller's current device is restored on every return path
+  if (!guard.ok) { set_error("cannot make device %d current", device); return TSFF_E_CUDA; }
 
   tsff_ctx* c = new tsff_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->tune_fwd_r4 = getenv("TSFF_FWD_R4") != nullptr;
   c->sm_count = prop.multiProcessorCount;
   c->mode = cfg->mode; c->W = cfg->W; c->A = cfg->A; c->G = cfg->G; c->I = cfg->I; c->V = cfg->V;
   c->NP = TSFF_P_ION0 + TSFF_ION_STRIDE * cfg->I;
@@ -137,6 +141,7 @@ extern "C" int tsff_ctx_set_profile_events(tsff_ctx* ctx, void* e0, void* e1, vo
 
 extern "C" void tsff_ctx_destroy(tsff_ctx* ctx) {
   if (!ctx) return;
+  DeviceGuard guard(ctx->device);
   cudaFree(ctx->tstat);
   cudaFree(ctx->dev_blob);
   delete ctx;

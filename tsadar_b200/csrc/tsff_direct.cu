@@ -410,7 +410,7 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   if (c->pv_precision == TSFF_PV_FP64) {
     a.ntiles = (WA + kThreads - 1) / kThreads;
     k_direct_fwd<1, T, TSFF_PV_FP64><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
-  } else if ((long long)B * c->G * tiles4 >= 2LL * c->sm_count && getenv("TSFF_FWD_R4")) {  // tuning switch: measured slower
+  } else if ((long long)B * c->G * tiles4 >= 2LL * c->sm_count && c->tune_fwd_r4) {  // tuning switch: measured slower
     a.ntiles = (int)tiles4;
     TSFF_SMEM_OPTIN((k_direct_fwd<4, T, TSFF_PV_FP32, 2>));
     k_direct_fwd<4, T, TSFF_PV_FP32, 2><<<(unsigned)(B * c->G * a.ntiles), kThreads, smem, st>>>(a);

@@ -163,7 +163,8 @@ def _adam_fit_graphed(loss_closure, ts_params, learning_rate, num_steps, b1, b2,
     dev = leaves[0].device
     mu = [torch.zeros_like(t) for t in leaves]
     nu = [torch.zeros_like(t) for t in leaves]
-    hist = torch.zeros(num_steps, dtype=torch.float64, device=dev)
+    n_warm = 3
+    hist = torch.zeros(max(num_steps, n_warm), dtype=torch.float64, device=dev)   # the warm-up steps write slots 0..2 too
     step = torch.zeros((), dtype=torch.float64, device=dev)          # device-side iteration counter
     slot = torch.zeros((), dtype=torch.long, device=dev)
 
@@ -185,15 +186,7 @@ def _adam_fit_graphed(loss_closure, ts_params, learning_rate, num_steps, b1, b2,
             for t, m, v in zip(leaves, mu, nu):
                 t.sub_(learning_rate * (m / c1) / (torch.sqrt(v / c2) + eps))
 
-    # warm-up on a side stream (lazy context creation, scratch buffers, shared-memory opt-ins), state restored afterwards
     keep = [t.detach().clone() for t in leaves]
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            one_step()
-    torch.cuda.current_stream(dev).wait_stream(side)
-    torch.cuda.synchronize(dev)
 
     def reset():
         with torch.no_grad():
@@ -203,11 +196,24 @@ def _adam_fit_graphed(loss_closure, ts_params, learning_rate, num_steps, b1, b2,
                 m.zero_()
             step.zero_(); slot.zero_(); hist.zero_()
 
-    reset()
+    # warm-up on a side stream (lazy context creation, scratch buffers, shared-memory opt-ins).  The warm-up advances the live
+    # leaves and the moments: whatever happens in it (or in the capture), the caller's parameters are restored.
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    try:
+        with torch.cuda.stream(side):
+            for _ in range(n_warm):
+                one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+    finally:
+        reset()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        one_step()
-    reset()                                   # capture does not execute; make the state pristine anyway
+    try:
+        with torch.cuda.graph(graph):
+            one_step()
+    finally:
+        reset()                               # capture does not execute; make the state pristine anyway
     for _ in range(num_steps):
         graph.replay()
-    return hist.cpu().numpy()
+    return hist[:num_steps].cpu().numpy()
