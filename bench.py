@@ -6,13 +6,21 @@ wavelengths on [400,700] nm, one scattering angle (60 deg), one ion species, f(v
 direct-pole mode: 1024 x 4094 (omega, v) pairs per lineout and pass.  One "step" = for B lineouts per GPU:
     tsff_ff_fwd  (spectrum)  ->  tsff_loss_fwd_bwd (L2 vs a seeded target: the VJP seed)  ->  tsff_ff_bwd (params_bar, fe_bar)
 Lineouts are independent, so N GPUs = N ranks each owning B lineouts (weak scaling); the only collective is the NCCL
-all-reduce of the scalar loss.
+all-reduce of the scalar loss, once per step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--lineouts B] [--impl ours|reference]
 
+The JSON line carries, besides the contract's keys:
+  roofline    EXECUTED FP32 flop of the dominant kernel (opcode counts of this binary from the committed ncu source-page
+              capture, profiles/ncu_latest.json) / its CUDA-event duration measured here / the FFMA peak measured here.
+              The pairwise-equivalent figure of SURVEY 8(d) (what an all-pairs sweep would need) is a separate key.
+  parity      two lineouts of the timed batch against the float64 oracle (spectrum, gradients) after the timed region.
+  sustained   the same step back to back for >= 2 s, with its own clock record.
+  configs     the reference's named decks (1d, 1d_series, arts-1d, arts-2d): fwd+VJP ms on the device, the oracle-port
+              CPU time of a bounded sample beside it; arts-2d runs wavelength-sharded over the N ranks (strong scaling).
 --impl reference times the oracle restatement of the reference's algorithm (torch float64 forward + autograd, all host
-threads) -- JAX is not installable in this image, so the reference itself cannot run.
-"""
+threads) on a bounded sample of the same workload per step -- JAX is not installable in this image, so the reference
+itself cannot run."""
 from __future__ import annotations
 
 import argparse
@@ -31,10 +39,10 @@ sys.path.insert(0, ROOT)
 
 PAIRS_PER_LINEOUT = 1024 * 4094          # (omega, v) pairs per lineout and pass (N-2 quirk of ratintn)
 FLOP_PER_PAIR_STEP = 19                  # fwd 7 + dI/dxi 5 + f-table adjoint 7
-MUFU_PER_PAIR_STEP = 3
 FLOP_PER_PAIR_FWD = 12                   # the forward pole sweep computes I and dI/dxi
 FLOP_PER_PAIR_BWD = 7
-
+CPU_SAMPLE_LINEOUTS = 32                 # bounded CPU sample per step: the first lineouts of the rank-0 batch (seed 42)
+METRIC = "lineouts/sec (form-factor fwd+VJP)"
 
 # stdout must carry exactly ONE JSON line (the driver parses it).  Libraries write there too (NCCL prints its version
 # banner on stdout when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole run
@@ -60,44 +68,62 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def _clock_sampler(path, stop):
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                             stdout=open(path, "w"), stderr=subprocess.DEVNULL)
-    except Exception:
-        return
-    stop.wait()
-    p.terminate()
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons every 100 ms while a timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, tag):
+        self.path = os.path.join(tempfile.gettempdir(), f"tsff_clocks_{tag}_{os.getpid()}.csv")
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)
+        except Exception:
+            self.p = None
+        return self
+
+    def stop(self, dev_index):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                pass
+        sm, smax, pw, reasons = [], 0.0, 0.0, set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8 or not f[0].isdigit() or int(f[0]) != dev_index:
+                    continue
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+                try:
+                    pw = max(pw, float(f[3]))
+                except ValueError:
+                    pass
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "power_w_max": pw}
 
 
-def _parse_clocks(path, dev_index):
-    sm, smax, reasons = [], 0.0, set()
-    try:
-        for line in open(path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8 or not f[0].isdigit() or int(f[0]) != dev_index:
-                continue
-            sm.append(float(f[1]))
-            smax = max(smax, float(f[2]))
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-    except Exception:
-        pass
-    if not sm:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def oracle_step(params, fe, vx, target):
-    """The reference-semantics CPU path: torch-f64 forward + autograd VJP of the same loss, per lineout."""
+# ---- the reference-semantics CPU path -----------------------------------------------------------------------------------
+def oracle_step(params, fe, vx, target, grids, keep=None):
+    """torch-f64 forward + autograd VJP of the same loss, per lineout (oracle/torch_oracle.py: the reference's complex-log
+    ratintn over all 1024 x 4094 pairs).  keep: optional dict filled with modl / params_bar / fe_bar of every lineout."""
     import torch
-    from oracle import np_oracle as O, torch_oracle as TO
-    grids = oracle_step.grids
+    from oracle import torch_oracle as TO
     tot = 0.0
-    for b in range(params.shape[0]):
+    B = params.shape[0]
+    for b in range(B):
         leaves, p = TO.params_from_block(params[b], 1)
         fet = torch.tensor(fe[b].astype(np.float64), requires_grad=True)
         ff = TO.form_factor_direct(p, fet, vx, grids, np.array([60.0]), 1, 0.0)
@@ -105,41 +131,85 @@ def oracle_step(params, fe, vx, target):
         loss = torch.sum((torch.tensor(target[b]) - modl) ** 2) / target.shape[1]
         loss.backward()
         tot += float(loss.detach())
+        if keep is not None:
+            keep.setdefault("modl", []).append(modl.detach().numpy())
+            keep.setdefault("pbar", []).append(leaves.grad.numpy().copy())
+            keep.setdefault("fbar", []).append(fet.grad.numpy().copy())
     return tot
 
 
+def workload_config(B, world):
+    from tsadar_b200.synthetic import W_SYN, V_SYN
+    ws_mib = int(B * (V_SYN * 4 * 2 + 2 * W_SYN * 8 + 19 * 8 + 3 * W_SYN * 8) / 2**20)   # tables + cotangents, residuals, spectra
+    return {"workload": "synthetic_sweep", "W": W_SYN, "V": V_SYN, "angles": 1, "ions": 1, "lineouts_per_gpu": B,
+            "pairs_per_lineout": PAIRS_PER_LINEOUT, "parallelism": f"lineouts x{world}",
+            "cache": f"working set {ws_mib} MiB per step > 126 MiB L2 (inputs larger than L2, no flush needed)"}
+
+
 def run_reference(args):
-    import torch
-    from oracle import np_oracle as O
-    from tsadar_b200.synthetic import make_lineouts, LAM_RANGE, W_SYN, V_SYN
+    """--impl reference: the oracle port on the host cores, rank 0 only.  Same metric / unit / config as our arm; a step is
+    a bounded sample (CPU_SAMPLE_LINEOUTS lineouts of the rank-0 batch, seed 42 -- the sample cpu_baseline uses too)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    from oracle import np_oracle as O
+    from tsadar_b200.synthetic import make_lineouts, LAM_RANGE, W_SYN
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nb = args.ref_lineouts
+    nb, K, Wm = args.cpu_lineouts, args.steps, args.warmup
     params, fe, vx, _ = make_lineouts(nb, seed=42)
-    oracle_step.grids = O.Grids(list(LAM_RANGE), W_SYN)
+    grids = O.Grids(list(LAM_RANGE), W_SYN)
     target = np.zeros((nb, W_SYN))
-    for _ in range(args.warmup_ref):
-        oracle_step(params[:1], fe[:1], vx, target[:1])
+    for _ in range(Wm):
+        oracle_step(params, fe, vx, target, grids)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_step(params, fe, vx, target)
+    for _ in range(K):
+        oracle_step(params, fe, vx, target, grids)
     dt = time.perf_counter() - t0
-    val = nb * args.steps / dt
+    val = nb * K / dt
+    cfg = workload_config(args.lineouts, max(args.gpus, 1))
     line = {
-        "metric": "lineouts/sec (form-factor fwd+VJP)", "value": val, "unit": "lineouts/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "synthetic_sweep", "W": W_SYN, "V": V_SYN, "angles": 1, "ions": 1,
-                   "lineouts_per_step": nb, "note": "oracle port of the reference algorithm (JAX not installable here)"},
+        "metric": METRIC, "value": val, "unit": "lineouts/s", "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "lineouts/s", "cores": cores, "kind": "port",
-                         "sample": f"{nb} lineouts x {args.steps} steps, torch-f64 forward + autograd"},
+                         "sample": f"each step = the first {nb} lineouts of the workload's rank-0 batch (seed 42), torch-f64 forward + "
+                                   f"autograd VJP (oracle/torch_oracle.py; JAX not installable here)"},
         "e2e": {"value": val, "unit": "lineouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+# ---- executed-work counts of this binary (ncu source page), for the in-run roofline ----------------------------------------
+def load_counts():
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_latest.json")))
+    except Exception:
+        return None, "profiles/ncu_latest.json missing"
+    stale = None
+    try:
+        from tsadar_b200 import build as _b
+        if prof.get("source_stamp") and prof["source_stamp"] != _b._stamp():
+            stale = "kernel sources changed since the ncu capture: counts are from the previous binary"
+    except Exception:
+        pass
+    return prof, stale
+
+
+def kernel_view(prof, key, B, ms, ffma_peak, sm_mhz, n_sm):
+    """Executed rates of one kernel: counts per lineout (ncu) x B / the duration measured in this run."""
+    k = (prof or {}).get("kernels", {}).get(key)
+    if not k or not ms:
+        return None
+    s = ms * 1e-3
+    out = {"fp32_tflops": k["fp32_flop_per_lineout"] * B / s / 1e12, "fp64_tflops": k["fp64_flop_per_lineout"] * B / s / 1e12,
+           "mufu_gops": k["mufu_per_lineout"] * B / s / 1e9, "dram_bytes": k.get("dram_bytes_per_lineout", 0.0) * B}
+    out["frac"] = out["fp32_tflops"] * 1e12 / (2 * ffma_peak)
+    if sm_mhz:
+        out["issue_slot_frac"] = k["warp_inst_per_lineout"] * B / (s * sm_mhz * 1e6 * n_sm * 4)
+    return out
 
 
 def main():
@@ -149,14 +219,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lineouts", type=int, default=16384, help="lineouts per GPU per step (measured: 4096 -> 1.74M, 8192 -> 1.79M, 16384 -> 1.82M lineouts/s: fewer partial waves)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-lineouts", type=int, default=8)
-    ap.add_argument("--warmup-ref", type=int, default=1)
-    ap.add_argument("--cpu-baseline-lineouts", type=int, default=128)
+    ap.add_argument("--cpu-lineouts", type=int, default=CPU_SAMPLE_LINEOUTS, help="lineouts per step of the CPU arm / the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the named-deck block")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
-        args.steps = min(args.steps, 5)
         return run_reference(args)
 
     import torch
@@ -201,6 +271,7 @@ def main():
     target = target.clone()
     unc = 1.0
     scale = 1.0 / (B * world)
+    last = {}
 
     def step(p, f):
         modl, _, _ = eng.forward(p, f, saved=saved)
@@ -208,6 +279,7 @@ def main():
         if world > 1:
             dist.all_reduce(loss)
         eng.backward(p, f, saved, modl_bar=tbar, params_bar=pbar, fe_bar=fbar)
+        last["modl"] = modl
 
     launches_per_step = eng.launches_fwd() + 1 + eng.launches_bwd()
 
@@ -223,12 +295,7 @@ def main():
     barrier()
 
     # ---- clocks during the timed regions
-    stop = threading.Event()
-    clk_path = os.path.join(tempfile.gettempdir(), f"tsff_clocks_{rank}.csv")
-    th = threading.Thread(target=_clock_sampler, args=(clk_path, stop), daemon=True)
-    if rank == 0:
-        th.start()
-        time.sleep(0.3)
+    clk = ClockSampler("main").start() if rank == 0 else None
 
     # ---- leg 1: device-resident inputs (value)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,35 +318,66 @@ def main():
         tb += ev_b[0].elapsed_time(ev_b[1])
     eng.set_profile_events(None, None)
     tf, tb = tf / nprof, tb / nprof
+    # results of the device leg, kept for the parity block
+    par_idx = [0, B - 1]
+    got = {"modl": last["modl"][par_idx].cpu().numpy(), "pbar": pbar[par_idx].cpu().numpy(),
+           "fbar": fbar[par_idx].double().cpu().numpy(), "target": target[par_idx].cpu().numpy()} if rank == 0 else None
 
-    # ---- leg 2: end to end through the public call with HOST buffers: every step copies params + fe from pinned host
-    # memory and reads loss + params_bar back.  The batch is cut into chunks that alternate between two streams (each
-    # with its own engine = its own scratch), so the H2D copy of one chunk overlaps the kernels of the other.
+    # ---- leg 2: end to end through the C ABI with HOST buffers: every step copies params + fe from pinned host memory and
+    # reads loss, params_bar AND fe_bar back.  The batch is cut into chunks that alternate between two streams (each with
+    # its own engine = its own scratch), so the copies of one chunk overlap the kernels of the other; the scalar loss is
+    # all-reduced every step.
     NCH = int(os.environ.get("TSFF_E2E_CHUNKS", "2"))   # measured on B200: 2 chunks 1.69M, 4 chunks 1.61M, 8 chunks 1.48M lineouts/s
     NCH = NCH if B % NCH == 0 and B >= 64 else 1
     Bc = B // NCH
     pbar_pin = torch.empty_like(params_pin).pin_memory()
+    fbar_pin = torch.empty_like(fe_pin).pin_memory()
     loss_pin = torch.zeros(NCH, dtype=torch.float64).pin_memory()
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     engs = [eng, FormFactorEngine(LAM_RANGE, W_SYN, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")]
+    loss_tot = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
     ch = []
     for c in range(NCH):
         ch.append(dict(p=torch.empty((Bc, NP), dtype=torch.float64, device=dev), f=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev),
                        saved=torch.empty(eng.saved_bytes(Bc), dtype=torch.uint8, device=dev), pbar=torch.empty((Bc, NP), dtype=torch.float64, device=dev),
-                       fbar=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev), loss=torch.zeros(1, dtype=torch.float64, device=dev),
+                       fbar=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev),
+                       loss=[torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)],   # double-buffered by step parity
+                       loss_ev=[torch.cuda.Event() for _ in range(2)],
                        tgt=target[c * Bc:(c + 1) * Bc].contiguous()))
+    red_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_count = [0]
 
     def step_e2e():
+        par = e2e_count[0] & 1
+        e2e_count[0] += 1
         for c in range(NCH):
             st, e, k = streams[c % 2], engs[c % 2], ch[c]
             with torch.cuda.stream(st):
                 k["p"].copy_(params_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
                 k["f"].copy_(fe_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
                 modl, _, _ = e.forward(k["p"], k["f"], saved=k["saved"])
-                _, tbar = loss_fwd_bwd(modl, k["tgt"], wq, unc, scale, "l2", loss_out=k["loss"], want_grad=True)
+                if world > 1 and e2e_count[0] > 2:
+                    st.wait_event(red_done[par])          # the reduce that read this loss slot two steps ago
+                _, tbar = loss_fwd_bwd(modl, k["tgt"], wq, unc, scale, "l2", loss_out=k["loss"][par], want_grad=True)
+                k["loss_ev"][par].record(st)
                 e.backward(k["p"], k["f"], k["saved"], modl_bar=tbar, params_bar=k["pbar"], fe_bar=k["fbar"])
                 pbar_pin[c * Bc:(c + 1) * Bc].copy_(k["pbar"], non_blocking=True)
-                loss_pin[c:c + 1].copy_(k["loss"], non_blocking=True)
+                fbar_pin[c * Bc:(c + 1) * Bc].copy_(k["fbar"], non_blocking=True)
+                if world == 1:
+                    loss_pin[c:c + 1].copy_(k["loss"][par], non_blocking=True)
+        if world > 1:
+            # the scalar loss of the sharded batch: ONE all-reduce per step, issued on the last chunk's stream as soon as both
+            # chunks' loss kernels are done; the other stream runs on into the next step's copies
+            st = streams[(NCH - 1) % 2]
+            with torch.cuda.stream(st):
+                for c in range(NCH - 1):
+                    st.wait_event(ch[c]["loss_ev"][par])
+                torch.add(ch[0]["loss"][par], ch[-1]["loss"][par] if NCH > 1 else 0.0, out=loss_tot[par])
+                for c in range(1, NCH - 1):
+                    loss_tot[par].add_(ch[c]["loss"][par])
+                dist.all_reduce(loss_tot[par])
+                loss_pin[:1].copy_(loss_tot[par], non_blocking=True)
+                red_done[par].record(st)
 
     def e2e_region(nsteps):
         cur = torch.cuda.current_stream(dev)
@@ -289,9 +387,6 @@ def main():
             step_e2e()
         for st in streams:
             cur.wait_stream(st)
-        if world > 1:
-            tot = loss_pin.sum().to(dev)   # the scalar loss all-reduce of the sharded fit
-            dist.all_reduce(tot)
 
     e2e_region(2)
     barrier()
@@ -301,93 +396,135 @@ def main():
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
-    stop.set()
+    clocks = clk.stop(local) if clk else None
 
-    t = torch.tensor([ms_total, ms_e2e, tf, tb], dtype=torch.float64, device=dev)
+    # ---- leg 3: sustained -- the device-resident step back to back for >= 2 s, its own clock record
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(K, int(np.ceil(args.sustained_seconds * 1e3 / (ms_total / K))))
+        clk2 = ClockSampler("sustained").start() if rank == 0 else None
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        for _ in range(n_sus):
+            step(params_d, fe_d)
+        s1.record()
+        barrier()
+        ms_sus = s0.elapsed_time(s1)
+        sustained = {"steps": n_sus, "ms": ms_sus, "clocks": clk2.stop(local) if clk2 else None}
+
+    t = torch.tensor([ms_total, ms_e2e, tf, tb, sustained["ms"] if sustained else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, tf, tb = [float(x) for x in t.cpu()]
+    ms_total, ms_e2e, tf, tb, ms_sus = [float(x) for x in t.cpu()]
+
+    # ---- the reference's named decks (every rank takes part: arts-2d is wavelength-sharded over the ranks)
+    configs = None
+    if not args.no_configs:
+        try:
+            from tools.bench_configs import run_named_configs
+            configs = run_named_configs(rank, world, dev, cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:   # the headline line must not depend on the side block
+            configs = {"error": f"{type(exc).__name__}: {exc}"}
+        barrier()
 
     if rank == 0:
         ffma_peak = microbench(0)   # FFMA/s  (x2 = FLOP/s)
         mufu_peak = microbench(1)   # MUFU op/s
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         value = B * world * K / (ms_total * 1e-3)
         e2e_val = B * world * K / (ms_e2e * 1e-3)
         pairs = B * PAIRS_PER_LINEOUT
-        fwd_tf = FLOP_PER_PAIR_FWD * pairs / (tf * 1e-3) / 1e12
-        bwd_tf = FLOP_PER_PAIR_BWD * pairs / (tb * 1e-3) / 1e12
         peak_tf = 2 * ffma_peak / 1e12
-        nominal_tf = 148 * 128 * 2 * 1.965e9 / 1e12
-        step_tf = value / world * PAIRS_PER_LINEOUT * FLOP_PER_PAIR_STEP / 1e12
-        clocks = _parse_clocks(clk_path, local)
-        # per-launch DRAM traffic and executed pipe utilisation of the dominant kernel come from the committed ncu capture
-        # of this same command (profiles/ncu_latest.json, written by tools/ncu_summary.py json); scaled to this batch
-        traffic, executed = None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_latest.json")))
-            traffic = prof["dram_bytes_per_launch"] * B / prof["lineouts_per_launch"]
-            executed = {k: prof[k] for k in ("kernel", "issue_slots_busy_pct", "fma_pipe_pct", "xu_pipe_pct", "fp64_pipe_pct")}
-            executed["thread_instructions_per_pole"] = prof["warp_instructions"] * 32 / (prof["lineouts_per_launch"] * W_SYN)
-            executed["source"] = prof["source"]
-        except Exception:
-            pass
-        # the HBM view of the same kernel (why "bound" is not "hbm"): algorithmic bytes per launch = the f tables read once
-        # (FP32) + the pole / spectrum rows, against the measured copy bandwidth of MEASURED_PEAKS.json (driver-written;
-        # fallback: the profiling guide's 7.7 TB/s nominal)
-        hbm_peak, hbm_src = 7700.0, "nominal (B200_PROFILING.md fallback)"
+        nominal_tf = n_sm * 128 * 2 * 1.965e9 / 1e12
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        prof, stale = load_counts()
+        kf = kernel_view(prof, "k_direct_fwd", B, tf, ffma_peak, sm_mhz, n_sm)
+        kb = kernel_view(prof, "k_pv_nodes", B, tb, ffma_peak, sm_mhz, n_sm)
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
             hbm_src = "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
         alg_bytes = B * (V_SYN * 4 + W_SYN * 8 * 2 + NP * 8)
-        hbm_view = {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (tf * 1e-3) / 1e9,
-                    "traffic_gbs": (traffic / (tf * 1e-3) / 1e9) if traffic else None, "peak_gbs": hbm_peak,
-                    "frac": alg_bytes / (tf * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                    "note": "traffic (ncu dram bytes) exceeds the algorithmic bytes because the sweep reads, once, the 59 KB "
-                            "block-multipole blob k_direct_prep derives from each 16 KB f table, and writes the residuals the "
-                            "adjoint needs; neither is re-read within the launch"}
+        h2d = int(params_pin.numel() * 8 + fe_pin.numel() * 4)
+        d2h = int(pbar_pin.numel() * 8 + fbar_pin.numel() * 4 + 8 * NCH)
+        roofline = {
+            "bound": "fp32", "kernel": "k_direct_fwd<2,float,FP32,3> (pole sweep: I and dI/dxi, block-multipole form)",
+            "achieved": kf["fp32_tflops"] if kf else None, "peak": peak_tf, "unit": "TFLOP/s", "frac": kf["frac"] if kf else None,
+            "traffic": kf["dram_bytes"] if kf else None, "ms_per_launch": tf,
+            "definition": "achieved = FP32 flop this kernel EXECUTES per launch (2 FFMA + 4 FFMA2 + FMUL + FADD + 2 FMUL2 + 2 FADD2 thread "
+                          "instructions, ncu source page of this binary, x lineouts) / its CUDA-event duration in this run; peak = FFMA "
+                          "microbenchmark in this run",
+            "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry); nominal %.1f" % nominal_tf,
+            "counts_source": (prof or {}).get("source", "none"), "counts_stale": stale,
+            "issue_slot_frac": kf.get("issue_slot_frac") if kf else None,
+            "fp64_tflops_executed": kf["fp64_tflops"] if kf else None, "mufu_gops_executed": kf["mufu_gops"] if kf else None,
+            "mufu_peak_gops": mufu_peak / 1e9,
+            "pairwise_equivalent_tflops": FLOP_PER_PAIR_FWD * pairs / (tf * 1e-3) / 1e12,
+            "pairwise_equivalent_frac": FLOP_PER_PAIR_FWD * pairs / (tf * 1e-3) / 1e12 / peak_tf,
+            "pairwise_equivalent_note": "what an all-pairs sweep (12 flop per (omega,v) pair, SURVEY 8d) would need to match this time; "
+                                        "NOT a roofline fraction -- the block-multipole form executes ~15x fewer instructions",
+            "adjoint_kernel": "k_pv_nodes", "adjoint_ms_per_launch": tb,
+            "adjoint_achieved": kb["fp32_tflops"] if kb else None, "adjoint_frac": kb["frac"] if kb else None,
+            "adjoint_issue_slot_frac": kb.get("issue_slot_frac") if kb else None,
+            "step_pairwise_equivalent_tflops": value / world * PAIRS_PER_LINEOUT * FLOP_PER_PAIR_STEP / 1e12,
+            "hbm_algorithmic_bytes_per_launch": alg_bytes, "hbm_achieved_gbs": alg_bytes / (tf * 1e-3) / 1e9,
+            "hbm_traffic_gbs": (kf["dram_bytes"] / (tf * 1e-3) / 1e9) if kf and kf["dram_bytes"] else None,
+            "hbm_peak_gbs": hbm_peak, "hbm_frac": alg_bytes / (tf * 1e-3) / 1e9 / hbm_peak, "hbm_peak_source": hbm_src,
+        }
         line = {
-            "metric": "lineouts/sec (form-factor fwd+VJP)", "value": value, "unit": "lineouts/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "lineouts/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 PV sweeps / f64 assembly", "data": "synthetic",
-            "config": {"workload": "synthetic_sweep", "W": W_SYN, "V": V_SYN, "angles": 1, "ions": 1,
-                       "lineouts_per_gpu": B, "pairs_per_lineout": PAIRS_PER_LINEOUT, "parallelism": f"lineouts x{world}",
-                       "cache": f"working set {int((fe_d.numel()*4*2 + saved.numel() + B*W_SYN*8*3)/2**20)} MiB per step > 126 MiB L2"},
-            "e2e": {"value": e2e_val, "unit": "lineouts/s", "h2d_bytes_per_step": int(params_pin.numel() * 8 + fe_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(pbar_pin.numel() * 8 + 8 * NCH), "ms_per_step": ms_e2e / K,
-                    "pipeline": f"{NCH} chunks alternating on 2 streams (H2D of a chunk overlaps the kernels of the previous one)",
+            "config": workload_config(B, world),
+            "e2e": {"value": e2e_val, "unit": "lineouts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K, "h2d_gbs_per_gpu": h2d / (ms_e2e / K * 1e-3) / 1e9,
+                    "bound": "host<->device copies (pinned H2D of the f tables)" if ms_e2e > 1.03 * ms_total else "kernels (copies hidden)",
+                    "entry": "raw C-ABI operands: params [B,14] f64 + fe [B,4096] f32 in; loss, params_bar, fe_bar out",
+                    "pipeline": f"{NCH} chunks alternating on 2 streams; loss all-reduced every step",
                     "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
-            "roofline": {
-                "bound": "fp32", "kernel": "k_direct_fwd (pole sweep: I and dI/dxi)", "achieved": fwd_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": fwd_tf / peak_tf, "traffic": traffic, "executed": executed,
-                "note": "achieved = ALGORITHMIC flops (12 per (omega,v) pair for I and dI/dxi, SURVEY 8d) / kernel time; the block-multipole "
-                        "sweep executes ~15x fewer instructions than that pairwise count, so frac may exceed 1: 'executed' (ncu) is the pipe view",
-                "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry); nominal %.1f" % nominal_tf,
-                "frac_of_nominal": fwd_tf / nominal_tf, "ms_per_launch": tf, "hbm": hbm_view,
-                "mufu": {"achieved_gops": pairs / (tf * 1e-3) / 1e9, "peak_gops": mufu_peak / 1e9,
-                         "frac": pairs / (tf * 1e-3) / mufu_peak},
-                "adjoint_kernel": {"kernel": "k_pv_nodes", "achieved": bwd_tf, "frac": bwd_tf / peak_tf, "ms_per_launch": tb,
-                                   "mufu_frac": pairs / (tb * 1e-3) / mufu_peak},
-                "step": {"algorithmic_tflops": step_tf, "frac": step_tf / peak_tf, "frac_of_nominal": step_tf / nominal_tf,
-                         "mufu_frac": value / world * PAIRS_PER_LINEOUT * MUFU_PER_PAIR_STEP / mufu_peak},
-            },
+            "roofline": roofline,
         }
-        if not args.no_cpu_baseline:
-            from oracle import np_oracle as O
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            nb = args.cpu_baseline_lineouts
-            oracle_step.grids = O.Grids(list(LAM_RANGE), W_SYN)
+        if sustained:
+            line["sustained"] = {"value": B * world * sustained["steps"] / (ms_sus * 1e-3), "unit": "lineouts/s", "steps": sustained["steps"],
+                                 "seconds": ms_sus * 1e-3, "clocks": sustained["clocks"]}
+        if configs is not None:
+            line["configs"] = configs
+        # ---- parity of two lineouts of the timed batch against the float64 oracle, and the CPU baseline on the same sample
+        from oracle import np_oracle as O
+        grids = O.Grids(list(LAM_RANGE), W_SYN)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        keep = {}
+        oracle_step(params_h[par_idx], fe_h[par_idx], vx, got["target"], grids, keep=keep)
+        sp_mx = sp_pw = gp = gf = 0.0
+        for i in range(len(par_idx)):
+            ref = keep["modl"][i]
+            sp_mx = max(sp_mx, float(np.abs(got["modl"][i] - ref).max() / np.abs(ref).max()))
+            m = np.abs(ref) >= 1e-6 * np.abs(ref).max()
+            sp_pw = max(sp_pw, float((np.abs(got["modl"][i] - ref)[m] / np.abs(ref)[m]).max()))
+            rp = keep["pbar"][i] / (B * world)         # the oracle's loss is per lineout; the kernel's carries 1/B_total
+            for k in (0, 1, 2, 11, 12):
+                gp = max(gp, float(abs(got["pbar"][i][k] - rp[k]) / abs(rp[k])))
+            rf = keep["fbar"][i] / (B * world)
+            gf = max(gf, float(np.abs(got["fbar"][i] - rf).max() / np.abs(rf).max()))
+        line["parity"] = {"lineouts_checked": par_idx, "spectrum_rel": sp_mx, "spectrum_pointwise_rel": sp_pw, "grad_rel": gp,
+                          "fe_bar_rel": gf, "bars": {"spectrum": 1e-5, "grad": 1e-4},
+                          "ok": bool(sp_mx <= 1e-5 and gp <= 1e-4 and gf <= 1e-4),
+                          "oracle": "oracle/np_oracle.py + torch_oracle.py (float64, all pairs, autograd VJP of the same l2 loss)"}
+        if not args.no_cpu_baseline and world == 1:
+            nb = min(args.cpu_lineouts, B)
             tgt = target[:nb].cpu().numpy()
-            oracle_step(params_h[:1], fe_h[:1], vx, tgt[:1])
             t0 = time.perf_counter()
-            oracle_step(params_h[:nb], fe_h[:nb], vx, tgt)
+            oracle_step(params_h[:nb], fe_h[:nb], vx, tgt, grids)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": nb / dt, "unit": "lineouts/s", "cores": cores, "kind": "port",
-                                    "sample": f"{nb} lineouts of the same workload, torch-f64 forward + autograd VJP (oracle/torch_oracle.py)"}
+                                    "sample": f"the first {nb} lineouts of the timed batch (seed 42), torch-f64 forward + autograd VJP "
+                                              f"(oracle/torch_oracle.py); --impl reference times the same sample per step"}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -9,8 +9,8 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
 def test_reference_arm_prints_one_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--ref-lineouts", "1"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-lineouts", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
@@ -23,6 +23,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "lineouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0
+    assert d["steps"] == 2 and d["warmup"] == 1                       # the arm honours the driver's --steps / --warmup
+    # same config dictionary as the GPU arm prints (bench.workload_config), so the driver's same_config check holds
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(16384, 1)
 
 
 def test_gpu_arm_refuses_without_a_device():
