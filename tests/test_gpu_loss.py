@@ -66,7 +66,7 @@ def test_loss_kernel_value_and_seed_vs_oracle(method):
     else:
         e = tq - dq * torch.log(torch.where(m, tq, torch.ones_like(tq)))
     (torch.where(m, e, torch.zeros_like(e)) * wq).sum().div(B).backward()
-    np.testing.assert_allclose(tbar.cpu().numpy(), tq.grad.numpy(), rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(tbar.cpu().numpy(), tq.grad.numpy(), rtol=1e-10, atol=1e-300)   # the kernel divides, autograd multiplies by a reciprocal
     assert float(tbar[:, :50].abs().max()) == 0.0
 
 

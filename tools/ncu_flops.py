@@ -91,7 +91,7 @@ def latest(rep, lineouts, source):
     for k in parse(rep):
         for key in ("k_direct_fwd", "k_direct_step", "k_pv_nodes", "k_direct_bwd_poles", "k_direct_prep"):
             if key in k["kernel"] and key not in out["kernels"]:
-                r = raw.get(k["kernel"], {})
+                r = next((v for n, v in raw.items() if key in n), {})
                 out["kernels"][key] = {
                     "name": k["kernel"].split("(")[0][-60:], "fp32_flop_per_lineout": k["fp32_flop"] / lineouts,
                     "fp64_flop_per_lineout": k["fp64_flop"] / lineouts, "mufu_per_lineout": k["mufu"] / lineouts,

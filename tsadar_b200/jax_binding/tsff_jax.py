@@ -19,6 +19,13 @@ except ImportError as e:  # pragma: no cover - JAX is absent where this reposito
     raise ImportError("tsadar_b200.jax_binding.tsff_jax needs jax/jaxlib (and libtsff_xla.so built from "
                       "tsff_xla_ffi.cc against jax.ffi.include_dir())") from e
 
+# Batching rule of every custom call: "broadcast_all" -- under jax.vmap (the reference vmaps its model over lineouts,
+# thomson_diagnostic.py:35-36) XLA passes operands with the mapped axis as an extra leading dimension (unmapped operands
+# broadcast to it) and the handlers of tsff_xla_ffi.cc fold all leading dimensions into the kernels' own batch axis B:
+# ONE launch for the whole vmapped batch.  ("sequential" would issue one FFI call per lineout and defeat the batched
+# kernels; "expand_dims" leaves unmapped operands with a leading 1, which the flat [B, ...] kernels cannot index.)
+_VMAP = "broadcast_all"
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _XLA_LIB = ctypes.CDLL(os.environ.get("TSFF_XLA_LIB", os.path.join(_HERE, "..", "_lib", "libtsff_xla.so")))
 for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffPvFwd", "TsffChi2vFwd", "TsffLossFwdBwd"):
@@ -29,7 +36,8 @@ def make_form_factor(ctx: int, B: int, W: int, V: int, NP: int, saved_bytes: int
     """-> f(params [B, NP] f64, fe [B, V]) = modl [B, W] f64, differentiable in both arguments.
     `ctx` = the integer value of a tsff_ctx* made with tsff_ctx_create (ctypes); saved_bytes / ws_bytes from
     tsff_ff_saved_bytes / tsff_ff_workspace_bytes for this batch size.  The lineout axis is the kernel's own batch axis, so
-    the reference's vmap over lineouts (thomson_diagnostic.py:35) is dropped."""
+    the reference's vmap over lineouts (thomson_diagnostic.py:35) can be dropped -- or kept: with B = 1 per call the
+    vmapped call arrives as ONE handler invocation with params [N, 1, NP] and runs as a batch of N (see _VMAP)."""
     cid = np.int64(ctx)
 
     @jax.custom_vjp
@@ -40,7 +48,7 @@ def make_form_factor(ctx: int, B: int, W: int, V: int, NP: int, saved_bytes: int
         modl, saved, _ = jax.ffi.ffi_call(
             "TsffFfFwd",
             (jax.ShapeDtypeStruct((B, W), jnp.float64), jax.ShapeDtypeStruct((saved_bytes,), jnp.uint8),
-             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, ctx=cid)
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method=_VMAP)(params, fe, ctx=cid)
         return modl, (params, fe, saved)
 
     def _bwd(res, modl_bar):
@@ -48,7 +56,7 @@ def make_form_factor(ctx: int, B: int, W: int, V: int, NP: int, saved_bytes: int
         pbar, fbar, _ = jax.ffi.ffi_call(
             "TsffFfBwd",
             (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct((B, V), fe.dtype),
-             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, saved, modl_bar, ctx=cid)
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method=_VMAP)(params, fe, saved, modl_bar, ctx=cid)
         return pbar, fbar
 
     ff.defvjp(_fwd, _bwd)
@@ -67,7 +75,7 @@ def make_form_factor_full(ctx: int, B: int, G: int, W: int, A: int, fe_shape, NP
         out, saved, _ = jax.ffi.ffi_call(
             "TsffFfFullFwd",
             (jax.ShapeDtypeStruct((B, G, W, A), jnp.float64), jax.ShapeDtypeStruct((saved_bytes,), jnp.uint8),
-             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, ctx=cid)
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method=_VMAP)(params, fe, ctx=cid)
         return out, (params, fe, saved)
 
     def _bwd(res, ff_bar):
@@ -75,7 +83,7 @@ def make_form_factor_full(ctx: int, B: int, G: int, W: int, A: int, fe_shape, NP
         pbar, fbar, _ = jax.ffi.ffi_call(
             "TsffFfFullBwd",
             (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct(tuple(fe_shape), fe.dtype),
-             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method="sequential")(params, fe, saved, ff_bar, ctx=cid)
+             jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method=_VMAP)(params, fe, saved, ff_bar, ctx=cid)
         return pbar, fbar
 
     ff.defvjp(_fwd, _bwd)
@@ -98,6 +106,6 @@ def calc_all_chi_vals(ctx: int, DF, beta, xie_mag, klde_mag):
     """FormFactor.calc_all_chi_vals (form_factor.py:390-447) on a TSFF_MODE_2V context -> (fe_vphi, chiEI, chiERrat), each
     shaped like beta.  Forward only: inside calc_in_2D the whole stage is one custom call with its own VJP."""
     P = int(np.prod(beta.shape))
-    chi = jax.ffi.ffi_call("TsffChi2vFwd", jax.ShapeDtypeStruct((3, P), jnp.float64), vmap_method="sequential")(
+    chi = jax.ffi.ffi_call("TsffChi2vFwd", jax.ShapeDtypeStruct((3, P), jnp.float64), vmap_method=_VMAP)(
         DF, beta.reshape(-1), xie_mag.reshape(-1), klde_mag.reshape(-1), ctx=np.int64(ctx))
     return chi[0].reshape(beta.shape), chi[1].reshape(beta.shape), chi[2].reshape(beta.shape)

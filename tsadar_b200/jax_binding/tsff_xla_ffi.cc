@@ -21,12 +21,21 @@ namespace {
 
 inline ffi::Error status(int rc) { return rc ? ffi::Error::Internal(tsff_last_error()) : ffi::Error::Success(); }
 inline int fe_dtype(const ffi::AnyBuffer& fe) { return fe.element_type() == ffi::F32 ? TSFF_F32 : TSFF_F64; }
+// Lineouts in the call.  The Python side registers every call with vmap_method="broadcast_all": under the reference's
+// vmap over lineouts (thomson_diagnostic.py:35-36) XLA hands the handler operands with extra LEADING batch dimensions
+// (params [N, B, NP], fe [N, B, V], ...).  All leading dimensions are folded into the kernel's own batch axis -- one launch
+// for the whole vmapped batch, never one call per lineout.  saved / ws arrive as [N, bytes(B)] >= bytes(N * B) (every
+// segment of the layout is 256-byte aligned, so N * align(x) >= align(N * x)) and are used as one flat buffer.
+inline int64_t lineouts(const ffi::Buffer<ffi::F64>& params) {
+  const auto d = params.dimensions();
+  return static_cast<int64_t>(params.element_count()) / d[d.size() - 1];
+}
 
 // FormFactor.__call__ + FitModel angle sum (form_factor.py:163-298, generate_spectra.py:164-165,193-197):
 // params [B, NP] f64, fe [B, V] f32|f64 -> modl [B, W] f64; saved / ws are result buffers sized by tsff_ff_*_bytes.
 ffi::Error FfFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe,
                  ffi::ResultBuffer<ffi::F64> modl, ffi::ResultBuffer<ffi::U8> saved, ffi::ResultBuffer<ffi::U8> ws) {
-  const int64_t B = params.dimensions()[0];
+  const int64_t B = lineouts(params);
   return status(tsff_ff_fwd(reinterpret_cast<tsff_ctx*>(ctx), B, params.typed_data(), fe.untyped_data(), fe_dtype(fe),
                             modl->typed_data(), nullptr, saved->typed_data(), ws->typed_data(), stream));
 }
@@ -34,7 +43,7 @@ ffi::Error FfFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params,
 // the same returning the full formfactor [B, G, W, A] (ARTS: the weight matrix product follows in JAX)
 ffi::Error FfFullFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe,
                      ffi::ResultBuffer<ffi::F64> ff, ffi::ResultBuffer<ffi::U8> saved, ffi::ResultBuffer<ffi::U8> ws) {
-  const int64_t B = params.dimensions()[0];
+  const int64_t B = lineouts(params);
   return status(tsff_ff_fwd(reinterpret_cast<tsff_ctx*>(ctx), B, params.typed_data(), fe.untyped_data(), fe_dtype(fe),
                             nullptr, ff->typed_data(), saved->typed_data(), ws->typed_data(), stream));
 }
@@ -43,7 +52,7 @@ ffi::Error FfFullFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> par
 ffi::Error FfBwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe, ffi::Buffer<ffi::U8> saved,
                  ffi::Buffer<ffi::F64> modl_bar, ffi::ResultBuffer<ffi::F64> params_bar, ffi::Result<ffi::AnyBuffer> fe_bar,
                  ffi::ResultBuffer<ffi::U8> ws) {
-  const int64_t B = params.dimensions()[0];
+  const int64_t B = lineouts(params);
   return status(tsff_ff_bwd(reinterpret_cast<tsff_ctx*>(ctx), B, params.typed_data(), fe.untyped_data(), fe_dtype(fe),
                             saved.typed_data(), modl_bar.typed_data(), nullptr, params_bar->typed_data(),
                             fe_bar->untyped_data(), ws->typed_data(), stream));
@@ -52,7 +61,7 @@ ffi::Error FfBwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params,
 ffi::Error FfFullBwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe,
                      ffi::Buffer<ffi::U8> saved, ffi::Buffer<ffi::F64> ff_bar, ffi::ResultBuffer<ffi::F64> params_bar,
                      ffi::Result<ffi::AnyBuffer> fe_bar, ffi::ResultBuffer<ffi::U8> ws) {
-  const int64_t B = params.dimensions()[0];
+  const int64_t B = lineouts(params);
   return status(tsff_ff_bwd(reinterpret_cast<tsff_ctx*>(ctx), B, params.typed_data(), fe.untyped_data(), fe_dtype(fe),
                             saved.typed_data(), nullptr, ff_bar.typed_data(), params_bar->typed_data(),
                             fe_bar->untyped_data(), ws->typed_data(), stream));
@@ -61,7 +70,8 @@ ffi::Error FfFullBwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> par
 // vmap(ratintn) on uniform nodes (ratintn.py:4-23): f [B, N], pole [B, P] -> out [B, P], dout_dpole [B, P]
 ffi::Error PvFwd(cudaStream_t stream, double z0, double h, ffi::Buffer<ffi::F64> f, ffi::Buffer<ffi::F64> pole,
                  ffi::ResultBuffer<ffi::F64> out, ffi::ResultBuffer<ffi::F64> dout, ffi::ResultBuffer<ffi::U8> ws) {
-  const int64_t B = f.dimensions()[0], N = f.dimensions()[1], P = pole.dimensions()[1];
+  const auto fd = f.dimensions(), pd = pole.dimensions();
+  const int64_t N = fd[fd.size() - 1], P = pd[pd.size() - 1], B = static_cast<int64_t>(f.element_count()) / N;   // leading dims folded
   return status(tsff_pv_fwd(B, N, P, f.typed_data(), z0, h, pole.typed_data(), out->typed_data(), dout->typed_data(),
                             TSFF_PV_FP32, ws->typed_data(), stream));
 }
@@ -78,8 +88,9 @@ ffi::Error Chi2vFwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> fe, 
 ffi::Error LossFwdBwd(cudaStream_t stream, double uncert, double scale, int64_t method, ffi::Buffer<ffi::F64> theory,
                       ffi::Buffer<ffi::F64> data, ffi::Buffer<ffi::F64> weight, ffi::ResultBuffer<ffi::F64> loss,
                       ffi::ResultBuffer<ffi::F64> theory_bar) {
-  const int64_t B = theory.dimensions()[0];
-  const int32_t n = static_cast<int32_t>(theory.dimensions()[1]);
+  const auto td = theory.dimensions();
+  const int32_t n = static_cast<int32_t>(td[td.size() - 1]);
+  const int64_t B = static_cast<int64_t>(theory.element_count()) / n;
   cudaError_t e = cudaMemsetAsync(loss->typed_data(), 0, sizeof(double), stream);   // the entry point accumulates
   if (e != cudaSuccess) return ffi::Error::Internal(cudaGetErrorString(e));
   return status(tsff_loss_fwd_bwd(B, n, theory.typed_data(), data.typed_data(), weight.typed_data(), uncert, scale,
