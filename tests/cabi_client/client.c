@@ -139,11 +139,13 @@ int main(int argc, char** argv) {
     printf("lineout %d: spectrum %.2e  fe_bar %.2e  params_bar", b, es, ef);
     if (!(es <= 1e-5) || !(ef <= 1e-4)) bad = 1;
     const int act[] = {TSFF_P_TE, TSFF_P_NE, TSFF_P_LAM, TSFF_P_ION0 + TSFF_ION_Z, TSFF_P_ION0 + TSFF_ION_TI};
+    double rmax = 0.0;   /* a gradient component is compared relative to its own size, floored at 1e-6 of the row's largest */
+    for (int k = 0; k < 5; k++) rmax = fmax(rmax, fabs(x_pbar[b * NP + act[k]]));
     for (int k = 0; k < 5; k++) {
       const double g = pbar[b * NP + act[k]], r = x_pbar[b * NP + act[k]];
-      const double e = fabs(g - r) / fabs(r);
+      const double e = fabs(g - r) / fmax(fabs(r), 1e-6 * rmax);
       printf(" %.1e", e);
-      if (!(e <= 1e-4)) bad = 1;
+      if (!(e <= 1e-4)) { bad = 1; printf(" [got %.6e, oracle %.6e]", g, r); }
     }
     printf("\n");
   }

@@ -21,7 +21,8 @@
 using namespace tsff;
 
 namespace {
-constexpr int kThreads2V = 1024;
+constexpr int kThreads2V = 1024;   // adjoint
+constexpr int kThreadsFwd2V = 1024; // forward
 
 struct Args2V {
   int W, A, G, nI, V, NP, P;       // P = G*W*A poles per parameter set
@@ -37,7 +38,8 @@ struct Args2V {
   double* chi_out;                            // [3][P]: fe_vphi, chiEI, chiERrat
   // backward
   const double* ff_bar;   // [B][G][W][A]
-  double* fe_bar;         // [B][V][V]   (atomically accumulated: zero it)
+  double* fe_bar;         // [B][V][V]
+  double* fe_part;        // [grid][V][V] per-CTA partial tables of the adjoint (workspace), summed in order by k_ff2v_reduce
   double* lgbar;          // [B][G][kLGDoubles] (atomically accumulated: zero it)
 };
 
@@ -72,20 +74,19 @@ __device__ __forceinline__ void hermite4(double q, double v0, double idv, int V,
 }
 
 // dynamic smem: f [V][V+1] | f1 [NG][V] | df [NG][V] | red [NG][8] | pole scalars [NG][8]
-template <int NGMAX>
-__global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long long b_lineout) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_ff2v_fwd(const Args2V a, long long b_lineout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int V = a.V, VP = V + 1;
   const int GS = (V + 31) / 32 * 32;           // threads per pole group
-  const int NG = kThreads2V / GS;              // poles in flight per CTA
+  const int NG = NT / GS;              // poles in flight per CTA
   double* sf = reinterpret_cast<double*>(smem_raw);
   double* sf1 = sf + (size_t)V * VP;
   double* sdf = sf1 + (size_t)NG * V;
   double* sred = sdf + (size_t)NG * V;         // [NG][8]
-  double* spol = sred + (size_t)NG * 8;        // [NG][8]: beta-cos, beta-sin, |xi|, valid
   __shared__ LG sL[8];                          // G <= 8 gradient points
   const double* fe = a.fe + b_lineout * (long long)V * V;
-  for (int i = threadIdx.x; i < V * V; i += kThreads2V) sf[(i / V) * VP + (i % V)] = fe[i];
+  for (int i = threadIdx.x; i < V * V; i += NT) sf[(i / V) * VP + (i % V)] = fe[i];
   if (threadIdx.x < a.G) {
     LG L;
     lg_zero(L);
@@ -142,6 +143,9 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_fwd(const Args2V a, long
       // the bank stride; every thread still sums all V points, only the order of the sum changes.
       int aoff = 0;
       if (fabs(cb - sb) < 0.75) aoff = fabs(2.0 * cb) >= fabs(2.0 * sb) ? tb : (tb == 0 ? 0 : V - tb);
+      // (a sliding 4x4 register window along the walk -- load only the entering row / column, ~5.7 instead of 16 LDS.64 per
+      // point -- was built and measured in round 2: at the 512 threads it needs for 128 registers it ran 39.1 ms against the
+      // 27.4 ms of this plain form: divergent shifts, 48 register moves per point and half the warps to hide latency)
       for (int it = 0; it < V; it++) {
         int aa = it + aoff;
         if (aa >= V) aa -= V;
@@ -242,32 +246,89 @@ __device__ __forceinline__ void hermite4d(double q, double v0, double idv, int V
 
 __device__ __forceinline__ void atomic_add_shared(double* addr, double v) { atomicAdd(addr, v); }
 
+// ---- FIXED-POINT accumulation in shared memory ------------------------------------------------------------------------
+// sm_100 has ONE native shared-memory atomic add, the 32-bit integer one (ATOMS.ADD); FP64, FP32 and 64-bit integer adds
+// on shared memory compile to compare-and-swap spin loops (ATOMS.CAST.SPIN, ~3x the shared-memory wavefronts).  A table
+// cell is therefore a fixed-point number in CARRY-SAVE form, two 32-bit words (L, H) with value = H * 2^24 + L: an addend
+// q (a signed integer, |q| < 2^51) is split into its low 24 bits (added to L) and the signed rest (added to H), both with
+// the non-returning form of the native atomic -- fire and forget, no dependent second add waiting on the first one's
+// return value.  L collects at most ~25 addends per pole and is normalised (carry moved into H) by a sweep of the CTA after
+// every batch of poles, long before its 8 bits of headroom (255 addends) run out; H holds |sum| / 2^24 < 2^31, i.e. sums up
+// to 2^55 units.  Integer addition is exact and associative, so the cell sums do not depend on the order in which the warps
+// arrive (deterministic).  The addend arrives as t = value * 2^E + 1.5 * 2^52 (round to nearest in the FMA / add that forms
+// it): for |value * 2^E| < 2^51 the low 52 mantissa bits of t hold 2^51 + q, so q = bits(t) - 0x4338000000000000 -- no
+// F2I conversion.
+constexpr double kFxMagic = 6755399441055744.0;   // 1.5 * 2^52
+constexpr int kFxDigit = 24;
+__device__ __forceinline__ long long fx_load(const unsigned int* cell) {
+  return (long long)(int)cell[1] * (1LL << kFxDigit) + (long long)cell[0];
+}
+__device__ __forceinline__ void fx_store(unsigned int* cell, long long v) {
+  cell[0] = (unsigned int)(v & ((1LL << kFxDigit) - 1));
+  cell[1] = (unsigned int)(int)(v >> kFxDigit);
+}
+// Out-of-grid points (a query outside the table in x or y) extrapolate the edge cell's cubic: their weights reach ~1e9 and
+// would eat the fixed-point range, and all of their taps land in the BAND of cells within three rows / columns of the table
+// edge (hermite4's clamped windows).  They are accumulated in FP64 (CAS adds, ~15 % of the points) in a compact copy of
+// that band: rows 0..2 and V-3..V-1 in full (6 V cells), then columns 0..2 and V-3..V-1 of the other rows.
+__device__ __forceinline__ int band_cells(int V) { return 12 * V - 36; }
+__device__ __forceinline__ int band_index(int r, int c, int V) {
+  if (r < 3) return r * V + c;
+  if (r >= V - 3) return (3 + r - (V - 3)) * V + c;
+  const int cc = c < 3 ? c : (c >= V - 3 ? 3 + c - (V - 3) : -1);
+  return cc < 0 ? -1 : 6 * V + (r - 3) * 6 + cc;
+}
+
+// Four fixed-point adds (carry-save form, see above): eight independent non-returning atomics.  t = value * 2^E + kFxMagic.
+__device__ __forceinline__ void fx_add4(unsigned int* c0, unsigned int* c1, unsigned int* c2, unsigned int* c3, double t0, double t1,
+                                        double t2, double t3) {
+  unsigned int* cell[4] = {c0, c1, c2, c3};
+  const double t[4] = {t0, t1, t2, t3};
+#pragma unroll
+  for (int n = 0; n < 4; n++) {
+    const long long q = __double_as_longlong(t[n]) - 0x4338000000000000LL;
+    atomicAdd(cell[n], (unsigned int)(q & ((1LL << kFxDigit) - 1)));
+    atomicAdd(cell[n] + 1, (unsigned int)(int)(q >> kFxDigit));
+  }
+}
+
 // One CTA works on kThreads2V / GS poles at a time (as the forward).  Per pole:
 //   f1 (saved by the forward) -> df; per-node PV weights Wt_i and dWt_i/dxi -> I, dI/dxi; thread 0 reverses the
 //   assembly -> Ibar, dfe_bar, fphi_bar, kinematic cotangents; df_bar -> f1_bar; then the rotate/project adjoint: every
-//   (a, b) point scatters f1_bar[b] dv wx wy into the CTA's private fbar (shared memory, FP64 CAS adds; a warp owns a
-//   column b and its lanes take points four nodes apart so that their 4x4 stencils barely collide) and gathers
-//   d f1[b] / d beta from f; finally the kinematics reverse (|xi|, beta -> parameters).
-// dynamic smem: f [V][V+1] | fbar [V][V+1] | 3 x [NG][V] | red [NG][16] | scal [NG][16]
+//   (a, b) point scatters f1_bar[b] dv wx wy into the CTA's private fbar in shared memory -- in-grid points into the
+//   64-bit fixed-point table (two native 32-bit atomics per tap, fx_add), out-of-grid points into the FP64 edge band (a warp
+//   owns a line of the mesh and its lanes take points four nodes apart so that their 4x4 stencils barely collide) -- and
+//   gathers d f1[b] / d beta from f; finally the kinematics reverse (|xi|, beta -> parameters).
+// Fixed-point scale: the table holds sums scaled by 2^E.  Per pole a cell gains at most ~1.7 max_b|f1_bar_b| dv from the
+// in-grid points (the |wx wy| of the ~16 mesh points whose stencils cover it sum to (int |w|)^2 = 1.64); kFxGrow = 26 is the
+// bound used.  E is chosen at the first batch of poles for kFxGrow * (poles of this CTA) * (first batch's max) with a
+// factor 4 to spare (table sums up to 2^54 units), which leaves ~2^-36 of a typical addend as the rounding unit; a running bound is kept, and should a
+// later batch exceed it (or bring addends >= 2^49 units) the whole table is shifted right first (rare, exact to one unit).
+// dynamic smem: f [V][V+1] f32 | fbar [V][V+1] int64 | 2 x [NG][V] f64 | band [12 V - 36] f64 | red [NG][16] | scal [NG][16]
 // WANT_PARAMS = false: no kinematic parameter is trainable (only the table is, as in the reference's arts-2d deck):
 // d f1 / d beta, the 2-vector kinematics reverse and the lineout-scalar cotangents are skipped.
+constexpr double kFxGrow = 26.0;
 template <bool WANT_PARAMS>
 __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long long b_lineout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int V = a.V, VP = V + 1;
   const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS, NWG = GS / 32;
   float* sf = reinterpret_cast<float*>(smem_raw);                 // f as FP32 (only d/dbeta reads it; 1e-4 is asked)
-  double* sfb = reinterpret_cast<double*>(smem_raw + (((size_t)V * VP * 4 + 15) / 16) * 16);
-  double* sA = sfb + (size_t)V * VP;           // [NG][V]: f1, later df_bar
+  unsigned int* sfx = reinterpret_cast<unsigned int*>(smem_raw + (((size_t)V * VP * 4 + 15) / 16) * 16);   // [V][VP] x (lo, hi)
+  double* sA = reinterpret_cast<double*>(sfx) + (size_t)V * VP;   // [NG][V]: f1, later df_bar
   double* sB = sA + (size_t)NG * V;            // [NG][V]: df, later f1_bar
-  double* sW = sB + (size_t)NG * V;            // [NG][V]: Wt
-  double* sred = sW + (size_t)NG * V;          // [NG][16]
+  double* sband = sB + (size_t)NG * V;         // [12 V - 36] out-of-grid contributions (FP64)
+  double* sred = sband + band_cells(V);        // [NG][16]
   double* ssc = sred + (size_t)NG * 16;        // [NG][16]
   __shared__ LG sL[8];
   __shared__ double sLb[8][kLGDoubles];
+  __shared__ double s_scale, s_bound;          // 2^E; running bound on |cell| in table units / 2^E
+  __shared__ int s_E, s_shift, s_have;
   const double* fe = a.fe + b_lineout * (long long)V * V;
-  for (int i = threadIdx.x; i < V * V; i += kThreads2V) sf[(i / V) * VP + (i % V)] = (float)fe[i];
-  for (int i = threadIdx.x; i < V * VP; i += kThreads2V) sfb[i] = 0.0;
+  if (WANT_PARAMS)
+    for (int i = threadIdx.x; i < V * V; i += kThreads2V) sf[(i / V) * VP + (i % V)] = (float)fe[i];
+  for (int i = threadIdx.x; i < 2 * V * VP; i += kThreads2V) sfx[i] = 0u;
+  for (int i = threadIdx.x; i < band_cells(V); i += kThreads2V) sband[i] = 0.0;
   for (int i = threadIdx.x; i < 8 * kLGDoubles; i += kThreads2V) (&sLb[0][0])[i] = 0.0;
   if (threadIdx.x < a.G) {
     LG L;
@@ -275,11 +336,14 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
     lg_forward(a.params + b_lineout * a.NP, a.nI, threadIdx.x, a.G, a.lam_shift, L);
     sL[threadIdx.x] = L;
   }
+  if (threadIdx.x == 0) { s_scale = 0.0; s_bound = 0.0; s_E = 0; s_shift = 0; s_have = 0; }
   __syncthreads();
   const int grp = threadIdx.x / GS, tb = threadIdx.x % GS, wg = tb >> 5, lane = tb & 31;
   const bool active_grp = grp < NG;
   const double idv = fast_rcp(a.dv), h = a.dv;
   const int WA = a.W * a.A, M = V - 2;
+  const double vlast = a.v0 + (double)(V - 1) * a.dv;
+  const long long nbatch_cta = (((long long)a.P + NG - 1) / NG - blockIdx.x + gridDim.x - 1) / gridDim.x;   // batches this CTA will see
 
   for (long long p0 = (long long)blockIdx.x * NG; p0 < a.P; p0 += (long long)gridDim.x * NG) {
     const long long p = p0 + grp;
@@ -316,9 +380,9 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
       sB[grp * V + tb] = tb == 0 ? (f1[1] - f1[0]) * idv : (tb == V - 1 ? (f1[V - 1] - f1[V - 2]) * idv : (f1[tb + 1] - f1[tb - 1]) * (0.5 * idv));
     }
     __syncthreads();
-    double tI = 0.0, tJ = 0.0;
+    double tI = 0.0, tJ = 0.0, wt = 0.0;        // wt: this thread's PV node weight (kept in a register until df_bar)
     if (valid && tb < V) {
-      double wt = 0.0, dwt = 0.0;
+      double dwt = 0.0;
       if (tb <= M) {
         const double gi = a.v0 + (double)tb * h - xmag;
         const double lc = log_abs(gi);
@@ -336,7 +400,6 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
           dwt = -(lp - 2.0 * lc + lm) * idv;
         }
       }
-      sW[grp * V + tb] = wt;
       tI = sB[grp * V + tb] * wt;
       tJ = sB[grp * V + tb] * dwt;
     }
@@ -381,12 +444,13 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
       Ibar = sc[0]; dfe_bar = sc[1]; fphi_bar = sc[2]; i_f = (int)sc[3]; t_f = sc[4];
     }
     if (valid && tb < V) {
-      double v = Ibar * sW[grp * V + tb];
+      double v = Ibar * wt;
       if (tb == i_f) v += (1.0 - t_f) * dfe_bar;
       if (tb == i_f + 1) v += t_f * dfe_bar;
       sA[grp * V + tb] = v;
     }
     __syncthreads();
+    double amax = 0.0;                           // max_b |f1_bar_b| dv of this group's pole (for the fixed-point bound)
     if (valid && tb < V) {
       const double* dfb = sA + grp * V;
       const int k = tb;
@@ -398,10 +462,57 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
       if (k == i_f) fb += (1.0 - t_f) * fphi_bar;
       if (k == i_f + 1) fb += t_f * fphi_bar;
       sB[grp * V + k] = fb;
+      amax = fabs(fb) * a.dv;
+      if (!(amax < 1e300)) amax = 0.0;           // NaN / inf cotangents propagate through the band-free FP64 flush below
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) sred[(threadIdx.x >> 5)] = amax;          // one slot per warp of the CTA (sred holds NG * 16 >= 32 doubles)
+    __syncthreads();
+    // ---- fixed-point scale for this batch (thread 0), table shift if the running bound would overflow
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int w = 0; w < kThreads2V / 32; w++) m = fmax(m, sred[w]);
+      int shift = 0;
+      if (m > 0.0) {
+        int em;
+        frexp(m, &em);                                       // m < 2^em
+        if (!s_have) {
+          int eb;
+          frexp(kFxGrow * (double)NG * m * (double)nbatch_cta * 4.0, &eb);
+          int E = 53 - eb;
+          if (E > 49 - em) E = 49 - em;
+          s_E = E; s_scale = ldexp(1.0, E); s_bound = 0.0; s_have = 1;
+        }
+        const double need = s_bound + kFxGrow * (double)NG * m;
+        int en;
+        frexp(need, &en);
+        int E = s_E;
+        if (en + E > 53) E = 53 - en;
+        if (em + E > 49) E = 49 - em;
+        shift = s_E - E;
+        if (shift > 0) { s_E = E; s_scale = ldexp(1.0, E); }
+        s_bound = need;
+      }
+      s_shift = shift;
     }
     __syncthreads();
+    if (s_shift > 0) {
+      const int sh = s_shift;
+      for (int i = threadIdx.x; i < V * VP; i += kThreads2V) {
+        long long v = fx_load(sfx + 2 * i);
+        v = sh >= 63 ? (v < 0 ? -1 : 0) : (v >> sh);
+        fx_store(sfx + 2 * i, v);
+      }
+      __syncthreads();
+    }
+    const double scale = s_scale;
     // ---- rotate/project adjoint: warp wg of the group owns lines o = wg, wg + NWG, ... of the mesh (columns b, or rows a),
-    //      lanes take the points 4 lane + c along the line
+    //      lanes take the points 4 lane + c along the line.
+    //      (Measured alternative, round 2: one thread per line walking it with a 4x4 accumulator window in registers and
+    //      flushing only the row / column that leaves the window -- ~11 instead of 32 atomics per point -- needs 128 registers,
+    //      i.e. 512 threads, and executes ~470 instructions per warp-step with the divergent shifts: 122 ms against the 104 ms
+    //      of this form at arts-2d, table-only.)
     double bbar = 0.0;
     if (valid) {
       // lanes step 4 nodes along a (address step 4 (cb VP + sb), i.e. 4 (cb + sb) banks since VP = 1 mod 16) or along b
@@ -426,33 +537,58 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
             hermite4(xq, a.v0, idv, V, ix, wx);
             hermite4(yq, a.v0, idv, V, iy, wy);
           }
-          const float* fb = sf + ix * VP + iy;
-          double* ob = sfb + ix * VP + iy;
-          double sx = 0.0, sy = 0.0;
+          const bool ingrid = xq >= a.v0 && xq <= vlast && yq >= a.v0 && yq <= vlast && wcol == wcol;
+          if (WANT_PARAMS) {
+            const float* fb = sf + ix * VP + iy;
+            double sx = 0.0, sy = 0.0;
 #pragma unroll
-          for (int m = 0; m < 4; m++) {
-            double r0 = 0.0, r1 = 0.0;
+            for (int m = 0; m < 4; m++) {
+              double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-            for (int n = 0; n < 4; n++) {
-              if (WANT_PARAMS) {
+              for (int n = 0; n < 4; n++) {
                 const double fv = (double)fb[m * VP + n];
                 r0 = fma(wy[n], fv, r0);
                 r1 = fma(dwy[n], fv, r1);
               }
-              const double wv = wcol * wx[m] * wy[n];
-              if (wv != 0.0) atomic_add_shared(ob + m * VP + n, wv);
-            }
-            if (WANT_PARAMS) {
               sx = fma(dwx[m], r0, sx);
               sy = fma(wx[m], r1, sy);
             }
+            // d xq / d beta = -yq, d yq / d beta = xq;  d/dxq = idv d/dt
+            bbar += wcol * (-yq * sx + xq * sy) * idv;
           }
-          // d xq / d beta = -yq, d yq / d beta = xq;  d/dxq = idv d/dt
-          if (WANT_PARAMS) bbar += wcol * (-yq * sx + xq * sy) * idv;
+          if (ingrid) {
+            // one DFMA per tap forms value * 2^E + magic; eight independent native atomics per stencil row
+            unsigned int* ob = sfx + 2 * (ix * VP + iy);
+            const double ws = wcol * scale;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+              const double wm = ws * wx[m];
+              unsigned int* r = ob + 2 * (m * VP);
+              fx_add4(r, r + 2, r + 4, r + 6, fma(wm, wy[0], kFxMagic), fma(wm, wy[1], kFxMagic), fma(wm, wy[2], kFxMagic),
+                      fma(wm, wy[3], kFxMagic));
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+#pragma unroll
+              for (int n = 0; n < 4; n++) {
+                const double wv = wcol * wx[m] * wy[n];
+                if (wv != 0.0) atomic_add_shared(sband + band_index(ix + m, iy + n, V), wv);
+              }
+            }
+          }
         }
       }
     }
     bbar = warp_sum(bbar);
+    __syncthreads();                                       // all adds of this batch are in; sred is reused below
+    for (int i = threadIdx.x; i < V * VP; i += kThreads2V) {   // carry-save normalisation: L's carry into H
+      const unsigned int L = sfx[2 * i];
+      if (L >> kFxDigit) {
+        sfx[2 * i] = L & ((1u << kFxDigit) - 1u);
+        sfx[2 * i + 1] += L >> kFxDigit;
+      }
+    }
     if (active_grp && lane == 0) sred[grp * 16 + wg] = bbar;
     __syncthreads();
     // ---- kinematics reverse for (|xi|, beta) and the rest of kb
@@ -501,16 +637,30 @@ __global__ void __launch_bounds__(kThreads2V, 1) k_ff2v_bwd(const Args2V a, long
     }
     __syncthreads();
   }
-  // ---- flush the CTA's private accumulators
-  double* feb = a.fe_bar + b_lineout * (long long)V * V;
+  // ---- flush: this CTA's table (fixed point -> FP64, plus the edge band) goes to ITS OWN slab of the workspace; the slabs
+  //      are summed in a fixed order by k_ff2v_reduce (no floating-point atomics across CTAs: deterministic)
+  double* part = a.fe_part + (long long)blockIdx.x * V * V;
+  const double inv_scale = s_have ? ldexp(1.0, -s_E) : 0.0;
   for (int i = threadIdx.x; i < V * V; i += kThreads2V) {
-    const double v = sfb[(i / V) * VP + (i % V)];
-    if (v != 0.0) atomicAdd(&feb[i], v);
+    const int r = i / V, c = i % V;
+    double v = (double)fx_load(sfx + 2 * (r * VP + c)) * inv_scale;
+    const int bi = band_index(r, c, V);
+    if (bi >= 0) v += sband[bi];
+    part[i] = v;
   }
   for (int i = threadIdx.x; i < a.G * kLGDoubles; i += kThreads2V) {
     const double v = sLb[i / kLGDoubles][i % kLGDoubles];
     if (v != 0.0) atomicAdd(&a.lgbar[(b_lineout * a.G) * kLGDoubles + i], v);
   }
+}
+
+// fe_bar[b][i] = sum over the CTAs' slabs, in CTA order
+__global__ void __launch_bounds__(256) k_ff2v_reduce(const double* part, int nparts, int n, double* out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < nparts; k++) s += part[(long long)k * n + i];
+  out[i] = s;
 }
 
 __global__ void k_ff2v_params_bar(const Args2V a, double* params_bar, int64_t B) {
@@ -530,7 +680,9 @@ __global__ void k_ff2v_params_bar(const Args2V a, double* params_bar, int64_t B)
 
 namespace tsff {
 size_t ff2v_saved_bytes(const tsff_ctx* c, int64_t B) { return align_up((size_t)B * c->G * c->W * c->A * c->V * 8); }
-size_t ff2v_ws_bytes(const tsff_ctx* c, int64_t B) { return align_up((size_t)B * c->G * kLGDoubles * 8); }
+size_t ff2v_ws_bytes(const tsff_ctx* c, int64_t B) {
+  return align_up((size_t)B * c->G * kLGDoubles * 8) + align_up((size_t)c->sm_count * c->V * c->V * 8);   // lgbar | per-CTA partial tables
+}
 
 int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, double* ff_out, void* saved, cudaStream_t st) {
   const int V = c->V;
@@ -544,13 +696,13 @@ int ff2v_fwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, dou
   a.cos_ud = cos(c->ud_angle_deg * kPi / 180.0); a.sin_ud = sin(c->ud_angle_deg * kPi / 180.0);
   a.omgs = c->omgs; a.costh = c->costh; a.sinth = c->sinth; a.zt = c->zt;
   a.params = params; a.fe = fe; a.ff = ff_out; a.f1save = static_cast<double*>(saved);
-  const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
+  const int GS = (V + 31) / 32 * 32, NG = kThreadsFwd2V / GS;
   const size_t smem = ((size_t)V * (V + 1) + (size_t)NG * V * 2 + (size_t)NG * 16) * 8;
-  TSFF_SMEM_OPTIN(k_ff2v_fwd<32>);
+  TSFF_SMEM_OPTIN(k_ff2v_fwd<kThreadsFwd2V>);
   const long long nbatch = ((long long)a.P + NG - 1) / NG;
   const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
   for (int64_t b = 0; b < B; b++) {
-    k_ff2v_fwd<32><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
+    k_ff2v_fwd<kThreadsFwd2V><<<grid, kThreadsFwd2V, smem, st>>>(a, (long long)b);
     TSFF_LAUNCH_OK("k_ff2v_fwd");
   }
   return TSFF_OK;
@@ -567,12 +719,12 @@ int chi2v_fwd(tsff_ctx* c, const double* fe, const double* beta, const double* x
   a.W = 1; a.A = 1; a.G = 0; a.nI = c->I; a.V = V; a.NP = c->NP; a.P = (int)P;
   a.v0 = c->v0; a.dv = c->dv; a.zt = c->zt;
   a.fe = fe; a.beta_in = beta; a.xie_in = xie_mag; a.klde_in = klde_mag; a.chi_out = chi_out;
-  const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
+  const int GS = (V + 31) / 32 * 32, NG = kThreadsFwd2V / GS;
   const size_t smem = ((size_t)V * (V + 1) + (size_t)NG * V * 2 + (size_t)NG * 16) * 8;
-  TSFF_SMEM_OPTIN(k_ff2v_fwd<32>);
+  TSFF_SMEM_OPTIN(k_ff2v_fwd<kThreadsFwd2V>);
   const long long nbatch = ((long long)a.P + NG - 1) / NG;
   const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
-  k_ff2v_fwd<32><<<grid, kThreads2V, smem, st>>>(a, 0LL);
+  k_ff2v_fwd<kThreadsFwd2V><<<grid, kThreadsFwd2V, smem, st>>>(a, 0LL);
   TSFF_LAUNCH_OK("k_ff2v_fwd (chi)");
   return TSFF_OK;
 }
@@ -590,18 +742,20 @@ int ff2v_bwd(tsff_ctx* c, int64_t B, const double* params, const double* fe, con
   a.omgs = c->omgs; a.costh = c->costh; a.sinth = c->sinth; a.zt = c->zt;
   a.params = params; a.fe = fe; a.f1save = const_cast<double*>(static_cast<const double*>(saved));
   a.ff_bar = ff_bar; a.fe_bar = fe_bar; a.lgbar = static_cast<double*>(ws);
-  TSFF_CUDA_OK(cudaMemsetAsync(fe_bar, 0, (size_t)B * V * V * 8, st));
+  a.fe_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)B * c->G * kLGDoubles * 8));
   TSFF_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)B * c->G * kLGDoubles * 8, st));
   const int GS = (V + 31) / 32 * 32, NG = kThreads2V / GS;
-  const size_t smem = (((size_t)V * (V + 1) * 4 + 15) / 16) * 16 + ((size_t)V * (V + 1) + (size_t)NG * V * 3 + (size_t)NG * 32) * 8;
+  const size_t smem = (((size_t)V * (V + 1) * 4 + 15) / 16) * 16 + ((size_t)V * (V + 1) + (size_t)NG * V * 2 + (size_t)(12 * V - 36) + (size_t)NG * 32) * 8;
   TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));
-  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));  // 225 KB at V = 128
+  TSFF_CUDA_OK(cudaFuncSetAttribute(k_ff2v_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 228 * 1024 - 4096));  // 224 KB at V = 128
   const long long nbatch = ((long long)a.P + NG - 1) / NG;
   const unsigned grid = (unsigned)(nbatch < c->sm_count ? nbatch : c->sm_count);
   for (int64_t b = 0; b < B; b++) {
     if (params_bar) k_ff2v_bwd<true><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
     else k_ff2v_bwd<false><<<grid, kThreads2V, smem, st>>>(a, (long long)b);
     TSFF_LAUNCH_OK("k_ff2v_bwd");
+    k_ff2v_reduce<<<(unsigned)((V * V + 255) / 256), 256, 0, st>>>(a.fe_part, (int)grid, V * V, fe_bar + b * (long long)V * V);
+    TSFF_LAUNCH_OK("k_ff2v_reduce");
   }
   if (params_bar) {
     k_ff2v_params_bar<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(a, params_bar, B);
