@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import np_oracle as O
+from oracle import np_oracle as O, torch_oracle as TO
 
 pytestmark = pytest.mark.gpu
 
@@ -249,3 +249,106 @@ def test_chi2v_needs_2v_context():
     assert rc != 0
     with pytest.raises(RuntimeError, match="2V"):
         _ffi.check(rc)
+
+
+def _arts2d_deck(npts):
+    """The arts-2d deck (tests/configs/arts2v_test_defaults + arts2d_test_inputs): SphericalHarmonics table on 128 x 128."""
+    import os
+    from oracle import params_oracle as P
+    from tests.common import load_cfg
+    cfg = load_cfg("cfg_arts2v")
+    cfg["other"]["lamrangE"] = [cfg["data"]["fit_rng"]["forward_epw_start"], cfg["data"]["fit_rng"]["forward_epw_end"]]
+    cfg["other"]["npts"] = npts
+    p = P.thomson_params(cfg["parameters"], activate=False)
+    return cfg, p
+
+
+@pytest.mark.gpu
+def test_arts2d_deck_full_shape_pole_sample_vs_oracle(monkeypatch):
+    """BASELINE.json configs[3] at its OWN shape: V = 128 table (the deck's SphericalHarmonics f), W = 1024 wavelengths x 241
+    angles = 246 784 poles.  The oracle (4.0e9 bicubic interpolations in NumPy) cannot do the whole image, so a random
+    sample of 256 of the deck's own (beta, |xi|, k lambda_De) poles is checked: (i) tsff_chi2v_fwd (boundary B2, the kernel
+    the full forward runs) against the oracle's per-pole calc_chi_vals (form_factor.py:349-388) at 1e-9; (ii) the full
+    tsff_ff_fwd image at those poles against the oracle's kinematics + assembly fed with the oracle's chi at 1e-9."""
+    from tsadar_b200.engine import FormFactorEngine
+    cfg, p = _arts2d_deck(1024)
+    vx, DF = np.asarray(p["electron"]["v"], dtype=np.float64), np.asarray(p["electron"]["fe"], dtype=np.float64)
+    assert DF.shape == (128, 128)
+    sa = np.arange(19, 139.5, 0.5)
+    gen = cfg["parameters"]["general"]
+    ud_ang, va_ang = gen.get("ud", {}).get("angle", 0.0), gen.get("Va", {}).get("angle", 0.0)
+    grids = O.Grids(cfg["other"]["lamrangE"], 1024)
+    lam_shift = cfg["data"]["ele_lam_shift"]
+    # the oracle's pole set for the whole image: form_factor_2d with the per-pole chi stubbed out (kinematics only)
+    real_chi = O.calc_chi_vals_2d
+    monkeypatch.setattr(O, "calc_chi_vals_2d", lambda vx_, DF_, b, x, k: (0.0, 0.0, 0.0, None))
+    _, _, parts = O.form_factor_2d(p, grids, sa, 1, lam_shift, ud_ang, va_ang, return_parts=True)
+    monkeypatch.setattr(O, "calc_chi_vals_2d", real_chi)
+    beta, xmag, klde = parts["beta"], parts["xie_mag"], parts["kin"]["klde"] * np.ones_like(parts["beta"])
+    assert beta.shape == (1, 1024, 241)
+    rng = np.random.default_rng(11)
+    flat = rng.choice(beta.size, 256, replace=False)
+    eng = FormFactorEngine(cfg["other"]["lamrangE"], 1024, lam_shift, sa, np.ones(241), 1, 1, vx, mode="2v", ud_ang=ud_ang, va_ang=va_ang)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), device="cuda")
+    # (i) the chi kernel on the sampled poles
+    fphi, chiEI, chiER = eng.chi_vals_2v(t(DF), t(beta.ravel()[flat]), t(xmag.ravel()[flat]), t(klde.ravel()[flat]))
+    ref = np.array([real_chi(vx, DF, beta.ravel()[i], xmag.ravel()[i], klde.ravel()[i])[:3] for i in flat])
+    for got, want, name in ((fphi, ref[:, 0], "fe_vphi"), (chiEI, ref[:, 1], "chiEI"), (chiER, ref[:, 2], "chiERrat")):
+        e = np.max(np.abs(got.cpu().numpy() - want)) / np.max(np.abs(want))
+        assert e <= 1e-9, (name, e)
+    # (ii) the full image: the oracle's assembly with the oracle's chi at the sampled poles (the kernel's own chi elsewhere,
+    # so that the vectorised oracle assembly can run on the whole grid)
+    fa, ca, cr = eng.chi_vals_2v(t(DF), t(beta), t(xmag), t(klde))
+    fe_vphi, chiE = fa.cpu().numpy().copy(), (cr.cpu().numpy() + 1j * ca.cpu().numpy())
+    fe_vphi.ravel()[flat] = ref[:, 0]
+    chiE.ravel()[flat] = ref[:, 2] + 1j * ref[:, 1]
+    want_ff, _ = O._assemble(parts["kin"], chiE, parts["chiI"], fe_vphi, grids)
+    row = np.array([[p["electron"]["Te"], p["electron"]["ne"], p["general"]["lam"], p["general"]["Va"], p["general"]["ud"],
+                     p["general"]["ne_gradient"], p["general"]["Te_gradient"], p["general"]["amp1"], p["general"]["amp2"], p["general"]["amp3"],
+                     p["ion-1"]["A"], p["ion-1"]["Z"], p["ion-1"]["Ti"], p["ion-1"]["fract"]]], dtype=np.float64)
+    _, ff, _ = eng.forward(t(row), t(DF[None]), want_ff=True)
+    got_ff = ff.cpu().numpy()[0]
+    e = np.max(np.abs(got_ff.ravel()[flat] - want_ff.ravel()[flat])) / np.max(np.abs(want_ff.ravel()[flat]))
+    print(f"arts-2d full shape, 256 sampled poles: formfactor max|diff|/max {e:.2e}")
+    assert e <= 1e-9, e
+
+
+@pytest.mark.gpu
+def test_calc_in_2D_vjp_full_size_table_vs_oracle_autograd():
+    """V = 128 (the arts-2d table: the adjoint's 224 KB shared-memory layout, fixed-point table + edge band) against the
+    ORACLE's autograd (torch float64 restatement of calc_in_2D, bicubic taps and all): fe_bar at 1e-9 of its max norm,
+    parameters at 1e-4.  The run is repeated: the interior of fe_bar must be bit-identical (integer accumulation)."""
+    from tsadar_b200.engine import FormFactorEngine
+    V, W = 128, 3
+    vx = _grid(V)
+    dv = vx[1] - vx[0]
+    X, Y = np.meshgrid(vx, vx, indexing="ij")
+    DF = np.exp(-0.5 * (X**2 + 1.3 * Y**2)) * (1 + 0.1 * X)
+    DF = np.clip(DF, 1e-30, None)
+    DF = DF / DF.sum() / dv**2
+    sa = np.array([60.0, 120.0])
+    row = np.array([0.8, 0.3, 526.5, 0.3, 0.2, 0.0, 0.0, 1, 1, 1, 40.0, 8.0, 0.2, 1.0])
+    eng = FormFactorEngine((450.0, 600.0), W, 0.0, sa, np.ones(2), 1, 1, vx, mode="2v", ud_ang=20.0, va_ang=70.0)
+    pt, ft = torch.tensor(row[None], device="cuda"), torch.tensor(DF[None], device="cuda")
+    _, ff, saved = eng.forward(pt, ft, want_ff=True)
+    grids = O.Grids([450.0, 600.0], W)
+    leaves, po = TO.params_from_block(row, 1)
+    fo = torch.tensor(DF, requires_grad=True)
+    ffo = TO.form_factor_2d(po, fo, vx, grids, sa, 1, 0.0, ud_ang=20.0, va_ang=70.0)
+    assert np.abs(ff.cpu().numpy()[0] - ffo.detach().numpy()).max() / np.abs(ffo.detach().numpy()).max() < 1e-10
+    cot = np.random.default_rng(0).normal(size=tuple(ffo.shape)) / float(ffo.detach().abs().max())
+    (ffo * torch.tensor(cot)).sum().backward()
+    gp, gf = leaves.grad.numpy(), fo.grad.numpy()
+    pb, fb = eng.backward(pt, ft, saved, ff_bar=torch.tensor(cot[None], device="cuda"))
+    pb, fb1 = pb.cpu().numpy()[0], fb.clone()
+    e = np.abs(fb1.cpu().numpy()[0] - gf).max() / np.abs(gf).max()
+    print(f"V = 128 fe_bar vs oracle autograd: {e:.2e}")
+    assert e < 1e-9, e
+    inner = np.abs(gf[3:-3, 3:-3]).max()
+    assert np.abs(fb1.cpu().numpy()[0][3:-3, 3:-3] - gf[3:-3, 3:-3]).max() / inner < 1e-9       # and on the interior's own scale
+    for k in [0, 1, 2, 3, 4, 11, 12, 13]:
+        assert abs(pb[k] - gp[k]) <= 1e-4 * max(abs(gp[k]), 1e-8 * np.abs(gp).max()), (k, pb[k], gp[k])
+    _, fb2 = eng.backward(pt, ft, saved, ff_bar=torch.tensor(cot[None], device="cuda"))
+    assert torch.equal(fb2[0, 3:-3, 3:-3], fb1[0, 3:-3, 3:-3])                                 # deterministic interior
+    _, fb3 = eng.backward(pt, ft, saved, ff_bar=torch.tensor(cot[None], device="cuda"), want_params=False)
+    assert torch.equal(fb3[0, 3:-3, 3:-3], fb1[0, 3:-3, 3:-3])

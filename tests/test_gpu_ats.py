@@ -92,6 +92,26 @@ def test_arts1v_diagnostic_forward_matches_oracle():
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
 
 
+def test_arts1v_diagnostic_full_deck_shape_matches_oracle():
+    """The arts-1d deck at its OWN shape (BASELINE.json configs[2]; tests/test_forward/test_angular_1v.py): npts = 2048
+    wavelengths x 241 angles = 493 568 (omega, angle) points, [1024, 241] weight matrix, ATS IRF on the [1024, 2048] image,
+    reduction to resolution units -- the whole diagnostic against the NumPy oracle."""
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg, sa, batch = _arts_setup(2048)
+    p = P.thomson_params(cfg["parameters"], activate=True)
+    ref, lamb, modl_ref = O.diagnostic_arts(p, cfg, sa, batch)
+    ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=sa)
+    ts_params = ThomsonParams(cfg["parameters"], num_params=1, batch=False, activate=True)
+    ThryE, ThryI, lamE, _ = ts_diag(ts_params, batch)
+    got = ThryE.detach().cpu().numpy()
+    assert got.shape == ref.shape == (cfg["data"]["lineouts"]["end"] - cfg["data"]["lineouts"]["start"], 1024)
+    np.testing.assert_allclose(lamE, lamb, rtol=1e-13)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"arts-1d full shape: max|diff|/max {err:.2e}")
+    assert err < 1e-5
+
+
 def test_arts1v_loss_gradient_matches_oracle():
     """d loss / d (Te, ne, amp1, amp2, lam) through weights-GEMM -> ATS IRF -> reduction, vs torch autograd of the oracle."""
     from tsadar_b200.generate_spectra import FitModel
