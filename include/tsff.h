@@ -187,6 +187,17 @@ int tsff_ats_fwd(const tsff_ats_cfg* cfg, const double* modl, const double* para
 int tsff_ats_bwd(const tsff_ats_cfg* cfg, const double* params, const double* e_amps, const void* saved,
                  const double* thry_bar, double* modl_bar, double* amp_bar, void* ws, void* stream);
 
+/* ---- a7 (ARTS): angular weighting of FitModel.electron_spectrum, spectype "angular_full" -------------------------------- */
+/* replaces  modlE = jnp.matmul(weights, mean(formfactor, axis=0).T) * iaw_filter   (generate_spectra.py:193-197, 210-216):
+ *   ff [G][W][A] (one parameter set, as tsff_ff_fwd's ff_out with B = 1), weights [NA][A] (DEVICE: the [1024, 241] matrix
+ *   angleWghtsFredfine), jmul [W] (DEVICE, the static IAW-filter multiplier, or NULL)  ->  modl [NA][W].
+ * Hand-written FP64 tiled contraction (no cuBLAS); deterministic. */
+int tsff_arts_weights_fwd(const double* ff, int32_t G, int32_t W, int32_t A, const double* weights, int32_t NA,
+                          const double* jmul, double* modl, void* stream);
+/* VJP: modl_bar [NA][W] -> ff_bar [G][W][A] (overwritten) */
+int tsff_arts_weights_bwd(const double* modl_bar, int32_t G, int32_t W, int32_t A, const double* weights, int32_t NA,
+                          const double* jmul, double* ff_bar, void* stream);
+
 /* ---- B5: loss -------------------------------------------------------------------------------------------------- */
 /* replaces LossFunction.calc_ei_error + loss_functionals (loss_function.py:190-267, 386-418) and the seed of the
  * reverse pass: loss += scale * sum_{b,q} weight[q] * err(data, theory), theory_bar = d loss / d theory.

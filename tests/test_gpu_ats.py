@@ -132,8 +132,9 @@ def test_arts1v_loss_gradient_matches_oracle():
     fet = torch.tensor(fe[None], device="cuda", requires_grad=True)
     eng = fm.electron_form_factor.engine(vx, 1)
     ff = form_factor_full(eng, block, fet)[0]
-    wm = torch.tensor(sa["weights"], device="cuda")
-    modlE = torch.matmul(wm, ff.mean(0).t()) * torch.tensor(fm._jmulE, device="cuda")
+    from tsadar_b200.generate_spectra import arts_weights
+    wm = torch.tensor(sa["weights"], device="cuda").contiguous()
+    modlE = arts_weights(ff, wm, torch.tensor(fm._jmulE, device="cuda"))          # tsff_arts_weights_fwd / _bwd
     st = AtsStage(cfg, sa, oth["lamrangE"], oth["npts"], 64)
     thry = st(modlE, block, torch.ones(st.nrows, dtype=torch.float64, device="cuda"))
     cot = rng.normal(size=tuple(thry.shape))
@@ -153,3 +154,26 @@ def test_arts1v_loss_gradient_matches_oracle():
         assert abs(gb[k] - gp[k]) <= 1e-4 * abs(gp[k]), (k, gb[k], gp[k])
     gf = feo.grad.numpy()
     assert np.abs(fet.grad.cpu().numpy()[0] - gf).max() / np.abs(gf).max() < 1e-4
+
+
+@pytest.mark.parametrize("G,W,A,NA", [(1, 2048, 241, 1024), (3, 301, 241, 1024), (2, 65, 17, 130)])
+def test_arts_weight_contraction_kernel_vs_numpy(G, W, A, NA):
+    """tsff_arts_weights_fwd / _bwd (generate_spectra.py:193-197, 210-216: mean over gradient points, weights @ ThryE.T, IAW
+    filter) against the same arithmetic in NumPy float64 at 1e-12, forward and VJP, full arts-1d shape and ragged shapes."""
+    from tsadar_b200.generate_spectra import arts_weights
+    rng = np.random.default_rng(G + W)
+    ff = rng.uniform(0.1, 2.0, (G, W, A)) * np.exp(rng.normal(size=(1, W, 1)))
+    wm = rng.uniform(0.0, 1.0, (NA, A)) * (rng.uniform(size=(NA, A)) < 0.3)            # sparse-ish, like the FRED weight matrix
+    jm = np.where(rng.uniform(size=W) < 0.1, 1e-4, 1.0)
+    cot = rng.normal(size=(NA, W))
+    fft = torch.tensor(ff, device="cuda", requires_grad=True)
+    out = arts_weights(fft, torch.tensor(wm, device="cuda"), torch.tensor(jm, device="cuda"))
+    ref = (wm @ ff.mean(0).T) * jm
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    (out * torch.tensor(cot, device="cuda")).sum().backward()
+    gref = np.broadcast_to(((cot * jm).T @ wm) / G, (G, W, A))
+    assert np.abs(fft.grad.cpu().numpy() - gref).max() <= 1e-12 * np.abs(gref).max()
+    out2 = arts_weights(fft.detach(), torch.tensor(wm, device="cuda"), None)               # no filter
+    ref2 = wm @ ff.mean(0).T
+    assert np.abs(out2.cpu().numpy() - ref2).max() <= 1e-12 * np.abs(ref2).max()
+    assert torch.equal(out2, arts_weights(fft.detach(), torch.tensor(wm, device="cuda"), None))   # deterministic

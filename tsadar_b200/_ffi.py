@@ -21,6 +21,7 @@ EXPORTS = [
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
     "tsff_ats_saved_bytes", "tsff_ats_workspace_bytes", "tsff_ats_fwd", "tsff_ats_bwd",
+    "tsff_arts_weights_fwd", "tsff_arts_weights_bwd",
 ]
 
 
@@ -112,6 +113,10 @@ def lib():
     L.tsff_ats_fwd.restype = C.c_int
     L.tsff_ats_bwd.argtypes = [C.POINTER(AtsCfg), dp, dp, vp, dp, dp, dp, vp, vp]
     L.tsff_ats_bwd.restype = C.c_int
+    L.tsff_arts_weights_fwd.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, dp, C.c_int32, dp, dp, vp]
+    L.tsff_arts_weights_fwd.restype = C.c_int
+    L.tsff_arts_weights_bwd.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, dp, C.c_int32, dp, dp, vp]
+    L.tsff_arts_weights_bwd.restype = C.c_int
     L.tsff_loss_fwd_bwd.argtypes = [i64, C.c_int32, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, vp]
     L.tsff_loss_fwd_bwd.restype = C.c_int
     _lib = L

@@ -1,14 +1,49 @@
 """FitModel -- mirror of tsadar.core.physics.generate_spectra.FitModel (generate_spectra.py:8-220) for 1V distributions.
 Temporal / imaging / 1d spectypes: the mean over gradient points, the weighted angle sum and the IAW filter are fused
 into the form-factor kernel (`modl` output of tsff_ff_fwd).  "angular_full" (ARTS): the kernel returns the full
-formfactor [G, W, A]; the angular weight matrix product (generate_spectra.py:194-195) is a plain FP64 GEMM (cuBLAS via
-torch.matmul) followed by the IAW filter."""
+formfactor [G, W, A]; the mean over gradient points, the angular weight matrix product (generate_spectra.py:193-197) and
+the IAW filter (:210-216) are one hand-written FP64 tiled contraction, tsff_arts_weights_fwd / _bwd (csrc/tsff_arts.cu)."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
+from . import _ffi
 from .form_factor import FormFactor, pack_params
+
+
+class _ArtsWeights(torch.autograd.Function):
+    """modlE [NA, W] = jmul * (weights [NA, A] @ mean_g(ff [G, W, A]).T)  -- tsff_arts_weights_fwd, VJP tsff_arts_weights_bwd."""
+
+    @staticmethod
+    def forward(ctx, ff, wmat, jmul):
+        if not ff.is_cuda:
+            raise RuntimeError("tsadar_b200 has no CPU path")
+        ff = ff.contiguous()
+        G, W, A = ff.shape
+        NA = wmat.shape[0]
+        out = torch.empty((NA, W), dtype=torch.float64, device=ff.device)
+        st = torch.cuda.current_stream(ff.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_arts_weights_fwd(ff.data_ptr(), G, W, A, wmat.data_ptr(), NA,
+                                                    jmul.data_ptr() if jmul is not None else None, out.data_ptr(), st))
+        ctx.shape = (G, W, A)
+        ctx.wmat, ctx.jmul = wmat, jmul
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        G, W, A = ctx.shape
+        g = g.contiguous()
+        ffb = torch.empty((G, W, A), dtype=torch.float64, device=g.device)
+        st = torch.cuda.current_stream(g.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_arts_weights_bwd(g.data_ptr(), G, W, A, ctx.wmat.data_ptr(), ctx.wmat.shape[0],
+                                                    ctx.jmul.data_ptr() if ctx.jmul is not None else None, ffb.data_ptr(), st))
+        return ffb, None, None
+
+
+def arts_weights(ff, wmat, jmul=None):
+    """ff [G, W, A] float64 cuda, wmat [NA, A], jmul [W] or None (both float64 cuda, contiguous) -> modlE [NA, W]."""
+    return _ArtsWeights.apply(ff, wmat, jmul)
 
 
 class FitModel:
@@ -71,17 +106,18 @@ class FitModel:
                 assert ff.shape[0] == 1, "angular_full takes a single parameter set (thomson_diagnostic.py:37-38)"
                 ff = ff[0]
             dev = ff.device
-            ThryE = ff.mean(dim=0)                                               # generate_spectra.py:193
             wm = getattr(self, "_wmat_dev", None)
             if wm is None or wm.device != dev:
-                wm = self._wmat_dev = torch.tensor(self._wmat, dtype=torch.float64, device=dev)
+                wm = self._wmat_dev = torch.tensor(self._wmat, dtype=torch.float64, device=dev).contiguous()
             jm = self._jmulE
             if self.w_shard is not None:                                         # this rank's wavelengths, halo dropped
-                ThryE = ThryE[: self.w_shard.keep]
+                ff = ff[:, : self.w_shard.keep]
                 jm = None if jm is None else jm[self.w_shard.j0:self.w_shard.j1]
-            modlE = torch.matmul(wm, ThryE.t())                                  # :194-195  [1024, W]
-            if jm is not None:
-                modlE = modlE * torch.tensor(jm, dtype=torch.float64, device=dev)   # :210-216
+            jkey = None if jm is None else (self.w_shard.j0 if self.w_shard is not None else 0)
+            if jm is not None and (getattr(self, "_jm_dev", None) is None or self._jm_key != (jkey, dev)):
+                self._jm_dev, self._jm_key = torch.tensor(np.ascontiguousarray(jm), dtype=torch.float64, device=dev), (jkey, dev)
+            # mean over gradient points (:193), weights @ ThryE.T (:194-195), IAW filter (:210-216): one kernel
+            modlE = arts_weights(ff, wm, self._jm_dev if jm is not None else None)
             if self.w_shard is not None:
                 from .parallel import gather_columns
                 modlE = gather_columns(modlE.contiguous(), self.w_shard.npts, self.w_shard.group)
