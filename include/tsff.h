@@ -29,6 +29,7 @@ extern "C" {
 
 #define TSFF_ABI_VERSION 3
 #define TSFF_MAX_IONS 4
+#define TSFF_MAX_LEAVES 24 /* 10 + 3 * TSFF_MAX_IONS + 1, rounded up */
 
 enum {
   TSFF_OK = 0,
@@ -205,6 +206,34 @@ int tsff_arts_weights_bwd(const double* modl_bar, int32_t G, int32_t W, int32_t 
  * method: 0 l2, 1 l1, 2 log-cosh, 3 poisson.  *loss_out (device scalar) is ACCUMULATED into: zero it first. */
 int tsff_loss_fwd_bwd(int64_t B, int32_t n, const double* theory, const double* data, const double* weight,
                       double uncert, double scale, int method, double* loss_out, double* theory_bar, void* stream);
+
+/* ---- N1 / N3: parameter transforms, DLM1V producer, optimiser update (the stages either side of the path on a fit step) -- */
+/* replaces ThomsonParams.__call__ (ts_params.py:583-603; ElectronParams :202-218, IonParams :308-326, GeneralParams :459-495,
+ * ion-fraction renormalisation and tied Ti :543-563) fused with DLM1V.__call__ (distribution_functions/base.py:277-294).
+ * Leaf columns, NL = 10 + 3 I + 1:  Te ne | lam Va ud ne_gradient Te_gradient amp1 amp2 amp3 | per ion: Z Ti fract | m.
+ * active_slot[k] >= 0: leaf k is trainable, its normalised value is x_active[b][slot] and physical = sigmoid(x) scale + shift
+ * (ts_params.py:93-104, 329-350); otherwise its value is x_static[b][k] and physical = x scale + shift.
+ * f table: f_vx_m [nm][V] (DEVICE, row i = the projected super-Gaussian of order m0 + i dm on the lineout's velocity grid);
+ * fe = lerp in m (+ m_offset), normalised to sum fe dv = 1.  nm == 1: a fixed table (Maxwellian), no m leaf; V == 0: no fe. */
+typedef struct tsff_params_cfg {
+  int32_t I, V, nm, fe_dtype, NLA, reserved;
+  double dv, m_offset, m0, dm;
+  int32_t active_slot[TSFF_MAX_LEAVES];
+  double scale[TSFF_MAX_LEAVES], shift[TSFF_MAX_LEAVES];
+  double ionA[TSFF_MAX_IONS];       /* atomic masses (static in the reference, ts_params.py:290-298) */
+  int32_t ti_same[TSFF_MAX_IONS];   /* 1: Ti tied to ion-1's (ts_params.py:555-557) */
+  const double* f_vx_m;             /* DEVICE [nm][V] */
+} tsff_params_cfg;
+/* x_active [B][NLA], x_static [B][NL]  ->  params [B][NP] (physical block of tsff_ff_fwd), fe [B][V] (fe_dtype) or NULL */
+int tsff_params_fwd(const tsff_params_cfg* cfg, int64_t B, const double* x_active, const double* x_static, double* params,
+                    void* fe, void* stream);
+/* VJP: params_bar [B][NP], fe_bar [B][V] or NULL  ->  x_active_bar [B][NLA] (overwritten) */
+int tsff_params_bwd(const tsff_params_cfg* cfg, int64_t B, const double* x_active, const double* x_static,
+                    const double* params_bar, const void* fe_bar, double* x_active_bar, void* stream);
+/* replaces optax.adam(learning_rate).update + apply_updates (inverse/loops.py:87-89, 239-241) for all lineouts in one launch:
+ * x, grad, mu, nu [B][n_active]; count [B] = steps taken so far per lineout (device; advanced by the call). */
+int tsff_adam_step(int64_t B, int32_t n_active, double* x, const double* grad, double* mu, double* nu, double* count,
+                   double lr, double b1, double b2, double eps, void* stream);
 
 /* ---- microbenchmarks used for the roofline denominators --------------------------------- */
 /* runs `iters` dependent-chain FFMA (kind 0) or MUFU.LG2 (kind 1) per thread on the whole device; returns the

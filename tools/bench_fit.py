@@ -28,6 +28,19 @@ for graphed in (False, True):
         torch.cuda.synchronize(); dt = min(dt, time.perf_counter() - t0)
     print(f"B={B} {'CUDA graph' if graphed else 'eager     '}: {dt / N * 1e3:7.3f} ms/step ({N} adam steps, loss {hist[0]:.4e} -> {hist[-1]:.4e})")
 
+# ---- fused path: params kernel + adam kernel (tsff_params_fwd/_bwd, tsff_adam_step), one CUDA graph per step
+from tsadar_b200.ts_params import FusedThomsonParams
+from tsadar_b200.fit import fused_adam_fit
+closure = lambda p: loss_fn.calc_loss(p, batch_t)[0]
+fused_adam_fit(closure, FusedThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True), 0.01, 5)
+dt = 1e30
+for _ in range(3):
+    fz = FusedThomsonParams(copy.deepcopy(cfg["parameters"]), num_params=B, batch=True, activate=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    hist = fused_adam_fit(closure, fz, 0.01, N)
+    torch.cuda.synchronize(); dt = min(dt, time.perf_counter() - t0)
+print(f"B={B} fused kernels + CUDA graph: {dt / N * 1e3:7.3f} ms/step ({N} adam steps, loss {hist[0]:.4e} -> {hist[-1]:.4e})")
+
 # ---- the reference's default optimiser: L-BFGS-B through SciPy, eager vs graphed function evaluations
 from tsadar_b200.fit import scipy_fit
 for graphed in (False, True):

@@ -21,7 +21,7 @@ EXPORTS = [
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
     "tsff_ats_saved_bytes", "tsff_ats_workspace_bytes", "tsff_ats_fwd", "tsff_ats_bwd",
-    "tsff_arts_weights_fwd", "tsff_arts_weights_bwd",
+    "tsff_arts_weights_fwd", "tsff_arts_weights_bwd", "tsff_params_fwd", "tsff_params_bwd", "tsff_adam_step",
 ]
 
 
@@ -54,6 +54,18 @@ class AtsCfg(C.Structure):
         ("ang_t0", C.c_int32), ("ang_t1", C.c_int32), ("lam_t0", C.c_int32), ("lam_t1", C.c_int32),
         ("lam_min", C.c_double), ("lam_max", C.c_double),
         ("taps_ang", C.c_void_p), ("taps_lam", C.c_void_p),
+    ]
+
+
+MAX_LEAVES, MAX_IONS = 24, 4
+
+
+class ParamsCfg(C.Structure):
+    _fields_ = [
+        ("I", C.c_int32), ("V", C.c_int32), ("nm", C.c_int32), ("fe_dtype", C.c_int32), ("NLA", C.c_int32), ("reserved", C.c_int32),
+        ("dv", C.c_double), ("m_offset", C.c_double), ("m0", C.c_double), ("dm", C.c_double),
+        ("active_slot", C.c_int32 * MAX_LEAVES), ("scale", C.c_double * MAX_LEAVES), ("shift", C.c_double * MAX_LEAVES),
+        ("ionA", C.c_double * MAX_IONS), ("ti_same", C.c_int32 * MAX_IONS), ("f_vx_m", C.c_void_p),
     ]
 
 
@@ -117,6 +129,12 @@ def lib():
     L.tsff_arts_weights_fwd.restype = C.c_int
     L.tsff_arts_weights_bwd.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, dp, C.c_int32, dp, dp, vp]
     L.tsff_arts_weights_bwd.restype = C.c_int
+    L.tsff_params_fwd.argtypes = [C.POINTER(ParamsCfg), i64, dp, dp, dp, vp, vp]
+    L.tsff_params_fwd.restype = C.c_int
+    L.tsff_params_bwd.argtypes = [C.POINTER(ParamsCfg), i64, dp, dp, dp, vp, dp, vp]
+    L.tsff_params_bwd.restype = C.c_int
+    L.tsff_adam_step.argtypes = [i64, C.c_int32, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
+    L.tsff_adam_step.restype = C.c_int
     L.tsff_loss_fwd_bwd.argtypes = [i64, C.c_int32, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, vp]
     L.tsff_loss_fwd_bwd.restype = C.c_int
     _lib = L

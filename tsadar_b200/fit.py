@@ -217,3 +217,60 @@ def _adam_fit_graphed(loss_closure, ts_params, learning_rate, num_steps, b1, b2,
     for _ in range(num_steps):
         graph.replay()
     return hist[:num_steps].cpu().numpy()
+
+
+def fused_adam_fit(loss_closure, ts_params, learning_rate, num_steps, b1=0.9, b2=0.999, eps=1e-8, cuda_graph=True):
+    """adam_fit for a FusedThomsonParams: per step ONE launch turns the normalised leaves into the
+    parameter block and the f tables (tsff_params_fwd), the form factor / IRF / loss kernels and their adjoints run, ONE
+    launch reverses the transforms (tsff_params_bwd) and ONE launch applies optax.adam to every active leaf of every lineout
+    (tsff_adam_step, step counters on the device) -- captured as one CUDA graph.  -> loss history [num_steps] (numpy)."""
+    from . import _ffi
+    x = ts_params.x
+    B, n = x.shape
+    dev = x.device
+    mu, nu = torch.zeros_like(x), torch.zeros_like(x)
+    count = torch.zeros(B, dtype=torch.float64, device=dev)
+    n_warm = 3
+    hist = torch.zeros(max(num_steps, n_warm), dtype=torch.float64, device=dev)
+    slot = torch.zeros((), dtype=torch.long, device=dev)
+
+    def one_step():
+        loss = loss_closure(ts_params)
+        (g,) = torch.autograd.grad(loss, [x])
+        with torch.no_grad():
+            hist.index_put_((slot,), loss.detach())
+            slot.add_(1)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _ffi.check(_ffi.lib().tsff_adam_step(B, n, x.data_ptr(), g.contiguous().data_ptr(), mu.data_ptr(), nu.data_ptr(), count.data_ptr(),
+                                                 float(learning_rate), b1, b2, eps, st))
+
+    if not cuda_graph:
+        for _ in range(num_steps):
+            one_step()
+        return hist[:num_steps].cpu().numpy()
+    keep = x.detach().clone()
+
+    def reset():
+        with torch.no_grad():
+            x.copy_(keep)
+            mu.zero_(); nu.zero_(); count.zero_(); slot.zero_(); hist.zero_()
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    try:
+        with torch.cuda.stream(side):
+            for _ in range(n_warm):
+                one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+    finally:
+        reset()
+    graph = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.graph(graph):
+            one_step()
+    finally:
+        reset()
+    for _ in range(num_steps):
+        graph.replay()
+    return hist[:num_steps].cpu().numpy()

@@ -19,6 +19,8 @@ C_CM = 2.99792458e10
 
 def pack_params(params, device):
     """nested dict -> (block [B, NP] float64, fe [B, V], vx numpy [V], batched?)"""
+    if "_packed" in params:            # FusedThomsonParams: the block and the table come out of tsff_params_fwd already packed
+        return params["_packed"]
     ions = sorted([k for k in params if k.startswith("ion-")], key=lambda s: int(s.split("-")[1]))
     ele, gen = params["electron"], params["general"]
 

@@ -182,3 +182,118 @@ class ThomsonParams:
                     fitted[k][k2] = param_dict[k][k2]
                     num_params += 1
         return fitted, num_params
+
+
+# ---- fused path: the transforms + the DLM1V producer as ONE kernel each way ----------------------
+class _ParamsFn(torch.autograd.Function):
+    """(x_active [B, NLA]) -> (params block [B, NP], fe [B, V]) through tsff_params_fwd; VJP tsff_params_bwd."""
+
+    @staticmethod
+    def forward(ctx, xa, owner):
+        from . import _ffi
+        B = xa.shape[0]
+        block = torch.empty((B, owner.NP), dtype=DT, device=xa.device)
+        fe = torch.empty((B, owner.V), dtype=owner.fe_dtype, device=xa.device)
+        st = torch.cuda.current_stream(xa.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_params_fwd(owner._cfg_ref(), B, xa.data_ptr(), owner.x_static.data_ptr(), block.data_ptr(),
+                                              fe.data_ptr(), st))
+        ctx.owner = owner
+        ctx.save_for_backward(xa)
+        return block, fe
+
+    @staticmethod
+    def backward(ctx, block_bar, fe_bar):
+        from . import _ffi
+        (xa,) = ctx.saved_tensors
+        owner = ctx.owner
+        B = xa.shape[0]
+        if block_bar is None:
+            block_bar = torch.zeros((B, owner.NP), dtype=DT, device=xa.device)
+        out = torch.empty_like(xa)
+        st = torch.cuda.current_stream(xa.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_params_bwd(owner._cfg_ref(), B, xa.data_ptr(), owner.x_static.data_ptr(),
+                                              block_bar.contiguous().data_ptr(),
+                                              fe_bar.contiguous().data_ptr() if fe_bar is not None else None, out.data_ptr(), st))
+        return out, None
+
+
+class FusedThomsonParams:
+    """ThomsonParams for the 1-D DLM / Maxwellian decks with every per-step stage on the device in two launches:
+    `__call__` = tsff_params_fwd (de-normalisation of all leaves, ion-fraction renormalisation, DLM table lerp in m and
+    normalisation), its reverse = tsff_params_bwd.  All trainable leaves of all lineouts live in ONE tensor `x` [B, NLA]
+    (column order `active_names`), which is what the fused optimiser update (tsff_adam_step, fit.fused_adam_fit) advances.
+    Values are identical to ThomsonParams (tests/test_gpu_params_kernels.py).  The returned dict carries the standard entries
+    (views of the block) and the pre-packed operands of the form-factor call, so nothing is re-stacked downstream."""
+
+    def __init__(self, param_cfg, num_params, batch=True, activate=False, device=None, dlm_m_offset=0.0, fe_dtype=torch.float64):
+        import ctypes as C
+        from . import _ffi
+        ref = ThomsonParams(param_cfg, num_params, batch=batch, activate=activate, device=device, dlm_m_offset=dlm_m_offset)
+        if ref.dist is not None or ref.fe_dim != 1:
+            raise NotImplementedError("FusedThomsonParams covers the DLM and Maxwellian 1-D distributions; use ThomsonParams for the others")
+        self.param_cfg, self.B, self.device, self.ions = param_cfg, ref.B, ref.device, ref.ions
+        self.vx, self.dv, self.fe_type, self.fe_dim, self.fe_dtype = ref.vx, ref.dv, ref.fe_type, 1, fe_dtype
+        I = len(self.ions)
+        self.NP, self.V = _ffi.P_ION0 + _ffi.ION_STRIDE * I, int(self.vx.size)
+        keys = [("electron", "Te"), ("electron", "ne")] + [("general", k) for k in ["lam", "Va", "ud", "ne_gradient", "Te_gradient", "amp1", "amp2", "amp3"]]
+        for ion in self.ions:
+            keys += [(ion, "Z"), (ion, "Ti"), (ion, "fract")]
+        has_m = self.fe_type == "dlm"
+        keys.append(("electron", "m"))
+        self.NL = len(keys)
+        cfg = _ffi.ParamsCfg()
+        cfg.I, cfg.V, cfg.fe_dtype = I, self.V, (_ffi.TSFF_F32 if fe_dtype == torch.float32 else _ffi.TSFF_F64)
+        cfg.dv, cfg.m_offset = float(self.dv), float(dlm_m_offset)
+        xs = torch.zeros((self.B, self.NL), dtype=DT, device=self.device)
+        cols, self.active_names = [], []
+        for k, key in enumerate(keys):
+            s = ref.leaves.get(key)
+            cfg.active_slot[k], cfg.scale[k], cfg.shift[k] = -1, 1.0, 0.0
+            if s is None:
+                continue
+            cfg.scale[k], cfg.shift[k] = float(s.scale), float(s.shift)
+            if s.active:
+                cfg.active_slot[k] = len(cols)
+                cols.append(s.value.detach())
+                self.active_names.append(key)
+            else:
+                xs[:, k] = s.value.detach()
+        cfg.NLA = len(cols)
+        for i, ion in enumerate(self.ions):
+            cfg.ionA[i] = float(param_cfg[ion]["A"]["val"])
+            cfg.ti_same[i] = int(bool(i > 0 and param_cfg[ion]["Ti"].get("same", False)))
+        if has_m:
+            self._tab = ref.f_vx_m.t().contiguous()                   # [31][V]
+            cfg.nm, cfg.m0, cfg.dm = int(ref.m_ax.numel()), float(ref.m_ax[0]), float(ref.m_ax[1] - ref.m_ax[0])
+        else:
+            self._tab = (ref.f_fixed * 1.0).reshape(1, -1).contiguous()
+            cfg.nm, cfg.m0, cfg.dm = 1, 0.0, 1.0
+        cfg.f_vx_m = self._tab.data_ptr()
+        self._cfg, self._C = cfg, C
+        self.x_static = xs
+        self.x = (torch.stack(cols, dim=1).contiguous() if cols else torch.zeros((self.B, 0), dtype=DT, device=self.device)).requires_grad_(bool(cols))
+        self.NLA = cfg.NLA
+        self._keys = keys
+
+    def _cfg_ref(self):
+        return self._C.byref(self._cfg)
+
+    def parameters(self):
+        return [self.x] if self.NLA else []
+
+    def physical(self):
+        """-> (block [B, NP], fe [B, V]), differentiable with respect to `x`."""
+        return _ParamsFn.apply(self.x, self)
+
+    def __call__(self):
+        from . import _ffi
+        block, fe = self.physical()
+        out = {"electron": {"Te": block[:, _ffi.P_TE], "ne": block[:, _ffi.P_NE], "fe": fe, "v": np.broadcast_to(self.vx, (self.B, self.vx.size))},
+               "general": {"lam": block[:, _ffi.P_LAM], "Va": block[:, _ffi.P_VA], "ud": block[:, _ffi.P_UD], "ne_gradient": block[:, _ffi.P_NE_GRAD],
+                           "Te_gradient": block[:, _ffi.P_TE_GRAD], "amp1": block[:, _ffi.P_AMP1], "amp2": block[:, _ffi.P_AMP2],
+                           "amp3": block[:, _ffi.P_AMP3]}}
+        for i, ion in enumerate(self.ions):
+            o = _ffi.P_ION0 + _ffi.ION_STRIDE * i
+            out[ion] = {"A": block[:, o + _ffi.ION_A], "Z": block[:, o + _ffi.ION_Z], "Ti": block[:, o + _ffi.ION_TI], "fract": block[:, o + _ffi.ION_FRACT]}
+        out["_packed"] = (block, fe, self.vx, True, len(self.ions))
+        return out
