@@ -252,7 +252,7 @@ def main():
         numa_cpus = bind_to_gpu_numa_node(local)
 
     # ---- inputs (pinned host copies for the e2e leg, resident device copies for the kernel leg)
-    params_h, fe_h, vx, _ = make_lineouts(B, seed=42 + rank)
+    params_h, fe_h, vx, m_syn = make_lineouts(B, seed=42 + rank)
     NP = params_h.shape[1]
     eng = FormFactorEngine(LAM_RANGE, W_SYN, 0.0, SA_SYN, np.array([1.0]), 1, 1, vx, mode="direct")
     params_pin = torch.from_numpy(params_h).pin_memory()
@@ -323,13 +323,36 @@ def main():
     got = {"modl": last["modl"][par_idx].cpu().numpy(), "pbar": pbar[par_idx].cpu().numpy(),
            "fbar": fbar[par_idx].double().cpu().numpy(), "target": target[par_idx].cpu().numpy()} if rank == 0 else None
 
-    # ---- leg 2: end to end through the C ABI with HOST buffers: every step copies params + fe from pinned host memory and
-    # reads loss, params_bar AND fe_bar back.  The batch is cut into chunks that alternate between two streams (each with
-    # its own engine = its own scratch), so the copies of one chunk overlap the kernels of the other; the scalar loss is
-    # all-reduced every step.
+    # ---- leg 2: end to end with HOST buffers, two entries:
+    #  "params" (the line's `e2e`): where the reference's public call enters -- LossFunction.vg_loss(weights, batch)
+    #      (loss_function.py:149-168): the normalised trainable leaves [B, 6] and the data batch [B, 1024] come from pinned
+    #      host memory every step; tsff_params_fwd produces the parameter block and the f tables ON THE DEVICE (ThomsonParams
+    #      + DLM1V), then form factor -> loss -> adjoint -> tsff_params_bwd; loss and d loss / d leaves go back to the host.
+    #  "raw" (`e2e_raw_tables`): the raw operands of tsff_ff_fwd / _bwd -- params [B, 14] + fe [B, 4096] f32 in; loss,
+    #      params_bar AND fe_bar out.
+    # The batch is cut into chunks that alternate between two streams (each with its own engine = its own scratch), so the
+    # copies of one chunk overlap the kernels of the other; the scalar loss is all-reduced every step.
+    from tsadar_b200 import _ffi
+    from tsadar_b200.ts_params import FusedThomsonParams
     NCH = int(os.environ.get("TSFF_E2E_CHUNKS", "2"))   # measured on B200: 2 chunks 1.69M, 4 chunks 1.61M, 8 chunks 1.48M lineouts/s
     NCH = NCH if B % NCH == 0 and B >= 64 else 1
     Bc = B // NCH
+    # the producer side: the reference's 1d deck (tests/golden/cfg_1d.json = tests/configs/1d-*.yaml) on the 4096-node grid; the
+    # active leaves (Te, ne, lam, amp1, amp2, m: those of test_1d_random.py) are set so that the physical values are the
+    # synthetic lineouts' own
+    par = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg_1d.json")))["parameters"]
+    par["electron"]["fe"]["nvx"] = V_SYN
+    fz = FusedThomsonParams(par, num_params=B, batch=True, activate=True, fe_dtype=torch.float32)
+    phys = {("electron", "Te"): params_h[:, 0], ("electron", "ne"): params_h[:, 1], ("general", "lam"): params_h[:, 2],
+            ("general", "amp1"): params_h[:, 7], ("general", "amp2"): params_h[:, 8], ("electron", "m"): m_syn}
+    x_h = np.zeros((B, fz.NLA))
+    for k, name in enumerate(fz.active_names):
+        lo, sc = float(fz._cfg.shift[fz._keys.index(name)]), float(fz._cfg.scale[fz._keys.index(name)])
+        u = (phys[name] - lo) / sc
+        x_h[:, k] = np.log(u / (1.0 - u))
+    x_pin = torch.from_numpy(x_h).pin_memory()
+    xbar_pin = torch.empty_like(x_pin).pin_memory()
+    tgt_pin = target.cpu().pin_memory()
     pbar_pin = torch.empty_like(params_pin).pin_memory()
     fbar_pin = torch.empty_like(fe_pin).pin_memory()
     loss_pin = torch.zeros(NCH, dtype=torch.float64).pin_memory()
@@ -341,61 +364,81 @@ def main():
         ch.append(dict(p=torch.empty((Bc, NP), dtype=torch.float64, device=dev), f=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev),
                        saved=torch.empty(eng.saved_bytes(Bc), dtype=torch.uint8, device=dev), pbar=torch.empty((Bc, NP), dtype=torch.float64, device=dev),
                        fbar=torch.empty((Bc, V_SYN), dtype=fe_d.dtype, device=dev),
+                       xa=torch.empty((Bc, fz.NLA), dtype=torch.float64, device=dev), xab=torch.empty((Bc, fz.NLA), dtype=torch.float64, device=dev),
+                       xs=fz.x_static[c * Bc:(c + 1) * Bc].contiguous(), tg=torch.empty((Bc, W_SYN), dtype=torch.float64, device=dev),
                        loss=[torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)],   # double-buffered by step parity
                        loss_ev=[torch.cuda.Event() for _ in range(2)],
                        tgt=target[c * Bc:(c + 1) * Bc].contiguous()))
     red_done = [torch.cuda.Event() for _ in range(2)]
     e2e_count = [0]
+    L = _ffi.lib()
 
-    def step_e2e():
-        par = e2e_count[0] & 1
+    def step_e2e(entry):
+        par_ = e2e_count[0] & 1
         e2e_count[0] += 1
         for c in range(NCH):
             st, e, k = streams[c % 2], engs[c % 2], ch[c]
+            sl = slice(c * Bc, (c + 1) * Bc)
             with torch.cuda.stream(st):
-                k["p"].copy_(params_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
-                k["f"].copy_(fe_pin[c * Bc:(c + 1) * Bc], non_blocking=True)
+                if entry == "params":
+                    k["xa"].copy_(x_pin[sl], non_blocking=True)
+                    k["tg"].copy_(tgt_pin[sl], non_blocking=True)
+                    _ffi.check(L.tsff_params_fwd(fz._cfg_ref(), Bc, k["xa"].data_ptr(), k["xs"].data_ptr(), k["p"].data_ptr(), k["f"].data_ptr(),
+                                                 st.cuda_stream))
+                    tg = k["tg"]
+                else:
+                    k["p"].copy_(params_pin[sl], non_blocking=True)
+                    k["f"].copy_(fe_pin[sl], non_blocking=True)
+                    tg = k["tgt"]
                 modl, _, _ = e.forward(k["p"], k["f"], saved=k["saved"])
                 if world > 1 and e2e_count[0] > 2:
-                    st.wait_event(red_done[par])          # the reduce that read this loss slot two steps ago
-                _, tbar = loss_fwd_bwd(modl, k["tgt"], wq, unc, scale, "l2", loss_out=k["loss"][par], want_grad=True)
-                k["loss_ev"][par].record(st)
+                    st.wait_event(red_done[par_])          # the reduce that read this loss slot two steps ago
+                _, tbar = loss_fwd_bwd(modl, tg, wq, unc, scale, "l2", loss_out=k["loss"][par_], want_grad=True)
+                k["loss_ev"][par_].record(st)
                 e.backward(k["p"], k["f"], k["saved"], modl_bar=tbar, params_bar=k["pbar"], fe_bar=k["fbar"])
-                pbar_pin[c * Bc:(c + 1) * Bc].copy_(k["pbar"], non_blocking=True)
-                fbar_pin[c * Bc:(c + 1) * Bc].copy_(k["fbar"], non_blocking=True)
+                if entry == "params":
+                    _ffi.check(L.tsff_params_bwd(fz._cfg_ref(), Bc, k["xa"].data_ptr(), k["xs"].data_ptr(), k["pbar"].data_ptr(),
+                                                 k["fbar"].data_ptr(), k["xab"].data_ptr(), st.cuda_stream))
+                    xbar_pin[sl].copy_(k["xab"], non_blocking=True)
+                else:
+                    pbar_pin[sl].copy_(k["pbar"], non_blocking=True)
+                    fbar_pin[sl].copy_(k["fbar"], non_blocking=True)
                 if world == 1:
-                    loss_pin[c:c + 1].copy_(k["loss"][par], non_blocking=True)
+                    loss_pin[c:c + 1].copy_(k["loss"][par_], non_blocking=True)
         if world > 1:
             # the scalar loss of the sharded batch: ONE all-reduce per step, issued on the last chunk's stream as soon as both
             # chunks' loss kernels are done; the other stream runs on into the next step's copies
             st = streams[(NCH - 1) % 2]
             with torch.cuda.stream(st):
                 for c in range(NCH - 1):
-                    st.wait_event(ch[c]["loss_ev"][par])
-                torch.add(ch[0]["loss"][par], ch[-1]["loss"][par] if NCH > 1 else 0.0, out=loss_tot[par])
+                    st.wait_event(ch[c]["loss_ev"][par_])
+                torch.add(ch[0]["loss"][par_], ch[-1]["loss"][par_] if NCH > 1 else 0.0, out=loss_tot[par_])
                 for c in range(1, NCH - 1):
-                    loss_tot[par].add_(ch[c]["loss"][par])
-                dist.all_reduce(loss_tot[par])
-                loss_pin[:1].copy_(loss_tot[par], non_blocking=True)
-                red_done[par].record(st)
+                    loss_tot[par_].add_(ch[c]["loss"][par_])
+                dist.all_reduce(loss_tot[par_])
+                loss_pin[:1].copy_(loss_tot[par_], non_blocking=True)
+                red_done[par_].record(st)
 
-    def e2e_region(nsteps):
+    def e2e_region(nsteps, entry):
         cur = torch.cuda.current_stream(dev)
         for st in streams:
             st.wait_stream(cur)
         for _ in range(nsteps):
-            step_e2e()
+            step_e2e(entry)
         for st in streams:
             cur.wait_stream(st)
 
-    e2e_region(2)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    e2e_region(K)
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e = {}
+    for entry in ("params", "raw"):
+        e2e_count[0] = 0
+        e2e_region(2, entry)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        e2e_region(K, entry)
+        e3.record()
+        barrier()
+        ms_e2e[entry] = e2.elapsed_time(e3)
     clocks = clk.stop(local) if clk else None
 
     # ---- leg 3: sustained -- the device-resident step back to back for >= 2 s, its own clock record
@@ -413,10 +456,10 @@ def main():
         ms_sus = s0.elapsed_time(s1)
         sustained = {"steps": n_sus, "ms": ms_sus, "clocks": clk2.stop(local) if clk2 else None}
 
-    t = torch.tensor([ms_total, ms_e2e, tf, tb, sustained["ms"] if sustained else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e["params"], ms_e2e["raw"], tf, tb, sustained["ms"] if sustained else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, tf, tb, ms_sus = [float(x) for x in t.cpu()]
+    ms_total, ms_e2e_p, ms_e2e_r, tf, tb, ms_sus = [float(x) for x in t.cpu()]
 
     # ---- the reference's named decks (every rank takes part: arts-2d is wavelength-sharded over the ranks)
     configs = None
@@ -433,7 +476,6 @@ def main():
         mufu_peak = microbench(1)   # MUFU op/s
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         value = B * world * K / (ms_total * 1e-3)
-        e2e_val = B * world * K / (ms_e2e * 1e-3)
         pairs = B * PAIRS_PER_LINEOUT
         peak_tf = 2 * ffma_peak / 1e12
         nominal_tf = n_sm * 128 * 2 * 1.965e9 / 1e12
@@ -448,8 +490,18 @@ def main():
         except Exception:
             pass
         alg_bytes = B * (V_SYN * 4 + W_SYN * 8 * 2 + NP * 8)
-        h2d = int(params_pin.numel() * 8 + fe_pin.numel() * 4)
-        d2h = int(pbar_pin.numel() * 8 + fbar_pin.numel() * 4 + 8 * NCH)
+        def e2e_block(ms, h2d, d2h, entry):
+            return {"value": B * world * K / (ms * 1e-3), "unit": "lineouts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms / K, "h2d_gbs_per_gpu": h2d / (ms / K * 1e-3) / 1e9,
+                    "bound": "host<->device copies" if ms > 1.03 * ms_total else "kernels (copies hidden)", "entry": entry,
+                    "pipeline": f"{NCH} chunks alternating on 2 streams; loss all-reduced every step",
+                    "host_cpus_bound_to_gpu_numa_node": numa_cpus}
+        e2e = e2e_block(ms_e2e_p, x_pin.numel() * 8 + tgt_pin.numel() * 8, xbar_pin.numel() * 8 + 8 * NCH,
+                        "LossFunction.vg_loss-style: normalised leaves [B,6] f64 + data batch [B,1024] f64 in (pinned host); "
+                        "tsff_params_fwd (ThomsonParams + DLM1V on the device) -> ff fwd -> loss -> ff bwd -> tsff_params_bwd; "
+                        "loss + d loss / d leaves [B,6] out")
+        e2e_raw = e2e_block(ms_e2e_r, params_pin.numel() * 8 + fe_pin.numel() * 4, pbar_pin.numel() * 8 + fbar_pin.numel() * 4 + 8 * NCH,
+                            "raw C-ABI operands: params [B,14] f64 + fe [B,4096] f32 in; loss, params_bar, fe_bar out")
         roofline = {
             "bound": "fp32", "kernel": "k_direct_fwd<2,float,FP32,3> (pole sweep: I and dI/dxi, block-multipole form)",
             "achieved": kf["fp32_tflops"] if kf else None, "peak": peak_tf, "unit": "TFLOP/s", "frac": kf["frac"] if kf else None,
@@ -479,12 +531,7 @@ def main():
             "steps": K, "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 PV sweeps / f64 assembly", "data": "synthetic",
             "config": workload_config(B, world),
-            "e2e": {"value": e2e_val, "unit": "lineouts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / K, "h2d_gbs_per_gpu": h2d / (ms_e2e / K * 1e-3) / 1e9,
-                    "bound": "host<->device copies (pinned H2D of the f tables)" if ms_e2e > 1.03 * ms_total else "kernels (copies hidden)",
-                    "entry": "raw C-ABI operands: params [B,14] f64 + fe [B,4096] f32 in; loss, params_bar, fe_bar out",
-                    "pipeline": f"{NCH} chunks alternating on 2 streams; loss all-reduced every step",
-                    "host_cpus_bound_to_gpu_numa_node": numa_cpus},
+            "e2e": e2e, "e2e_raw_tables": e2e_raw,
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": roofline,
