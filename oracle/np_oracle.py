@@ -569,6 +569,30 @@ def diagnostic_arts(params, cfg, sa, batch, mode="table"):
     return ThryE + np.asarray(batch["noise_e"]), lamE, modlE
 
 
+def rotate_pixels(A, theta):
+    """vector_tools.rotate (tsadar/utils/vector_tools.py:94-138): bilinear rotation of a table about its centre on the pixel
+    grid, as the multiplexed-shot loss applies to f(vx, vy) (loss_function.py:291-293).  `jnp.asarray(., dtype=int)` truncates
+    toward zero, `% 1` is the floor-based fraction, the clip upper bound n is clamped to n - 1 by the gather."""
+    A = np.asarray(A, dtype=np.float64)
+    n0, n1 = A.shape
+    rp = [n0 / 2, n1 / 2]
+    x, y = np.meshgrid(np.arange(n0), np.arange(n1))
+    R = np.array([[np.cos(-theta), -np.sin(-theta)], [np.sin(-theta), np.cos(-theta)]])
+    o = R @ np.array([x.flatten() - rp[0], y.flatten() - rp[1]])
+    or_x, or_y = o[0].reshape(x.shape), o[1].reshape(y.shape)
+    w11 = (1 - or_x % 1) * (1 - or_y % 1)
+    w12 = (1 - or_x % 1) * (or_y % 1)
+    w21 = (or_x % 1) * (1 - or_y % 1)
+    w22 = (or_x % 1) * (or_y % 1)
+
+    def q(dy, dx):
+        r = np.minimum(np.clip(np.trunc(or_y + rp[1] + dy).astype(int), 0, n1), A.shape[0] - 1)
+        c = np.minimum(np.clip(np.trunc(or_x + rp[0] + dx).astype(int), 0, n0), A.shape[1] - 1)
+        return A[r, c]
+
+    return w11 * q(0, 0) + w12 * q(1, 0) + w21 * q(0, 1) + w22 * q(1, 1)
+
+
 # --------------------------------------------------------------------------------------
 # a10: loss (loss_function.py:190-267, 269-342, 364-373, 386-418)
 # --------------------------------------------------------------------------------------

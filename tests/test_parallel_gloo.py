@@ -134,3 +134,66 @@ def test_numa_binding_is_a_no_op_without_gpu_topology():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+# ---- multiplexed shots: one shot per half of the ranks -----------------------------------------------------
+def test_shot_split():
+    from tsadar_b200.parallel import shot_split
+    assert shot_split(0, 1) == (None, [0])
+    assert [shot_split(r, 2)[0] for r in range(2)] == [0, 1]
+    assert [shot_split(r, 8) for r in (0, 3, 4, 7)] == [(0, [0, 1, 2, 3]), (0, [0, 1, 2, 3]), (1, [4, 5, 6, 7]), (1, [4, 5, 6, 7])]
+    with pytest.raises(ValueError):
+        shot_split(0, 3)
+
+
+def _worker_shots(rank, world, port, q):
+    """The recipe of LossFunction's shot sharding on a toy model: loss = sum over two shots of g_k(theta); half of the ranks
+    evaluate each shot, the total and the gradient of the shared leaf must equal the single-process ones on every rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tsadar_b200.parallel import shot_assignment, allreduce_sum_identity_grad
+    shot, half, grp = shot_assignment()
+    theta = torch.tensor([0.3, -1.1], dtype=torch.float64, requires_grad=True)
+    g = [lambda t: (t ** 2).sum() * 1.5, lambda t: torch.sin(t).sum() + t[0] * t[1]]
+    local = g[shot](theta)
+    total = allreduce_sum_identity_grad(local) / half
+    total.backward()
+    dist.all_reduce(theta.grad)
+    t0 = torch.tensor([0.3, -1.1], dtype=torch.float64, requires_grad=True)
+    ref = g[0](t0) + g[1](t0)
+    ref.backward()
+    ok = bool(torch.allclose(total, ref, rtol=1e-14)) and bool(torch.allclose(theta.grad, t0.grad, rtol=1e-14))
+    ok = ok and ((grp is None) == (half == 1)) and shot == (0 if rank < world // 2 else 1)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shot_sharding_recipe(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shots, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_pixel_rotation_matches_the_oracle():
+    """tsadar_b200.vector_tools.rotate (torch) vs oracle.rotate_pixels (NumPy restatement of vector_tools.py:94-138), several
+    angles, and the properties that follow from the source: rotation by 0 is the identity, by pi/2 a quarter turn."""
+    import numpy as np
+    from oracle import np_oracle as O
+    from tsadar_b200.vector_tools import rotate
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(24, 24))
+    for th in (0.0, 0.3, -1.2, np.pi / 2, 2.5, 33.0 * np.pi / 180):
+        a, b = O.rotate_pixels(A, th), rotate(torch.tensor(A), th).numpy()
+        assert np.abs(a - b).max() <= 1e-13
+    assert np.array_equal(O.rotate_pixels(A, 0.0), A)
+    At = torch.tensor(A, requires_grad=True)
+    rotate(At, 0.4).sum().backward()
+    assert torch.isfinite(At.grad).all() and float(At.grad.abs().sum()) > 0

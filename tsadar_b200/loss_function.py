@@ -32,8 +32,21 @@ class LossFunction:
             self.e_norm = float(np.amax(np.asarray(dummy_batch["e_data"])))
         else:
             self.i_norm = self.e_norm = 1.0
-        if isinstance(cfg["data"]["shotnum"], list):
-            raise NotImplementedError("multiplexed shots: 'behavior has not been checked' in the reference (loss_function.py:288)")
+        # Multiplexed shots (loss_function.py:101, 287-317): cfg["data"]["shotnum"] is a LIST of two shots of the same plasma;
+        # the second one sees the electron distribution rotated by data.shot_rot degrees (vector_tools.rotate) and the loss is the
+        # sum of both shots' errors.  (As written the reference assigns into the ThomsonParams module, `ts_params["electron"]
+        # ["fe"] = rotate(...)`, which an equinox Module does not allow -- "behavior has not been checked"; what it states is
+        # implemented here on the physical-parameter dictionary.)  The two shots are independent forward models: with several
+        # ranks, shot 1 goes to the first half of the ranks and shot 2 to the second half, each half
+        # W-sharding its own image; the only exchange is the scalar loss sum and the all-reduce of the shared leaves' gradients.
+        self.multiplex_ang = isinstance(cfg["data"]["shotnum"], list)
+        self.shot = None          # None: this rank evaluates both shots; 0 / 1: only that one (shot sharding)
+        self.shot_half = 1
+        if self.multiplex_ang:
+            from .parallel import shot_assignment
+            self.shot, self.shot_half, grp = shot_assignment()
+            if self.shot is not None:
+                shard_group = grp if grp is not None else False
         self.ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group)
         self._w = {}
 
@@ -58,8 +71,32 @@ class LossFunction:
                        "I": None if wI is None else torch.tensor(wI, dtype=torch.float64, device=dev)}
         return self._w["E"], self._w["I"]
 
-    def calc_loss(self, ts_params, batch, world_batch=None):
+    def _calc_loss_multiplexed(self, ts_params, batch):
+        """loss_function.py:287-317: shot "b1" with f, shot "b2" with f rotated by data.shot_rot; errors summed."""
+        from .vector_tools import rotate
+        from .parallel import allreduce_sum_identity_grad
+        phys = ts_params() if callable(ts_params) else ts_params
+        total, ThryE_out, ThryI_out = None, None, None
+        for k, key in enumerate(("b1", "b2")):
+            if self.shot is not None and self.shot != k:
+                continue
+            p = phys
+            if k == 1:
+                p = {a: (dict(b) if isinstance(b, dict) else b) for a, b in phys.items()}
+                fe = p["electron"]["fe"]
+                p["electron"]["fe"] = rotate(fe.reshape(fe.shape[-2:]), self.cfg["data"]["shot_rot"] * np.pi / 180.0).reshape(fe.shape)
+            t, ThryE, ThryI = self.calc_loss(p, batch[key], _multiplex=False)
+            total = t if total is None else total + t
+            if k == 0 or ThryE_out is None:
+                ThryE_out, ThryI_out = ThryE, ThryI
+        if self.shot is not None:      # shot-sharded: every rank of a half holds the same shot loss
+            total = allreduce_sum_identity_grad(total) / self.shot_half
+        return total, ThryE_out, ThryI_out
+
+    def calc_loss(self, ts_params, batch, world_batch=None, _multiplex=True):
         """-> total_loss (torch scalar on the GPU), ThryE, ThryI     (loss_function.py:269-342, 364-373)"""
+        if self.multiplex_ang and _multiplex:
+            return self._calc_loss_multiplexed(ts_params, batch)
         ThryE, ThryI, lamE, lamI = self.ts_diag(ts_params, batch)
         dev = torch.device("cuda", torch.cuda.current_device())
         wE, wI = self._weights(np.asarray(lamE), np.asarray(lamI), dev)
@@ -84,6 +121,13 @@ class LossFunction:
             t.grad = None
         loss, ThryE, _ = self.calc_loss(ts_params, batch)
         loss.backward()
+        if self.multiplex_ang and self.shot is not None:
+            # every rank of a half holds (1 / half) x its own shot's gradient of the shared leaves (already summed over that
+            # half's wavelength shards): the sum over all ranks is the sum over the two shots
+            import torch.distributed as dist
+            for t in leaves:
+                if t.grad is not None:
+                    dist.all_reduce(t.grad)
         return (loss.detach(), [ThryE.detach() if isinstance(ThryE, torch.Tensor) else ThryE, ts_params]), [t.grad for t in leaves]
 
     def loss(self, ts_params, batch):

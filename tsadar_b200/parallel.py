@@ -111,6 +111,56 @@ class WShard:
         self.keep = self.j1 - self.j0
 
 
+# ---- multiplexed shots: one shot per half of the ranks ---------------------------------------------------
+def shot_split(rank: int, world: int):
+    """(shot index, ranks of my half): ranks [0, world/2) evaluate shot 0, the rest shot 1; world must be even (or 1)."""
+    if world < 2:
+        return None, [0]
+    if world % 2:
+        raise ValueError(f"multiplexed shots need an even number of ranks, got {world}")
+    half = world // 2
+    shot = 0 if rank < half else 1
+    return shot, list(range(shot * half, (shot + 1) * half))
+
+
+_shot_groups = {}
+
+
+def shot_assignment():
+    """-> (shot or None, ranks per half, process group of my half or None).  Every rank must call it (new_group is
+    collective); the groups are cached per world size."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return None, 1, None
+    world, rank = dist.get_world_size(), dist.get_rank()
+    shot, mine = shot_split(rank, world)
+    half = world // 2
+    if half == 1:
+        return shot, 1, None
+    if world not in _shot_groups:
+        _shot_groups[world] = [dist.new_group(list(range(k * half, (k + 1) * half))) for k in range(2)]
+    return shot, half, _shot_groups[world][shot]
+
+
+class _AllReduceSumIdentityGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = x.detach().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def allreduce_sum_identity_grad(x: torch.Tensor) -> torch.Tensor:
+    """sum over ranks of per-rank partial losses; d total / d my partial = 1 (the other ranks' partials do not depend on my
+    graph)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    return _AllReduceSumIdentityGrad.apply(x)
+
+
 def bind_to_gpu_numa_node(device_index):
     """Restrict the calling process to the CPUs NVML reports as local to this GPU (nvmlDeviceSetCpuAffinity), so that the
     pinned staging buffers it allocates afterwards are first-touched on the GPU's own NUMA node and the H2D copies of the
