@@ -418,9 +418,14 @@ def fit_model_electron(params, grids, sa, cfg_other, num_grad_points=1, lam_shif
         modlE = np.sum(ThryE * sa["weights"][0], axis=1)  # :197
     lam = float(params["general"]["lam"])
     if cfg_other.get("iawoff", 0) and (cfg_other["lamrangE"][0] < lam < cfg_other["lamrangE"][1]):
-        # :199-208.  NB for an ascending axis lamlocb > lamlocr, so the concatenation is
-        # ill-formed in the reference; every checked-in deck has iawoff: 0.
-        raise NotImplementedError("iawoff branch is untested in the reference (SURVEY.md A9)")
+        # :199-208 "set the ion feature to 0".  As written, lamlocb = argmin|lam_axis - lam - 3| is the index nearest lam + 3 and
+        # lamlocr the one nearest lam - 3, so on an ascending axis lamlocb > lamlocr and jnp.zeros(lamlocr - lamlocb) has a
+        # negative size: the branch cannot run (every checked-in deck has iawoff: 0).  What it evidently means -- the model
+        # zeroed between the samples nearest lam - 3 nm and lam + 3 nm -- is what is restated here.
+        i_lo = int(np.argmin(np.abs(lamAxisE - (lam - 3.0))))
+        i_hi = int(np.argmin(np.abs(lamAxisE - (lam + 3.0))))
+        modlE = np.array(modlE, dtype=np.float64, copy=True)
+        modlE[..., i_lo:i_hi] = 0.0
     iawf = cfg_other.get("iawfilter", [0])
     if iawf[0]:
         filterb = iawf[3] - iawf[2] / 2

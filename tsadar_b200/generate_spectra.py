@@ -83,13 +83,28 @@ class FitModel:
             self._w = np.full(nA, float(w0)) if np.ndim(w0) == 0 else np.asarray(w0, dtype=np.float64)
         lamE = np.linspace(oth["lamrangE"][0], oth["lamrangE"][1], oth["npts"])
         self._jmulE = None
-        if oth.get("iawoff", 0):
-            raise NotImplementedError("iawoff: untested branch in the reference (SURVEY.md A9)")
+        # iawoff (generate_spectra.py:199-208, "set the ion feature to 0"): as written the branch is ill-formed (its two indices
+        # are swapped, so jnp.zeros gets a negative size) and no deck switches it on; its evident meaning -- the model zeroed
+        # between the samples nearest lam - 3 nm and lam + 3 nm -- is applied after the kernel (_apply_iawoff)
+        self._iawoff = bool(oth.get("iawoff", 0))
         f = oth.get("iawfilter", [0])
         if f[0]:
             fb, fr = f[3] - f[2] / 2, f[3] + f[2] / 2
             if oth["lamrangE"][0] < fr and oth["lamrangE"][1] > fb:
                 self._jmulE = np.where((fb < lamE) & (fr > lamE), 10.0 ** (-f[1]), 1.0)   # generate_spectra.py:210-216
+
+    def _apply_iawoff(self, modlE, block):
+        """modlE [..., W] with the samples in [nearest(lam - 3), nearest(lam + 3)) zeroed, per parameter set (row of block)."""
+        oth = self.config["other"]
+        lamE = torch.linspace(oth["lamrangE"][0], oth["lamrangE"][1], oth["npts"], dtype=torch.float64, device=modlE.device)
+        lam = block[:, _ffi.P_LAM].detach()
+        i_lo = torch.argmin((lamE[None, :] - (lam[:, None] - 3.0)).abs(), dim=1)
+        i_hi = torch.argmin((lamE[None, :] - (lam[:, None] + 3.0)).abs(), dim=1)
+        j = torch.arange(oth["npts"], device=modlE.device)[None, :]
+        inside = (j >= i_lo[:, None]) & (j < i_hi[:, None]) & ((lam > oth["lamrangE"][0]) & (lam < oth["lamrangE"][1]))[:, None]
+        if modlE.dim() == 2 and modlE.shape[0] != block.shape[0]:       # angular_full: one parameter set, [NA, W] image
+            inside = inside[:1]
+        return torch.where(inside, torch.zeros((), dtype=modlE.dtype, device=modlE.device), modlE)
 
     def ion_spectrum(self, all_params):
         if self.config["other"]["extraoptions"]["load_ion_spec"]:
@@ -122,12 +137,16 @@ class FitModel:
                 from .parallel import gather_columns
                 modlE = gather_columns(modlE.contiguous(), self.w_shard.npts, self.w_shard.group)
             block, _, _, _, _ = pack_params(all_params, dev)
+            if self._iawoff:
+                modlE = self._apply_iawoff(modlE, block)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
             return lamE, modlE, block
         if self.config["other"]["extraoptions"]["load_ele_spec"] and self.dim == 2:
             raise NotImplementedError("2V distributions with a temporal/imaging spectype: no reference deck (calc_in_2D is wired for angular_full)")
         if self.config["other"]["extraoptions"]["load_ele_spec"]:
             modlE, block = self.electron_form_factor.modl(all_params, self._w, jmul=self._jmulE)
+            if self._iawoff:
+                modlE = self._apply_iawoff(modlE, block)
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
             return lamE, modlE, block
         return [], 0, None
