@@ -98,6 +98,15 @@ int tsff_abi_version(void);
  * (ev_bwd_*).  Used by bench.py for the live per-kernel roofline number; pass NULLs to switch off. */
 int tsff_ctx_set_profile_events(tsff_ctx* ctx, void* ev_fwd_start, void* ev_fwd_stop, void* ev_bwd_start, void* ev_bwd_stop);
 
+/* Second-order path (TSFF_MODE_TABLE).  The reference takes the Hessian with jax.hessian (loss_function.py:110, 170-188), which
+ * differentiates jnp.interp with the cell index held constant.  mode 1: tsff_ff_fwd records, per (lineout, gradient point,
+ * wavelength, angle), the cells of its linear interpolations (PV table at xi_e, Z' table at every xi_i) into
+ * cells [B][G][W][A][1 + TSFF_MAX_IONS] (int32, device, tsff_ff_cells_bytes); mode 2: tsff_ff_fwd and tsff_ff_bwd extend those
+ * recorded cells linearly instead of looking the cell up, so that finite differences of the adjoint gradient around the
+ * recording point converge to the reference's Hessian; mode 0: off.  Not re-entrant while switched on. */
+size_t tsff_ff_cells_bytes(const tsff_ctx* ctx, int64_t B);
+int tsff_ctx_set_frozen_cells(tsff_ctx* ctx, int mode, int32_t* cells, int64_t B);
+
 /* bytes the caller must provide: `saved` lives from *_fwd to the matching *_bwd, `ws` is scratch per call */
 size_t tsff_ff_saved_bytes(const tsff_ctx* ctx, int64_t B);
 size_t tsff_ff_workspace_bytes(const tsff_ctx* ctx, int64_t B);

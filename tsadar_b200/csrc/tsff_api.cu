@@ -33,11 +33,26 @@ extern "C" size_t tsff_ff_workspace_bytes(const tsff_ctx* c, int64_t B) {
   return c->mode == TSFF_MODE_TABLE ? table_ws_bytes(c, B) : direct_ws_bytes(c, B);
 }
 
+// ---- second-order path: frozen lerp cells (table mode) -----------------------------------------------------------------------
+extern "C" size_t tsff_ff_cells_bytes(const tsff_ctx* c, int64_t B) {
+  if (!c || B < 1 || c->mode != TSFF_MODE_TABLE) return 0;
+  return (size_t)B * c->G * c->W * c->A * kCellStride * sizeof(int);
+}
+extern "C" int tsff_ctx_set_frozen_cells(tsff_ctx* c, int mode, int32_t* cells, int64_t B) {
+  if (!c) { set_error("null ctx"); return TSFF_E_INVALID; }
+  if (mode == 0) { c->cells = nullptr; c->cell_mode = 0; c->cells_B = 0; return TSFF_OK; }
+  if (c->mode != TSFF_MODE_TABLE) { set_error("frozen cells: table mode only"); return TSFF_E_INVALID; }
+  if ((mode != 1 && mode != 2) || !cells || B < 1) { set_error("frozen cells: bad argument"); return TSFF_E_INVALID; }
+  c->cells = cells; c->cell_mode = mode; c->cells_B = B;
+  return TSFF_OK;
+}
+
 static int check_common(const tsff_ctx* c, int64_t B, const void* params, const void* fe, int fe_dtype, const void* saved,
                         const void* ws) {
   if (!c || !params || !fe || !saved || !ws) { set_error("null argument"); return TSFF_E_INVALID; }
   if (B < 1) { set_error("B must be >= 1"); return TSFF_E_INVALID; }
   if (fe_dtype != TSFF_F32 && fe_dtype != TSFF_F64) { set_error("fe_dtype must be TSFF_F32 or TSFF_F64"); return TSFF_E_INVALID; }
+  if (c->cell_mode && B > c->cells_B) { set_error("frozen-cell buffer holds %lld lineouts, call has %lld", c->cells_B, (long long)B); return TSFF_E_INVALID; }
   const long long blocks = (long long)B * c->G * (((long long)c->W * c->A + 255) / 256);
   if (blocks > 0x7fffffffLL) { set_error("batch too large for one launch: split the call"); return TSFF_E_INVALID; }
   return TSFF_OK;

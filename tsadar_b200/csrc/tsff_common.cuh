@@ -180,5 +180,8 @@ struct tsff_ctx {
   double pv_z0, pv_h;
   double* tstat; // static expansion tables (k_tree_static) for pv_nodes
   cudaEvent_t ev[4];  // optional profile events (fwd start/stop, bwd start/stop)
+  int* cells;         // frozen lerp cells of the table-mode assembly (tsff_ctx_set_frozen_cells), or null
+  int cell_mode;      // 0 off, 1 record, 2 replay
+  long long cells_B;  // lineouts the cells buffer holds
   int tune_fwd_r4;    // TSFF_FWD_R4 tuning switch, read once at creation (four poles per thread in k_direct_fwd: measured slower)
 };

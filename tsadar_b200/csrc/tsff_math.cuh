@@ -294,6 +294,45 @@ TSFF_HD void zprime_lerp(const ZTab& z, double x, double& zr, double& zi, double
   dzi = (i1 - i0) * ih;
 }
 
+// Frozen-cell variants (second-order path).  jax.hessian of a jnp.interp treats the cell index as a
+// constant: inside a cell the interpolant is linear in x, so its second derivative is zero and the kinks at the nodes do
+// not contribute.  A finite difference of the adjoint gradient across a node DOES see the kink (on average it reproduces the
+// curvature of the underlying smooth function), so to reproduce the reference's Hessian the perturbed evaluations must
+// extend the cell of the unperturbed point linearly.  mode 0: normal; 1: normal + record the cell used; 2: use the
+// recorded cell (t may leave [0, 1]).  Cell codes: >= 0 the cell; -1 / -2 the left / right out-of-table branch.
+constexpr int kCellStride = 1 + TSFF_MAX_IONS;   // per (omega, angle) point: T-table cell, then one Z' cell per ion
+
+TSFF_HD void zprime_lerp_cell(const ZTab& z, double x, double& zr, double& zi, double& dzr, double& dzi, int mode, int* cell) {
+  if (mode != 2) {
+    zprime_lerp(z, x, zr, zi, dzr, dzi);
+    if (mode == 1) {
+      int c = -1;
+      if (!(x < z.x0 || x > z.xlast)) {
+        c = (int)((x - z.x0) * fast_rcp(z.h));
+        c = c > z.n - 2 ? z.n - 2 : (c < 0 ? 0 : c);
+      }
+      *cell = c;
+    }
+    return;
+  }
+  const int i = *cell;
+  if (i < 0) {
+    double x2 = x * x;
+    zr = fast_rcp(x2);
+    dzr = -2.0 * zr * fast_rcp(x);
+    zi = 0.0;
+    dzi = 0.0;
+    return;
+  }
+  const double ih = fast_rcp(z.h);
+  const double t = (x - z.x0) * ih - (double)i;
+  double r0 = z.zr[i], r1 = z.zr[i + 1], i0 = z.zi[i], i1 = z.zi[i + 1];
+  zr = r0 + t * (r1 - r0);
+  zi = i0 + t * (i1 - i0);
+  dzr = (r1 - r0) * ih;
+  dzi = (i1 - i0) * ih;
+}
+
 // edge-clamped linear interpolation on a uniform grid (jnp.interp default; form_factor.py:270,376-377)
 // returns value; idx/t/slope for the adjoint (slope = 0 and weights collapse on the edge when clamped)
 template <typename T>
@@ -311,6 +350,28 @@ TSFF_HD double lerp_uniform(const T* f, int n, double x0, double h, double x, in
   i = (int)u;
   t = u - (double)i;
   double a = (double)f[i], b = (double)f[i + 1];
+  slope = (b - a) * ih;
+  return a + t * (b - a);
+}
+
+template <typename T>
+TSFF_HD double lerp_uniform_cell(const T* f, int n, double x0, double h, double x, int& i, double& t, double& slope, int mode,
+                                 int* cell) {
+  if (mode != 2) {
+    const double v = lerp_uniform(f, n, x0, h, x, i, t, slope);
+    if (mode == 1) {
+      const double u = (x - x0) * fast_rcp(h);
+      *cell = !(u > 0.0) ? -1 : (u >= (double)(n - 1) ? -2 : i);
+    }
+    return v;
+  }
+  const int c = *cell;
+  if (c == -1) { i = 0; t = 0.0; slope = 0.0; return (double)f[0]; }
+  if (c == -2) { i = n - 2; t = 1.0; slope = 0.0; return (double)f[n - 1]; }
+  const double ih = fast_rcp(h);
+  i = c;
+  t = (x - x0) * ih - (double)c;
+  const double a = (double)f[c], b = (double)f[c + 1];
   slope = (b - a) * ih;
   return a + t * (b - a);
 }
@@ -338,7 +399,7 @@ struct IonOut {
   double chiIr, chiIi, sion;
 };
 
-TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonOut& o) {
+TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonOut& o, int cell_mode = 0, int* cells = nullptr) {
   o.chiIr = o.chiIi = o.sion = 0.0;
 #pragma unroll
   for (int i = 0; i < TSFF_MAX_IONS; i++) {   // fixed trip count + predicate: the per-ion arrays stay in registers
@@ -346,7 +407,7 @@ TSFF_HD void ion_forward(const LG& L, int nI, const ZTab& zt, const Kin& q, IonO
     double xii = L.inv_s2vTi[i] * q.w;
     double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;
-    zprime_lerp(zt, xii, zr, zi, dzr, dzi);
+    zprime_lerp_cell(zt, xii, zr, zi, dzr, dzi, cell_mode, cells + i);
     o.chiIr += -0.5 * ikldi2 * zr;
     o.chiIi += -0.5 * ikldi2 * zi;
     o.sion += L.ioncf[i] * fast_exp_neg(-xii * xii);
@@ -387,7 +448,7 @@ struct KinBar {
 
 TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q, const IonOut& io, double chiEr,
                                double chiEi, double fphi, const Asm& s, double Pbar, PointBar& pb, KinBar& kb,
-                               LG& Lb) {
+                               LG& Lb, int cell_mode = 0, int* cells = nullptr) {
   double Ssum = s.Sion + s.Sele;
   double Ssum_bar = Pbar * s.dop * L.ne_g * s.cP;
   double dop_bar = Pbar * Ssum * L.ne_g * s.cP;
@@ -416,7 +477,7 @@ TSFF_HD void assemble_backward(const LG& L, int nI, const ZTab& zt, const Kin& q
     double xii = L.inv_s2vTi[i] * q.w;
     double ikldi2 = fast_rcp(L.c_kldi[i] * L.c_kldi[i] * q.k2);
     double zr, zi, dzr, dzi;
-    zprime_lerp(zt, xii, zr, zi, dzr, dzi);
+    zprime_lerp_cell(zt, xii, zr, zi, dzr, dzi, cell_mode == 2 ? 2 : 0, cells + i);
     double E = fast_exp_neg(-xii * xii);
     Lb.ioncf[i] += sion_bar * E;
     double xii_bar = sion_bar * L.ioncf[i] * E * (-2.0 * xii);

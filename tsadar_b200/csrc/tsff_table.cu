@@ -78,6 +78,8 @@ struct TableArgs {
   double *Tbar, *lnfbar, *slopebar, *pnear, *Dbar, *lgbar;
   double* params_bar;
   void* fe_bar;
+  int* cells;      // frozen lerp cells [B][G][W][A][kCellStride] (second-order path) or null
+  int cell_mode;   // 0 off, 1 record, 2 replay
 };
 
 __device__ __forceinline__ void load_lg(const double* src, LG& L) {
@@ -198,11 +200,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
       const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) / (xi_n - q.xie) : 0.0;           // :258-259
       if (out) {
         int ip; double tp, slp;
-        const double Tl = lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);               // :270
+        int* cp = a.cells ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+        const int cm = a.cells ? a.cell_mode : 0;
+        const double Tl = lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp);  // :270
         const double chiEr = -q.ikl2 * Tl;                                                                // :271
         const double chiEi = kPi * q.ikl2 * df;                                                           // :261
         IonOut io;
-        ion_forward(L, a.nI, a.zt, q, io);
+        ion_forward(L, a.nI, a.zt, q, io, cm, cp + 1);
         Asm s;
         const double P = assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
         if (WRITE_FF) a.ff[((b * a.G + g) * (long long)a.W + j) * a.A + ia] = P;
@@ -268,13 +272,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_table_bwd(const TableArgs a) {
       if (valid && lane < 31) {
         double Pbar = mb * a.wts[ia];
         if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
-        Tl = lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);
+        int* cp = a.cells ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+        const int cm = (a.cells && a.cell_mode == 2) ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
+        Tl = lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp);
         const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
         IonOut io;
-        ion_forward(L, a.nI, a.zt, q, io);
+        ion_forward(L, a.nI, a.zt, q, io, cm, cp + 1);
         Asm s;
         assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
-        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
+        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb, cm, cp + 1);
         dfbar = has_df ? kPi * q.ikl2 * pb.chiEi : 0.0;
         kb.ikl2 += -Tl * pb.chiEr + kPi * df * pb.chiEi;
       }
@@ -431,6 +437,7 @@ int table_angle_split(long long ctas, int A, int sm_count) {
 }
 
 void fill_static(const tsff_ctx* c, TableArgs& a) {
+  a.cells = c->cells; a.cell_mode = c->cell_mode;
   a.W = c->W; a.A = c->A; a.G = c->G; a.nI = c->I; a.V = c->V; a.NP = c->NP;
   a.nodes = c->pv_nodes; a.npad = c->pv_npad;
   a.lam_shift = c->lam_shift; a.v0 = c->v0; a.dv = c->dv;

@@ -168,6 +168,18 @@ class FormFactorEngine:
             ws.data_ptr(), st))
         return params_bar, fe_bar
 
+    def set_frozen_cells(self, mode, B=None):
+        """Second-order path (table mode): mode "record" -- the next forward stores the cells of its linear interpolations;
+        "replay" -- forward and backward extend the recorded cells linearly (what jax.hessian differentiates); "off"."""
+        m = {"off": 0, "record": 1, "replay": 2}[mode]
+        if m == 0:
+            _ffi.check(_ffi.lib().tsff_ctx_set_frozen_cells(self._ctx, 0, None, 0))
+            return
+        if m == 1:
+            self._cells_B = int(B)
+            self._cells = torch.zeros(int(_ffi.lib().tsff_ff_cells_bytes(self._ctx, self._cells_B)), dtype=torch.uint8, device=self.device)
+        _ffi.check(_ffi.lib().tsff_ctx_set_frozen_cells(self._ctx, m, self._cells.data_ptr(), self._cells_B))
+
     def set_profile_events(self, fwd=None, bwd=None):
         """fwd/bwd: (start, stop) torch.cuda.Event pairs (enable_timing=True) recorded around the dominant kernels."""
         self._prof = (fwd, bwd)  # keep the events alive

@@ -204,27 +204,52 @@ class LossFunction:
             total = total + ((wI > 0).to(torch.float64) * (d - ThryI) ** 2 / (d.abs() + 1e-10)).sum()
         return total
 
-    def h_loss_wrt_params(self, ts_params, batch, rel_step=1e-4, loss=None):
+    def _table_engines(self):
+        m = self.ts_diag.model
+        return [e for ff in (m.electron_form_factor, m.ion_form_factor) for e in ff._engines.values() if e.mode == "table"]
+
+    def h_loss_wrt_params(self, ts_params, batch, rel_step=1e-4, loss=None, frozen_cells=True):
         """Hessian of `loss_for_hess` with respect to the flattened active leaves: central differences of the gradient
         that the adjoint kernels return exactly (the custom-VJP path has no forward-over-reverse; 2 n gradient calls,
-        n = number of active scalars).  -> (H [n, n] float64 numpy, symmetrised; list of (leaf index, element) per row)."""
+        n = number of active scalars).  frozen_cells=True (table mode): the linear interpolations of the form factor (PV table
+        at xi_e, Z' at xi_i) keep the cells of the unperturbed point in the perturbed evaluations -- jax.hessian
+        (loss_function.py:110) differentiates jnp.interp with the cell held constant, so this is what reproduces the
+        reference's Hessian; with False the differences also see the kinks at the table nodes (the curvature of the
+        underlying smooth function: up to 6 % different in d2/dTe2 on the 1d deck).
+        -> (H [n, n] float64 numpy, symmetrised; list of (leaf index, element) per row)."""
         from .fit import ravel_leaves, unravel_into, value_and_grad
         leaves = ts_params.parameters()
         x0 = ravel_leaves(leaves)
         closure = (lambda tp: self.loss_for_hess(tp, batch)) if loss is None else loss
         n = x0.size
         H = np.zeros((n, n))
-        for k in range(n):
-            h = rel_step * max(1.0, abs(x0[k]))
-            xp, xm = x0.copy(), x0.copy()
-            xp[k] += h
-            xm[k] -= h
-            unravel_into(leaves, xp)
-            _, gp = value_and_grad(closure, ts_params)
-            unravel_into(leaves, xm)
-            _, gm = value_and_grad(closure, ts_params)
-            H[k] = (gp - gm) / (2 * h)
-        unravel_into(leaves, x0)
+        engines = []
+        if frozen_cells:
+            with torch.no_grad():
+                closure(ts_params)                                  # makes sure the engines exist
+            engines = self._table_engines()
+            B = leaves[0].shape[0] if leaves and leaves[0].dim() else 1
+            for e in engines:
+                e.set_frozen_cells("record", B)
+            with torch.no_grad():
+                closure(ts_params)                                  # records the cells at the unperturbed point
+            for e in engines:
+                e.set_frozen_cells("replay")
+        try:
+            for k in range(n):
+                h = rel_step * max(1.0, abs(x0[k]))
+                xp, xm = x0.copy(), x0.copy()
+                xp[k] += h
+                xm[k] -= h
+                unravel_into(leaves, xp)
+                _, gp = value_and_grad(closure, ts_params)
+                unravel_into(leaves, xm)
+                _, gm = value_and_grad(closure, ts_params)
+                H[k] = (gp - gm) / (2 * h)
+        finally:
+            unravel_into(leaves, x0)
+            for e in engines:
+                e.set_frozen_cells("off")
         rows = [(li, e) for li, t in enumerate(leaves) for e in range(t.numel())]
         return 0.5 * (H + H.T), rows
 
