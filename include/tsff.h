@@ -244,6 +244,15 @@ int tsff_params_bwd(const tsff_params_cfg* cfg, int64_t B, const double* x_activ
 int tsff_adam_step(int64_t B, int32_t n_active, double* x, const double* grad, double* mu, double* nu, double* count,
                    double lr, double b1, double b2, double eps, void* stream);
 
+/* ---- N4: data-side stage in front of the fit --------------------------------------------------------------------------------- */
+/* replaces the lineout extraction of get_lineouts (tsadar/utils/process/lineouts.py:85-165) for one spectrometer image:
+ *   image [NY][NX] float64 (wavelength x time/space, background already subtracted), pixels [L] int32 lineout centres (DEVICE,
+ *   and the same list on the HOST for the bounds check), dpixel, gain (other.gain), window [NY] uint8 fit-window mask (DEVICE,
+ *   or NULL = all)  ->  data [L][NY] (column sum over [a - dpixel, a + dpixel), boxcar of 2 dpixel + 1 rows, / gain),
+ *   amps [L] (max over the window; NULL to skip). */
+int tsff_lineouts_fwd(const double* image, int32_t NY, int32_t NX, const int32_t* pixels, const int32_t* pixels_host, int32_t L,
+                      int32_t dpixel, double gain, const unsigned char* window, double* data, double* amps, void* stream);
+
 /* ---- microbenchmarks used for the roofline denominators --------------------------------- */
 /* runs `iters` dependent-chain FFMA (kind 0) or MUFU.LG2 (kind 1) per thread on the whole device; returns the
  * number of operations issued (FFMA counts 1 op = 2 flop) in *ops; time it with events on `stream`. */

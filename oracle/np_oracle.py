@@ -574,6 +574,19 @@ def diagnostic_arts(params, cfg, sa, batch, mode="table"):
     return ThryE + np.asarray(batch["noise_e"]), lamE, modlE
 
 
+def extract_lineouts(image, pixels, dpixel, gain, window=None):
+    """The lineout extraction of get_lineouts (tsadar/utils/process/lineouts.py:85-93, 125-152) for one spectrometer image
+    [NY, NX]: column sums over [a - dpixel, a + dpixel), boxcar smoothing with span 2 dpixel + 1, / gain, amplitude = max over
+    the fit-window mask.  -> (data [L, NY], amps [L])."""
+    image = np.asarray(image, dtype=np.float64)
+    span = 2 * dpixel + 1
+    raw = [np.sum(image[:, a - dpixel: a + dpixel], axis=1) for a in pixels]
+    smooth = [np.convolve(r, np.ones(span) / span, "same") for r in raw]
+    data = np.array([s / gain for s in smooth])
+    m = np.ones(image.shape[0], dtype=bool) if window is None else np.asarray(window, dtype=bool)
+    return data, np.amax(data[:, m], axis=1)
+
+
 def rotate_pixels(A, theta):
     """vector_tools.rotate (tsadar/utils/vector_tools.py:94-138): bilinear rotation of a table about its centre on the pixel
     grid, as the multiplexed-shot loss applies to f(vx, vy) (loss_function.py:291-293).  `jnp.asarray(., dtype=int)` truncates

@@ -185,6 +185,20 @@ def flm_arbitrary_vr(flm_sign, flm_mag):
     return 10**mag * sign
 
 
+def flm_nn(vr, f00, mag_weights, sign_weights):
+    """FLM_NN.__call__ (spherical_harmonics.py:41-49): two eqx.nn.MLP(in 1, out 1, width 32, depth 3, relu between the layers)
+    evaluated at every vr: flm = 10^(-relu-MLP(vr)) * f00 * tanh-MLP(vr).  weights: list of (W [out, in], b [out]) per layer."""
+    def mlp(ws, x, final):
+        h = x[:, None]
+        for k, (W, b) in enumerate(ws):
+            h = h @ np.asarray(W).T + np.asarray(b)
+            if k < len(ws) - 1:
+                h = np.maximum(h, 0.0)
+        return final(h[:, 0])
+    mag = -mlp(mag_weights, np.asarray(vr, dtype=np.float64), lambda z: np.maximum(z, 0.0))
+    return np.power(10.0, mag) * f00 * mlp(sign_weights, np.asarray(vr, dtype=np.float64), np.tanh)
+
+
 def spherical_harmonics_fe(dist_cfg, normed_m=None, flm_leaves=None):
     """SphericalHarmonics.__init__ + __call__ (spherical_harmonics.py:199-247, 267-318) -> vx, f[V, V].
     `normed_m` / `flm_leaves[(l, m)]` override the initial trainable values ({"log_10_LT": x} for mora-yahi,
@@ -218,6 +232,8 @@ def spherical_harmonics_fe(dist_cfg, normed_m=None, flm_leaves=None):
                 flm = flm_mora_yahi(vr, lv.get("log_10_LT", np.log10(LT)), m_f0, f00)
             elif typ == "arbitrary":
                 flm = flm_arbitrary_vr(lv.get("flm_sign", np.zeros(p["nvr"])), lv.get("flm_mag", np.zeros(p["nvr"])))
+            elif typ == "nn":      # the MLP weights must be given: JAX's PRNG stream (PRNGKey(0) / PRNGKey(42)) is not available here
+                flm = flm_nn(vr, f00, lv["mag_weights"], lv["sign_weights"])
             else:
                 raise NotImplementedError(typ)
             flm_xy = np.interp(vr_vxvy, vr, flm, right=1e-32)

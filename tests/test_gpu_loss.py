@@ -85,7 +85,7 @@ def test_loss_function_end_to_end_other_functionals(method):
     lamb = np.linspace(400, 700, 1024)
     e_data = 0.6 * np.exp(-0.5 * ((lamb - 470) / 12.0) ** 2) + 0.5 * np.exp(-0.5 * ((lamb - 590) / 15.0) ** 2) + 0.01
     batch = dict(e_data=np.stack([e_data, 1.2 * e_data]), i_data=np.ones((B, 1024)), e_amps=np.array([1.0, 1.2]),
-                 i_amps=np.ones(B), noise_e=np.zeros((B, 1024)), noise_i=np.zeros((B, 1024)))
+                 i_amps=np.ones(B), noise_e=np.zeros((B, 1024)), noise_i=np.zeros(1))
     loss_fn = LossFunction(cfg, SA_P9, batch)
     tp = ThomsonParams(cfg["parameters"], num_params=B, batch=True, activate=True)
     with torch.no_grad():

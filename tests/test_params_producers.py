@@ -148,3 +148,32 @@ def test_get_unnormed_and_fitted_params():
     fitted2, n2 = tp2.get_fitted_params(cfg2)
     assert n2 == 0 and set(fitted2["electron"]) == {"flm"}
     assert fitted2["electron"]["flm"]["fvxvy"].shape == (48, 48) and set(fitted2["electron"]["flm"]) >= {0, 1, "fvxvy", "v"}
+
+
+def test_flm_nn_radial_model_matches_oracle():
+    """SphericalHarmonics with flm_type 'nn' (FLM_NN, spherical_harmonics.py:14-49: two eqx.nn.MLP(1, 1, 32, 3)) on the same
+    weights as the NumPy restatement; and the table is differentiable with respect to every MLP weight."""
+    import copy
+    import torch
+    from oracle import params_oracle as P
+    from tests.common import load_cfg
+    from tsadar_b200.distribution_functions import SphericalHarmonics
+    fe = copy.deepcopy(load_cfg("cfg_arts2v")["parameters"]["electron"]["fe"])
+    fe["nvx"], fe["params"]["nvr"], fe["params"]["flm_type"], fe["params"]["Nl"] = 24, 16, "nn", 1
+    sh = SphericalHarmonics(fe, torch.device("cpu"), True)
+    f = sh()
+    leaves = {}
+    for key, net in sh.flm.items():
+        w = {n: [(W.detach().numpy(), b.detach().numpy()) for W, b in ls] for n, ls in net.nets.items()}
+        leaves[key] = {"mag_weights": w["mag"], "sign_weights": w["sign"]}
+    vx, ref = P.spherical_harmonics_fe(fe, flm_leaves=leaves)
+    assert np.abs(f.detach().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(ref - ref.T).max() > 1e-6 * np.abs(ref).max()        # the l = 1 terms make the table anisotropic
+    (f * torch.linspace(0, 1, f.numel(), dtype=torch.float64).reshape(f.shape)).sum().backward()
+    g = [t.grad for t in sh.leaves().values()]
+    assert len(g) == 1 + 2 * 2 * 8 and all(x is not None and torch.isfinite(x).all() for x in g)
+    # weights exported from elsewhere (e.g. a JAX run) are taken as they are
+    fe2 = copy.deepcopy(fe)
+    fe2["params"]["nn_weights"] = {key: {n: [(W.detach().numpy(), b.detach().numpy()) for W, b in ls] for n, ls in net.nets.items()}
+                                   for key, net in sh.flm.items()}
+    assert torch.equal(SphericalHarmonics(fe2, torch.device("cpu"), False)(), f.detach())

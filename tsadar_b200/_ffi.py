@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libtsff.so")
+LIB_PATH = os.environ.get("TSFF_LIB_PATH") or os.path.join(_HERE, "_lib", "libtsff.so")   # TSFF_LIB_PATH: A/B builds of the same ABI
 
 TSFF_ABI_VERSION = 3
 TSFF_MODE_TABLE, TSFF_MODE_DIRECT, TSFF_MODE_2V = 0, 1, 2
@@ -22,6 +22,7 @@ EXPORTS = [
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
     "tsff_ats_saved_bytes", "tsff_ats_workspace_bytes", "tsff_ats_fwd", "tsff_ats_bwd",
     "tsff_arts_weights_fwd", "tsff_arts_weights_bwd", "tsff_params_fwd", "tsff_params_bwd", "tsff_adam_step",
+    "tsff_lineouts_fwd",
 ]
 
 
@@ -139,6 +140,8 @@ def lib():
     L.tsff_params_bwd.restype = C.c_int
     L.tsff_adam_step.argtypes = [i64, C.c_int32, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, vp]
     L.tsff_adam_step.restype = C.c_int
+    L.tsff_lineouts_fwd.argtypes = [dp, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_double, vp, dp, dp, vp]
+    L.tsff_lineouts_fwd.restype = C.c_int
     L.tsff_loss_fwd_bwd.argtypes = [i64, C.c_int32, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, dp, vp]
     L.tsff_loss_fwd_bwd.restype = C.c_int
     _lib = L

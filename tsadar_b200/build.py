@@ -5,7 +5,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT, "libtsff.so")
-SOURCES = ["tsff_ctx.cu", "tsff_api.cu", "tsff_direct.cu", "tsff_table.cu", "tsff_irf.cu", "tsff_ats.cu", "tsff_2v.cu", "tsff_arts.cu", "tsff_params.cu"]
+SOURCES = ["tsff_ctx.cu", "tsff_api.cu", "tsff_direct.cu", "tsff_table.cu", "tsff_irf.cu", "tsff_ats.cu", "tsff_2v.cu", "tsff_arts.cu", "tsff_params.cu", "tsff_data.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

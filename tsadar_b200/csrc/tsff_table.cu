@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
 // dynamic smem: lnf[V] | slope[V] | T[1640]
 constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
 
-template <bool WRITE_FF>
+// FROZEN: the second-order path's cell record / replay (tsff_ctx_set_frozen_cells); a template so that the normal path carries
+// none of it
+template <bool WRITE_FF, bool FROZEN = false>
 __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LG sL;   // CTA-uniform scalars of the (lineout, gradient point)
@@ -200,9 +202,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
       const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) / (xi_n - q.xie) : 0.0;           // :258-259
       if (out) {
         int ip; double tp, slp;
-        int* cp = a.cells ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
-        const int cm = a.cells ? a.cell_mode : 0;
-        const double Tl = lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp);  // :270
+        int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+        const int cm = FROZEN ? a.cell_mode : 0;
+        const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
+                                 : lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);      // :270
         const double chiEr = -q.ikl2 * Tl;                                                                // :271
         const double chiEi = kPi * q.ikl2 * df;                                                           // :261
         IonOut io;
@@ -220,7 +223,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
 // ---- backward assembly ----------------------------------------------------------------------------------------
 constexpr int kBwdJ = 30;  // outputs per warp: lanes 1..30; lane 0 = left halo, lane 31 = right halo
 
-__global__ void __launch_bounds__(kThreads, 2) k_table_bwd(const TableArgs a) {
+#ifndef TSFF_TBWD_MINB
+#define TSFF_TBWD_MINB 2      // (3 CTAs per SM at 80 registers and 490 B of spills measured 1.4 % slower)
+#endif
+template <bool FROZEN>
+__global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sred[kLGDoubles * kWarps];
   __shared__ LG sL;   // the (lineout, gradient point) scalars are CTA-uniform: shared, not 19 doubles of registers per thread
@@ -272,9 +279,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_table_bwd(const TableArgs a) {
       if (valid && lane < 31) {
         double Pbar = mb * a.wts[ia];
         if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
-        int* cp = a.cells ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
-        const int cm = (a.cells && a.cell_mode == 2) ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
-        Tl = lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp);
+        int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+        const int cm = FROZEN ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
+        Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
+                    : lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);
         const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
         IonOut io;
         ion_forward(L, a.nI, a.zt, q, io, cm, cp + 1);
@@ -498,13 +506,12 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
     // the fused angle sum (modl) needs all angles in one CTA; the plain formfactor output can split them
     a.asplit = modl_out ? 1 : table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
-    if (ff_out) {
-      TSFF_SMEM_OPTIN(k_table_fwd<true>);
-      k_table_fwd<true><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
-    } else {
-      TSFF_SMEM_OPTIN(k_table_fwd<false>);
-      k_table_fwd<false><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
-    }
+    const unsigned grid = (unsigned)(B * a.ntiles * a.asplit);
+    const bool frozen = a.cells && a.cell_mode;
+    if (ff_out && frozen) { TSFF_SMEM_OPTIN((k_table_fwd<true, true>)); k_table_fwd<true, true><<<grid, kThreads, smem, st>>>(a); }
+    else if (ff_out) { TSFF_SMEM_OPTIN((k_table_fwd<true, false>)); k_table_fwd<true, false><<<grid, kThreads, smem, st>>>(a); }
+    else if (frozen) { TSFF_SMEM_OPTIN((k_table_fwd<false, true>)); k_table_fwd<false, true><<<grid, kThreads, smem, st>>>(a); }
+    else { TSFF_SMEM_OPTIN((k_table_fwd<false, false>)); k_table_fwd<false, false><<<grid, kThreads, smem, st>>>(a); }
     TSFF_LAUNCH_OK("k_table_fwd");
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
   }
@@ -532,8 +539,13 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
     a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
     a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
-    TSFF_SMEM_OPTIN(k_table_bwd);
-    k_table_bwd<<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
+    if (a.cells && a.cell_mode == 2) {
+      TSFF_SMEM_OPTIN(k_table_bwd<true>);
+      k_table_bwd<true><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
+    } else {
+      TSFF_SMEM_OPTIN(k_table_bwd<false>);
+      k_table_bwd<false><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
+    }
     TSFF_LAUNCH_OK("k_table_bwd");
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }

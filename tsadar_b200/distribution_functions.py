@@ -11,8 +11,10 @@ Everything static is folded at construction time so that one call is a handful o
 * the Hann smoothing of ArbitraryVr (`jnp.convolve(..., "same")`) likewise;
 * `jnp.interp(vr_vxvy, vr, .)` onto the Cartesian grid becomes a fixed gather + lerp (indices and weights precomputed);
 * the real spherical harmonics Re Y_l^m on the (vx, vy) mesh are constants.
-FLM_NN (two equinox MLPs initialised from jax.random.PRNGKey) is not mirrored: its initial weights are a function of
-JAX's threefry generator, which is not available here."""
+FLM_NN (two equinox MLPs, spherical_harmonics.py:14-49) is mirrored with the same architecture and forward arithmetic; its
+INITIAL weights in the reference come from jax.random.PRNGKey(0) / PRNGKey(42) through equinox's Linear initialiser --
+JAX's threefry stream is not available here, so the weights are either loaded (`params.nn_weights`: the arrays exported from
+a JAX run) or drawn from the same distribution, U(-1/sqrt(fan_in), 1/sqrt(fan_in)), with torch's generator seeded alike."""
 from __future__ import annotations
 
 import math
@@ -166,6 +168,46 @@ class _FlmArbitraryVr:
         return 10**mag * sign
 
 
+class _FlmNN:
+    """FLM_NN (spherical_harmonics.py:14-49): flm(vr) = 10^(-MLP_mag(vr)) f00 tanh-MLP_sign(vr), both MLPs = eqx.nn.MLP(in 1,
+    out 1, width 32, depth 3): Linear(1,32) relu Linear(32,32) relu Linear(32,32) relu Linear(32,1), final activation relu
+    (magnitude) / tanh (sign).  All weights trainable when the distribution is."""
+
+    def __init__(self, vr, device, trainable, weights=None, seeds=(0, 42)):
+        self.vr = vr
+        sizes = [(32, 1), (32, 32), (32, 32), (1, 32)]
+        self.nets = {}
+        for name, seed in zip(("mag", "sign"), seeds):
+            layers = []
+            g = torch.Generator().manual_seed(seed)
+            for k, (o, i) in enumerate(sizes):
+                if weights is not None:
+                    W, b = weights[name][k]
+                    W, b = torch.as_tensor(np.asarray(W), dtype=DT).reshape(o, i), torch.as_tensor(np.asarray(b), dtype=DT).reshape(o)
+                else:        # equinox Linear: weight and bias ~ U(-1/sqrt(in_features), 1/sqrt(in_features))
+                    lim = 1.0 / math.sqrt(i)
+                    W = (torch.rand((o, i), dtype=DT, generator=g) * 2 - 1) * lim
+                    b = (torch.rand((o,), dtype=DT, generator=g) * 2 - 1) * lim
+                layers.append((W.to(device).requires_grad_(bool(trainable)), b.to(device).requires_grad_(bool(trainable))))
+            self.nets[name] = layers
+
+    def leaves(self):
+        return {f"flm_{n}.layers[{k}].{w}": t for n, ls in self.nets.items() for k, (W, b) in enumerate(ls) for w, t in (("weight", W), ("bias", b))}
+
+    def _mlp(self, name, final):
+        h = self.vr[:, None]
+        ls = self.nets[name]
+        for k, (W, b) in enumerate(ls):
+            h = h @ W.t() + b
+            if k < len(ls) - 1:
+                h = torch.relu(h)
+        return final(h[:, 0])
+
+    def __call__(self, m_f0, f00):
+        mag = -self._mlp("mag", torch.relu)                      # from minus inf to 0
+        return torch.pow(10.0, mag) * f00 * self._mlp("sign", torch.tanh)
+
+
 class SphericalHarmonics:
     """f(vx, vy) = f00(|v|) + sum_{l,m} flm(|v|) Re Y_l^m, floored at 1e-32 and normalised (spherical_harmonics.py:287-318).
     f00 = super-Gaussian of order m = 2 + 3 sigmoid(normed_m) on the radial grid vr (:267-285); the radial functions are
@@ -211,7 +253,7 @@ class SphericalHarmonics:
                 elif self.flm_type == "arbitrary":
                     self.flm[(l, m)] = _FlmArbitraryVr(nvr, device, trainable and l == 1)   # base.py:487-499: only l=1 is trained
                 elif self.flm_type == "nn":
-                    raise NotImplementedError("flm_type 'nn': equinox MLPs seeded by jax.random.PRNGKey cannot be reproduced without JAX")
+                    self.flm[(l, m)] = _FlmNN(self.vr, device, trainable, weights=(p.get("nn_weights") or {}).get((l, m)))
                 else:
                     raise NotImplementedError(f"Unknown flm_type: {p['flm_type']}")
                 # Re Y_l^m(azimuth = phi, polar = th)  (jax.scipy.special.sph_harm(m, n, theta, phi), :310-312):
