@@ -37,7 +37,7 @@ def setup(name, npts, nvx=None):
 
 
 def run(cfg, batch, shard):
-    diag = ThomsonScatteringDiagnostic(cfg, sa, shard_group=None if shard else False)
+    diag = ThomsonScatteringDiagnostic(cfg, sa, shard_group=None if shard else False, force_shard=True)   # also below the size threshold
     tp = ThomsonParams(cfg["parameters"], num_params=1, batch=False, activate=True)
     rng = np.random.default_rng(0)
 

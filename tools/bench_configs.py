@@ -159,9 +159,10 @@ def run_named_configs(rank=0, world=1, dev=None, cpu=True):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    ms = arts("cfg_arts1v", 2048, None, False)
+    ms = arts("cfg_arts1v", 2048, None, world > 1)     # a shard group is offered; FitModel.SHARD_MIN_POLES_1V declines it for this size
     out["arts-1d"] = {"shape": "table mode, one image: formfactor [1,2048,241] -> weights[1024,241] -> ATS stage, fwd + VJP of the fitted leaves",
-                      "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms, "sharding": "none (below the sharding threshold: one GPU is faster than the collectives)"}
+                      "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms,
+                      "sharding": "none: 493 568 poles < FitModel.SHARD_MIN_POLES_1V, the collectives would cost more than they save (every rank evaluates the image)"}
     ms = arts("cfg_arts2v", 1024, 128, world > 1)
     out["arts-2d"] = {"shape": "2V mode, one image: calc_in_2D on 246 784 poles x 128^2 bicubic points -> weights -> ATS stage, fwd + VJP",
                       "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms,

@@ -47,9 +47,15 @@ def arts_weights(ff, wmat, jmul=None):
 
 
 class FitModel:
-    def __init__(self, config, scattering_angles, mode="table", pv_precision="fp32", shard_group=False):
+    # wavelength-axis sharding pays only when one image is many milliseconds of work: the 2V path (V^2 bicubic points per pole,
+    # 130 ms per arts-2d image) always qualifies; the 1V table path (arts-1d: 0.16 ms of kernels per image) would be slowed
+    # down by the all-gather / all-reduce latency (measured 2.41 -> 2.86 ms on two GPUs), so it needs this many poles
+    SHARD_MIN_POLES_1V = 8_000_000
+
+    def __init__(self, config, scattering_angles, mode="table", pv_precision="fp32", shard_group=False, force_shard=False):
         """shard_group: False = single GPU; None or a process group = "angular_full" spectra are evaluated W-sharded over
-        that group's ranks (tsadar_b200/parallel.py), every rank returning the full modlE."""
+        that group's ranks (tsadar_b200/parallel.py), every rank returning the full modlE -- unless the image is too small
+        for the collectives to pay (SHARD_MIN_POLES_1V; force_shard=True overrides)."""
         self.config = config
         self.scattering_angles = scattering_angles
         gen = config["parameters"]["general"]
@@ -61,7 +67,9 @@ class FitModel:
         self.w_shard = None
         if shard_group is not False and config["other"]["extraoptions"]["spectype"] == "angular_full":
             from .parallel import WShard, _active
-            if _active(shard_group):
+            nA_ = np.asarray(scattering_angles["sa"]).size
+            worth = self.dim == 2 or force_shard or oth["npts"] * nA_ * G >= self.SHARD_MIN_POLES_1V
+            if _active(shard_group) and worth:
                 self.w_shard = WShard(oth["npts"], group=shard_group, halo=(self.dim == 1 and mode == "table"))
         self.electron_form_factor = FormFactor(oth["lamrangE"], npts=oth["npts"], lam_shift=config["data"]["ele_lam_shift"],
                                                scattering_angles=scattering_angles, num_grad_points=G,

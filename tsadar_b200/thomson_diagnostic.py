@@ -19,7 +19,7 @@ def _dev_vec(x, B, dev):
 
 
 class ThomsonScatteringDiagnostic:
-    def __init__(self, cfg, scattering_angles, mode="table", pv_precision="fp32", shard_group=False):
+    def __init__(self, cfg, scattering_angles, mode="table", pv_precision="fp32", shard_group=False, force_shard=False):
         self.cfg = cfg
         self.scattering_angles = scattering_angles
         st = cfg["other"]["extraoptions"]["spectype"]
@@ -29,7 +29,7 @@ class ThomsonScatteringDiagnostic:
         self.unbatched = "angular" in st and not self.angular
         if not ("temporal" in st or "imaging" in st or "1d" in st or "angular" in st):
             raise NotImplementedError(f"Unknown spectype: {st}")
-        self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group)
+        self.model = FitModel(cfg, scattering_angles, mode=mode, pv_precision=pv_precision, shard_group=shard_group, force_shard=force_shard)
         self._ats = None
 
     def __call__(self, ts_params, batch):
