@@ -38,7 +38,13 @@ constexpr double kTs0 = 8.0;
 constexpr int kTS = 64;              // nodes per level-1 block
 constexpr int kTS2 = 256;            // nodes per level-2 block
 constexpr int kTK = 14;              // expansion order of the forward sweep
-constexpr int kTKA = 12;             // expansion order of the adjoint sweep (gradients need 1e-4, not 1e-5)
+// expansion order of the adjoint sweep: gradients need 1e-4, not 1e-5.  Measured at the benchmark shape (W = 1024, V = 4096,
+// f32 tables) against the oracle's autograd: K = 12 -> fe_bar 3.0e-7, 4.18 ms per 16384 lineouts for the whole adjoint;
+// K = 10 -> 5.1e-7, 3.79 ms; K = 8 -> 2.2e-6, 3.68 ms.  (Even values only: two orders per packed instruction.)
+#ifndef TSFF_KTKA
+#define TSFF_KTKA 10
+#endif
+constexpr int kTKA = TSFF_KTKA;
 constexpr double kTs = 32.0;         // scale of the level-1 block-local coordinate (half a block)
 constexpr double kTs2 = 128.0;
 constexpr int kTWin = 3 * kTS;       // near-window nodes per pole
