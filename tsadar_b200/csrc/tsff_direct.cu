@@ -261,8 +261,14 @@ __global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, cons
 }
 
 // ---- backward: poles --------------------------------------------------------------------------------------
+#ifndef TSFF_BWDP_MINB
+#define TSFF_BWDP_MINB 2
+#endif
+#ifndef TSFF_BWDP_RB
+#define TSFF_BWDP_RB 4
+#endif
 template <int R, typename T>
-__global__ void __launch_bounds__(kThreads, 2) k_direct_bwd_poles(const DirectArgs a) {
+__global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(const DirectArgs a) {
   __shared__ LG sL;
   __shared__ double sred[kLGDoubles * (kThreads / 32)];
   const int tile = blockIdx.x % a.ntiles;
@@ -457,7 +463,7 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   const bool fused = n.nsplit == 1;
   const size_t z0 = fused ? L.w_accfe : L.w_zero_begin;
   TSFF_CUDA_OK(cudaMemsetAsync(w + z0, 0, L.w_zero_end - z0, st));
-  constexpr int RB = 4;
+  constexpr int RB = TSFF_BWDP_RB;
   a.ntiles = (WA + RB * kThreads - 1) / (RB * kThreads);
   k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
