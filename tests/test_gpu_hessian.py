@@ -46,7 +46,7 @@ def _oracle_loss_for_hess(x, tp, cfg, names, batch, grids, jmul):
     return 0.5 * e[torch.as_tensor(mask)].sum()           # both EPW windows fitted: the halves are averaged (loss_function.py:262-264)
 
 
-@pytest.mark.parametrize("pv,tol", [("fp64", 2e-4), ("fp32", 2e-2)])
+@pytest.mark.parametrize("pv,tol", [("fp64", 1e-3), ("fp32", 2e-2)])
 def test_hessian_matches_the_oracles_double_backward(pv, tol):
     from tsadar_b200.loss_function import LossFunction
     from tsadar_b200.ts_params import ThomsonParams
