@@ -154,10 +154,13 @@ int tsff_pv_bwd(int64_t B, int64_t N, int64_t P, const double* f, double z0, dou
 /* ---- B4: instrument response, pixel binning, amplitude scaling ------------------------------------------------ */
 /* replaces irf.add_electron_IRF (kind 0, irf.py:90-132) / irf.add_ion_IRF (kind 1, irf.py:50-87) under the reference's
  * vmap over lineouts (thomson_diagnostic.py:35-36, 42-76), plus the noise add of thomson_diagnostic.py:139-140.
- * Only PhysParams.norm == 0 (all reference decks).  The Gaussian taps are truncated at cut_sigma (<=0: 12). */
+ * PhysParams.norm == 0 (all reference decks): amps / max scaling and the amp1 | amp2 split after the binning (irf.py:125-130);
+ * norm > 0 (irf.py:117-124; un-jittable in the reference: boolean-mask indexing with a traced mask): the blue and the red side of
+ * the probe wavelength are normalised to their own maxima at full resolution, then binned; the ion spectrum is binned only.
+ * The Gaussian taps are truncated at cut_sigma (<=0: 12). */
 typedef struct tsff_irf_cfg {
   int32_t W, nbins;       /* model samples, CCD pixels (1024 in the reference, irf.py:74,124); W % nbins == 0 */
-  int32_t norm, kind;     /* PhysParams.norm (must be 0);  0 electron / 1 ion */
+  int32_t norm, kind;     /* PhysParams.norm (>= 0);  0 electron / 1 ion */
   double lam_min, lam_max; /* wavelength axis of the model spectrum in nm: linspace(lam_min, lam_max, W) */
   double stddev;          /* widIRF.spect_stddev_ele / spect_stddev_ion [nm] */
   double cut_sigma;

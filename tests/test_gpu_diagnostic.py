@@ -306,3 +306,54 @@ def test_iawoff_zeroes_the_ion_feature_window():
     # differentiable (the mask is piecewise constant in lam)
     ThryE.sum().backward()
     assert all(t.grad is not None and torch.isfinite(t.grad).all() for t in tp.parameters())
+
+
+@pytest.mark.parametrize("W", [1024, 5120])
+def test_irf_norm_positive_branch_matches_oracle_and_autograd(W):
+    """PhysParams.norm > 0 (irf.py:117-124): blue / red side normalised to its own maximum at full resolution, then binned;
+    the ion spectrum binned only.  Forward vs np_oracle.add_*_irf(norm=1); VJP vs float64 autograd of the same arithmetic."""
+    from tsadar_b200 import irf
+    rng = np.random.default_rng(2)
+    B = 3
+    lam = np.linspace(400.0, 700.0, W)
+    x = np.stack([np.exp(-0.5 * ((lam - c) / s) ** 2) + 0.4 * np.exp(-0.5 * ((lam - 610) / 9.0) ** 2) + 1e-5
+                  for c, s in [(450, 6.0), (470, 8.0), (500.37, 4.0)]])   # peaks off the sample grid: no arg-max ties
+    block = np.zeros((B, 14))
+    block[:, 2] = [524.0, 526.5, 527.3]
+    block[:, 7] = [1.1, 0.8, 2.0]
+    block[:, 8] = [0.9, 1.3, 0.5]
+    block[:, 9] = [1.0, 0.7, 1.5]
+    amps = np.array([1.0, 2.5, 0.3])
+    cfg = {"other": {"PhysParams": {"norm": 1, "widIRF": {"spect_stddev_ele": 1.3, "spect_stddev_ion": 0.5}}}}
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    bt = torch.tensor(block, device="cuda", requires_grad=True)
+    at = torch.tensor(amps, device="cuda")
+    lamb, thE = irf.add_electron_IRF(cfg, (400.0, 700.0), W, xt, at, bt, None)
+    _, thI = irf.add_ion_IRF(cfg, (400.0, 700.0), W, xt.detach(), at, bt.detach(), None)
+    assert len(lamb) == W                                   # the reference bins the axis only when norm == 0
+    for b in range(B):
+        _, ref = O.add_electron_irf(lam, x[b], amps[b], block[b, 2], block[b, 7], block[b, 8], 1.3, norm=1)
+        np.testing.assert_allclose(thE.detach().cpu().numpy()[b], ref, rtol=1e-9, atol=1e-14)
+        _, refI = O.add_ion_irf(lam, x[b], amps[b], block[b, 9], 0.5, norm=1)
+        np.testing.assert_allclose(thI.cpu().numpy()[b], refI, rtol=1e-9, atol=1e-14)
+    cot = rng.normal(size=(B, 1024))
+    (thE * torch.tensor(cot, device="cuda")).sum().backward()
+    # the same arithmetic in float64 torch on the CPU
+    xo = torch.tensor(x, requires_grad=True)
+    bo = torch.tensor(block, requires_grad=True)
+    tot = 0.0
+    lt = torch.tensor(lam)
+    for b in range(B):
+        g = torch.tensor(O._gauss(lam, 1.3))
+        n = W
+        full = torch.nn.functional.conv1d(xo[b].reshape(1, 1, -1), g.flip(0).reshape(1, 1, -1), padding=n - 1).reshape(-1)
+        y = full[(n - 1) // 2:(n - 1) // 2 + n]               # np.convolve(..., "same")
+        y = (xo[b].max() / y.max()) * y
+        blue, red = lt < block[b, 2], lt > block[b, 2]
+        z = torch.where(blue, bo[b, 7] * (y / y[blue].max()), bo[b, 8] * (y / y[red].max()))
+        tot = tot + (z.reshape(1024, -1).mean(dim=1) * torch.tensor(cot[b])).sum()
+    tot.backward()
+    gx, gb = xt.grad.cpu().numpy(), bt.grad.cpu().numpy()
+    assert np.abs(gx - xo.grad.numpy()).max() <= 1e-9 * np.abs(xo.grad.numpy()).max()
+    for k in (7, 8):
+        np.testing.assert_allclose(gb[:, k], bo.grad.numpy()[:, k], rtol=1e-9)

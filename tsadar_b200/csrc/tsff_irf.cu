@@ -73,6 +73,8 @@ IrfGeom irf_geom(const tsff_irf_cfg* c) {
 struct IrfStats {  // per lineout, written by k_irf_finish, read by the backward kernels
   double mx, my, mb;
   int im, iy, qm, pad;
+  double Mb, Mr;   // PhysParams.norm > 0: maxima of the rescaled convolution on the blue / red side of the probe wavelength
+  int ib, ir;      // and their sample indices
 };
 
 struct IrfLayout {
@@ -191,6 +193,65 @@ __global__ void __launch_bounds__(kThreads) k_irf_finish(const IrfGeom g, const 
   }
   __syncthreads();
   const double s = s_stat[0] / s_stat[1];  // irf.py:73,115  max(model)/max(conv)
+  if (c.norm > 0) {
+    // PhysParams.norm > 0 (irf.py:117-124; ion :74): the blue and the red side of the probe wavelength are normalised to their
+    // own maxima at full resolution, THEN binned; no amps / max scaling afterwards.  (Boolean-mask indexing with a traced mask:
+    // the reference can run this branch only un-jitted; no deck uses it.)
+    __shared__ double s_mv[2 * (kThreads / 32)];
+    __shared__ int s_mi[2 * (kThreads / 32)];
+    __shared__ double s_M[2];
+    __shared__ int s_I[2];
+    const double* p = c.params + b * c.NP;
+    if (c.kind == 0) {
+      double vb = -INFINITY, vr = -INFINITY;
+      int ib = 0, ir = 0;
+      for (int n = threadIdx.x; n < g.W; n += kThreads) {
+        const double lam = c.lam_min + (double)n * g.dlam, y = s * yc[b * g.W + n];
+        if (lam < p[P_LAM]) { if (y > vb) { vb = y; ib = n; } }
+        else if (lam > p[P_LAM]) { if (y > vr) { vr = y; ir = n; } }
+      }
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double v = __shfl_down_sync(0xffffffffu, vb, o); int i = __shfl_down_sync(0xffffffffu, ib, o);
+        if (v > vb || (v == vb && i < ib)) { vb = v; ib = i; }
+        v = __shfl_down_sync(0xffffffffu, vr, o); i = __shfl_down_sync(0xffffffffu, ir, o);
+        if (v > vr || (v == vr && i < ir)) { vr = v; ir = i; }
+      }
+      if (lane == 0) { s_mv[2 * wid] = vb; s_mi[2 * wid] = ib; s_mv[2 * wid + 1] = vr; s_mi[2 * wid + 1] = ir; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; w++) {
+          if (s_mv[2 * w] > vb || (s_mv[2 * w] == vb && s_mi[2 * w] < ib)) { vb = s_mv[2 * w]; ib = s_mi[2 * w]; }
+          if (s_mv[2 * w + 1] > vr || (s_mv[2 * w + 1] == vr && s_mi[2 * w + 1] < ir)) { vr = s_mv[2 * w + 1]; ir = s_mi[2 * w + 1]; }
+        }
+        s_M[0] = vb; s_M[1] = vr; s_I[0] = ib; s_I[1] = ir;
+      }
+      __syncthreads();
+    }
+    for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
+      double a = 0.0;
+      for (int k = 0; k < g.r; k++) {
+        const int n = q * g.r + k;
+        const double y = s * yc[b * g.W + n];
+        if (c.kind == 0) {
+          const double lam = c.lam_min + (double)n * g.dlam;
+          a += lam < p[P_LAM] ? p[P_AMP1] * (y / s_M[0]) : p[P_AMP2] * (y / s_M[1]);
+        } else {
+          a += y;
+        }
+      }
+      double v = a / (double)g.r;
+      if (c.noise) v += c.noise[b * g.nbins + q];
+      c.thry[b * g.nbins + q] = v;
+    }
+    if (threadIdx.x == 0) {
+      IrfStats st; st.mx = s_stat[0]; st.my = s_stat[1]; st.mb = 1.0; st.im = s_idx[0]; st.iy = s_idx[1]; st.qm = 0; st.pad = 0;
+      st.Mb = c.kind == 0 ? s_M[0] : 1.0; st.Mr = c.kind == 0 ? s_M[1] : 1.0; st.ib = c.kind == 0 ? s_I[0] : 0; st.ir = c.kind == 0 ? s_I[1] : 0;
+      c.stats[b] = st;
+    }
+    return;
+  }
   for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
     double a = 0.0;
     for (int k = 0; k < g.r; k++) a += yc[b * g.W + q * g.r + k];
@@ -202,6 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_irf_finish(const IrfGeom g, const 
     for (int q = 0; q < g.nbins; q++) if (s_yb[q] > mb) { mb = s_yb[q]; qm = q; }
     s_stat[2] = mb; s_idx[2] = qm;
     IrfStats st; st.mx = s_stat[0]; st.my = s_stat[1]; st.mb = mb; st.im = s_idx[0]; st.iy = s_idx[1]; st.qm = qm; st.pad = 0;
+    st.Mb = st.Mr = 1.0; st.ib = st.ir = 0;
     c.stats[b] = st;
   }
   __syncthreads();
@@ -235,6 +297,57 @@ __global__ void __launch_bounds__(kThreads) k_irf_bwd_pre(const IrfGeom g, const
   const double s = st.mx / st.my;
   const double* p = c.params + b * c.NP;
   const double amps = c.amps[b];
+  if (c.norm > 0) {
+    // reverse of the norm > 0 branch of k_irf_finish: out_q = mean_k z_n, z_n = a_n y_n / M_side(n), y_n = s yc_n
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // amp1_bar, amp2_bar, Mb_bar, Mr_bar
+    double sbar = 0.0;
+    for (int n = threadIdx.x; n < g.W; n += kThreads) {
+      const double zb = c.thry_bar[b * g.nbins + n / g.r] / (double)g.r;
+      const double ycn = yc[b * g.W + n], y = s * ycn;
+      double ybar;
+      if (c.kind == 0) {
+        const double lam = c.lam_min + (double)n * g.dlam;
+        const bool blue = lam < p[P_LAM];
+        const double a = blue ? p[P_AMP1] : p[P_AMP2], M = blue ? st.Mb : st.Mr;
+        acc[blue ? 0 : 1] += zb * y / M;
+        acc[blue ? 2 : 3] += -zb * a * y / (M * M);
+        ybar = zb * a / M;
+      } else {
+        ybar = zb;
+      }
+      c.ycbar[b * g.W + n] = s * ybar;
+      sbar += ybar * ycn;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < 4; k++) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) sred[k * (kThreads / 32) + wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double v = 0.0;
+      for (int w = 0; w < kThreads / 32; w++) v += sred[threadIdx.x * (kThreads / 32) + w];
+      s_tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    sbar = warp_sum(sbar);
+    if (lane == 0) sred[wid] = sbar;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; w++) t += sred[w];
+      double* ab = c.amp_bar + b * 3;
+      ab[0] = c.kind == 0 ? s_tot[0] : 0.0; ab[1] = c.kind == 0 ? s_tot[1] : 0.0; ab[2] = 0.0;
+      if (c.kind == 0) {   // the side maxima route their cotangents to their arg-max samples (y = s yc there)
+        c.ycbar[b * g.W + st.ib] += s * s_tot[2];
+        c.ycbar[b * g.W + st.ir] += s * s_tot[3];
+        t += s_tot[2] * yc[b * g.W + st.ib] + s_tot[3] * yc[b * g.W + st.ir];
+      }
+      c.ycbar[b * g.W + st.iy] += -t * st.mx / (st.my * st.my);   // s = mx / my
+      c.xbar_max[b] = t / st.my;
+    }
+    return;
+  }
   // out_q = A_q * yb_q / mb with A_q = a_q*amps (electron) or amp3*amps (ion); yb_q = s * mean_k yc
   double part[4] = {0.0, 0.0, 0.0, 0.0};  // mb_bar, amp1_bar|amp3_bar, amp2_bar, unused
   for (int q = threadIdx.x; q < g.nbins; q += kThreads) {
@@ -363,7 +476,7 @@ int check_cfg(const tsff_irf_cfg* c) {
     set_error("bad irf cfg (W must be a multiple of nbins, stddev > 0)");
     return TSFF_E_INVALID;
   }
-  if (c->norm != 0) { set_error("PhysParams.norm > 0 is not implemented (every reference deck uses norm: 0)"); return TSFF_E_INVALID; }
+  if (c->norm < 0) { set_error("PhysParams.norm must be >= 0"); return TSFF_E_INVALID; }
   if (c->kind != 0 && c->kind != 1) { set_error("irf kind must be 0 (electron) or 1 (ion)"); return TSFF_E_INVALID; }
   return TSFF_OK;
 }

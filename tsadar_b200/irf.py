@@ -62,6 +62,8 @@ def add_electron_IRF(config, lam_range, W, modlE, amps, block, noise=None, nbins
     pp = config["other"]["PhysParams"]
     cfg = _cfg(W, nbins, lam_range[0], lam_range[1], pp["widIRF"]["spect_stddev_ele"], 0, pp["norm"])
     thry = _IrfFunction.apply(modlE.contiguous(), block, amps.contiguous(), noise, cfg)
+    if pp["norm"] > 0:     # the reference bins the axis only in its norm == 0 branch (irf.py:125-126)
+        return np.linspace(lam_range[0], lam_range[1], W), thry
     return binned_axis(lam_range[0], lam_range[1], W, nbins), thry
 
 
@@ -73,4 +75,6 @@ def add_ion_IRF(config, lam_range, W, modlI, amps, block, noise=None, nbins=1024
         return np.linspace(lam_range[0], lam_range[1], W), modlI if noise is None else modlI + noise
     cfg = _cfg(W, nbins, lam_range[0], lam_range[1], std, 1, pp["norm"])
     thry = _IrfFunction.apply(modlI.contiguous(), block, amps.contiguous(), noise, cfg)
+    if pp["norm"] > 0:     # irf.py:76-78: axis binned and amp3 * amps / max applied only when norm == 0
+        return np.linspace(lam_range[0], lam_range[1], W), thry
     return binned_axis(lam_range[0], lam_range[1], W, nbins), thry
