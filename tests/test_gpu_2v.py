@@ -352,3 +352,42 @@ def test_calc_in_2D_vjp_full_size_table_vs_oracle_autograd():
     assert torch.equal(fb2[0, 3:-3, 3:-3], fb1[0, 3:-3, 3:-3])                                 # deterministic interior
     _, fb3 = eng.backward(pt, ft, saved, ff_bar=torch.tensor(cot[None], device="cuda"), want_params=False)
     assert torch.equal(fb3[0, 3:-3, 3:-3], fb1[0, 3:-3, 3:-3])
+
+
+@pytest.mark.gpu
+def test_2v_table_with_the_decks_own_angular_spectype_matches_oracle():
+    """The arts-2d deck's own spectype is "angular" (tests/configs/arts2v_test_defaults.yaml): a 2-D table through calc_in_2D,
+    the un-batched angle sum with the first row of the weight matrix (generate_spectra.py:187-197) and the electron IRF
+    (thomson_diagnostic.py:67-73) -- against the NumPy oracle of the same chain."""
+    import os
+    from oracle import params_oracle as P
+    from tests.common import load_cfg
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg = load_cfg("cfg_arts2v")
+    assert cfg["other"]["extraoptions"]["spectype"] == "angular"
+    cfg["other"]["lamrangE"] = [cfg["data"]["fit_rng"]["forward_epw_start"], cfg["data"]["fit_rng"]["forward_epw_end"]]
+    cfg["other"]["lamrangI"] = [cfg["data"]["fit_rng"]["forward_iaw_start"], cfg["data"]["fit_rng"]["forward_iaw_end"]]
+    cfg["other"]["npts"] = 1024
+    cfg["parameters"]["electron"]["fe"]["nvx"] = 24
+    cfg["parameters"]["electron"]["fe"]["params"]["nvr"] = 16
+    cfg["parameters"]["electron"]["fe"]["params"]["LTx"] = 60.0
+    cfg["parameters"]["electron"]["fe"]["active"] = True
+    tab = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tsadar_b200", "data", "arts_angles.npz"))
+    sa = dict(sa=np.arange(19, 139.5, 0.5)[::12], weights=tab["weightMatrix"][:, ::12], angAxis=tab["angsFRED"])     # 21 angles: the oracle's 2V path is slow
+    batch = dict(i_data=np.ones(1024), e_data=np.ones(1024), noise_e=np.array([0.0]), noise_i=np.array([0.0]),
+                 e_amps=np.array([1.0]), i_amps=np.array([1.0]))
+    cfg["other"]["npts"] = 64           # 64 x 21 poles for the oracle; pixel binning needs W % 1024 == 0 -> 64 bins here
+    from tsadar_b200 import irf
+    p = P.thomson_params(cfg["parameters"], activate=True)
+    grids = O.Grids(cfg["other"]["lamrangE"], 64)
+    lamE, mE = O.fit_model_electron(p, grids, sa, cfg["other"], 1, cfg["data"]["ele_lam_shift"])
+    diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=sa)
+    tp = ThomsonParams(cfg["parameters"], num_params=1, batch=False, activate=True)
+    lam_got, modlE, block = diag.model.electron_spectrum(tp())
+    assert modlE.shape == (1, 64)
+    np.testing.assert_allclose(lam_got, lamE, rtol=1e-12)
+    assert np.abs(modlE.detach().cpu().numpy()[0] - mE).max() / np.abs(mE).max() < 1e-8
+    modlE.sum().backward()
+    g = [t.grad for t in tp.parameters()]
+    assert g and all(x is not None and torch.isfinite(x).all() for x in g)

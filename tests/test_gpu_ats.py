@@ -177,3 +177,24 @@ def test_arts_weight_contraction_kernel_vs_numpy(G, W, A, NA):
     ref2 = wm @ ff.mean(0).T
     assert np.abs(out2.cpu().numpy() - ref2).max() <= 1e-12 * np.abs(ref2).max()
     assert torch.equal(out2, arts_weights(fft.detach(), torch.tensor(wm, device="cuda"), None))   # deterministic
+
+
+def test_angular_full_with_an_ion_spectrum():
+    """postprocess_theory applies add_ion_IRF whatever the spectype (thomson_diagnostic.py:61-62): with load_ion_spec on, the
+    ARTS diagnostic also returns the (un-batched) ion spectrum of its single parameter set."""
+    from tsadar_b200.thomson_diagnostic import ThomsonScatteringDiagnostic
+    from tsadar_b200.ts_params import ThomsonParams
+    cfg, sa, batch = _arts_setup(1024)
+    cfg["other"]["extraoptions"]["load_ion_spec"] = True
+    p = P.thomson_params(cfg["parameters"], activate=True)
+    ts_diag = ThomsonScatteringDiagnostic(cfg, scattering_angles=sa)
+    tp = ThomsonParams(cfg["parameters"], num_params=1, batch=False, activate=True)
+    ThryE, ThryI, lamE, lamI = ts_diag(tp, batch)
+    gI = O.Grids(cfg["other"]["lamrangI"], 1024)
+    lI, mI = O.fit_model_ion(p, gI, sa, cfg["parameters"]["general"]["Te_gradient"]["num_grad_points"])
+    lI, tI = O.add_ion_irf(lI, mI, 1.0, float(p["general"]["amp3"]), cfg["other"]["PhysParams"]["widIRF"]["spect_stddev_ion"],
+                           cfg["other"]["PhysParams"]["norm"])
+    assert ThryI.shape == (1024,)
+    assert np.abs(ThryI.detach().cpu().numpy() - tI).max() / np.abs(tI).max() < 1e-5
+    np.testing.assert_allclose(np.asarray(lamI), lI, rtol=1e-12)
+    assert isinstance(ThryE, torch.Tensor) and ThryE.shape[0] == cfg["data"]["lineouts"]["end"] - cfg["data"]["lineouts"]["start"]

@@ -86,9 +86,11 @@ class FitModel:
             self._wmat = np.asarray(scattering_angles["weights"], dtype=np.float64)   # [1024, A]
             assert self._wmat.ndim == 2 and self._wmat.shape[1] == nA
             self._w = np.ones(nA)
+            self._w_ion = np.ascontiguousarray(self._wmat[0])      # ion_spectrum always sums with weights[0] (:165): row 0 of the matrix
         else:
             w0 = np.asarray(scattering_angles["weights"])[0]
             self._w = np.full(nA, float(w0)) if np.ndim(w0) == 0 else np.asarray(w0, dtype=np.float64)
+            self._w_ion = self._w
         lamE = np.linspace(oth["lamrangE"][0], oth["lamrangE"][1], oth["npts"])
         self._jmulE = None
         # iawoff (generate_spectra.py:199-208, "set the ion feature to 0"): as written the branch is ill-formed (its two indices
@@ -114,9 +116,30 @@ class FitModel:
             inside = inside[:1]
         return torch.where(inside, torch.zeros((), dtype=modlE.dtype, device=modlE.device), modlE)
 
+    def _spectrum_2v(self, ff_obj, all_params, jmul, weights):
+        """dim == 2 with a non-ARTS spectype (generate_spectra.py:159-160, 187-188 + :164-165, 193, 197): calc_in_2D, mean over
+        the gradient points, weighted angle sum -- the contraction kernel with a one-row weight matrix."""
+        ff, _ = ff_obj.calc_in_2D(all_params)                                          # [G, W, A]
+        dev = ff.device
+        w = torch.tensor(np.ascontiguousarray(weights).reshape(1, -1), dtype=torch.float64, device=dev)
+        jm = None if jmul is None else torch.tensor(np.ascontiguousarray(jmul), dtype=torch.float64, device=dev)
+        return arts_weights(ff, w, jm)                                                 # [1, W]
+
+    @staticmethod
+    def _block_2v(all_params, dev):
+        """the one-row parameter block of a 2V parameter set (the instrument stage reads lam and the amplitudes from it)"""
+        p1 = {k: (dict(v) if isinstance(v, dict) else v) for k, v in all_params.items()}
+        p1["electron"]["fe"] = torch.zeros(4, dtype=torch.float64)
+        p1["electron"]["v"] = np.zeros(4)
+        return pack_params(p1, dev)[0][:1].contiguous()
+
     def ion_spectrum(self, all_params):
+        if self.config["other"]["extraoptions"]["load_ion_spec"] and self.dim == 2:
+            modlI = self._spectrum_2v(self.ion_form_factor, all_params, None, self._w_ion)
+            lamI = np.linspace(*self.config["other"]["lamrangI"], self.config["other"]["npts"])
+            return lamI, modlI, self._block_2v(all_params, modlI.device)
         if self.config["other"]["extraoptions"]["load_ion_spec"]:
-            modlI, block = self.ion_form_factor.modl(all_params, self._w)
+            modlI, block = self.ion_form_factor.modl(all_params, self._w_ion)
             lamI = np.linspace(*self.config["other"]["lamrangI"], self.config["other"]["npts"])
             return lamI, modlI, block
         return np.zeros(1), 0, None
@@ -150,7 +173,12 @@ class FitModel:
             lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
             return lamE, modlE, block
         if self.config["other"]["extraoptions"]["load_ele_spec"] and self.dim == 2:
-            raise NotImplementedError("2V distributions with a temporal/imaging spectype: no reference deck (calc_in_2D is wired for angular_full)")
+            modlE = self._spectrum_2v(self.electron_form_factor, all_params, self._jmulE, self._w)
+            block = self._block_2v(all_params, modlE.device)
+            if self._iawoff:
+                modlE = self._apply_iawoff(modlE, block)
+            lamE = np.linspace(*self.config["other"]["lamrangE"], self.config["other"]["npts"])
+            return lamE, modlE, block
         if self.config["other"]["extraoptions"]["load_ele_spec"]:
             modlE, block = self.electron_form_factor.modl(all_params, self._w, jmul=self._jmulE)
             if self._iawoff:

@@ -70,8 +70,14 @@ class ThomsonScatteringDiagnostic:
     def _call_angular(self, physical_params, batch, dev):
         """spectype "angular_full" (thomson_diagnostic.py:131-142 with :58-61, 136-137): electron spectrum only."""
         oth = self.cfg["other"]
+        ThryI, lamAxisI = 0, []
         if oth["extraoptions"]["load_ion_spec"]:
-            raise NotImplementedError("angular_full with an ion spectrum: no reference deck does this")
+            # postprocess_theory runs add_ion_IRF whatever the spectype (thomson_diagnostic.py:61-62): one parameter set, one
+            # un-batched ion spectrum beside the image (no reference deck loads both)
+            lamI, modlI, blockI = self.model.ion_spectrum(physical_params)
+            noise_i = self._noise(batch["noise_i"], 1, dev)
+            lamAxisI, ThryI = irf.add_ion_IRF(self.cfg, oth["lamrangI"], oth["npts"], modlI, _dev_vec(batch["i_amps"], 1, dev), blockI, noise_i)
+            ThryI = ThryI[0]
         lamE, modlE, block = self.model.electron_spectrum(physical_params)
         n_lam_data = np.asarray(batch["e_data"]).shape[1]
         if self._ats is None:
@@ -85,4 +91,4 @@ class ThomsonScatteringDiagnostic:
         if not (noise.size == 1 and float(noise.reshape(-1)[0]) == 0.0):
             noise_t = torch.as_tensor(np.broadcast_to(noise, (st.nrows, st.nl)).copy(), dtype=torch.float64, device=dev)
         ThryE = st(modlE, block, e_amps, noise_t)
-        return ThryE, 0, st.lam_units, []
+        return ThryE, ThryI, st.lam_units, lamAxisI
