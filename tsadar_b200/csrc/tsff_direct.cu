@@ -66,6 +66,7 @@ DirectLayout direct_layout(const tsff_ctx* c, int64_t B) {
 struct DirectArgs {
   // static
   int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  int stage_fe;   // forward: the f table is staged into shared memory behind the blob
   double lam_shift, v0, dv;
   const double *omgs, *costh, *wts, *jmul;
   ZTab zt;
@@ -201,9 +202,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_cons
   const int M = a.nodes - 1;
   const TreeBlob tb = tree_blob(a.npad);
   if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
-  if (PREC == TSFF_PV_FP32) stage_blob(smem_raw, a.D + b * tb.bytes, (uint32_t)tb.bytes, &bar);
-  else __syncthreads();
+  // the lineout's f table rides along with the blob (same bulk copy, same barrier) when it is a float table that keeps three
+  // CTAs per SM: the exact zone (7 nodes around the pole) and the lerps of f and f' gather from it per lane -- from shared
+  // memory instead of 32 scattered global loads per warp (the region held 20 % of the kernel's stall samples)
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
+  if (PREC == TSFF_PV_FP32) {
+    const uint32_t febytes = a.stage_fe ? (uint32_t)(a.V * sizeof(T)) : 0u;
+    stage_blob2(smem_raw, a.D + b * tb.bytes, (uint32_t)tb.bytes, smem_raw + tb.bytes, fe, febytes, &bar);
+    if (a.stage_fe) fe = reinterpret_cast<const T*>(smem_raw + tb.bytes);
+  } else {
+    __syncthreads();
+  }
   const int WA = a.W * a.A;
 
   TreePole tp[R];
@@ -409,7 +418,14 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
   }
   TSFF_LAUNCH_OK("k_direct_prep");
   const int WA = c->W * c->A;
-  const size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
+  size_t smem = (size_t)tree_blob(c->pv_npad).bytes;
+  // stage the f table too when it is 16-byte copyable and three CTAs per SM still fit (float tables up to ~4096 nodes)
+  {
+    const size_t febytes = (size_t)c->V * sizeof(T);
+    const bool aligned = febytes % 16 == 0 && (reinterpret_cast<uintptr_t>(fe) % 16 == 0);
+    a.stage_fe = (c->pv_precision != TSFF_PV_FP64 && aligned && 3 * (smem + febytes + 1024) <= 228 * 1024) ? 1 : 0;
+    if (a.stage_fe) smem += febytes;
+  }
   // poles per thread: 2 while the grid still fills the device, else 1 (4 poles/thread at 128 registers measured 7% slower)
   const long long tiles4 = (WA + 4 * kThreads - 1) / (4 * kThreads), tiles2 = (WA + 2 * kThreads - 1) / (2 * kThreads);
   if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));

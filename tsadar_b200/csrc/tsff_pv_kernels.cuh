@@ -32,6 +32,20 @@ __device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t 
   mbar_wait(bar, 0);
 }
 
+// The same with a second region (the lineout's f table) on the same mbarrier: dst2 / src2 / bytes2 (bytes2 = 0: none).
+__device__ __forceinline__ void stage_blob2(void* dst, const void* src, uint32_t bytes, void* dst2, const void* src2, uint32_t bytes2,
+                                            uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes + bytes2);
+    for (uint32_t o = 0; o < bytes; o += 32768u)
+      bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, min(32768u, bytes - o), bar);
+    if (bytes2) bulk_g2s(dst2, src2, bytes2, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
 // Static tables of the expansion (tree_static_entry): built once per context / call.
 static __global__ void __launch_bounds__(256) k_tree_static(int M, double* out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kTreeStaticDoubles; i += gridDim.x * blockDim.x) out[i] = tree_static_entry(i, M);
