@@ -116,13 +116,10 @@ __device__ __forceinline__ void tree_prep_cta_f(PGet pget, int M, int npad, unsi
         const int i = kTS0 * b0 + o;
         const double pv = (i >= 1 && i <= M - 1) ? pget(i) : 0.0;
         wv[o] = (float)pv;
-        const double x = -((double)o - 0.5 * (double)(kTS0 - 1)) * (1.0 / kTs0);   // exact
-        double pw = pv;
+        // m0[k] += p x_o^k with x_o = -(o - 7.5) / 8: o and k are unrolled, so the powers fold to immediate operands (one DFMA
+        // per (node, order) instead of a DADD and a DMUL)
 #pragma unroll
-        for (int k = 0; k < kTK; k++) {
-          m0[k] += pw;
-          pw *= x;
-        }
+        for (int k = 0; k < kTK; k++) m0[k] = fma(pv, tree_xpow0(o, k), m0[k]);
       }
       float4* w4 = reinterpret_cast<float4*>(Wt + kTS0 * b0);
 #pragma unroll

@@ -102,6 +102,13 @@ TSFF_HD constexpr double tree_cm(int m, int j, double s) {
   for (int i = 0; i < 2 * j; i++) s2j /= s;
   return tree_binom(m, 2 * j) / ((double)(2 * j + 1) * (double)(j + 1)) * s2j;
 }
+// x_o^k for the level-0 in-block coordinate x_o = -(o - (kTS0 - 1)/2) / kTs0 of offset o (exact dyadic rationals up to rounding)
+TSFF_HD constexpr double tree_xpow0(int o, int k) {
+  const double x = -((double)o - 0.5 * (double)(kTS0 - 1)) * (1.0 / kTs0);
+  double v = 1.0;
+  for (int q = 0; q < k; q++) v *= x;
+  return v;
+}
 // moment translation child c (of four) -> parent: x_parent = (x_child - D) / 4 with D = 2 c - 3, so
 //   mu_parent_k += sum_{j <= k} T(c, k, j) mu_child_j,   T = C(k, j) (-D)^(k-j) / 4^k     (exact in double)
 TSFF_HD constexpr double tree_T(int c, int k, int j) {
