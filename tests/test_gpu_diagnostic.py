@@ -59,15 +59,17 @@ def test_irf_kernel_matches_oracle_batch():
         np.testing.assert_allclose(thI.cpu().numpy()[b], refI, rtol=1e-9, atol=1e-14)
 
 
-def test_loss_and_gradients_full_chain():
+@pytest.mark.parametrize("npts,nvx", [(1024, 64), (5120, 128)])
+def test_loss_and_gradients_full_chain(npts, nvx):
     """LossFunction.vg_loss on a 2-lineout batch: loss and d loss / d (normalised active params) vs the torch-f64
-    oracle of the same chain (ThomsonParams transforms -> form factor -> IRF -> masked L2 nanmean)."""
+    oracle of the same chain (ThomsonParams transforms -> form factor -> IRF -> masked L2 nanmean).  (5120, 128) is the 1d
+    deck at its OWN shape (BASELINE.json configs[0]: W = 5120 = 1024 pixels x 5 points, A = 10, f on 128 nodes)."""
     from tsadar_b200.loss_function import LossFunction
     from tsadar_b200.ts_params import ThomsonParams
     cfg = load_cfg("cfg_1d")
-    cfg["other"]["points_per_pixel"] = 1
-    cfg["other"]["npts"] = 1024
-    cfg["parameters"]["electron"]["fe"]["nvx"] = 64
+    cfg["other"]["points_per_pixel"] = npts // 1024
+    cfg["other"]["npts"] = npts
+    cfg["parameters"]["electron"]["fe"]["nvx"] = nvx
     B = 2
     rng = np.random.default_rng(1)
     lamb = np.linspace(400, 700, 1024)
@@ -83,7 +85,7 @@ def test_loss_and_gradients_full_chain():
     names = [k for k, s in tp.leaves.items() if s.active]
 
     # ---- oracle: same chain in torch float64 on the CPU
-    grids = O.Grids(cfg["other"]["lamrangE"], 1024)
+    grids = O.Grids(cfg["other"]["lamrangE"], npts)
     w0 = float(SA_P9["weights"][0])
     fb, fr_ = 528 - 12, 528 + 12
     jmul = np.where((fb < grids.lam_axis) & (fr_ > grids.lam_axis), 1e-4, 1.0)
