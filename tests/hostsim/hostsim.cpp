@@ -117,6 +117,62 @@ int main() {
     }
     printf("point chain checked\n");
   }
+  // ---- 2b. the "_x" point chain (invariant reciprocals hoisted) against the plain one: values and every cotangent
+  {
+    const double lam_nm[4] = {450.0, 526.2, 526.6, 610.0};
+    double worst = 0;
+    for (int c = 0; c < 4; c++) {
+      const double omgs = 2e7 * kPi * kC / lam_nm[c], cth = cos((50.0 + 7 * c) * kPi / 180);
+      LG L; lg_zero(L); lg_forward(params, nI, 0, 1, lam_shift, L);
+      LGX X; lgx_make(L, nI, T.zt.h, X);
+      Kin q; kin_forward(L, omgs, cth, q);
+      KinX qx; kin_forward_x(L, X, omgs, cth, qx);
+      IonOut io; ion_forward(L, nI, T.zt, q, io);
+      IonX iox; ion_forward_x<0>(L, X, nI, T.zt, qx, iox);
+      IonX iox2; ion_forward_x<2>(L, X, 0, T.zt, qx, iox2);
+      const double chiEr = -q.ikl2 * 0.3, chiEi = kPi * q.ikl2 * 0.2, fp = 0.37;
+      Asm s; const double P = assemble_forward(L, q, io, chiEr, chiEi, fp, omgs, s);
+      AsmX sx; const double Px = assemble_forward_x(L, X, qx, iox, chiEr, chiEi, fp, omgs, sx);
+      PointBar pb, pbx; KinBar kb = {0, 0, 0, 0, 0, 0}, kbx = {0, 0, 0, 0, 0, 0}; LG Lb, Lbx; lg_zero(Lb); lg_zero(Lbx);
+      assemble_backward(L, nI, T.zt, q, io, chiEr, chiEi, fp, s, 1.3, pb, kb, Lb);
+      assemble_backward_x<0>(L, X, nI, qx, iox, chiEr, chiEi, fp, sx, 1.3, pbx, kbx, Lbx);
+      kb.ikl2 += 0.11 * pb.chiEr; kb.xie += 0.7 * pb.fphi;
+      kbx.ikl2 += 0.11 * pbx.chiEr; kbx.xie += 0.7 * pbx.fphi;
+      kin_backward(L, omgs, cth, q, kb, Lb);
+      kin_backward_x(L, X, cth, qx, kbx, Lbx);
+      double a[kLGDoubles + 8], b[kLGDoubles + 8];
+      a[0] = Lb.ne_g; a[1] = Lb.omgL; a[2] = Lb.omgpe2; a[3] = Lb.kL; a[4] = Lb.vTe; a[5] = Lb.Va6; a[6] = Lb.ud6;
+      b[0] = Lbx.ne_g; b[1] = Lbx.omgL; b[2] = Lbx.omgpe2; b[3] = Lbx.kL; b[4] = Lbx.vTe; b[5] = Lbx.Va6; b[6] = Lbx.ud6;
+      for (int i = 0; i < TSFF_MAX_IONS; i++) {
+        a[7 + i] = Lb.c_kldi[i]; a[11 + i] = Lb.inv_s2vTi[i]; a[15 + i] = Lb.ioncf[i];
+        b[7 + i] = Lbx.c_kldi[i]; b[11 + i] = Lbx.inv_s2vTi[i]; b[15 + i] = Lbx.ioncf[i];
+      }
+      a[19] = P; b[19] = Px; a[20] = q.xie; b[20] = qx.xie; a[21] = q.ikl2; b[21] = qx.ikl2;
+      a[22] = pb.chiEr; b[22] = pbx.chiEr; a[23] = pb.chiEi; b[23] = pbx.chiEi; a[24] = pb.fphi; b[24] = pbx.fphi;
+      a[25] = io.chiIr; b[25] = iox2.chiIr; a[26] = io.sion; b[26] = iox2.sion;
+      for (int k = 0; k < 27; k++) {
+        const double e = relerr(a[k], b[k]);
+        if (a[k] != 0.0 || b[k] != 0.0) worst = std::max(worst, e);
+        if (e > 1e-11) { printf("FAIL x-chain lam=%g k=%d plain=%.15e x=%.15e\n", lam_nm[c], k, a[k], b[k]); fails++; }
+      }
+    }
+    // Hermite / lerp with the inverse spacing passed in
+    const int V = 64; const double x0 = -6 + 6.0 / V, h = 12.0 / V;
+    std::vector<double> lnf(V), sl(V);
+    for (int i = 0; i < V; i++) { double x = x0 + i * h; lnf[i] = -0.5 * x * x; sl[i] = -x; }
+    for (double x : {-5.9, -5.5, -1.234, 0.0, 0.777, 4.9, 5.9, 7.0}) {
+      Herm h1, h2;
+      const double H1 = hermite_uniform(lnf.data(), sl.data(), V, x0, h, x, -50.0, h1);
+      const double H2 = hermite_uniform_ih(lnf.data(), sl.data(), V, x0, h, 1.0 / h, x, -50.0, h2);
+      int i1, i2; double t1, t2, s1, s2;
+      const double l1 = lerp_uniform(lnf.data(), V, x0, h, x, i1, t1, s1), l2 = lerp_uniform_ih(lnf.data(), V, x0, 1.0 / h, x, i2, t2, s2);
+      if (relerr(H1, H2) > 1e-13 || fabs(h1.dHdx - h2.dHdx) > 1e-12 * std::max(1.0, fabs(h1.dHdx)) || h1.inside != h2.inside ||
+          (h1.i != h2.i && fabs(h1.t + (h1.i - h2.i) - h2.t) > 1e-9) || relerr(l1, l2) > 1e-13 || fabs(s1 - s2) > 1e-12 * std::max(1.0, fabs(s1))) {
+        printf("FAIL hermite/lerp ih x=%g H %.15e %.15e dH %.12e %.12e lerp %.15e %.15e\n", x, H1, H2, h1.dHdx, h2.dHdx, l1, l2); fails++;
+      }
+    }
+    printf("x-chain vs plain chain: worst rel diff %.2e\n", worst);
+  }
   // ---- 3. PV sums
   {
     const int N = 512; const double z0 = -6 + 6.0 / N, h = 12.0 / N;

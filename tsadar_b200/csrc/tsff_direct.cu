@@ -276,10 +276,21 @@ __global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, cons
 #ifndef TSFF_BWDP_RB
 #define TSFF_BWDP_RB 4
 #endif
+#ifndef TSFF_BWDP_SMEM_LB
+#define TSFF_BWDP_SMEM_LB 0
+#endif
 template <int R, typename T>
 __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(const DirectArgs a) {
   __shared__ LG sL;
   __shared__ double sred[kLGDoubles * (kThreads / 32)];
+#if TSFF_BWDP_SMEM_LB
+  // the per-thread LG cotangent accumulators (19 doubles) live in shared memory, 21-double stride (conflict-free for 64-bit
+  // accesses), so that the kernel fits three CTAs per SM
+  __shared__ double s_Lb[kThreads][21];
+  LG& Lb = *reinterpret_cast<LG*>(&s_Lb[threadIdx.x][0]);
+#else
+  LG Lb;
+#endif
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
@@ -288,7 +299,6 @@ __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(c
   __syncthreads();
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int WA = a.W * a.A;
-  LG Lb;
   lg_zero(Lb);
   for (int r = 0; r < R; r++) {
     const int idx = (tile * kThreads + threadIdx.x) * R + r;

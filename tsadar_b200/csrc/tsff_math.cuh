@@ -518,6 +518,211 @@ TSFF_HD void kin_backward(const LG& L, double omgs, double cth, const Kin& q, Ki
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same point chain with the loop-invariant reciprocals taken out ("_x" variants, used by the 1V kernels).
+// A (lineout, gradient point) has ~8 reciprocals that do not depend on (omega, angle): 1/vTe, 1/omgL, 1/omgpe2, 1/c_kldi,
+// 1/c_kldi^2, ...; 1/k and 1/ks come for free with the square roots (Goldschmidt carries 1/(2 sqrt x)); 1/(k eps^2) is
+// formed once and handed from the forward assembly to its reverse, as are the ions' Z' cell values and exp(-xii^2).
+// Per point this leaves ONE FP64 reciprocal (1/eps^2) and two square roots, against ~26 MUFU seeds + Newton steps before.
+// Results differ from the plain functions by rounding only (tests/hostsim checks both against each other).
+// ------------------------------------------------------------------------------------------------
+struct LGX {
+  double ivTe, iomgL, iomgpe2, opv, kL2, zih;          // opv = omgpe2 / vTe^2 ; zih = 1 / (Z' table spacing)
+  double ickl[TSFF_MAX_IONS], ickl2[TSFF_MAX_IONS];    // 1 / c_kldi, 1 / c_kldi^2
+};
+TSFF_HD void lgx_make(const LG& L, int nI, double zh, LGX& X) {
+  X.ivTe = 1.0 / L.vTe;
+  X.iomgL = 1.0 / L.omgL;
+  X.iomgpe2 = 1.0 / L.omgpe2;
+  X.opv = L.omgpe2 * X.ivTe * X.ivTe;
+  X.kL2 = L.kL * L.kL;
+  X.zih = 1.0 / zh;
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    X.ickl[i] = i < nI ? 1.0 / L.c_kldi[i] : 0.0;
+    X.ickl2[i] = X.ickl[i] * X.ickl[i];
+  }
+}
+
+// sqrt(x) and 1/sqrt(x) together (x a positive normal number)
+TSFF_HD void fast_sqrt_rsqrt(double x, double& s, double& r) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * y, g = x * y;
+  double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  s = fma(fma(-g, g, x), h, g);
+  r = h + h;
+#else
+  s = sqrt(x);
+  r = 1.0 / s;
+#endif
+}
+
+struct KinX {
+  double ks, k2, k, omgdop, w, xie, ikl2;   // as Kin
+  double ik, ik2, iks;                      // 1/k, 1/k^2, 1/ks
+};
+
+TSFF_HD void kin_forward_x(const LG& L, const LGX& X, double omgs, double cth, KinX& q) {
+  double rs;
+  fast_sqrt_rsqrt(omgs * omgs - L.omgpe2, q.ks, rs);
+  q.ks *= (1.0 / kC);
+  q.iks = rs * kC;
+  q.k2 = q.ks * q.ks + X.kL2 - 2.0 * q.ks * L.kL * cth;
+  fast_sqrt_rsqrt(q.k2, q.k, q.ik);
+  q.ik2 = q.ik * q.ik;
+  q.omgdop = omgs - L.omgL - q.k * L.Va6;
+  q.w = q.omgdop * q.ik;
+  q.xie = (q.w - L.ud6) * X.ivTe;
+  q.ikl2 = X.opv * q.ik2;
+}
+
+// Z' lookup with the inverse spacing passed in; mode / cell as zprime_lerp_cell
+TSFF_HD void zprime_lerp_x(const ZTab& z, double ih, double x, double& zr, double& zi, double& dzr, double& dzi, int mode,
+                           int* cell) {
+  int i;
+  if (mode == 2) {
+    i = *cell;
+  } else {
+    i = -1;
+    if (!(x < z.x0 || x > z.xlast)) {
+      i = (int)((x - z.x0) * ih);
+      i = i > z.n - 2 ? z.n - 2 : (i < 0 ? 0 : i);
+    }
+    if (mode == 1) *cell = i;
+  }
+  if (i < 0) {
+    const double ix = fast_rcp(x);
+    zr = ix * ix;
+    dzr = -2.0 * zr * ix;
+    zi = 0.0;
+    dzi = 0.0;
+    return;
+  }
+  const double t = (x - z.x0) * ih - (double)i;
+  const double r0 = z.zr[i], r1 = z.zr[i + 1], i0 = z.zi[i], i1 = z.zi[i + 1];
+  zr = r0 + t * (r1 - r0);
+  zi = i0 + t * (i1 - i0);
+  dzr = (r1 - r0) * ih;
+  dzi = (i1 - i0) * ih;
+}
+
+// ion susceptibility; keeps what its reverse needs (per ion: xii, 1/(k lambda_Di)^2, the Z' values / slopes, exp(-xii^2))
+struct IonX {
+  double chiIr, chiIi, sion;
+  double xii[TSFF_MAX_IONS], ikldi2[TSFF_MAX_IONS], zr[TSFF_MAX_IONS], zi[TSFF_MAX_IONS], dzr[TSFF_MAX_IONS],
+      dzi[TSFF_MAX_IONS], E[TSFF_MAX_IONS];
+};
+
+// NI > 0: the ion count at compile time (the per-ion arrays of the unused slots then cost no registers); NI == 0: nI at run time
+template <int NI>
+TSFF_HD void ion_forward_x(const LG& L, const LGX& X, int nI, const ZTab& zt, const KinX& q, IonX& o, int cell_mode = 0,
+                           int* cells = nullptr) {
+  o.chiIr = o.chiIi = o.sion = 0.0;
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    if (NI > 0 ? i >= NI : i >= nI) break;
+    const double xii = L.inv_s2vTi[i] * q.w;
+    const double ikldi2 = X.ickl2[i] * q.ik2;
+    zprime_lerp_x(zt, X.zih, xii, o.zr[i], o.zi[i], o.dzr[i], o.dzi[i], cell_mode, cells + i);
+    o.xii[i] = xii;
+    o.ikldi2[i] = ikldi2;
+    o.E[i] = fast_exp_neg(-xii * xii);
+    o.chiIr += -0.5 * ikldi2 * o.zr[i];
+    o.chiIi += -0.5 * ikldi2 * o.zi[i];
+    o.sion += L.ioncf[i] * o.E[i];
+  }
+}
+
+constexpr double kCP = kRe * kRe / (2.0 * kPi * kC);   // re^2 * 2 pi C / lams^2 = kCP * omgs^2
+
+struct AsmX {
+  double er, ei, eps2, ce2, a1, Sion, Sele, dop, cP, P, ike;   // ike = 1 / (k eps2)
+};
+
+TSFF_HD double assemble_forward_x(const LG& L, const LGX& X, const KinX& q, const IonX& io, double chiEr, double chiEi,
+                                  double fphi, double omgs, AsmX& s) {
+  const double ci = 1.0 + io.chiIr;
+  s.er = ci + chiEr;
+  s.ei = chiEi + io.chiIi;
+  s.eps2 = s.er * s.er + s.ei * s.ei;
+  s.ce2 = chiEr * chiEr + chiEi * chiEi;
+  s.a1 = ci * ci + io.chiIi * io.chiIi;
+  s.ike = q.ik * fast_rcp(s.eps2);
+  s.Sion = io.sion * s.ce2 * kInvSqrt2Pi * s.ike;
+  s.Sele = s.a1 * fphi * s.ike * X.ivTe;
+  s.dop = 1.0 + 2.0 * q.omgdop * X.iomgL;
+  s.cP = omgs * omgs * kCP;
+  s.P = (s.Sion + s.Sele) * s.dop * L.ne_g * s.cP;
+  return s.P;
+}
+
+template <int NI>
+TSFF_HD void assemble_backward_x(const LG& L, const LGX& X, int nI, const KinX& q, const IonX& io, double chiEr, double chiEi,
+                                 double fphi, const AsmX& s, double Pbar, PointBar& pb, KinBar& kb, LG& Lb) {
+  const double Ssum = s.Sion + s.Sele;
+  const double pc = Pbar * s.cP;
+  const double Ssum_bar = pc * s.dop * L.ne_g;
+  const double dop_bar = pc * Ssum * L.ne_g;
+  Lb.ne_g += pc * Ssum * s.dop;
+  const double t2 = dop_bar * 2.0 * X.iomgL;
+  kb.omgdop += t2;
+  Lb.omgL += -t2 * q.omgdop * X.iomgL;
+  const double sk = Ssum_bar * s.ike;                 // Ssum_bar / (k eps2)
+  const double sion_bar = sk * s.ce2 * kInvSqrt2Pi;
+  const double ce2_bar = sk * io.sion * kInvSqrt2Pi;
+  const double eps2_bar = -sk * Ssum * q.k;
+  kb.k += -Ssum_bar * Ssum * q.ik;
+  const double skv = sk * X.ivTe;
+  const double a1_bar = skv * fphi;
+  pb.fphi = skv * s.a1;
+  Lb.vTe += -Ssum_bar * s.Sele * X.ivTe;
+  const double er_bar = 2.0 * s.er * eps2_bar, ei_bar = 2.0 * s.ei * eps2_bar;
+  pb.chiEr = er_bar + 2.0 * chiEr * ce2_bar;
+  pb.chiEi = ei_bar + 2.0 * chiEi * ce2_bar;
+  const double chiIr_bar = er_bar + 2.0 * (1.0 + io.chiIr) * a1_bar;
+  const double chiIi_bar = ei_bar + 2.0 * io.chiIi * a1_bar;
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    if (NI > 0 ? i >= NI : i >= nI) break;
+    const double xii = io.xii[i], ikldi2 = io.ikldi2[i], E = io.E[i];
+    Lb.ioncf[i] += sion_bar * E;
+    double xii_bar = sion_bar * L.ioncf[i] * E * (-2.0 * xii);
+    const double ikldi2_bar = -0.5 * (io.zr[i] * chiIr_bar + io.zi[i] * chiIi_bar);
+    xii_bar += -0.5 * ikldi2 * (io.dzr[i] * chiIr_bar + io.dzi[i] * chiIi_bar);
+    const double ib = ikldi2_bar * ikldi2;
+    Lb.c_kldi[i] += -2.0 * ib * X.ickl[i];
+    kb.k2 += -ib * q.ik2;
+    Lb.inv_s2vTi[i] += xii_bar * q.w;
+    kb.w += xii_bar * L.inv_s2vTi[i];
+  }
+}
+
+TSFF_HD void kin_backward_x(const LG& L, const LGX& X, double cth, const KinX& q, KinBar kb, LG& Lb) {
+  const double ib = kb.ikl2 * q.ikl2;                 // ikl2 = omgpe2 / (vTe^2 k2)
+  Lb.omgpe2 += ib * X.iomgpe2;
+  kb.k2 += -ib * q.ik2;
+  const double xv = kb.xie * X.ivTe;                  // xie = (w - ud6) / vTe
+  kb.w += xv;
+  Lb.ud6 += -xv;
+  Lb.vTe += -(2.0 * ib + kb.xie * q.xie) * X.ivTe;
+  const double wk = kb.w * q.ik;                      // w = omgdop / k
+  kb.omgdop += wk;
+  kb.k += -wk * q.w;
+  Lb.omgL += -kb.omgdop;                              // omgdop = omgs - omgL - k Va6
+  kb.k += -kb.omgdop * L.Va6;
+  Lb.Va6 += -kb.omgdop * q.k;
+  kb.k2 += kb.k * (0.5 * q.ik);                       // k = sqrt(k2)
+  const double ks_bar = kb.k2 * (2.0 * q.ks - 2.0 * L.kL * cth);   // k2 = ks^2 + kL^2 - 2 ks kL cth
+  Lb.kL += kb.k2 * (2.0 * L.kL - 2.0 * q.ks * cth);
+  Lb.omgpe2 += -ks_bar * (0.5 / (kC * kC)) * q.iks;  // ks = sqrt(omgs^2 - omgpe2) / C
+}
+
+// ------------------------------------------------------------------------------------------------
 // interpax cubic Hermite on a uniform grid with pre-computed node slopes (form_factor.py:256,263;
 // SURVEY.md A-note 1).  lnf[V], slope[V]; returns H(x) (or `fill` outside [x0, x_last]) and the pieces
 // for the adjoint.
@@ -547,6 +752,46 @@ TSFF_HD double hermite_uniform(const double* lnf, const double* slope, int V, do
   o.i = i; o.t = t; o.inside = true;
   o.dHdx = (m0 + t * (2.0 * c2 + 3.0 * c3 * t)) / h;
   return f0 + t * (m0 + t * (c2 + c3 * t));
+}
+
+// the same with the inverse spacing passed in (no FP64 divisions: the table kernels evaluate this once per (omega, angle))
+TSFF_HD double hermite_uniform_ih(const double* lnf, const double* slope, int V, double x0, double h, double ih, double x,
+                                  double fill, Herm& o) {
+  const double xlast = x0 + (double)(V - 1) * h;
+  if (x < x0 || x > xlast || !(x == x)) {
+    o.i = 0; o.t = 0.0; o.dHdx = 0.0; o.inside = false;
+    return fill;
+  }
+  const double u = (x - x0) * ih;
+  int i = (int)u + 1;                       // u >= 0 here
+  if (i > V - 1) i = V - 1;
+  const double t = u - (double)(i - 1);
+  const double f0 = lnf[i - 1], f1 = lnf[i], m0 = slope[i - 1] * h, m1 = slope[i] * h;
+  const double d = f1 - f0;
+  const double c2 = 3.0 * d - 2.0 * m0 - m1;
+  const double c3 = m0 + m1 - 2.0 * d;
+  o.i = i; o.t = t; o.inside = true;
+  o.dHdx = (m0 + t * (2.0 * c2 + 3.0 * c3 * t)) * ih;
+  return f0 + t * (m0 + t * (c2 + c3 * t));
+}
+
+// lerp_uniform with the inverse spacing passed in
+template <typename T>
+TSFF_HD double lerp_uniform_ih(const T* f, int n, double x0, double ih, double x, int& i, double& t, double& slope) {
+  const double u = (x - x0) * ih;
+  if (!(u > 0.0)) {  // left clamp (also NaN)
+    i = 0; t = 0.0; slope = 0.0;
+    return (double)f[0];
+  }
+  if (u >= (double)(n - 1)) {
+    i = n - 2; t = 1.0; slope = 0.0;
+    return (double)f[n - 1];
+  }
+  i = (int)u;
+  t = u - (double)i;
+  const double a = (double)f[i], b = (double)f[i + 1];
+  slope = (b - a) * ih;
+  return a + t * (b - a);
 }
 
 // adjoint weights of H wrt (lnf[i-1], lnf[i], slope[i-1], slope[i])

@@ -57,6 +57,7 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
 
 struct TableArgs {
   int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  int kper;     // backward: consecutive wavelengths per thread
   int asplit;   // angle chunks per wavelength tile (ARTS: one lineout, 241 angles -- the grid would not fill the device otherwise)
   double lam_shift, v0, dv, xi1_0, xi1_h, xi2_0, xi2_h;
   const double *omgs, *costh, *wts, *jmul, *xi2;
@@ -169,6 +170,7 @@ template <bool WRITE_FF, bool FROZEN = false>
 __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LG sL;   // CTA-uniform scalars of the (lineout, gradient point)
+  __shared__ LGX sX;  // ... and their reciprocals
   double* s_lnf = reinterpret_cast<double*>(smem_raw);
   double* s_slope = s_lnf + a.V;
   double* s_T = s_slope + a.V;
@@ -186,32 +188,37 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
   const int jc = min(j, a.W - 1);
   const bool out = (lane < kFwdJ) && (j < a.W);
   const double omgs = a.omgs[jc];
+  const double idv = 1.0 / a.dv, ih2 = 1.0 / a.xi2_h;
   double acc = 0.0;
   for (int g = 0; g < a.G; g++) {
     __syncthreads();
-    if (threadIdx.x == 0) load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+    if (threadIdx.x == 0) {
+      load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+      lgx_make(sL, a.nI, a.zt.h, sX);
+    }
     __syncthreads();
     const LG& L = sL;
+    const LGX& X = sX;
     for (int ia = ia0; ia < ia1; ia++) {
-      Kin q;
-      kin_forward(L, omgs, a.costh[ia], q);
+      KinX q;
+      kin_forward_x(L, X, omgs, a.costh[ia], q);
       Herm hm;
-      const double fphi = exp_logf(hermite_uniform(s_lnf, s_slope, a.V, a.v0, a.dv, q.xie, kFillLog, hm));  // :256
+      const double fphi = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));  // :256
       const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
       const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
-      const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) / (xi_n - q.xie) : 0.0;           // :258-259
+      const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) * fast_rcp(xi_n - q.xie) : 0.0;   // :258-259
       if (out) {
         int ip; double tp, slp;
         int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
         const int cm = FROZEN ? a.cell_mode : 0;
         const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
-                                 : lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);      // :270
+                                 : lerp_uniform_ih(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);       // :270
         const double chiEr = -q.ikl2 * Tl;                                                                // :271
         const double chiEi = kPi * q.ikl2 * df;                                                           // :261
-        IonOut io;
-        ion_forward(L, a.nI, a.zt, q, io, cm, cp + 1);
-        Asm s;
-        const double P = assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
+        IonX io;
+        ion_forward_x<0>(L, X, a.nI, a.zt, q, io, cm, cp + 1);
+        AsmX s;
+        const double P = assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
         if (WRITE_FF) a.ff[((b * a.G + g) * (long long)a.W + j) * a.A + ia] = P;
         acc += a.wts[ia] * P;
       }
@@ -221,16 +228,62 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
 }
 
 // ---- backward assembly ----------------------------------------------------------------------------------------
-constexpr int kBwdJ = 30;  // outputs per warp: lanes 1..30; lane 0 = left halo, lane 31 = right halo
-
+// A thread owns `kper` CONSECUTIVE wavelengths of one (lineout, angle chunk) and walks them in order.  The forward difference
+// along omega (form_factor.py:258-259) couples point j to j + 1: the thread looks one point ahead (kinematics + f(xi) only) and
+// carries d loss / d df_j to the next point in two registers; the share of its last forward difference that belongs to the first
+// point of the NEXT thread is applied by this thread itself (the reverse is linear in the cotangents, and the look-ahead already
+// holds that point's kinematics), so threads exchange nothing.  The scatter targets -- the T-table cell and the log-f Hermite cell
+// -- change slowly along omega: each is accumulated in registers over the run of equal cell and flushed with atomics when the
+// cell changes (a move to the adjacent cell keeps the shared node's partial sum in registers); when a whole warp ends on the
+// same cell (the ion-acoustic window: thousands of wavelengths inside a few cells) the final flush is reduced across the warp.
 #ifndef TSFF_TBWD_MINB
-#define TSFF_TBWD_MINB 2      // (3 CTAs per SM at 80 registers and 490 B of spills measured 1.4 % slower)
+#define TSFF_TBWD_MINB 2
 #endif
-template <bool FROZEN>
+#ifndef TSFF_TBWD_K
+#define TSFF_TBWD_K 8          // target wavelengths per thread (lowered at launch until the grid fills the device)
+#endif
+
+__device__ __forceinline__ void run_flush2(double* dst, int k, double v0, double v1) {
+  if (k < 0) return;
+  if (v0 != 0.0) atomicAdd(&dst[k], v0);
+  if (v1 != 0.0) atomicAdd(&dst[k + 1], v1);
+}
+// accumulate (w0, w1) onto cells (k, k + 1) of dst, run-length compressed in (rk, r0, r1)
+__device__ __forceinline__ void run_add2(double* dst, int& rk, double& r0, double& r1, int k, double w0, double w1) {
+  if (k != rk) {
+    if (k == rk + 1) {            // moved one cell up: node rk + 1 stays in registers
+      if (r0 != 0.0) atomicAdd(&dst[rk], r0);
+      r0 = r1; r1 = 0.0;
+    } else if (k == rk - 1) {     // one cell down: node rk stays
+      if (r1 != 0.0) atomicAdd(&dst[rk + 1], r1);
+      r1 = r0; r0 = 0.0;
+    } else {
+      run_flush2(dst, rk, r0, r1);
+      r0 = r1 = 0.0;
+    }
+    rk = k;
+  }
+  r0 += w0;
+  r1 += w1;
+}
+// final flush: one lane issues the atomics when the whole warp ended on the same cell
+__device__ __forceinline__ void run_flush2_warp(double* dst, int k, double v0, double v1) {
+  const int k0 = __shfl_sync(0xffffffffu, k, 0);
+  if (__all_sync(0xffffffffu, k == k0)) {
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    if ((threadIdx.x & 31) == 0) run_flush2(dst, k, v0, v1);
+  } else {
+    run_flush2(dst, k, v0, v1);
+  }
+}
+
+template <bool FROZEN, int NI>
 __global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sred[kLGDoubles * kWarps];
-  __shared__ LG sL;   // the (lineout, gradient point) scalars are CTA-uniform: shared, not 19 doubles of registers per thread
+  __shared__ LG sL;   // the (lineout, gradient point) scalars are CTA-uniform: shared, not registers
+  __shared__ LGX sX;
   double* s_lnf = reinterpret_cast<double*>(smem_raw);
   double* s_slope = s_lnf + a.V;
   double* s_T = s_slope + a.V;
@@ -243,105 +296,107 @@ __global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const Ta
     s_slope[i] = a.slope[b * a.V + i];
   }
   for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = (tile * kWarps + wid) * kBwdJ - 1 + lane;
-  const bool valid = (j >= 0) && (j < a.W);
-  const int jc = min(max(j, 0), a.W - 1);
-  const bool own = valid && lane >= 1 && lane <= kBwdJ;
-  const double omgs = a.omgs[jc];
-  const double mb = (valid && a.modl_bar) ? a.modl_bar[b * a.W + jc] * a.jmul[jc] / (double)a.G : 0.0;
+  const int j0 = (tile * kThreads + threadIdx.x) * a.kper;
+  const int jend = min(j0 + a.kper, a.W);
+  const double idv = 1.0 / a.dv, ih2 = 1.0 / a.xi2_h, iG = 1.0 / (double)a.G;
   double* Tbar = a.Tbar + b * kXi2N;
   double* lnfbar = a.lnfbar + b * a.V;
   double* slopebar = a.slopebar + b * a.V;
+  const double* mbar = a.modl_bar ? a.modl_bar + b * a.W : nullptr;
   for (int g = 0; g < a.G; g++) {
     __syncthreads();   // first pass: the staged tables; later passes: everyone is done with the previous sL
-    if (threadIdx.x == 0) load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+    if (threadIdx.x == 0) {
+      load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
+      lgx_make(sL, a.nI, a.zt.h, sX);
+    }
     __syncthreads();
     const LG& L = sL;
-    LG Lb;             // lanes 1..kBwdJ: cotangents of the points they own; halo lanes: discarded below
+    const LGX& X = sX;
+    LG Lb;
     lg_zero(Lb);
     for (int ia = ia0; ia < ia1; ia++) {
-      const double cth = a.costh[ia];
-      Kin q;
-      kin_forward(L, omgs, cth, q);
-      Herm hm;
-      const double fphi = exp_logf(hermite_uniform(s_lnf, s_slope, a.V, a.v0, a.dv, q.xie, kFillLog, hm));
-      const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
-      const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
-      const bool has_df = valid && (j + 1 < a.W) && (lane < 31);
-      const double delta = has_df ? (xi_n - q.xie) : 1.0;
-      const double df = has_df ? (fphi_n - fphi) / delta : 0.0;
-      // phase 2: reverse of the assembly at this point (lanes 0..30)
-      double dfbar = 0.0;
-      PointBar pb = {0.0, 0.0, 0.0};
-      KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      int ip = 0; double tp = 0.0, slp = 0.0, Tl = 0.0;
-      if (valid && lane < 31) {
-        double Pbar = mb * a.wts[ia];
-        if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
-        int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
-        const int cm = FROZEN ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
-        Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
-                    : lerp_uniform(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp);
-        const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
-        IonOut io;
-        ion_forward(L, a.nI, a.zt, q, io, cm, cp + 1);
-        Asm s;
-        assemble_forward(L, q, io, chiEr, chiEi, fphi, omgs, s);
-        assemble_backward(L, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb, cm, cp + 1);
-        dfbar = has_df ? kPi * q.ikl2 * pb.chiEi : 0.0;
-        kb.ikl2 += -Tl * pb.chiEr + kPi * df * pb.chiEi;
-      }
-      const double dfbar_p = __shfl_up_sync(0xffffffffu, dfbar, 1);
-      const double df_p = __shfl_up_sync(0xffffffffu, df, 1);
-      const double delta_p = __shfl_up_sync(0xffffffffu, delta, 1);
-      // scatter-adds of this point: T table (cells ip, ip + 1) and the log-f Hermite data (nodes hm.i - 1, hm.i).  The cell
-      // indices change slowly along the warp (consecutive wavelengths), so runs of equal index are summed with shuffles
-      // and only the first lane of a run issues the atomics (~20x fewer, and no same-address pile-up in L2).
-      double tb0 = 0.0, tb1 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-      int kT = -1, kH = -1;
-      if (own) {
-        double fphibar = pb.fphi - dfbar / delta;
-        double xiebar = kb.xie + dfbar * df / delta;
-        if (j >= 1) {
-          fphibar += dfbar_p / delta_p;
-          xiebar -= dfbar_p * df_p / delta_p;
+      const double cth = a.costh[ia], wt = a.wts[ia] * iG;
+      int kT = -1, kH = -1;                                   // open runs: T cell (nodes kT, kT + 1); Hermite cell (nodes kH - 1, kH)
+      double tb0 = 0.0, tb1 = 0.0, cf0 = 0.0, cf1 = 0.0, cm0 = 0.0, cm1 = 0.0;
+      if (j0 < a.W) {
+        KinX q;
+        kin_forward_x(L, X, a.omgs[j0], cth, q);
+        Herm hm;
+        double fphi = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));
+        double carry_f = 0.0, carry_x = 0.0;                  // d loss / d (fphi_j, xie_j) through df_{j-1}
+        for (int j = j0; j < jend; j++) {
+          const double omgs = a.omgs[j];
+          // look one point ahead for the forward difference
+          KinX qn = q;
+          Herm hn = hm;
+          double fphi_n = fphi, df = 0.0, idelta = 0.0;
+          const bool has_df = j + 1 < a.W;
+          if (has_df) {
+            kin_forward_x(L, X, a.omgs[j + 1], cth, qn);
+            fphi_n = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, qn.xie, kFillLog, hn));
+            idelta = fast_rcp(qn.xie - q.xie);
+            df = (fphi_n - fphi) * idelta;
+          }
+          // reverse of the assembly at point j
+          double Pbar = mbar ? mbar[j] * a.jmul[j] * wt : 0.0;
+          if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
+          int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+          const int cm = FROZEN ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
+          int ip; double tp, slp;
+          const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
+                                   : lerp_uniform_ih(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);
+          const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
+          IonX io;
+          ion_forward_x<NI>(L, X, a.nI, a.zt, q, io, cm, cp + 1);
+          AsmX s;
+          assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
+          PointBar pb;
+          KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+          assemble_backward_x<NI>(L, X, a.nI, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
+          const double dfbar = has_df ? kPi * q.ikl2 * pb.chiEi : 0.0;
+          kb.ikl2 += -Tl * pb.chiEr + kPi * df * pb.chiEi;
+          const double gd = dfbar * idelta;
+          const double fphibar = pb.fphi - gd + carry_f;
+          double xiebar = kb.xie + gd * df + carry_x;
+          carry_f = gd;
+          carry_x = -gd * df;
+          const double Tlbar = -q.ikl2 * pb.chiEr;
+          xiebar += Tlbar * slp;
+          run_add2(Tbar, kT, tb0, tb1, ip, (1.0 - tp) * Tlbar, tp * Tlbar);
+          if (hm.inside) {
+            const double Hbar = fphibar * fphi;
+            xiebar += Hbar * hm.dHdx;
+            double wf0, wf1, wm0, wm1;
+            hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
+            int kk = kH;
+            run_add2(lnfbar - 1, kk, cf0, cf1, hm.i, Hbar * wf0, Hbar * wf1);
+            run_add2(slopebar - 1, kH, cm0, cm1, hm.i, Hbar * wm0, Hbar * wm1);
+          }
+          kb.xie = xiebar;
+          kin_backward_x(L, X, cth, q, kb, Lb);
+          q = qn; hm = hn; fphi = fphi_n;
         }
-        const double Tlbar = -q.ikl2 * pb.chiEr;
-        xiebar += Tlbar * slp;
-        kT = ip;
-        tb0 = (1.0 - tp) * Tlbar;
-        tb1 = tp * Tlbar;
-        if (hm.inside) {
-          const double Hbar = fphibar * fphi;
-          xiebar += Hbar * hm.dHdx;
-          double wf0, wf1, wm0, wm1;
-          hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
-          kH = hm.i;
-          c0 = Hbar * wf0; c1 = Hbar * wf1; c2 = Hbar * wm0; c3 = Hbar * wm1;
-        }
-        kb.xie = xiebar;
-        kin_backward(L, omgs, cth, q, kb, Lb);
-      }
-      {
-        const int hT = run_head(kT);
-        tb0 = run_sum(tb0, hT);
-        tb1 = run_sum(tb1, hT);
-        if (lane == hT && kT >= 0) {
-          if (tb0 != 0.0) atomicAdd(&Tbar[kT], tb0);
-          if (tb1 != 0.0) atomicAdd(&Tbar[kT + 1], tb1);
-        }
-        const int hH = run_head(kH);
-        c0 = run_sum(c0, hH); c1 = run_sum(c1, hH); c2 = run_sum(c2, hH); c3 = run_sum(c3, hH);
-        if (lane == hH && kH >= 0) {
-          atomicAdd(&lnfbar[kH - 1], c0);
-          atomicAdd(&lnfbar[kH], c1);
-          atomicAdd(&slopebar[kH - 1], c2);
-          atomicAdd(&slopebar[kH], c3);
+        // the point after this thread's last one (q holds it) takes its share of the last forward difference
+        if (jend < a.W) {
+          double xiebar = carry_x;
+          if (hm.inside) {
+            const double Hbar = carry_f * fphi;
+            xiebar += Hbar * hm.dHdx;
+            double wf0, wf1, wm0, wm1;
+            hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
+            int kk = kH;
+            run_add2(lnfbar - 1, kk, cf0, cf1, hm.i, Hbar * wf0, Hbar * wf1);
+            run_add2(slopebar - 1, kH, cm0, cm1, hm.i, Hbar * wm0, Hbar * wm1);
+          }
+          KinBar kb = {0.0, 0.0, 0.0, 0.0, xiebar, 0.0};
+          kin_backward_x(L, X, cth, q, kb, Lb);
         }
       }
+      // all 32 lanes (idle ones with empty runs) take part in the final flush
+      run_flush2_warp(Tbar, kT, tb0, tb1);
+      run_flush2_warp(lnfbar - 1, kH, cf0, cf1);
+      run_flush2_warp(slopebar - 1, kH, cm0, cm1);
     }
-    if (lane < 1 || lane > kBwdJ) lg_zero(Lb);   // a halo lane only ran the assembly for its neighbour's forward difference
     double vals[kLGDoubles];
     store_lg(vals, Lb);
     block_accumulate<kWarps>(vals, kLGDoubles, sred, a.lgbar + (b * a.G + g) * kLGDoubles);
@@ -536,16 +591,24 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
-    a.ntiles = (c->W + kWarps * kBwdJ - 1) / (kWarps * kBwdJ);
+    // wavelengths per thread: the target, halved until (lineouts x tiles x angles) can give two CTAs per SM
+    int kper = TSFF_TBWD_K;
+    while (kper > 1 && (long long)B * ((c->W + kThreads * kper - 1) / (kThreads * kper)) * c->A < 2LL * c->sm_count) kper /= 2;
+    a.ntiles = (c->W + kThreads * kper - 1) / (kThreads * kper);
+    a.kper = (c->W + kThreads * a.ntiles - 1) / (kThreads * a.ntiles);   // balanced over the tiles
     a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
-    if (a.cells && a.cell_mode == 2) {
-      TSFF_SMEM_OPTIN(k_table_bwd<true>);
-      k_table_bwd<true><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
-    } else {
-      TSFF_SMEM_OPTIN(k_table_bwd<false>);
-      k_table_bwd<false><<<(unsigned)(B * a.ntiles * a.asplit), kThreads, smem, st>>>(a);
-    }
+    const unsigned grid = (unsigned)(B * a.ntiles * a.asplit);
+    const bool frozen = a.cells && a.cell_mode == 2;
+#define TSFF_TBWD_LAUNCH(FZ, NI_)                                    \
+  do {                                                               \
+    TSFF_SMEM_OPTIN((k_table_bwd<FZ, NI_>));                         \
+    k_table_bwd<FZ, NI_><<<grid, kThreads, smem, st>>>(a);           \
+  } while (0)
+    if (frozen) TSFF_TBWD_LAUNCH(true, 0);
+    else if (c->I == 1) TSFF_TBWD_LAUNCH(false, 1);
+    else TSFF_TBWD_LAUNCH(false, 0);
+#undef TSFF_TBWD_LAUNCH
     TSFF_LAUNCH_OK("k_table_bwd");
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }
