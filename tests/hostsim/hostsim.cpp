@@ -171,6 +171,30 @@ int main() {
         printf("FAIL hermite/lerp ih x=%g H %.15e %.15e dH %.12e %.12e lerp %.15e %.15e\n", x, H1, H2, h1.dHdx, h2.dHdx, l1, l2); fails++;
       }
     }
+    {  // branch-free forms against the branchy ones
+      std::vector<ZZ> zz(1640);
+      for (int i = 0; i < 1640; i++) { zz[i].r = T.zr[i]; zz[i].i = T.zi[i]; }
+      for (double x : {-9.0, -8.2, -8.19999, -3.3, -0.004, 0.0, 0.5, 2.22, 8.1899, 8.195, 12.0, 300.0}) {
+        double a[4], b[4];
+        zprime_lerp_x(T.zt, 1.0 / T.zt.h, x, a[0], a[1], a[2], a[3], 0, nullptr);
+        zprime_lerp_bf(zz.data(), T.zt.n, T.zt.x0, T.zt.xlast, 1.0 / T.zt.h, x, b[0], b[1], b[2], b[3]);
+        for (int k = 0; k < 4; k++)
+          if (relerr(a[k], b[k]) > 1e-12 && fabs(a[k] - b[k]) > 1e-15) { printf("FAIL zprime bf x=%g k=%d %.15e %.15e\n", x, k, a[k], b[k]); fails++; }
+      }
+      for (double x : {-7.0, -5.9, -5.5, -1.234, 0.0, 0.777, 4.9, 5.9, 5.95, 7.0}) {
+        Herm h1, h2;
+        const double H1 = hermite_uniform_ih(lnf.data(), sl.data(), V, x0, h, 1.0 / h, x, -50.0, h1);
+        const double H2 = hermite_uniform_bf(lnf.data(), sl.data(), V, x0, h, 1.0 / h, x, -50.0, h2);
+        int i1, i2; double t1, t2, s1, s2;
+        const double l1 = lerp_uniform_ih(lnf.data(), V, x0, 1.0 / h, x, i1, t1, s1), l2 = lerp_uniform_bf(lnf.data(), V, x0, 1.0 / h, x, i2, t2, s2);
+        if (H1 != H2 || h1.dHdx != h2.dHdx || h1.inside != h2.inside || h1.i != h2.i || h1.t != h2.t || l1 != l2 || s1 != s2 || i1 != i2 || t1 != t2) {
+          printf("FAIL hermite/lerp bf x=%g H %.15e %.15e lerp %.15e %.15e i %d %d t %g %g\n", x, H1, H2, l1, l2, i1, i2, t1, t2); fails++;
+        }
+      }
+      for (double y : {-800.0, -700.0, -699.0, -50.0, -1.0, -1e-9, 0.0, 0.3, 5.0}) {
+        if (relerr(fast_exp_bf(y), y > -700.0 ? exp(y) : 0.0) > 1e-14) { printf("FAIL exp bf y=%g\n", y); fails++; }
+      }
+    }
     printf("x-chain vs plain chain: worst rel diff %.2e\n", worst);
   }
   // ---- 3. PV sums

@@ -529,16 +529,32 @@ struct LGX {
   double ivTe, iomgL, iomgpe2, opv, kL2, zih;          // opv = omgpe2 / vTe^2 ; zih = 1 / (Z' table spacing)
   double ickl[TSFF_MAX_IONS], ickl2[TSFF_MAX_IONS];    // 1 / c_kldi, 1 / c_kldi^2
 };
+constexpr int kLGXDoubles = 6 + 2 * TSFF_MAX_IONS;
+// field f of the LGX of L, in declaration order (so that kLGXDoubles threads can fill a shared LGX, one division each)
+TSFF_HD double lgx_field(const LG& L, int nI, double zh, int f) {
+  switch (f) {
+    case 0: return 1.0 / L.vTe;
+    case 1: return 1.0 / L.omgL;
+    case 2: return 1.0 / L.omgpe2;
+    case 3: return L.omgpe2 / (L.vTe * L.vTe);
+    case 4: return L.kL * L.kL;
+    case 5: return 1.0 / zh;
+    default: break;
+  }
+  const int i = (f - 6) % TSFF_MAX_IONS;
+  if (i >= nI) return 0.0;
+  return f - 6 < TSFF_MAX_IONS ? 1.0 / L.c_kldi[i] : 1.0 / (L.c_kldi[i] * L.c_kldi[i]);
+}
 TSFF_HD void lgx_make(const LG& L, int nI, double zh, LGX& X) {
-  X.ivTe = 1.0 / L.vTe;
-  X.iomgL = 1.0 / L.omgL;
-  X.iomgpe2 = 1.0 / L.omgpe2;
-  X.opv = L.omgpe2 * X.ivTe * X.ivTe;
-  X.kL2 = L.kL * L.kL;
-  X.zih = 1.0 / zh;
+  X.ivTe = lgx_field(L, nI, zh, 0);
+  X.iomgL = lgx_field(L, nI, zh, 1);
+  X.iomgpe2 = lgx_field(L, nI, zh, 2);
+  X.opv = lgx_field(L, nI, zh, 3);
+  X.kL2 = lgx_field(L, nI, zh, 4);
+  X.zih = lgx_field(L, nI, zh, 5);
   for (int i = 0; i < TSFF_MAX_IONS; i++) {
-    X.ickl[i] = i < nI ? 1.0 / L.c_kldi[i] : 0.0;
-    X.ickl2[i] = X.ickl[i] * X.ickl[i];
+    X.ickl[i] = lgx_field(L, nI, zh, 6 + i);
+    X.ickl2[i] = lgx_field(L, nI, zh, 6 + TSFF_MAX_IONS + i);
   }
 }
 
@@ -792,6 +808,106 @@ TSFF_HD double lerp_uniform_ih(const T* f, int n, double x0, double ih, double x
   const double a = (double)f[i], b = (double)f[i + 1];
   slope = (b - a) * ih;
   return a + t * (b - a);
+}
+
+// ---- branch-free forms (the table adjoint keeps one point chain per thread in flight, so its speed is the length of that
+// chain; straight-line code lets the compiler overlap the look-ahead point with the reverse sweep of the current one) ----
+// exp(y) for y in [-700, 700] (clamped above), 0 below, NaN -> NaN; even / odd split of the degree-12 polynomial
+TSFF_HD double fast_exp_bf(double y) {
+#if defined(__CUDA_ARCH__)
+  const double yc = fmin(fmax(y, -700.0), 700.0);
+  const double n = rint(yc * 1.4426950408889634);
+  double f = fma(-n, 0.693147180369123816490, yc);
+  f = fma(-n, 1.90821492927058770002e-10, f);
+  const double f2 = f * f;
+  double pe = 1.0 / 479001600.0;             // even powers: 1, 1/2!, 1/4!, ...
+  pe = fma(pe, f2, 1.0 / 3628800.0);
+  pe = fma(pe, f2, 1.0 / 40320.0);
+  pe = fma(pe, f2, 1.0 / 720.0);
+  pe = fma(pe, f2, 1.0 / 24.0);
+  pe = fma(pe, f2, 0.5);
+  pe = fma(pe, f2, 1.0);
+  double po = 1.0 / 39916800.0;              // odd powers: 1, 1/3!, 1/5!, ...
+  po = fma(po, f2, 1.0 / 362880.0);
+  po = fma(po, f2, 1.0 / 5040.0);
+  po = fma(po, f2, 1.0 / 120.0);
+  po = fma(po, f2, 1.0 / 6.0);
+  po = fma(po, f2, 1.0);
+  const double p = fma(po, f, pe);
+  const double r = __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+  return y > -700.0 ? r : (y == y ? 0.0 : y);
+#else
+  return y > -700.0 ? exp(fmin(y, 700.0)) : (y == y ? 0.0 : y);
+#endif
+}
+
+TSFF_HD double hermite_uniform_bf(const double* lnf, const double* slope, int V, double x0, double h, double ih, double x,
+                                  double fill, Herm& o) {
+  const double xlast = x0 + (double)(V - 1) * h;
+  const bool inside = (x >= x0) && (x <= xlast);
+  const double u = fmin(fmax((x - x0) * ih, 0.0), (double)(V - 1));
+  int i = (int)u + 1;
+  i = i > V - 1 ? V - 1 : i;
+  const double t = u - (double)(i - 1);
+  const double f0 = lnf[i - 1], f1 = lnf[i], m0 = slope[i - 1] * h, m1 = slope[i] * h;
+  const double d = f1 - f0;
+  const double c2 = 3.0 * d - 2.0 * m0 - m1;
+  const double c3 = m0 + m1 - 2.0 * d;
+  o.i = inside ? i : 0;
+  o.t = inside ? t : 0.0;
+  o.inside = inside;
+  o.dHdx = inside ? (m0 + t * (2.0 * c2 + 3.0 * c3 * t)) * ih : 0.0;
+  return inside ? f0 + t * (m0 + t * (c2 + c3 * t)) : fill;
+}
+
+template <typename T>
+TSFF_HD double lerp_uniform_bf(const T* f, int n, double x0, double ih, double x, int& i, double& t, double& slope) {
+  const double u = (x - x0) * ih;
+  const bool edge = !(u > 0.0) || (u >= (double)(n - 1));
+  const double uc = fmin(fmax(u, 0.0), (double)(n - 1));
+  int ii = (int)uc;
+  ii = ii > n - 2 ? n - 2 : ii;
+  const double tt = uc - (double)ii;
+  const double a = (double)f[ii], b = (double)f[ii + 1];
+  i = ii;
+  t = tt;
+  slope = edge ? 0.0 : (b - a) * ih;
+  return a + tt * (b - a);
+}
+
+// Z' lookup from an interleaved table zz[i] = (Zr_i, Zi_i) (shared memory), asymptotic form outside; no branches
+struct ZZ { double r, i; };
+TSFF_HD void zprime_lerp_bf(const ZZ* zz, int n, double x0, double xlast, double ih, double x, double& zr, double& zi, double& dzr,
+                            double& dzi) {
+  const bool out = (x < x0) || (x > xlast);
+  const double u = fmin(fmax((x - x0) * ih, 0.0), (double)(n - 2));
+  const int i = (int)u;
+  const double t = (x - x0) * ih - (double)i;
+  const ZZ a = zz[i], b = zz[i + 1];
+  const double ix = fast_rcp(out ? x : 1.0);
+  const double ar = ix * ix;
+  zr = out ? ar : a.r + t * (b.r - a.r);
+  zi = out ? 0.0 : a.i + t * (b.i - a.i);
+  dzr = out ? -2.0 * ar * ix : (b.r - a.r) * ih;
+  dzi = out ? 0.0 : (b.i - a.i) * ih;
+}
+
+template <int NI>
+TSFF_HD void ion_forward_bf(const LG& L, const LGX& X, int nI, const ZZ* zz, const ZTab& zt, const KinX& q, IonX& o) {
+  o.chiIr = o.chiIi = o.sion = 0.0;
+#pragma unroll
+  for (int i = 0; i < TSFF_MAX_IONS; i++) {
+    if (NI > 0 ? i >= NI : i >= nI) break;
+    const double xii = L.inv_s2vTi[i] * q.w;
+    const double ikldi2 = X.ickl2[i] * q.ik2;
+    zprime_lerp_bf(zz, zt.n, zt.x0, zt.xlast, X.zih, xii, o.zr[i], o.zi[i], o.dzr[i], o.dzi[i]);
+    o.xii[i] = xii;
+    o.ikldi2[i] = ikldi2;
+    o.E[i] = fast_exp_bf(-xii * xii);
+    o.chiIr += -0.5 * ikldi2 * o.zr[i];
+    o.chiIi += -0.5 * ikldi2 * o.zi[i];
+    o.sion += L.ioncf[i] * o.E[i];
+  }
 }
 
 // adjoint weights of H wrt (lnf[i-1], lnf[i], slope[i-1], slope[i])

@@ -192,10 +192,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
   double acc = 0.0;
   for (int g = 0; g < a.G; g++) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-      load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
-      lgx_make(sL, a.nI, a.zt.h, sX);
-    }
+    if (threadIdx.x < kLGDoubles) reinterpret_cast<double*>(&sL)[threadIdx.x] = a.lg[(b * a.G + g) * kLGDoubles + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < kLGXDoubles) reinterpret_cast<double*>(&sX)[threadIdx.x] = lgx_field(sL, a.nI, a.zt.h, threadIdx.x);
     __syncthreads();
     const LG& L = sL;
     const LGX& X = sX;
@@ -240,8 +239,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
 #define TSFF_TBWD_MINB 2
 #endif
 #ifndef TSFF_TBWD_K
-#define TSFF_TBWD_K 8          // target wavelengths per thread (lowered at launch until the grid fills the device)
+#define TSFF_TBWD_K 4          // target wavelengths per thread (lowered at launch until the grid fills the device)
 #endif
+#ifndef TSFF_TBWD_THREADS
+#define TSFF_TBWD_THREADS 256
+#endif
+#ifndef TSFF_TBWD_RECOMP_KIN
+#define TSFF_TBWD_RECOMP_KIN 1  // 1: carry only (xie, f(xie), Hermite cell) of the look-ahead point and redo its kinematics
+#endif
+constexpr int kBwdThreads = TSFF_TBWD_THREADS;
 
 __device__ __forceinline__ void run_flush2(double* dst, int k, double v0, double v1) {
   if (k < 0) return;
@@ -278,76 +284,106 @@ __device__ __forceinline__ void run_flush2_warp(double* dst, int k, double v0, d
   }
 }
 
+// dynamic smem: lnf[V] | slope[V] | T[1640] | Z'[1640] as (re, im) pairs | omgs of the CTA's wavelengths (+1) | modl_bar * jmul of them
+__host__ __device__ inline size_t table_bwd_smem(int V, int kper) {
+  return (size_t)(2 * V + kXi2N + 2 * kXi2N + 2 * (kBwdThreads * kper + 1)) * 8;
+}
+
 template <bool FROZEN, int NI>
-__global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const TableArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double sred[kLGDoubles * kWarps];
+  __shared__ double sred[kLGDoubles * (kBwdThreads / 32)];
   __shared__ LG sL;   // the (lineout, gradient point) scalars are CTA-uniform: shared, not registers
   __shared__ LGX sX;
+  __shared__ int s_next;
   double* s_lnf = reinterpret_cast<double*>(smem_raw);
   double* s_slope = s_lnf + a.V;
   double* s_T = s_slope + a.V;
+  ZZ* s_zz = reinterpret_cast<ZZ*>(s_T + kXi2N);
+  double* s_omg = reinterpret_cast<double*>(s_zz + kXi2N);
+  const int span = kBwdThreads * a.kper + 1;   // wavelengths of the CTA plus the look-ahead of its last one
+  double* s_pm = s_omg + span;
   const int chunk = blockIdx.x % a.asplit;
   const int tile = (blockIdx.x / a.asplit) % a.ntiles;
   const long long b = blockIdx.x / ((long long)a.asplit * a.ntiles);
   const int aper = (a.A + a.asplit - 1) / a.asplit, ia0 = chunk * aper, ia1 = min(a.A, ia0 + aper);
-  for (int i = threadIdx.x; i < a.V; i += kThreads) {
+  const int jbase = tile * kBwdThreads * a.kper;
+  const double iG = 1.0 / (double)a.G;
+  for (int i = threadIdx.x; i < a.V; i += kBwdThreads) {
     s_lnf[i] = a.lnf[b * a.V + i];
     s_slope[i] = a.slope[b * a.V + i];
   }
-  for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
-  const int j0 = (tile * kThreads + threadIdx.x) * a.kper;
-  const int jend = min(j0 + a.kper, a.W);
-  const double idv = 1.0 / a.dv, ih2 = 1.0 / a.xi2_h, iG = 1.0 / (double)a.G;
+  for (int i = threadIdx.x; i < kXi2N; i += kBwdThreads) {
+    s_T[i] = a.T[b * kXi2N + i];
+    s_zz[i].r = a.zt.zr[i];
+    s_zz[i].i = a.zt.zi[i];
+  }
+  for (int i = threadIdx.x; i < span; i += kBwdThreads) {
+    const int j = min(jbase + i, a.W - 1);
+    s_omg[i] = a.omgs[j];
+    s_pm[i] = a.modl_bar ? a.modl_bar[b * a.W + j] * a.jmul[j] * iG : 0.0;
+  }
+  const int lane = threadIdx.x & 31;
+  constexpr int kNW = kBwdThreads / 32;
+  const double idv = 1.0 / a.dv, ih2 = 1.0 / a.xi2_h;
   double* Tbar = a.Tbar + b * kXi2N;
   double* lnfbar = a.lnfbar + b * a.V;
   double* slopebar = a.slopebar + b * a.V;
-  const double* mbar = a.modl_bar ? a.modl_bar + b * a.W : nullptr;
+  // work items of the CTA: (warp-sized chunk of wavelength runs, angle), drawn by the warps from a shared counter
+  const int nitems = kNW * (ia1 - ia0);
   for (int g = 0; g < a.G; g++) {
     __syncthreads();   // first pass: the staged tables; later passes: everyone is done with the previous sL
-    if (threadIdx.x == 0) {
-      load_lg(a.lg + (b * a.G + g) * kLGDoubles, sL);
-      lgx_make(sL, a.nI, a.zt.h, sX);
-    }
+    if (threadIdx.x < kLGDoubles) reinterpret_cast<double*>(&sL)[threadIdx.x] = a.lg[(b * a.G + g) * kLGDoubles + threadIdx.x];
+    if (threadIdx.x == 32) s_next = 0;
+    __syncthreads();
+    if (threadIdx.x < kLGXDoubles) reinterpret_cast<double*>(&sX)[threadIdx.x] = lgx_field(sL, a.nI, a.zt.h, threadIdx.x);
     __syncthreads();
     const LG& L = sL;
     const LGX& X = sX;
     LG Lb;
     lg_zero(Lb);
-    for (int ia = ia0; ia < ia1; ia++) {
-      const double cth = a.costh[ia], wt = a.wts[ia] * iG;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&s_next, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nitems) break;
+      const int ia = ia0 + item / kNW;
+      const int j0 = jbase + ((item % kNW) * 32 + lane) * a.kper;
+      const int jend = min(j0 + a.kper, a.W);
+      const double cth = a.costh[ia], wt = a.wts[ia];
       int kT = -1, kH = -1;                                   // open runs: T cell (nodes kT, kT + 1); Hermite cell (nodes kH - 1, kH)
       double tb0 = 0.0, tb1 = 0.0, cf0 = 0.0, cf1 = 0.0, cm0 = 0.0, cm1 = 0.0;
       if (j0 < a.W) {
         KinX q;
-        kin_forward_x(L, X, a.omgs[j0], cth, q);
+        kin_forward_x(L, X, s_omg[j0 - jbase], cth, q);
         Herm hm;
-        double fphi = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));
+        double fphi = fast_exp_bf(hermite_uniform_bf(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));
         double carry_f = 0.0, carry_x = 0.0;                  // d loss / d (fphi_j, xie_j) through df_{j-1}
         for (int j = j0; j < jend; j++) {
-          const double omgs = a.omgs[j];
-          // look one point ahead for the forward difference
-          KinX qn = q;
-          Herm hn = hm;
-          double fphi_n = fphi, df = 0.0, idelta = 0.0;
+          const double omgs = s_omg[j - jbase];
+          // look one point ahead for the forward difference (form_factor.py:258-259); the last wavelength has none: the staged
+          // omgs repeats it, the difference quotient is discarded
           const bool has_df = j + 1 < a.W;
-          if (has_df) {
-            kin_forward_x(L, X, a.omgs[j + 1], cth, qn);
-            fphi_n = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, qn.xie, kFillLog, hn));
-            idelta = fast_rcp(qn.xie - q.xie);
-            df = (fphi_n - fphi) * idelta;
-          }
+          KinX qn;
+          kin_forward_x(L, X, s_omg[j + 1 - jbase], cth, qn);
+          Herm hn;
+          const double fphi_n = fast_exp_bf(hermite_uniform_bf(s_lnf, s_slope, a.V, a.v0, a.dv, idv, qn.xie, kFillLog, hn));
+          const double idelta = has_df ? fast_rcp(qn.xie - q.xie) : 0.0;
+          const double df = has_df ? (fphi_n - fphi) * idelta : 0.0;
           // reverse of the assembly at point j
-          double Pbar = mbar ? mbar[j] * a.jmul[j] * wt : 0.0;
+          double Pbar = s_pm[j - jbase] * wt;
           if (a.ff_bar) Pbar += a.ff_bar[((b * a.G + g) * (long long)a.W + j) * a.A + ia];
-          int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
-          const int cm = FROZEN ? 2 : 0;   // the adjoint never records: it re-uses what the forward used
-          int ip; double tp, slp;
-          const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
-                                   : lerp_uniform_ih(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);
-          const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
+          int ip; double tp, slp, Tl;
           IonX io;
-          ion_forward_x<NI>(L, X, a.nI, a.zt, q, io, cm, cp + 1);
+          if (FROZEN) {
+            int* cp = a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride);
+            Tl = lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, 2, cp);   // the adjoint re-uses the recorded cells
+            ion_forward_x<NI>(L, X, a.nI, a.zt, q, io, 2, cp + 1);
+          } else {
+            Tl = lerp_uniform_bf(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);
+            ion_forward_bf<NI>(L, X, a.nI, s_zz, a.zt, q, io);
+          }
+          const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
           AsmX s;
           assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
           PointBar pb;
@@ -362,19 +398,24 @@ __global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const Ta
           carry_x = -gd * df;
           const double Tlbar = -q.ikl2 * pb.chiEr;
           xiebar += Tlbar * slp;
+          const double Hbar = hm.inside ? fphibar * fphi : 0.0;
+          xiebar += Hbar * hm.dHdx;
+          double wf0, wf1, wm0, wm1;
+          hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
+          kb.xie = xiebar;
+          kin_backward_x(L, X, cth, q, kb, Lb);
           run_add2(Tbar, kT, tb0, tb1, ip, (1.0 - tp) * Tlbar, tp * Tlbar);
           if (hm.inside) {
-            const double Hbar = fphibar * fphi;
-            xiebar += Hbar * hm.dHdx;
-            double wf0, wf1, wm0, wm1;
-            hermite_weights(hm.t, a.dv, wf0, wf1, wm0, wm1);
             int kk = kH;
             run_add2(lnfbar - 1, kk, cf0, cf1, hm.i, Hbar * wf0, Hbar * wf1);
             run_add2(slopebar - 1, kH, cm0, cm1, hm.i, Hbar * wm0, Hbar * wm1);
           }
-          kb.xie = xiebar;
-          kin_backward_x(L, X, cth, q, kb, Lb);
-          q = qn; hm = hn; fphi = fphi_n;
+#if TSFF_TBWD_RECOMP_KIN
+          kin_forward_x(L, X, s_omg[j + 1 - jbase], cth, q);
+#else
+          q = qn;
+#endif
+          hm = hn; fphi = fphi_n;
         }
         // the point after this thread's last one (q holds it) takes its share of the last forward difference
         if (jend < a.W) {
@@ -399,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, TSFF_TBWD_MINB) k_table_bwd(const Ta
     }
     double vals[kLGDoubles];
     store_lg(vals, Lb);
-    block_accumulate<kWarps>(vals, kLGDoubles, sred, a.lgbar + (b * a.G + g) * kLGDoubles);
+    block_accumulate<kBwdThreads / 32>(vals, kLGDoubles, sred, a.lgbar + (b * a.G + g) * kLGDoubles);
   }
 }
 
@@ -590,20 +631,20 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   a.params_bar = params_bar; a.fe_bar = fe_bar;
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   {
-    const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
     // wavelengths per thread: the target, halved until (lineouts x tiles x angles) can give two CTAs per SM
     int kper = TSFF_TBWD_K;
-    while (kper > 1 && (long long)B * ((c->W + kThreads * kper - 1) / (kThreads * kper)) * c->A < 2LL * c->sm_count) kper /= 2;
-    a.ntiles = (c->W + kThreads * kper - 1) / (kThreads * kper);
-    a.kper = (c->W + kThreads * a.ntiles - 1) / (kThreads * a.ntiles);   // balanced over the tiles
+    while (kper > 1 && (long long)B * ((c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper)) * c->A < 2LL * c->sm_count) kper /= 2;
+    a.ntiles = (c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper);
+    a.kper = (c->W + kBwdThreads * a.ntiles - 1) / (kBwdThreads * a.ntiles);   // balanced over the tiles
     a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
+    const size_t smem = table_bwd_smem(c->V, a.kper);
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
     const unsigned grid = (unsigned)(B * a.ntiles * a.asplit);
     const bool frozen = a.cells && a.cell_mode == 2;
 #define TSFF_TBWD_LAUNCH(FZ, NI_)                                    \
   do {                                                               \
     TSFF_SMEM_OPTIN((k_table_bwd<FZ, NI_>));                         \
-    k_table_bwd<FZ, NI_><<<grid, kThreads, smem, st>>>(a);           \
+    k_table_bwd<FZ, NI_><<<grid, kBwdThreads, smem, st>>>(a);          \
   } while (0)
     if (frozen) TSFF_TBWD_LAUNCH(true, 0);
     else if (c->I == 1) TSFF_TBWD_LAUNCH(false, 1);
@@ -645,6 +686,7 @@ int table_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int 
 }
 int table_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
               const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+  if (table_bwd_smem(c->V, TSFF_TBWD_K) > 200 * 1024) { set_error("V=%d too large for the table-mode adjoint", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? table_bwd_t<float>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
                               : table_bwd_t<double>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
 }
