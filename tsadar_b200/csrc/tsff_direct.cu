@@ -20,6 +20,7 @@ using namespace tsff;
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kLGSDoubles = kLGDoubles + kLGXDoubles;   // a saved (lineout, gradient point) row: the LG scalars, then their LGX
 
 // np.gradient(f, dv) at node i (form_factor.py:372): central inside, first-order one-sided at the ends
 // (division by the uniform spacing as a multiplication by its reciprocal: every consumer of df goes through this one
@@ -32,6 +33,8 @@ __device__ __forceinline__ double grad_at(const T* f, int V, double dv, int i) {
   return ((double)f[i + 1] - (double)f[i - 1]) * (0.5 * idv);
 }
 
+struct LGS { LG L; LGX X; };
+
 struct DirectLayout {  // byte offsets inside `saved` and `ws` for a batch of B lineouts
   size_t s_lg, s_I, s_dI, saved_bytes;
   size_t w_D, w_D64, w_pend, w_ff, w_desc, w_accfe, w_accdf, w_pendbar, w_Dbar, w_lgbar, w_zero_begin, w_zero_end,
@@ -42,7 +45,7 @@ DirectLayout direct_layout(const tsff_ctx* c, int64_t B) {
   DirectLayout L;
   const size_t P = (size_t)c->G * c->W * c->A;
   size_t o = 0;
-  L.s_lg = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
+  L.s_lg = o; o += align_up((size_t)B * c->G * kLGSDoubles * 8);
   L.s_I = o; o += align_up((size_t)B * P * 8);
   L.s_dI = o; o += align_up((size_t)B * P * 8);
   L.saved_bytes = o;
@@ -116,7 +119,10 @@ __global__ void __launch_bounds__(128) k_direct_lg(const DirectArgs a, long long
   LG L;
   lg_zero(L);
   lg_forward(a.params + b * a.NP, a.nI, (int)(t % a.G), a.G, a.lam_shift, L);
-  store_lg(a.lg + t * kLGDoubles, L);
+  store_lg(a.lg + t * kLGSDoubles, L);
+  LGX X;
+  lgx_make(L, a.nI, a.zt.h, X);
+  for (int i = 0; i < kLGXDoubles; i++) a.lg[t * kLGSDoubles + kLGDoubles + i] = reinterpret_cast<const double*>(&X)[i];
 }
 
 template <typename T>
@@ -153,15 +159,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_direct_prep(const DirectArgs a)
 // FP64 tail of one pole: exact near nodes, ion susceptibility, lerp of f and f', assembly; stores P, I, dI/dxi.
 // Not inlined: shared by the R poles of a thread (the kernel would otherwise carry R copies of the FP64 log code).
 template <typename T, int PREC>
-__device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, const T* fe, long long b, int g, int idx, int n,
-                                          int wb0, double farI, double farJ, double g0d) {
+__device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, const LGX& sX, const T* fe, long long b, int g, int idx,
+                                          int n, int wb0, double farI, double farJ, double g0d) {
   const int j = idx / a.A, ia = idx % a.A;
   const int M = a.nodes - 1;
   const double omgs = a.omgs[j];
-  Kin q;
-  kin_forward(sL, omgs, a.costh[ia], q);
-  IonOut io;
-  ion_forward(sL, a.nI, a.zt, q, io);
+  KinX q;
+  kin_forward_x(sL, sX, omgs, a.costh[ia], q);
+  IonX io;
+  ion_forward_x<0>(sL, sX, a.nI, a.zt, q, io);
   double I, dI;
   if (PREC == TSFF_PV_FP32) {
     const int V = a.V;
@@ -179,8 +185,8 @@ __device__ __noinline__ void direct_point(const DirectArgs& a, const LG& sL, con
   const double dfe = d0 + t_f * (d1 - d0);  // form_factor.py:377 (clamped: t_f in {0,1} picks the edge value)
   const double chiEr = -q.ikl2 * I;          // form_factor.py:385-386
   const double chiEi = kPi * q.ikl2 * dfe;   // form_factor.py:381
-  Asm s;
-  const double P = assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
+  AsmX s;
+  const double P = assemble_forward_x(sL, sX, q, io, chiEr, chiEi, fphi, omgs, s);
   const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
   if (a.ff) a.ff[pidx] = P;
   if (a.modl1) a.modl1[pidx] = a.jmul[j] * (0.0 + P * a.wts[0]) / 1.0;   // k_reduce_modl's arithmetic for A = G = 1
@@ -194,14 +200,16 @@ template <int R, typename T, int PREC, int MINB = 3>
 __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_constant__ DirectArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ LG sL;
+  __shared__ LGS sLS;   // the (lineout, gradient point) scalars and their reciprocals
+  const LG& sL = sLS.L;
+  const LGX& sX = sLS.X;
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
   const long long b = bg / a.G;
   const int M = a.nodes - 1;
   const TreeBlob tb = tree_blob(a.npad);
-  if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
+  if (threadIdx.x < kLGSDoubles) reinterpret_cast<double*>(&sLS)[threadIdx.x] = a.lg[bg * kLGSDoubles + threadIdx.x];
   // the lineout's f table rides along with the blob (same bulk copy, same barrier) when it is a float table that keeps three
   // CTAs per SM: the exact zone (7 nodes around the pole) and the lerps of f and f' gather from it per lane -- from shared
   // memory instead of 32 scattered global loads per warp (the region held 20 % of the kernel's stall samples)
@@ -221,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_cons
   for (int r = 0; r < R; r++) {
     int idx = (tile * kThreads + threadIdx.x) * R + r;
     if (idx >= WA) idx = WA - 1;
-    Kin q;
-    kin_forward(sL, a.omgs[idx / a.A], a.costh[idx % a.A], q);
+    KinX q;
+    kin_forward_x(sL, sX, a.omgs[idx / a.A], a.costh[idx % a.A], q);
     tp[r] = tree_pole(q.xie, a.v0, a.dv, M, a.npad);
     g0d[r] = a.v0 - q.xie;
   }
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_direct_fwd(const __grid_cons
       farI += nrI[r];
       farJ = accJ[r] / (kTs * a.dv) + accJ2[r] / (kTs2 * a.dv) + nrJ[r] / a.dv;
     }
-    direct_point<T, PREC>(a, sL, fe, b, g, idx, (int)(-tp[r].un), tp[r].wb0, farI, farJ, g0d[r]);
+    direct_point<T, PREC>(a, sL, sX, fe, b, g, idx, (int)(-tp[r].un), tp[r].wb0, farI, farJ, g0d[r]);
   }
 }
 
@@ -276,29 +284,68 @@ __global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, cons
 #ifndef TSFF_BWDP_RB
 #define TSFF_BWDP_RB 4
 #endif
-#ifndef TSFF_BWDP_SMEM_LB
-#define TSFF_BWDP_SMEM_LB 0
-#endif
-template <int R, typename T>
+
+// Exact-zone adjoint of one pole, the kNearHalf nodes either side of its nearest node n:  d I / d p_i = W_i, the second difference
+// of u ln|u| at u_i = (z_i - xi)/h (the h ln h parts cancel in the difference).  The FORWARD needs these weights in FP64 (they
+// multiply p_i in a sum with cancellation against the far field); the adjoint only scales them by Ibar, so FP32 logarithms
+// (u_i formed in FP64, then rounded) give the cotangent to ~1e-6 of its scale against a 1e-4 bar -- 9 MUFU.LG2 instead of
+// 9 FP64 log polynomials (half of this kernel's FP64 instructions before).  End nodes keep the FP64 form (rare).
+__device__ __forceinline__ void pv_bwd_pole_exact_f32(double gw, double xi, double Ibar, double z0, double h, int nodes, int n,
+                                                      int wb0, double* pnear, int ei0, double ev0, int ei1, double ev1) {
+  const int M = nodes - 1;
+  const int lo = max(1, n - kNearHalf), hi = min(M - 1, n + kNearHalf);
+  if (lo <= hi && Ibar != 0.0) {
+    auto phi = [gw](int i) {
+      const float u = (float)(gw + (double)i);
+      return u * (__log2f(fmaxf(fabsf(u), 1e-30f)) * 0.69314718f);
+    };
+    float pm = phi(lo - 1), pc = phi(lo);
+    for (int i = lo; i <= hi; i++) {
+      const float pp = phi(i + 1);
+      double v = Ibar * (double)(pp - 2.f * pc + pm);
+      if (i == ei0) { v += ev0; ev0 = 0.0; }
+      if (i == ei1) { v += ev1; ev1 = 0.0; }
+      atomicAdd(&pnear[i], v);
+      pm = pc;
+      pc = pp;
+    }
+  }
+  if (ev0 != 0.0) atomicAdd(&pnear[ei0], ev0);
+  if (ev1 != 0.0) atomicAdd(&pnear[ei1], ev1);
+  if (Ibar == 0.0) return;
+  const double ih = fast_rcp(h);
+  if (wb0 == 0) {
+    const double g0 = z0 - xi;
+    atomicAdd(&pnear[0], Ibar * ((pv_phi(g0 + h) - pv_phi(g0)) * ih - 1.0 - log_abs(g0)));
+  }
+  if ((unsigned)(M / kTS - wb0) <= 2u) {
+    const double gM = z0 + (double)M * h - xi;
+    atomicAdd(&pnear[M], Ibar * ((pv_phi(gM - h) - pv_phi(gM)) * ih + 1.0 + log_abs(gM)));
+  }
+}
+
+template <int R, typename T, int NI>
 __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(const DirectArgs a) {
-  __shared__ LG sL;
+  __shared__ LGS sLS;
   __shared__ double sred[kLGDoubles * (kThreads / 32)];
-#if TSFF_BWDP_SMEM_LB
-  // the per-thread LG cotangent accumulators (19 doubles) live in shared memory, 21-double stride (conflict-free for 64-bit
-  // accesses), so that the kernel fits three CTAs per SM
-  __shared__ double s_Lb[kThreads][21];
-  LG& Lb = *reinterpret_cast<LG*>(&s_Lb[threadIdx.x][0]);
-#else
-  LG Lb;
-#endif
+  __shared__ ZZ s_zz[kXi2N];   // the Z' table as (re, im) pairs
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
   const long long b = bg / a.G;
-  if (threadIdx.x == 0) load_lg(a.lg + bg * kLGDoubles, sL);
+  if (threadIdx.x < kLGSDoubles) reinterpret_cast<double*>(&sLS)[threadIdx.x] = a.lg[bg * kLGSDoubles + threadIdx.x];
+  for (int i = threadIdx.x; i < kXi2N; i += kThreads) {
+    s_zz[i].r = a.zt.zr[i];
+    s_zz[i].i = a.zt.zi[i];
+  }
   __syncthreads();
+  const LG& L = sLS.L;
+  const LGX& X = sLS.X;
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int WA = a.W * a.A;
+  const double idv = fast_rcp(a.dv), iG = 1.0 / (double)a.G;
+  const double xlast = a.v0 + (a.V - 1) * a.dv;
+  LG Lb;
   lg_zero(Lb);
   for (int r = 0; r < R; r++) {
     const int idx = (tile * kThreads + threadIdx.x) * R + r;
@@ -306,42 +353,44 @@ __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(c
     const int j = idx / a.A, ia = idx % a.A;
     const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
     double Pbar = 0.0;
-    if (a.modl_bar) Pbar += a.modl_bar[b * a.W + j] * a.jmul[j] * a.wts[ia] / (double)a.G;
+    if (a.modl_bar) Pbar += a.modl_bar[b * a.W + j] * a.jmul[j] * a.wts[ia] * iG;
     if (a.ff_bar) Pbar += a.ff_bar[pidx];
     const double omgs = a.omgs[j], cth = a.costh[ia];
-    Kin q;
-    kin_forward(sL, omgs, cth, q);
-    IonOut io;
-    ion_forward(sL, a.nI, a.zt, q, io);
+    KinX q;
+    kin_forward_x(L, X, omgs, cth, q);
+    IonX io;
+    ion_forward_bf<NI>(L, X, a.nI, s_zz, a.zt, q, io);
     const double I = a.sI[pidx], dI = a.sdI[pidx];
     int i_f; double t_f, sl_f;
-    const double fphi = lerp_uniform(fe, a.V, a.v0, a.dv, q.xie, i_f, t_f, sl_f);
+    const double fphi = lerp_uniform_bf(fe, a.V, a.v0, idv, q.xie, i_f, t_f, sl_f);
     const double d0 = grad_at(fe, a.V, a.dv, i_f), d1 = grad_at(fe, a.V, a.dv, i_f + 1);
-    const bool clamped = (q.xie <= a.v0) || (q.xie >= a.v0 + (a.V - 1) * a.dv) || !(q.xie == q.xie);
+    const bool clamped = (q.xie <= a.v0) || (q.xie >= xlast) || !(q.xie == q.xie);
     const double dfe = d0 + t_f * (d1 - d0);
-    const double sl_d = clamped ? 0.0 : (d1 - d0) / a.dv;
+    const double sl_d = clamped ? 0.0 : (d1 - d0) * idv;
     const double chiEr = -q.ikl2 * I, chiEi = kPi * q.ikl2 * dfe;
-    Asm s;
-    assemble_forward(sL, q, io, chiEr, chiEi, fphi, omgs, s);
+    AsmX s;
+    assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
     PointBar pb;
     KinBar kb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    assemble_backward(sL, a.nI, a.zt, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
+    assemble_backward_x<NI>(L, X, a.nI, q, io, chiEr, chiEi, fphi, s, Pbar, pb, kb, Lb);
     // chi_e provider reverse (form_factor.py:376-386)
     kb.ikl2 += -I * pb.chiEr + kPi * dfe * pb.chiEi;
     const double Ibar = -q.ikl2 * pb.chiEr;
     const double dfe_bar = kPi * q.ikl2 * pb.chiEi;
     kb.xie += Ibar * dI + dfe_bar * sl_d + pb.fphi * sl_f;
+    kin_backward_x(L, X, cth, q, kb, Lb);
     if (pb.fphi != 0.0) {
       atomicAdd(&a.accfe[b * a.V + i_f], (1.0 - t_f) * pb.fphi);
       atomicAdd(&a.accfe[b * a.V + i_f + 1], t_f * pb.fphi);
     }
-    // d I / d p_i for the nodes next to the pole (and an end node inside its window), exactly (FP64); the rest is
-    // k_pv_nodes' (far blocks + near-window series)
-    int np, wb0;
-    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] = pv_desc(q.xie, Ibar, a.v0, a.dv, a.nodes, a.npad, np, wb0);
-    pv_bwd_pole_exact(q.xie, Ibar, a.v0, a.dv, a.nodes, np, wb0, a.accdf + b * a.V, i_f, (1.0 - t_f) * dfe_bar, i_f + 1,
-                      t_f * dfe_bar);
-    kin_backward(sL, omgs, cth, q, kb, Lb);
+    // d I / d p_i for the nodes next to the pole (and an end node inside its window); the rest is k_pv_nodes'
+    // (far blocks + near-window series)
+    const TreePole tp = tree_pole(q.xie, a.v0, a.dv, a.nodes - 1, a.npad);
+    const int np = (int)(-tp.un);
+    a.desc[b * ((long long)a.G * WA) + (long long)g * WA + idx] =
+        make_float4(tp.un, tp.ndh, (float)Ibar, __int_as_float((np >> 4) | (tp.wb0 << 10) | (tp.w2 << 18)));   // = pv_desc
+    pv_bwd_pole_exact_f32(tp.gw, q.xie, Ibar, a.v0, a.dv, a.nodes, np, tp.wb0, a.accdf + b * a.V, i_f, (1.0 - t_f) * dfe_bar,
+                          i_f + 1, t_f * dfe_bar);
   }
   double vals[kLGDoubles];
   store_lg(vals, Lb);
@@ -491,7 +540,8 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   TSFF_CUDA_OK(cudaMemsetAsync(w + z0, 0, L.w_zero_end - z0, st));
   constexpr int RB = TSFF_BWDP_RB;
   a.ntiles = (WA + RB * kThreads - 1) / (RB * kThreads);
-  k_direct_bwd_poles<RB, T><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
+  if (c->I == 1) k_direct_bwd_poles<RB, T, 1><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
+  else k_direct_bwd_poles<RB, T, 0><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
   if (fused) {
     n.accdf = a.accdf; n.accfe = a.accfe; n.fe_bar = fe_bar; n.fe_f32 = sizeof(T) == 4; n.ih = 1.0 / c->dv;
