@@ -149,6 +149,14 @@ __device__ __forceinline__ void block_accumulate(const double* vals, int n, doub
   }
   __syncthreads();
 }
+// The same per warp, no CTA barrier: each warp adds its own totals (warps of a CTA then finish independently).
+__device__ __forceinline__ void warp_accumulate(const double* vals, int n, double* dst) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < n; k++) {
+    const double s = warp_sum(vals[k]);
+    if (lane == 0 && s != 0.0) atomicAdd(&dst[k], s);
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace tsff

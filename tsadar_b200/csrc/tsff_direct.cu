@@ -279,11 +279,21 @@ __global__ void __launch_bounds__(kThreads) k_reduce_modl(const double* ff, cons
 
 // ---- backward: poles --------------------------------------------------------------------------------------
 #ifndef TSFF_BWDP_MINB
-#define TSFF_BWDP_MINB 2
+#define TSFF_BWDP_MINB 4
 #endif
 #ifndef TSFF_BWDP_RB
 #define TSFF_BWDP_RB 4
 #endif
+#ifndef TSFF_BWDP_THREADS
+#define TSFF_BWDP_THREADS 128
+#endif
+#ifndef TSFF_BWDP_STAGE_Z
+#define TSFF_BWDP_STAGE_Z 0    // 1: Z' table staged per CTA (measured slower: the CTA is short, the table is L1-resident)
+#endif
+#ifndef TSFF_BWDP_WARPFIN
+#define TSFF_BWDP_WARPFIN 0
+#endif
+constexpr int kBwdpThreads = TSFF_BWDP_THREADS;
 
 // Exact-zone adjoint of one pole, the kNearHalf nodes either side of its nearest node n:  d I / d p_i = W_i, the second difference
 // of u ln|u| at u_i = (z_i - xi)/h (the h ln h parts cancel in the difference).  The FORWARD needs these weights in FP64 (they
@@ -325,19 +335,23 @@ __device__ __forceinline__ void pv_bwd_pole_exact_f32(double gw, double xi, doub
 }
 
 template <int R, typename T, int NI>
-__global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(const DirectArgs a) {
+__global__ void __launch_bounds__(kBwdpThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(const DirectArgs a) {
   __shared__ LGS sLS;
-  __shared__ double sred[kLGDoubles * (kThreads / 32)];
+  __shared__ double sred[kLGDoubles * (kBwdpThreads / 32)];
+#if TSFF_BWDP_STAGE_Z
   __shared__ ZZ s_zz[kXi2N];   // the Z' table as (re, im) pairs
+#endif
   const int tile = blockIdx.x % a.ntiles;
   const long long bg = blockIdx.x / a.ntiles;
   const int g = (int)(bg % a.G);
   const long long b = bg / a.G;
   if (threadIdx.x < kLGSDoubles) reinterpret_cast<double*>(&sLS)[threadIdx.x] = a.lg[bg * kLGSDoubles + threadIdx.x];
-  for (int i = threadIdx.x; i < kXi2N; i += kThreads) {
+#if TSFF_BWDP_STAGE_Z
+  for (int i = threadIdx.x; i < kXi2N; i += kBwdpThreads) {
     s_zz[i].r = a.zt.zr[i];
     s_zz[i].i = a.zt.zi[i];
   }
+#endif
   __syncthreads();
   const LG& L = sLS.L;
   const LGX& X = sLS.X;
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(c
   LG Lb;
   lg_zero(Lb);
   for (int r = 0; r < R; r++) {
-    const int idx = (tile * kThreads + threadIdx.x) * R + r;
+    const int idx = (tile * kBwdpThreads + threadIdx.x) * R + r;
     if (idx >= WA) continue;
     const int j = idx / a.A, ia = idx % a.A;
     const long long pidx = ((b * a.G + g) * (long long)a.W + j) * a.A + ia;
@@ -359,7 +373,11 @@ __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(c
     KinX q;
     kin_forward_x(L, X, omgs, cth, q);
     IonX io;
-    ion_forward_bf<NI>(L, X, a.nI, s_zz, a.zt, q, io);
+#if TSFF_BWDP_STAGE_Z
+    ion_forward_bf<NI>(L, X, a.nI, (const ZZ*)s_zz, a.zt, q, io);
+#else
+    ion_forward_bf<NI>(L, X, a.nI, ZRows{a.zt.zr, a.zt.zi}, a.zt, q, io);
+#endif
     const double I = a.sI[pidx], dI = a.sdI[pidx];
     int i_f; double t_f, sl_f;
     const double fphi = lerp_uniform_bf(fe, a.V, a.v0, idv, q.xie, i_f, t_f, sl_f);
@@ -394,7 +412,11 @@ __global__ void __launch_bounds__(kThreads, TSFF_BWDP_MINB) k_direct_bwd_poles(c
   }
   double vals[kLGDoubles];
   store_lg(vals, Lb);
-  block_accumulate<kThreads / 32>(vals, kLGDoubles, sred, a.lgbar + bg * kLGDoubles);
+#if TSFF_BWDP_WARPFIN
+  warp_accumulate(vals, kLGDoubles, a.lgbar + bg * kLGDoubles);
+#else
+  block_accumulate<kBwdpThreads / 32>(vals, kLGDoubles, sred, a.lgbar + bg * kLGDoubles);
+#endif
 }
 
 // ---- backward: finish ---------------------------------------------------------------------------------------
@@ -539,9 +561,9 @@ int direct_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, c
   const size_t z0 = fused ? L.w_accfe : L.w_zero_begin;
   TSFF_CUDA_OK(cudaMemsetAsync(w + z0, 0, L.w_zero_end - z0, st));
   constexpr int RB = TSFF_BWDP_RB;
-  a.ntiles = (WA + RB * kThreads - 1) / (RB * kThreads);
-  if (c->I == 1) k_direct_bwd_poles<RB, T, 1><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
-  else k_direct_bwd_poles<RB, T, 0><<<(unsigned)(B * c->G * a.ntiles), kThreads, 0, st>>>(a);
+  a.ntiles = (WA + RB * kBwdpThreads - 1) / (RB * kBwdpThreads);
+  if (c->I == 1) k_direct_bwd_poles<RB, T, 1><<<(unsigned)(B * c->G * a.ntiles), kBwdpThreads, 0, st>>>(a);
+  else k_direct_bwd_poles<RB, T, 0><<<(unsigned)(B * c->G * a.ntiles), kBwdpThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_direct_bwd_poles");
   if (fused) {
     n.accdf = a.accdf; n.accfe = a.accfe; n.fe_bar = fe_bar; n.fe_f32 = sizeof(T) == 4; n.ih = 1.0 / c->dv;

@@ -892,8 +892,25 @@ TSFF_HD void zprime_lerp_bf(const ZZ* zz, int n, double x0, double xlast, double
   dzi = out ? 0.0 : (b.i - a.i) * ih;
 }
 
-template <int NI>
-TSFF_HD void ion_forward_bf(const LG& L, const LGX& X, int nI, const ZZ* zz, const ZTab& zt, const KinX& q, IonX& o) {
+// the same from the two separate rows (global memory)
+struct ZRows { const double* zr; const double* zi; };
+TSFF_HD void zprime_lerp_bf(ZRows z, int n, double x0, double xlast, double ih, double x, double& zr, double& zi, double& dzr,
+                            double& dzi) {
+  const bool out = (x < x0) || (x > xlast);
+  const double u = fmin(fmax((x - x0) * ih, 0.0), (double)(n - 2));
+  const int i = (int)u;
+  const double t = (x - x0) * ih - (double)i;
+  const double ar0 = z.zr[i], ar1 = z.zr[i + 1], ai0 = z.zi[i], ai1 = z.zi[i + 1];
+  const double ix = fast_rcp(out ? x : 1.0);
+  const double ar = ix * ix;
+  zr = out ? ar : ar0 + t * (ar1 - ar0);
+  zi = out ? 0.0 : ai0 + t * (ai1 - ai0);
+  dzr = out ? -2.0 * ar * ix : (ar1 - ar0) * ih;
+  dzi = out ? 0.0 : (ai1 - ai0) * ih;
+}
+
+template <int NI, typename ZT>
+TSFF_HD void ion_forward_bf(const LG& L, const LGX& X, int nI, ZT zz, const ZTab& zt, const KinX& q, IonX& o) {
   o.chiIr = o.chiIi = o.sion = 0.0;
 #pragma unroll
   for (int i = 0; i < TSFF_MAX_IONS; i++) {

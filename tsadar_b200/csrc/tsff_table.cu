@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
 #ifndef TSFF_TBWD_RECOMP_KIN
 #define TSFF_TBWD_RECOMP_KIN 1  // 1: carry only (xie, f(xie), Hermite cell) of the look-ahead point and redo its kinematics
 #endif
+#ifndef TSFF_TBWD_STAGE_Z
+#define TSFF_TBWD_STAGE_Z 1
+#endif
 constexpr int kBwdThreads = TSFF_TBWD_THREADS;
 
 __device__ __forceinline__ void run_flush2(double* dst, int k, double v0, double v1) {
@@ -315,8 +318,10 @@ __global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const
   }
   for (int i = threadIdx.x; i < kXi2N; i += kBwdThreads) {
     s_T[i] = a.T[b * kXi2N + i];
+#if TSFF_TBWD_STAGE_Z
     s_zz[i].r = a.zt.zr[i];
     s_zz[i].i = a.zt.zi[i];
+#endif
   }
   for (int i = threadIdx.x; i < span; i += kBwdThreads) {
     const int j = min(jbase + i, a.W - 1);
@@ -381,7 +386,11 @@ __global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const
             ion_forward_x<NI>(L, X, a.nI, a.zt, q, io, 2, cp + 1);
           } else {
             Tl = lerp_uniform_bf(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);
-            ion_forward_bf<NI>(L, X, a.nI, s_zz, a.zt, q, io);
+#if TSFF_TBWD_STAGE_Z
+            ion_forward_bf<NI>(L, X, a.nI, (const ZZ*)s_zz, a.zt, q, io);
+#else
+            ion_forward_bf<NI>(L, X, a.nI, ZRows{a.zt.zr, a.zt.zi}, a.zt, q, io);
+#endif
           }
           const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
           AsmX s;
