@@ -58,6 +58,7 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
 struct TableArgs {
   int W, A, G, nI, V, NP, nodes, npad, ntiles;
   int kper;     // backward: consecutive wavelengths per thread
+  int stage_z;  // backward: Z' table staged in shared memory (pays once a CTA evaluates a few thousand points)
   int asplit;   // angle chunks per wavelength tile (ARTS: one lineout, 241 angles -- the grid would not fill the device otherwise)
   double lam_shift, v0, dv, xi1_0, xi1_h, xi2_0, xi2_h;
   const double *omgs, *costh, *wts, *jmul, *xi2;
@@ -166,8 +167,11 @@ constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
 
 // FROZEN: the second-order path's cell record / replay (tsff_ctx_set_frozen_cells); a template so that the normal path carries
 // none of it
+#ifndef TSFF_TFWD_MINB
+#define TSFF_TFWD_MINB 4
+#endif
 template <bool WRITE_FF, bool FROZEN = false>
-__global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
+__global__ void __launch_bounds__(kThreads, TSFF_TFWD_MINB) k_table_fwd(const TableArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LG sL;   // CTA-uniform scalars of the (lineout, gradient point)
   __shared__ LGX sX;  // ... and their reciprocals
@@ -247,9 +251,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_table_fwd(const TableArgs a) {
 #ifndef TSFF_TBWD_RECOMP_KIN
 #define TSFF_TBWD_RECOMP_KIN 1  // 1: carry only (xie, f(xie), Hermite cell) of the look-ahead point and redo its kinematics
 #endif
-#ifndef TSFF_TBWD_STAGE_Z
-#define TSFF_TBWD_STAGE_Z 1
-#endif
 constexpr int kBwdThreads = TSFF_TBWD_THREADS;
 
 __device__ __forceinline__ void run_flush2(double* dst, int k, double v0, double v1) {
@@ -318,10 +319,10 @@ __global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const
   }
   for (int i = threadIdx.x; i < kXi2N; i += kBwdThreads) {
     s_T[i] = a.T[b * kXi2N + i];
-#if TSFF_TBWD_STAGE_Z
-    s_zz[i].r = a.zt.zr[i];
-    s_zz[i].i = a.zt.zi[i];
-#endif
+    if (a.stage_z) {
+      s_zz[i].r = a.zt.zr[i];
+      s_zz[i].i = a.zt.zi[i];
+    }
   }
   for (int i = threadIdx.x; i < span; i += kBwdThreads) {
     const int j = min(jbase + i, a.W - 1);
@@ -386,11 +387,8 @@ __global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const
             ion_forward_x<NI>(L, X, a.nI, a.zt, q, io, 2, cp + 1);
           } else {
             Tl = lerp_uniform_bf(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);
-#if TSFF_TBWD_STAGE_Z
-            ion_forward_bf<NI>(L, X, a.nI, (const ZZ*)s_zz, a.zt, q, io);
-#else
-            ion_forward_bf<NI>(L, X, a.nI, ZRows{a.zt.zr, a.zt.zi}, a.zt, q, io);
-#endif
+            if (a.stage_z) ion_forward_bf<NI>(L, X, a.nI, (const ZZ*)s_zz, a.zt, q, io);
+            else ion_forward_bf<NI>(L, X, a.nI, ZRows{a.zt.zr, a.zt.zi}, a.zt, q, io);
           }
           const double chiEr = -q.ikl2 * Tl, chiEi = kPi * q.ikl2 * df;
           AsmX s;
@@ -642,11 +640,13 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   {
     // wavelengths per thread: the target, halved until (lineouts x tiles x angles) can give two CTAs per SM
     int kper = TSFF_TBWD_K;
-    while (kper > 1 && (long long)B * ((c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper)) * c->A < 2LL * c->sm_count) kper /= 2;
+    const long long fill = (long long)c->sm_count * c->tune_tbwd_fill / 100;
+    while (kper > 1 && (long long)B * ((c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper)) * c->A < fill) kper /= 2;
     a.ntiles = (c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper);
     a.kper = (c->W + kBwdThreads * a.ntiles - 1) / (kBwdThreads * a.ntiles);   // balanced over the tiles
     a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
     const size_t smem = table_bwd_smem(c->V, a.kper);
+    a.stage_z = (long long)a.kper * ((c->A + a.asplit - 1) / a.asplit) >= 8 ? 1 : 0;   // >= 2048 points per CTA
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
     const unsigned grid = (unsigned)(B * a.ntiles * a.asplit);
     const bool frozen = a.cells && a.cell_mode == 2;
