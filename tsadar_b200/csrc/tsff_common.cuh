@@ -191,6 +191,5 @@ struct tsff_ctx {
   int* cells;         // frozen lerp cells of the table-mode assembly (tsff_ctx_set_frozen_cells), or null
   int cell_mode;      // 0 off, 1 record, 2 replay
   long long cells_B;  // lineouts the cells buffer holds
-  int tune_tbwd_fill; // TSFF_TBWD_FILL tuning switch (percent of the SM count the table adjoint's grid should reach before wavelengths are chained per thread), read once at creation
   int tune_fwd_r4;    // TSFF_FWD_R4 tuning switch, read once at creation (four poles per thread in k_direct_fwd: measured slower)
 };

@@ -60,7 +60,6 @@ extern "C" int tsff_ctx_create(int device, const tsff_static_cfg* cfg, tsff_ctx*
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->tune_fwd_r4 = getenv("TSFF_FWD_R4") != nullptr;
-  c->tune_tbwd_fill = getenv("TSFF_TBWD_FILL") ? atoi(getenv("TSFF_TBWD_FILL")) : 50;
   c->sm_count = prop.multiProcessorCount;
   c->mode = cfg->mode; c->W = cfg->W; c->A = cfg->A; c->G = cfg->G; c->I = cfg->I; c->V = cfg->V;
   c->NP = TSFF_P_ION0 + TSFF_ION_STRIDE * cfg->I;

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, TSFF_TFWD_MINB) k_table_fwd(const Ta
 #define TSFF_TBWD_MINB 2
 #endif
 #ifndef TSFF_TBWD_K
-#define TSFF_TBWD_K 4          // target wavelengths per thread (lowered at launch until the grid fills the device)
+#define TSFF_TBWD_K 4          // preferred wavelengths per thread (the launch picks 1 .. 2x this, see table_bwd_t)
 #endif
 #ifndef TSFF_TBWD_THREADS
 #define TSFF_TBWD_THREADS 256
@@ -638,13 +638,28 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   a.params_bar = params_bar; a.fe_bar = fe_bar;
   TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   {
-    // wavelengths per thread: the target, halved until (lineouts x tiles x angles) can give two CTAs per SM
-    int kper = TSFF_TBWD_K;
-    const long long fill = (long long)c->sm_count * c->tune_tbwd_fill / 100;
-    while (kper > 1 && (long long)B * ((c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper)) * c->A < fill) kper /= 2;
-    a.ntiles = (c->W + kBwdThreads * kper - 1) / (kBwdThreads * kper);
-    a.kper = (c->W + kBwdThreads * a.ntiles - 1) / (kBwdThreads * a.ntiles);   // balanced over the tiles
-    a.asplit = table_angle_split(B * a.ntiles, c->A, c->sm_count);
+    // wavelengths per thread (kper) and angle chunks per tile (asplit): the pair with the smallest modelled time
+    //   waves x (prologue + kper x angles-per-chunk x (1 + look-ahead share)),  waves = CTAs / (2 per SM), whole while few
+    // (a long chain amortises the look-ahead point and the run flushes; a short one fills the device when lineouts are few)
+    {
+      const double slots = 2.0 * c->sm_count;
+      double best = 1e300;
+      for (int kt = 1; kt <= 2 * TSFF_TBWD_K; kt++) {
+        const int nt = (c->W + kBwdThreads * kt - 1) / (kBwdThreads * kt);
+        const int kb = (c->W + kBwdThreads * nt - 1) / (kBwdThreads * nt);   // balanced over the tiles
+        if (kb != kt) continue;
+        for (int as = 1; as <= c->A; as++) {
+          const int aper = (c->A + as - 1) / as;
+          if (as > 1 && (c->A + as - 2) / (as - 1) == aper) continue;        // same chunk length as the previous split
+          const double ctas = (double)B * nt * as;
+          double waves = ctas / slots;
+          if (waves < 8.0) waves = ceil(waves - 1e-9);
+          const double over = kb > TSFF_TBWD_K ? 1.0 + 0.05 * (kb - TSFF_TBWD_K) : 1.0;   // long chains: measured slower (tail effects)
+          const double t = waves * (1.5 + kb * aper * (1.0 + 0.6 / kb) * over);
+          if (t < best) { best = t; a.kper = kb; a.ntiles = nt; a.asplit = as; }
+        }
+      }
+    }
     const size_t smem = table_bwd_smem(c->V, a.kper);
     a.stage_z = (long long)a.kper * ((c->A + a.asplit - 1) / a.asplit) >= 8 ? 1 : 0;   // >= 2048 points per CTA
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[2], st));
@@ -657,6 +672,7 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   } while (0)
     if (frozen) TSFF_TBWD_LAUNCH(true, 0);
     else if (c->I == 1) TSFF_TBWD_LAUNCH(false, 1);
+    else if (c->I == 2) TSFF_TBWD_LAUNCH(false, 2);
     else TSFF_TBWD_LAUNCH(false, 0);
 #undef TSFF_TBWD_LAUNCH
     TSFF_LAUNCH_OK("k_table_bwd");
@@ -695,7 +711,7 @@ int table_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int 
 }
 int table_bwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved,
               const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
-  if (table_bwd_smem(c->V, TSFF_TBWD_K) > 200 * 1024) { set_error("V=%d too large for the table-mode adjoint", c->V); return TSFF_E_INVALID; }
+  if (table_bwd_smem(c->V, 2 * TSFF_TBWD_K) > 200 * 1024) { set_error("V=%d too large for the table-mode adjoint", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? table_bwd_t<float>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
                               : table_bwd_t<double>(c, B, params, fe, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
 }
