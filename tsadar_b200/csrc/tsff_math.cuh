@@ -162,6 +162,17 @@ TSFF_HD void lg_backward(const double* p, int nI, int g, int G, double lam_shift
 // divisions, 2 square roots and 1 exponential per pole; the reference is float64 and parity is asked to 1e-5.
 // Arguments are positive normal numbers (the kernels' NaN policy is "propagate": NaN in -> NaN out still holds).
 // ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// Polynomial coefficients as constant-bank operands: an FP64 immediate costs two UMOV per use (the compiler re-materialises the
+// 64-bit constants of a Horner chain through one uniform-register pair: 12 % of k_table_fwd's issue slots), a c[bank][offset]
+// operand costs nothing.
+static __constant__ double kExpC[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                                        1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0,
+                                        0.5,               1.0,              1.0};
+static __constant__ double kLogC[10] = {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
+                                        1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0,  1.0};
+static __constant__ double kLn2Split[3] = {1.4426950408889634, 0.693147180369123816490, 1.90821492927058770002e-10};
+#endif
 TSFF_HD double fast_rcp(double d) {
 #if defined(__CUDA_ARCH__)
   double r;
@@ -192,22 +203,12 @@ TSFF_HD double fast_sqrt(double x) {
 TSFF_HD double fast_exp_neg(double y) {       // exp(y), y <= 0
 #if defined(__CUDA_ARCH__)
   if (!(y > -700.0)) return y == y ? 0.0 : y;
-  const double n = rint(y * 1.4426950408889634);
-  double f = fma(-n, 0.693147180369123816490, y);   // ln2 split hi/lo
-  f = fma(-n, 1.90821492927058770002e-10, f);
-  double p = 1.0 / 479001600.0;
-  p = fma(p, f, 1.0 / 39916800.0);
-  p = fma(p, f, 1.0 / 3628800.0);
-  p = fma(p, f, 1.0 / 362880.0);
-  p = fma(p, f, 1.0 / 40320.0);
-  p = fma(p, f, 1.0 / 5040.0);
-  p = fma(p, f, 1.0 / 720.0);
-  p = fma(p, f, 1.0 / 120.0);
-  p = fma(p, f, 1.0 / 24.0);
-  p = fma(p, f, 1.0 / 6.0);
-  p = fma(p, f, 0.5);
-  p = fma(p, f, 1.0);
-  p = fma(p, f, 1.0);
+  const double n = rint(y * kLn2Split[0]);
+  double f = fma(-n, kLn2Split[1], y);   // ln2 split hi/lo
+  f = fma(-n, kLn2Split[2], f);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 13; i++) p = fma(p, f, kExpC[i]);
   return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));   // p * 2^n, n >= -1010
 #else
   return exp(y);
@@ -243,6 +244,11 @@ TSFF_HD double fast_log_pos(double x) {
   const double s = (m - 1.0) / (m + 1.0);
 #endif
   const double s2 = s * s;
+#if defined(__CUDA_ARCH__)
+  double p = kLogC[0];
+#pragma unroll
+  for (int i = 1; i < 10; i++) p = fma(p, s2, kLogC[i]);
+#else
   double p = 1.0 / 19.0;
   p = fma(p, s2, 1.0 / 17.0);
   p = fma(p, s2, 1.0 / 15.0);
@@ -253,6 +259,7 @@ TSFF_HD double fast_log_pos(double x) {
   p = fma(p, s2, 1.0 / 5.0);
   p = fma(p, s2, 1.0 / 3.0);
   p = fma(p, s2, 1.0);
+#endif
   return fma((double)e, kLn2, 2.0 * s * p);
 }
 // ln|g| with the clamp the PV code uses (a pole exactly on a node: g ln|g| -> 0)
@@ -816,23 +823,16 @@ TSFF_HD double lerp_uniform_ih(const T* f, int n, double x0, double ih, double x
 TSFF_HD double fast_exp_bf(double y) {
 #if defined(__CUDA_ARCH__)
   const double yc = fmin(fmax(y, -700.0), 700.0);
-  const double n = rint(yc * 1.4426950408889634);
-  double f = fma(-n, 0.693147180369123816490, yc);
-  f = fma(-n, 1.90821492927058770002e-10, f);
+  const double n = rint(yc * kLn2Split[0]);
+  double f = fma(-n, kLn2Split[1], yc);
+  f = fma(-n, kLn2Split[2], f);
   const double f2 = f * f;
-  double pe = 1.0 / 479001600.0;             // even powers: 1, 1/2!, 1/4!, ...
-  pe = fma(pe, f2, 1.0 / 3628800.0);
-  pe = fma(pe, f2, 1.0 / 40320.0);
-  pe = fma(pe, f2, 1.0 / 720.0);
-  pe = fma(pe, f2, 1.0 / 24.0);
-  pe = fma(pe, f2, 0.5);
-  pe = fma(pe, f2, 1.0);
-  double po = 1.0 / 39916800.0;              // odd powers: 1, 1/3!, 1/5!, ...
-  po = fma(po, f2, 1.0 / 362880.0);
-  po = fma(po, f2, 1.0 / 5040.0);
-  po = fma(po, f2, 1.0 / 120.0);
-  po = fma(po, f2, 1.0 / 6.0);
-  po = fma(po, f2, 1.0);
+  double pe = kExpC[0];                      // even powers: 1/12!, 1/10!, ..., 1
+#pragma unroll
+  for (int i = 2; i < 13; i += 2) pe = fma(pe, f2, kExpC[i]);
+  double po = kExpC[1];                      // odd powers: 1/11!, 1/9!, ..., 1
+#pragma unroll
+  for (int i = 3; i < 13; i += 2) po = fma(po, f2, kExpC[i]);
   const double p = fma(po, f, pe);
   const double r = __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
   return y > -700.0 ? r : (y == y ? 0.0 : y);
