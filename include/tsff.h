@@ -130,6 +130,22 @@ int tsff_ff_bwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, 
                 const double* modl_bar, const double* ff_bar, double* params_bar, void* fe_bar, void* ws,
                 void* stream);
 
+/* ---- B3': two spectral windows of one plasma ----------------------------------------------------------------------- */
+/* The reference evaluates the electron-feature and the ion-feature spectra with two FormFactor instances on the same
+ * parameters and the same f (generate_spectra.py:136-165; FitModel.__call__ :332-336); each re-derives the f-dependent tables --
+ * log f, the cubic's node slopes, ratmod on xi1, its gradient and the principal-value table on xi2 (form_factor.py:256-270) --
+ * that depend on neither the wavelength window nor the kinematic parameters.  These two calls build them once: ctx_a's tables
+ * serve both windows, and in the adjoint both windows' table cotangents are accumulated before ONE principal-value adjoint
+ * sweep.  Both contexts TSFF_MODE_TABLE on the same device with the same V / velocity grid, G, I and PV precision (W, A, the
+ * wavelength range, lam_shift, weights and jmul may differ); frozen cells off.
+ *   modl_a [B][W_a], modl_b [B][W_b]; saved_a / saved_b / ws_a / ws_b sized by tsff_ff_saved_bytes / tsff_ff_workspace_bytes of
+ *   the respective context; params_bar [B][NP] and fe_bar [B][V] are the SUMS over the two windows (overwritten). */
+int tsff_ff_pair_fwd(tsff_ctx* ctx_a, tsff_ctx* ctx_b, int64_t B, const double* params, const void* fe, int fe_dtype,
+                     double* modl_a, double* modl_b, void* saved_a, void* saved_b, void* ws_a, void* stream);
+int tsff_ff_pair_bwd(tsff_ctx* ctx_a, tsff_ctx* ctx_b, int64_t B, const double* params, const void* fe, int fe_dtype,
+                     const void* saved_a, const void* saved_b, const double* modl_bar_a, const double* modl_bar_b,
+                     double* params_bar, void* fe_bar, void* ws_a, void* ws_b, void* stream);
+
 /* ---- B2: electron susceptibility pieces of the 2V path ---------------------------------------------------------- */
 /* replaces FormFactor.calc_all_chi_vals(vx, DF, beta, xie_mag, klde_mag) -> (fe_vphi, chiEI, chiERrat)
  * (form_factor.py:390-447; per pole calc_chi_vals :349-388 with rotate :300-324) for a TSFF_MODE_2V context:

@@ -88,3 +88,55 @@ def test_table_vjp(W, V, A):
         for k in [0, 1, 2, 3, 4, 5, 6, 11, 12, 13, 15, 16, 17]:
             assert abs(pb[b, k] - gp[k]) <= 1e-4 * max(abs(gp[k]), 1e-8 * np.abs(gp).max()), (b, k, pb[b, k], gp[k])
         assert np.abs(fb[b] - gf).max() / np.abs(gf).max() < 1e-4, (b, np.abs(fb[b] - gf).max() / np.abs(gf).max())
+
+
+@pytest.mark.parametrize("fdt", [torch.float64, torch.float32])
+def test_pair_of_windows_equals_the_two_separate_calls(fdt):
+    """tsff_ff_pair_fwd / _bwd (electron + ion windows of one plasma: f-dependent tables built once, one PV adjoint sweep) against
+    two tsff_ff_fwd / _bwd calls: same spectra bit for bit, cotangents = the sums (atomics reorder: 1e-10)."""
+    from tsadar_b200.engine import form_factor_modl_pair, form_factor_modl
+    from tsadar_b200.synthetic import vgrid, super_gaussian_projected
+    B, W, nI = 3, 700, 2
+    sa = np.linspace(53.6, 66.1, 5)
+    vx = vgrid(192)
+    rng = np.random.default_rng(5)
+    fe = np.stack([super_gaussian_projected(vx, m) for m in (2.0, 2.6, 3.4)])
+    p = np.zeros((B, 10 + 4 * nI))
+    p[:, 0], p[:, 1], p[:, 2] = [0.5, 0.7, 0.9], [0.2, 0.3, 0.25], 526.5
+    p[:, 3], p[:, 4] = [0.0, 0.4, -0.3], [0.0, 0.2, 0.5]
+    p[:, 7:10] = 1.0
+    p[:, 10:14] = [40.0, 8.0, 0.2, 0.6]
+    p[:, 14:18] = [1.0, 1.0, 0.35, 0.4]
+    engE = _engine(W, vx, sa, np.full(5, 0.2), nI=nI, lam=(380.0, 690.0), lam_shift=0.3, jmul=np.linspace(0.5, 1.5, W))
+    engI = _engine(W + 37, vx, sa, np.linspace(0.1, 0.3, 5), nI=nI, lam=(524.0, 529.0), lam_shift=0.0)
+    cE = torch.tensor(rng.normal(size=(B, W)), device="cuda")
+    cI = torch.tensor(rng.normal(size=(B, W + 37)), device="cuda")
+
+    def run(pair):
+        pt = torch.tensor(p, device="cuda", requires_grad=True)
+        ft = torch.tensor(fe, device="cuda", dtype=fdt, requires_grad=True)
+        if pair:
+            mE, mI = form_factor_modl_pair(engE, engI, pt, ft)
+        else:
+            mE, mI = form_factor_modl(engE, pt, ft), form_factor_modl(engI, pt, ft)
+        ((mE * cE).sum() + (mI * cI).sum()).backward()
+        return mE.detach(), mI.detach(), pt.grad, ft.grad
+
+    mE, mI, pb, fb = run(True)
+    mE0, mI0, pb0, fb0 = run(False)
+    assert torch.equal(mE, mE0) and torch.equal(mI, mI0)
+    # params_bar: FP64 sums in a different order.  fe_bar: the PV adjoint sweep runs its far field in FP32, so one sweep over the
+    # summed table cotangent and the sum of two sweeps agree to FP32 rounding of the sweep, not to FP64
+    tol, tolf = 1e-10, 5e-6
+    assert float((pb - pb0).abs().max()) <= tol * float(pb0.abs().max())
+    assert float((fb.double() - fb0.double()).abs().max()) <= tolf * float(fb0.double().abs().max())
+    # only one window's cotangent given
+    pt = torch.tensor(p, device="cuda", requires_grad=True)
+    ft = torch.tensor(fe, device="cuda", dtype=fdt, requires_grad=True)
+    mE, mI = form_factor_modl_pair(engE, engI, pt, ft)
+    (mI * cI).sum().backward()
+    pt0 = torch.tensor(p, device="cuda", requires_grad=True)
+    ft0 = torch.tensor(fe, device="cuda", dtype=fdt, requires_grad=True)
+    (form_factor_modl(engI, pt0, ft0) * cI).sum().backward()
+    assert float((pt.grad - pt0.grad).abs().max()) <= tol * float(pt0.grad.abs().max())
+    assert float((ft.grad.double() - ft0.grad.double()).abs().max()) <= tolf * float(ft0.grad.double().abs().max())

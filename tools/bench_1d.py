@@ -15,7 +15,16 @@ engI = FormFactorEngine((523.1, 530.0), 5120, 0.0, P9, np.full(10, 0.1), 1, 1, v
 p = np.zeros((B, 14)); p[:, 0], p[:, 1], p[:, 2] = 0.6, 0.25, 526.5; p[:, 7:10] = 1.0; p[:, 10:14] = [40.0, 8.0, 0.2, 1.0]
 pr = torch.tensor(p, device=dev)
 cot = torch.randn(B, 5120, dtype=torch.float64, device=dev)
+from tsadar_b200.engine import _FFPairFunction
+PAIR = "--separate" not in sys.argv
+class _Ctx:   # the autograd Function's forward / backward driven by hand (no graph bookkeeping in the timed loop)
+    def save_for_backward(self, *t): self.saved_tensors = t
 def step():
+    if PAIR:   # the product path (FitModel.__call__): both windows in one tsff_ff_pair_fwd / _bwd
+        c = _Ctx()
+        _FFPairFunction.forward(c, engE, engI, pr, fe)
+        _FFPairFunction.backward(c, cot, cot)
+        return
     for e in (engE, engI):
         modl, _, saved = e.forward(pr, fe)
         e.backward(pr, fe, saved, modl_bar=cot)
@@ -26,4 +35,4 @@ e0.record()
 for _ in range(5): step()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"1d B={B} (EPW+IAW windows, W=5120, A=10) fwd+VJP: {ms:.3f} ms -> {B / ms * 1e3:.0f} lineouts/s")
+print(f"1d B={B} (EPW+IAW windows, W=5120, A=10{', paired' if PAIR else ', separate calls'}) fwd+VJP: {ms:.3f} ms -> {B / ms * 1e3:.0f} lineouts/s")

@@ -94,7 +94,7 @@ def _cpu_arts2d(npoles=64):
 def run_named_configs(rank=0, world=1, dev=None, cpu=True):
     """-> dict for bench.py's JSON line.  Every rank must call it (collectives in the sharded arts-2d leg)."""
     import torch.distributed as dist
-    from tsadar_b200.engine import FormFactorEngine
+    from tsadar_b200.engine import FormFactorEngine, _FFPairFunction
     from tsadar_b200.synthetic import vgrid, super_gaussian_projected
     dev = dev or torch.device("cuda", torch.cuda.current_device())
     cores = os.cpu_count() or 1
@@ -108,12 +108,16 @@ def run_named_configs(rank=0, world=1, dev=None, cpu=True):
         pr = torch.tensor(row(B, nI), device=dev)
         cot = torch.randn(B, 5120, dtype=torch.float64, device=dev)
 
+        class _Ctx:   # the pair Function's forward / backward driven by hand (what FitModel.__call__ runs, minus autograd bookkeeping)
+            def save_for_backward(self, *t):
+                self.saved_tensors = t
+
         def step():
-            for e in (engE, engI):
-                modl, _, saved = e.forward(pr, fe)
-                e.backward(pr, fe, saved, modl_bar=cot)
+            c = _Ctx()
+            _FFPairFunction.forward(c, engE, engI, pr, fe)
+            _FFPairFunction.backward(c, cot, cot)
         ms = timeit(step)
-        out[name] = {"shape": f"table mode, EPW+IAW instances, W=5120, A=10, I={nI}, B={B} lineouts per GPU", "fwd_vjp_ms": ms,
+        out[name] = {"shape": f"table mode, EPW+IAW windows (one tsff_ff_pair_fwd / _bwd), W=5120, A=10, I={nI}, B={B} lineouts per GPU", "fwd_vjp_ms": ms,
                      "lineouts_per_s": B * world / ms * 1e3}
         del engE, engI
     if cpu:

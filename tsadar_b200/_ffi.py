@@ -17,7 +17,7 @@ ION_A, ION_Z, ION_TI, ION_FRACT, ION_STRIDE = range(5)
 
 EXPORTS = [
     "tsff_ctx_create", "tsff_ctx_destroy", "tsff_last_error", "tsff_abi_version", "tsff_ctx_set_profile_events",
-    "tsff_ff_cells_bytes", "tsff_ctx_set_frozen_cells", "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd", "tsff_chi2v_fwd",
+    "tsff_ff_cells_bytes", "tsff_ctx_set_frozen_cells", "tsff_ff_saved_bytes", "tsff_ff_workspace_bytes", "tsff_ff_fwd", "tsff_ff_bwd", "tsff_ff_pair_fwd", "tsff_ff_pair_bwd", "tsff_chi2v_fwd",
     "tsff_pv_workspace_bytes", "tsff_pv_fwd", "tsff_pv_bwd", "tsff_microbench",
     "tsff_irf_workspace_bytes", "tsff_irf_saved_bytes", "tsff_irf_fwd", "tsff_irf_bwd", "tsff_loss_fwd_bwd",
     "tsff_ats_saved_bytes", "tsff_ats_workspace_bytes", "tsff_ats_fwd", "tsff_ats_bwd",
@@ -104,6 +104,10 @@ def lib():
     L.tsff_ff_fwd.restype = C.c_int
     L.tsff_ff_bwd.argtypes = [vp, i64, dp, vp, C.c_int, vp, dp, dp, dp, vp, vp, vp]
     L.tsff_ff_bwd.restype = C.c_int
+    L.tsff_ff_pair_fwd.argtypes = [vp, vp, i64, dp, vp, C.c_int, dp, dp, vp, vp, vp, vp]
+    L.tsff_ff_pair_fwd.restype = C.c_int
+    L.tsff_ff_pair_bwd.argtypes = [vp, vp, i64, dp, vp, C.c_int, vp, vp, dp, dp, dp, vp, vp, vp, vp]
+    L.tsff_ff_pair_bwd.restype = C.c_int
     L.tsff_chi2v_fwd.argtypes = [vp, dp, dp, dp, dp, i64, dp, vp]
     L.tsff_chi2v_fwd.restype = C.c_int
     L.tsff_pv_workspace_bytes.argtypes = [i64, i64, i64]

@@ -13,6 +13,10 @@ int direct_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*,
 size_t table_saved_bytes(const tsff_ctx*, int64_t);
 size_t table_ws_bytes(const tsff_ctx*, int64_t);
 int table_fwd(tsff_ctx*, int64_t, const double*, const void*, int, double*, double*, void*, void*, cudaStream_t);
+bool table_pair_compatible(const tsff_ctx*, const tsff_ctx*);
+int table_pair_fwd(tsff_ctx*, tsff_ctx*, int64_t, const double*, const void*, int, double*, double*, void*, void*, void*, cudaStream_t);
+int table_pair_bwd(tsff_ctx*, tsff_ctx*, int64_t, const double*, const void*, int, const void*, const void*, const double*, const double*,
+                   double*, void*, void*, void*, cudaStream_t);
 int table_bwd(tsff_ctx*, int64_t, const double*, const void*, int, const void*, const double*, const double*, double*, void*,
               void*, cudaStream_t);
 int ff2v_fwd(tsff_ctx*, int64_t, const double*, const double*, double*, void*, cudaStream_t);
@@ -101,6 +105,41 @@ extern "C" int tsff_ff_bwd(tsff_ctx* c, int64_t B, const double* params, const v
   return c->mode == TSFF_MODE_TABLE
              ? table_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st)
              : direct_bwd(c, B, params, fe, fe_dtype, saved, modl_bar, ff_bar, params_bar, fe_bar, ws, st);
+}
+
+// ---- B3': two windows of one plasma ---------------------------------------------------------------------------------
+static int check_pair(const tsff_ctx* a, const tsff_ctx* b) {
+  if (!a || !b) { set_error("null context"); return TSFF_E_INVALID; }
+  if (!table_pair_compatible(a, b)) {
+    set_error("pair calls need two TSFF_MODE_TABLE contexts on one device with the same V / velocity grid, G, I, PV precision, frozen cells off");
+    return TSFF_E_INVALID;
+  }
+  return TSFF_OK;
+}
+extern "C" int tsff_ff_pair_fwd(tsff_ctx* a, tsff_ctx* b, int64_t B, const double* params, const void* fe, int fe_dtype,
+                                double* modl_a, double* modl_b, void* saved_a, void* saved_b, void* ws_a, void* stream) {
+  int rc = check_pair(a, b);
+  if (rc) return rc;
+  if (B == 0) return TSFF_OK;
+  if ((rc = check_common(a, B, params, fe, fe_dtype, saved_a, ws_a))) return rc;
+  if ((rc = check_common(b, B, params, fe, fe_dtype, saved_b, ws_a))) return rc;
+  if (!modl_a || !modl_b) { set_error("null output"); return TSFF_E_INVALID; }
+  TSFF_ON_DEVICE(a);
+  return table_pair_fwd(a, b, B, params, fe, fe_dtype, modl_a, modl_b, saved_a, saved_b, ws_a, static_cast<cudaStream_t>(stream));
+}
+extern "C" int tsff_ff_pair_bwd(tsff_ctx* a, tsff_ctx* b, int64_t B, const double* params, const void* fe, int fe_dtype,
+                                const void* saved_a, const void* saved_b, const double* modl_bar_a, const double* modl_bar_b,
+                                double* params_bar, void* fe_bar, void* ws_a, void* ws_b, void* stream) {
+  int rc = check_pair(a, b);
+  if (rc) return rc;
+  if (B == 0) return TSFF_OK;
+  if ((rc = check_common(a, B, params, fe, fe_dtype, saved_a, ws_a))) return rc;
+  if ((rc = check_common(b, B, params, fe, fe_dtype, saved_b, ws_b))) return rc;
+  if (!modl_bar_a || !modl_bar_b) { set_error("no cotangent given"); return TSFF_E_INVALID; }
+  if (!fe_bar || !params_bar) { set_error("null output"); return TSFF_E_INVALID; }
+  TSFF_ON_DEVICE(a);
+  return table_pair_bwd(a, b, B, params, fe, fe_dtype, saved_a, saved_b, modl_bar_a, modl_bar_b, params_bar, fe_bar, ws_a, ws_b,
+                        static_cast<cudaStream_t>(stream));
 }
 
 // ---- B1: stand-alone PV integral -----------------------------------------------------------------------------

@@ -57,6 +57,7 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
 
 struct TableArgs {
   int W, A, G, nI, V, NP, nodes, npad, ntiles;
+  int jrep;     // forward: groups of 31 wavelengths a warp takes in turn
   int kper;     // backward: consecutive wavelengths per thread
   int stage_z;  // backward: Z' table staged in shared memory (pays once a CTA evaluates a few thousand points)
   int asplit;   // angle chunks per wavelength tile (ARTS: one lineout, 241 angles -- the grid would not fill the device otherwise)
@@ -188,46 +189,52 @@ __global__ void __launch_bounds__(kThreads, TSFF_TFWD_MINB) k_table_fwd(const Ta
   }
   for (int i = threadIdx.x; i < kXi2N; i += kThreads) s_T[i] = a.T[b * kXi2N + i];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = (tile * kWarps + wid) * kFwdJ + lane;
-  const int jc = min(j, a.W - 1);
-  const bool out = (lane < kFwdJ) && (j < a.W);
-  const double omgs = a.omgs[jc];
   const double idv = 1.0 / a.dv, ih2 = 1.0 / a.xi2_h;
-  double acc = 0.0;
-  for (int g = 0; g < a.G; g++) {
-    __syncthreads();
-    if (threadIdx.x < kLGDoubles) reinterpret_cast<double*>(&sL)[threadIdx.x] = a.lg[(b * a.G + g) * kLGDoubles + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x < kLGXDoubles) reinterpret_cast<double*>(&sX)[threadIdx.x] = lgx_field(sL, a.nI, a.zt.h, threadIdx.x);
-    __syncthreads();
-    const LG& L = sL;
-    const LGX& X = sX;
-    for (int ia = ia0; ia < ia1; ia++) {
-      KinX q;
-      kin_forward_x(L, X, omgs, a.costh[ia], q);
-      Herm hm;
-      const double fphi = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));  // :256
-      const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
-      const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
-      const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) * fast_rcp(xi_n - q.xie) : 0.0;   // :258-259
-      if (out) {
-        int ip; double tp, slp;
-        int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
-        const int cm = FROZEN ? a.cell_mode : 0;
-        const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
-                                 : lerp_uniform_ih(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);       // :270
-        const double chiEr = -q.ikl2 * Tl;                                                                // :271
-        const double chiEi = kPi * q.ikl2 * df;                                                           // :261
-        IonX io;
-        ion_forward_x<0>(L, X, a.nI, a.zt, q, io, cm, cp + 1);
-        AsmX s;
-        const double P = assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
-        if (WRITE_FF) a.ff[((b * a.G + g) * (long long)a.W + j) * a.A + ia] = P;
-        acc += a.wts[ia] * P;
+  // a warp takes a.jrep groups of 31 wavelengths in turn: the staged tables (18 KB per CTA) are then paid once per jrep x 248
+  // wavelengths (at one group per warp the staging and its barrier held ~20 % of the kernel's warp-time)
+  for (int rep = 0; rep < a.jrep; rep++) {
+    const int j = ((tile * a.jrep + rep) * kWarps + wid) * kFwdJ + lane;
+    const int jc = min(j, a.W - 1);
+    const bool out = (lane < kFwdJ) && (j < a.W);
+    const double omgs = a.omgs[jc];
+    double acc = 0.0;
+    for (int g = 0; g < a.G; g++) {
+      if (rep == 0 || a.G > 1) {
+        __syncthreads();
+        if (threadIdx.x < kLGDoubles) reinterpret_cast<double*>(&sL)[threadIdx.x] = a.lg[(b * a.G + g) * kLGDoubles + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x < kLGXDoubles) reinterpret_cast<double*>(&sX)[threadIdx.x] = lgx_field(sL, a.nI, a.zt.h, threadIdx.x);
+        __syncthreads();
+      }
+      const LG& L = sL;
+      const LGX& X = sX;
+      for (int ia = ia0; ia < ia1; ia++) {
+        KinX q;
+        kin_forward_x(L, X, omgs, a.costh[ia], q);
+        Herm hm;
+        const double fphi = exp_logf(hermite_uniform_ih(s_lnf, s_slope, a.V, a.v0, a.dv, idv, q.xie, kFillLog, hm));  // :256
+        const double xi_n = __shfl_down_sync(0xffffffffu, q.xie, 1);
+        const double fphi_n = __shfl_down_sync(0xffffffffu, fphi, 1);
+        const double df = (j + 1 < a.W && lane < 31) ? (fphi_n - fphi) * fast_rcp(xi_n - q.xie) : 0.0;   // :258-259
+        if (out) {
+          int ip; double tp, slp;
+          int* cp = FROZEN ? a.cells + ((((b * a.G + g) * (long long)a.W + j) * a.A + ia) * kCellStride) : nullptr;
+          const int cm = FROZEN ? a.cell_mode : 0;
+          const double Tl = FROZEN ? lerp_uniform_cell(s_T, kXi2N, a.xi2_0, a.xi2_h, q.xie, ip, tp, slp, cm, cp)
+                                   : lerp_uniform_ih(s_T, kXi2N, a.xi2_0, ih2, q.xie, ip, tp, slp);       // :270
+          const double chiEr = -q.ikl2 * Tl;                                                                // :271
+          const double chiEi = kPi * q.ikl2 * df;                                                           // :261
+          IonX io;
+          ion_forward_x<0>(L, X, a.nI, a.zt, q, io, cm, cp + 1);
+          AsmX s;
+          const double P = assemble_forward_x(L, X, q, io, chiEr, chiEi, fphi, omgs, s);
+          if (WRITE_FF) a.ff[((b * a.G + g) * (long long)a.W + j) * a.A + ia] = P;
+          acc += a.wts[ia] * P;
+        }
       }
     }
+    if (out && a.modl) a.modl[b * a.W + j] = a.jmul[j] * acc / (double)a.G;
   }
-  if (out && a.modl) a.modl[b * a.W + j] = a.jmul[j] * acc / (double)a.G;
 }
 
 // ---- backward assembly ----------------------------------------------------------------------------------------
@@ -539,6 +546,28 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd_finish(const TableArgs a
   }
 }
 
+// ---- two windows of one plasma (pair path) ----------------------------------------------------------------------
+// LG scalars alone (the second window re-uses the first one's f-dependent tables, so k_table_prep does not run for it)
+__global__ void __launch_bounds__(128) k_table_lg(const TableArgs a, long long BG) {
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (t >= BG) return;
+  LG L;
+  lg_zero(L);
+  lg_forward(a.params + (t / a.G) * a.NP, a.nI, (int)(t % a.G), a.G, a.lam_shift, L);
+  store_lg(a.lg + t * kLGDoubles, L);
+}
+// params_bar += reverse of the second window's LG scalars (the first window's finish kernel wrote params_bar)
+__global__ void __launch_bounds__(64) k_table_params_bar_add(const TableArgs a, long long B) {
+  const long long b = (long long)blockIdx.x * 64 + threadIdx.x;
+  if (b >= B) return;
+  double* pbar = a.params_bar + b * a.NP;
+  for (int g = 0; g < a.G; g++) {
+    LG Lb;
+    load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
+    lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+  }
+}
+
 // angle chunks per wavelength tile: 1 when the (lineout, tile) grid alone gives two CTAs per SM, else enough to get there
 int table_angle_split(long long ctas, int A, int sm_count) {
   if (ctas >= 2LL * sm_count) return 1;
@@ -564,7 +593,7 @@ void bind_saved(const TableLayout& L, char* sv, TableArgs& a) {
 
 template <typename T>
 int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, double* modl_out, double* ff_out, void* saved,
-                void* ws, cudaStream_t st) {
+                void* ws, cudaStream_t st, const void* tables_from = nullptr) {
   const TableLayout L = table_layout(c, B);
   char* w = static_cast<char*>(ws);
   TableArgs a;
@@ -576,6 +605,15 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   a.D64 = c->pv_precision == TSFF_PV_FP64 ? (double*)(w + L.w_D64) : nullptr;
   a.pend = (double*)(w + L.w_pend); a.ratdf = (double*)(w + L.w_ratdf);
   a.modl = modl_out; a.ff = ff_out;
+  if (tables_from) {
+    // pair path, second window: its own LG scalars; log f, slopes, ratmod and the PV table are the first window's
+    const long long BG = (long long)B * c->G;
+    k_table_lg<<<(unsigned)((BG + 127) / 128), 128, 0, st>>>(a, BG);
+    TSFF_LAUNCH_OK("k_table_lg");
+    double* own_lg = a.lg;
+    bind_saved(L, const_cast<char*>(static_cast<const char*>(tables_from)), a);
+    a.lg = own_lg;
+  } else {
   {
     const size_t smem = (size_t)(2 * c->V + 2 * kXi1N) * 8 + tree_prep_scratch_bytes(c->pv_npad);
     TSFF_SMEM_OPTIN(k_table_prep<T>);
@@ -603,9 +641,16 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
     }
     TSFF_LAUNCH_OK("k_pv_poles");
   }
+  }
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
-    a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
+    // groups per warp: 4 while the grid keeps >= 8 CTAs per SM, else 2, else 1
+    a.jrep = 4;
+    while (a.jrep > 1 && (long long)B * ((c->W + kWarps * kFwdJ * a.jrep - 1) / (kWarps * kFwdJ * a.jrep)) < 8LL * c->sm_count) a.jrep /= 2;
+#ifdef TSFF_TFWD_JREP
+    a.jrep = TSFF_TFWD_JREP;
+#endif
+    a.ntiles = (c->W + kWarps * kFwdJ * a.jrep - 1) / (kWarps * kFwdJ * a.jrep);
     // the fused angle sum (modl) needs all angles in one CTA; the plain formfactor output can split them
     a.asplit = modl_out ? 1 : table_angle_split(B * a.ntiles, c->A, c->sm_count);
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
@@ -621,9 +666,13 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   return TSFF_OK;
 }
 
+// pair path: `tables_from` = the first window's saved buffer (this window's f-dependent tables live there); `acc_ws` non-null =
+// accumulate-only: this window's table cotangents are added into that workspace (the first window's, already zeroed) and nothing
+// else runs -- the first window's call (skip_zero) then finishes both; params_bar of this window is added by table_pair_bwd.
 template <typename T>
 int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, const void* saved, const double* modl_bar,
-                const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st) {
+                const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st, const void* tables_from = nullptr,
+                void* acc_ws = nullptr, bool skip_zero = false) {
   const TableLayout L = table_layout(c, B);
   char* w = static_cast<char*>(ws);
   TableArgs a;
@@ -636,7 +685,18 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   a.lnfbar = (double*)(w + L.w_lnfbar); a.slopebar = (double*)(w + L.w_slopebar); a.pnear = (double*)(w + L.w_pnear);
   a.lgbar = (double*)(w + L.w_lgbar);
   a.params_bar = params_bar; a.fe_bar = fe_bar;
-  TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
+  if (tables_from) {
+    double* own_lg = a.lg;
+    bind_saved(L, const_cast<char*>(static_cast<const char*>(tables_from)), a);
+    a.lg = own_lg;
+  }
+  if (acc_ws) {
+    char* wa = static_cast<char*>(acc_ws);
+    a.Tbar = (double*)(wa + L.w_Tbar); a.lnfbar = (double*)(wa + L.w_lnfbar); a.slopebar = (double*)(wa + L.w_slopebar);
+    TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_lgbar, 0, L.w_zero_end - L.w_lgbar, st));
+  } else if (!skip_zero) {
+    TSFF_CUDA_OK(cudaMemsetAsync(w + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
+  }
   {
     // wavelengths per thread (kper) and angle chunks per tile (asplit): the pair with the smallest modelled time
     //   waves x (prologue + kper x angles-per-chunk x (1 + look-ahead share)),  waves = CTAs / (2 per SM), whole while few
@@ -678,6 +738,7 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
     TSFF_LAUNCH_OK("k_table_bwd");
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }
+  if (acc_ws) return TSFF_OK;
   k_table_tbar<<<(unsigned)B, kThreads, 0, st>>>(a);
   TSFF_LAUNCH_OK("k_table_tbar");
   {
@@ -699,7 +760,52 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
 
 }  // namespace
 
+namespace {
+template <typename T>
+int table_pair_bwd_t(tsff_ctx* ca, tsff_ctx* cb, int64_t B, const double* params, const void* fe, const void* saved_a,
+                     const void* saved_b, const double* modl_bar_a, const double* modl_bar_b, double* params_bar, void* fe_bar,
+                     void* ws_a, void* ws_b, cudaStream_t st) {
+  const TableLayout L = table_layout(ca, B);
+  TSFF_CUDA_OK(cudaMemsetAsync(static_cast<char*>(ws_a) + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
+  int rc = table_bwd_t<T>(cb, B, params, fe, saved_b, modl_bar_b, nullptr, params_bar, fe_bar, ws_b, st, saved_a, ws_a, false);
+  if (rc) return rc;
+  rc = table_bwd_t<T>(ca, B, params, fe, saved_a, modl_bar_a, nullptr, params_bar, fe_bar, ws_a, st, nullptr, nullptr, true);
+  if (rc) return rc;
+  TableArgs b;
+  memset(&b, 0, sizeof(b));
+  fill_static(cb, b);
+  b.params = params; b.params_bar = params_bar;
+  b.lgbar = (double*)(static_cast<char*>(ws_b) + table_layout(cb, B).w_lgbar);
+  k_table_params_bar_add<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(b, (long long)B);
+  TSFF_LAUNCH_OK("k_table_params_bar_add");
+  return TSFF_OK;
+}
+}  // namespace
+
 namespace tsff {
+int table_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
+              void* saved, void* ws, cudaStream_t st);
+// the two contexts must describe the same plasma tables: same V / velocity grid, gradient points, ions, PV precision
+bool table_pair_compatible(const tsff_ctx* a, const tsff_ctx* b) {
+  return a->mode == TSFF_MODE_TABLE && b->mode == TSFF_MODE_TABLE && a->device == b->device && a->V == b->V && a->G == b->G &&
+         a->I == b->I && a->NP == b->NP && a->v0 == b->v0 && a->dv == b->dv && a->pv_precision == b->pv_precision &&
+         a->pv_npad == b->pv_npad && !a->cell_mode && !b->cell_mode;
+}
+int table_pair_fwd(tsff_ctx* ca, tsff_ctx* cb, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_a,
+                   double* modl_b, void* saved_a, void* saved_b, void* ws_a, cudaStream_t st) {
+  int rc = table_fwd(ca, B, params, fe, fe_dtype, modl_a, nullptr, saved_a, ws_a, st);
+  if (rc) return rc;
+  return fe_dtype == TSFF_F32 ? table_fwd_t<float>(cb, B, params, fe, modl_b, nullptr, saved_b, ws_a, st, saved_a)
+                              : table_fwd_t<double>(cb, B, params, fe, modl_b, nullptr, saved_b, ws_a, st, saved_a);
+}
+int table_pair_bwd(tsff_ctx* ca, tsff_ctx* cb, int64_t B, const double* params, const void* fe, int fe_dtype, const void* saved_a,
+                   const void* saved_b, const double* modl_bar_a, const double* modl_bar_b, double* params_bar, void* fe_bar,
+                   void* ws_a, void* ws_b, cudaStream_t st) {
+  if (table_bwd_smem(ca->V, 2 * TSFF_TBWD_K) > 200 * 1024) { set_error("V=%d too large for the table-mode adjoint", ca->V); return TSFF_E_INVALID; }
+  return fe_dtype == TSFF_F32
+             ? table_pair_bwd_t<float>(ca, cb, B, params, fe, saved_a, saved_b, modl_bar_a, modl_bar_b, params_bar, fe_bar, ws_a, ws_b, st)
+             : table_pair_bwd_t<double>(ca, cb, B, params, fe, saved_a, saved_b, modl_bar_a, modl_bar_b, params_bar, fe_bar, ws_a, ws_b, st);
+}
 size_t table_saved_bytes(const tsff_ctx* c, int64_t B) { return table_layout(c, B).saved_bytes; }
 size_t table_ws_bytes(const tsff_ctx* c, int64_t B) { return table_layout(c, B).ws_bytes; }
 

@@ -172,6 +172,7 @@ class FormFactorEngine:
         """Second-order path (table mode): mode "record" -- the next forward stores the cells of its linear interpolations;
         "replay" -- forward and backward extend the recorded cells linearly (what jax.hessian differentiates); "off"."""
         m = {"off": 0, "record": 1, "replay": 2}[mode]
+        self._cell_mode = m
         if m == 0:
             _ffi.check(_ffi.lib().tsff_ctx_set_frozen_cells(self._ctx, 0, None, 0))
             return
@@ -201,6 +202,59 @@ class FormFactorEngine:
 
     def launches_bwd(self):
         return 4 if self.mode == "table" else 3  # (+1 memset node, not a kernel of ours)
+
+
+class _FFPairFunction(torch.autograd.Function):
+    """Two spectral windows of one plasma (the reference's electron and ion FormFactor instances on the same parameters and f):
+    tsff_ff_pair_fwd / _bwd build the f-dependent tables once and run one principal-value adjoint sweep for both."""
+
+    @staticmethod
+    def forward(ctx, eng_a, eng_b, params, fe):
+        _require_cuda(params, torch.float64, "params")
+        _require_cuda(fe, fe.dtype, "fe")
+        B = params.shape[0]
+        assert params.shape == (B, eng_a.NP) and fe.shape == (B, eng_a.V) and eng_b.V == eng_a.V and eng_b.NP == eng_a.NP
+        dev = eng_a.device
+        modl_a = torch.empty((B, eng_a.W), dtype=torch.float64, device=dev)
+        modl_b = torch.empty((B, eng_b.W), dtype=torch.float64, device=dev)
+        saved_a = torch.empty(eng_a.saved_bytes(B), dtype=torch.uint8, device=dev)
+        saved_b = torch.empty(eng_b.saved_bytes(B), dtype=torch.uint8, device=dev)
+        ws_a = eng_a._scratch("ws", max(eng_a.workspace_bytes(B), eng_b.workspace_bytes(B)))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(_ffi.lib().tsff_ff_pair_fwd(
+            eng_a._ctx, eng_b._ctx, B, params.data_ptr(), fe.data_ptr(), _ffi.TSFF_F32 if fe.dtype == torch.float32 else _ffi.TSFF_F64,
+            modl_a.data_ptr(), modl_b.data_ptr(), saved_a.data_ptr(), saved_b.data_ptr(), ws_a.data_ptr(), st))
+        ctx.eng_a, ctx.eng_b = eng_a, eng_b
+        ctx.save_for_backward(params, fe, saved_a, saved_b)
+        return modl_a, modl_b
+
+    @staticmethod
+    def backward(ctx, bar_a, bar_b):
+        params, fe, saved_a, saved_b = ctx.saved_tensors
+        eng_a, eng_b = ctx.eng_a, ctx.eng_b
+        B = params.shape[0]
+        bar_a = (torch.zeros((B, eng_a.W), dtype=torch.float64, device=params.device) if bar_a is None else bar_a).contiguous()
+        bar_b = (torch.zeros((B, eng_b.W), dtype=torch.float64, device=params.device) if bar_b is None else bar_b).contiguous()
+        params_bar = torch.empty((B, eng_a.NP), dtype=torch.float64, device=params.device)
+        fe_bar = torch.empty_like(fe)
+        ws_a = eng_a._scratch("ws", max(eng_a.workspace_bytes(B), eng_b.workspace_bytes(B)))
+        ws_b = eng_b._scratch("ws", eng_b.workspace_bytes(B))
+        st = torch.cuda.current_stream(params.device).cuda_stream
+        _ffi.check(_ffi.lib().tsff_ff_pair_bwd(
+            eng_a._ctx, eng_b._ctx, B, params.data_ptr(), fe.data_ptr(), _ffi.TSFF_F32 if fe.dtype == torch.float32 else _ffi.TSFF_F64,
+            saved_a.data_ptr(), saved_b.data_ptr(), bar_a.data_ptr(), bar_b.data_ptr(), params_bar.data_ptr(), fe_bar.data_ptr(),
+            ws_a.data_ptr(), ws_b.data_ptr(), st))
+        return None, None, params_bar, fe_bar
+
+
+def form_factor_modl_pair(eng_a, eng_b, params, fe):
+    """Differentiable (modl_a [B,W_a], modl_b [B,W_b]) of two table-mode engines on the same (params, fe)."""
+    return _FFPairFunction.apply(eng_a, eng_b, params, fe)
+
+
+def pair_compatible(eng_a, eng_b):
+    return (eng_a.mode == "table" and eng_b.mode == "table" and eng_a.V == eng_b.V and eng_a.G == eng_b.G and eng_a.NP == eng_b.NP
+            and eng_a.device == eng_b.device and not getattr(eng_a, "_cell_mode", 0) and not getattr(eng_b, "_cell_mode", 0))
 
 
 class _FFFunction(torch.autograd.Function):

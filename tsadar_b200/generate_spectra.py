@@ -225,6 +225,21 @@ class FitModel:
         return modlE, modlI, ThryE, ThryI, lamAxisE, lamAxisI
 
     def __call__(self, all_params):
+        ex, oth = self.config["other"]["extraoptions"], self.config["other"]
+        if (ex["load_ion_spec"] and ex["load_ele_spec"] and self.dim == 1 and not self.angular_full and self.w_shard is None
+                and self.electron_form_factor.mode == "table" and self.ion_form_factor.mode == "table"):
+            # both windows of one plasma: the f-dependent tables (form_factor.py:256-270) are built once, the principal-value
+            # adjoint runs once (tsff_ff_pair_fwd / _bwd) -- the reference derives them in each FormFactor instance
+            from .engine import form_factor_modl_pair, pair_compatible
+            dev = torch.device("cuda", torch.cuda.current_device())
+            block, fe, vx, _, nI = pack_params(all_params, dev)
+            engE = self.electron_form_factor.engine(vx, nI, weights=self._w, jmul=self._jmulE)
+            engI = self.ion_form_factor.engine(vx, nI, weights=self._w_ion)
+            if pair_compatible(engE, engI):
+                modlE, modlI = form_factor_modl_pair(engE, engI, block, fe)
+                if self._iawoff:
+                    modlE = self._apply_iawoff(modlE, block)
+                return modlE, modlI, np.linspace(*oth["lamrangE"], oth["npts"]), np.linspace(*oth["lamrangI"], oth["npts"])
         lamAxisI, modlI, _ = self.ion_spectrum(all_params)
         lamAxisE, modlE, _ = self.electron_spectrum(all_params)
         return modlE, modlI, lamAxisE, lamAxisI
