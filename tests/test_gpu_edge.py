@@ -1,8 +1,8 @@
 """Edge cases and size-independent properties of the CUDA path through the C ABI (task statement, parity section):
 empty batches, ragged shapes (nothing a multiple of a tile), poles outside the f grid, NaN propagation confined to its
-lineout, batch-position invariance, determinism, and -- at the FULL benchmark size (W = 1024, V = 4096) where the oracle
-is too slow -- linearity of the principal-value map in f, linearity of the VJP in its cotangent and the adjoint identity
-<Ibar, PV f> = <PV^T Ibar, f>."""
+lineout, batch-position invariance, determinism, and -- at the FULL benchmark size (W = 1024, V = 4096), beside the oracle
+parity of tests/test_gpu_headline.py at that same size -- linearity of the principal-value map in f, linearity of the VJP in
+its cotangent and the adjoint identity <Ibar, PV f> = <PV^T Ibar, f>."""
 import numpy as np
 import pytest
 import torch
