@@ -134,7 +134,7 @@ def run_named_configs(rank=0, world=1, dev=None, cpu=True):
     tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tsadar_b200", "data", "arts_angles.npz"))
     sa = dict(sa=SA_ARTS, weights=tab["weightMatrix"], angAxis=tab["angsFRED"])
 
-    def arts(name, npts, nvx, shard):
+    def arts(name, npts, nvx, shard, graph=False):
         cfg = load_cfg(name)
         cfg["other"]["lamrangE"] = [cfg["data"]["fit_rng"]["forward_epw_start"], cfg["data"]["fit_rng"]["forward_epw_end"]]
         cfg["other"]["lamrangI"] = [cfg["data"]["fit_rng"]["forward_iaw_start"], cfg["data"]["fit_rng"]["forward_iaw_end"]]
@@ -161,13 +161,32 @@ def run_named_configs(rank=0, world=1, dev=None, cpu=True):
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        graph_ms = None
+        if graph and world == 1:
+            # the same step captured once in a CUDA graph and replayed (what a fit loop does with fixed shapes: no per-step Python)
+            try:
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        step()
+                cur.wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step()
+                graph_ms = timeit(g.replay, n=5, warm=2)
+            except Exception as e:   # a host synchronisation inside the step: report it, keep the eager number
+                graph_ms = f"capture failed: {type(e).__name__}: {str(e)[:120]}"
+                torch.cuda.synchronize()
+        return float(t), graph_ms
 
-    ms = arts("cfg_arts1v", 2048, None, world > 1)     # a shard group is offered; FitModel.SHARD_MIN_POLES_1V declines it for this size
+    ms, gms = arts("cfg_arts1v", 2048, None, world > 1, graph=True)     # a shard group is offered; FitModel.SHARD_MIN_POLES_1V declines it for this size
     out["arts-1d"] = {"shape": "table mode, one image: formfactor [1,2048,241] -> weights[1024,241] -> ATS stage, fwd + VJP of the fitted leaves",
-                      "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms,
+                      "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms, "fwd_vjp_cuda_graph_ms": gms,
                       "sharding": "none: 493 568 poles < FitModel.SHARD_MIN_POLES_1V, the collectives would cost more than they save (every rank evaluates the image)"}
-    ms = arts("cfg_arts2v", 1024, 128, world > 1)
+    ms, _ = arts("cfg_arts2v", 1024, 128, world > 1)
     out["arts-2d"] = {"shape": "2V mode, one image: calc_in_2D on 246 784 poles x 128^2 bicubic points -> weights -> ATS stage, fwd + VJP",
                       "fwd_vjp_ms": ms, "images_per_s": 1e3 / ms,
                       "sharding": f"wavelength axis over {world} GPUs (all-gather of modlE slabs, all-reduce of the table cotangent)" if world > 1 else "none (1 GPU)",

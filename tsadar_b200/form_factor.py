@@ -67,6 +67,13 @@ class FormFactor:
         omgs = 2e7 * np.pi * C_CM / lam
         self._lams = (2 * np.pi * C_CM / omgs)[None, :, None]
 
+    def _lams_on(self, dev):
+        """the wavelength axis on `dev`, uploaded once (a per-call host-to-device copy would also break CUDA-graph capture)"""
+        c = getattr(self, "_lams_dev", None)
+        if c is None or c.device != dev:
+            c = self._lams_dev = torch.as_tensor(self._lams, device=dev)
+        return c
+
     def _enter(self, t):
         if self.w_shard is None:
             return t
@@ -90,7 +97,7 @@ class FormFactor:
         block, fe, vx, batched, nI = pack_params(params, dev)
         eng = self.engine(vx, nI)
         ff = form_factor_full(eng, self._enter(block), self._enter(fe))
-        return (ff if batched else ff[0]), torch.as_tensor(self._lams, device=dev)
+        return (ff if batched else ff[0]), self._lams_on(dev)
 
     def modl(self, params, weights, jmul=None):
         """Fused FormFactor + FitModel angle integration -> modl [B,W] (generate_spectra.py:164-165,193,197)."""
@@ -144,4 +151,4 @@ class FormFactor:
         block, _, vx, _, nI = pack_params(p1, dev)
         eng = self._engine_2v(vx, nI)
         ff = form_factor_full(eng, self._enter(block[:1].contiguous()), self._enter(fe.contiguous()))
-        return ff[0], torch.as_tensor(self._lams, device=dev)
+        return ff[0], self._lams_on(dev)

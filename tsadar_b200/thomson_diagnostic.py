@@ -57,6 +57,16 @@ class ThomsonScatteringDiagnostic:
             ThryI = ThryI[0] if isinstance(ThryI, torch.Tensor) else ThryI
         return ThryE, ThryI, lamAxisE, lamAxisI
 
+    def _cached_upload(self, key, arr, dev):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        sig = (arr.shape, hash(arr.tobytes()), dev)
+        c = getattr(self, "_uploads", None)
+        if c is None:
+            c = self._uploads = {}
+        if key not in c or c[key][0] != sig:
+            c[key] = (sig, torch.as_tensor(arr.copy(), dtype=torch.float64, device=dev))
+        return c[key][1]
+
     @staticmethod
     def _noise(n, B, dev, nbins=1024):
         t = n if isinstance(n, torch.Tensor) else torch.as_tensor(n, dtype=torch.float64)
@@ -83,12 +93,22 @@ class ThomsonScatteringDiagnostic:
         if self._ats is None:
             self._ats = AtsStage(self.cfg, self.scattering_angles, oth["lamrangE"], oth["npts"], n_lam_data, device=dev.index)
         st = self._ats
-        ea = np.asarray(batch["e_amps"], dtype=np.float64).reshape(-1)
-        ea = np.full(st.nrows, ea[0]) if ea.size == 1 else ea[:st.nrows]
-        e_amps = torch.as_tensor(ea.copy(), dtype=torch.float64, device=dev)
-        noise = np.asarray(batch["noise_e"], dtype=np.float64)
+        # amplitudes / noise: device tensors are used as they are; host arrays are uploaded once per distinct content (a per-call
+        # host-to-device copy costs a launch-sized stall and cannot be captured in a CUDA graph)
+        if isinstance(batch["e_amps"], torch.Tensor) and batch["e_amps"].is_cuda:
+            e_amps = batch["e_amps"].to(torch.float64).reshape(-1)
+            e_amps = e_amps.expand(st.nrows) if e_amps.numel() == 1 else e_amps[:st.nrows]
+            e_amps = e_amps.contiguous()
+        else:
+            ea = np.asarray(batch["e_amps"], dtype=np.float64).reshape(-1)
+            ea = np.full(st.nrows, ea[0]) if ea.size == 1 else ea[:st.nrows]
+            e_amps = self._cached_upload("e_amps", ea, dev)
         noise_t = None
-        if not (noise.size == 1 and float(noise.reshape(-1)[0]) == 0.0):
-            noise_t = torch.as_tensor(np.broadcast_to(noise, (st.nrows, st.nl)).copy(), dtype=torch.float64, device=dev)
+        if isinstance(batch["noise_e"], torch.Tensor) and batch["noise_e"].is_cuda:
+            noise_t = batch["noise_e"].to(torch.float64).expand(st.nrows, st.nl).contiguous()
+        else:
+            noise = np.asarray(batch["noise_e"], dtype=np.float64)
+            if not (noise.size == 1 and float(noise.reshape(-1)[0]) == 0.0):
+                noise_t = self._cached_upload("noise_e", np.broadcast_to(noise, (st.nrows, st.nl)), dev)
         ThryE = st(modlE, block, e_amps, noise_t)
         return ThryE, ThryI, st.lam_units, lamAxisI
