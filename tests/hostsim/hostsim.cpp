@@ -240,6 +240,23 @@ int main() {
     }
     printf("hermite checked\n");
   }
+  // ---- 4b. child -> parent moment translation: Pascal recurrence (run-time child) vs the explicit matrix tree_T
+  {
+    double worst = 0;
+    for (int c = 0; c < 4; c++) {
+      double m0[kTK], m[kTK];
+      for (int k = 0; k < kTK; k++) m0[k] = sin(1.0 + 0.7 * k + c) / (1.0 + 0.3 * k);
+      tree_translate_shift(c, m0, m);
+      for (int k = 0; k < kTK; k++) {
+        double ref = 0.0, mag = 0.0;
+        for (int j = 0; j <= k; j++) { ref += tree_T(c, k, j) * m0[j]; mag += fabs(tree_T(c, k, j) * m0[j]); }
+        const double e = fabs(m[k] - ref) / std::max(1e-300, mag);
+        worst = std::max(worst, e);
+        if (e > 1e-14) { printf("FAIL translate c=%d k=%d %.16e %.16e\n", c, k, m[k], ref); fails++; }
+      }
+    }
+    printf("moment translation (recurrence vs matrix): worst %.2e of the term magnitudes\n", worst);
+  }
   // ---- 5. block-multipole PV evaluation (tsff_tree.cuh) vs the literal ratintn, several grid sizes
   for (int N : {4096, 1024, 512, 130, 37}) {
     const double z0 = -6 + 6.0 / N, h = 12.0 / N;

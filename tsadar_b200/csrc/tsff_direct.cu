@@ -131,12 +131,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_direct_prep(const DirectArgs a)
   const T* fe = static_cast<const T*>(a.fe) + b * a.V;
   const int M = a.nodes - 1;
   {
-    // node values p_i = gradient(f)_i straight from the table (16 consecutive nodes per thread), then the tree blob
+    // node values p_i = gradient(f)_i (16 consecutive nodes per thread), then the tree blob.  The lineout's f row is staged in
+    // shared memory first (coalesced): a thread's 16-node run read straight from global memory touches 32 sectors per request
     extern __shared__ __align__(16) unsigned char prep_smem[];
+    // (one pad element per 16: a warp's lanes read elements 16 apart, which would otherwise all fall into two banks)
+    T* sfe = reinterpret_cast<T*>(prep_smem + tree_prep_scratch_bytes(a.npad));
+    for (int i = threadIdx.x; i < a.V; i += kThreads) sfe[i + (i >> 4)] = fe[i];
     const int V = a.V;
-    const double dv = a.dv;
-    tree_prep_cta_f([fe, V, dv](int i) { return grad_at(fe, V, dv, i); }, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat,
-                    reinterpret_cast<double*>(prep_smem));
+    const double idv = fast_rcp(a.dv);
+    auto at = [sfe](int i) { return (double)sfe[i + (i >> 4)]; };
+    // np.gradient at node i, the arithmetic of grad_at (tree_prep_cta_f synchronises the CTA before its first pget)
+    auto pget = [at, V, idv](int i) {
+      if (i <= 0) return (at(1) - at(0)) * idv;
+      if (i >= V - 1) return (at(V - 1) - at(V - 2)) * idv;
+      return (at(i + 1) - at(i - 1)) * (0.5 * idv);
+    };
+    tree_prep_cta_f(pget, M, a.npad, a.D + b * tree_blob(a.npad).bytes, a.tstat, reinterpret_cast<double*>(prep_smem));
   }
   if (a.D64) {  // log-form weights for the FP64 validation path
     for (int i = threadIdx.x; i < a.npad; i += kThreads) {
@@ -493,7 +503,7 @@ int direct_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, d
     const long long BG = (long long)B * c->G;
     k_direct_lg<<<(unsigned)((BG + 127) / 128), 128, 0, st>>>(a, BG);
     TSFF_LAUNCH_OK("k_direct_lg");
-    const size_t psm = tree_prep_scratch_bytes(c->pv_npad);
+    const size_t psm = tree_prep_scratch_bytes(c->pv_npad) + (size_t)(c->V + c->V / 16 + 1) * sizeof(T);
     TSFF_SMEM_OPTIN(k_direct_prep<T>);
     k_direct_prep<T><<<(unsigned)B, kThreads, psm, st>>>(a);
   }
@@ -593,7 +603,7 @@ size_t direct_ws_bytes(const tsff_ctx* c, int64_t B) { return direct_layout(c, B
 
 int direct_fwd(tsff_ctx* c, int64_t B, const double* params, const void* fe, int fe_dtype, double* modl_out, double* ff_out,
                void* saved, void* ws, cudaStream_t st) {
-  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024 || tree_prep_scratch_bytes(c->pv_npad) > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
+  if ((size_t)tree_blob(c->pv_npad).bytes > 200 * 1024 || tree_prep_scratch_bytes(c->pv_npad) + (size_t)(c->V + c->V / 16 + 1) * 8 > 200 * 1024) { set_error("V=%d too large for shared-memory staging", c->V); return TSFF_E_INVALID; }
   return fe_dtype == TSFF_F32 ? direct_fwd_t<float>(c, B, params, fe, modl_out, ff_out, saved, ws, st)
                               : direct_fwd_t<double>(c, B, params, fe, modl_out, ff_out, saved, ws, st);
 }

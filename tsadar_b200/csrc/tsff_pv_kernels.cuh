@@ -63,12 +63,7 @@ __device__ __forceinline__ void tree_translate_fixed(const double (&m0)[kTK], do
   }
 }
 __device__ __forceinline__ void tree_translate_child(int c, const double (&m0)[kTK], double (&m)[kTK]) {
-  switch (c) {
-    case 0: tree_translate_fixed<0>(m0, m); break;
-    case 1: tree_translate_fixed<1>(m0, m); break;
-    case 2: tree_translate_fixed<2>(m0, m); break;
-    default: tree_translate_fixed<3>(m0, m); break;
-  }
+  tree_translate_shift(c, m0, m);   // run-time child index without divergence (tsff_tree.cuh)
 }
 
 // Per-lineout preparation, executed by one CTA.  pget(i), 0 <= i <= M: node values p_i (FP64).

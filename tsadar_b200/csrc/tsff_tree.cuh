@@ -119,6 +119,33 @@ TSFF_HD constexpr double tree_T(int c, int k, int j) {
   for (int q = 0; q < k; q++) v *= 0.25;
   return v;
 }
+// The same translation child c -> parent for a RUN-TIME c, as a Taylor shift: m'_k = 4^-k sum_j C(k,j) d^(k-j) m_j with d = 3 - 2c,
+// by the in-place Pascal recurrence (45 multiply-adds for K = 10, no branches).  The prep kernel's lanes hold the four children
+// of a parent side by side: a switch over four compile-time matrices made every warp execute all four 105-term products.
+TSFF_HD void tree_translate_shift(int c, const double* m0, double* m) {
+  const double d = 3.0 - 2.0 * (double)c;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < kTK; k++) m[k] = m0[k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < kTK; i++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = kTK - 1; k >= i; k--) m[k] = fma(d, m[k - 1], m[k]);
+  }
+  double sc = 1.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 1; k < kTK; k++) {
+    sc *= 0.25;
+    m[k] *= sc;
+  }
+}
 // q_m(e): d A_m / d p_i for an interior node at offset e = i - c  (also the spreading weight of the adjoint)
 TSFF_HD double tree_q(int m, double e, double s) {
   const double eh = -e / s;
