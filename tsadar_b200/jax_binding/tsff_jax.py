@@ -28,7 +28,8 @@ _VMAP = "broadcast_all"
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _XLA_LIB = ctypes.CDLL(os.environ.get("TSFF_XLA_LIB", os.path.join(_HERE, "..", "_lib", "libtsff_xla.so")))
-for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffPvFwd", "TsffChi2vFwd", "TsffLossFwdBwd"):
+for _name in ("TsffFfFwd", "TsffFfFullFwd", "TsffFfBwd", "TsffFfFullBwd", "TsffFfPairFwd", "TsffFfPairBwd", "TsffPvFwd", "TsffChi2vFwd",
+              "TsffLossFwdBwd"):
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_XLA_LIB, _name)), platform="CUDA")
 
 
@@ -57,6 +58,38 @@ def make_form_factor(ctx: int, B: int, W: int, V: int, NP: int, saved_bytes: int
             "TsffFfBwd",
             (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct((B, V), fe.dtype),
              jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)), vmap_method=_VMAP)(params, fe, saved, modl_bar, ctx=cid)
+        return pbar, fbar
+
+    ff.defvjp(_fwd, _bwd)
+    return ff
+
+
+def make_form_factor_pair(ctx_a: int, ctx_b: int, B: int, W_a: int, W_b: int, V: int, NP: int, saved_a: int, saved_b: int,
+                          ws_a: int, ws_b: int):
+    """-> f(params [B, NP], fe [B, V]) = (modl_a [B, W_a], modl_b [B, W_b]): the electron and ion windows of FitModel.__call__
+    (generate_spectra.py:332-336) in one custom call each way; the f-dependent tables are built once (tsff_ff_pair_fwd / _bwd).
+    ws_a must be max(workspace bytes of a, of b)."""
+    ca, cb = np.int64(ctx_a), np.int64(ctx_b)
+
+    @jax.custom_vjp
+    def ff(params, fe):
+        return _fwd(params, fe)[0]
+
+    def _fwd(params, fe):
+        ma, mb, sa, sb, _ = jax.ffi.ffi_call(
+            "TsffFfPairFwd",
+            (jax.ShapeDtypeStruct((B, W_a), jnp.float64), jax.ShapeDtypeStruct((B, W_b), jnp.float64),
+             jax.ShapeDtypeStruct((saved_a,), jnp.uint8), jax.ShapeDtypeStruct((saved_b,), jnp.uint8),
+             jax.ShapeDtypeStruct((ws_a,), jnp.uint8)), vmap_method=_VMAP)(params, fe, ctx=ca, ctx_b=cb)
+        return (ma, mb), (params, fe, sa, sb)
+
+    def _bwd(res, bars):
+        params, fe, sa, sb = res
+        pbar, fbar, _, _ = jax.ffi.ffi_call(
+            "TsffFfPairBwd",
+            (jax.ShapeDtypeStruct((B, NP), jnp.float64), jax.ShapeDtypeStruct((B, V), fe.dtype),
+             jax.ShapeDtypeStruct((ws_a,), jnp.uint8), jax.ShapeDtypeStruct((ws_b,), jnp.uint8)),
+            vmap_method=_VMAP)(params, fe, sa, sb, bars[0], bars[1], ctx=ca, ctx_b=cb)
         return pbar, fbar
 
     ff.defvjp(_fwd, _bwd)

@@ -67,6 +67,28 @@ ffi::Error FfFullBwd(cudaStream_t stream, int64_t ctx, ffi::Buffer<ffi::F64> par
                             fe_bar->untyped_data(), ws->typed_data(), stream));
 }
 
+// Two windows of one plasma (the electron and ion FormFactor instances of FitModel, generate_spectra.py:136-165): ctx = window a
+// (its f-dependent tables serve both), ctx_b = window b.  One call forward, one call for the VJP of both outputs.
+ffi::Error FfPairFwd(cudaStream_t stream, int64_t ctx, int64_t ctx_b, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe,
+                     ffi::ResultBuffer<ffi::F64> modl_a, ffi::ResultBuffer<ffi::F64> modl_b, ffi::ResultBuffer<ffi::U8> saved_a,
+                     ffi::ResultBuffer<ffi::U8> saved_b, ffi::ResultBuffer<ffi::U8> ws) {
+  const int64_t B = lineouts(params);
+  return status(tsff_ff_pair_fwd(reinterpret_cast<tsff_ctx*>(ctx), reinterpret_cast<tsff_ctx*>(ctx_b), B, params.typed_data(),
+                                 fe.untyped_data(), fe_dtype(fe), modl_a->typed_data(), modl_b->typed_data(), saved_a->typed_data(),
+                                 saved_b->typed_data(), ws->typed_data(), stream));
+}
+
+ffi::Error FfPairBwd(cudaStream_t stream, int64_t ctx, int64_t ctx_b, ffi::Buffer<ffi::F64> params, ffi::AnyBuffer fe,
+                     ffi::Buffer<ffi::U8> saved_a, ffi::Buffer<ffi::U8> saved_b, ffi::Buffer<ffi::F64> bar_a,
+                     ffi::Buffer<ffi::F64> bar_b, ffi::ResultBuffer<ffi::F64> params_bar, ffi::Result<ffi::AnyBuffer> fe_bar,
+                     ffi::ResultBuffer<ffi::U8> ws_a, ffi::ResultBuffer<ffi::U8> ws_b) {
+  const int64_t B = lineouts(params);
+  return status(tsff_ff_pair_bwd(reinterpret_cast<tsff_ctx*>(ctx), reinterpret_cast<tsff_ctx*>(ctx_b), B, params.typed_data(),
+                                 fe.untyped_data(), fe_dtype(fe), saved_a.typed_data(), saved_b.typed_data(), bar_a.typed_data(),
+                                 bar_b.typed_data(), params_bar->typed_data(), fe_bar->untyped_data(), ws_a->typed_data(),
+                                 ws_b->typed_data(), stream));
+}
+
 // vmap(ratintn) on uniform nodes (ratintn.py:4-23): f [B, N], pole [B, P] -> out [B, P], dout_dpole [B, P]
 ffi::Error PvFwd(cudaStream_t stream, double z0, double h, ffi::Buffer<ffi::F64> f, ffi::Buffer<ffi::F64> pole,
                  ffi::ResultBuffer<ffi::F64> out, ffi::ResultBuffer<ffi::F64> dout, ffi::ResultBuffer<ffi::U8> ws) {
@@ -112,6 +134,16 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffFfBwd, FfBwd,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffFfFullBwd, FfFullBwd,
                               TSFF_FF_BINDING().Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::U8>>());
+#define TSFF_PAIR_BINDING()                                                                                              \
+  ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("ctx").Attr<int64_t>("ctx_b")                       \
+      .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::AnyBuffer>()
+XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffFfPairFwd, FfPairFwd,
+                              TSFF_PAIR_BINDING().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffFfPairBwd, FfPairBwd,
+                              TSFF_PAIR_BINDING().Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::Buffer<ffi::U8>>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TsffPvFwd, PvFwd,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<double>("z0").Attr<double>("h")
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
