@@ -138,8 +138,8 @@ int tsff_ff_bwd(tsff_ctx* ctx, int64_t B, const double* params, const void* fe, 
  * serve both windows, and in the adjoint both windows' table cotangents are accumulated before ONE principal-value adjoint
  * sweep.  Both contexts TSFF_MODE_TABLE on the same device with the same V / velocity grid, G, I and PV precision (W, A, the
  * wavelength range, lam_shift, weights and jmul may differ); frozen cells off.
- *   modl_a [B][W_a], modl_b [B][W_b]; saved_a / saved_b / ws_a / ws_b sized by tsff_ff_saved_bytes / tsff_ff_workspace_bytes of
- *   the respective context; params_bar [B][NP] and fe_bar [B][V] are the SUMS over the two windows (overwritten). */
+ *   modl_a [B][W_a], modl_b [B][W_b]; saved_a / saved_b / ws_b sized by tsff_ff_saved_bytes / tsff_ff_workspace_bytes of the
+ *   respective context, ws_a by the LARGER of the two contexts' tsff_ff_workspace_bytes (both windows' forward passes use it); params_bar [B][NP] and fe_bar [B][V] are the SUMS over the two windows (overwritten). */
 int tsff_ff_pair_fwd(tsff_ctx* ctx_a, tsff_ctx* ctx_b, int64_t B, const double* params, const void* fe, int fe_dtype,
                      double* modl_a, double* modl_b, void* saved_a, void* saved_b, void* ws_a, void* stream);
 int tsff_ff_pair_bwd(tsff_ctx* ctx_a, tsff_ctx* ctx_b, int64_t B, const double* params, const void* fe, int fe_dtype,

@@ -317,7 +317,10 @@ inline size_t pv_nodes_smem(int npad) {
 inline int pv_nodes_split(int64_t B, int P, int sm_count) {
   if (B >= 2LL * sm_count) return 1;
   long long want = (2LL * sm_count + B - 1) / B;
-  long long most = (P + kNodeChunk - 1) / kNodeChunk;
+  // a few lineouts (a fit batch of 2-8): latency is what counts, and the pole loops shrink with the split while the O(nodes)
+  // spreading each split repeats is short -- allow splits down to 256 poles; otherwise one split per chunk of poles
+  const int grain = B * 8 <= sm_count ? 256 : kNodeChunk;
+  long long most = (P + grain - 1) / grain;
   if (want > most) want = most;
   return want < 1 ? 1 : (int)want;
 }

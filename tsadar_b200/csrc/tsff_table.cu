@@ -24,9 +24,17 @@ constexpr int kWarps = kThreads / 32;
 
 struct TableLayout {
   size_t s_lg, s_lnf, s_slope, s_ratmod, s_T, saved_bytes;
-  size_t w_D, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
+  size_t w_mpart, w_D, w_D64, w_pend, w_ratdf, w_desc, w_Dbar, w_zero_begin, w_Tbar, w_lnfbar, w_slopebar, w_pnear, w_lgbar, w_zero_end,
       ws_bytes;
 };
+
+// forward with the fused angle sum: few lineouts leave most SMs idle at one CTA per (lineout, wavelength tile); the angles are then
+// split over CTAs too, each writing its partial sum, and a second small kernel adds the partials in chunk order (deterministic)
+constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
+inline bool table_fwd_split_angles(const tsff_ctx* c, int64_t B) {
+  const long long tiles = (c->W + (256 / 32) * kFwdJ - 1) / ((256 / 32) * kFwdJ);
+  return c->A > 1 && B * tiles < 2LL * c->sm_count;
+}
 
 TableLayout table_layout(const tsff_ctx* c, int64_t B) {
   TableLayout L;
@@ -51,6 +59,8 @@ TableLayout table_layout(const tsff_ctx* c, int64_t B) {
   L.w_pnear = o; o += align_up((size_t)B * kXi1N * 8);
   L.w_lgbar = o; o += align_up((size_t)B * c->G * kLGDoubles * 8);
   L.w_zero_end = o;
+  // last: the only region whose size depends on (A, W) -- the pair path addresses one context's workspace with the other's layout
+  L.w_mpart = o; o += align_up(table_fwd_split_angles(c, B) ? (size_t)c->A * B * c->W * 8 : 0);
   L.ws_bytes = o;
   return L;
 }
@@ -73,12 +83,16 @@ struct TableArgs {
   double* pend;
   double* ratdf;
   double* modl;
+  double* mpart;   // forward, angles split over CTAs: partial angle sums [asplit][B][W] (then k_table_modl_reduce), else null
+  long long Bn;    // lineouts of the call
   double* ff;
   // backward
   const double* modl_bar;
   const double* ff_bar;
   float4* desc;
   double *Tbar, *lnfbar, *slopebar, *pnear, *Dbar, *lgbar;
+  const double* lgbar2;   // pair path: the second window's LG cotangents (its params_bar is added by this window's finish), else null
+  double lam_shift2;
   double* params_bar;
   void* fe_bar;
   int* cells;      // frozen lerp cells [B][G][W][A][kCellStride] (second-order path) or null
@@ -164,8 +178,6 @@ __global__ void __launch_bounds__(kThreads) k_table_prep(const TableArgs a) {
 
 // ---- forward assembly -----------------------------------------------------------------------------------------
 // dynamic smem: lnf[V] | slope[V] | T[1640]
-constexpr int kFwdJ = 31;  // outputs per warp (lane 31 is the right halo)
-
 // FROZEN: the second-order path's cell record / replay (tsff_ctx_set_frozen_cells); a template so that the normal path carries
 // none of it
 #ifndef TSFF_TFWD_MINB
@@ -233,8 +245,17 @@ __global__ void __launch_bounds__(kThreads, TSFF_TFWD_MINB) k_table_fwd(const Ta
         }
       }
     }
-    if (out && a.modl) a.modl[b * a.W + j] = a.jmul[j] * acc / (double)a.G;
+    if (out && a.mpart) a.mpart[((long long)chunk * a.Bn + b) * a.W + j] = acc;
+    else if (out && a.modl) a.modl[b * a.W + j] = a.jmul[j] * acc / (double)a.G;
   }
+}
+
+__global__ void __launch_bounds__(kThreads) k_table_modl_reduce(const TableArgs a, long long total) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  double s = 0.0;
+  for (int ch = 0; ch < a.asplit; ch++) s += a.mpart[(long long)ch * total + t];
+  a.modl[t] = a.jmul[t % a.W] * s / (double)a.G;
 }
 
 // ---- backward assembly ----------------------------------------------------------------------------------------
@@ -459,9 +480,10 @@ __global__ void __launch_bounds__(kBwdThreads, TSFF_TBWD_MINB) k_table_bwd(const
 }
 
 // ---- Tbar -> descriptors for the far-field sweep + exact near / endpoint contributions ---------------------------
-__global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a) {
-  const long long b = blockIdx.x;
-  for (int p = threadIdx.x; p < kXi2N; p += kThreads) {
+__global__ void __launch_bounds__(kThreads) k_table_tbar(const TableArgs a, int nsplit) {
+  const long long b = blockIdx.x / nsplit;
+  const int per = (kXi2N + nsplit - 1) / nsplit, p0 = (blockIdx.x % nsplit) * per, p1 = min(kXi2N, p0 + per);
+  for (int p = p0 + threadIdx.x; p < p1; p += kThreads) {
     const double xi = a.xi2[p];
     const double tb = a.Tbar[b * kXi2N + p];
     int np, wb0;
@@ -535,15 +557,22 @@ __global__ void __launch_bounds__(kThreads) k_table_bwd_finish(const TableArgs a
     if (k == V - 1) lb += s_slb[V - 1] * idv;
     fe_bar[k] = (T)(lb / (double)fe[k]);
   }
-  if (threadIdx.x == 0) {
-    double* pbar = a.params_bar + b * a.NP;
-    for (int k = 0; k < a.NP; k++) pbar[k] = 0.0;
+  // params_bar: this window's LG cotangents (thread 0) and, on the pair path, the second window's (thread 32), each reversed into its
+  // own accumulator, then added -- one launch, two short serial chains side by side
+  __shared__ double spb[2][10 + 4 * TSFF_MAX_IONS];
+  if (threadIdx.x == 0 || (threadIdx.x == 32 && a.lgbar2)) {
+    const int w = threadIdx.x == 0 ? 0 : 1;
+    double pb[10 + 4 * TSFF_MAX_IONS];
+    for (int k = 0; k < a.NP; k++) pb[k] = 0.0;
     for (int g = 0; g < a.G; g++) {
       LG Lb;
-      load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
-      lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
+      load_lg((w ? a.lgbar2 : a.lgbar) + (b * a.G + g) * kLGDoubles, Lb);
+      lg_backward(a.params + b * a.NP, a.nI, g, a.G, w ? a.lam_shift2 : a.lam_shift, Lb, pb);
     }
+    for (int k = 0; k < a.NP; k++) spb[w][k] = pb[k];
   }
+  __syncthreads();
+  if (threadIdx.x < a.NP) a.params_bar[b * a.NP + threadIdx.x] = spb[0][threadIdx.x] + (a.lgbar2 ? spb[1][threadIdx.x] : 0.0);
 }
 
 // ---- two windows of one plasma (pair path) ----------------------------------------------------------------------
@@ -556,18 +585,6 @@ __global__ void __launch_bounds__(128) k_table_lg(const TableArgs a, long long B
   lg_forward(a.params + (t / a.G) * a.NP, a.nI, (int)(t % a.G), a.G, a.lam_shift, L);
   store_lg(a.lg + t * kLGDoubles, L);
 }
-// params_bar += reverse of the second window's LG scalars (the first window's finish kernel wrote params_bar)
-__global__ void __launch_bounds__(64) k_table_params_bar_add(const TableArgs a, long long B) {
-  const long long b = (long long)blockIdx.x * 64 + threadIdx.x;
-  if (b >= B) return;
-  double* pbar = a.params_bar + b * a.NP;
-  for (int g = 0; g < a.G; g++) {
-    LG Lb;
-    load_lg(a.lgbar + (b * a.G + g) * kLGDoubles, Lb);
-    lg_backward(a.params + b * a.NP, a.nI, g, a.G, a.lam_shift, Lb, pbar);
-  }
-}
-
 // angle chunks per wavelength tile: 1 when the (lineout, tile) grid alone gives two CTAs per SM, else enough to get there
 int table_angle_split(long long ctas, int A, int sm_count) {
   if (ctas >= 2LL * sm_count) return 1;
@@ -644,15 +661,19 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
   }
   {
     const size_t smem = (size_t)(2 * c->V + kXi2N) * 8;
-    // groups per warp: 4 while the grid keeps >= 8 CTAs per SM, else 2, else 1
-    a.jrep = 4;
+    // groups per warp: 2 while the grid keeps >= 8 CTAs per SM, else 1 (A/B: 1 -> 6.12, 2 -> 6.03, 4 -> 6.06, 8 -> 6.07 ms on the 1d deck)
+    a.jrep = 2;
     while (a.jrep > 1 && (long long)B * ((c->W + kWarps * kFwdJ * a.jrep - 1) / (kWarps * kFwdJ * a.jrep)) < 8LL * c->sm_count) a.jrep /= 2;
 #ifdef TSFF_TFWD_JREP
     a.jrep = TSFF_TFWD_JREP;
 #endif
     a.ntiles = (c->W + kWarps * kFwdJ * a.jrep - 1) / (kWarps * kFwdJ * a.jrep);
     // the fused angle sum (modl) needs all angles in one CTA; the plain formfactor output can split them
-    a.asplit = modl_out ? 1 : table_angle_split(B * a.ntiles, c->A, c->sm_count);
+    const bool split_modl = modl_out && !ff_out && table_fwd_split_angles(c, B);
+    if (split_modl) a.jrep = 1, a.ntiles = (c->W + kWarps * kFwdJ - 1) / (kWarps * kFwdJ);
+    a.asplit = (modl_out && !split_modl) ? 1 : table_angle_split(B * a.ntiles, c->A, c->sm_count);
+    a.mpart = (split_modl && a.asplit > 1) ? (double*)(w + L.w_mpart) : nullptr;
+    a.Bn = B;
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[0], st));
     const unsigned grid = (unsigned)(B * a.ntiles * a.asplit);
     const bool frozen = a.cells && a.cell_mode;
@@ -661,6 +682,11 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
     else if (frozen) { TSFF_SMEM_OPTIN((k_table_fwd<false, true>)); k_table_fwd<false, true><<<grid, kThreads, smem, st>>>(a); }
     else { TSFF_SMEM_OPTIN((k_table_fwd<false, false>)); k_table_fwd<false, false><<<grid, kThreads, smem, st>>>(a); }
     TSFF_LAUNCH_OK("k_table_fwd");
+    if (a.mpart) {
+      const long long total = (long long)B * c->W;
+      k_table_modl_reduce<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(a, total);
+      TSFF_LAUNCH_OK("k_table_modl_reduce");
+    }
     if (c->ev[0] && c->ev[1]) TSFF_CUDA_OK(cudaEventRecord(c->ev[1], st));
   }
   return TSFF_OK;
@@ -672,7 +698,7 @@ int table_fwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, do
 template <typename T>
 int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, const void* saved, const double* modl_bar,
                 const double* ff_bar, double* params_bar, void* fe_bar, void* ws, cudaStream_t st, const void* tables_from = nullptr,
-                void* acc_ws = nullptr, bool skip_zero = false) {
+                void* acc_ws = nullptr, bool skip_zero = false, const double* lgbar2 = nullptr, double lam_shift2 = 0.0) {
   const TableLayout L = table_layout(c, B);
   char* w = static_cast<char*>(ws);
   TableArgs a;
@@ -685,6 +711,7 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
   a.lnfbar = (double*)(w + L.w_lnfbar); a.slopebar = (double*)(w + L.w_slopebar); a.pnear = (double*)(w + L.w_pnear);
   a.lgbar = (double*)(w + L.w_lgbar);
   a.params_bar = params_bar; a.fe_bar = fe_bar;
+  a.lgbar2 = lgbar2; a.lam_shift2 = lam_shift2;
   if (tables_from) {
     double* own_lg = a.lg;
     bind_saved(L, const_cast<char*>(static_cast<const char*>(tables_from)), a);
@@ -739,7 +766,11 @@ int table_bwd_t(tsff_ctx* c, int64_t B, const double* params, const void* fe, co
     if (c->ev[2] && c->ev[3]) TSFF_CUDA_OK(cudaEventRecord(c->ev[3], st));
   }
   if (acc_ws) return TSFF_OK;
-  k_table_tbar<<<(unsigned)B, kThreads, 0, st>>>(a);
+  {
+    // per lineout 1640 poles x (descriptor + exact near zone in FP64): one CTA per lineout when lineouts fill the device, else split
+    const int ts = B >= c->sm_count ? 1 : (kXi2N + kThreads - 1) / kThreads;
+    k_table_tbar<<<(unsigned)(B * ts), kThreads, 0, st>>>(a, ts);
+  }
   TSFF_LAUNCH_OK("k_table_tbar");
   {
     PvNodesArgs n;
@@ -769,16 +800,9 @@ int table_pair_bwd_t(tsff_ctx* ca, tsff_ctx* cb, int64_t B, const double* params
   TSFF_CUDA_OK(cudaMemsetAsync(static_cast<char*>(ws_a) + L.w_zero_begin, 0, L.w_zero_end - L.w_zero_begin, st));
   int rc = table_bwd_t<T>(cb, B, params, fe, saved_b, modl_bar_b, nullptr, params_bar, fe_bar, ws_b, st, saved_a, ws_a, false);
   if (rc) return rc;
-  rc = table_bwd_t<T>(ca, B, params, fe, saved_a, modl_bar_a, nullptr, params_bar, fe_bar, ws_a, st, nullptr, nullptr, true);
-  if (rc) return rc;
-  TableArgs b;
-  memset(&b, 0, sizeof(b));
-  fill_static(cb, b);
-  b.params = params; b.params_bar = params_bar;
-  b.lgbar = (double*)(static_cast<char*>(ws_b) + table_layout(cb, B).w_lgbar);
-  k_table_params_bar_add<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(b, (long long)B);
-  TSFF_LAUNCH_OK("k_table_params_bar_add");
-  return TSFF_OK;
+  const double* lgbar_b = (const double*)(static_cast<char*>(ws_b) + table_layout(cb, B).w_lgbar);
+  return table_bwd_t<T>(ca, B, params, fe, saved_a, modl_bar_a, nullptr, params_bar, fe_bar, ws_a, st, nullptr, nullptr, true, lgbar_b,
+                        cb->lam_shift);
 }
 }  // namespace
 
