@@ -4,7 +4,7 @@
 #           executed-work counts belong to the binary it times.
 #   bench : GPU tests, smoke, bench lines (own arm + reference arm), fit step, 2V timings, ncu launch list
 set -x
-TAG=${1:-r02f}
+TAG=${1:-r02g}
 PHASE=${2:-all}
 O=gpurun_out/$TAG
 mkdir -p $O
