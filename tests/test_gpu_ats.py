@@ -177,6 +177,10 @@ def test_arts_weight_contraction_kernel_vs_numpy(G, W, A, NA):
     ref2 = wm @ ff.mean(0).T
     assert np.abs(out2.cpu().numpy() - ref2).max() <= 1e-12 * np.abs(ref2).max()
     assert torch.equal(out2, arts_weights(fft.detach(), torch.tensor(wm, device="cuda"), None))   # deterministic
+    # the adjoint at this shape may run its k range in two halves added atomically: a two-term sum is order-independent
+    f2 = torch.tensor(ff, device="cuda", requires_grad=True)
+    (arts_weights(f2, torch.tensor(wm, device="cuda"), torch.tensor(jm, device="cuda")) * torch.tensor(cot, device="cuda")).sum().backward()
+    assert torch.equal(f2.grad, fft.grad)
 
 
 def test_angular_full_with_an_ion_spectrum():

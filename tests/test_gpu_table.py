@@ -108,7 +108,8 @@ def test_pair_of_windows_equals_the_two_separate_calls(fdt):
     p[:, 10:14] = [40.0, 8.0, 0.2, 0.6]
     p[:, 14:18] = [1.0, 1.0, 0.35, 0.4]
     engE = _engine(W, vx, sa, np.full(5, 0.2), nI=nI, lam=(380.0, 690.0), lam_shift=0.3, jmul=np.linspace(0.5, 1.5, W))
-    engI = _engine(W + 37, vx, sa, np.linspace(0.1, 0.3, 5), nI=nI, lam=(524.0, 529.0), lam_shift=0.0)
+    # (a different wavelength count AND a different angle count: the two contexts' workspaces are laid out independently)
+    engI = _engine(W + 37, vx, sa[:3], np.linspace(0.1, 0.3, 3), nI=nI, lam=(524.0, 529.0), lam_shift=0.0)
     cE = torch.tensor(rng.normal(size=(B, W)), device="cuda")
     cI = torch.tensor(rng.normal(size=(B, W + 37)), device="cuda")
 
@@ -140,3 +141,27 @@ def test_pair_of_windows_equals_the_two_separate_calls(fdt):
     (form_factor_modl(engI, pt0, ft0) * cI).sum().backward()
     assert float((pt.grad - pt0.grad).abs().max()) <= tol * float(pt0.grad.abs().max())
     assert float((ft.grad.double() - ft0.grad.double()).abs().max()) <= tolf * float(ft0.grad.double().abs().max())
+
+
+def test_forward_with_angles_split_over_ctas_equals_the_unsplit_one():
+    """A fit batch of a few lineouts runs the fused-angle-sum forward with the angles split over CTAs (partial sums reduced in chunk
+    order by a second kernel); a batch that fills the device runs one CTA per (lineout, tile).  Same lineouts, same spectra (the
+    angle sum is re-associated: 1e-14), and the split path repeats bit for bit."""
+    from tsadar_b200.synthetic import vgrid, super_gaussian_projected
+    W, A, nI = 900, 10, 1
+    sa = np.linspace(53.6, 66.1, A)
+    vx = vgrid(160)
+    eng = _engine(W, vx, sa, np.linspace(0.05, 0.15, A), nI=nI, lam=(400.0, 700.0), jmul=np.linspace(0.8, 1.2, W))
+    Bbig = 400
+    rng = np.random.default_rng(11)
+    p = np.zeros((Bbig, 14))
+    p[:, 0], p[:, 1], p[:, 2] = rng.uniform(0.3, 1.2, Bbig), rng.uniform(0.1, 0.5, Bbig), 526.5
+    p[:, 7:10] = 1.0
+    p[:, 10:14] = [40.0, 8.0, 0.2, 1.0]
+    fe = np.stack([super_gaussian_projected(vx, m) for m in rng.uniform(2.0, 4.0, Bbig)])
+    pt, ft = torch.tensor(p, device="cuda"), torch.tensor(fe, device="cuda")
+    big, _, _ = eng.forward(pt, ft)
+    small, _, _ = eng.forward(pt[:3].contiguous(), ft[:3].contiguous())
+    again, _, _ = eng.forward(pt[:3].contiguous(), ft[:3].contiguous())
+    assert torch.equal(small, again)
+    assert float((small - big[:3]).abs().max()) <= 1e-13 * float(big[:3].abs().max())
