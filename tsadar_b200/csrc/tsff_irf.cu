@@ -26,12 +26,18 @@ constexpr int kTile = kConvThreads * kConvR;     // outputs per CTA in the convo
 // taps beyond the real ones are zero), every output summed in tap order.  The eight-sample window lives in registers and
 // rotates by one per tap (fully unrolled: no moves): one shared-memory load of a sample and one broadcast load of a tap
 // feed eight DFMAs, instead of two loads per DFMA.
+// The halo is stored with one pad element per eight samples (physical index i + (i >> 3)): thread t reads sample 8 t + c, a
+// 64-byte lane stride that would put the 32 lanes of a warp into two bank pairs (16-way conflicts: the walk was bound by the
+// shared-memory pipe, 17 of the kernel's 20 us at a fit batch of two lineouts); with the pad the stride is 72 bytes, conflict-free.
+__device__ __forceinline__ int hpad(int i) { return i + (i >> 3); }
+
 template <int DIR>
-__device__ __forceinline__ void conv_tile8(const double* __restrict__ s, const double* __restrict__ sg, int ntp, int i0,
+__device__ __forceinline__ void conv_tile8(const double* __restrict__ sp, const double* __restrict__ sg, int ntp, int i0,
                                            double (&acc)[kConvR]) {
+  auto ldh = [sp](int i) { return sp[hpad(i)]; };
   double v[kConvR];
 #pragma unroll
-  for (int r = 0; r < kConvR; r++) v[r] = s[i0 + r];
+  for (int r = 0; r < kConvR; r++) v[r] = ldh(i0 + r);
   for (int ib = 0; ib < ntp; ib += kConvR) {
 #pragma unroll
     for (int u = 0; u < kConvR; u++) {
@@ -39,11 +45,11 @@ __device__ __forceinline__ void conv_tile8(const double* __restrict__ s, const d
       if (DIR > 0) {
 #pragma unroll
         for (int r = 0; r < kConvR; r++) acc[r] = fma(v[(r + u) & (kConvR - 1)], gv, acc[r]);
-        v[u] = s[i0 + ib + u + kConvR];                                   // enters as r = 7 of the next tap
+        v[u] = ldh(i0 + ib + u + kConvR);                                 // enters as r = 7 of the next tap
       } else {
 #pragma unroll
         for (int r = 0; r < kConvR; r++) acc[r] = fma(v[(r - u) & (kConvR - 1)], gv, acc[r]);
-        v[(kConvR - 1 - u) & (kConvR - 1)] = s[i0 - ib - u - 1];          // enters as r = 0 of the next tap
+        v[(kConvR - 1 - u) & (kConvR - 1)] = ldh(i0 - ib - u - 1);        // enters as r = 0 of the next tap
       }
     }
   }
@@ -104,15 +110,15 @@ __global__ void __launch_bounds__(kConvThreads) k_irf_conv(const IrfGeom g, cons
   __shared__ double s_rv[2 * (kConvThreads / 32)];
   __shared__ int s_ri[2 * (kConvThreads / 32)];
   const int ntp = (2 * g.K + 1 + kConvR - 1) / kConvR * kConvR;
-  double* s_x = reinterpret_cast<double*>(smem_raw) + 8;
-  double* s_g = s_x + (kTile + 2 * g.K) + 8;
+  double* s_x = reinterpret_cast<double*>(smem_raw) + 9;           // logical index -8 -> physical -9
+  double* s_g = s_x + hpad(kTile + 2 * g.K + 8) + 1;
   const int tile = blockIdx.x % g.ntiles;
   const long long b = blockIdx.x / g.ntiles;
   const int n0 = tile * kTile;
   const double* xb = x + b * g.W;
   for (int i = threadIdx.x - 8; i < kTile + 2 * g.K + 8; i += kConvThreads) {
     const int m = n0 - g.K + i;
-    s_x[i] = (i >= 0 && i < kTile + 2 * g.K && m >= 0 && m < g.W) ? xb[m] : 0.0;
+    s_x[hpad(i)] = (i >= 0 && i < kTile + 2 * g.K && m >= 0 && m < g.W) ? xb[m] : 0.0;
   }
   // taps for offsets o = n - m in [-K, K]: s_g[o + K]
   for (int i = threadIdx.x; i < ntp; i += kConvThreads) {
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kConvThreads) k_irf_conv(const IrfGeom g, cons
       if (n < g.W) {
         yc[b * g.W + n] = acc[r];
         if (acc[r] > vmax_y) { vmax_y = acc[r]; imax_y = n; }
-        const double xv = s_x[t0 + r + g.K];
+        const double xv = s_x[hpad(t0 + r + g.K)];
         if (xv > vmax_x) { vmax_x = xv; imax_x = n; }
       }
     }
@@ -258,9 +264,26 @@ __global__ void __launch_bounds__(kThreads) k_irf_finish(const IrfGeom g, const 
     s_yb[q] = s * a / (double)g.r;             // irf.py:74,124  reshape(1024,-1).mean
   }
   __syncthreads();
+  // arg-max over the bins, first index on ties (jnp.argmax); by the whole CTA: a serial walk of 1024 bins by one thread was half
+  // of this kernel at the batch sizes fits run at
+  __shared__ double s_wv[kThreads / 32];
+  __shared__ int s_wi[kThreads / 32];
+  {
+    double v = -INFINITY; int ix = 0x7fffffff;
+    for (int q = threadIdx.x; q < g.nbins; q += kThreads) if (s_yb[q] > v) { v = s_yb[q]; ix = q; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v2 = __shfl_down_sync(0xffffffffu, v, o);
+      const int i2 = __shfl_down_sync(0xffffffffu, ix, o);
+      if (v2 > v || (v2 == v && i2 < ix)) { v = v2; ix = i2; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_wv[threadIdx.x >> 5] = v; s_wi[threadIdx.x >> 5] = ix; }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double mb = -INFINITY; int qm = 0;
-    for (int q = 0; q < g.nbins; q++) if (s_yb[q] > mb) { mb = s_yb[q]; qm = q; }
+    double mb = s_wv[0]; int qm = s_wi[0];
+    for (int w = 1; w < kThreads / 32; w++) if (s_wv[w] > mb || (s_wv[w] == mb && s_wi[w] < qm)) { mb = s_wv[w]; qm = s_wi[w]; }
+    if (qm == 0x7fffffff) qm = 0;   // every bin NaN or -inf: the serial walk's answer
     s_stat[2] = mb; s_idx[2] = qm;
     IrfStats st; st.mx = s_stat[0]; st.my = s_stat[1]; st.mb = mb; st.im = s_idx[0]; st.iy = s_idx[1]; st.qm = qm; st.pad = 0;
     st.Mb = st.Mr = 1.0; st.ib = st.ir = 0;
@@ -412,14 +435,14 @@ __global__ void __launch_bounds__(kThreads) k_irf_bwd_pre(const IrfGeom g, const
 __global__ void __launch_bounds__(kConvThreads) k_irf_bwd_conv(const IrfGeom g, const IrfCall c, double* __restrict__ xbar) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ntp = (2 * g.K + 1 + kConvR - 1) / kConvR * kConvR;
-  double* s_y = reinterpret_cast<double*>(smem_raw) + 8;
-  double* s_g = s_y + (kTile + 2 * g.K) + 8;
+  double* s_y = reinterpret_cast<double*>(smem_raw) + 9;
+  double* s_g = s_y + hpad(kTile + 2 * g.K + 8) + 1;
   const int tile = blockIdx.x % g.ntiles;
   const long long b = blockIdx.x / g.ntiles;
   const int m0 = tile * kTile;
   for (int i = threadIdx.x - 8; i < kTile + 2 * g.K + 8; i += kConvThreads) {
     const int n = m0 - g.K + i;
-    s_y[i] = (i >= 0 && i < kTile + 2 * g.K && n >= 0 && n < g.W) ? c.ycbar[b * g.W + n] : 0.0;
+    s_y[hpad(i)] = (i >= 0 && i < kTile + 2 * g.K && n >= 0 && n < g.W) ? c.ycbar[b * g.W + n] : 0.0;
   }
   for (int i = threadIdx.x; i < ntp; i += kConvThreads) {
     const double d = ((double)(i - g.K) - g.half) * g.dlam;
@@ -506,7 +529,7 @@ extern "C" int tsff_irf_fwd(const tsff_irf_cfg* c, int64_t B, const double* modl
   // conv(x) is kept in `saved` for the backward pass
   double* yc = (double*)(sv + align_up((size_t)B * sizeof(IrfStats)));
   double* pmax = (double*)(w + L.w_pmax);
-  const size_t smem = (size_t)(kTile + 2 * g.K + 16 + 2 * g.K + 1 + kConvR) * 8;
+  const size_t smem = (size_t)((kTile + 2 * g.K + 16) * 9 / 8 + 12 + 2 * g.K + 1 + kConvR) * 8;
   if (smem > 200 * 1024) { set_error("IRF too wide for shared memory (K=%d)", g.K); return TSFF_E_INVALID; }
   TSFF_SMEM_OPTIN(k_irf_conv);
   k_irf_conv<<<(unsigned)(B * g.ntiles), kConvThreads, smem, st>>>(g, modl, yc, pmax);
@@ -541,7 +564,7 @@ extern "C" int tsff_irf_bwd(const tsff_irf_cfg* c, int64_t B, const double* para
   call.xbar_max = (double*)(w + L.bytes);
   k_irf_bwd_pre<<<(unsigned)B, kThreads, (size_t)g.nbins * 8, st>>>(g, call, yc);
   TSFF_LAUNCH_OK("k_irf_bwd_pre");
-  const size_t smem = (size_t)(kTile + 2 * g.K + 16 + 2 * g.K + 1 + kConvR) * 8;
+  const size_t smem = (size_t)((kTile + 2 * g.K + 16) * 9 / 8 + 12 + 2 * g.K + 1 + kConvR) * 8;
   TSFF_SMEM_OPTIN(k_irf_bwd_conv);
   k_irf_bwd_conv<<<(unsigned)(B * g.ntiles), kConvThreads, smem, st>>>(g, call, modl_bar);
   TSFF_LAUNCH_OK("k_irf_bwd_conv");
