@@ -4,7 +4,7 @@
 #           executed-work counts belong to the binary it times.
 #   bench : GPU tests, smoke, bench lines (own arm + reference arm), fit step, 2V timings, ncu launch list
 set -x
-TAG=${1:-r02g}
+TAG=${1:-r02h}
 PHASE=${2:-all}
 O=gpurun_out/$TAG
 mkdir -p $O
