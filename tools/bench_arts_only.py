@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""arts-1d alone (scratch): python tools/bench_arts_only.py"""
-import os, sys, json
+"""The named-deck timings alone (bench.py's `configs` block without the headline sweep): python tools/bench_arts_only.py [key-prefix]"""
+import json
+import os
+import sys
+
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import bench_configs as bc
-import types
-# run only the arts-1d leg: reuse run_named_configs' inner function through a tiny shim
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_configs.py")).read()
+
+prefix = sys.argv[1] if len(sys.argv) > 1 else "arts-1d"
 out = bc.run_named_configs(cpu=False)
-print(json.dumps({k: v for k, v in out.items() if k.startswith("arts-1d")}, indent=1))
+print(json.dumps({k: v for k, v in out.items() if k.startswith(prefix)}, indent=1))
