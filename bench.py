@@ -446,12 +446,10 @@ def main():
     # ---- leg 3: sustained -- the device-resident step back to back for >= 2 s, its own clock record
     sustained = None
     if not args.no_sustained:
-        # the step count must be THE SAME on every rank (each step all-reduces the loss): derive it from the slowest rank's timing,
-        # not from this rank's own (ranks whose ceil() differed by one step left the others waiting in a collective forever)
-        ms_ref = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms_ref, op=dist.ReduceOp.MAX)
-        n_sus = max(K, int(np.ceil(args.sustained_seconds * 1e3 / (float(ms_ref.item()) / K))))
+        # the step count must be THE SAME on every rank (each step all-reduces the loss): the slowest rank's timing decides, not this
+        # rank's own (ranks whose ceil() differed by one step left the others waiting in a collective forever)
+        from tsadar_b200.parallel import agreed_step_count
+        n_sus = agreed_step_count(ms_total / K, args.sustained_seconds, K, device=dev)
         clk2 = ClockSampler("sustained").start() if rank == 0 else None
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()

@@ -197,3 +197,41 @@ def test_pixel_rotation_matches_the_oracle():
     At = torch.tensor(A, requires_grad=True)
     rotate(At, 0.4).sum().backward()
     assert torch.isfinite(At.grad).all() and float(At.grad.abs().sum()) > 0
+
+
+# ---- loops that contain a collective run equally often on every rank ----------------------------------------------------
+def _worker_steps(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tsadar_b200.parallel import agreed_step_count
+    # step times either side of the 297 / 298 boundary of ceil(2000 / ms) (2000 / 297 = 6.734): each rank's own clock would say
+    # 298, 297, 297, 298 steps; the agreed count is the slowest rank's
+    ms = [6.730, 6.740, 6.7345, 6.7339][rank]
+    own = int(np.ceil(2000.0 / ms))
+    n = agreed_step_count(ms, 2.0, 20)
+    # the loop the count is for: one all-reduce per step, then a barrier -- with per-rank counts this never returns
+    acc = torch.zeros(1, dtype=torch.float64)
+    for _ in range(n):
+        t = torch.ones(1, dtype=torch.float64)
+        dist.all_reduce(t)
+        acc += t
+    dist.barrier()
+    q.put((rank, own, n, float(acc)))
+    dist.destroy_process_group()
+
+
+def test_step_count_is_agreed_across_ranks():
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_steps, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert len({own for _, own, _, _ in res}) == 2          # the ranks' own clocks disagree ...
+    assert {n for _, _, n, _ in res} == {297}               # ... the agreed count does not (slowest rank: 6.740 ms -> 297)
+    assert all(acc == 297.0 * world for _, _, _, acc in res)

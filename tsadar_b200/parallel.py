@@ -13,6 +13,7 @@ so the partial cotangents of the shared parameters / f table are summed across r
 computed redundantly downstream (amp1/amp2/lam in the instrument stage, the loss) is left alone."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -29,6 +30,16 @@ def allreduce_loss(loss: torch.Tensor) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)
     return loss
+
+
+def agreed_step_count(ms_per_step: float, seconds: float, at_least: int, device=None) -> int:
+    """Steps that fill `seconds` at `ms_per_step`, THE SAME on every rank: the slowest rank's step time (all-reduce MAX) decides.
+    A loop whose body holds a collective (the per-step loss all-reduce) must run equally often everywhere; a count rounded from each
+    rank's own clock can differ by one between ranks and leaves them waiting for each other in mismatched collectives."""
+    t = torch.tensor([float(ms_per_step)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return max(int(at_least), int(np.ceil(seconds * 1e3 / float(t.item()))))
 
 
 def gather_rows(x: torch.Tensor, n_total: int) -> torch.Tensor:
